@@ -1,0 +1,942 @@
+// bns_api.cu -- host side of libbonsai_b200.so: the C ABI of include/bonsai_b200.h.
+//
+// Owns one CUDA device per context: the bucketised k-mer table, the Euler-tour taxonomy arrays, a small
+// ring of stream slots through which host batches are pipelined (H2D copy / kernel / D2H copy overlap
+// across slots), and the counters ClassifierGeneric keeps (classifier.h:138,170-171).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bonsai_b200.h"
+#include "bns_device.cuh"
+#include "bns_kernels.h"
+
+using namespace bns;
+
+namespace {
+
+constexpr int N_SLOTS = 3;
+constexpr u64 CHUNK_BASES = 96ull << 20;      // bases per pipelined chunk
+constexpr u64 CHUNK_READS = 1ull << 20;
+constexpr double TARGET_LOAD = 2.5;           // entries per 4-slot bucket (0.63 of the slots, like khash's fill)
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    char *d_bases = nullptr;       size_t cap_bases = 0;
+    u64 *d_offsets = nullptr;      size_t cap_offsets = 0;
+    u32 *d_out = nullptr;          size_t cap_out = 0;       // taxon | nhit | nmiss (3 * reads)
+    u32 *d_taxa = nullptr;         size_t cap_taxa = 0;
+    u64 *d_taxa_offsets = nullptr; size_t cap_taxa_offsets = 0;
+    u64 *d_kmers = nullptr;        size_t cap_kmers = 0;
+    u64 *d_out_offsets = nullptr;  size_t cap_out_offsets = 0;
+};
+
+template <class T>
+int ensure(T *&p, size_t &cap, size_t need) {
+    if(need <= cap) return BNS_OK;
+    if(p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need + need / 4 + 256;
+    if(cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return BNS_E_NOMEM; }
+    cap = want;
+    return BNS_OK;
+}
+
+}  // namespace
+
+struct bns_b200_ctx {
+    int device = 0;
+    int n_sm = 148;
+    bns_b200_config cfg{};
+    EncParams enc{};
+    u32 c = 0, w = 0, W = 1;
+    bool unspaced = true, unwindowed = true, canon = false;
+    u32 ring_cap = 0;
+    // table
+    u64 *d_slots = nullptr;
+    u64 n_buckets = 0, n_keys = 0, n_displaced = 0, n_overflowed = 0;
+    u32 bucket_bits = 0, max_disp = 0;
+    std::vector<u32> values;          // sorted distinct DB values (value id -> taxid)
+    u32 *d_values = nullptr;
+    // taxonomy
+    bool tax_loaded = false, tax_ready = false;
+    std::vector<u32> tax_child, tax_parent;
+    uint4 *d_val_info = nullptr, *d_node_info = nullptr;
+    u32 n_nodes = 0, node_of_one = 0;
+    // misc device state
+    unsigned long long *d_counters = nullptr;   // [0] classified [1] unclassified [2..7] scratch
+    u32 *d_status = nullptr;
+    Slot slots[N_SLOTS];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bns_b200_stats stats{};
+    std::string err;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? BNS_E_NOMEM : BNS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if(e__ != cudaSuccess) return ctx->cuda_fail(e__, #call);         \
+    } while(0)
+
+namespace {
+
+thread_local std::string g_open_err;
+
+// Spacer (spacer.h:59-71) + Encoder ctor (encoder.h:133-150) + the for_each dispatch (encoder.h:416-464)
+int derive_encoder(bns_b200_ctx *ctx) {
+    const bns_b200_config &cf = ctx->cfg;
+    if(cf.k < 1 || cf.k > BNS_MAX_K) return ctx->fail(BNS_E_INVAL, "k must be in [1,32], got %u", cf.k);
+    if(cf.score > BNS_SCORE_ENTROPY || cf.api > BNS_API_PATH || cf.entropy_cast > BNS_CAST_WRAP)
+        return ctx->fail(BNS_E_INVAL, "bad score/api/entropy_cast selector");
+    EncParams &P = ctx->enc;
+    memset(&P, 0, sizeof P);
+    const u32 k = cf.k;
+    u32 c = k;
+    bool unspaced = true;
+    for(u32 i = 0; i + 1 < k; ++i) { c += cf.gaps[i]; if(cf.gaps[i]) unspaced = false; }
+    if(c > (u32)CMAX) return ctx->fail(BNS_E_INVAL, "comb size %u exceeds the supported maximum %d", c, CMAX);
+    const u32 w = std::max<int>((int)c, (int)cf.w);
+    ctx->c = c; ctx->w = w; ctx->unspaced = unspaced; ctx->unwindowed = (k == w);
+    ctx->canon = cf.canonicalize && unspaced;                      // encoder.h:148-150
+    ctx->W = w - c + 1;
+    P.k = k; P.c = c; P.W = ctx->W;
+    P.cast_wrap = cf.entropy_cast == BNS_CAST_WRAP;
+    // contiguous runs of the comb
+    {
+        u32 pos = 0, run_start = 0, run_len = 1, ns = 0;
+        for(u32 i = 0; i + 1 < k; ++i) {
+            const u32 step = cf.gaps[i] + 1u;
+            if(step == 1) ++run_len;
+            else {
+                P.seg_off[ns] = (uint16_t)run_start; P.seg_len[ns] = (uint16_t)run_len; ++ns;
+                run_start = pos + step; run_len = 1;
+            }
+            pos += step;
+        }
+        P.seg_off[ns] = (uint16_t)run_start; P.seg_len[ns] = (uint16_t)run_len; ++ns;
+        P.n_seg = ns;
+    }
+    // n/k * log(n/k) with the host's libm, written exactly as entropy.h:46-47 evaluates it
+    {
+        const double qi = 1. / k;
+        for(u32 n = 1; n <= k; ++n) {
+            volatile double p = (double)n * qi;
+            volatile double l = std::log(p);
+            P.plogp[n] = p * l;
+        }
+    }
+    const bool ent = cf.score == BNS_SCORE_ENTROPY;
+    const bool windowed = !ctx->unwindowed;
+    P.score_kind = SC_LEX;
+    if(cf.api == BNS_API_STRING) {
+        if(ctx->canon) {
+            if(!windowed) { P.family = FAM_U; P.canon_elem = 1; }
+            else if(ent) { P.family = FAM_R; P.score_kind = SC_ENT_ROLL; P.canon_emit = 1; P.tail_flush = 1; }
+            else { P.family = FAM_K; P.canon_elem = 1; P.filter_none = 1; }
+        } else if(unspaced) {
+            if(!windowed) P.family = FAM_U;
+            else { P.family = FAM_R; P.tail_flush = 1; P.score_kind = ent ? SC_ENT_ROLL : SC_LEX; }
+        } else P.family = FAM_NONE;                                   // encoder.h:437-440
+    } else {
+        if(ctx->canon) {
+            if(!windowed) { P.family = FAM_U; P.canon_elem = 1; }
+            else { P.family = FAM_K; P.canon_elem = 1; P.filter_none = 1; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX; }
+        } else if(unspaced) {
+            if(!windowed) P.family = FAM_U;
+            else { P.family = FAM_R; P.tail_flush = 1; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX; }
+        } else { P.family = FAM_K; P.filter_none = 1; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX; }
+    }
+    if(P.family == FAM_R && k == 32)
+        return ctx->fail(BNS_E_INVAL, "k = 32 with a windowed non-canonical rolling encoder is not supported "
+                                      "(the reference restarts on 32 consecutive T there, encoder.h:283)");
+    ctx->ring_cap = (ctx->W > 1 && P.family != FAM_U && P.family != FAM_NONE) ? (ctx->W - 1 + TILE) : 0;
+    const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
+    if(smem > 200 * 1024) return ctx->fail(BNS_E_INVAL, "window %u needs %zu bytes of shared memory per CTA", w, smem);
+    return BNS_OK;
+}
+
+int grid_for(bns_b200_ctx *ctx, u64 n_units, int occ) {
+    const u64 want = (n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const u64 cap = (u64)ctx->n_sm * (occ > 0 ? occ : 1);
+    return (int)std::max<u64>(1, std::min(want, cap));
+}
+
+void free_table(bns_b200_ctx *ctx) {
+    if(ctx->d_slots) cudaFree(ctx->d_slots);
+    if(ctx->d_values) cudaFree(ctx->d_values);
+    ctx->d_slots = nullptr; ctx->d_values = nullptr;
+    ctx->n_buckets = ctx->n_keys = 0; ctx->bucket_bits = 0;
+    ctx->values.clear();
+    ctx->tax_ready = false;
+}
+
+u32 bits_for(u64 n) { u32 b = 0; while((1ull << b) < n) ++b; return b; }
+
+int alloc_table(bns_b200_ctx *ctx, u32 b) {
+    if(b > 32) return ctx->fail(BNS_E_NOMEM, "table would need 2^%u buckets", b);
+    ctx->bucket_bits = b;
+    ctx->n_buckets = 1ull << b;
+    CK(cudaMalloc((void **)&ctx->d_slots, ctx->n_buckets * 32));
+    CK(cudaMemsetAsync(ctx->d_slots, 0xff, ctx->n_buckets * 32, ctx->slots[0].st));
+    return BNS_OK;
+}
+
+u32 choose_bits(u64 n_keys, u32 n_values) {
+    u32 b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / TARGET_LOAD));
+    b = std::max(b, 12u);
+    b = std::max(b, bits_for(std::max<u32>(n_values, 1)) + 4u);
+    return b;
+}
+
+int upload_values(bns_b200_ctx *ctx) {
+    const size_t n = std::max<size_t>(ctx->values.size(), 1);
+    CK(cudaMalloc((void **)&ctx->d_values, n * sizeof(u32)));
+    if(!ctx->values.empty())
+        CK(cudaMemcpyAsync(ctx->d_values, ctx->values.data(), ctx->values.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->slots[0].st));
+    return BNS_OK;
+}
+
+int refresh_table_stats(bns_b200_ctx *ctx) {
+    cudaStream_t st = ctx->slots[0].st;
+    CK(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
+    CK(launch_table_stats(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_counters + 2));
+    ++ctx->stats.kernel_launches;
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, ctx->d_counters + 2, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->n_keys = h[0]; ctx->n_overflowed = h[1]; ctx->max_disp = (u32)h[2];
+    return BNS_OK;
+}
+
+// Insert host pairs through a pinned staging buffer; `next` fills up to cap pairs and returns how many.
+template <class Next>
+int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
+    const size_t CH = 1u << 22;
+    u64 *h_keys = nullptr, *d_keys = nullptr;
+    u32 *h_vals = nullptr, *d_vals = nullptr;
+    cudaStream_t st = ctx->slots[0].st;
+    int rc = BNS_OK;
+    if(cudaMallocHost((void **)&h_keys, 2 * CH * sizeof(u64)) != cudaSuccess ||
+       cudaMallocHost((void **)&h_vals, 2 * CH * sizeof(u32)) != cudaSuccess ||
+       cudaMalloc((void **)&d_keys, 2 * CH * sizeof(u64)) != cudaSuccess ||
+       cudaMalloc((void **)&d_vals, 2 * CH * sizeof(u32)) != cudaSuccess) {
+        rc = ctx->cuda_fail(cudaGetLastError(), "staging allocation");
+    } else {
+        cudaEvent_t done[2];
+        cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+        cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), st);
+        for(int buf = 0;; buf ^= 1) {
+            cudaEventSynchronize(done[buf]);
+            const size_t n = next(h_keys + buf * CH, h_vals + buf * CH, CH);
+            if(!n) break;
+            cudaMemcpyAsync(d_keys + buf * CH, h_keys + buf * CH, n * sizeof(u64), cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_vals + buf * CH, h_vals + buf * CH, n * sizeof(u32), cudaMemcpyHostToDevice, st);
+            cudaError_t e = launch_insert(st, ctx->d_slots, ctx->bucket_bits, d_keys + buf * CH, d_vals + buf * CH, n,
+                                          ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5);
+            ++ctx->stats.kernel_launches;
+            ctx->stats.h2d_bytes += n * 12;
+            if(e != cudaSuccess) { rc = ctx->cuda_fail(e, "insert kernel"); break; }
+            cudaEventRecord(done[buf], st);
+        }
+        cudaMemcpyAsync(h_stats, ctx->d_counters + 5, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if(rc == BNS_OK && e != cudaSuccess) rc = ctx->cuda_fail(e, "table build");
+        cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+    }
+    if(h_keys) cudaFreeHost(h_keys);
+    if(h_vals) cudaFreeHost(h_vals);
+    if(d_keys) cudaFree(d_keys);
+    if(d_vals) cudaFree(d_vals);
+    return rc;
+}
+
+// Taxonomy -> Euler-tour arrays. Node 0 is "none". Lenient where the reference is UB (SURVEY B-9): a parent
+// that is not itself a node is treated as 0, a DB value that is not a node becomes an isolated root.
+int finalize_taxonomy(bns_b200_ctx *ctx) {
+    if(ctx->tax_ready) return BNS_OK;
+    if(!ctx->tax_loaded) return ctx->fail(BNS_E_STATE, "taxonomy not loaded");
+    std::vector<u32> ids(ctx->tax_child);
+    ids.push_back(1);
+    ids.insert(ids.end(), ctx->values.begin(), ctx->values.end());
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    if(!ids.empty() && ids[0] == 0) ids.erase(ids.begin());          // taxid 0 is "no taxon"
+    const u32 n = (u32)ids.size();
+    auto node_of = [&](u32 taxid) -> u32 {
+        auto it = std::lower_bound(ids.begin(), ids.end(), taxid);
+        return (it != ids.end() && *it == taxid) ? (u32)(it - ids.begin()) + 1 : 0;
+    };
+    std::vector<u32> parent(n + 1, 0);
+    for(size_t i = 0; i < ctx->tax_child.size(); ++i) {              // later lines overwrite earlier ones (kh_put + assign)
+        const u32 nd = node_of(ctx->tax_child[i]);
+        if(nd) parent[nd] = node_of(ctx->tax_parent[i]);
+    }
+    const u32 one = node_of(1);
+    parent[one] = 0;                                                  // util.h:780-781
+    // children CSR
+    std::vector<u32> deg(n + 2, 0), start(n + 2, 0), kids(n ? n : 1);
+    for(u32 v = 1; v <= n; ++v) ++deg[parent[v]];
+    for(u32 v = 0; v <= n; ++v) start[v + 1] = start[v] + deg[v];
+    {
+        std::vector<u32> fill(start.begin(), start.end() - 1);
+        for(u32 v = 1; v <= n; ++v) kids[fill[parent[v]]++] = v;
+    }
+    std::vector<u32> tin(n + 1, 0), tout(n + 1, 0), it(n + 1, 0), stack;
+    u32 clock = 0, visited = 0;
+    for(u32 ri = start[0]; ri < start[1]; ++ri) {                     // every root (parent 0)
+        stack.push_back(kids[ri]);
+        tin[kids[ri]] = clock++; ++visited;
+        while(!stack.empty()) {
+            const u32 v = stack.back();
+            if(it[v] < deg[v]) {
+                const u32 ch = kids[start[v] + it[v]++];
+                tin[ch] = clock++; ++visited;
+                stack.push_back(ch);
+            } else { tout[v] = clock; stack.pop_back(); }
+        }
+    }
+    if(visited != n) return ctx->fail(BNS_E_TAXONOMY, "taxonomy has a cycle: %u of %u nodes are not reachable from a root", n - visited, n);
+    std::vector<uint4> node_info(n + 1), val_info(std::max<size_t>(ctx->values.size(), 1));
+    node_info[0] = make_uint4(0xffffffffu, 0, 0, 0);
+    for(u32 v = 1; v <= n; ++v) node_info[v] = make_uint4(tin[v], tout[v], parent[v], ids[v - 1]);
+    for(size_t i = 0; i < ctx->values.size(); ++i) {
+        const u32 nd = node_of(ctx->values[i]);
+        // value 0 never scores (resolve_tree's `while(node)`): an empty interval
+        val_info[i] = nd ? make_uint4(tin[nd], tout[nd], nd, ctx->values[i]) : make_uint4(0xffffffffu, 0, 0, 0);
+    }
+    if(ctx->d_node_info) cudaFree(ctx->d_node_info);
+    if(ctx->d_val_info) cudaFree(ctx->d_val_info);
+    ctx->d_node_info = ctx->d_val_info = nullptr;
+    CK(cudaMalloc((void **)&ctx->d_node_info, node_info.size() * sizeof(uint4)));
+    CK(cudaMalloc((void **)&ctx->d_val_info, val_info.size() * sizeof(uint4)));
+    CK(cudaMemcpy(ctx->d_node_info, node_info.data(), node_info.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_val_info, val_info.data(), val_info.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    ctx->n_nodes = n + 1;
+    ctx->node_of_one = one;
+    ctx->tax_ready = true;
+    return BNS_OK;
+}
+
+TableView table_view(const bns_b200_ctx *ctx) {
+    TableView T;
+    T.slots = ctx->d_slots;
+    T.bucket_bits = ctx->bucket_bits;
+    T.tag_shift = ctx->bucket_bits - 3;
+    T.val_mask = (1u << (ctx->bucket_bits - 4)) - 1;
+    T.n_values = (u32)ctx->values.size();
+    return T;
+}
+TaxView tax_view(const bns_b200_ctx *ctx) {
+    TaxView X;
+    X.val_info = ctx->d_val_info;
+    X.node_info = ctx->d_node_info;
+    X.n_nodes = ctx->n_nodes;
+    X.node_of_one = ctx->node_of_one;
+    return X;
+}
+
+int finish_table(bns_b200_ctx *ctx, const unsigned long long *h_stats) {
+    if(h_stats[2]) return ctx->fail(BNS_E_INVAL, "%llu values were not in the value dictionary", h_stats[2]);
+    ctx->n_displaced = h_stats[1];
+    int rc = refresh_table_stats(ctx);
+    ctx->tax_ready = false;
+    return rc;
+}
+
+int check_status(bns_b200_ctx *ctx, u32 st) {
+    if(st & 2u) return ctx->fail(BNS_E_CAPACITY, "a record hit more than %d distinct taxa", AGG_CAP);
+    if(st & 1u) return ctx->fail(BNS_E_CAPACITY, "an output window was too small for the k-mers produced");
+    if(st & 4u) return ctx->fail(BNS_E_INVAL, "a taxid passed to resolve is not a database value");
+    return BNS_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *bns_b200_version(void) { return "bonsai_b200 0.1 (sm_100a), ABI 1"; }
+
+const char *bns_b200_strerror(int code) {
+    switch(code) {
+        case BNS_OK: return "ok";
+        case BNS_E_INVAL: return "invalid argument";
+        case BNS_E_CUDA: return "CUDA error";
+        case BNS_E_NOMEM: return "out of memory";
+        case BNS_E_STATE: return "table or taxonomy not loaded";
+        case BNS_E_TAXONOMY: return "malformed taxonomy";
+        case BNS_E_CAPACITY: return "output capacity exceeded";
+        case BNS_E_IO: return "I/O error";
+        default: return "unknown error";
+    }
+}
+const char *bns_b200_last_error(const bns_b200_t *ctx) { return ctx ? ctx->err.c_str() : g_open_err.c_str(); }
+
+int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
+    if(!cfg || !out) return BNS_E_INVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if(e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_open_err = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return BNS_E_CUDA;                              // no CPU fallback, by design
+    }
+    bns_b200_ctx *ctx = new bns_b200_ctx();
+    ctx->cfg = *cfg;
+    int rc = derive_encoder(ctx);
+    if(rc != BNS_OK) { g_open_err = ctx->err; delete ctx; return rc; }
+    int dev = cfg->device;
+    if(dev < 0) cudaGetDevice(&dev);
+    if(dev >= ndev) { g_open_err = "device ordinal out of range"; delete ctx; return BNS_E_INVAL; }
+    ctx->device = dev;
+    auto bail = [&](cudaError_t er, const char *what) {
+        g_open_err = std::string(what) + ": " + cudaGetErrorString(er);
+        cudaGetLastError();
+        bns_b200_close(ctx);
+        return BNS_E_CUDA;
+    };
+    if((e = cudaSetDevice(dev)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->n_sm = prop.multiProcessorCount;
+    for(int i = 0; i < N_SLOTS; ++i)
+        if((e = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if((e = cudaMalloc((void **)&ctx->d_status, sizeof(u32))) != cudaSuccess) return bail(e, "cudaMalloc");
+    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_status, 0, sizeof(u32));
+    *out = ctx;
+    return BNS_OK;
+}
+
+void bns_b200_close(bns_b200_t *ctx) {
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_table(ctx);
+    if(ctx->d_val_info) cudaFree(ctx->d_val_info);
+    if(ctx->d_node_info) cudaFree(ctx->d_node_info);
+    if(ctx->d_counters) cudaFree(ctx->d_counters);
+    if(ctx->d_status) cudaFree(ctx->d_status);
+    for(auto &s : ctx->slots) {
+        if(s.d_bases) cudaFree(s.d_bases);
+        if(s.d_offsets) cudaFree(s.d_offsets);
+        if(s.d_out) cudaFree(s.d_out);
+        if(s.d_taxa) cudaFree(s.d_taxa);
+        if(s.d_taxa_offsets) cudaFree(s.d_taxa_offsets);
+        if(s.d_kmers) cudaFree(s.d_kmers);
+        if(s.d_out_offsets) cudaFree(s.d_out_offsets);
+        if(s.st) cudaStreamDestroy(s.st);
+    }
+    if(ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if(ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int bns_b200_geometry(const bns_b200_t *ctx, uint32_t *c, uint32_t *w, int *unspaced, int *unwindowed, int *canon) {
+    if(!ctx) return BNS_E_INVAL;
+    if(c) *c = ctx->c;
+    if(w) *w = ctx->w;
+    if(unspaced) *unspaced = ctx->unspaced;
+    if(unwindowed) *unwindowed = ctx->unwindowed;
+    if(canon) *canon = ctx->canon;
+    return BNS_OK;
+}
+
+uint64_t bns_b200_encode_bound(const bns_b200_t *ctx, uint64_t len) {
+    if(!ctx || len < ctx->c) return 0;
+    return len - ctx->c + 1;         // one element per position at most; the tail flush only fires when nothing else was emitted
+}
+
+// ---- table --------------------------------------------------------------------------------------
+int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, const uint32_t *flags, uint64_t n_buckets) {
+    if(!ctx || (n_buckets && (!keys || !vals || !flags))) return ctx ? ctx->fail(BNS_E_INVAL, "null khash arrays") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    auto occupied = [&](u64 i) { return ((flags[i >> 4] >> ((i & 0xfu) << 1)) & 3u) == 0; };   // !__ac_iseither, khash64.h:171
+    u64 n_keys = 0;
+    std::vector<u32> values;
+    {
+        std::vector<u32> tmp;
+        tmp.reserve(1 << 16);
+        for(u64 i = 0; i < n_buckets; ++i)
+            if(occupied(i)) {
+                ++n_keys;
+                tmp.push_back(vals[i]);
+                if(tmp.size() >= (1u << 22)) {
+                    std::sort(tmp.begin(), tmp.end());
+                    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                    std::vector<u32> merged;
+                    std::set_union(values.begin(), values.end(), tmp.begin(), tmp.end(), std::back_inserter(merged));
+                    values.swap(merged);
+                    tmp.clear();
+                }
+            }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        std::vector<u32> merged;
+        std::set_union(values.begin(), values.end(), tmp.begin(), tmp.end(), std::back_inserter(merged));
+        values.swap(merged);
+    }
+    for(u32 b = choose_bits(n_keys, (u32)values.size());; ++b) {
+        free_table(ctx);
+        ctx->values = values;
+        int rc = upload_values(ctx);
+        if(rc == BNS_OK) rc = alloc_table(ctx, b);
+        if(rc != BNS_OK) return rc;
+        u64 cursor = 0;
+        unsigned long long st[3] = {0, 0, 0};
+        rc = insert_stream(ctx, [&](u64 *hk, u32 *hv, size_t cap) {
+            size_t n = 0;
+            while(cursor < n_buckets && n < cap) {
+                if(occupied(cursor)) { hk[n] = keys[cursor]; hv[n] = vals[cursor]; ++n; }
+                ++cursor;
+            }
+            return n;
+        }, st);
+        if(rc != BNS_OK) return rc;
+        if(st[0] == 0) return finish_table(ctx, st);
+        // some key found no room within 6 buckets of home: grow and rebuild
+    }
+}
+
+int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, uint64_t n) {
+    if(!ctx || (n && (!keys || !vals))) return ctx ? ctx->fail(BNS_E_INVAL, "null key/value arrays") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<u32> values(vals, vals + n);
+    std::sort(values.begin(), values.end());
+    values.erase(std::unique(values.begin(), values.end()), values.end());
+    for(u32 b = choose_bits(n, (u32)values.size());; ++b) {
+        free_table(ctx);
+        ctx->values = values;
+        int rc = upload_values(ctx);
+        if(rc == BNS_OK) rc = alloc_table(ctx, b);
+        if(rc != BNS_OK) return rc;
+        u64 cursor = 0;
+        unsigned long long st[3] = {0, 0, 0};
+        rc = insert_stream(ctx, [&](u64 *hk, u32 *hv, size_t cap) {
+            const size_t m = (size_t)std::min<u64>(cap, n - cursor);
+            memcpy(hk, keys + cursor, m * sizeof(u64));
+            memcpy(hv, vals + cursor, m * sizeof(u32));
+            cursor += m;
+            return m;
+        }, st);
+        if(rc != BNS_OK) return rc;
+        if(st[0] == 0) return finish_table(ctx, st);
+    }
+}
+
+int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const uint32_t *d_vals, uint64_t n,
+                               const uint32_t *values, uint32_t n_values) {
+    if(!ctx || !values || !n_values || (n && (!d_keys || !d_vals))) return ctx ? ctx->fail(BNS_E_INVAL, "bad arguments") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<u32> vs(values, values + n_values);
+    std::sort(vs.begin(), vs.end());
+    vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+    cudaStream_t st = ctx->slots[0].st;
+    for(u32 b = choose_bits(n, (u32)vs.size());; ++b) {
+        free_table(ctx);
+        ctx->values = vs;
+        int rc = upload_values(ctx);
+        if(rc == BNS_OK) rc = alloc_table(ctx, b);
+        if(rc != BNS_OK) return rc;
+        CK(cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), st));
+        const u64 CH = 1ull << 28;
+        for(u64 off = 0; off < n; off += CH) {
+            CK(launch_insert(st, ctx->d_slots, b, (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
+                             ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5));
+            ++ctx->stats.kernel_launches;
+        }
+        unsigned long long h[3];
+        CK(cudaMemcpyAsync(h, ctx->d_counters + 5, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if(h[0] == 0) return finish_table(ctx, h);
+    }
+}
+
+int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info) {
+    if(!ctx || !info) return BNS_E_INVAL;
+    memset(info, 0, sizeof *info);
+    info->n_keys = ctx->n_keys;
+    info->n_buckets = ctx->n_buckets;
+    info->bytes = ctx->n_buckets * 32;
+    info->bucket_bits = ctx->bucket_bits;
+    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - 4 : 0;
+    info->n_values = (u32)ctx->values.size();
+    info->max_disp = ctx->max_disp;
+    info->n_displaced = ctx->n_displaced;
+    info->n_overflowed = ctx->n_overflowed;
+    return BNS_OK;
+}
+
+int bns_b200_lookup_batch(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint32_t *vals_out, uint8_t *found_out) {
+    if(!ctx || (n && (!keys || !vals_out || !found_out))) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    const u64 CH = 1ull << 24;
+    for(u64 off = 0; off < n; off += CH) {
+        const u64 m = std::min(CH, n - off);
+        int rc = ensure(s.d_kmers, s.cap_kmers, m);
+        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, m + (m + 3) / 4);
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        uint8_t *d_found = (uint8_t *)(s.d_out + m);
+        CK(cudaMemcpyAsync(s.d_kmers, keys + off, m * sizeof(u64), cudaMemcpyHostToDevice, s.st));
+        CK(launch_lookup(s.st, table_view(ctx), ctx->d_values, s.d_kmers, m, s.d_out, d_found));
+        ++ctx->stats.kernel_launches;
+        CK(cudaMemcpyAsync(vals_out + off, s.d_out, m * sizeof(u32), cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(found_out + off, d_found, m, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+    }
+    return BNS_OK;
+}
+
+// ---- taxonomy ------------------------------------------------------------------------------------
+int bns_b200_load_taxonomy(bns_b200_t *ctx, const uint32_t *child, const uint32_t *parent, uint64_t n) {
+    if(!ctx || (n && (!child || !parent))) return ctx ? ctx->fail(BNS_E_INVAL, "null taxonomy arrays") : BNS_E_INVAL;
+    ctx->tax_child.assign(child, child + n);
+    ctx->tax_parent.assign(parent, parent + n);
+    ctx->tax_loaded = true;
+    ctx->tax_ready = false;
+    return BNS_OK;
+}
+
+// build_parent_map, util.h:766-785: key = atoi(line), parent = atoi(strchr(line, '|') + 2); '#', empty lines skipped
+int bns_b200_load_taxonomy_file(bns_b200_t *ctx, const char *path) {
+    if(!ctx || !path) return BNS_E_INVAL;
+    FILE *fp = fopen(path, "r");
+    if(!fp) return ctx->fail(BNS_E_IO, "cannot open %s", path);
+    std::vector<u32> child, parent;
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t len;
+    while((len = getline(&line, &cap, fp)) >= 0) {
+        if(len && line[len - 1] == '\n') line[len - 1] = 0;
+        if(line[0] == '\n' || line[0] == '\0' || line[0] == '#') continue;
+        const char *p = strchr(line, '|');
+        child.push_back((u32)atoi(line));
+        parent.push_back(p ? (u32)atoi(p + 2) : 0xffffffffu);
+    }
+    free(line);
+    fclose(fp);
+    if(child.size() < 1) return ctx->fail(BNS_E_IO, "Failed to create taxmap from %s", path);   // util.h:782
+    return bns_b200_load_taxonomy(ctx, child.data(), parent.data(), child.size());
+}
+
+int bns_b200_resolve_batch(bns_b200_t *ctx, const uint32_t *taxa, const uint16_t *counts, const uint64_t *offsets,
+                           uint64_t n_lists, uint32_t *taxon_out) {
+    if(!ctx || !offsets || !taxon_out) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!ctx->d_values) return ctx->fail(BNS_E_STATE, "no table loaded (resolve needs its value dictionary)");
+    CK(cudaSetDevice(ctx->device));
+    int rc = finalize_taxonomy(ctx);
+    if(rc != BNS_OK) return rc;
+    if(!n_lists) return BNS_OK;
+    const u64 total = offsets[n_lists];
+    u32 *d_taxa = nullptr, *d_out = nullptr;
+    uint16_t *d_counts = nullptr;
+    u64 *d_off = nullptr;
+    cudaStream_t st = ctx->slots[0].st;
+    CK(cudaMalloc((void **)&d_taxa, std::max<u64>(total, 1) * 4));
+    CK(cudaMalloc((void **)&d_counts, std::max<u64>(total, 1) * 2));
+    CK(cudaMalloc((void **)&d_off, (n_lists + 1) * 8));
+    CK(cudaMalloc((void **)&d_out, n_lists * 4));
+    CK(cudaMemcpyAsync(d_taxa, taxa, total * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_counts, counts, total * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, offsets, (n_lists + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_status, 0, 4, st));
+    CK(launch_resolve(grid_for(ctx, n_lists, 4), st, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), d_taxa, d_counts,
+                      d_off, n_lists, d_out, ctx->d_status));
+    ++ctx->stats.kernel_launches;
+    u32 status = 0;
+    CK(cudaMemcpyAsync(taxon_out, d_out, n_lists * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_taxa); cudaFree(d_counts); cudaFree(d_off); cudaFree(d_out);
+    return check_status(ctx, status);
+}
+
+// ---- replication -----------------------------------------------------------------------------------
+int bns_b200_db_export_header(const bns_b200_t *ctx_, bns_b200_db_header *hdr) {
+    bns_b200_t *ctx = const_cast<bns_b200_t *>(ctx_);
+    if(!ctx || !hdr) return BNS_E_INVAL;
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    int rc = finalize_taxonomy(ctx);
+    if(rc != BNS_OK) return rc;
+    memset(hdr, 0, sizeof *hdr);
+    hdr->words[0] = 0x42304e53424e5331ull;      // magic
+    hdr->words[1] = ctx->bucket_bits;
+    hdr->words[2] = ctx->values.size();
+    hdr->words[3] = ctx->n_nodes;
+    hdr->words[4] = ctx->node_of_one;
+    hdr->words[5] = ctx->n_keys;
+    hdr->words[6] = ctx->n_displaced;
+    hdr->words[7] = ctx->n_overflowed;
+    hdr->words[8] = ctx->max_disp;
+    return BNS_OK;
+}
+
+int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr) {
+    if(!ctx || !hdr || hdr->words[0] != 0x42304e53424e5331ull) return ctx ? ctx->fail(BNS_E_INVAL, "bad database header") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    free_table(ctx);
+    if(ctx->d_node_info) cudaFree(ctx->d_node_info);
+    if(ctx->d_val_info) cudaFree(ctx->d_val_info);
+    ctx->d_node_info = ctx->d_val_info = nullptr;
+    ctx->values.assign((size_t)hdr->words[2], 0);
+    ctx->n_nodes = (u32)hdr->words[3];
+    ctx->node_of_one = (u32)hdr->words[4];
+    ctx->n_keys = hdr->words[5]; ctx->n_displaced = hdr->words[6]; ctx->n_overflowed = hdr->words[7];
+    ctx->max_disp = (u32)hdr->words[8];
+    int rc = alloc_table(ctx, (u32)hdr->words[1]);
+    if(rc != BNS_OK) return rc;
+    CK(cudaMalloc((void **)&ctx->d_values, std::max<size_t>(ctx->values.size(), 1) * sizeof(u32)));
+    CK(cudaMalloc((void **)&ctx->d_val_info, std::max<size_t>(ctx->values.size(), 1) * sizeof(uint4)));
+    CK(cudaMalloc((void **)&ctx->d_node_info, std::max<u32>(ctx->n_nodes, 1) * sizeof(uint4)));
+    CK(cudaStreamSynchronize(ctx->slots[0].st));
+    return BNS_OK;
+}
+
+int bns_b200_db_segments(const bns_b200_t *ctx, void **dev_ptrs, uint64_t *bytes, int cap, int *n) {
+    if(!ctx || !dev_ptrs || !bytes || !n || cap < 4) return BNS_E_INVAL;
+    if(!ctx->d_slots || !ctx->d_val_info) return BNS_E_STATE;
+    dev_ptrs[0] = ctx->d_slots;     bytes[0] = ctx->n_buckets * 32;
+    dev_ptrs[1] = ctx->d_values;    bytes[1] = ctx->values.size() * sizeof(u32);
+    dev_ptrs[2] = ctx->d_val_info;  bytes[2] = ctx->values.size() * sizeof(uint4);
+    dev_ptrs[3] = ctx->d_node_info; bytes[3] = (uint64_t)ctx->n_nodes * sizeof(uint4);
+    *n = 4;
+    return BNS_OK;
+}
+
+int bns_b200_db_commit(bns_b200_t *ctx) {
+    if(!ctx) return BNS_E_INVAL;
+    if(!ctx->d_slots || !ctx->d_val_info) return ctx->fail(BNS_E_STATE, "nothing to commit");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if(!ctx->values.empty())
+        CK(cudaMemcpy(ctx->values.data(), ctx->d_values, ctx->values.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+    ctx->tax_ready = true;
+    ctx->tax_loaded = true;
+    return BNS_OK;
+}
+
+// ---- encode ----------------------------------------------------------------------------------------
+int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
+                          uint64_t *kmers_out, const uint64_t *out_offsets, uint32_t *counts_out) {
+    if(!ctx || !offsets || !out_offsets || !counts_out) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!n_seqs) return BNS_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t smem = stream_smem_bytes(ctx->ring_cap, false);
+    const int occ = encode_occupancy(smem);
+    u32 status_acc = 0;
+    int slot_i = 0;
+    u64 r0 = 0;
+    u32 h_status[N_SLOTS] = {0, 0, 0};
+    while(r0 < n_seqs) {
+        u64 r1 = r0;
+        while(r1 < n_seqs && r1 - r0 < CHUNK_READS && (r1 == r0 || offsets[r1 + 1] - offsets[r0] <= CHUNK_BASES)) ++r1;
+        const u64 nb = offsets[r1] - offsets[r0], nr = r1 - r0;
+        const u64 nk = out_offsets[r1] - out_offsets[r0];
+        Slot &s = ctx->slots[slot_i];
+        CK(cudaStreamSynchronize(s.st));
+        status_acc |= h_status[slot_i];
+        int rc = ensure(s.d_bases, s.cap_bases, nb + 16);
+        if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_out_offsets, s.cap_out_offsets, nr + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_kmers, s.cap_kmers, nk + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, nr + 1);
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_out_offsets, out_offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemsetAsync(s.d_out + nr, 0, 4, s.st));
+        CK(launch_encode(ctx->enc, grid_for(ctx, nr, occ), smem, s.st, s.d_bases - offsets[r0], s.d_offsets, nr, offsets[r1],
+                         s.d_kmers - out_offsets[r0], s.d_out_offsets, s.d_out, ctx->ring_cap, s.d_out + nr));
+        ++ctx->stats.kernel_launches;
+        if(nk) CK(cudaMemcpyAsync(kmers_out + out_offsets[r0], s.d_kmers, nk * 8, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(counts_out + r0, s.d_out, nr * 4, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(&h_status[slot_i], s.d_out + nr, 4, cudaMemcpyDeviceToHost, s.st));
+        ctx->stats.h2d_bytes += nb + 16 * (nr + 1);
+        ctx->stats.d2h_bytes += nk * 8 + nr * 4;
+        ctx->stats.reads_processed += nr;
+        ctx->stats.bases_processed += nb;
+        r0 = r1;
+        slot_i = (slot_i + 1) % N_SLOTS;
+    }
+    for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); status_acc |= h_status[i]; }
+    return check_status(ctx, status_acc & 1u);
+}
+
+// ---- classify --------------------------------------------------------------------------------------
+static int classify_ready(bns_b200_t *ctx) {
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    return finalize_taxonomy(ctx);
+}
+
+int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
+                             uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,
+                             uint32_t *d_taxa, const uint64_t *d_taxa_offsets, void *stream) {
+    if(!ctx || !d_offsets || !d_taxon) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = classify_ready(ctx);
+    if(rc != BNS_OK) return rc;
+    const u32 mates = paired ? 2 : 1;
+    const u64 n_rec = n_reads / mates;
+    if(!n_rec) return BNS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // total bases = offsets[n_reads] lives on the device; the kernel only uses it to bound the 16-byte staging loads
+    u64 total_bases = 0;
+    CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
+    const int occ = classify_occupancy(smem);
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_classify(ctx->enc, grid_for(ctx, n_rec, occ), smem, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
+                       table_view(ctx), tax_view(ctx), ctx->d_values, d_taxon, d_n_hit, d_n_missing, d_taxa,
+                       (const u64 *)d_taxa_offsets, ctx->ring_cap, ctx->d_counters, ctx->d_status));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ++ctx->stats.kernel_launches;
+    ctx->stats.reads_processed += n_reads;
+    ctx->stats.bases_processed += total_bases;
+    return BNS_OK;
+}
+
+int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                            uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
+                            uint32_t *taxa_out, const uint64_t *taxa_offsets) {
+    if(!ctx || !offsets || !taxon_out || (taxa_out && !taxa_offsets)) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = classify_ready(ctx);
+    if(rc != BNS_OK) return rc;
+    const u32 mates = paired ? 2 : 1;
+    const u64 n_rec_total = n_reads / mates;
+    if(!n_rec_total) return BNS_OK;
+    const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
+    const int occ = classify_occupancy(smem);
+    CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
+    CK(cudaStreamSynchronize(ctx->slots[0].st));
+    int slot_i = 0;
+    u64 q0 = 0;                                                    // record cursor
+    while(q0 < n_rec_total) {
+        u64 q1 = q0;
+        while(q1 < n_rec_total && (q1 - q0) * mates < CHUNK_READS &&
+              (q1 == q0 || offsets[(q1 + 1) * mates] - offsets[q0 * mates] <= CHUNK_BASES)) ++q1;
+        const u64 r0 = q0 * mates, r1 = q1 * mates, nr = r1 - r0, nq = q1 - q0;
+        const u64 nb = offsets[r1] - offsets[r0];
+        Slot &s = ctx->slots[slot_i];
+        CK(cudaStreamSynchronize(s.st));
+        rc = ensure(s.d_bases, s.cap_bases, nb + 16);
+        if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 3 * nq);
+        u64 nt = 0;
+        if(rc == BNS_OK && taxa_out) {
+            nt = taxa_offsets[q1] - taxa_offsets[q0];
+            rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
+            if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
+        }
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        CK(launch_classify(ctx->enc, grid_for(ctx, nq, occ), smem, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
+                           table_view(ctx), tax_view(ctx), ctx->d_values, s.d_out, n_hit_out ? s.d_out + nq : nullptr,
+                           n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
+                           taxa_out ? s.d_taxa_offsets : nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
+        ++ctx->stats.kernel_launches;
+        CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(n_hit_out) CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(taxa_out && nt) CK(cudaMemcpyAsync(taxa_out + taxa_offsets[q0], s.d_taxa, nt * 4, cudaMemcpyDeviceToHost, s.st));
+        ctx->stats.h2d_bytes += nb + 8 * (nr + 1) + (taxa_out ? 8 * (nq + 1) : 0);
+        ctx->stats.d2h_bytes += nq * 4 * (1 + (n_hit_out != nullptr) + (n_missing_out != nullptr)) + nt * 4;
+        ctx->stats.reads_processed += nr;
+        ctx->stats.bases_processed += nb;
+        q0 = q1;
+        slot_i = (slot_i + 1) % N_SLOTS;
+    }
+    for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st));
+    u32 status = 0;
+    CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
+    return check_status(ctx, status & 2u);
+}
+
+int bns_b200_sync(bns_b200_t *ctx) {
+    if(!ctx) return BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    return BNS_OK;
+}
+
+int bns_b200_stats_get(const bns_b200_t *ctx_, bns_b200_stats *out) {
+    bns_b200_t *ctx = const_cast<bns_b200_t *>(ctx_);
+    if(!ctx || !out) return BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    ctx->stats.n_classified = h[0];
+    ctx->stats.n_unclassified = h[1];
+    float ms = 0.f;
+    if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+    else cudaGetLastError();
+    *out = ctx->stats;
+    return BNS_OK;
+}
+
+int bns_b200_stats_reset(bns_b200_t *ctx) {
+    if(!ctx) return BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long)));
+    ctx->stats = bns_b200_stats{};
+    return BNS_OK;
+}
+
+int bns_b200_host_alloc(void **ptr, size_t bytes) {
+    if(!ptr) return BNS_E_INVAL;
+    if(cudaMallocHost(ptr, bytes) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return BNS_E_NOMEM; }
+    return BNS_OK;
+}
+int bns_b200_host_free(void *ptr) {
+    if(ptr && cudaFreeHost(ptr) != cudaSuccess) { cudaGetLastError(); return BNS_E_CUDA; }
+    return BNS_OK;
+}
+
+int bns_b200_bench_gather(bns_b200_t *ctx, uint64_t n_loads, uint64_t seed, double *ms_out) {
+    if(!ctx || !ms_out) return BNS_E_INVAL;
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].st;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_gather(ctx->n_sm * 8, st, ctx->d_slots, ctx->bucket_bits, n_loads, seed, ctx->d_counters + 7));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ++ctx->stats.kernel_launches;
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *ms_out = ms;
+    return BNS_OK;
+}
+
+}  // extern "C"

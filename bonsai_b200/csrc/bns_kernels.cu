@@ -1,0 +1,707 @@
+// bns_kernels.cu -- hand-written sm_100a kernels of the classify hot path.
+//
+//   bns_stream_kernel<Sink>   warp-per-record: stage the read tile in shared memory (2-bit packed), generate the
+//                             k-mer / minimizer stream of Encoder::for_each (include/bonsai/encoder.h:416-442 and the
+//                             mode bodies :211-353), and hand every emitted k-mer to the sink:
+//       StoreSink             write the stream out                      (Encoder API parity surface)
+//       ClassifySink          probe the device table (kh_get, khash64.h:250-263), keep the per-record distinct-taxon
+//                             counts (linear::counter, linear.h:229), then resolve_tree (util.h:831-869) in the same warp
+//   bns_insert_kernel         builds the bucketised open-addressed table with 64-bit CAS
+//   bns_lookup_kernel         kh_get + kh_val over a key batch
+//   bns_resolve_kernel        resolve_tree over explicit (taxid,count) lists
+//   bns_gather_kernel         random 32-byte-sector gather (the measured random-access ceiling)
+#include "bns_device.cuh"
+#include "bns_kernels.h"
+
+namespace bns {
+
+
+// ---------------------------------------------------------------------------------------------
+// per-warp shared memory carve-up (dynamic)
+// ---------------------------------------------------------------------------------------------
+constexpr int NWORDS = (TILE + CMAX + 16) / 16 + 3;     // 2-bit code words / invalid-bit words per tile
+
+struct WarpSmem {
+    u32 *codes;      // [NWORDS] 16 bases per word, first base in the top bits
+    u32 *bad;        // [NWORDS] 16 invalid-bits per word (low half), first base in bit 15
+    u64 *rel;        // [ring_cap] window ring: elements
+    u64 *rsc;        // [ring_cap] window ring: scores
+    u32 *ids;        // [AGG_CAP] distinct value ids      (ClassifySink)
+    u32 *cnt;        // [AGG_CAP] their counts
+    u32 *tin;        // [AGG_CAP] scratch for resolve
+    u32 *tout;       // [AGG_CAP]
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(u32 ring_cap, bool classify) {
+    size_t b = 2 * NWORDS * sizeof(u32);
+    b = (b + 7) & ~size_t(7);
+    b += 2 * (size_t)ring_cap * sizeof(u64);
+    if(classify) b += 4 * AGG_CAP * sizeof(u32);
+    return (b + 15) & ~size_t(15);
+}
+__device__ inline WarpSmem carve(unsigned char *base, u32 ring_cap, bool classify) {
+    WarpSmem s;
+    s.codes = (u32 *)base;
+    s.bad = s.codes + NWORDS;
+    size_t off = 2 * NWORDS * sizeof(u32);
+    off = (off + 7) & ~size_t(7);
+    s.rel = (u64 *)(base + off);
+    s.rsc = s.rel + ring_cap;
+    off += 2 * (size_t)ring_cap * sizeof(u64);
+    s.ids = (u32 *)(base + off);
+    s.cnt = s.ids + AGG_CAP;
+    s.tin = s.cnt + AGG_CAP;
+    s.tout = s.tin + AGG_CAP;
+    (void)classify;
+    return s;
+}
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+// exclusive prefix sum of a small per-lane count + warp total
+__device__ __forceinline__ u32 warp_excl_scan(u32 v, u32 lane, u32 &total) {
+    u32 x = v;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const u32 y = __shfl_up_sync(FULL, x, d);
+        if(lane >= (u32)d) x += y;
+    }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile staging: bases [p0, p0+span) of the sequence -> shared memory. Returns the coordinate shift (the
+// tile's first base sits at coordinate `shift` because loads are 16-byte aligned) and whether any staged
+// base is invalid.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 stage_tile(const WarpSmem &S, const char *seq, u64 p0, u64 L, u32 span,
+                                          const char *buf_end, u32 lane, bool &any_invalid) {
+    const char *a0 = seq + p0;
+    const u32 shift = (u32)((uintptr_t)a0 & 15u);
+    const char *aligned = a0 - shift;
+    const u64 remaining = L - p0;
+    const u32 nbases = (u32)(remaining < span ? remaining : span);      // bases of this sequence in the tile
+    const u32 hi = shift + nbases;                                      // valid coordinates: [shift, hi)
+    const u32 nblk = (hi + 15) >> 4;
+    u32 codes = 0, bad = 0xffffu;
+    if(lane < nblk) {
+        const char *p = aligned + 16 * lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if(p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p));
+        pack16(v, codes, bad);
+        // bases outside [shift, hi) belong to neighbours (or to nobody): never read by a k-mer, but they
+        // must not trigger the slow path
+        const int before = (int)shift - (int)(16 * lane);
+        const int after = (int)hi - (int)(16 * lane);
+        u32 keep = 0xffffu;
+        if(before > 0) keep &= (before >= 16) ? 0u : (0xffffu >> before);
+        if(after < 16) keep &= (after <= 0) ? 0u : ~(0xffffu >> after);
+        bad &= keep;
+    } else {
+        bad = 0;
+    }
+    if(lane < NWORDS) { S.codes[lane] = codes; S.bad[lane] = bad; }
+    any_invalid = __any_sync(FULL, bad != 0);
+    __syncwarp();
+    return shift;
+}
+
+// the comb's k bases starting at coordinate q; invalid -> KMER_NONE (Encoder::kmer, encoder.h:547-592)
+__device__ __forceinline__ u64 gather_kmer(const EncParams &cP, const WarpSmem &S, u32 q, bool check_bad) {
+    u64 x = 0;
+    bool inval = false;
+    const u32 ns = cP.n_seg;
+    for(u32 s = 0; s < ns; ++s) {
+        const u32 off = cP.seg_off[s], len = cP.seg_len[s];
+        const u64 bits = extract_bases(S.codes, q + off, len);
+        x = (len == 32) ? bits : ((x << (2 * len)) | bits);
+        if(check_bad) inval |= any_bad(S.bad, q + off, len) != 0;
+    }
+    return inval ? KMER_NONE : x;
+}
+
+// score of one window element (scorer_(kmer, data), encoder.h:616-628 ; :337 for the rolling entropy)
+__device__ __forceinline__ u64 score_of(const EncParams &cP, u64 x) {
+    const u32 sk = cP.score_kind;
+    if(sk == SC_LEX) return lex_score(x);
+    if(sk == SC_ENT_NOTFULL)                       // ent_score with CircusEnt::NOT_FULL, encoder.h:55-58, entropy.h:45
+        return cast_u64(__ull2double_rn(x) / (-1. + 1e-4), cP.cast_wrap);
+    // rolling entropy over the k bases of x: sum in ska::flat_hash_map iteration order A, G, C, T
+    // (fibonacci-hashed slots 0,1,4,6 of its 8-slot table, hll/include/flat_hash_map/flat_hash_map.hpp:1268)
+    const u32 k = cP.k;
+    const u64 m = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+    const u64 lo = x & 0x5555555555555555ull, hi = (x >> 1) & 0x5555555555555555ull;
+    const u32 nT = __popcll(hi & lo), nG = __popcll(hi & ~lo), nC = __popcll(~hi & lo & m);
+    const u32 nA = k - nT - nG - nC;
+    double h = 0.;
+    if(nA) h = h + cP.plogp[nA];
+    if(nG) h = h + cP.plogp[nG];
+    if(nC) h = h + cP.plogp[nC];
+    if(nT) h = h + cP.plogp[nT];
+    return cast_u64(__ull2double_rn(x) / (h + .001), cP.cast_wrap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sinks
+// ---------------------------------------------------------------------------------------------
+struct StoreSink {
+    u64 *out;         // this record's output window
+    u64 cap, n;       // warp-uniform
+    __device__ __forceinline__ void begin(u64 *o, u64 c) { out = o; cap = c; n = 0; }
+    __device__ __forceinline__ void consume(const WarpSmem &, const u64 (&x)[PPL], u32 mask, u32 lane) {
+        u32 total;
+        const u32 ex = warp_excl_scan(__popc(mask), lane, total);
+        u64 idx = n + ex;
+#pragma unroll
+        for(int i = 0; i < PPL; ++i)
+            if(mask >> i & 1u) { if(idx < cap) out[idx] = x[i]; ++idx; }
+        n += total;
+    }
+};
+
+struct ClassifySink {
+    TableView T;
+    u32 *taxa_out;    // optional ordered hit list of this record (raw taxids), or nullptr
+    const u32 *dict;  // value id -> taxid (only for taxa_out)
+    u32 n_distinct, n_hit, n_miss, overflow;   // warp-uniform
+
+    __device__ __forceinline__ void begin(u32 *taxa) { taxa_out = taxa; n_distinct = n_hit = n_miss = overflow = 0; }
+
+    __device__ __forceinline__ u32 match4(u64 tag, u64 s0, u64 s1, u64 s2, u64 s3) const {
+        const u32 sh = T.tag_shift;
+        u32 v = VAL_MISS;
+        if(((s0 ^ tag) >> sh) == 0) v = (u32)s0 & T.val_mask;
+        if(((s1 ^ tag) >> sh) == 0) v = (u32)s1 & T.val_mask;
+        if(((s2 ^ tag) >> sh) == 0) v = (u32)s2 & T.val_mask;
+        if(((s3 ^ tag) >> sh) == 0) v = (u32)s3 & T.val_mask;
+        return v;
+    }
+
+    // kh_get + kh_val for up to PPL keys per lane: all home-bucket sectors are requested before any is inspected
+    __device__ __forceinline__ void probe(const u64 (&x)[PPL], u32 mask, u32 (&val)[PPL]) const {
+        const u32 b = T.bucket_bits;
+        u64 h[PPL], s[PPL][4];
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) {
+            h[i] = mix64(x[i]);
+            s[i][0] = s[i][1] = s[i][2] = s[i][3] = ~0ull;
+            if(mask >> i & 1u) ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
+        }
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) {
+            val[i] = VAL_MISS;
+            if(!(mask >> i & 1u)) continue;
+            const u64 tag = h[i] << b;
+            u32 v = match4(tag, s[i][0], s[i][1], s[i][2], s[i][3]);
+            // rare: a key homed here was displaced (overflow mark lives in slot 0 of a full bucket)
+            if(v == VAL_MISS && s[i][3] != ~0ull && ((s[i][0] >> (T.tag_shift - 1)) & 1ull)) {
+                const u64 bmask = (1ull << b) - 1;
+                const u64 home = h[i] >> (64 - b);
+                for(u32 d = 1; d <= 6; ++d) {
+                    u64 a, bb, c, e;
+                    ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
+                    v = match4(tag | ((u64)d << T.tag_shift), a, bb, c, e);
+                    if(v != VAL_MISS || e == ~0ull) break;
+                }
+            }
+            val[i] = v;
+        }
+    }
+
+    __device__ __forceinline__ void consume(const WarpSmem &S, const u64 (&x)[PPL], u32 mask, u32 lane) {
+        if(!__any_sync(FULL, mask != 0)) return;
+        u32 val[PPL];
+        probe(x, mask, val);
+        u32 todo = 0;
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) if((mask >> i & 1u) && val[i] != VAL_MISS) todo |= 1u << i;
+        const u32 my_hits = __popc(todo);
+        u32 hits_total;
+        const u32 ex = warp_excl_scan(my_hits, lane, hits_total);
+        const u32 emitted = __reduce_add_sync(FULL, __popc(mask));
+        if(taxa_out) {
+            u32 idx = n_hit + ex;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) taxa_out[idx++] = dict[val[i]];
+        }
+        n_hit += hits_total;
+        n_miss += emitted - hits_total;
+        // fold the hits into the per-record distinct list (linear::counter::add)
+        for(;;) {
+            const u32 bal = __ballot_sync(FULL, todo != 0);
+            if(!bal) break;
+            const u32 leader = __ffs(bal) - 1;
+            u32 fv = 0;
+#pragma unroll
+            for(int i = PPL - 1; i >= 0; --i) if(todo >> i & 1u) fv = val[i];
+            const u32 v = __shfl_sync(FULL, fv, leader);
+            u32 c = 0;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) if((todo >> i & 1u) && val[i] == v) { ++c; todo &= ~(1u << i); }
+            const u32 total = __reduce_add_sync(FULL, c);
+            int found = -1;
+            for(u32 base = 0; base < n_distinct; base += 32) {
+                const u32 idx = base + lane;
+                const u32 bm = __ballot_sync(FULL, idx < n_distinct && S.ids[idx] == v);
+                if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
+            }
+            if(found < 0) {
+                if(n_distinct < AGG_CAP) {
+                    if(lane == 0) { S.ids[n_distinct] = v; S.cnt[n_distinct] = total; }
+                    ++n_distinct;
+                } else overflow = 1;
+            } else if(lane == 0) S.cnt[found] += total;
+            __syncwarp();
+        }
+    }
+
+    // resolve_tree (util.h:831-869): score(t) = sum of u16 counts over t's root path; unique max wins, ties -> lca of
+    // all tied taxa. Root paths are tested with Euler-tour intervals instead of walking the parent map.
+    __device__ __forceinline__ u32 resolve(const WarpSmem &S, const TaxView &X, u32 lane) const {
+        const u32 n = n_distinct;
+        if(n == 0) return 0;
+        if(n == 1) return X.val_info[S.ids[0]].w;
+        for(u32 i = lane; i < n; i += 32) {
+            const uint4 inf = X.val_info[S.ids[i]];
+            S.tin[i] = inf.x; S.tout[i] = inf.y;
+        }
+        __syncwarp();
+        u32 best = 0;
+        for(u32 base = 0; base < n; base += 32) {
+            const u32 i = base + lane;
+            u32 sc = 0;
+            if(i < n) {
+                const u32 ti = S.tin[i];
+                for(u32 j = 0; j < n; ++j)
+                    if(S.tin[j] <= ti && ti < S.tout[j]) sc += S.cnt[j] & 0xffffu;
+            }
+            best = max(best, __reduce_max_sync(FULL, sc));
+        }
+        // ties (score == best), folded in list order
+        u32 node = 0, ntied = 0, first_id = 0;
+        for(u32 base = 0; base < n; base += 32) {
+            const u32 i = base + lane;
+            u32 sc = 0;
+            if(i < n) {
+                const u32 ti = S.tin[i];
+                for(u32 j = 0; j < n; ++j)
+                    if(S.tin[j] <= ti && ti < S.tout[j]) sc += S.cnt[j] & 0xffffu;
+            }
+            u32 tied = __ballot_sync(FULL, i < n && sc == best);
+            while(tied) {
+                const u32 l = __ffs(tied) - 1;
+                tied &= tied - 1;
+                const u32 id = S.ids[base + l];
+                const uint4 inf = X.val_info[id];            // uniform address
+                if(ntied == 0) { node = inf.z; first_id = id; }
+                else {
+                    // lca(node, b): climb from `node` until its interval covers b (util.h:634-663)
+                    const u32 tb = inf.x;
+                    u32 a = node;
+                    while(a) {
+                        const uint4 na = X.node_info[a];
+                        if(na.x <= tb && tb < na.y) break;
+                        a = na.z;
+                    }
+                    node = a ? a : X.node_of_one;
+                }
+                ++ntied;
+            }
+        }
+        if(ntied == 1) return X.val_info[first_id].w;
+        return X.node_info[node].w;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// window ring (QueueMap, qmap.h:79-96) over the elements a tile produced. `m` new elements were written to
+// S.rel/S.rsc[hist .. hist+m) by the caller. Produces the window minima for the new elements this lane owns
+// (indices j = PPL*lane + i) and rolls the ring forward. total_before = elements pushed before this tile.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 window_outputs(const WarpSmem &S, u32 hist, u32 m, u64 total_before, u32 W, u32 lane,
+                                              u64 (&o)[PPL]) {
+    u32 mask = 0;
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) {
+        const u32 j = PPL * lane + i;
+        o[i] = KMER_NONE;
+        if(j < m && total_before + j + 1 >= W) {
+            const u32 end = hist + j;                 // inclusive
+            u64 be = S.rel[end], bs = S.rsc[end];
+            for(u32 t = 1; t < W; ++t) {
+                const u64 e = S.rel[end - t], s = S.rsc[end - t];
+                if(s < bs || (s == bs && e < be)) { be = e; bs = s; }     // ElScore::operator<, qmap.h:23
+            }
+            o[i] = be;
+            mask |= 1u << i;
+        }
+    }
+    __syncwarp();
+    return mask;
+}
+__device__ __forceinline__ u32 roll_ring(const WarpSmem &S, u32 hist, u32 m, u32 W, u32 lane) {
+    const u32 have = hist + m;
+    const u32 keep = have < W - 1 ? have : W - 1;
+    const u32 src = have - keep;
+    if(src) {
+        for(u32 base = 0; base < keep; base += 32) {
+            const u32 i = base + lane;
+            u64 e = 0, s = 0;
+            if(i < keep) { e = S.rel[src + i]; s = S.rsc[src + i]; }
+            __syncwarp();
+            if(i < keep) { S.rel[i] = e; S.rsc[i] = s; }
+            __syncwarp();
+        }
+    }
+    return keep;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one sequence (one mate) through the encoder; every emitted k-mer goes to sink.consume in emission order
+// ---------------------------------------------------------------------------------------------
+template <class Sink>
+__device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L, const char *buf_end,
+                                                Sink &sink, u32 lane) {
+    const u32 fam = cP.family;
+    const u32 k = cP.k, c = cP.c, W = cP.W;
+    if(fam == FAM_NONE || L < c) return;                       // has_next_kmer(), encoder.h:418,594
+    const u64 npos = L - c + 1;
+    const u32 span = TILE + c - 1;
+    u32 hist = 0;                                               // ring entries carried from earlier tiles
+    u64 total = 0;                                              // elements pushed so far (QueueMap list_)
+    for(u64 p0 = 0; p0 < npos; p0 += TILE) {
+        bool any_invalid;
+        const u32 shift = stage_tile(S, seq, p0, L, span, buf_end, lane, any_invalid);
+        u64 x[PPL];
+        u32 live = 0;                                           // positions of this lane inside the sequence
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) {
+            const u64 p = p0 + PPL * lane + i;
+            x[i] = KMER_NONE;
+            if(p < npos) {
+                live |= 1u << i;
+                x[i] = gather_kmer(cP, S, shift + PPL * lane + i, any_invalid);
+            }
+        }
+        if(fam == FAM_U) {
+            u32 mask = 0;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) {
+                // an invalid window is skipped; a valid T*32 (== ~0 for k = 32) is emitted (encoder.h:251-253)
+                const bool ok = (live >> i & 1u) && !(x[i] == KMER_NONE && any_invalid &&
+                                any_bad(S.bad, shift + PPL * lane + i, k));
+                if(ok) { mask |= 1u << i; if(cP.canon_elem) x[i] = canonical(x[i], k); }
+            }
+            __syncwarp();
+            sink.consume(S, x, mask, lane);
+            continue;
+        }
+        // element set of this tile
+        u32 emask;
+        if(fam == FAM_K) {
+            emask = live;                                       // every position pushes (invalid -> ~0, or 0 if canon)
+            if(cP.canon_elem) {
+#pragma unroll
+                for(int i = 0; i < PPL; ++i) if(live >> i & 1u) x[i] = canonical(x[i], k);
+            }
+        } else {                                                // FAM_R: only valid k-mers push
+            emask = 0;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) if((live >> i & 1u) && x[i] != KMER_NONE) emask |= 1u << i;
+        }
+        if(W == 1) {                                            // window of one: the element itself
+            u32 mask = emask;
+            if(cP.filter_none) {
+#pragma unroll
+                for(int i = 0; i < PPL; ++i) if(x[i] == KMER_NONE) mask &= ~(1u << i);
+            }
+            if(cP.canon_emit) {
+#pragma unroll
+                for(int i = 0; i < PPL; ++i) if(mask >> i & 1u) x[i] = canonical(x[i], k);
+            }
+            __syncwarp();
+            sink.consume(S, x, mask, lane);
+            total += __reduce_add_sync(FULL, __popc(emask));
+            continue;
+        }
+        u32 m;
+        const u32 ex = warp_excl_scan(__popc(emask), lane, m);
+        {
+            u32 idx = hist + ex;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i)
+                if(emask >> i & 1u) { S.rel[idx] = x[i]; S.rsc[idx] = score_of(cP, x[i]); ++idx; }
+        }
+        __syncwarp();
+        u64 o[PPL];
+        u32 mask = window_outputs(S, hist, m, total, W, lane, o);
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) {
+            if(cP.filter_none && o[i] == KMER_NONE) mask &= ~(1u << i);
+            if(cP.canon_emit && (mask >> i & 1u)) o[i] = canonical(o[i], k);
+        }
+        hist = roll_ring(S, hist, m, W, lane);
+        total += m;
+        sink.consume(S, o, mask, lane);
+    }
+    // tail flush: a queue that never filled emits its minimum once (encoder.h:304-305,343-344)
+    if(cP.tail_flush && W > 1 && total > 0 && total < W) {
+        u64 be = S.rel[0], bs = S.rsc[0];
+        for(u32 t = 1; t < (u32)total; ++t) {
+            const u64 e = S.rel[t], s = S.rsc[t];
+            if(s < bs || (s == bs && e < be)) { be = e; bs = s; }
+        }
+        u64 o[PPL] = {cP.canon_emit ? canonical(be, k) : be, KMER_NONE, KMER_NONE, KMER_NONE};
+        __syncwarp();
+        sink.consume(S, o, lane == 0 ? 1u : 0u, lane);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char g_smem[];
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+bns_encode_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_seqs, u64 total_bases,
+                  u64 *__restrict__ kmers_out, const u64 *__restrict__ out_offsets, u32 *__restrict__ counts_out,
+                  u32 ring_cap, u32 *__restrict__ status) {
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, false), ring_cap, false);
+    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    StoreSink sink;
+    for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_seqs; r += nwarps) {
+        const u64 b = offsets[r], e = offsets[r + 1];
+        const u64 ob = out_offsets[r], oe = out_offsets[r + 1];
+        sink.begin(kmers_out + ob, oe - ob);
+        encode_sequence(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+        if(lane == 0) {
+            counts_out[r] = (u32)sink.n;
+            if(sink.n > sink.cap) atomicOr(status, 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records, u32 mates,
+                    u64 total_bases, TableView T, TaxView X, const u32 *__restrict__ dict,
+                    u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out, u32 *__restrict__ nmiss_out,
+                    u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 ring_cap,
+                    unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, true), ring_cap, true);
+    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    ClassifySink sink;
+    sink.T = T;
+    sink.dict = dict;
+    u32 n_cls = 0, n_uncls = 0;
+    for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_records; r += nwarps) {
+        sink.begin(taxa_out ? taxa_out + taxa_offsets[r] : nullptr);
+        for(u32 mt = 0; mt < mates; ++mt) {
+            const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
+            encode_sequence(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+        }
+        const u32 taxon = sink.resolve(S, X, lane);
+        if(lane == 0) {
+            taxon_out[r] = taxon;
+            if(nhit_out) nhit_out[r] = sink.n_hit;
+            if(nmiss_out) nmiss_out[r] = sink.n_miss;
+            if(sink.overflow) atomicOr(status, 2u);
+        }
+        if(taxon) ++n_cls; else ++n_uncls;
+        __syncwarp();
+    }
+    if(lane == 0 && (n_cls | n_uncls)) {
+        atomicAdd(&counters[0], (unsigned long long)n_cls);
+        atomicAdd(&counters[1], (unsigned long long)n_uncls);
+    }
+}
+
+// value -> dense id by binary search in the sorted distinct-value list
+__device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u32 v) {
+    u32 lo = 0, hi = n;
+    while(lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if(values[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && values[lo] == v) ? lo : VAL_MISS;
+}
+
+// Bucketised open addressing, 4 x u64 slots per 32-byte bucket:
+//   slot = [ low (64-b) bits of mix64(key) | disp:3 | ovf:1 | value id:(b-4) ],  empty = ~0.
+// A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 6);
+// the home bucket's slot 0 then carries the ovf mark so that misses stop after one sector otherwise.
+__global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__restrict__ keys,
+                                  const u32 *__restrict__ vals, u64 n, const u32 *__restrict__ values, u32 n_values,
+                                  unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const u64 key = keys[i];
+    const u32 vid = value_id(values, n_values, vals[i]);
+    if(vid == VAL_MISS) { atomicAdd(&stats[2], 1ull); return; }
+    const u64 h = mix64(key);
+    const u64 home = h >> (64 - b), bmask = (1ull << b) - 1;
+    const u32 tag_shift = b - 3;
+    const u64 tag = h << b;
+    for(u32 d = 0; d <= 6; ++d) {
+        u64 *bk = slots + (((home + d) & bmask) << 2);
+        const u64 entry = tag | ((u64)d << tag_shift) | vid;
+        for(int s = 0; s < 4; ++s) {
+            u64 cur = bk[s];
+            if(cur == ~0ull) {
+                cur = atomicCAS((unsigned long long *)&bk[s], ~0ull, (unsigned long long)entry);
+                if(cur == ~0ull) { if(d) atomicAdd(&stats[1], 1ull); return; }
+            }
+            if(((cur ^ entry) >> tag_shift) == 0) return;          // same key already present: first value stays
+        }
+        if(d == 0) atomicOr((unsigned long long *)&bk[0], 1ull << (tag_shift - 1));
+    }
+    atomicAdd(&stats[0], 1ull);
+}
+
+__global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b,
+                                       unsigned long long *__restrict__ out /* [0] entries [1] ovf buckets [2] max disp */) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_buckets) return;
+    const u32 tag_shift = b - 3;
+    u32 cnt = 0, md = 0;
+    for(int s = 0; s < 4; ++s) {
+        const u64 v = slots[4 * i + s];
+        if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & 7u)); }
+    }
+    if(cnt) atomicAdd(&out[0], (unsigned long long)cnt);
+    if(cnt == 4 && ((slots[4 * i] >> (tag_shift - 1)) & 1ull)) atomicAdd(&out[1], 1ull);
+    if(md) atomicMax(&out[2], (unsigned long long)md);
+}
+
+__global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, const u64 *__restrict__ keys, u64 n,
+                                  u32 *__restrict__ vals_out, uint8_t *__restrict__ found_out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    ClassifySink s;
+    s.T = T;
+    u64 x[PPL] = {keys[i], 0, 0, 0};
+    u32 val[PPL];
+    s.probe(x, 1u, val);
+    found_out[i] = val[0] != VAL_MISS;
+    vals_out[i] = val[0] != VAL_MISS ? dict[val[0]] : 0u;
+}
+
+// resolve_tree over explicit lists; one warp per list. Values must be DB values (they are looked up in `values`).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+bns_resolve_kernel(TaxView X, const u32 *__restrict__ values, u32 n_values, const u32 *__restrict__ taxa,
+                   const uint16_t *__restrict__ counts, const u64 *__restrict__ offsets, u64 n_lists,
+                   u32 *__restrict__ taxon_out, u32 *__restrict__ status) {
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(0, true), 0, true);
+    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    ClassifySink sink;
+    for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_lists; r += nwarps) {
+        sink.begin(nullptr);
+        const u64 b = offsets[r], e = offsets[r + 1];
+        // linear::counter::add semantics: repeated keys accumulate (u16 wrap applied at resolve time)
+        for(u64 i = b; i < e; ++i) {
+            const u32 id = value_id(values, n_values, taxa[i]);
+            if(id == VAL_MISS) { if(lane == 0) atomicOr(status, 4u); continue; }
+            int found = -1;
+            for(u32 base = 0; base < sink.n_distinct; base += 32) {
+                const u32 idx = base + lane;
+                const u32 bm = __ballot_sync(FULL, idx < sink.n_distinct && S.ids[idx] == id);
+                if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
+            }
+            if(found < 0) {
+                if(sink.n_distinct < AGG_CAP) {
+                    if(lane == 0) { S.ids[sink.n_distinct] = id; S.cnt[sink.n_distinct] = counts[i]; }
+                    ++sink.n_distinct;
+                } else if(lane == 0) atomicOr(status, 2u);
+            } else if(lane == 0) S.cnt[found] += counts[i];
+            __syncwarp();
+        }
+        const u32 t = sink.resolve(S, X, lane);
+        if(lane == 0) taxon_out[r] = t;
+        __syncwarp();
+    }
+}
+
+// independent 32-byte loads at uniformly random buckets: the random-access ceiling the lookup is measured against
+__global__ void bns_gather_kernel(const u64 *__restrict__ slots, u32 b, u64 n_loads, u64 seed,
+                                  unsigned long long *__restrict__ sink_out) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (u64)gridDim.x * blockDim.x;
+    u64 acc = 0;
+    for(u64 i = tid * 4; i < n_loads; i += nthreads * 4) {
+        u64 s[4][4];
+#pragma unroll
+        for(int j = 0; j < 4; ++j) {
+            const u64 h = mix64(seed + i + j);
+            ld_bucket(slots + ((h >> (64 - b)) << 2), s[j][0], s[j][1], s[j][2], s[j][3]);
+        }
+#pragma unroll
+        for(int j = 0; j < 4; ++j) acc ^= s[j][0] ^ s[j][1] ^ s[j][2] ^ s[j][3];
+    }
+    if(acc == 0x1234567u) *sink_out = acc;       // keep the loads alive
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (called from bns_api.cu)
+// ---------------------------------------------------------------------------------------------
+size_t stream_smem_bytes(u32 ring_cap, bool classify) { return WARPS_PER_CTA * warp_smem_bytes(ring_cap, classify); }
+
+cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
+                          u64 total_bases, u64 *kmers_out, const u64 *out_offsets, u32 *counts_out, u32 ring_cap, u32 *status) {
+    cudaFuncSetAttribute(bns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bns_encode_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, kmers_out, out_offsets,
+                                                             counts_out, ring_cap, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
+                            u32 mates, u64 total_bases, const TableView &T, const TaxView &X, const u32 *dict,
+                            u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
+                            u32 ring_cap, unsigned long long *counters, u32 *status) {
+    cudaFuncSetAttribute(bns_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bns_classify_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, dict,
+                                                               taxon_out, nhit_out, nmiss_out, taxa_out, taxa_offsets,
+                                                               ring_cap, counters, status);
+    return cudaGetLastError();
+}
+int classify_occupancy(size_t smem) {
+    int nb = 0;
+    cudaFuncSetAttribute(bns_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bns_classify_kernel, WARPS_PER_CTA * 32, smem);
+    return nb;
+}
+int encode_occupancy(size_t smem) {
+    int nb = 0;
+    cudaFuncSetAttribute(bns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bns_encode_kernel, WARPS_PER_CTA * 32, smem);
+    return nb;
+}
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+                          u32 n_values, unsigned long long *stats) {
+    if(!n) return cudaSuccess;
+    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, b, keys, vals, n, values, n_values, stats);
+    return cudaGetLastError();
+}
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, unsigned long long *out) {
+    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
+                          uint8_t *found_out) {
+    if(!n) return cudaSuccess;
+    bns_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, dict, keys, n, vals_out, found_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u32 *values, u32 n_values, const u32 *taxa,
+                           const uint16_t *counts, const u64 *offsets, u64 n_lists, u32 *taxon_out, u32 *status) {
+    const size_t smem = WARPS_PER_CTA * warp_smem_bytes(0, true);
+    bns_resolve_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(X, values, n_values, taxa, counts, offsets, n_lists, taxon_out, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather(int grid, cudaStream_t st, const u64 *slots, u32 b, u64 n_loads, u64 seed, unsigned long long *sink) {
+    bns_gather_kernel<<<grid, 256, 0, st>>>(slots, b, n_loads, seed, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace bns

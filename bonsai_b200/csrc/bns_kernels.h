@@ -1,0 +1,37 @@
+// bns_kernels.h -- launcher interface between the host API (bns_api.cu) and the kernels (bns_kernels.cu)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bns {
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+constexpr int WARPS_PER_CTA = 8;
+
+struct EncParams;
+struct TableView;
+struct TaxView;
+
+size_t stream_smem_bytes(u32 ring_cap, bool classify);
+int classify_occupancy(size_t smem);
+int encode_occupancy(size_t smem);
+
+cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
+                          u64 total_bases, u64 *kmers_out, const u64 *out_offsets, u32 *counts_out, u32 ring_cap, u32 *status);
+cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
+                            u32 mates, u64 total_bases, const TableView &T, const TaxView &X, const u32 *dict,
+                            u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
+                            u32 ring_cap, unsigned long long *counters, u32 *status);
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+                          u32 n_values, unsigned long long *stats);
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, unsigned long long *out);
+cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
+                          uint8_t *found_out);
+cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u32 *values, u32 n_values, const u32 *taxa,
+                           const uint16_t *counts, const u64 *offsets, u64 n_lists, u32 *taxon_out, u32 *status);
+cudaError_t launch_gather(int grid, cudaStream_t st, const u64 *slots, u32 b, u64 n_loads, u64 seed, unsigned long long *sink);
+
+}  // namespace bns

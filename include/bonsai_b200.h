@@ -1,0 +1,165 @@
+/* bonsai_b200.h -- C ABI of libbonsai_b200.so: the B200-native `classify` hot path of dnbaker/bonsai.
+ *
+ * The reference has no FFI layer; its boundary for this path is the C++ template surface in
+ * namespace bns. Each entry point below names the reference interface it replaces
+ * (file:line under the reference tree @ 6741de9c). include/bonsai_b200/bonsai.hpp re-creates those C++
+ * names (Spacer, Encoder<Score>::for_each, ClassifierGeneric, classify_seqs, process_dataset, Database)
+ * on top of this ABI, and INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: every call returns 0 (BNS_OK) or a negative BNS_E_* code and never exits or throws;
+ * bns_b200_last_error() gives the message. All buffers are caller-owned. Host-pointer calls block
+ * until their outputs are written. A context is bound to one CUDA device (one process per GPU);
+ * it is thread-compatible (one call at a time per context). There is NO CPU fallback: without a
+ * usable CUDA device bns_b200_open() fails with BNS_E_CUDA.
+ */
+#ifndef BONSAI_B200_H
+#define BONSAI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNS_B200_ABI_VERSION 1
+#define BNS_MAX_K 32
+
+enum {
+    BNS_OK = 0,
+    BNS_E_INVAL = -1,      /* bad argument / unsupported configuration */
+    BNS_E_CUDA = -2,       /* CUDA runtime error (no device, launch failure, ...) */
+    BNS_E_NOMEM = -3,      /* host or device allocation failed */
+    BNS_E_STATE = -4,      /* call order: table / taxonomy not loaded yet */
+    BNS_E_TAXONOMY = -5,   /* malformed taxonomy (cycle) */
+    BNS_E_CAPACITY = -6,   /* an output buffer the caller sized is too small */
+    BNS_E_IO = -7          /* file could not be read / parsed */
+};
+
+/* score::Lex / score::Entropy -- include/bonsai/encoder.h:76-89 */
+enum { BNS_SCORE_LEX = 0, BNS_SCORE_ENTROPY = 1 };
+/* Which overload family of Encoder is reproduced:
+ *   BNS_API_STRING  Encoder::for_each(fn, const char*, u64)          encoder.h:416-442 (classify_seq uses it;
+ *                   spaced seeds emit nothing there -- reference quirk)
+ *   BNS_API_PATH    Encoder::for_each_canon / for_each_uncanon on one record, encoder.h:448-464 (what the
+ *                   database builder uses; spaced seeds work: for_each_uncanon_spaced, encoder.h:233) */
+enum { BNS_API_STRING = 0, BNS_API_PATH = 1 };
+/* The entropy score casts a negative double to u64 (encoder.h:337, :55-58), which is UB; an x86-64 build of
+ * the reference saturates (AVX-512 vcvttsd2usi) or wraps (cvttsd2si sequence) depending on -march. */
+enum { BNS_CAST_SATURATE = 0, BNS_CAST_WRAP = 1 };
+
+/* Spacer(k, w, gaps) + Encoder(sp, canonicalize) -- include/bonsai/spacer.h:59-71, encoder.h:133-153 */
+typedef struct bns_b200_config {
+    uint32_t k;                 /* k-mer length, 1..32 */
+    uint32_t w;                 /* window; the Spacer uses max(comb, w) */
+    uint16_t gaps[BNS_MAX_K];   /* gaps[0..k-2], 0 = adjacent (spvec_t before the +1 of spacer.h:65) */
+    uint32_t score;             /* BNS_SCORE_* */
+    uint32_t canonicalize;      /* requested; switched off for spaced seeds as encoder.h:148-150 does */
+    uint32_t api;               /* BNS_API_* */
+    uint32_t entropy_cast;      /* BNS_CAST_* */
+    int32_t  device;            /* CUDA ordinal, -1 = current device */
+    uint32_t reserved[7];
+} bns_b200_config;
+
+typedef struct bns_b200_ctx bns_b200_t;
+
+typedef struct bns_b200_table_info {
+    uint64_t n_keys;            /* entries resident */
+    uint64_t n_buckets;         /* 32-byte buckets of 4 slots (power of two) */
+    uint64_t bytes;             /* device bytes of the slot array */
+    uint32_t bucket_bits, val_bits, n_values, max_disp;
+    uint64_t n_displaced;       /* entries not in their home bucket */
+    uint64_t n_overflowed;      /* home buckets with the overflow mark */
+} bns_b200_table_info;
+
+typedef struct bns_b200_stats {
+    uint64_t n_classified, n_unclassified;   /* ClassifierGeneric::n_classified()/n_unclassified(), classifier.h:170-171 */
+    uint64_t kernel_launches;                /* kernels of this library launched since open */
+    uint64_t reads_processed, bases_processed;
+    uint64_t h2d_bytes, d2h_bytes;
+    double   last_kernel_ms;                 /* device time of the last classify/encode kernel (CUDA events) */
+    double   kernel_ms_total;
+} bns_b200_stats;
+
+const char *bns_b200_version(void);
+const char *bns_b200_strerror(int code);
+const char *bns_b200_last_error(const bns_b200_t *ctx);
+
+/* ClassifierGeneric(map, spaces, k, wsz, ...) + Encoder copy per worker -- classifier.h:155-166,258 */
+int  bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out);
+void bns_b200_close(bns_b200_t *ctx);
+/* Spacer geometry after construction: comb c_, window w_, unspaced(), unwindowed(), effective canonicalize */
+int  bns_b200_geometry(const bns_b200_t *ctx, uint32_t *c, uint32_t *w, int *unspaced, int *unwindowed, int *canon);
+/* Upper bound on k-mers Encoder::for_each emits for one sequence of `len` bases */
+uint64_t bns_b200_encode_bound(const bns_b200_t *ctx, uint64_t len);
+
+/* ---- database: khash_t(c) -> device table ------------------------------------------------------
+ * load_table takes the raw khash arrays the reference holds (struct kh_c_t, include/bonsai/khash64.h:213-219;
+ * flags: 2 bits per bucket, bit1 empty / bit0 deleted, :169-177) exactly as Database<khash_t(c)>::db_ exposes
+ * them (include/bonsai/database.h:17-31). Only kh_get's result (hit/miss + value, khash64.h:250-263) is
+ * preserved; the device layout is this library's own. */
+int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, const uint32_t *flags, uint64_t n_buckets);
+/* same, from a dense list of distinct keys */
+int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, uint64_t n);
+/* same, keys/vals already in device memory (values must come from `values[n_values]`) */
+int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const uint32_t *d_vals, uint64_t n,
+                               const uint32_t *values, uint32_t n_values);
+int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info);
+/* kh_get + kh_val over a batch of keys (host pointers): found_out[i] = 1/0, vals_out[i] = value if found */
+int bns_b200_lookup_batch(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint32_t *vals_out, uint8_t *found_out);
+
+/* ---- taxonomy: khash_t(p) child -> parent ---------------------------------------------------------
+ * build_parent_map, include/bonsai/util.h:766-785 (taxid 1 is forced to parent 0) */
+int bns_b200_load_taxonomy(bns_b200_t *ctx, const uint32_t *child, const uint32_t *parent, uint64_t n);
+int bns_b200_load_taxonomy_file(bns_b200_t *ctx, const char *nodes_dmp);
+/* resolve_tree(counter, parent_map), util.h:831-869, over a batch of (taxid,count) lists: list r is
+ * taxa[offsets[r]..offsets[r+1]) with u16 counts as linear::counter<tax_t,u16> keeps them */
+int bns_b200_resolve_batch(bns_b200_t *ctx, const uint32_t *taxa, const uint16_t *counts, const uint64_t *offsets,
+                           uint64_t n_lists, uint32_t *taxon_out);
+
+/* ---- replication: one broadcast at load ------------------------------------------------
+ * Rank 0 loads table + taxonomy, every rank calls db_blob_size, non-root ranks db_blob_alloc, then the host
+ * plumbing broadcasts the device segments (NCCL / torch.distributed) and every rank calls db_blob_commit. */
+typedef struct bns_b200_db_header { uint64_t words[16]; } bns_b200_db_header;
+int bns_b200_db_export_header(const bns_b200_t *ctx, bns_b200_db_header *hdr);
+int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr);
+/* device segments that make up the database: fills up to `cap` (ptr, bytes) pairs, returns the count in *n */
+int bns_b200_db_segments(const bns_b200_t *ctx, void **dev_ptrs, uint64_t *bytes, int cap, int *n);
+int bns_b200_db_commit(bns_b200_t *ctx);
+
+/* ---- Encoder<Score>::for_each(fn, str, len) over a batch -- encoder.h:416 ------------------------------
+ * bases: all sequences concatenated (ASCII); offsets[n+1]. Sequence r's k-mers are written in emission order
+ * to kmers_out[out_offsets[r] ...], at most out_offsets[r+1]-out_offsets[r] of them (BNS_E_CAPACITY if more
+ * were produced); counts_out[r] = number emitted. */
+int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_seqs,
+                          uint64_t *kmers_out, const uint64_t *out_offsets, uint32_t *counts_out);
+
+/* ---- classify_seqs / classify_seq core -- classifier.h:213-238,269-289 ---------------------------------
+ * One record per read (paired = 0) or per interleaved mate pair (paired = 1, classifier.h:233-236,257):
+ *   taxon_out[r]  resolve_tree result (0 = unclassified)
+ *   n_hit_out[r]  taxa.size()       n_missing_out[r]  missing_count     (either may be NULL)
+ *   taxa_out      optional ordered per-k-mer hit taxids (std::vector<tax_t> taxa, classifier.h:228) of record
+ *                 r at taxa_out[taxa_offsets[r] ...]; NULL to skip. */
+int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                            uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
+                            uint32_t *taxa_out, const uint64_t *taxa_offsets);
+/* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). */
+int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
+                             uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,
+                             uint32_t *d_taxa, const uint64_t *d_taxa_offsets, void *stream);
+
+int bns_b200_sync(bns_b200_t *ctx);
+int bns_b200_stats_get(const bns_b200_t *ctx, bns_b200_stats *out);
+int bns_b200_stats_reset(bns_b200_t *ctx);
+
+/* pinned host buffers for ingest rings (kseq -> bseq1_t batches, include/bonsai/kseq_declare.h:112-145) */
+int bns_b200_host_alloc(void **ptr, size_t bytes);
+int bns_b200_host_free(void *ptr);
+
+/* measurement helper: independent 32-byte loads at uniformly random buckets of the resident table;
+ * returns device milliseconds for n_loads loads (the "random-gather ceiling" of SURVEY 8d) */
+int bns_b200_bench_gather(bns_b200_t *ctx, uint64_t n_loads, uint64_t seed, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BONSAI_B200_H */

@@ -1,0 +1,332 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (bonsai_b200/capi.py -> libbonsai_b200.so), against
+the CPU oracle on the same seeded inputs and against the golden vectors the unmodified reference produced.
+Bit-exact everywhere: k-mer streams, hit/miss + value of every lookup, per-record taxon / hit / missing counts
+and the ordered hit lists."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from bonsai_b200 import capi as m
+    m.load_library()          # fails loudly if the extension was not built
+    return m
+
+
+def hx(a):
+    return [format(int(x), "x") for x in a]
+
+
+def gpu_encode_one(capi, seq, k, w, gaps, score, canon, api, cast):
+    with capi.Context(k, w, gaps, score, canon, api, cast) as ctx:
+        b, o = po.pack_reads([seq])
+        return ctx.encode_lists(b, o)[0]
+
+
+def supported(k, w, gaps, score, canon, api):
+    """k = 32 with the rolling windowed family is fenced off (BNS_E_INVAL)."""
+    if k != 32:
+        return True
+    c = k + (sum(gaps) if gaps else 0)
+    unspaced = not gaps or not any(gaps)
+    windowed = max(c, w) != k
+    canon_eff = canon and unspaced
+    rolling = unspaced and windowed and (not canon_eff or (score == 1 and api == 0))
+    return not rolling
+
+
+def test_encode_small_golden(capi, golden):
+    ctxs = {}
+    n = 0
+    for e in golden["encode_small"]:
+        if not supported(e["k"], e["w"], e["gaps"], e["score"], e["canon"], e["api"]):
+            with pytest.raises(capi.BnsError):
+                capi.Context(e["k"], e["w"], e["gaps"], e["score"], e["canon"], e["api"])
+            continue
+        for cast, key in ((capi.CAST_SATURATE, "saturate"), (capi.CAST_WRAP, "wrap")):
+            exp = e[key] if e[key] is not None else e["saturate"]
+            ck = (e["k"], e["w"], tuple(e["gaps"] or ()), e["score"], e["canon"], e["api"], cast)
+            if ck not in ctxs:
+                ctxs[ck] = capi.Context(e["k"], e["w"], e["gaps"], e["score"], e["canon"], e["api"], cast)
+            b, o = po.pack_reads([e["seq"]])
+            got = hx(ctxs[ck].encode_lists(b, o)[0])
+            assert got == exp, (e, key)
+            n += 1
+    assert n > 1000
+    for c in ctxs.values():
+        c.close()
+
+
+@pytest.mark.parametrize("tag", ["saturate", "wrap"])
+def test_encode_streams_golden(capi, golden, genomes, reads2000, tag):
+    bases, offs, _ = reads2000
+    cast = capi.CAST_SATURATE if tag == "saturate" else capi.CAST_WRAP
+    pb, poff = po.pack_reads([bytes(genomes["phix"])])
+    for name, s in golden["streams"].items():
+        if not name.endswith(":" + tag):
+            continue
+        with capi.Context(s["k"], s["w"], s["gaps"], s["score"], s["canon"], s["api"], cast) as ctx:
+            kmers, oo, cnt = ctx.encode(bases, offs)
+            allk = np.concatenate([kmers[int(oo[i]):int(oo[i]) + int(cnt[i])] for i in range(cnt.size)])
+            assert list(H.digest(allk)) == s["reads"], name
+            px = ctx.encode_lists(pb, poff)[0]
+            assert list(H.digest(px)) == s["phix"], name
+            assert int(np.unique(px).size) == s["phix_distinct"], name
+
+
+def test_encode_fuzz_vs_oracle(capi, oracle):
+    rng = random.Random(99)
+    for it in range(60):
+        k = rng.choice([1, 2, 3, 5, 7, 13, 16, 21, 31, 31, 31, 32])
+        gaps = None
+        if rng.random() < 0.35 and k > 1:
+            gaps = [rng.choice([0, 0, 0, 1, 2, 3]) for _ in range(k - 1)]
+        c = k + (sum(gaps) if gaps else 0)
+        w = rng.choice([0, k, c, c + 1, c + 3, c + 19, c + 50, c + 200])
+        seqs = []
+        for _ in range(40):
+            L = rng.choice([0, 1, k - 1, k, c, c + 1, c + 5, 60, 150, 300, 700, 1500])
+            alphabet = rng.choice(["ACGT", "ACGT", "ACGTN", "ACGTacgtNnUu-", "AT", "A", "T", "AC"])
+            s = "".join(rng.choice(alphabet) for _ in range(L))
+            if rng.random() < 0.2 and L > 40:
+                p = rng.randrange(L - 35)
+                s = s[:p] + rng.choice("ACGT") * 35 + s[p + 35:]
+            seqs.append(s)
+        b, o = po.pack_reads(seqs)
+        for score in (0, 1):
+            for canon in (0, 1):
+                for api in (0, 1):
+                    if not supported(k, w, gaps, score, canon, api):
+                        continue
+                    cast = rng.choice([capi.CAST_SATURATE, capi.CAST_WRAP])
+                    with capi.Context(k, w, gaps, score, canon, api, cast) as ctx:
+                        got = ctx.encode_lists(b, o)
+                    for s, g in zip(seqs, got):
+                        exp = oracle.encode(s, k, w, gaps, score, canon, api, cast_mode=cast)
+                        assert np.array_equal(g, exp), dict(k=k, w=w, gaps=gaps, score=score, canon=canon, api=api, cast=cast, seq=s)
+
+
+def test_lookup_matches_kh_get(capi, oracle, dbcache):
+    db = dbcache.get("ent_k31_w50")
+    keys, vals, flags, nb, size = oracle.db_arrays(db)
+    with capi.Context(31) as ctx:
+        ctx.load_table(keys, vals, flags, nb)          # the raw khash arrays, as Database::db_ holds them
+        info = ctx.table_info()
+        assert info["n_keys"] == size
+        k, v = oracle.db_pairs(db)
+        gv, gf = ctx.lookup(k)
+        assert gf.all() and np.array_equal(gv, v)
+        rng = np.random.default_rng(3)
+        q = rng.integers(0, 2**62, 200000, dtype=np.uint64)
+        q[::7] = k[rng.integers(0, k.size, q[::7].size)]
+        gv, gf = ctx.lookup(q)
+        pos = np.searchsorted(k, q)
+        pos[pos == k.size] = 0
+        hit = k[pos] == q
+        assert np.array_equal(gf, hit)
+        assert np.array_equal(gv[hit], v[pos][hit])
+        # load_pairs builds the same table
+        with capi.Context(31) as ctx2:
+            ctx2.load_pairs(k, v)
+            gv2, gf2 = ctx2.lookup(q)
+            assert np.array_equal(gf2, hit) and np.array_equal(gv2[hit], v[pos][hit])
+
+
+def test_lookup_small_and_adversarial(capi):
+    """tiny tables, many distinct values, keys that collide in the low / high bits"""
+    rng = np.random.default_rng(17)
+    for n, nvals in ((0, 1), (1, 1), (5, 5), (1000, 1000), (70000, 50000), (300000, 7)):
+        keys = np.unique(rng.integers(0, 2**64 - 1, n, dtype=np.uint64))
+        if n >= 1000:
+            keys[: n // 4] = np.arange(n // 4, dtype=np.uint64) << np.uint64(40)     # only high bits differ
+            keys[n // 4: n // 2] = np.arange(n // 4, n // 2, dtype=np.uint64)          # dense small integers
+            keys = np.unique(keys)
+        vals = rng.integers(1, 2**32 - 1, max(nvals, 1), dtype=np.uint64).astype(np.uint32)[rng.integers(0, max(nvals, 1), keys.size)]
+        with capi.Context(31) as ctx:
+            ctx.load_pairs(keys, vals)
+            assert ctx.table_info()["n_keys"] == keys.size
+            gv, gf = ctx.lookup(keys)
+            assert gf.all() and np.array_equal(gv, vals)
+            miss = keys ^ np.uint64(1 << 63) if keys.size else np.array([5], np.uint64)
+            miss = miss[~np.isin(miss, keys)]
+            _, gf = ctx.lookup(miss)
+            assert not gf.any()
+
+
+def test_resolve_golden(capi, golden):
+    c, p = H.toy_tax_arrays()
+    with capi.Context(31) as ctx:
+        vals = np.array([1, 2, 10, 11, 12, 13, 20], np.uint32)
+        ctx.load_pairs(np.arange(vals.size, dtype=np.uint64), vals)
+        ctx.load_taxonomy(c, p)
+        cases = [x for x, _ in golden["resolve"]]
+        got = ctx.resolve(cases)
+        assert got.tolist() == [e for _, e in golden["resolve"]]
+
+
+def test_resolve_fuzz_vs_oracle(capi, oracle):
+    rng = np.random.default_rng(5)
+    ids = np.unique(rng.integers(2, 500000, 3000))[:2500]
+    nodes = np.concatenate([[1], ids]).astype(np.uint32)
+    parent = np.zeros(nodes.size, np.uint32)
+    parent[0] = 1
+    for i in range(1, nodes.size):
+        parent[i] = nodes[rng.integers(max(0, i - 40), i)]       # deep-ish tree
+    T = oracle.tax_from_pairs(nodes, parent)
+    with capi.Context(31) as ctx:
+        ctx.load_pairs(np.arange(nodes.size, dtype=np.uint64), nodes)
+        ctx.load_taxonomy(nodes, parent)
+        cases = []
+        for _ in range(3000):
+            n = int(rng.integers(1, 40))
+            taxa = rng.choice(nodes, n, replace=False)
+            cnt = rng.integers(1, 4, n)
+            cases.append(list(zip(taxa.tolist(), cnt.tolist())))
+        got = ctx.resolve(cases)
+        exp = [oracle.resolve(T, [a for a, _ in cs], [b for _, b in cs]) for cs in cases]
+        assert got.tolist() == exp
+
+
+@pytest.fixture(scope="module")
+def gpu_dbs(capi, oracle, dbcache, golden):
+    """one context per golden classify case, loaded from the oracle-built khash arrays"""
+    c, p = H.toy_tax_arrays()
+    out = {}
+
+    def make(cname):
+        if cname not in out:
+            spec = golden["classify"][cname]
+            keys, vals, flags, nb, _ = oracle.db_arrays(dbcache.get(spec["db"]))
+            ctx = capi.Context(spec["k"], spec["w"], spec["gaps"], capi.SCORE_LEX, spec["canon"], spec["api"])
+            ctx.load_table(keys, vals, flags, nb)
+            ctx.load_taxonomy(c, p)
+            out[cname] = ctx
+        return out[cname]
+    yield make
+    for ctx in out.values():
+        ctx.close()
+
+
+@pytest.mark.parametrize("cname", ["config1_lex_w31", "config2_entdb", "config4_spaced", "windowed_lex_w50_on_reads",
+                                   "windowed_lex_w50_nocanon"])
+def test_classify_golden(capi, golden, gpu_dbs, reads2000, cname):
+    bases, offs, _ = reads2000
+    spec = golden["classify"][cname]
+    ctx = gpu_dbs(cname)
+    taxon, nhit, nmiss, lists = ctx.classify(bases, offs, want_taxa=True)
+    assert taxon.tolist() == spec["taxon"]
+    assert nhit.tolist() == spec["nhit"]
+    assert nmiss.tolist() == spec["nmiss"]
+    assert hashlib.md5(np.concatenate(lists).tobytes()).hexdigest() == spec["taxa_md5"]
+    # the lean call (taxon only) agrees
+    t2, _, _ = ctx.classify(bases, offs, want_counts=False)
+    assert np.array_equal(t2, taxon)
+    st = ctx.stats()
+    assert st["kernel_launches"] > 0
+
+
+def test_classify_phix_and_paired(capi, golden, gpu_dbs, reads2000, genomes):
+    ctx = gpu_dbs("config1_lex_w31")
+    pb, poff = po.pack_reads([bytes(genomes["phix"])])
+    taxon, nhit, nmiss = ctx.classify(pb, poff)
+    g = golden["classify"]["phix"]
+    assert (int(taxon[0]), int(nhit[0]), int(nmiss[0])) == (g["taxon"], g["nhit"], g["nmiss"]) == (0, 0, 5356)
+    bases, offs, _ = reads2000
+    g = golden["classify"]["paired_lex_w31"]
+    taxon, nhit, nmiss = ctx.classify(bases, offs, paired=True)
+    assert taxon.tolist() == g["taxon"] and nhit.tolist() == g["nhit"] and nmiss.tolist() == g["nmiss"]
+
+
+def test_classify_ragged_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, genomes):
+    """empty reads, reads shorter than k, long reads (multi-tile), contig-sized records"""
+    bases, offs, _ = H.make_reads(3000, seed=7, ragged=True)
+    ctx = gpu_dbs("config1_lex_w31")
+    db = dbcache.get("lex_k31_w31")
+    exp = oracle.classify(db, toy_tax, bases, offs, 31, 31, want_taxa=True)
+    got = ctx.classify(bases, offs, want_taxa=True)
+    for a, b in zip(exp[:3], got[:3]):
+        assert np.array_equal(a, b)
+    assert all(np.array_equal(a, b) for a, b in zip(exp[3], got[3]))
+    # a few long records: 20 kb slices of the genomes (hundreds of tiles per warp)
+    g = genomes
+    rng = np.random.default_rng(1)
+    recs = []
+    for _ in range(12):
+        s = int(rng.integers(0, g["bases"].size - 20000))
+        recs.append(bytes(g["bases"][s:s + int(rng.integers(2000, 20000))]))
+    b, o = po.pack_reads(recs)
+    exp = oracle.classify(db, toy_tax, b, o, 31, 31)
+    got = ctx.classify(b, o)
+    for a, bb in zip(exp, got):
+        assert np.array_equal(a, bb)
+    # empty batch
+    t, h, m = ctx.classify(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert t.size == 0
+
+
+def test_classify_device_and_replication(capi, golden, gpu_dbs, reads2000):
+    """device-resident call + the broadcast path (header, segments, commit) into a second context"""
+    import torch
+    bases, offs, _ = reads2000
+    spec = golden["classify"]["config1_lex_w31"]
+    src = gpu_dbs("config1_lex_w31")
+    hdr = src.db_export_header()
+    with capi.Context(31, 31) as dst:
+        dst.db_alloc_from_header(hdr)
+        for (sp, sb), (dp, db) in zip(src.db_segments(), dst.db_segments()):
+            assert sb == db
+            if sb:           # plain device-to-device copies stand in for the NCCL broadcast
+                torch.as_tensor(capi.DevMem(dp, db), device="cuda").copy_(torch.as_tensor(capi.DevMem(sp, sb), device="cuda"))
+        torch.cuda.synchronize()
+        dst.db_commit()
+        d_b = torch.from_numpy(bases).cuda()
+        d_o = torch.from_numpy(offs.astype(np.int64)).cuda()
+        n = offs.size - 1
+        d_t = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_h = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_m = torch.zeros(n, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        dst.classify_device(d_b.data_ptr(), d_o.data_ptr(), n, d_t.data_ptr(), d_h.data_ptr(), d_m.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        assert d_t.cpu().numpy().astype(np.uint32).tolist() == spec["taxon"]
+        assert d_h.cpu().numpy().tolist() == spec["nhit"]
+        assert d_m.cpu().numpy().tolist() == spec["nmiss"]
+        s = dst.stats()
+        assert s["n_classified"] + s["n_unclassified"] == n
+        assert s["n_unclassified"] == spec["taxon"].count(0)
+
+
+def test_full_size_properties(capi, gpu_dbs, golden, oracle, dbcache, toy_tax):
+    """BASELINE-scale batch (1M reads): size-independent properties -- determinism, batch-split invariance,
+    reverse-complement invariance of canonical classification, and hit + missing == valid windows."""
+    ctx = gpu_dbs("config1_lex_w31")
+    bases, offs, _ = H.make_reads(1_000_000, seed=123, frac_n=0.0)
+    t1, h1, m1 = ctx.classify(bases, offs)
+    t2, h2, m2 = ctx.classify(bases, offs)
+    assert np.array_equal(t1, t2) and np.array_equal(h1, h2)
+    assert ((h1 + m1) == 120).all()                      # no N: every window is looked up exactly once
+    half = 400_003
+    ta, _, _ = ctx.classify(bases[: int(offs[half])], offs[: half + 1])
+    tb, _, _ = ctx.classify(bases[int(offs[half]):], offs[half:] - offs[half])
+    assert np.array_equal(np.concatenate([ta, tb]), t1)
+    # reverse-complementing every read leaves canonical k-mer sets, hence taxa, unchanged
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = comp[bases.reshape(-1, 150)[:, ::-1]].reshape(-1)
+    t3, h3, m3 = ctx.classify(np.ascontiguousarray(rc), offs)
+    assert np.array_equal(t3, t1) and np.array_equal(h3, h1)
+    # and the first 20k reads agree with the CPU oracle record by record
+    n = 20000
+    et, eh, em = oracle.classify(dbcache.get("lex_k31_w31"), toy_tax, bases[: int(offs[n])], offs[: n + 1], 31, 31, nthreads=0)
+    assert np.array_equal(et, t1[:n]) and np.array_equal(eh, h1[:n]) and np.array_equal(em, m1[:n])
