@@ -165,9 +165,10 @@ int derive_encoder(bns_b200_ctx *ctx) {
             else { P.family = FAM_R; P.tail_flush = 1; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX; }
         } else { P.family = FAM_K; P.filter_none = 1; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX; }
     }
-    if(P.family == FAM_R && k == 32)
-        return ctx->fail(BNS_E_INVAL, "k = 32 with a windowed non-canonical rolling encoder is not supported "
-                                      "(the reference restarts on 32 consecutive T there, encoder.h:283)");
+    if(P.family == FAM_R) {
+        P.filter_none = 1;                                            // `!= ENCODE_OVERFLOW`, encoder.h:299,337
+        P.t_restart = (P.score_kind != SC_ENT_ROLL && k >= 31);       // encoder.h:283 (see stage_tile)
+    }
     ctx->ring_cap = (ctx->W > 1 && P.family != FAM_U && P.family != FAM_NONE) ? (ctx->W - 1 + TILE) : 0;
     const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
     if(smem > 200 * 1024) return ctx->fail(BNS_E_INVAL, "window %u needs %zu bytes of shared memory per CTA", w, smem);

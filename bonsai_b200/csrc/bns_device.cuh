@@ -44,6 +44,7 @@ struct EncParams {
     u32 canon_emit;              // canonicalise only on emit (entropy canon wrapper, encoder.h:347-353)
     u32 filter_none;             // drop window results equal to ~0 (FAM_K)
     u32 tail_flush;              // FAM_R
+    u32 t_restart;               // FAM_R + Lex, k >= 31: 32 consecutive T restart the rolling state (encoder.h:283)
     u32 n_seg;                   // contiguous runs of the comb
     uint16_t seg_off[MAX_SEG];   // base offset of each run from the k-mer start
     uint16_t seg_len[MAX_SEG];   // bases in the run
@@ -127,7 +128,7 @@ __device__ __forceinline__ u64 cast_u64(double x, u32 wrap) {
 // 16 ASCII bases -> one u32 of 2-bit codes (first base in the top bits) + 16 "invalid" bits (first
 // base in bit 15). Codes: A/a 0, C/c 1, G/g 2, T/t 3; everything else invalid (alphabet.h:128).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4) {
+__device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4, u32 &t4) {
     u32 t = (w >> 1) & 0x03030303u;
     t ^= (t >> 1) & 0x01010101u;                       // per byte: A0 C1 G2 T3
     code8 = (t * 0x40100401u) >> 24;                   // b0<<6 | b1<<4 | b2<<2 | b3
@@ -136,12 +137,14 @@ __device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4) {
     const u32 diff = expect ^ (w & 0xdfdfdfdfu);
     const u32 nz = (((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu) | diff) & 0x80808080u;
     bad4 = (((nz >> 7) * 0x08040201u) >> 24) & 0xfu;   // byte0 -> bit 3
+    t4 = ((((hi & lo) * 0x08040201u) >> 24) & 0xfu) & ~bad4;   // valid T
 }
-__device__ __forceinline__ void pack16(uint4 v, u32 &codes, u32 &bad) {
-    u32 c0, c1, c2, c3, b0, b1, b2, b3;
-    pack4(v.x, c0, b0); pack4(v.y, c1, b1); pack4(v.z, c2, b2); pack4(v.w, c3, b3);
+__device__ __forceinline__ void pack16(uint4 v, u32 &codes, u32 &bad, u32 &tmask) {
+    u32 c0, c1, c2, c3, b0, b1, b2, b3, t0, t1, t2, t3;
+    pack4(v.x, c0, b0, t0); pack4(v.y, c1, b1, t1); pack4(v.z, c2, b2, t2); pack4(v.w, c3, b3, t3);
     codes = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
     bad = (b0 << 12) | (b1 << 8) | (b2 << 4) | b3;
+    tmask = (t0 << 12) | (t1 << 8) | (t2 << 4) | t3;
 }
 
 // n (1..32) bases starting at base coordinate q of a big-endian 2-bit word array in shared memory

@@ -75,8 +75,8 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, u32 lane, u32 &total) {
 // tile's first base sits at coordinate `shift` because loads are 16-byte aligned) and whether any staged
 // base is invalid.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 stage_tile(const WarpSmem &S, const char *seq, u64 p0, u64 L, u32 span,
-                                          const char *buf_end, u32 lane, bool &any_invalid) {
+__device__ __forceinline__ u32 stage_tile(const EncParams &cP, const WarpSmem &S, const char *seq, u64 p0, u64 L, u32 span,
+                                          const char *buf_end, u32 lane, bool &any_invalid, u32 &t_carry) {
     const char *a0 = seq + p0;
     const u32 shift = (u32)((uintptr_t)a0 & 15u);
     const char *aligned = a0 - shift;
@@ -84,12 +84,12 @@ __device__ __forceinline__ u32 stage_tile(const WarpSmem &S, const char *seq, u6
     const u32 nbases = (u32)(remaining < span ? remaining : span);      // bases of this sequence in the tile
     const u32 hi = shift + nbases;                                      // valid coordinates: [shift, hi)
     const u32 nblk = (hi + 15) >> 4;
-    u32 codes = 0, bad = 0xffffu;
+    u32 codes = 0, bad = 0, tmask = 0;
     if(lane < nblk) {
         const char *p = aligned + 16 * lane;
         uint4 v = make_uint4(0, 0, 0, 0);
         if(p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p));
-        pack16(v, codes, bad);
+        pack16(v, codes, bad, tmask);
         // bases outside [shift, hi) belong to neighbours (or to nobody): never read by a k-mer, but they
         // must not trigger the slow path
         const int before = (int)shift - (int)(16 * lane);
@@ -98,8 +98,38 @@ __device__ __forceinline__ u32 stage_tile(const WarpSmem &S, const char *seq, u6
         if(before > 0) keep &= (before >= 16) ? 0u : (0xffffu >> before);
         if(after < 16) keep &= (after <= 0) ? 0u : ~(0xffffu >> after);
         bad &= keep;
-    } else {
-        bad = 0;
+        tmask &= keep;
+    }
+    if(cP.t_restart) {
+        // for_each_uncanon_unspaced_windowed tests the OR-ed 64-bit word against ~0 BEFORE masking (encoder.h:283):
+        // with k >= 31 that word holds 32 bases, so the 32nd, 64th, ... consecutive T of a run restarts the rolling
+        // state exactly like an invalid base. Mark those bases invalid. e = T-run length entering each word.
+        u32 e = t_carry, e_at_cx = 0;
+        const u32 cx = shift + TILE - 1;                     // the next tile starts right after this coordinate
+        for(u32 wd = 0; wd < nblk; ++wd) {
+            const u32 tm = __shfl_sync(FULL, tmask, wd);
+            const u32 first = wd == 0 ? shift : 0u;
+            if(wd == (cx >> 4)) e_at_cx = e;
+            const u32 m = tm << (16 + first);                // first in-range base of the word at bit 31
+            u32 lead = __clz(~m);
+            lead = lead < 16 - first ? lead : 16 - first;
+            if(lead) {
+                const u32 i = 31u - (e & 31u);
+                if(i < lead && lane == wd) bad |= 0x8000u >> (first + i);
+            }
+            if(lead == 16 - first) e += lead;
+            else e = __ffs(~tm) - 1;                          // trailing T of the word start a new run
+        }
+        // run length ending at coordinate cx (carried into the next tile)
+        if((cx >> 4) < nblk) {
+            const u32 wd = cx >> 4, first = wd == 0 ? shift : 0u;
+            const u32 tm = __shfl_sync(FULL, tmask, wd);
+            const u32 upto = (tm >> (15 - (cx & 15u)));       // bit 0 = coordinate cx, bit j = cx - j
+            const u32 nbits = (cx & 15u) + 1 - first;         // in-range bases of the word up to cx
+            u32 run = __ffs(~upto) - 1;                       // consecutive T ending at cx
+            if(run >= nbits) run = nbits + e_at_cx;
+            t_carry = run;
+        } else t_carry = 0;
     }
     if(lane < NWORDS) { S.codes[lane] = codes; S.bad[lane] = bad; }
     any_invalid = __any_sync(FULL, bad != 0);
@@ -108,9 +138,9 @@ __device__ __forceinline__ u32 stage_tile(const WarpSmem &S, const char *seq, u6
 }
 
 // the comb's k bases starting at coordinate q; invalid -> KMER_NONE (Encoder::kmer, encoder.h:547-592)
-__device__ __forceinline__ u64 gather_kmer(const EncParams &cP, const WarpSmem &S, u32 q, bool check_bad) {
+__device__ __forceinline__ u64 gather_kmer(const EncParams &cP, const WarpSmem &S, u32 q, bool check_bad, bool &inval) {
     u64 x = 0;
-    bool inval = false;
+    inval = false;
     const u32 ns = cP.n_seg;
     for(u32 s = 0; s < ns; ++s) {
         const u32 off = cP.seg_off[s], len = cP.seg_len[s];
@@ -118,7 +148,7 @@ __device__ __forceinline__ u64 gather_kmer(const EncParams &cP, const WarpSmem &
         x = (len == 32) ? bits : ((x << (2 * len)) | bits);
         if(check_bad) inval |= any_bad(S.bad, q + off, len) != 0;
     }
-    return inval ? KMER_NONE : x;
+    return x;
 }
 
 // score of one window element (scorer_(kmer, data), encoder.h:616-628 ; :337 for the rolling entropy)
@@ -370,46 +400,45 @@ __device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpS
     const u32 span = TILE + c - 1;
     u32 hist = 0;                                               // ring entries carried from earlier tiles
     u64 total = 0;                                              // elements pushed so far (QueueMap list_)
+    u32 t_carry = 0;                                            // T-run length entering the tile (t_restart only)
     for(u64 p0 = 0; p0 < npos; p0 += TILE) {
         bool any_invalid;
-        const u32 shift = stage_tile(S, seq, p0, L, span, buf_end, lane, any_invalid);
+        const u32 shift = stage_tile(cP, S, seq, p0, L, span, buf_end, lane, any_invalid, t_carry);
         u64 x[PPL];
         u32 live = 0;                                           // positions of this lane inside the sequence
+        u32 okm = 0;                                            // ... whose comb covers only valid bases
 #pragma unroll
         for(int i = 0; i < PPL; ++i) {
             const u64 p = p0 + PPL * lane + i;
             x[i] = KMER_NONE;
             if(p < npos) {
+                bool inval;
                 live |= 1u << i;
-                x[i] = gather_kmer(cP, S, shift + PPL * lane + i, any_invalid);
+                x[i] = gather_kmer(cP, S, shift + PPL * lane + i, any_invalid, inval);
+                if(!inval) okm |= 1u << i;
             }
         }
         if(fam == FAM_U) {
-            u32 mask = 0;
+            // an invalid window is skipped; a valid T*32 (== ~0 for k = 32) is emitted (encoder.h:251-253)
+            if(cP.canon_elem) {
 #pragma unroll
-            for(int i = 0; i < PPL; ++i) {
-                // an invalid window is skipped; a valid T*32 (== ~0 for k = 32) is emitted (encoder.h:251-253)
-                const bool ok = (live >> i & 1u) && !(x[i] == KMER_NONE && any_invalid &&
-                                any_bad(S.bad, shift + PPL * lane + i, k));
-                if(ok) { mask |= 1u << i; if(cP.canon_elem) x[i] = canonical(x[i], k); }
+                for(int i = 0; i < PPL; ++i) if(okm >> i & 1u) x[i] = canonical(x[i], k);
             }
             __syncwarp();
-            sink.consume(S, x, mask, lane);
+            sink.consume(S, x, okm, lane);
             continue;
         }
         // element set of this tile
         u32 emask;
         if(fam == FAM_K) {
             emask = live;                                       // every position pushes (invalid -> ~0, or 0 if canon)
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) if(!(okm >> i & 1u)) x[i] = KMER_NONE;
             if(cP.canon_elem) {
 #pragma unroll
                 for(int i = 0; i < PPL; ++i) if(live >> i & 1u) x[i] = canonical(x[i], k);
             }
-        } else {                                                // FAM_R: only valid k-mers push
-            emask = 0;
-#pragma unroll
-            for(int i = 0; i < PPL; ++i) if((live >> i & 1u) && x[i] != KMER_NONE) emask |= 1u << i;
-        }
+        } else emask = okm;                                     // FAM_R: only valid k-mers push
         if(W == 1) {                                            // window of one: the element itself
             u32 mask = emask;
             if(cP.filter_none) {
