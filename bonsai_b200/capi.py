@@ -20,7 +20,7 @@ MAX_K = 32
 SYMBOLS = [
     "bns_b200_version", "bns_b200_strerror", "bns_b200_last_error", "bns_b200_open", "bns_b200_close",
     "bns_b200_geometry", "bns_b200_encode_bound", "bns_b200_load_table", "bns_b200_load_pairs",
-    "bns_b200_load_pairs_device", "bns_b200_table_info_get", "bns_b200_lookup_batch", "bns_b200_load_taxonomy",
+    "bns_b200_load_pairs_device", "bns_b200_table_info_get", "bns_b200_lookup_batch", "bns_b200_lookup_sectors", "bns_b200_load_taxonomy",
     "bns_b200_load_taxonomy_file", "bns_b200_resolve_batch", "bns_b200_db_export_header",
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
     "bns_b200_classify_batch", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
@@ -91,6 +91,7 @@ def load_library(path=None):
     lib.bns_b200_load_pairs_device.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_uint32]
     lib.bns_b200_table_info_get.argtypes = [vp, C.POINTER(TableInfo)]
     lib.bns_b200_lookup_batch.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    lib.bns_b200_lookup_sectors.argtypes = [vp, vp, C.c_uint64, u64p]
     lib.bns_b200_load_taxonomy.argtypes = [vp, vp, vp, C.c_uint64]
     lib.bns_b200_load_taxonomy_file.argtypes = [vp, C.c_char_p]
     lib.bns_b200_resolve_batch.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
@@ -191,6 +192,13 @@ class Context:
         self._ck(self.lib.bns_b200_lookup_batch(self.h, _p(keys), keys.size, _p(vals), _p(found)))
         return vals, found.astype(bool)
 
+    def lookup_sectors(self, keys):
+        """total 32-byte buckets touched by probing `keys` (p-bar = result / len(keys))"""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        out = C.c_uint64()
+        self._ck(self.lib.bns_b200_lookup_sectors(self.h, _p(keys), keys.size, C.byref(out)))
+        return out.value
+
     # ---- taxonomy ----
     def load_taxonomy(self, child, parent):
         child = np.ascontiguousarray(child, np.uint32)
@@ -275,6 +283,11 @@ class Context:
             lists = [taxa[int(toffs[i]):int(toffs[i]) + int(nhit[i])].copy() for i in range(nrec)]
             return taxon, nhit, nmiss, lists
         return taxon, nhit, nmiss
+
+    def classify_into(self, bases_ptr, offsets_ptr, n_reads, taxon_ptr, nhit_ptr=None, nmiss_ptr=None, paired=False):
+        """bns_b200_classify_batch on raw HOST pointers (e.g. pinned buffers): blocks until outputs are written."""
+        self._ck(self.lib.bns_b200_classify_batch(self.h, bases_ptr, offsets_ptr, n_reads, int(paired), taxon_ptr,
+                                                  nhit_ptr, nmiss_ptr, None, None))
 
     def classify_device(self, d_bases, d_offsets, n_reads, d_taxon, d_nhit=0, d_nmiss=0, paired=False, stream=0,
                         d_taxa=0, d_taxa_offsets=0):

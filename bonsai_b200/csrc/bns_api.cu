@@ -615,6 +615,28 @@ int bns_b200_lookup_batch(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uin
     return BNS_OK;
 }
 
+int bns_b200_lookup_sectors(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint64_t *sectors_out) {
+    if(!ctx || !sectors_out || (n && !keys)) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    CK(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), s.st));
+    const u64 CH = 1ull << 24;
+    for(u64 off = 0; off < n; off += CH) {
+        const u64 m = std::min(CH, n - off);
+        int rc = ensure(s.d_kmers, s.cap_kmers, m);
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        CK(cudaMemcpyAsync(s.d_kmers, keys + off, m * sizeof(u64), cudaMemcpyHostToDevice, s.st));
+        CK(launch_sectors(s.st, table_view(ctx), s.d_kmers, m, ctx->d_counters + 4));
+        ++ctx->stats.kernel_launches;
+        CK(cudaStreamSynchronize(s.st));
+    }
+    unsigned long long h = 0;
+    CK(cudaMemcpy(&h, ctx->d_counters + 4, sizeof h, cudaMemcpyDeviceToHost));
+    *sectors_out = h;
+    return BNS_OK;
+}
+
 // ---- taxonomy ------------------------------------------------------------------------------------
 int bns_b200_load_taxonomy(bns_b200_t *ctx, const uint32_t *child, const uint32_t *parent, uint64_t n) {
     if(!ctx || (n && (!child || !parent))) return ctx ? ctx->fail(BNS_E_INVAL, "null taxonomy arrays") : BNS_E_INVAL;

@@ -618,6 +618,26 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
     vals_out[i] = val[0] != VAL_MISS ? dict[val[0]] : 0u;
 }
 
+__global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u64 n, unsigned long long *__restrict__ total) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 touched = 0;
+    if(i < n) {
+        const u32 b = T.bucket_bits;
+        const u64 h = mix64(keys[i]), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
+        ClassifySink s;
+        s.T = T;
+        for(u32 d = 0; d <= 6; ++d) {
+            u64 a, bb, c, e;
+            ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
+            ++touched;
+            if(s.match4(tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
+            if(d == 0 ? !(e != ~0ull && ((a >> (T.tag_shift - 1)) & 1ull)) : (e == ~0ull)) break;
+        }
+    }
+    touched = __reduce_add_sync(FULL, touched);
+    if((threadIdx.x & 31) == 0 && touched) atomicAdd(total, (unsigned long long)touched);
+}
+
 // resolve_tree over explicit lists; one warp per list. Values must be DB values (they are looked up in `values`).
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 bns_resolve_kernel(TaxView X, const u32 *__restrict__ values, u32 n_values, const u32 *__restrict__ taxa,
@@ -720,6 +740,11 @@ cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, 
                           uint8_t *found_out) {
     if(!n) return cudaSuccess;
     bns_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, dict, keys, n, vals_out, found_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_sectors(cudaStream_t st, const TableView &T, const u64 *keys, u64 n, unsigned long long *total) {
+    if(!n) return cudaSuccess;
+    bns_sectors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, keys, n, total);
     return cudaGetLastError();
 }
 cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u32 *values, u32 n_values, const u32 *taxa,

@@ -30,6 +30,7 @@ cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, c
 cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, unsigned long long *out);
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
                           uint8_t *found_out);
+cudaError_t launch_sectors(cudaStream_t st, const TableView &T, const u64 *keys, u64 n, unsigned long long *total);
 cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u32 *values, u32 n_values, const u32 *taxa,
                            const uint16_t *counts, const u64 *offsets, u64 n_lists, u32 *taxon_out, u32 *status);
 cudaError_t launch_gather(int grid, cudaStream_t st, const u64 *slots, u32 b, u64 n_loads, u64 seed, unsigned long long *sink);

@@ -107,6 +107,9 @@ int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info);
 /* kh_get + kh_val over a batch of keys (host pointers): found_out[i] = 1/0, vals_out[i] = value if found */
 int bns_b200_lookup_batch(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint32_t *vals_out, uint8_t *found_out);
 
+/* number of 32-byte buckets (DRAM sectors) the probes of `keys` touch in total: the p-bar of SURVEY 8(d) */
+int bns_b200_lookup_sectors(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint64_t *sectors_out);
+
 /* ---- taxonomy: khash_t(p) child -> parent ---------------------------------------------------------
  * build_parent_map, include/bonsai/util.h:766-785 (taxid 1 is forced to parent 0) */
 int bns_b200_load_taxonomy(bns_b200_t *ctx, const uint32_t *child, const uint32_t *parent, uint64_t n);
