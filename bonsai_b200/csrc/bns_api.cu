@@ -772,7 +772,7 @@ int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *of
     if(!n_seqs) return BNS_OK;
     CK(cudaSetDevice(ctx->device));
     const size_t smem = stream_smem_bytes(ctx->ring_cap, false);
-    const int occ = encode_occupancy(smem);
+    const int occ = encode_occupancy(ctx->enc, smem);
     u32 status_acc = 0;
     int slot_i = 0;
     u64 r0 = 0;
@@ -834,10 +834,10 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
-    const int occ = classify_occupancy(smem);
+    const int occ = classify_occupancy(ctx->enc, d_taxa != nullptr, smem);
     CK(cudaEventRecord(ctx->ev0, st));
     CK(launch_classify(ctx->enc, grid_for(ctx, n_rec, occ), smem, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
-                       table_view(ctx), tax_view(ctx), ctx->d_values, d_taxon, d_n_hit, d_n_missing, d_taxa,
+                       table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
                        (const u64 *)d_taxa_offsets, ctx->ring_cap, ctx->d_counters, ctx->d_status));
     CK(cudaEventRecord(ctx->ev1, st));
     ++ctx->stats.kernel_launches;
@@ -857,7 +857,7 @@ int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *
     const u64 n_rec_total = n_reads / mates;
     if(!n_rec_total) return BNS_OK;
     const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
-    const int occ = classify_occupancy(smem);
+    const int occ = classify_occupancy(ctx->enc, taxa_out != nullptr, smem);
     CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
     CK(cudaStreamSynchronize(ctx->slots[0].st));
     int slot_i = 0;
@@ -884,7 +884,7 @@ int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *
         CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
         CK(launch_classify(ctx->enc, grid_for(ctx, nq, occ), smem, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
-                           table_view(ctx), tax_view(ctx), ctx->d_values, s.d_out, n_hit_out ? s.d_out + nq : nullptr,
+                           table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
                            taxa_out ? s.d_taxa_offsets : nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
         ++ctx->stats.kernel_launches;

@@ -139,6 +139,21 @@ __device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4, u32 &t4) {
     bad4 = (((nz >> 7) * 0x08040201u) >> 24) & 0xfu;   // byte0 -> bit 3
     t4 = ((((hi & lo) * 0x08040201u) >> 24) & 0xfu) & ~bad4;   // valid T
 }
+// fast path: codes only, plus a word that is non-zero iff some byte is not one of ACGTacgt
+__device__ __forceinline__ u32 pack4_fast(u32 w, u32 &code8) {
+    u32 t = (w >> 1) & 0x03030303u;
+    t ^= (t >> 1) & 0x01010101u;
+    code8 = (t * 0x40100401u) >> 24;
+    const u32 hi = (t >> 1) & 0x01010101u, lo = t & 0x01010101u;
+    const u32 expect = 0x41414141u + 2u * t + 2u * hi + 11u * (hi & lo);
+    return expect ^ (w & 0xdfdfdfdfu);
+}
+__device__ __forceinline__ u32 pack16_fast(uint4 v, u32 &codes) {
+    u32 c0, c1, c2, c3;
+    const u32 d = pack4_fast(v.x, c0) | pack4_fast(v.y, c1) | pack4_fast(v.z, c2) | pack4_fast(v.w, c3);
+    codes = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    return d;
+}
 __device__ __forceinline__ void pack16(uint4 v, u32 &codes, u32 &bad, u32 &tmask) {
     u32 c0, c1, c2, c3, b0, b1, b2, b3, t0, t1, t2, t3;
     pack4(v.x, c0, b0, t0); pack4(v.y, c1, b1, t1); pack4(v.z, c2, b2, t2); pack4(v.w, c3, b3, t3);

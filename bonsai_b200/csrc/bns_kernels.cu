@@ -1,25 +1,31 @@
 // bns_kernels.cu -- hand-written sm_100a kernels of the classify hot path.
 //
-//   bns_stream_kernel<Sink>   warp-per-record: stage the read tile in shared memory (2-bit packed), generate the
-//                             k-mer / minimizer stream of Encoder::for_each (include/bonsai/encoder.h:416-442 and the
-//                             mode bodies :211-353), and hand every emitted k-mer to the sink:
-//       StoreSink             write the stream out                      (Encoder API parity surface)
-//       ClassifySink          probe the device table (kh_get, khash64.h:250-263), keep the per-record distinct-taxon
-//                             counts (linear::counter, linear.h:229), then resolve_tree (util.h:831-869) in the same warp
+//   bns_classify_kernel<FAM,TAXA>  warp per record: stage the read tile in shared memory (2-bit packed), generate the
+//                             k-mer / minimizer stream of Encoder::for_each (include/bonsai/encoder.h:416-442 and the mode
+//                             bodies :211-353), probe the device table (kh_get, khash64.h:250-263), keep the per-record
+//                             distinct-taxon counts (linear::counter, linear.h:229) and finish with resolve_tree
+//                             (util.h:831-869) -- all in the same warp, nothing round-trips through HBM.
+//   bns_encode_kernel<FAM>    the same front end writing the stream out (Encoder API parity surface)
 //   bns_insert_kernel         builds the bucketised open-addressed table with 64-bit CAS
-//   bns_lookup_kernel         kh_get + kh_val over a key batch
+//   bns_lookup_kernel         kh_get + kh_val over a key batch;  bns_sectors_kernel counts sectors per probe
 //   bns_resolve_kernel        resolve_tree over explicit (taxid,count) lists
 //   bns_gather_kernel         random 32-byte-sector gather (the measured random-access ceiling)
+//
+// FAM is a template parameter so that the default classify mode (FAM_U: unspaced, unwindowed, what `bonsai classify`
+// always runs, bin/bonsai.cpp:152) compiles to a lean kernel without the window / spaced-seed machinery.
 #include "bns_device.cuh"
 #include "bns_kernels.h"
 
 namespace bns {
 
-
 // ---------------------------------------------------------------------------------------------
 // per-warp shared memory carve-up (dynamic)
 // ---------------------------------------------------------------------------------------------
 constexpr int NWORDS = (TILE + CMAX + 16) / 16 + 3;     // 2-bit code words / invalid-bit words per tile
+#ifndef BNS_CLASSIFY_MIN_CTAS
+#define BNS_CLASSIFY_MIN_CTAS 3
+#endif
+constexpr int VI_CAP = 512;                              // val_info records staged in shared memory by TMA
 
 struct WarpSmem {
     u32 *codes;      // [NWORDS] 16 bases per word, first base in the top bits
@@ -39,7 +45,7 @@ __host__ __device__ inline size_t warp_smem_bytes(u32 ring_cap, bool classify) {
     if(classify) b += 4 * AGG_CAP * sizeof(u32);
     return (b + 15) & ~size_t(15);
 }
-__device__ inline WarpSmem carve(unsigned char *base, u32 ring_cap, bool classify) {
+__device__ inline WarpSmem carve(unsigned char *base, u32 ring_cap) {
     WarpSmem s;
     s.codes = (u32 *)base;
     s.bad = s.codes + NWORDS;
@@ -52,7 +58,6 @@ __device__ inline WarpSmem carve(unsigned char *base, u32 ring_cap, bool classif
     s.cnt = s.ids + AGG_CAP;
     s.tin = s.cnt + AGG_CAP;
     s.tout = s.tin + AGG_CAP;
-    (void)classify;
     return s;
 }
 
@@ -73,7 +78,7 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, u32 lane, u32 &total) {
 // ---------------------------------------------------------------------------------------------
 // tile staging: bases [p0, p0+span) of the sequence -> shared memory. Returns the coordinate shift (the
 // tile's first base sits at coordinate `shift` because loads are 16-byte aligned) and whether any staged
-// base is invalid.
+// base is invalid. One LDG.128 per lane covers the whole tile (<= 398 bytes).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 stage_tile(const EncParams &cP, const WarpSmem &S, const char *seq, u64 p0, u64 L, u32 span,
                                           const char *buf_end, u32 lane, bool &any_invalid, u32 &t_carry) {
@@ -85,59 +90,66 @@ __device__ __forceinline__ u32 stage_tile(const EncParams &cP, const WarpSmem &S
     const u32 hi = shift + nbases;                                      // valid coordinates: [shift, hi)
     const u32 nblk = (hi + 15) >> 4;
     u32 codes = 0, bad = 0, tmask = 0;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    u32 suspicious = 0;
     if(lane < nblk) {
         const char *p = aligned + 16 * lane;
-        uint4 v = make_uint4(0, 0, 0, 0);
         if(p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p));
-        pack16(v, codes, bad, tmask);
-        // bases outside [shift, hi) belong to neighbours (or to nobody): never read by a k-mer, but they
-        // must not trigger the slow path
-        const int before = (int)shift - (int)(16 * lane);
-        const int after = (int)hi - (int)(16 * lane);
-        u32 keep = 0xffffu;
-        if(before > 0) keep &= (before >= 16) ? 0u : (0xffffu >> before);
-        if(after < 16) keep &= (after <= 0) ? 0u : ~(0xffffu >> after);
-        bad &= keep;
-        tmask &= keep;
+        suspicious = pack16_fast(v, codes);
     }
-    if(cP.t_restart) {
-        // for_each_uncanon_unspaced_windowed tests the OR-ed 64-bit word against ~0 BEFORE masking (encoder.h:283):
-        // with k >= 31 that word holds 32 bases, so the 32nd, 64th, ... consecutive T of a run restarts the rolling
-        // state exactly like an invalid base. Mark those bases invalid. e = T-run length entering each word.
-        u32 e = t_carry, e_at_cx = 0;
-        const u32 cx = shift + TILE - 1;                     // the next tile starts right after this coordinate
-        for(u32 wd = 0; wd < nblk; ++wd) {
-            const u32 tm = __shfl_sync(FULL, tmask, wd);
-            const u32 first = wd == 0 ? shift : 0u;
-            if(wd == (cx >> 4)) e_at_cx = e;
-            const u32 m = tm << (16 + first);                // first in-range base of the word at bit 31
-            u32 lead = __clz(~m);
-            lead = lead < 16 - first ? lead : 16 - first;
-            if(lead) {
-                const u32 i = 31u - (e & 31u);
-                if(i < lead && lane == wd) bad |= 0x8000u >> (first + i);
-            }
-            if(lead == 16 - first) e += lead;
-            else e = __ffs(~tm) - 1;                          // trailing T of the word start a new run
+    // common case: every staged byte is one of ACGTacgt -> no invalid-mask work at all
+    any_invalid = false;
+    if(__any_sync(FULL, suspicious != 0) || cP.t_restart) {
+        if(lane < nblk) {
+            pack16(v, codes, bad, tmask);
+            // bases outside [shift, hi) belong to neighbours (or to nobody): never read by a k-mer of this sequence
+            const int before = (int)shift - (int)(16 * lane);
+            const int after = (int)hi - (int)(16 * lane);
+            u32 keep = 0xffffu;
+            if(before > 0) keep &= (before >= 16) ? 0u : (0xffffu >> before);
+            if(after < 16) keep &= (after <= 0) ? 0u : ~(0xffffu >> after);
+            bad &= keep;
+            tmask &= keep;
         }
-        // run length ending at coordinate cx (carried into the next tile)
-        if((cx >> 4) < nblk) {
-            const u32 wd = cx >> 4, first = wd == 0 ? shift : 0u;
-            const u32 tm = __shfl_sync(FULL, tmask, wd);
-            const u32 upto = (tm >> (15 - (cx & 15u)));       // bit 0 = coordinate cx, bit j = cx - j
-            const u32 nbits = (cx & 15u) + 1 - first;         // in-range bases of the word up to cx
-            u32 run = __ffs(~upto) - 1;                       // consecutive T ending at cx
-            if(run >= nbits) run = nbits + e_at_cx;
-            t_carry = run;
-        } else t_carry = 0;
+        if(cP.t_restart) {
+            // for_each_uncanon_unspaced_windowed tests the OR-ed 64-bit word against ~0 BEFORE masking (encoder.h:283):
+            // with k >= 31 that word holds 32 bases, so the 32nd, 64th, ... consecutive T of a run restarts the rolling
+            // state exactly like an invalid base. Mark those bases invalid. e = T-run length entering each word.
+            u32 e = t_carry, e_at_cx = 0;
+            const u32 cx = shift + TILE - 1;                     // the next tile starts right after this coordinate
+            for(u32 wd = 0; wd < nblk; ++wd) {
+                const u32 tm = __shfl_sync(FULL, tmask, wd);
+                const u32 first = wd == 0 ? shift : 0u;
+                if(wd == (cx >> 4)) e_at_cx = e;
+                const u32 m = tm << (16 + first);                // first in-range base of the word at bit 31
+                u32 lead = __clz(~m);
+                lead = lead < 16 - first ? lead : 16 - first;
+                if(lead) {
+                    const u32 i = 31u - (e & 31u);
+                    if(i < lead && lane == wd) bad |= 0x8000u >> (first + i);
+                }
+                if(lead == 16 - first) e += lead;
+                else e = __ffs(~tm) - 1;                          // trailing T of the word start a new run
+            }
+            if((cx >> 4) < nblk) {                                // run length ending at coordinate cx
+                const u32 wd = cx >> 4, first = wd == 0 ? shift : 0u;
+                const u32 tm = __shfl_sync(FULL, tmask, wd);
+                const u32 upto = (tm >> (15 - (cx & 15u)));       // bit 0 = coordinate cx, bit j = cx - j
+                const u32 nbits = (cx & 15u) + 1 - first;         // in-range bases of the word up to cx
+                u32 run = __ffs(~upto) - 1;                       // consecutive T ending at cx
+                if(run >= nbits) run = nbits + e_at_cx;
+                t_carry = run;
+            } else t_carry = 0;
+        }
+        any_invalid = __any_sync(FULL, bad != 0);
+        if(lane < NWORDS) S.bad[lane] = bad;
     }
-    if(lane < NWORDS) { S.codes[lane] = codes; S.bad[lane] = bad; }
-    any_invalid = __any_sync(FULL, bad != 0);
+    if(lane < NWORDS) S.codes[lane] = codes;
     __syncwarp();
     return shift;
 }
 
-// the comb's k bases starting at coordinate q; invalid -> KMER_NONE (Encoder::kmer, encoder.h:547-592)
+// the comb's k bases starting at coordinate q (Encoder::kmer, encoder.h:547-592); inval = some base is not ACGT
 __device__ __forceinline__ u64 gather_kmer(const EncParams &cP, const WarpSmem &S, u32 q, bool check_bad, bool &inval) {
     u64 x = 0;
     inval = false;
@@ -173,6 +185,55 @@ __device__ __forceinline__ u64 score_of(const EncParams &cP, u64 x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// table probe
+// ---------------------------------------------------------------------------------------------
+// exact test of the (64-b)-bit remainder and the 3-bit displacement of four slots against `tag`; returns the value id
+__device__ __forceinline__ u32 match4(const TableView &T, u64 tag, u64 s0, u64 s1, u64 s2, u64 s3) {
+    const u32 th = (u32)(tag >> 32), tl = (u32)tag, hm = ~0u << T.tag_shift;      // tag_shift <= 29
+    const u32 d0 = ((u32)(s0 >> 32) ^ th) | (((u32)s0 ^ tl) & hm);
+    const u32 d1 = ((u32)(s1 >> 32) ^ th) | (((u32)s1 ^ tl) & hm);
+    const u32 d2 = ((u32)(s2 >> 32) ^ th) | (((u32)s2 ^ tl) & hm);
+    const u32 d3 = ((u32)(s3 >> 32) ^ th) | (((u32)s3 ^ tl) & hm);
+    u32 v = VAL_MISS;
+    if(d0 == 0) v = (u32)s0;
+    if(d1 == 0) v = (u32)s1;
+    if(d2 == 0) v = (u32)s2;
+    if(d3 == 0) v = (u32)s3;
+    return (d0 && d1 && d2 && d3) ? VAL_MISS : (v & T.val_mask);
+}
+// buckets after the home bucket (rare: the home bucket overflowed when the table was built)
+__device__ __noinline__ u32 probe_displaced(const TableView T, u64 h) {
+    const u32 b = T.bucket_bits;
+    const u64 bmask = (1ull << b) - 1, home = h >> (64 - b), tag = h << b;
+    for(u32 d = 1; d <= 6; ++d) {
+        u64 a, bb, c, e;
+        ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
+        const u32 v = match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e);
+        if(v != VAL_MISS || e == ~0ull) return v;
+    }
+    return VAL_MISS;
+}
+// kh_get + kh_val for up to PPL keys per lane: all home-bucket sectors are requested before any is inspected
+__device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 mask, u32 (&val)[PPL]) {
+    const u32 b = T.bucket_bits;
+    u64 h[PPL], s[PPL][4];
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) {
+        h[i] = mix64(x[i]);
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = ~0ull;
+        if(mask >> i & 1u) ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
+    }
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) {
+        u32 v = match4(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
+        // an empty slot has disp == 7, which no probe tag carries, so unrequested (all ~0) buckets never match.
+        // The overflow mark lives in slot 0 of a FULL home bucket.
+        if(v == VAL_MISS && s[i][3] != ~0ull && (((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h[i]);
+        val[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sinks
 // ---------------------------------------------------------------------------------------------
 struct StoreSink {
@@ -190,74 +251,50 @@ struct StoreSink {
     }
 };
 
+template <bool TAXA>
 struct ClassifySink {
     TableView T;
-    u32 *taxa_out;    // optional ordered hit list of this record (raw taxids), or nullptr
-    const u32 *dict;  // value id -> taxid (only for taxa_out)
+    const uint4 *vi;  // val_info: shared-memory copy (TMA-staged) when it fits, else global
+    u32 *taxa_out;    // ordered hit list of this record (raw taxids) when TAXA
     u32 n_distinct, n_hit, n_miss, overflow;   // warp-uniform
 
     __device__ __forceinline__ void begin(u32 *taxa) { taxa_out = taxa; n_distinct = n_hit = n_miss = overflow = 0; }
 
-    __device__ __forceinline__ u32 match4(u64 tag, u64 s0, u64 s1, u64 s2, u64 s3) const {
-        const u32 sh = T.tag_shift;
-        u32 v = VAL_MISS;
-        if(((s0 ^ tag) >> sh) == 0) v = (u32)s0 & T.val_mask;
-        if(((s1 ^ tag) >> sh) == 0) v = (u32)s1 & T.val_mask;
-        if(((s2 ^ tag) >> sh) == 0) v = (u32)s2 & T.val_mask;
-        if(((s3 ^ tag) >> sh) == 0) v = (u32)s3 & T.val_mask;
-        return v;
-    }
-
-    // kh_get + kh_val for up to PPL keys per lane: all home-bucket sectors are requested before any is inspected
-    __device__ __forceinline__ void probe(const u64 (&x)[PPL], u32 mask, u32 (&val)[PPL]) const {
-        const u32 b = T.bucket_bits;
-        u64 h[PPL], s[PPL][4];
-#pragma unroll
-        for(int i = 0; i < PPL; ++i) {
-            h[i] = mix64(x[i]);
-            s[i][0] = s[i][1] = s[i][2] = s[i][3] = ~0ull;
-            if(mask >> i & 1u) ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
+    // linear::counter::add of `total` hits of value id v
+    __device__ __forceinline__ void add(const WarpSmem &S, u32 v, u32 total, u32 lane) {
+        int found = -1;
+        for(u32 base = 0; base < n_distinct; base += 32) {
+            const u32 idx = base + lane;
+            const u32 bm = __ballot_sync(FULL, idx < n_distinct && S.ids[idx] == v);
+            if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
         }
-#pragma unroll
-        for(int i = 0; i < PPL; ++i) {
-            val[i] = VAL_MISS;
-            if(!(mask >> i & 1u)) continue;
-            const u64 tag = h[i] << b;
-            u32 v = match4(tag, s[i][0], s[i][1], s[i][2], s[i][3]);
-            // rare: a key homed here was displaced (overflow mark lives in slot 0 of a full bucket)
-            if(v == VAL_MISS && s[i][3] != ~0ull && ((s[i][0] >> (T.tag_shift - 1)) & 1ull)) {
-                const u64 bmask = (1ull << b) - 1;
-                const u64 home = h[i] >> (64 - b);
-                for(u32 d = 1; d <= 6; ++d) {
-                    u64 a, bb, c, e;
-                    ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
-                    v = match4(tag | ((u64)d << T.tag_shift), a, bb, c, e);
-                    if(v != VAL_MISS || e == ~0ull) break;
-                }
-            }
-            val[i] = v;
-        }
+        if(found < 0) {
+            if(n_distinct < AGG_CAP) {
+                if(lane == 0) { S.ids[n_distinct] = v; S.cnt[n_distinct] = total; }
+                ++n_distinct;
+            } else overflow = 1;
+        } else if(lane == 0) S.cnt[found] += total;
+        __syncwarp();
     }
 
     __device__ __forceinline__ void consume(const WarpSmem &S, const u64 (&x)[PPL], u32 mask, u32 lane) {
         if(!__any_sync(FULL, mask != 0)) return;
         u32 val[PPL];
-        probe(x, mask, val);
+        probe4(T, x, mask, val);
         u32 todo = 0;
 #pragma unroll
-        for(int i = 0; i < PPL; ++i) if((mask >> i & 1u) && val[i] != VAL_MISS) todo |= 1u << i;
-        const u32 my_hits = __popc(todo);
-        u32 hits_total;
-        const u32 ex = warp_excl_scan(my_hits, lane, hits_total);
+        for(int i = 0; i < PPL; ++i) if(val[i] != VAL_MISS) todo |= 1u << i;
+        todo &= mask;
         const u32 emitted = __reduce_add_sync(FULL, __popc(mask));
-        if(taxa_out) {
-            u32 idx = n_hit + ex;
+        u32 hits_total;
+        if(TAXA) {
+            u32 idx = n_hit + warp_excl_scan(__popc(todo), lane, hits_total);
 #pragma unroll
-            for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) taxa_out[idx++] = dict[val[i]];
-        }
+            for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) taxa_out[idx++] = vi[val[i]].w;
+        } else hits_total = __reduce_add_sync(FULL, __popc(todo));
         n_hit += hits_total;
         n_miss += emitted - hits_total;
-        // fold the hits into the per-record distinct list (linear::counter::add)
+        // fold the hits into the per-record distinct list, one distinct value per iteration
         for(;;) {
             const u32 bal = __ballot_sync(FULL, todo != 0);
             if(!bal) break;
@@ -269,20 +306,7 @@ struct ClassifySink {
             u32 c = 0;
 #pragma unroll
             for(int i = 0; i < PPL; ++i) if((todo >> i & 1u) && val[i] == v) { ++c; todo &= ~(1u << i); }
-            const u32 total = __reduce_add_sync(FULL, c);
-            int found = -1;
-            for(u32 base = 0; base < n_distinct; base += 32) {
-                const u32 idx = base + lane;
-                const u32 bm = __ballot_sync(FULL, idx < n_distinct && S.ids[idx] == v);
-                if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
-            }
-            if(found < 0) {
-                if(n_distinct < AGG_CAP) {
-                    if(lane == 0) { S.ids[n_distinct] = v; S.cnt[n_distinct] = total; }
-                    ++n_distinct;
-                } else overflow = 1;
-            } else if(lane == 0) S.cnt[found] += total;
-            __syncwarp();
+            add(S, v, __reduce_add_sync(FULL, c), lane);
         }
     }
 
@@ -291,9 +315,9 @@ struct ClassifySink {
     __device__ __forceinline__ u32 resolve(const WarpSmem &S, const TaxView &X, u32 lane) const {
         const u32 n = n_distinct;
         if(n == 0) return 0;
-        if(n == 1) return X.val_info[S.ids[0]].w;
+        if(n == 1) return vi[S.ids[0]].w;
         for(u32 i = lane; i < n; i += 32) {
-            const uint4 inf = X.val_info[S.ids[i]];
+            const uint4 inf = vi[S.ids[i]];
             S.tin[i] = inf.x; S.tout[i] = inf.y;
         }
         __syncwarp();
@@ -323,7 +347,7 @@ struct ClassifySink {
                 const u32 l = __ffs(tied) - 1;
                 tied &= tied - 1;
                 const u32 id = S.ids[base + l];
-                const uint4 inf = X.val_info[id];            // uniform address
+                const uint4 inf = vi[id];                     // uniform address
                 if(ntied == 0) { node = inf.z; first_id = id; }
                 else {
                     // lca(node, b): climb from `node` until its interval covers b (util.h:634-663)
@@ -339,7 +363,7 @@ struct ClassifySink {
                 ++ntied;
             }
         }
-        if(ntied == 1) return X.val_info[first_id].w;
+        if(ntied == 1) return vi[first_id].w;
         return X.node_info[node].w;
     }
 };
@@ -388,14 +412,70 @@ __device__ __forceinline__ u32 roll_ring(const WarpSmem &S, u32 hist, u32 m, u32
 }
 
 // ---------------------------------------------------------------------------------------------
-// one sequence (one mate) through the encoder; every emitted k-mer goes to sink.consume in emission order
+// FAM_U fast path: unspaced, unwindowed (for_each_uncanon_unspaced_unwindowed, encoder.h:240-272, + canonical wrapper
+// :218-232). The lane's four consecutive k-mers and their reverse complements come out of ONE 96-bit window of the
+// staged tile: forward k-mer i = window bits [2i, 2i+2k), reverse complement i = low 2k bits of (rc(window) >> 2i).
 // ---------------------------------------------------------------------------------------------
 template <class Sink>
-__device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L, const char *buf_end,
-                                                Sink &sink, u32 lane) {
-    const u32 fam = cP.family;
+__device__ __forceinline__ void encode_sequence_u(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L,
+                                                  const char *buf_end, Sink &sink, u32 lane) {
+    const u32 k = cP.k;
+    if(L < k) return;                                            // has_next_kmer(), encoder.h:418,594
+    const u64 npos = L - k + 1;
+    const u32 span = TILE + k - 1;
+    const u32 down = 64 - 2 * k;
+    const bool canon = cP.canon_elem != 0;
+    u32 t_carry = 0;
+    for(u64 p0 = 0; p0 < npos; p0 += TILE) {
+        bool any_invalid;
+        const u32 shift = stage_tile(cP, S, seq, p0, L, span, buf_end, lane, any_invalid, t_carry);
+        const u32 q0 = shift + PPL * lane;
+        const u64 left = npos - p0;
+        const u32 nlive = left > (u64)PPL * lane ? (u32)min((u64)PPL, left - (u64)PPL * lane) : 0u;
+        u32 mask = (1u << nlive) - 1;
+        u64 x[PPL];
+        {
+            const u32 wi = q0 >> 4, s = (q0 & 15u) * 2u;
+            const u32 w0 = S.codes[wi], w1 = S.codes[wi + 1], w2 = S.codes[wi + 2], w3 = S.codes[wi + 3];
+            const u32 A = __funnelshift_l(w1, w0, s), B = __funnelshift_l(w2, w1, s), C = __funnelshift_l(w3, w2, s);
+            u32 R0 = 0, R1 = 0, R2 = 0;
+            if(canon) {
+                // rc of the 48-base window: reverse the bit string, swap the two bits of each pair back, complement
+                R0 = __brev(C); R1 = __brev(B); R2 = __brev(A);
+                R0 = ~(((R0 >> 1) & 0x55555555u) | ((R0 & 0x55555555u) << 1));
+                R1 = ~(((R1 >> 1) & 0x55555555u) | ((R1 & 0x55555555u) << 1));
+                R2 = ~(((R2 >> 1) & 0x55555555u) | ((R2 & 0x55555555u) << 1));
+            }
+            const u64 kmask = ~0ull >> down;
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) {
+                const u32 hi = __funnelshift_l(B, A, 2 * i), lo = __funnelshift_l(C, B, 2 * i);
+                u64 f = (((u64)hi << 32) | lo) >> down;
+                if(canon) {
+                    const u32 rl = __funnelshift_r(R2, R1, 2 * i), rh = __funnelshift_r(R1, R0, 2 * i);
+                    const u64 r = (((u64)rh << 32) | rl) & kmask;
+                    f = f < r ? f : r;
+                }
+                x[i] = f;
+            }
+        }
+        if(any_invalid) {                                        // rare: drop the windows that cover an invalid base
+#pragma unroll
+            for(int i = 0; i < PPL; ++i) if((mask >> i & 1u) && any_bad(S.bad, q0 + i, k)) mask &= ~(1u << i);
+        }
+        __syncwarp();
+        sink.consume(S, x, mask, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic path: FAM_K (kmer(pos)-based, windowed/spaced) and FAM_R (rolling + window + tail flush)
+// ---------------------------------------------------------------------------------------------
+template <int FAM, class Sink>
+__device__ __forceinline__ void encode_sequence_g(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L,
+                                                  const char *buf_end, Sink &sink, u32 lane) {
     const u32 k = cP.k, c = cP.c, W = cP.W;
-    if(fam == FAM_NONE || L < c) return;                       // has_next_kmer(), encoder.h:418,594
+    if(L < c) return;                                           // has_next_kmer(), encoder.h:418,594
     const u64 npos = L - c + 1;
     const u32 span = TILE + c - 1;
     u32 hist = 0;                                               // ring entries carried from earlier tiles
@@ -418,19 +498,9 @@ __device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpS
                 if(!inval) okm |= 1u << i;
             }
         }
-        if(fam == FAM_U) {
-            // an invalid window is skipped; a valid T*32 (== ~0 for k = 32) is emitted (encoder.h:251-253)
-            if(cP.canon_elem) {
-#pragma unroll
-                for(int i = 0; i < PPL; ++i) if(okm >> i & 1u) x[i] = canonical(x[i], k);
-            }
-            __syncwarp();
-            sink.consume(S, x, okm, lane);
-            continue;
-        }
         // element set of this tile
         u32 emask;
-        if(fam == FAM_K) {
+        if(FAM == FAM_K) {
             emask = live;                                       // every position pushes (invalid -> ~0, or 0 if canon)
 #pragma unroll
             for(int i = 0; i < PPL; ++i) if(!(okm >> i & 1u)) x[i] = KMER_NONE;
@@ -488,24 +558,33 @@ __device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpS
     __syncwarp();
 }
 
+template <int FAM, class Sink>
+__device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L,
+                                                const char *buf_end, Sink &sink, u32 lane) {
+    if(FAM == FAM_U) encode_sequence_u(cP, S, seq, L, buf_end, sink, lane);
+    else if(FAM == FAM_K || FAM == FAM_R) encode_sequence_g<FAM>(cP, S, seq, L, buf_end, sink, lane);
+    // FAM_NONE: the string overload with a spaced seed emits nothing (encoder.h:437-440)
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char g_smem[];
 
+template <int FAM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-bns_encode_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_seqs, u64 total_bases,
-                  u64 *__restrict__ kmers_out, const u64 *__restrict__ out_offsets, u32 *__restrict__ counts_out,
-                  u32 ring_cap, u32 *__restrict__ status) {
+bns_encode_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
+                  u64 n_seqs, u64 total_bases, u64 *__restrict__ kmers_out, const u64 *__restrict__ out_offsets,
+                  u32 *__restrict__ counts_out, u32 ring_cap, u32 *__restrict__ status) {
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
-    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, false), ring_cap, false);
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, false), ring_cap);
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
     StoreSink sink;
     for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_seqs; r += nwarps) {
         const u64 b = offsets[r], e = offsets[r + 1];
         const u64 ob = out_offsets[r], oe = out_offsets[r + 1];
         sink.begin(kmers_out + ob, oe - ob);
-        encode_sequence(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+        encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
         if(lane == 0) {
             counts_out[r] = (u32)sink.n;
             if(sink.n > sink.cap) atomicOr(status, 1u);
@@ -513,24 +592,55 @@ bns_encode_kernel(const __grid_constant__ EncParams P, const char *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records, u32 mates,
-                    u64 total_bases, TableView T, TaxView X, const u32 *__restrict__ dict,
+// The per-value taxonomy records (val_info: Euler interval, node, taxid) are the only taxonomy data a record with
+// <= 1 tied maximum touches. When they fit (n_values <= VI_CAP) each CTA brings them into shared memory with one
+// TMA bulk copy (cp.async.bulk -> UBLKCP) completing on an mbarrier, while the warps already stage their first reads.
+__device__ __forceinline__ void tma_stage_val_info(uint4 *dst, const uint4 *src, u32 bytes, unsigned long long *mbar) {
+    const u32 mb = (u32)__cvta_generic_to_shared(mbar), d = (u32)__cvta_generic_to_shared(dst);
+    if(threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, u32 parity) {
+    const u32 mb = (u32)__cvta_generic_to_shared(mbar);
+    u32 done = 0;
+    while(!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+    }
+}
+
+template <int FAM, bool TAXA>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, BNS_CLASSIFY_MIN_CTAS)
+bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
+                    u64 n_records, u32 mates, u64 total_bases, TableView T, TaxView X,
                     u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out, u32 *__restrict__ nmiss_out,
                     u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 ring_cap,
                     unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
+    __shared__ __align__(16) uint4 s_vi[VI_CAP];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
-    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, true), ring_cap, true);
+    const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
+    if(staged) tma_stage_val_info(s_vi, X.val_info, T.n_values * (u32)sizeof(uint4), &s_mbar);
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, true), ring_cap);
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
-    ClassifySink sink;
+    ClassifySink<TAXA> sink;
     sink.T = T;
-    sink.dict = dict;
+    sink.vi = staged ? s_vi : X.val_info;
+    if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
     for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_records; r += nwarps) {
-        sink.begin(taxa_out ? taxa_out + taxa_offsets[r] : nullptr);
+        sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
         for(u32 mt = 0; mt < mates; ++mt) {
             const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
-            encode_sequence(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+            encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
         }
         const u32 taxon = sink.resolve(S, X, lane);
         if(lane == 0) {
@@ -609,13 +719,13 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
                                   u32 *__restrict__ vals_out, uint8_t *__restrict__ found_out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    ClassifySink s;
-    s.T = T;
-    u64 x[PPL] = {keys[i], 0, 0, 0};
-    u32 val[PPL];
-    s.probe(x, 1u, val);
-    found_out[i] = val[0] != VAL_MISS;
-    vals_out[i] = val[0] != VAL_MISS ? dict[val[0]] : 0u;
+    const u64 h = mix64(keys[i]);
+    u64 a, b, c, d;
+    ld_bucket(T.slots + ((h >> (64 - T.bucket_bits)) << 2), a, b, c, d);
+    u32 v = match4(T, h << T.bucket_bits, a, b, c, d);
+    if(v == VAL_MISS && d != ~0ull && (((u32)a >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h);
+    found_out[i] = v != VAL_MISS;
+    vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
 }
 
 __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u64 n, unsigned long long *__restrict__ total) {
@@ -624,13 +734,11 @@ __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u6
     if(i < n) {
         const u32 b = T.bucket_bits;
         const u64 h = mix64(keys[i]), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
-        ClassifySink s;
-        s.T = T;
         for(u32 d = 0; d <= 6; ++d) {
             u64 a, bb, c, e;
             ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
             ++touched;
-            if(s.match4(tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
+            if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
             if(d == 0 ? !(e != ~0ull && ((a >> (T.tag_shift - 1)) & 1ull)) : (e == ~0ull)) break;
         }
     }
@@ -644,9 +752,10 @@ bns_resolve_kernel(TaxView X, const u32 *__restrict__ values, u32 n_values, cons
                    const uint16_t *__restrict__ counts, const u64 *__restrict__ offsets, u64 n_lists,
                    u32 *__restrict__ taxon_out, u32 *__restrict__ status) {
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
-    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(0, true), 0, true);
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(0, true), 0);
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
-    ClassifySink sink;
+    ClassifySink<false> sink;
+    sink.vi = X.val_info;
     for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_lists; r += nwarps) {
         sink.begin(nullptr);
         const u64 b = offsets[r], e = offsets[r + 1];
@@ -654,20 +763,9 @@ bns_resolve_kernel(TaxView X, const u32 *__restrict__ values, u32 n_values, cons
         for(u64 i = b; i < e; ++i) {
             const u32 id = value_id(values, n_values, taxa[i]);
             if(id == VAL_MISS) { if(lane == 0) atomicOr(status, 4u); continue; }
-            int found = -1;
-            for(u32 base = 0; base < sink.n_distinct; base += 32) {
-                const u32 idx = base + lane;
-                const u32 bm = __ballot_sync(FULL, idx < sink.n_distinct && S.ids[idx] == id);
-                if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
-            }
-            if(found < 0) {
-                if(sink.n_distinct < AGG_CAP) {
-                    if(lane == 0) { S.ids[sink.n_distinct] = id; S.cnt[sink.n_distinct] = counts[i]; }
-                    ++sink.n_distinct;
-                } else if(lane == 0) atomicOr(status, 2u);
-            } else if(lane == 0) S.cnt[found] += counts[i];
-            __syncwarp();
+            sink.add(S, id, counts[i], lane);
         }
+        if(sink.overflow && lane == 0) atomicOr(status, 2u);
         const u32 t = sink.resolve(S, X, lane);
         if(lane == 0) taxon_out[r] = t;
         __syncwarp();
@@ -697,33 +795,58 @@ __global__ void bns_gather_kernel(const u64 *__restrict__ slots, u32 b, u64 n_lo
 // ---------------------------------------------------------------------------------------------
 size_t stream_smem_bytes(u32 ring_cap, bool classify) { return WARPS_PER_CTA * warp_smem_bytes(ring_cap, classify); }
 
-cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
-                          u64 total_bases, u64 *kmers_out, const u64 *out_offsets, u32 *counts_out, u32 ring_cap, u32 *status) {
-    cudaFuncSetAttribute(bns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bns_encode_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, kmers_out, out_offsets,
-                                                             counts_out, ring_cap, status);
+typedef void (*encode_fn)(const EncParams, const char *, const u64 *, u64, u64, u64 *, const u64 *, u32 *, u32, u32 *);
+typedef void (*classify_fn)(const EncParams, const char *, const u64 *, u64, u32, u64, TableView, TaxView, u32 *, u32 *, u32 *,
+                            u32 *, const u64 *, u32, unsigned long long *, u32 *);
+
+static encode_fn pick_encode(u32 fam) {
+    switch(fam) {
+        case FAM_U: return bns_encode_kernel<FAM_U>;
+        case FAM_K: return bns_encode_kernel<FAM_K>;
+        case FAM_R: return bns_encode_kernel<FAM_R>;
+        default: return bns_encode_kernel<FAM_NONE>;
+    }
+}
+static classify_fn pick_classify(u32 fam, bool taxa) {
+    switch(fam) {
+        case FAM_U: return taxa ? bns_classify_kernel<FAM_U, true> : bns_classify_kernel<FAM_U, false>;
+        case FAM_K: return taxa ? bns_classify_kernel<FAM_K, true> : bns_classify_kernel<FAM_K, false>;
+        case FAM_R: return taxa ? bns_classify_kernel<FAM_R, true> : bns_classify_kernel<FAM_R, false>;
+        default: return taxa ? bns_classify_kernel<FAM_NONE, true> : bns_classify_kernel<FAM_NONE, false>;
+    }
+}
+
+cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
+                          u64 n_seqs, u64 total_bases, u64 *kmers_out, const u64 *out_offsets, u32 *counts_out, u32 ring_cap,
+                          u32 *status) {
+    encode_fn f = pick_encode(P.family);
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, kmers_out, out_offsets, counts_out,
+                                             ring_cap, status);
     return cudaGetLastError();
 }
-cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
-                            u32 mates, u64 total_bases, const TableView &T, const TaxView &X, const u32 *dict,
+cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
+                            u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 ring_cap, unsigned long long *counters, u32 *status) {
-    cudaFuncSetAttribute(bns_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bns_classify_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, dict,
-                                                               taxon_out, nhit_out, nmiss_out, taxa_out, taxa_offsets,
-                                                               ring_cap, counters, status);
+    classify_fn f = pick_classify(P.family, taxa_out != nullptr);
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
+                                             nmiss_out, taxa_out, taxa_offsets, ring_cap, counters, status);
     return cudaGetLastError();
 }
-int classify_occupancy(size_t smem) {
+int classify_occupancy(const EncParams &P, bool taxa, size_t smem) {
     int nb = 0;
-    cudaFuncSetAttribute(bns_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bns_classify_kernel, WARPS_PER_CTA * 32, smem);
+    classify_fn f = pick_classify(P.family, taxa);
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, smem);
     return nb;
 }
-int encode_occupancy(size_t smem) {
+int encode_occupancy(const EncParams &P, size_t smem) {
     int nb = 0;
-    cudaFuncSetAttribute(bns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bns_encode_kernel, WARPS_PER_CTA * 32, smem);
+    encode_fn f = pick_encode(P.family);
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, smem);
     return nb;
 }
 cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
