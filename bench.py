@@ -95,6 +95,10 @@ def workload_spec(name):
         return dict(db=dict(k=K, w=K, gaps=W.SPACED_GAPS, score=capi.SCORE_LEX, canon=False),
                     cls=dict(k=K, w=K, gaps=W.SPACED_GAPS, canon=False, api=capi.API_PATH), n_lookup=L_READ - 40 + 1,
                     label="synthetic 150bp reads, spaced seed k=31 comb=40 (for_each_uncanon_spaced), spaced 4-genome DB")
+    if name == "stress":
+        return dict(db=None, cls=dict(k=K, w=K, gaps=None, canon=True, api=capi.API_STRING), n_lookup=L_READ - K + 1,
+                    label="synthetic 150bp reads vs synthetic random-stream DB (HBM-bound lookup stress, BASELINE config 5 scaled "
+                          "by --stress-keys), 50% of reads hit on every k-mer")
     raise SystemExit("unknown workload " + name)
 
 
@@ -169,6 +173,7 @@ def main():
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stress-keys", type=int, default=1 << 28, help="DB keys of the stress workload (2^30 = the 16 GB table)")
     args = ap.parse_args()
     spec = workload_spec(args.workload)
     if args.impl == "reference":
@@ -196,7 +201,18 @@ def main():
     # ---- database: built on rank 0, replicated with one broadcast ------------------------------------
     t_db0 = time.perf_counter()
     keys = vals = None
-    if rank == 0:
+    stress = args.workload == "stress"
+    stream = None
+    if stress:
+        # every rank regenerates the same seeded stream (reads are sampled from it); only rank 0 builds the table
+        stream, d_keys, d_vals = W.make_stress_db(args.stress_keys, seed=77, device=dev)
+        if rank == 0:
+            tc, tp = W.toy_tax_arrays()
+            ctx.load_pairs_device(d_keys.data_ptr(), d_vals.data_ptr(), args.stress_keys, W.STRESS_VALUES)
+            ctx.load_taxonomy(tc, tp)
+        del d_keys, d_vals
+        torch.cuda.empty_cache()
+    elif rank == 0:
         keys, vals, tc, tp = build_database(spec, g)
         ctx.load_pairs(keys, vals)
         ctx.load_taxonomy(tc, tp)
@@ -224,7 +240,13 @@ def main():
 
     # ---- reads: generated on the device, different per rank -----------------------------------------
     n = args.reads
-    d_bases, d_offs = W.make_reads_torch(g, n, seed=1234 + rank, device=dev)
+    from_db = None
+    if stress:
+        d_bases, d_offs, from_db = W.make_stress_reads(stream, n, seed=1234 + rank, device=dev)
+        del stream
+        torch.cuda.empty_cache()
+    else:
+        d_bases, d_offs = W.make_reads_torch(g, n, seed=1234 + rank, device=dev)
     d_taxon = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     torch.cuda.synchronize()
@@ -264,6 +286,11 @@ def main():
     value = world * n * args.steps / (elapsed_ms * 1e-3) / 1e6
 
     taxon_dev = d_taxon.cpu().numpy().astype(np.uint32)
+    stress_ok = None
+    if stress:
+        # every read cut from the stream is classified (all 120 k-mers hit), no random read is
+        fd = from_db.cpu().numpy()
+        stress_ok = bool((taxon_dev[fd] != 0).all() and (taxon_dev[~fd] == 0).all())
 
     # ---- end to end: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region -------------
     h_bases = torch.empty(n * L_READ, dtype=torch.uint8, pin_memory=True)
@@ -329,7 +356,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -------------------------------------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not stress:
         from oracle import pyoracle as po          # the checker, timed as the reported baseline only
         cpu = po.load_ref() or po.load_oracle()
         tc, tp = W.toy_tax_arrays()
@@ -367,6 +394,9 @@ def main():
             "clocks": clk,
             "n_unclassified": int((taxon_dev == 0).sum()),
         }
+        if stress:
+            out["config"]["stress_keys"] = args.stress_keys
+            out["config"]["stress_reads_classified_as_expected"] = stress_ok
         print(json.dumps(out))
     ctx.close()
     if world > 1:

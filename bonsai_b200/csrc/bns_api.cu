@@ -23,7 +23,7 @@ namespace {
 constexpr int N_SLOTS = 3;
 constexpr u64 CHUNK_BASES = 96ull << 20;      // bases per pipelined chunk
 constexpr u64 CHUNK_READS = 1ull << 20;
-constexpr double TARGET_LOAD = 2.5;           // entries per 4-slot bucket (0.63 of the slots, like khash's fill)
+XX
 
 struct Slot {
     cudaStream_t st = nullptr;
@@ -204,7 +204,7 @@ int alloc_table(bns_b200_ctx *ctx, u32 b) {
 u32 choose_bits(u64 n_keys, u32 n_values) {
     u32 b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / TARGET_LOAD));
     b = std::max(b, 12u);
-    b = std::max(b, bits_for(std::max<u32>(n_values, 1)) + 4u);
+    b = std::max(b, bits_for(std::max<u32>(n_values, 1)) + (u32)DISP_BITS + 1u);
     return b;
 }
 
@@ -342,8 +342,8 @@ TableView table_view(const bns_b200_ctx *ctx) {
     TableView T;
     T.slots = ctx->d_slots;
     T.bucket_bits = ctx->bucket_bits;
-    T.tag_shift = ctx->bucket_bits - 3;
-    T.val_mask = (1u << (ctx->bucket_bits - 4)) - 1;
+    T.tag_shift = ctx->bucket_bits - DISP_BITS;
+    T.val_mask = (1u << (ctx->bucket_bits - DISP_BITS - 1)) - 1;
     T.n_values = (u32)ctx->values.size();
     return T;
 }
@@ -520,7 +520,7 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
         }, st);
         if(rc != BNS_OK) return rc;
         if(st[0] == 0) return finish_table(ctx, st);
-        // some key found no room within 6 buckets of home: grow and rebuild
+        // some key found no room within MAX_DISP buckets of home: grow and rebuild
     }
 }
 
@@ -585,7 +585,7 @@ int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info) {
     info->n_buckets = ctx->n_buckets;
     info->bytes = ctx->n_buckets * 32;
     info->bucket_bits = ctx->bucket_bits;
-    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - 4 : 0;
+    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - DISP_BITS - 1 : 0;
     info->n_values = (u32)ctx->values.size();
     info->max_disp = ctx->max_disp;
     info->n_displaced = ctx->n_displaced;

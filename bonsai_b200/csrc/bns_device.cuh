@@ -36,6 +36,8 @@ constexpr int TILE = 128;        // k-mer positions per warp tile (4 per lane, l
 constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
 constexpr int AGG_CAP = 128;     // distinct taxa tracked per record in shared memory
+constexpr int DISP_BITS = 4;     // slot displacement field; disp == 2^DISP_BITS - 1 is reserved for the empty slot
+constexpr int MAX_DISP = (1 << DISP_BITS) - 2;
 
 struct EncParams {
     u32 k, c, W;                 // W = w_ - c_ + 1  (QueueMap size, encoder.h:142)
@@ -54,8 +56,8 @@ struct EncParams {
 struct TableView {
     const u64 *slots;            // n_buckets * 4 u64
     u32 bucket_bits;             // b: bucket = h >> (64-b)
-    u32 tag_shift;               // b - 3: bits below it are {ovf, val}
-    u32 val_mask;                // (1 << (b-4)) - 1
+    u32 tag_shift;               // b - DISP_BITS: bits below it are {novf, val}
+    u32 val_mask;                // (1 << (b - DISP_BITS - 1)) - 1
     u32 n_values;
 };
 

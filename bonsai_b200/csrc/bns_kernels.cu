@@ -189,7 +189,7 @@ __device__ __forceinline__ u64 score_of(const EncParams &cP, u64 x) {
 // ---------------------------------------------------------------------------------------------
 // exact test of the (64-b)-bit remainder and the 3-bit displacement of four slots against `tag`; returns the value id
 __device__ __forceinline__ u32 match4(const TableView &T, u64 tag, u64 s0, u64 s1, u64 s2, u64 s3) {
-    const u32 th = (u32)(tag >> 32), tl = (u32)tag, hm = ~0u << T.tag_shift;      // tag_shift <= 29
+    const u32 th = (u32)(tag >> 32), tl = (u32)tag, hm = ~0u << T.tag_shift;      // tag_shift <= 28
     const u32 d0 = ((u32)(s0 >> 32) ^ th) | (((u32)s0 ^ tl) & hm);
     const u32 d1 = ((u32)(s1 >> 32) ^ th) | (((u32)s1 ^ tl) & hm);
     const u32 d2 = ((u32)(s2 >> 32) ^ th) | (((u32)s2 ^ tl) & hm);
@@ -205,7 +205,7 @@ __device__ __forceinline__ u32 match4(const TableView &T, u64 tag, u64 s0, u64 s
 __device__ __noinline__ u32 probe_displaced(const TableView T, u64 h) {
     const u32 b = T.bucket_bits;
     const u64 bmask = (1ull << b) - 1, home = h >> (64 - b), tag = h << b;
-    for(u32 d = 1; d <= 6; ++d) {
+    for(u32 d = 1; d <= (u32)MAX_DISP; ++d) {
         u64 a, bb, c, e;
         ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
         const u32 v = match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e);
@@ -213,22 +213,22 @@ __device__ __noinline__ u32 probe_displaced(const TableView T, u64 h) {
     }
     return VAL_MISS;
 }
-// kh_get + kh_val for up to PPL keys per lane: all home-bucket sectors are requested before any is inspected
-__device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 mask, u32 (&val)[PPL]) {
+// kh_get + kh_val for PPL keys per lane: all home-bucket sectors are requested before any is inspected. Lanes / slots
+// without a live k-mer probe anyway (their result is masked by the caller): no predication, no register init.
+__device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 (&val)[PPL]) {
     const u32 b = T.bucket_bits;
     u64 h[PPL], s[PPL][4];
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         h[i] = mix64(x[i]);
-        s[i][0] = s[i][1] = s[i][2] = s[i][3] = ~0ull;
-        if(mask >> i & 1u) ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
+        ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
     }
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         u32 v = match4(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
-        // an empty slot has disp == 7, which no probe tag carries, so unrequested (all ~0) buckets never match.
-        // The overflow mark lives in slot 0 of a FULL home bucket.
-        if(v == VAL_MISS && s[i][3] != ~0ull && (((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h[i]);
+        // The overflow mark is a CLEARED bit in slot 0 of a full home bucket (an empty slot is all ones, so an
+        // empty or part-filled bucket reads "no overflow"): a miss costs one sector unless a key was displaced.
+        if(v == VAL_MISS && !(((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h[i]);
         val[i] = v;
     }
 }
@@ -280,20 +280,21 @@ struct ClassifySink {
     __device__ __forceinline__ void consume(const WarpSmem &S, const u64 (&x)[PPL], u32 mask, u32 lane) {
         if(!__any_sync(FULL, mask != 0)) return;
         u32 val[PPL];
-        probe4(T, x, mask, val);
+        probe4(T, x, val);
         u32 todo = 0;
 #pragma unroll
         for(int i = 0; i < PPL; ++i) if(val[i] != VAL_MISS) todo |= 1u << i;
         todo &= mask;
-        const u32 emitted = __reduce_add_sync(FULL, __popc(mask));
-        u32 hits_total;
+        const u32 both = __reduce_add_sync(FULL, __popc(mask) | (__popc(todo) << 16));   // emitted | hits << 16
+        const u32 hits_total = both >> 16;
         if(TAXA) {
-            u32 idx = n_hit + warp_excl_scan(__popc(todo), lane, hits_total);
+            u32 dummy;
+            u32 idx = n_hit + warp_excl_scan(__popc(todo), lane, dummy);
 #pragma unroll
             for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) taxa_out[idx++] = vi[val[i]].w;
-        } else hits_total = __reduce_add_sync(FULL, __popc(todo));
+        }
         n_hit += hits_total;
-        n_miss += emitted - hits_total;
+        n_miss += (both & 0xffffu) - hits_total;
         // fold the hits into the per-record distinct list, one distinct value per iteration
         for(;;) {
             const u32 bal = __ballot_sync(FULL, todo != 0);
@@ -669,9 +670,9 @@ __device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u
 }
 
 // Bucketised open addressing, 4 x u64 slots per 32-byte bucket:
-//   slot = [ low (64-b) bits of mix64(key) | disp:3 | ovf:1 | value id:(b-4) ],  empty = ~0.
-// A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 6);
-// the home bucket's slot 0 then carries the ovf mark so that misses stop after one sector otherwise.
+//   slot = [ low (64-b) bits of mix64(key) | disp:4 | novf:1 | value id:(b-5) ],  empty = ~0.
+// A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 14);
+// the home bucket's slot 0 then gets its novf bit CLEARED so that misses stop after one sector otherwise.
 __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__restrict__ keys,
                                   const u32 *__restrict__ vals, u64 n, const u32 *__restrict__ values, u32 n_values,
                                   unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */) {
@@ -682,11 +683,11 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__r
     if(vid == VAL_MISS) { atomicAdd(&stats[2], 1ull); return; }
     const u64 h = mix64(key);
     const u64 home = h >> (64 - b), bmask = (1ull << b) - 1;
-    const u32 tag_shift = b - 3;
+    const u32 tag_shift = b - DISP_BITS;
     const u64 tag = h << b;
-    for(u32 d = 0; d <= 6; ++d) {
+    for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
         u64 *bk = slots + (((home + d) & bmask) << 2);
-        const u64 entry = tag | ((u64)d << tag_shift) | vid;
+        const u64 entry = tag | ((u64)d << tag_shift) | (1ull << (tag_shift - 1)) | vid;
         for(int s = 0; s < 4; ++s) {
             u64 cur = bk[s];
             if(cur == ~0ull) {
@@ -695,7 +696,7 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__r
             }
             if(((cur ^ entry) >> tag_shift) == 0) return;          // same key already present: first value stays
         }
-        if(d == 0) atomicOr((unsigned long long *)&bk[0], 1ull << (tag_shift - 1));
+        if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (tag_shift - 1)));
     }
     atomicAdd(&stats[0], 1ull);
 }
@@ -704,14 +705,14 @@ __global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buck
                                        unsigned long long *__restrict__ out /* [0] entries [1] ovf buckets [2] max disp */) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_buckets) return;
-    const u32 tag_shift = b - 3;
+    const u32 tag_shift = b - DISP_BITS;
     u32 cnt = 0, md = 0;
     for(int s = 0; s < 4; ++s) {
         const u64 v = slots[4 * i + s];
-        if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & 7u)); }
+        if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & ((1u << DISP_BITS) - 1))); }
     }
     if(cnt) atomicAdd(&out[0], (unsigned long long)cnt);
-    if(cnt == 4 && ((slots[4 * i] >> (tag_shift - 1)) & 1ull)) atomicAdd(&out[1], 1ull);
+    if(cnt == 4 && !((slots[4 * i] >> (tag_shift - 1)) & 1ull)) atomicAdd(&out[1], 1ull);
     if(md) atomicMax(&out[2], (unsigned long long)md);
 }
 
@@ -723,7 +724,7 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
     u64 a, b, c, d;
     ld_bucket(T.slots + ((h >> (64 - T.bucket_bits)) << 2), a, b, c, d);
     u32 v = match4(T, h << T.bucket_bits, a, b, c, d);
-    if(v == VAL_MISS && d != ~0ull && (((u32)a >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h);
+    if(v == VAL_MISS && !(((u32)a >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h);
     found_out[i] = v != VAL_MISS;
     vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
 }
@@ -734,12 +735,12 @@ __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u6
     if(i < n) {
         const u32 b = T.bucket_bits;
         const u64 h = mix64(keys[i]), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
-        for(u32 d = 0; d <= 6; ++d) {
+        for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
             u64 a, bb, c, e;
             ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
             ++touched;
             if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
-            if(d == 0 ? !(e != ~0ull && ((a >> (T.tag_shift - 1)) & 1ull)) : (e == ~0ull)) break;
+            if(d == 0 ? (((a >> (T.tag_shift - 1)) & 1ull) != 0) : (e == ~0ull)) break;
         }
     }
     touched = __reduce_add_sync(FULL, touched);

@@ -107,3 +107,70 @@ def make_reads_torch(g, n, seed, device, L=150, frac_random=0.10, sub_rate=0.01,
         out[s * L:(s + m) * L] = rd.reshape(-1)
     offs = torch.arange(n + 1, device=device, dtype=torch.int64) * L
     return out, offs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: HBM-bound lookup stress. DB = canonical 31-mers of a seeded random base stream (n_keys of them,
+# values uniform over the toy taxids), reads = 50 % windows of that stream (every k-mer hits), 50 % random (every
+# k-mer misses), half of all reads reverse-complemented. Everything is produced on the device with torch.
+# ------------------------------------------------------------------------------------------------------------------
+STRESS_VALUES = np.array([10, 11, 12, 13, 20, 2], np.uint32)
+
+
+def _kmers_torch(codes, k, canonical=True):
+    """codes: uint8 tensor of 2-bit codes (length n + k - 1) -> int64 tensor of n k-mers (two's complement view of u64)"""
+    import torch
+    n = codes.numel() - k + 1
+    c64 = codes.to(torch.int64)
+    f = torch.zeros(n, dtype=torch.int64, device=codes.device)
+    for j in range(k):
+        f = (f << 2) | c64[j:j + n]
+    if not canonical:
+        return f
+    r = torch.zeros(n, dtype=torch.int64, device=codes.device)
+    for j in range(k):
+        r = r | ((3 - c64[j:j + n]) << (2 * j))
+    # k <= 31: both are < 2^62, signed compare == unsigned compare
+    return torch.minimum(f, r)
+
+
+def make_stress_db(n_keys, seed, device, k=31, chunk=1 << 25):
+    """-> (stream codes uint8 [n_keys + k - 1] on device, keys int64 [n_keys], vals int32 [n_keys])"""
+    import torch
+    assert k <= 31
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    stream = torch.randint(0, 4, (n_keys + k - 1,), generator=gen, device=device, dtype=torch.uint8)
+    keys = torch.empty(n_keys, dtype=torch.int64, device=device)
+    for s in range(0, n_keys, chunk):
+        m = min(chunk, n_keys - s)
+        keys[s:s + m] = _kmers_torch(stream[s:s + m + k - 1], k)
+    vals_tab = torch.from_numpy(STRESS_VALUES.astype(np.int32)).to(device)
+    vals = vals_tab[(keys % len(STRESS_VALUES)).long()].contiguous()
+    return stream, keys, vals
+
+
+def make_stress_reads(stream, n, seed, device, L=150, frac_db=0.5, frac_rc=0.5, chunk=1 << 20):
+    """-> (bases uint8 ASCII [n*L], offsets int64 [n+1], from_db bool [n])"""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    out = torch.empty(n * L, dtype=torch.uint8, device=device)
+    from_db = torch.empty(n, dtype=torch.bool, device=device)
+    ar = torch.arange(L, device=device)
+    nmax = stream.numel() - L
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        u = torch.rand((3, m), generator=gen, device=device, dtype=torch.float64)
+        start = (u[0] * nmax).long()
+        codes = stream[start[:, None] + ar[None, :]]
+        rnd = torch.randint(0, 4, (m, L), generator=gen, device=device, dtype=torch.uint8)
+        db = u[1] < frac_db
+        codes = torch.where(db[:, None], codes, rnd)
+        rc = (3 - codes).flip(1)
+        codes = torch.where((u[2] < frac_rc)[:, None], rc, codes)
+        out[s * L:(s + m) * L] = acgt[codes.long()].reshape(-1)
+        from_db[s:s + m] = db
+    offs = torch.arange(n + 1, device=device, dtype=torch.int64) * L
+    return out, offs, from_db

@@ -323,3 +323,34 @@ def test_full_size_properties(capi, gpu_dbs, golden, oracle, dbcache, toy_tax):
     n = 20000
     et, eh, em = oracle.classify(dbcache.get("lex_k31_w31"), toy_tax, bases[: int(offs[n])], offs[: n + 1], 31, 31, nthreads=0)
     assert np.array_equal(et, t1[:n]) and np.array_equal(eh, h1[:n]) and np.array_equal(em, m1[:n])
+
+
+def test_stress_device_build_vs_oracle(capi, oracle, toy_tax):
+    """BASELINE config 5 at test scale: table built from device-resident keys, reads cut from the key stream."""
+    import torch
+    from bonsai_b200 import workload as W
+    dev = torch.device("cuda", 0)
+    n_keys = (1 << 20) + 12345
+    stream, d_keys, d_vals = W.make_stress_db(n_keys, seed=5, device=dev)
+    d_bases, d_offs, from_db = W.make_stress_reads(stream, 20000, seed=6, device=dev)
+    c, p = H.toy_tax_arrays()
+    with capi.Context(31, 31) as ctx:
+        ctx.load_pairs_device(d_keys.data_ptr(), d_vals.data_ptr(), n_keys, W.STRESS_VALUES)
+        ctx.load_taxonomy(c, p)
+        info = ctx.table_info()
+        keys = d_keys.cpu().numpy().astype(np.uint64)
+        vals = d_vals.cpu().numpy().astype(np.uint32)
+        assert info["n_keys"] == np.unique(keys).size
+        assert info["n_keys"] / info["n_buckets"] > 0.6
+        gv, gf = ctx.lookup(keys)
+        assert gf.all() and np.array_equal(gv, vals)
+        bases = d_bases.cpu().numpy()
+        offs = d_offs.cpu().numpy().astype(np.uint64)
+        t, h, m = ctx.classify(bases, offs)
+        fd = from_db.cpu().numpy()
+        assert (h[fd] == 120).all() and (h[~fd] == 0).all()
+        uk, ui = np.unique(keys, return_index=True)
+        D = oracle.db_from_pairs(uk, vals[ui])
+        et, eh, em = oracle.classify(D, toy_tax, bases, offs, 31, 31)
+        assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
+        oracle.db_free(D)
