@@ -47,5 +47,26 @@ def build(force=False, verbose=False, out=None, defines=()):
     return out
 
 
+CLI = os.path.join(HERE, "bin", "bonsai")
+CLI_SRC = os.path.join(CSRC, "cli", "bonsai_main.cpp")
+CLI_DEPS = [CLI_SRC, os.path.join(HERE, "..", "include", "bonsai_b200", "bonsai.hpp"), os.path.join(HERE, "..", "include", "bonsai_b200.h")]
+
+
+def build_cli(force=False):
+    """g++ the `bonsai` CLI (host C++ over the C ABI), linked against the in-tree library with an $ORIGIN rpath."""
+    build()
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in CLI_DEPS + [LIB]):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", CLI, CLI_SRC, "-L" + HERE, "-lbonsai_b200", "-lz",
+           "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building the bonsai CLI")
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))

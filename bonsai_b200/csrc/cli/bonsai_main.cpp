@@ -1,0 +1,200 @@
+// bonsai (B200) -- the `classify` subcommand of bin/bonsai.cpp:107-163 with its flag letters, over libbonsai_b200.so.
+// Also: `build` (a working replacement for the reference's broken phase2/build, SURVEY App. B-1/B-6: GPU encoder +
+// update_lca_map merge -> the DB file layout the reference intends), `dbwrite` / `dbcheck` (DB file tooling).
+#include <getopt.h>
+
+#include <map>
+#include <set>
+
+#include "../../../include/bonsai_b200/bonsai.hpp"
+
+using namespace bns;
+
+static int classify_usage(const char *ex) {
+    std::fprintf(stderr,
+                 "Usage:\n%s classify <opts> <dbpath> <tax_path> <inr1.fq> <inr2.fq>\nFlags:\n"
+                 "-o:\tRedirect output to path instead of stdout.\n-c:\tSet chunk size [1048576 bases]\n"
+                 "-a:\tEmit all records, not just classified.\n-p:\tSet number of threads. Default: 1.\n"
+                 "-k:\tEmit kraken-style output.\n-K:\tDo not emit kraken-style output.\n-f:\tEmit fastq-style output.\n"
+                 "-F:\tDo not emit fastq-style output.\n-C:\tDo not canonicalize.\n-S:\tSet records per worker set (ignored: one GPU call per chunk)\n",
+                 ex);
+    return EXIT_FAILURE;
+}
+
+// classify_main, bin/bonsai.cpp:107-163
+static int classify_main(int argc, char *argv[]) {
+    int co, num_threads(1), emit_kraken(1), emit_fastq(0), emit_all(0), chunk_size(1 << 20), per_set(32);
+    bool canonicalize(true);
+    std::FILE *ofp(stdout);
+    if(argc < 4) return classify_usage(argv[0]);
+    while((co = getopt(argc, argv, "Cc:p:o:S:afFkKh?")) >= 0) {
+        switch(co) {
+            case 'h': case '?': return classify_usage(argv[0]);
+            case 'a': emit_all = 1; break;
+            case 'C': canonicalize = false; break;
+            case 'c': chunk_size = std::atoi(optarg); break;
+            case 'F': emit_fastq = 0; break;
+            case 'f': emit_fastq = 1; break;
+            case 'K': emit_kraken = 0; break;
+            case 'k': emit_kraken = 1; break;
+            case 'p': num_threads = std::atoi(optarg); break;
+            case 'S': per_set = std::atoi(optarg); break;
+            case 'o': ofp = std::fopen(optarg, "w"); if(!ofp) { std::fprintf(stderr, "Could not open %s\n", optarg); return EXIT_FAILURE; } break;
+        }
+    }
+    if(argc - optind < 3) return classify_usage(argv[0]);
+    try {
+        Database db(argv[optind]);
+        // bin/bonsai.cpp:152: always score::Lex with window = k, whatever the DB was minimised with
+        Classifier c(db, db.s_, (u8)db.k_, (u16)db.k_, num_threads, emit_all, emit_fastq, emit_kraken, canonicalize);
+        std::unique_ptr<TaxMap> taxmap(build_parent_map(argv[optind + 1]));
+        const char *fq2 = (argc - optind >= 4) ? argv[optind + 3] : nullptr;
+        process_dataset(c, taxmap.get(), argv[optind + 2], fq2, ofp, (unsigned)chunk_size, (unsigned)per_set);
+        std::fprintf(stderr, "Successfully finished classify_main. classified %" PRIu64 ", unclassified %" PRIu64 "\n",
+                     c.n_classified(), c.n_unclassified());
+    } catch(const std::exception &e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return EXIT_FAILURE;
+    }
+    if(ofp != stdout) std::fclose(ofp);
+    return EXIT_SUCCESS;
+}
+
+// lca, util.h:634-663 over a std::map child -> parent
+static tax_t lca(const std::map<tax_t, tax_t> &pm, tax_t a, tax_t b) {
+    if(a == b) return a;
+    if(b == 0) return a;
+    if(a == 0) return b;
+    std::vector<tax_t> nodes;
+    while(a) {
+        nodes.push_back(a);
+        auto it = pm.find(a);
+        if(it == pm.end()) return tax_t(-1);
+        a = it->second;
+    }
+    while(b) {
+        if(std::find(nodes.begin(), nodes.end(), b) != nodes.end()) return b;
+        auto it = pm.find(b);
+        if(it == pm.end()) return tax_t(-1);
+        b = it->second;
+    }
+    return 1;
+}
+
+static int build_usage(const char *ex) {
+    std::fprintf(stderr,
+                 "Usage:\n%s build <opts> <dbpath> <tax_path> <taxid=genome.fa[.gz]> ...\nFlags:\n-k:\tk-mer length [31]\n"
+                 "-w:\twindow size [k]\n-s:\tspacing string, e.g. 1x3,0x5 [unspaced]\n-e:\tminimise by entropy instead of Lex\n"
+                 "-C:\tDo not canonicalize\n-z:\tgzip the database\n", ex);
+    return EXIT_FAILURE;
+}
+
+// fill_set_genome + update_lca_map (feature_min.h:68-83,205-228) with the GPU encoder, then Database::write
+template <typename Score>
+static void build_sets(const Spacer &sp, bool canon, const std::vector<std::pair<tax_t, std::string>> &genomes,
+                       const std::map<tax_t, tax_t> &pm, std::map<u64, tax_t> &kc) {
+    Encoder<Score> enc(sp, canon);
+    for(const auto &g : genomes) {
+        std::set<u64> kmers;
+        enc.for_each([&](u64 x) { kmers.insert(x); }, g.second.c_str());
+        for(const u64 x : kmers) {
+            auto it = kc.find(x);
+            if(it == kc.end()) kc.emplace(x, g.first);
+            else if(it->second != g.first) it->second = lca(pm, g.first, it->second);
+        }
+        std::fprintf(stderr, "[build] %s (taxid %u): %zu distinct k-mers, database now %zu\n", g.second.c_str(), g.first, kmers.size(), kc.size());
+    }
+}
+
+static int build_main(int argc, char *argv[]) {
+    int co, k(31), w(-1);
+    bool canon(true), entropy(false), gz(false);
+    std::string spacing;
+    while((co = getopt(argc, argv, "k:w:s:eCzh?")) >= 0) {
+        switch(co) {
+            case 'k': k = std::atoi(optarg); break;
+            case 'w': w = std::atoi(optarg); break;
+            case 's': spacing = optarg; break;
+            case 'e': entropy = true; break;
+            case 'C': canon = false; break;
+            case 'z': gz = true; break;
+            default: return build_usage(argv[0]);
+        }
+    }
+    if(argc - optind < 3) return build_usage(argv[0]);
+    try {
+        const spvec_t gaps = parse_spacing(spacing.c_str(), k);
+        Spacer sp(k, w < 0 ? k : w, gaps);
+        std::unique_ptr<TaxMap> tm(build_parent_map(argv[optind + 1]));
+        std::map<tax_t, tax_t> pm;
+        for(size_t i = 0; i < tm->size(); ++i) pm[tm->child[i]] = tm->parent[i];
+        std::vector<std::pair<tax_t, std::string>> genomes;
+        for(int i = optind + 2; i < argc; ++i) {
+            const char *eq = std::strchr(argv[i], '=');
+            if(!eq) { std::fprintf(stderr, "expected taxid=path, got %s\n", argv[i]); return EXIT_FAILURE; }
+            genomes.emplace_back((tax_t)std::atoi(argv[i]), std::string(eq + 1));
+        }
+        std::map<u64, tax_t> kc;
+        if(entropy) build_sets<score::Entropy>(sp, canon, genomes, pm, kc);
+        else build_sets<score::Lex>(sp, canon, genomes, pm, kc);
+        std::vector<u64> keys; std::vector<u32> vals;
+        keys.reserve(kc.size()); vals.reserve(kc.size());
+        for(const auto &kv : kc) { keys.push_back(kv.first); vals.push_back(kv.second); }
+        Database db;
+        db.assign(k, sp.w_, gaps, keys.data(), vals.data(), keys.size());
+        db.write(argv[optind], gz);
+        std::fprintf(stderr, "[build] wrote %s: k=%d w=%u keys=%zu buckets=%" PRIu64 "\n", argv[optind], k, sp.w_, keys.size(), db.n_buckets);
+    } catch(const std::exception &e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
+// dbwrite <out.db> <k> <w> <pairs.bin>: pairs.bin = u64 n, u64 keys[n], u32 vals[n]   (host only)
+static int dbwrite_main(int argc, char *argv[]) {
+    if(argc < 6) { std::fprintf(stderr, "Usage: %s dbwrite <out.db> <k> <w> <pairs.bin> [gz]\n", argv[0]); return EXIT_FAILURE; }
+    try {
+        std::FILE *fp = std::fopen(argv[5], "rb");
+        if(!fp) BNS_RUNTIME_ERROR("cannot open pairs file");
+        u64 n = 0;
+        if(std::fread(&n, 8, 1, fp) != 1) BNS_RUNTIME_ERROR("short pairs file");
+        std::vector<u64> keys(n); std::vector<u32> vals(n);
+        if(n && (std::fread(keys.data(), 8, n, fp) != n || std::fread(vals.data(), 4, n, fp) != n)) BNS_RUNTIME_ERROR("short pairs file");
+        std::fclose(fp);
+        Database db;
+        db.assign(std::atoi(argv[3]), std::atoi(argv[4]), spvec_t{}, keys.data(), vals.data(), n);
+        db.write(argv[2], argc > 6);
+    } catch(const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+}
+
+// dbcheck <db>: header + xor/sum digests of the occupied (key, value) pairs   (host only)
+static int dbcheck_main(int argc, char *argv[]) {
+    if(argc < 3) { std::fprintf(stderr, "Usage: %s dbcheck <db>\n", argv[0]); return EXIT_FAILURE; }
+    try {
+        Database db(argv[2]);
+        u64 n = 0, kx = 0, ks = 0, vs = 0;
+        for(u64 i = 0; i < db.n_buckets; ++i)
+            if(db.exists(i)) { ++n; kx ^= db.keys[i]; ks += db.keys[i]; vs += db.vals[i]; }
+        std::printf("k=%u w=%u n_buckets=%" PRIu64 " size=%" PRIu64 " occupied=%" PRIu64 " key_xor=%016" PRIx64 " key_sum=%016" PRIx64 " val_sum=%" PRIu64 "\n",
+                    db.k_, db.w_, db.n_buckets, db.size, n, kx, ks, vs);
+    } catch(const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+}
+
+static int usage(const char *ex) {
+    std::fprintf(stderr, "Usage: %s <subcommand> [options...]. Use %s <subcommand> for more options.\n"
+                         "Subcommands:\nclassify\nbuild\ndbwrite\ndbcheck\n", ex, ex);
+    return EXIT_FAILURE;
+}
+
+int main(int argc, char *argv[]) {                          // bin/bonsai.cpp:521-540
+    if(argc < 2) return usage(argv[0]);
+    const std::string cmd(argv[1]);
+    if(cmd == "classify") return classify_main(argc - 1, argv + 1);
+    if(cmd == "build" || cmd == "phase2" || cmd == "p2") return build_main(argc - 1, argv + 1);
+    if(cmd == "dbwrite") return dbwrite_main(argc, argv);
+    if(cmd == "dbcheck") return dbcheck_main(argc, argv);
+    return usage(argv[0]);
+}

@@ -1,0 +1,545 @@
+// bonsai.hpp -- the reference's C++ surface for the classify path, re-created over the B200 C ABI.
+//
+// Same names, argument meaning and error behaviour as dnbaker/bonsai @ 6741de9c (paths below are in that tree):
+//   bns::Spacer, parse_spacing            include/bonsai/spacer.h:29-71
+//   bns::Encoder<Score>::for_each         include/bonsai/encoder.h:416 (string overload) / :448-530 (record overloads)
+//   bns::Database                         include/bonsai/database.h:17-102 (file layout as the reference INTENDS it)
+//   bns::build_parent_map                 include/bonsai/util.h:766-785
+//   bns::ClassifierGeneric, classify_seqs, process_dataset, bseq1_t, the Kraken/FASTQ emitters
+//                                         include/bonsai/classifier.h:23-337, include/bonsai/kseq_declare.h:40-175
+// All k-mer / lookup / resolve work happens in libbonsai_b200.so on the GPU; this header is host plumbing and
+// text formatting only. There is no CPU fallback: constructing an Encoder or ClassifierGeneric without a CUDA
+// device throws std::runtime_error (the reference's RUNTIME_ERROR convention, util.h:540-551).
+#pragma once
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cinttypes>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+#include "../bonsai_b200.h"
+
+namespace bns {
+
+using u8 = std::uint8_t;
+using u16 = std::uint16_t;
+using u32 = std::uint32_t;
+using u64 = std::uint64_t;
+using tax_t = u32;
+using spvec_t = std::vector<u16>;
+
+#define BNS_RUNTIME_ERROR(msg) throw std::runtime_error(std::string("[") + __FILE__ + ":" + std::to_string(__LINE__) + "] " + (msg))
+
+// ---- Spacer ----------------------------------------------------------------------------------------------------
+inline u32 comb_size(const spvec_t &spaces) {                       // spacer.h:14-19
+    u32 ret(spaces.size() + 1);
+    for(const auto i : spaces) ret += i;
+    return ret;
+}
+inline spvec_t parse_spacing(const char *sss, unsigned k) {         // spacer.h:29-47, "1x3,0x5" syntax
+    char *ss = const_cast<char *>(sss);
+    if(!ss || *ss == '\0') return spvec_t(k - 1, 0);
+    spvec_t ret;
+    for(; *ss; ++ss) {
+        const int j = std::strtoul(ss, &ss, 10);
+        ret.emplace_back(j);
+        if(*ss == 'x') {
+            ss = std::strchr(ss, 'x') + 1;
+            auto n = std::max(int(std::strtoul(ss, &ss, 10)) - 1, 0);
+            if(n > 0) ret.insert(ret.end(), n, j);
+        }
+        ss = std::strchr(ss, ',');
+        if(!ss) break;
+    }
+    return ret;
+}
+struct Spacer {
+    spvec_t s_;        // offsets (gap + 1), spacer.h:65
+    u32 k_, c_, w_;
+    Spacer(unsigned k, u32 w, spvec_t spaces = spvec_t{})
+        : s_(spaces.size() ? spaces : spvec_t(k - 1, 0)), k_(k), c_(comb_size(s_)), w_(std::max((int)c_, (int)w)) {
+        for(auto &i : s_) ++i;
+        if(s_.size() + 1 != k) BNS_RUNTIME_ERROR("Error: input vector must have size 1 less than k.");
+    }
+    Spacer(unsigned k, u32 w, const char *space_string) : Spacer(k, w, parse_spacing(space_string, k)) {}
+    explicit Spacer(unsigned k) : Spacer(k, k) {}
+    u32 k() const { return k_; }
+    u32 w() const { return w_; }
+    u32 c() const { return c_; }
+    bool unspaced() const { return std::all_of(s_.begin(), s_.end(), [](u16 x) { return x == 1; }); }
+    bool unwindowed() const { return k_ == w_; }
+    spvec_t sub1() const { spvec_t r(s_); for(auto &x : r) --x; return r; }            // spacer.h:173
+    std::string to_string(u64 kmer) const {                                             // spacer.h:127-139
+        std::string ret;
+        int offset = ((k_ - 1) << 1);
+        ret.push_back("ACGT"[(kmer >> offset) & 0x3u]);
+        for(auto s : s_) {
+            offset -= 2;
+            while(s-- > 1) ret.push_back('-');
+            ret.push_back("ACGT"[(kmer >> offset) & 0x3u]);
+        }
+        return ret;
+    }
+};
+
+namespace score {
+struct Lex { static constexpr u32 id = BNS_SCORE_LEX; };
+struct Entropy { static constexpr u32 id = BNS_SCORE_ENTROPY; };
+}  // namespace score
+
+namespace detail {
+struct Handle {                        // RAII over bns_b200_t
+    bns_b200_t *h = nullptr;
+    Handle() = default;
+    Handle(const Handle &) = delete;
+    Handle &operator=(const Handle &) = delete;
+    ~Handle() { if(h) bns_b200_close(h); }
+};
+inline std::shared_ptr<Handle> open_handle(const Spacer &sp, u32 score, bool canon, u32 api, int device = -1) {
+    bns_b200_config cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.k = sp.k_; cfg.w = sp.w_;
+    const spvec_t gaps = sp.sub1();
+    std::copy(gaps.begin(), gaps.end(), cfg.gaps);
+    cfg.score = score; cfg.canonicalize = canon; cfg.api = api; cfg.device = device;
+    // the reference's entropy score casts a negative double to u64: do what THIS host's reference build would do
+    volatile double probe = -5.5;
+    cfg.entropy_cast = ((u64)probe == ~u64(0)) ? BNS_CAST_SATURATE : BNS_CAST_WRAP;
+    auto ret = std::make_shared<Handle>();
+    const int rc = bns_b200_open(&cfg, &ret->h);
+    if(rc) BNS_RUNTIME_ERROR(std::string("bns_b200_open: ") + bns_b200_last_error(nullptr));
+    return ret;
+}
+inline void check(bns_b200_t *h, int rc, const char *what) {
+    if(rc) BNS_RUNTIME_ERROR(std::string(what) + ": " + bns_b200_last_error(h));
+}
+
+// minimal kseq: FASTA/FASTQ records over gzread (klib/kseq.h:178 semantics: name up to the first space, comment the
+// rest of the header line, sequence lines concatenated, optional '+' quality)
+struct KSeq {
+    gzFile fp = nullptr;
+    std::vector<unsigned char> buf;
+    size_t pos = 0, end = 0;
+    bool eof = false;
+    int last_char = 0;
+    std::string name, comment, seq, qual;
+    explicit KSeq(const char *path) : buf(1 << 18) {
+        fp = gzopen(path, "rb");
+        if(!fp) BNS_RUNTIME_ERROR(std::string("Could not open file at ") + path);
+        gzbuffer(fp, 1 << 18);
+    }
+    ~KSeq() { if(fp) gzclose(fp); }
+    int getc_() {
+        if(pos >= end) {
+            if(eof) return -1;
+            const int n = gzread(fp, buf.data(), (unsigned)buf.size());
+            if(n <= 0) { eof = true; return -1; }
+            pos = 0; end = (size_t)n;
+        }
+        return buf[pos++];
+    }
+    // ks_getuntil: append bytes up to (not including) a delimiter (SEP_SPACE: isspace, SEP_LINE: newline, with a
+    // trailing CR stripped). Returns the number of bytes appended, or -1 at end of file with nothing read.
+    enum { SEP_SPACE = 0, SEP_LINE = 1 };
+    long getuntil(int delim, std::string &out, bool append, int *dret) {
+        if(!append) out.clear();
+        const size_t before = out.size();
+        bool got_any = false;
+        int c;
+        while((c = getc_()) >= 0) {
+            got_any = true;
+            if(delim == SEP_SPACE ? std::isspace(c) : c == '\n') break;
+            out.push_back((char)c);
+        }
+        if(!got_any) return -1;
+        if(delim == SEP_LINE && out.size() > before && out.back() == '\r') out.pop_back();
+        if(dret) *dret = c;
+        return (long)(out.size() - before);
+    }
+    // kseq_read (klib/kseq.h:178-217): >= 0 sequence length; -1 end of file; -2 truncated quality string
+    long read() {
+        int c;
+        if(last_char == 0) {                                   // jump to the next header line
+            while((c = getc_()) >= 0 && c != '>' && c != '@') {}
+            if(c < 0) return -1;
+            last_char = c;
+        }
+        comment.clear(); seq.clear(); qual.clear();
+        if(getuntil(SEP_SPACE, name, false, &c) < 0) return -1;
+        if(c != '\n') getuntil(SEP_LINE, comment, false, nullptr);
+        while((c = getc_()) >= 0 && c != '>' && c != '+' && c != '@') {
+            if(c == '\n') continue;                            // skip empty lines
+            seq.push_back((char)c);
+            getuntil(SEP_LINE, seq, true, nullptr);            // the rest of the line
+        }
+        if(c == '>' || c == '@') last_char = c;                // the first header char has been read
+        if(c != '+') return (long)seq.size();                  // FASTA
+        while((c = getc_()) >= 0 && c != '\n') {}              // skip the rest of the '+' line
+        if(c < 0) return -2;
+        while(qual.size() < seq.size() && getuntil(SEP_LINE, qual, true, nullptr) >= 0) {}
+        last_char = 0;
+        if(seq.size() != qual.size()) return -2;
+        return (long)seq.size();
+    }
+};
+}  // namespace detail
+
+// ---- Encoder ---------------------------------------------------------------------------------------------------
+// Encoder<Score>: borrows the string, calls fn(kmer) synchronously and in stream order (encoder.h:416). Not
+// thread-safe, one copy per worker (classifier.h:258). Copies share the device context.
+template <typename ScoreType = score::Lex>
+class Encoder {
+    std::shared_ptr<detail::Handle> str_, path_;       // lazily opened contexts for the two overload families
+    bool canonicalize_;
+    std::vector<u64> kmers_;
+    detail::Handle *get(bool path_api) {
+        auto &p = path_api ? path_ : str_;
+        if(!p) p = detail::open_handle(sp_, ScoreType::id, canonicalize_, path_api ? BNS_API_PATH : BNS_API_STRING);
+        return p.get();
+    }
+    template <typename F>
+    void run(const F &fn, const char *str, u64 l, bool path_api) {
+        bns_b200_t *h = get(path_api)->h;
+        const u64 offs[2] = {0, l};
+        const u64 bound = bns_b200_encode_bound(h, l);
+        const u64 ooffs[2] = {0, bound};
+        kmers_.resize(bound + 1);
+        u32 count = 0;
+        detail::check(h, bns_b200_encode_batch(h, str, offs, 1, kmers_.data(), ooffs, &count), "bns_b200_encode_batch");
+        for(u32 i = 0; i < count; ++i) fn(kmers_[i]);
+    }
+public:
+    Spacer sp_;
+    static constexpr u64 ENCODE_OVERFLOW = ~u64(0);
+    Encoder(const Spacer &sp, bool canonicalize = true) : canonicalize_(canonicalize && sp.unspaced()), sp_(sp) {}   // encoder.h:148-150
+    explicit Encoder(unsigned k, bool canonicalize = true) : Encoder(Spacer(k), canonicalize) {}
+    bool canonicalize() const { return canonicalize_; }
+    u32 k() const { return sp_.k_; }
+    // Encoder::for_each(fn, str, l), encoder.h:416-442
+    template <typename F> void for_each(const F &fn, const char *str, u64 l) { run(fn, str, l, false); }
+    // for_each_canon / for_each_uncanon on one record, encoder.h:448-464
+    template <typename F> void for_each_record(const F &fn, const char *str, u64 l) { run(fn, str, l, true); }
+    // for_each(fn, path), encoder.h:511-530: every record of a FASTA/FASTQ(.gz) file through the record overloads
+    template <typename F> void for_each(const F &fn, const char *path) {
+        detail::KSeq ks(path);
+        while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
+    }
+    // batched form of the string overload: fn(sequence index, kmer)
+    template <typename F> void for_each_batch(const F &fn, const char *bases, const u64 *offsets, u64 n) {
+        bns_b200_t *h = get(false)->h;
+        std::vector<u64> oo(n + 1, 0);
+        for(u64 i = 0; i < n; ++i) oo[i + 1] = oo[i] + bns_b200_encode_bound(h, offsets[i + 1] - offsets[i]);
+        kmers_.resize(oo[n] + 1);
+        std::vector<u32> counts(n);
+        detail::check(h, bns_b200_encode_batch(h, bases, offsets, n, kmers_.data(), oo.data(), counts.data()), "bns_b200_encode_batch");
+        for(u64 i = 0; i < n; ++i) for(u32 j = 0; j < counts[i]; ++j) fn(i, kmers_[oo[i] + j]);
+    }
+};
+
+// ---- taxonomy --------------------------------------------------------------------------------------------------
+struct TaxMap { std::vector<tax_t> child, parent; size_t size() const { return child.size(); } };
+inline TaxMap *build_parent_map(const char *fn) {                   // util.h:766-785
+    std::FILE *fp = std::fopen(fn, "r");
+    if(!fp) BNS_RUNTIME_ERROR(std::string("Failed to create taxmap from ") + fn);
+    auto ret = std::make_unique<TaxMap>();
+    char *line = nullptr; size_t cap = 0; ssize_t len;
+    while((len = getline(&line, &cap, fp)) >= 0) {
+        if(len && line[len - 1] == '\n') line[len - 1] = 0;
+        switch(line[0]) { case '\n': case '\0': case '#': continue; }
+        const char *p = std::strchr(line, '|');
+        ret->child.push_back((tax_t)std::atoi(line));
+        ret->parent.push_back(p ? (tax_t)std::atoi(p + 2) : tax_t(-1));
+    }
+    std::free(line);
+    std::fclose(fp);
+    ret->child.push_back(1); ret->parent.push_back(0);             // "Root of the tree"
+    if(ret->size() < 2) BNS_RUNTIME_ERROR(std::string("Failed to create taxmap from ") + fn);
+    return ret.release();
+}
+
+// ---- Database --------------------------------------------------------------------------------------------------
+// File layout the reference intends (database.h:81-102 + khash_write_impl util.h:281-296):
+//   u32 k, u32 w, (k-1) x u8 gaps, u64 n_buckets, u64 n_occupied, u64 size, u64 upper_bound,
+//   u32 flags[max(1, n_buckets/16)], u64 keys[n_buckets], u32 vals[n_buckets]          (little endian, no padding)
+// i.e. the raw khash_t(c) arrays (Wang64 hash, triangular probing, 2 flag bits per bucket, khash64.h:169-263).
+struct Database {
+    u32 k_ = 0, w_ = 0;
+    spvec_t s_;                                  // gaps (before the Spacer's +1)
+    u64 n_buckets = 0, n_occupied = 0, size = 0, upper_bound = 0;
+    std::vector<u32> flags;
+    std::vector<u64> keys;
+    std::vector<u32> vals;
+
+    static u64 wang64(u64 key) {                 // khash64.h:202-211
+        key = (~key) + (key << 21); key = key ^ (key >> 24);
+        key = (key + (key << 3)) + (key << 8); key = key ^ (key >> 14);
+        key = (key + (key << 2)) + (key << 4); key = key ^ (key >> 28);
+        return key + (key << 31);
+    }
+    bool exists(u64 i) const { return ((flags[i >> 4] >> ((i & 0xfU) << 1)) & 3u) == 0; }
+    Database() = default;
+    explicit Database(const char *path) {        // database.h:33-56 (with the fread / popen defects of App. B-1 not reproduced)
+        gzFile fp = gzopen(path, "rb");
+        if(!fp) BNS_RUNTIME_ERROR(std::string("Could not open database at ") + path);
+        auto rd = [&](void *p, size_t n) {
+            size_t got = 0;
+            while(got < n) {
+                const unsigned want = (unsigned)std::min<size_t>(n - got, 1u << 30);
+                const int r = gzread(fp, (char *)p + got, want);
+                if(r <= 0) { gzclose(fp); BNS_RUNTIME_ERROR("Could not read from database file"); }
+                got += (size_t)r;
+            }
+        };
+        rd(&k_, 4); rd(&w_, 4);
+        if(k_ < 1 || k_ > 32) { gzclose(fp); BNS_RUNTIME_ERROR("database: bad k"); }
+        std::vector<u8> g(k_ - 1);
+        if(k_ > 1) rd(g.data(), k_ - 1);
+        s_.assign(g.begin(), g.end());
+        rd(&n_buckets, 8); rd(&n_occupied, 8); rd(&size, 8); rd(&upper_bound, 8);
+        flags.resize(n_buckets < 16 ? 1 : n_buckets >> 4);
+        keys.resize(n_buckets); vals.resize(n_buckets);
+        rd(flags.data(), flags.size() * 4);
+        if(n_buckets) { rd(keys.data(), n_buckets * 8); rd(vals.data(), n_buckets * 4); }
+        gzclose(fp);
+    }
+    // build the khash arrays from distinct (key, value) pairs: kh_resize to hold n at load <= 0.77, then kh_put each
+    void assign(u32 k, u32 w, const spvec_t &gaps, const u64 *ks, const u32 *vs, u64 n) {
+        k_ = k; w_ = w; s_ = gaps.size() ? gaps : spvec_t(k - 1, 0);
+        n_buckets = 4;
+        while((u64)(n_buckets * 0.77 + 0.5) <= n) n_buckets <<= 1;
+        upper_bound = (u64)(n_buckets * 0.77 + 0.5);
+        flags.assign(n_buckets < 16 ? 1 : n_buckets >> 4, 0xaaaaaaaau);
+        keys.assign(n_buckets, 0); vals.assign(n_buckets, 0);
+        const u64 mask = n_buckets - 1;
+        size = 0;
+        for(u64 j = 0; j < n; ++j) {
+            u64 i = wang64(ks[j]) & mask, step = 0;
+            while(exists(i) && keys[i] != ks[j]) i = (i + (++step)) & mask;
+            if(!exists(i)) { flags[i >> 4] &= ~(3u << ((i & 0xfU) << 1)); keys[i] = ks[j]; ++size; }
+            vals[i] = vs[j];
+        }
+        n_occupied = size;
+    }
+    void write(const char *fn, bool write_gz = false) const {        // database.h:81-102
+        auto fail = [&]() { BNS_RUNTIME_ERROR(std::string("Error writing database to ") + fn); };
+        std::vector<u8> g(s_.begin(), s_.end());
+        g.resize(k_ ? k_ - 1 : 0, 0);
+        if(write_gz) {
+            gzFile fp = gzopen(fn, "wb");
+            if(!fp) fail();
+            auto wr = [&](const void *p, size_t n) {
+                size_t put = 0;
+                while(put < n) {
+                    const int r = gzwrite(fp, (const char *)p + put, (unsigned)std::min<size_t>(n - put, 1u << 30));
+                    if(r <= 0) { gzclose(fp); fail(); }
+                    put += (size_t)r;
+                }
+            };
+            wr(&k_, 4); wr(&w_, 4); if(!g.empty()) wr(g.data(), g.size());
+            wr(&n_buckets, 8); wr(&n_occupied, 8); wr(&size, 8); wr(&upper_bound, 8);
+            wr(flags.data(), flags.size() * 4); wr(keys.data(), keys.size() * 8); wr(vals.data(), vals.size() * 4);
+            gzclose(fp);
+            return;
+        }
+        std::FILE *fp = std::fopen(fn, "wb");
+        if(!fp) fail();
+        auto wr = [&](const void *p, size_t n) { if(n && std::fwrite(p, 1, n, fp) != n) { std::fclose(fp); fail(); } };
+        wr(&k_, 4); wr(&w_, 4); wr(g.data(), g.size());
+        wr(&n_buckets, 8); wr(&n_occupied, 8); wr(&size, 8); wr(&upper_bound, 8);
+        wr(flags.data(), flags.size() * 4); wr(keys.data(), keys.size() * 8); wr(vals.data(), vals.size() * 4);
+        std::fclose(fp);
+    }
+};
+
+// ---- reads -----------------------------------------------------------------------------------------------------
+struct bseq1_t {                                  // kseq_declare.h:40-44 (strings own their storage here)
+    int l_seq = 0, id = 0;
+    std::string name, comment, seq, qual, sam;
+};
+inline void trim_readno(std::string &s) {         // kseq_declare.h:106-110
+    if(s.size() > 2 && s[s.size() - 2] == '/' && std::isdigit((unsigned char)s.back())) s.resize(s.size() - 2);
+}
+// bseq_read, kseq_declare.h:112-145: records until the batch holds >= chunk_size BASES (and an even count)
+inline bool bseq_read(int chunk_size, std::vector<bseq1_t> &seqs, detail::KSeq *ks, detail::KSeq *ks2) {
+    seqs.clear();
+    long size = 0;
+    auto take = [&](detail::KSeq *k) {
+        seqs.emplace_back();
+        bseq1_t &s = seqs.back();
+        trim_readno(k->name);
+        s.name = k->name; s.comment = k->comment; s.seq = k->seq; s.qual = k->qual;
+        s.l_seq = (int)s.seq.size(); s.id = (int)seqs.size() - 1;
+        size += s.l_seq;
+    };
+    while(ks->read() >= 0) {
+        if(ks2 && ks2->read() < 0) { std::fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", __func__); break; }
+        take(ks);
+        if(ks2) take(ks2);
+        if(size >= chunk_size && (seqs.size() & 1) == 0) break;
+    }
+    if(size == 0 && ks2 && ks2->read() >= 0) std::fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", __func__);
+    return !seqs.empty();
+}
+
+// ---- classifier ------------------------------------------------------------------------------------------------
+enum output_format : int { KRAKEN = 1, FASTQ = 2, EMIT_ALL = 4 };   // classifier.h:23-27
+
+template <typename ScoreType>
+struct ClassifierGeneric {
+    const Spacer sp_;
+    Encoder<ScoreType> enc_;
+    u32 nt_ : 16;
+    u32 output_flag_ : 16;
+    std::shared_ptr<detail::Handle> h_;
+    bool tax_loaded_ = false;
+    void set_emit_all(bool s) { if(s) output_flag_ |= EMIT_ALL; else output_flag_ &= ~EMIT_ALL; }
+    void set_emit_kraken(bool s) { if(s) output_flag_ |= KRAKEN; else output_flag_ &= ~KRAKEN; }
+    void set_emit_fastq(bool s) { if(s) output_flag_ |= FASTQ; else output_flag_ &= ~FASTQ; }
+    int get_emit_all() const { return output_flag_ & EMIT_ALL; }
+    int get_emit_kraken() const { return output_flag_ & KRAKEN; }
+    int get_emit_fastq() const { return output_flag_ & FASTQ; }
+    // classifier.h:155-166; `map` = the database whose raw khash arrays go to the device
+    ClassifierGeneric(const Database &map, const spvec_t &spaces, u8 k, u16 wsz, int num_threads = 16, bool emit_all = true,
+                      bool emit_fastq = true, bool emit_kraken = false, bool canonicalize = true)
+        : sp_(k, wsz, spaces), enc_(sp_, canonicalize), nt_(num_threads > 0 ? (u16)num_threads : (u16)1), output_flag_(0) {
+        set_emit_all(emit_all); set_emit_fastq(emit_fastq); set_emit_kraken(emit_kraken);
+        h_ = detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING);
+        detail::check(h_->h, bns_b200_load_table(h_->h, map.keys.data(), map.vals.data(), map.flags.data(), map.n_buckets),
+                      "bns_b200_load_table");
+    }
+    void load_taxonomy(const TaxMap *t) {
+        detail::check(h_->h, bns_b200_load_taxonomy(h_->h, t->child.data(), t->parent.data(), t->size()), "bns_b200_load_taxonomy");
+        tax_loaded_ = true;
+    }
+    u64 n_classified() const { bns_b200_stats s; bns_b200_stats_get(h_->h, &s); return s.n_classified; }      // classifier.h:170
+    u64 n_unclassified() const { bns_b200_stats s; bns_b200_stats_get(h_->h, &s); return s.n_unclassified; }  // :171
+};
+using Classifier = ClassifierGeneric<score::Lex>;
+
+namespace detail {
+inline void put_u(std::string &s, u32 x) { char b[16]; s.append(b, std::snprintf(b, sizeof b, "%u", x)); }
+inline void put_i(std::string &s, long x) { char b[32]; s.append(b, std::snprintf(b, sizeof b, "%ld", x)); }
+inline void append_taxa_run(tax_t last, u32 run, std::string &s) {                // classifier.h:30-43
+    if(last == 0) s.push_back('U'); else if(last == (tax_t)-1) s.push_back('A'); else put_u(s, last);
+    s.push_back(':'); put_u(s, run); s.push_back('\t');
+}
+inline void append_taxa_runs(tax_t taxon, const tax_t *taxa, u32 n, std::string &s) {   // :46-61
+    if(taxon) {
+        tax_t last = taxa[0]; u32 run = 1;
+        for(u32 i = 1; i != n; ++i) {
+            if(taxa[i] == last) ++run;
+            else { append_taxa_run(last, run, s); last = taxa[i]; run = 1; }
+        }
+        append_taxa_run(last, run, s);
+        s.back() = '\n';
+    } else s.append("0:0\n", 4);
+}
+inline void append_counts(u32 count, char ch, std::string &s) {                   // :63-70
+    if(count) { s.push_back(ch); s.push_back(':'); put_u(s, count); s.push_back('\t'); }
+}
+inline void append_kraken_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
+                                         const bseq1_t *bs, std::string &s) {      // :112-129
+    s.push_back(taxon ? 'C' : 'U'); s.push_back('\t');
+    s += bs->name; s.push_back('\t');
+    put_u(s, taxon); s.push_back('\t');
+    put_i(s, bs->l_seq); s.push_back('\t');
+    append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
+    append_taxa_runs(taxon, taxa, ntaxa, s);
+}
+inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
+                                        const bseq1_t *bs, std::string &s, int verbose, int is_paired) {   // :72-108
+    s += bs->name; s.push_back(' ');
+    const size_t cms = s.size();
+    s.push_back(taxon == 0 ? 'U' : 'C'); s.push_back('\t');
+    put_u(s, taxon); s.push_back('\t');
+    put_i(s, bs->l_seq); s.push_back('\t');
+    append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
+    if(verbose) append_taxa_runs(taxon, taxa, ntaxa, s); else s.back() = '\n';
+    const std::string cm = s.substr(cms);      // the reference keeps raw pointers here and breaks on realloc
+    s += bs->seq; s.append("\n+\n", 3);
+    s += bs->qual.empty() ? bs->seq : bs->qual; s.push_back('\n');
+    if(is_paired) {
+        const bseq1_t *b2 = bs + 1;
+        s += b2->name; s.push_back(' ');
+        s += cm; s.push_back('\n');
+        s += b2->seq; s.append("\n+\n", 3);
+        s += b2->qual.empty() ? b2->seq : b2->qual; s.push_back('\n');
+    }
+}
+}  // namespace detail
+
+// classify_seqs, classifier.h:269-289: classify `chunk_size` reads (mates interleaved when is_paired) and append each
+// record's text to cks in read order. per_set / the thread pool of the reference have no role here: the batch is one
+// GPU call. The per-record epilogue is classify_seq's (classifier.h:232-246).
+template <typename ScoreType>
+void classify_seqs(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, bseq1_t *bs, std::string &cks,
+                   const unsigned chunk_size, const unsigned /*per_set*/, const int is_paired) {
+    if(!c.tax_loaded_) c.load_taxonomy(taxmap);
+    const unsigned inc = is_paired ? 2 : 1, nrec = chunk_size / inc;
+    if(!nrec) return;
+    std::string bases;
+    std::vector<u64> offs(1, 0), toffs(1, 0);
+    for(unsigned i = 0; i < nrec * inc; ++i) { bases += bs[i].seq; offs.push_back(bases.size()); }
+    for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
+    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), taxa(toffs.back() + 1);
+    bns_b200_t *h = c.h_->h;
+    detail::check(h, bns_b200_classify_batch(h, bases.data(), offs.data(), nrec * inc, is_paired, taxon.data(), nhit.data(),
+                                             nmiss.data(), taxa.data(), toffs.data()), "bns_b200_classify_batch");
+    const u32 comb = c.sp_.c_;
+    for(unsigned r = 0; r < nrec; ++r) {
+        bseq1_t *b = bs + r * inc;
+        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count)
+        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)nhit[r] - nmiss[r]);
+        if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
+        b->sam.clear();
+        if(c.get_emit_all() || taxon[r]) {
+            const tax_t *tx = taxa.data() + toffs[r];
+            if(c.output_flag_ & FASTQ)
+                detail::append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, b->sam, c.get_emit_kraken(), is_paired);
+            else if(c.output_flag_ & KRAKEN)
+                detail::append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, b->sam);
+        }
+        cks += b->sam;
+    }
+}
+
+// process_dataset, classifier.h:296-337
+template <typename ScoreType>
+void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, const char *fq1, const char *fq2, std::FILE *out,
+                     unsigned chunk_size, unsigned per_set) {
+    detail::KSeq ks1(fq1);
+    std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
+    std::string cks;
+    const int fn = fileno(out), is_paired = fq2 != nullptr;
+    std::vector<bseq1_t> seqs;
+    auto flush = [&]() {
+        std::fflush(out);
+        size_t put = 0;
+        while(put < cks.size()) {
+            const ssize_t r = ::write(fn, cks.data() + put, cks.size() - put);
+            if(r <= 0) BNS_RUNTIME_ERROR("write failed");
+            put += (size_t)r;
+        }
+        cks.clear();
+    };
+    bool first = true;
+    while(bseq_read((int)chunk_size, seqs, &ks1, ks2.get())) {
+        classify_seqs(c, taxmap, seqs.data(), cks, (unsigned)seqs.size(), per_set, is_paired);
+        if(first) { std::fprintf(stderr, "nseq: %i\n", (int)seqs.size()); first = false; }     // classifier.h:312
+        if(cks.size() > (1ull << 16)) flush();
+    }
+    if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
+    flush();
+}
+
+}  // namespace bns

@@ -1,0 +1,69 @@
+"""CPU: the host-only parts of the C++ mirror (include/bonsai_b200/bonsai.hpp) through the `bonsai` CLI:
+the database file is the raw khash_t(c) layout the reference intends (database.h:81-102, util.h:281-296), so the
+restated kh_get must find every key in the arrays the writer produced."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from bonsai_b200 import build
+    return build.build_cli()
+
+
+def read_db(path):
+    raw = open(path, "rb").read()
+    k, w = struct.unpack_from("<II", raw, 0)
+    off = 8
+    gaps = list(raw[off:off + k - 1]); off += k - 1
+    nb, nocc, size, ub = struct.unpack_from("<QQQQ", raw, off); off += 32
+    nfl = 1 if nb < 16 else nb >> 4
+    flags = np.frombuffer(raw, np.uint32, nfl, off); off += 4 * nfl
+    keys = np.frombuffer(raw, np.uint64, nb, off); off += 8 * nb
+    vals = np.frombuffer(raw, np.uint32, nb, off); off += 4 * nb
+    assert off == len(raw)
+    return dict(k=k, w=w, gaps=gaps, n_buckets=nb, n_occupied=nocc, size=size, upper_bound=ub, flags=flags, keys=keys, vals=vals)
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 1000, 200000])
+def test_db_file_is_a_khash(cli, oracle, tmp_path, n):
+    rng = np.random.default_rng(n)
+    keys = np.unique(rng.integers(0, 2**62, n, dtype=np.uint64))
+    vals = rng.integers(1, 1000, keys.size, dtype=np.uint64).astype(np.uint32)
+    pairs = tmp_path / "pairs.bin"
+    with open(pairs, "wb") as f:
+        f.write(struct.pack("<Q", keys.size)); f.write(keys.tobytes()); f.write(vals.tobytes())
+    db = tmp_path / "t.db"
+    subprocess.check_call([cli, "dbwrite", str(db), "31", "31", str(pairs)])
+    out = subprocess.check_output([cli, "dbcheck", str(db)], text=True)
+    d = read_db(db)
+    assert (d["k"], d["w"], d["gaps"], d["size"]) == (31, 31, [0] * 30, keys.size)
+    assert d["n_buckets"] & (d["n_buckets"] - 1) == 0 and d["size"] <= d["upper_bound"] == int(d["n_buckets"] * 0.77 + 0.5)
+    with np.errstate(over="ignore"):
+        assert "occupied=%d " % keys.size in out
+        assert "key_xor=%016x" % int(np.bitwise_xor.reduce(keys) if keys.size else 0) in out
+        assert "val_sum=%d" % int(vals.sum(dtype=np.uint64)) in out
+    # the reference's kh_get (restated in the oracle) over the written arrays
+    D = oracle.db_from_arrays(d["keys"], d["vals"], d["flags"], d["n_buckets"])
+    for i in rng.integers(0, max(keys.size, 1), min(keys.size, 2000)):
+        assert oracle.db_get(D, int(keys[i])) == int(vals[i])
+    for q in rng.integers(0, 2**62, 200, dtype=np.uint64):
+        if q not in keys:
+            assert oracle.db_get(D, int(q)) is None
+    k2, v2 = oracle.db_pairs(D)
+    assert np.array_equal(k2, keys) and np.array_equal(v2, vals)
+    # gz variant reads back identically
+    dbz = tmp_path / "t.db.gz"
+    subprocess.check_call([cli, "dbwrite", str(dbz), "31", "31", str(pairs), "gz"])
+    assert subprocess.check_output([cli, "dbcheck", str(dbz)], text=True) == out
+
+
+def test_cli_usage(cli):
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode != 0 and "classify" in r.stderr
+    r = subprocess.run([cli, "classify"], capture_output=True, text=True)
+    assert r.returncode != 0 and "-k:\tEmit kraken-style output." in r.stderr
