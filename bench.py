@@ -218,23 +218,14 @@ def main():
         ctx.load_taxonomy(tc, tp)
     bcast_ms = None
     if world > 1:
-        hdr = torch.zeros(16, dtype=torch.int64, device=dev)
-        if rank == 0:
-            hdr.copy_(torch.from_numpy(ctx.db_export_header().astype(np.int64)))
-        dist.broadcast(hdr, 0)
-        if rank != 0:
-            ctx.db_alloc_from_header(hdr.cpu().numpy().astype(np.uint64))
+        from bonsai_b200 import sharding
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for ptr, nb in ctx.db_segments():
-            if nb:
-                dist.broadcast(torch.as_tensor(capi.DevMem(ptr, nb), device=dev), 0)
+        moved = sharding.replicate_db(ctx, dist, rank, root=0, device=dev)       # ONE broadcast of the DB at load
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            ctx.db_commit()
     tinfo = ctx.table_info()
     t_db = time.perf_counter() - t_db0
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "bns_b200_load_pairs_device", "bns_b200_table_info_get", "bns_b200_lookup_batch", "bns_b200_lookup_sectors", "bns_b200_load_taxonomy",
     "bns_b200_load_taxonomy_file", "bns_b200_resolve_batch", "bns_b200_db_export_header",
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
-    "bns_b200_classify_batch", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
+    "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
 ]
 
@@ -101,6 +101,7 @@ def load_library(path=None):
     lib.bns_b200_db_commit.argtypes = [vp]
     lib.bns_b200_encode_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp]
     lib.bns_b200_classify_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp]
+    lib.bns_b200_classify_batch_ex.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.bns_b200_classify_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.bns_b200_sync.argtypes = [vp]
     lib.bns_b200_stats_get.argtypes = [vp, C.POINTER(Stats)]

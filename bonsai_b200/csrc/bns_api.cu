@@ -838,7 +838,7 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     CK(cudaEventRecord(ctx->ev0, st));
     CK(launch_classify(ctx->enc, grid_for(ctx, n_rec, occ), smem, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
                        table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
-                       (const u64 *)d_taxa_offsets, ctx->ring_cap, ctx->d_counters, ctx->d_status));
+                       (const u64 *)d_taxa_offsets, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
     CK(cudaEventRecord(ctx->ev1, st));
     ++ctx->stats.kernel_launches;
     ctx->stats.reads_processed += n_reads;
@@ -849,6 +849,13 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
 int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                             uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
                             uint32_t *taxa_out, const uint64_t *taxa_offsets) {
+    return bns_b200_classify_batch_ex(ctx, bases, offsets, n_reads, paired, taxon_out, n_hit_out, n_missing_out, taxa_out,
+                                      taxa_offsets, nullptr);
+}
+
+int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                               uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
+                               uint32_t *taxa_out, const uint64_t *taxa_offsets, uint32_t *mate1_kmers_out) {
     if(!ctx || !offsets || !taxon_out || (taxa_out && !taxa_offsets)) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
     CK(cudaSetDevice(ctx->device));
     int rc = classify_ready(ctx);
@@ -872,7 +879,7 @@ int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *
         CK(cudaStreamSynchronize(s.st));
         rc = ensure(s.d_bases, s.cap_bases, nb + 16);
         if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
-        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 3 * nq);
+        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 4 * nq);
         u64 nt = 0;
         if(rc == BNS_OK && taxa_out) {
             nt = taxa_offsets[q1] - taxa_offsets[q0];
@@ -886,11 +893,13 @@ int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *
         CK(launch_classify(ctx->enc, grid_for(ctx, nq, occ), smem, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
-                           taxa_out ? s.d_taxa_offsets : nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
+                           taxa_out ? s.d_taxa_offsets : nullptr, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap,
+                           ctx->d_counters, ctx->d_status));
         ++ctx->stats.kernel_launches;
         CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_hit_out) CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(mate1_kmers_out) CK(cudaMemcpyAsync(mate1_kmers_out + q0, s.d_out + 3 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(taxa_out && nt) CK(cudaMemcpyAsync(taxa_out + taxa_offsets[q0], s.d_taxa, nt * 4, cudaMemcpyDeviceToHost, s.st));
         ctx->stats.h2d_bytes += nb + 8 * (nr + 1) + (taxa_out ? 8 * (nq + 1) : 0);
         ctx->stats.d2h_bytes += nq * 4 * (1 + (n_hit_out != nullptr) + (n_missing_out != nullptr)) + nt * 4;

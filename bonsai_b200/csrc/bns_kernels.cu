@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, BNS_CLASSIFY_MIN_CTAS)
 bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                     u64 n_records, u32 mates, u64 total_bases, TableView T, TaxView X,
                     u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out, u32 *__restrict__ nmiss_out,
-                    u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 ring_cap,
+                    u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 *__restrict__ mate1_out, u32 ring_cap,
                     unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -642,6 +642,8 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
         for(u32 mt = 0; mt < mates; ++mt) {
             const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
             encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+            // k-mers the first mate produced (classify_seq's first ambig_count term, classifier.h:232)
+            if(mt == 0 && mate1_out && lane == 0) mate1_out[r] = sink.n_hit + sink.n_miss;
         }
         const u32 taxon = sink.resolve(S, X, lane);
         if(lane == 0) {
@@ -798,7 +800,7 @@ size_t stream_smem_bytes(u32 ring_cap, bool classify) { return WARPS_PER_CTA * w
 
 typedef void (*encode_fn)(const EncParams, const char *, const u64 *, u64, u64, u64 *, const u64 *, u32 *, u32, u32 *);
 typedef void (*classify_fn)(const EncParams, const char *, const u64 *, u64, u32, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                            u32 *, const u64 *, u32, unsigned long long *, u32 *);
+                            u32 *, const u64 *, u32 *, u32, unsigned long long *, u32 *);
 
 static encode_fn pick_encode(u32 fam) {
     switch(fam) {
@@ -829,11 +831,11 @@ cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_
 cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
-                            u32 ring_cap, unsigned long long *counters, u32 *status) {
+                            u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status) {
     classify_fn f = pick_classify(P.family, taxa_out != nullptr);
     cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
-                                             nmiss_out, taxa_out, taxa_offsets, ring_cap, counters, status);
+                                             nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status);
     return cudaGetLastError();
 }
 int classify_occupancy(const EncParams &P, bool taxa, size_t smem) {

@@ -145,6 +145,11 @@ int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *of
 int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                             uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
                             uint32_t *taxa_out, const uint64_t *taxa_offsets);
+/* As above plus mate1_kmers_out[r] (optional): the number of k-mers the FIRST mate of record r produced, which the
+ * reference's first ambig_count term needs (classifier.h:232 is evaluated before the second mate is encoded). */
+int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                               uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
+                               uint32_t *taxa_out, const uint64_t *taxa_offsets, uint32_t *mate1_kmers_out);
 /* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). */
 int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
                              uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,

@@ -491,15 +491,15 @@ void classify_seqs(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, bseq1_
     std::vector<u64> offs(1, 0), toffs(1, 0);
     for(unsigned i = 0; i < nrec * inc; ++i) { bases += bs[i].seq; offs.push_back(bases.size()); }
     for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
-    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), taxa(toffs.back() + 1);
+    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(nrec), taxa(toffs.back() + 1);
     bns_b200_t *h = c.h_->h;
-    detail::check(h, bns_b200_classify_batch(h, bases.data(), offs.data(), nrec * inc, is_paired, taxon.data(), nhit.data(),
-                                             nmiss.data(), taxa.data(), toffs.data()), "bns_b200_classify_batch");
+    detail::check(h, bns_b200_classify_batch_ex(h, bases.data(), offs.data(), nrec * inc, is_paired, taxon.data(), nhit.data(),
+                                                nmiss.data(), taxa.data(), toffs.data(), mate1.data()), "bns_b200_classify_batch");
     const u32 comb = c.sp_.c_;
     for(unsigned r = 0; r < nrec; ++r) {
         bseq1_t *b = bs + r * inc;
-        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count)
-        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)nhit[r] - nmiss[r]);
+        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
+        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)mate1[r]);
         if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
         b->sam.clear();
         if(c.get_emit_all() || taxon[r]) {
