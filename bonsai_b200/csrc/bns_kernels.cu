@@ -213,6 +213,16 @@ __device__ __noinline__ u32 probe_displaced(const TableView T, u64 h) {
     }
     return VAL_MISS;
 }
+// Home-bucket test relying on the build-time invariant that no two entries of a bucket share their upper 32 bits
+// (bns_insert_kernel rejects such a pair and the table is rebuilt one size up): pick the first slot whose high word
+// equals the tag's, then verify the remaining remainder + displacement bits of that one candidate exactly.
+__device__ __forceinline__ u32 match4_home(const TableView &T, u64 tag, u64 s0, u64 s1, u64 s2, u64 s3) {
+    const u32 th = (u32)(tag >> 32), tl = (u32)tag, hm = ~0u << T.tag_shift;
+    const bool m0 = (u32)(s0 >> 32) == th, m1 = (u32)(s1 >> 32) == th, m2 = (u32)(s2 >> 32) == th, m3 = (u32)(s3 >> 32) == th;
+    const u32 cand = m0 ? (u32)s0 : m1 ? (u32)s1 : m2 ? (u32)s2 : (u32)s3;       // slots fill in order: first match wins
+    const bool ok = (m0 | m1 | m2 | m3) && (((cand ^ tl) & hm) == 0);            // an empty slot (disp 15) never passes
+    return ok ? (cand & T.val_mask) : VAL_MISS;
+}
 // kh_get + kh_val for PPL keys per lane: all home-bucket sectors are requested before any is inspected. Lanes / slots
 // without a live k-mer probe anyway (their result is masked by the caller): no predication, no register init.
 __device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 (&val)[PPL]) {
@@ -223,13 +233,17 @@ __device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], 
         h[i] = mix64(x[i]);
         ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
     }
+    // The overflow mark is a CLEARED bit in slot 0 of a full home bucket (an empty slot is all ones, so an empty or
+    // part-filled bucket reads "no overflow"): a miss costs one sector unless a key homed there was displaced.
+    u32 more = 0;
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
-        u32 v = match4(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
-        // The overflow mark is a CLEARED bit in slot 0 of a full home bucket (an empty slot is all ones, so an
-        // empty or part-filled bucket reads "no overflow"): a miss costs one sector unless a key was displaced.
-        if(v == VAL_MISS && !(((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h[i]);
-        val[i] = v;
+        val[i] = match4_home(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
+        if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) more |= 1u << i;
+    }
+    if(more) {                                                    // rare (~1 % of lookups at <= 1.25 entries/bucket)
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) if(more >> i & 1u) val[i] = probe_displaced(T, h[i]);
     }
 }
 
@@ -697,6 +711,9 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__r
                 if(cur == ~0ull) { if(d) atomicAdd(&stats[1], 1ull); return; }
             }
             if(((cur ^ entry) >> tag_shift) == 0) return;          // same key already present: first value stays
+            // invariant for match4_home: upper words are unique within a bucket. A clash (2^-32 per pair) fails the
+            // build; the host rebuilds with one more bucket bit, which re-draws every upper word.
+            if((u32)(cur >> 32) == (u32)(entry >> 32)) { atomicAdd(&stats[0], 1ull); return; }
         }
         if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (tag_shift - 1)));
     }
@@ -725,7 +742,7 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
     const u64 h = mix64(keys[i]);
     u64 a, b, c, d;
     ld_bucket(T.slots + ((h >> (64 - T.bucket_bits)) << 2), a, b, c, d);
-    u32 v = match4(T, h << T.bucket_bits, a, b, c, d);
+    u32 v = match4_home(T, h << T.bucket_bits, a, b, c, d);
     if(v == VAL_MISS && !(((u32)a >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h);
     found_out[i] = v != VAL_MISS;
     vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
