@@ -251,12 +251,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    clocks = ClockSampler(local_rank)
+    clocks.start()                      # nvidia-smi needs ~0.3 s to produce its first row: start it before the warm-up
+    for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    time.sleep(0.3)
+    clocks.rows.clear()                 # keep only samples taken during the timed region
     launches0 = ctx.stats()["kernel_launches"]
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
