@@ -21,7 +21,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <unistd.h>
@@ -46,22 +49,25 @@ inline u32 comb_size(const spvec_t &spaces) {                       // spacer.h:
     for(const auto i : spaces) ret += i;
     return ret;
 }
-inline spvec_t parse_spacing(const char *sss, unsigned k) {         // spacer.h:29-47, "1x3,0x5" syntax
-    char *ss = const_cast<char *>(sss);
-    if(!ss || *ss == '\0') return spvec_t(k - 1, 0);
-    spvec_t ret;
-    for(; *ss; ++ss) {
-        const int j = std::strtoul(ss, &ss, 10);
-        ret.emplace_back(j);
-        if(*ss == 'x') {
-            ss = std::strchr(ss, 'x') + 1;
-            auto n = std::max(int(std::strtoul(ss, &ss, 10)) - 1, 0);
-            if(n > 0) ret.insert(ret.end(), n, j);
+// "1x3,0x5": comma-separated `gap` or `gap x repeat` items (spacer.h:29-47). An empty string means unspaced.
+inline spvec_t parse_spacing(const char *text, unsigned k) {
+    if(text == nullptr || text[0] == '\0') return spvec_t(k - 1, 0);
+    spvec_t gaps;
+    const char *p = text;
+    while(*p) {
+        char *endp = nullptr;
+        const int gap = (int)std::strtoul(p, &endp, 10);
+        int times = 1;
+        if(*endp == 'x') {
+            times = (int)std::strtoul(endp + 1, &endp, 10);
+            if(times < 1) times = 1;                       // "gx0" still contributes one entry, as in the reference
         }
-        ss = std::strchr(ss, ',');
-        if(!ss) break;
+        gaps.insert(gaps.end(), (size_t)times, (u16)gap);
+        const char *comma = std::strchr(endp, ',');
+        if(comma == nullptr) break;
+        p = comma + 1;
     }
-    return ret;
+    return gaps;
 }
 struct Spacer {
     spvec_t s_;        // offsets (gap + 1), spacer.h:65
@@ -79,16 +85,15 @@ struct Spacer {
     bool unspaced() const { return std::all_of(s_.begin(), s_.end(), [](u16 x) { return x == 1; }); }
     bool unwindowed() const { return k_ == w_; }
     spvec_t sub1() const { spvec_t r(s_); for(auto &x : r) --x; return r; }            // spacer.h:173
-    std::string to_string(u64 kmer) const {                                             // spacer.h:127-139
-        std::string ret;
-        int offset = ((k_ - 1) << 1);
-        ret.push_back("ACGT"[(kmer >> offset) & 0x3u]);
-        for(auto s : s_) {
-            offset -= 2;
-            while(s-- > 1) ret.push_back('-');
-            ret.push_back("ACGT"[(kmer >> offset) & 0x3u]);
+    // the comb spelled out: bases of `kmer` at their offsets, '-' in the gaps (Spacer::to_string, spacer.h:127-139)
+    std::string to_string(u64 kmer) const {
+        std::string out(c_, '-');
+        size_t at = 0;
+        for(u32 j = 0; j < k_; ++j) {
+            out[at] = "ACGT"[(kmer >> (2 * (k_ - 1 - j))) & 3u];
+            if(j + 1 < k_) at += s_[j];
         }
-        return ret;
+        return out;
     }
 };
 
@@ -427,6 +432,7 @@ struct ClassifierGeneric {
 using Classifier = ClassifierGeneric<score::Lex>;
 
 namespace detail {
+struct ReadView { const char *name, *seq, *qual; int l_seq; };          // what the emitters need of a bseq1_t
 inline void put_u(std::string &s, u32 x) { char b[16]; s.append(b, std::snprintf(b, sizeof b, "%u", x)); }
 inline void put_i(std::string &s, long x) { char b[32]; s.append(b, std::snprintf(b, sizeof b, "%ld", x)); }
 inline void append_taxa_run(tax_t last, u32 run, std::string &s) {                // classifier.h:30-43
@@ -448,16 +454,16 @@ inline void append_counts(u32 count, char ch, std::string &s) {                 
     if(count) { s.push_back(ch); s.push_back(':'); put_u(s, count); s.push_back('\t'); }
 }
 inline void append_kraken_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
-                                         const bseq1_t *bs, std::string &s) {      // :112-129
+                                         const ReadView &bs, std::string &s) {     // :112-129
     s.push_back(taxon ? 'C' : 'U'); s.push_back('\t');
-    s += bs->name; s.push_back('\t');
+    s += bs.name; s.push_back('\t');
     put_u(s, taxon); s.push_back('\t');
-    put_i(s, bs->l_seq); s.push_back('\t');
+    put_i(s, bs.l_seq); s.push_back('\t');
     append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
     append_taxa_runs(taxon, taxa, ntaxa, s);
 }
 inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
-                                        const bseq1_t *bs, std::string &s, int verbose, int is_paired) {   // :72-108
+                                        const ReadView *bs, std::string &s, int verbose, int is_paired) {   // :72-108
     s += bs->name; s.push_back(' ');
     const size_t cms = s.size();
     s.push_back(taxon == 0 ? 'U' : 'C'); s.push_back('\t');
@@ -466,62 +472,146 @@ inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxo
     append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
     if(verbose) append_taxa_runs(taxon, taxa, ntaxa, s); else s.back() = '\n';
     const std::string cm = s.substr(cms);      // the reference keeps raw pointers here and breaks on realloc
-    s += bs->seq; s.append("\n+\n", 3);
-    s += bs->qual.empty() ? bs->seq : bs->qual; s.push_back('\n');
+    s.append(bs->seq, bs->l_seq); s.append("\n+\n", 3);
+    s.append(bs->qual ? bs->qual : bs->seq, bs->l_seq); s.push_back('\n');
     if(is_paired) {
-        const bseq1_t *b2 = bs + 1;
+        const ReadView *b2 = bs + 1;
         s += b2->name; s.push_back(' ');
         s += cm; s.push_back('\n');
-        s += b2->seq; s.append("\n+\n", 3);
-        s += b2->qual.empty() ? b2->seq : b2->qual; s.push_back('\n');
+        s.append(b2->seq, b2->l_seq); s.append("\n+\n", 3);
+        s.append(b2->qual ? b2->qual : b2->seq, b2->l_seq); s.push_back('\n');
     }
+}
+
+// One GPU call for a batch laid out as concatenated bases + offsets, then classify_seq's epilogue per record
+// (classifier.h:232-246). `views` has one entry per read (mates interleaved).
+template <typename ScoreType>
+void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ReadView *views, unsigned n_reads,
+                    int is_paired, std::string &cks) {
+    const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
+    if(!nrec) return;
+    std::vector<u64> toffs(1, 0);
+    toffs.reserve(nrec + 1);
+    for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
+    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(nrec), taxa(toffs.back() + 1);
+    bns_b200_t *h = c.h_->h;
+    check(h, bns_b200_classify_batch_ex(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
+                                        taxa.data(), toffs.data(), mate1.data()), "bns_b200_classify_batch");
+    const u32 comb = c.sp_.c_;
+    for(unsigned r = 0; r < nrec; ++r) {
+        const ReadView *b = views + r * inc;
+        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
+        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)mate1[r]);
+        if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
+        if(c.get_emit_all() || taxon[r]) {
+            const tax_t *tx = taxa.data() + toffs[r];
+            if(c.output_flag_ & FASTQ)
+                append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, cks, c.get_emit_kraken(), is_paired);
+            else if(c.output_flag_ & KRAKEN)
+                append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], *b, cks);
+        }
+    }
+}
+
+// A batch parsed straight into PINNED host memory (bns_b200_host_alloc): the library DMAs from it without staging.
+struct PinnedBatch {
+    char *bases = nullptr; size_t cap_bases = 0, n_bases = 0;
+    u64 *offs = nullptr; size_t cap_offs = 0, n = 0;
+    std::vector<std::string> names, quals;
+    std::vector<char> has_qual;
+    PinnedBatch() = default;
+    PinnedBatch(const PinnedBatch &) = delete;
+    ~PinnedBatch() { bns_b200_host_free(bases); bns_b200_host_free(offs); }
+    template <class T> static void grow(T *&p, size_t &cap, size_t used, size_t need) {
+        if(need <= cap) return;
+        size_t ncap = std::max<size_t>(need, cap ? cap * 2 : 1 << 16);
+        void *np = nullptr;
+        if(bns_b200_host_alloc(&np, ncap * sizeof(T))) BNS_RUNTIME_ERROR("pinned host allocation failed");
+        if(used) std::memcpy(np, p, used * sizeof(T));
+        bns_b200_host_free(p);
+        p = (T *)np; cap = ncap;
+    }
+    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); }
+    void push(KSeq *k) {
+        trim_readno(k->name);
+        grow(bases, cap_bases, n_bases, n_bases + k->seq.size() + 16);
+        grow(offs, cap_offs, n + 1, n + 2);
+        if(n == 0) offs[0] = 0;
+        std::memcpy(bases + n_bases, k->seq.data(), k->seq.size());
+        n_bases += k->seq.size();
+        offs[++n] = n_bases;
+        names.push_back(k->name);
+        has_qual.push_back(!k->qual.empty());
+        quals.push_back(k->qual);
+    }
+};
+// bseq_read (kseq_declare.h:112-145) into a pinned batch: records until >= chunk_size bases and an even count
+inline bool read_pinned(int chunk_size, PinnedBatch &b, KSeq *ks, KSeq *ks2) {
+    b.clear();
+    while(ks->read() >= 0) {
+        if(ks2 && ks2->read() < 0) { std::fprintf(stderr, "[W::%s] the 2nd file has fewer sequences.\n", __func__); break; }
+        b.push(ks);
+        if(ks2) b.push(ks2);
+        if((long)b.n_bases >= chunk_size && (b.n & 1) == 0) break;
+    }
+    if(b.n_bases == 0 && ks2 && ks2->read() >= 0) std::fprintf(stderr, "[W::%s] the 1st file has fewer sequences.\n", __func__);
+    return b.n != 0;
 }
 }  // namespace detail
 
 // classify_seqs, classifier.h:269-289: classify `chunk_size` reads (mates interleaved when is_paired) and append each
 // record's text to cks in read order. per_set / the thread pool of the reference have no role here: the batch is one
-// GPU call. The per-record epilogue is classify_seq's (classifier.h:232-246).
+// GPU call.
 template <typename ScoreType>
 void classify_seqs(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, bseq1_t *bs, std::string &cks,
                    const unsigned chunk_size, const unsigned /*per_set*/, const int is_paired) {
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
-    const unsigned inc = is_paired ? 2 : 1, nrec = chunk_size / inc;
-    if(!nrec) return;
+    const unsigned inc = is_paired ? 2 : 1, n = (chunk_size / inc) * inc;
+    if(!n) return;
     std::string bases;
-    std::vector<u64> offs(1, 0), toffs(1, 0);
-    for(unsigned i = 0; i < nrec * inc; ++i) { bases += bs[i].seq; offs.push_back(bases.size()); }
-    for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
-    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(nrec), taxa(toffs.back() + 1);
-    bns_b200_t *h = c.h_->h;
-    detail::check(h, bns_b200_classify_batch_ex(h, bases.data(), offs.data(), nrec * inc, is_paired, taxon.data(), nhit.data(),
-                                                nmiss.data(), taxa.data(), toffs.data(), mate1.data()), "bns_b200_classify_batch");
-    const u32 comb = c.sp_.c_;
-    for(unsigned r = 0; r < nrec; ++r) {
-        bseq1_t *b = bs + r * inc;
-        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
-        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)mate1[r]);
-        if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
-        b->sam.clear();
-        if(c.get_emit_all() || taxon[r]) {
-            const tax_t *tx = taxa.data() + toffs[r];
-            if(c.output_flag_ & FASTQ)
-                detail::append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, b->sam, c.get_emit_kraken(), is_paired);
-            else if(c.output_flag_ & KRAKEN)
-                detail::append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, b->sam);
-        }
-        cks += b->sam;
-    }
+    std::vector<u64> offs(1, 0);
+    std::vector<detail::ReadView> views(n);
+    for(unsigned i = 0; i < n; ++i) { bases += bs[i].seq; offs.push_back(bases.size()); }
+    for(unsigned i = 0; i < n; ++i)
+        views[i] = detail::ReadView{bs[i].name.c_str(), bases.data() + offs[i], bs[i].qual.empty() ? nullptr : bs[i].qual.c_str(), bs[i].l_seq};
+    const size_t before = cks.size();
+    detail::classify_views(c, bases.data(), offs.data(), views.data(), n, is_paired, cks);
+    (void)before;
 }
 
-// process_dataset, classifier.h:296-337
+// process_dataset, classifier.h:296-337. Ingest is overlapped with the GPU: a reader thread parses FASTA/FASTQ(.gz)
+// records into a ring of pinned host batches while the caller's thread classifies the previous batch (the library DMAs
+// straight from the pinned buffer on its copy stream) and formats its text.
 template <typename ScoreType>
 void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, const char *fq1, const char *fq2, std::FILE *out,
-                     unsigned chunk_size, unsigned per_set) {
+                     unsigned chunk_size, unsigned /*per_set*/) {
+    if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     detail::KSeq ks1(fq1);
     std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
-    std::string cks;
     const int fn = fileno(out), is_paired = fq2 != nullptr;
-    std::vector<bseq1_t> seqs;
+    constexpr int NB = 3;
+    detail::PinnedBatch ring[NB];
+    int state[NB] = {0, 0, 0};                   // 0 free, 1 filled, 2 end of input
+    std::mutex mu;
+    std::condition_variable cv;
+    std::string reader_error;
+    std::thread reader([&]() {
+        try {
+            for(int i = 0;; i = (i + 1) % NB) {
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
+                const bool got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
+                { std::lock_guard<std::mutex> lk(mu); state[i] = got ? 1 : 2; }
+                cv.notify_all();
+                if(!got) return;
+            }
+        } catch(const std::exception &e) {
+            std::lock_guard<std::mutex> lk(mu);
+            reader_error = e.what();
+            for(int &s : state) s = 2;
+            cv.notify_all();
+        }
+    });
+    std::string cks;
     auto flush = [&]() {
         std::fflush(out);
         size_t put = 0;
@@ -533,11 +623,29 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
         cks.clear();
     };
     bool first = true;
-    while(bseq_read((int)chunk_size, seqs, &ks1, ks2.get())) {
-        classify_seqs(c, taxmap, seqs.data(), cks, (unsigned)seqs.size(), per_set, is_paired);
-        if(first) { std::fprintf(stderr, "nseq: %i\n", (int)seqs.size()); first = false; }     // classifier.h:312
-        if(cks.size() > (1ull << 16)) flush();
+    std::string failure;
+    std::vector<detail::ReadView> views;
+    for(int i = 0;; i = (i + 1) % NB) {
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] != 0; }); }
+        if(state[i] == 2) break;
+        detail::PinnedBatch &b = ring[i];
+        try {
+            if(failure.empty()) {
+                views.resize(b.n);
+                for(size_t r = 0; r < b.n; ++r)
+                    views[r] = detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
+                                                (int)(b.offs[r + 1] - b.offs[r])};
+                detail::classify_views(c, b.bases, b.offs, views.data(), (unsigned)b.n, is_paired, cks);
+                if(first) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
+                if(cks.size() > (1ull << 16)) flush();
+            }
+        } catch(const std::exception &e) { failure = e.what(); }
+        { std::lock_guard<std::mutex> lk(mu); state[i] = 0; }
+        cv.notify_all();
     }
+    reader.join();
+    if(!reader_error.empty()) BNS_RUNTIME_ERROR(reader_error);
+    if(!failure.empty()) BNS_RUNTIME_ERROR(failure);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
     flush();
 }

@@ -354,3 +354,18 @@ def test_stress_device_build_vs_oracle(capi, oracle, toy_tax):
         et, eh, em = oracle.classify(D, toy_tax, bases, offs, 31, 31)
         assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
         oracle.db_free(D)
+
+
+def test_bns_python_surface(capi, oracle, genomes, tmp_path):
+    from bonsai_b200 import bns
+    s = bytes(genomes["phix"]).decode()
+    assert np.array_equal(bns.from_str(s, 31), oracle.encode(s, 31, 31))
+    assert np.array_equal(bns.from_str(s, 31, "", 50, False), oracle.encode(s, 31, 50, canon=False))
+    p = tmp_path / "x.fa"
+    p.write_text(">a\n%s\n>b desc\n%s\n%s\n" % (s[:300], s[300:400], s[400:650]))
+    gaps = "1x2,0x28"
+    lists = bns.seqlist(str(p), 31, gaps, 0, True)
+    exp = [oracle.encode(x, 31, 0, bns.parse_spacing(gaps, 31), 0, True, po.API_PATH) for x in (s[:300], s[300:650])]
+    assert len(lists) == 2 and all(np.array_equal(a, b) for a, b in zip(lists, exp))
+    assert np.array_equal(bns.from_fasta(str(p), 31, unique=True), np.unique(np.concatenate(
+        [oracle.encode(x, 31, 31, None, 0, True, po.API_PATH) for x in (s[:300], s[300:650])])))
