@@ -102,14 +102,14 @@ def workload_spec(name):
     raise SystemExit("unknown workload " + name)
 
 
-def build_database(spec, g):
-    """rank 0: DB through the product's own builder (GPU encoder + host LCA merge)"""
-    from bonsai_b200 import dbbuild, workload as W
+def build_database(ctx, spec, g):
+    """rank 0: `bonsai build` on the device (encode -> insert-or-LCA-merge kernel), straight into ctx's table"""
+    from bonsai_b200 import capi, dbbuild, workload as W
     tc, tp = W.toy_tax_arrays()
-    d = spec["db"]
+    d, c = spec["db"], spec["cls"]
     genomes = [W.genome_records(g, gi) for gi in range(4)]
-    keys, vals = dbbuild.build_db(genomes, W.GENOME_TAXIDS, tc, tp, d["k"], d["w"], d["gaps"], d["score"], d["canon"])
-    return keys, vals, tc, tp
+    dbbuild.build_on_device(ctx, genomes, W.GENOME_TAXIDS, tc, tp, d["k"], d["w"], d["gaps"], d["score"], d["canon"])
+    ctx.reconfigure(c["k"], c["w"], c["gaps"], capi.SCORE_LEX, c["canon"], c["api"])
 
 
 def run_reference(args, spec):
@@ -213,9 +213,7 @@ def main():
         del d_keys, d_vals
         torch.cuda.empty_cache()
     elif rank == 0:
-        keys, vals, tc, tp = build_database(spec, g)
-        ctx.load_pairs(keys, vals)
-        ctx.load_taxonomy(tc, tp)
+        build_database(ctx, spec, g)
     bcast_ms = None
     if world > 1:
         from bonsai_b200 import sharding
@@ -354,6 +352,7 @@ def main():
         cpu = po.load_ref() or po.load_oracle()
         tc, tp = W.toy_tax_arrays()
         T = cpu.tax_from_pairs(tc, tp)
+        keys, vals = ctx.table_dump()               # the CPU arm probes its own khash built from the same pairs
         db = cpu.db_from_pairs(keys, vals)
         nthreads = os.cpu_count() or 1
         nb = 20000

@@ -21,7 +21,8 @@ SYMBOLS = [
     "bns_b200_version", "bns_b200_strerror", "bns_b200_last_error", "bns_b200_open", "bns_b200_close",
     "bns_b200_geometry", "bns_b200_encode_bound", "bns_b200_load_table", "bns_b200_load_pairs",
     "bns_b200_load_pairs_device", "bns_b200_table_info_get", "bns_b200_lookup_batch", "bns_b200_lookup_sectors", "bns_b200_load_taxonomy",
-    "bns_b200_load_taxonomy_file", "bns_b200_resolve_batch", "bns_b200_db_export_header",
+    "bns_b200_load_taxonomy_file", "bns_b200_resolve_batch", "bns_b200_build_begin", "bns_b200_build_add_genome",
+    "bns_b200_build_finish", "bns_b200_table_dump", "bns_b200_reconfigure", "bns_b200_db_export_header",
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
     "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
@@ -92,6 +93,11 @@ def load_library(path=None):
     lib.bns_b200_table_info_get.argtypes = [vp, C.POINTER(TableInfo)]
     lib.bns_b200_lookup_batch.argtypes = [vp, vp, C.c_uint64, vp, vp]
     lib.bns_b200_lookup_sectors.argtypes = [vp, vp, C.c_uint64, u64p]
+    lib.bns_b200_build_begin.argtypes = [vp, C.c_uint64, vp, C.c_uint32]
+    lib.bns_b200_build_add_genome.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32]
+    lib.bns_b200_build_finish.argtypes = [vp]
+    lib.bns_b200_table_dump.argtypes = [vp, vp, vp, C.c_uint64, u64p]
+    lib.bns_b200_reconfigure.argtypes = [vp, C.POINTER(Config)]
     lib.bns_b200_load_taxonomy.argtypes = [vp, vp, vp, C.c_uint64]
     lib.bns_b200_load_taxonomy_file.argtypes = [vp, C.c_char_p]
     lib.bns_b200_resolve_batch.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
@@ -121,9 +127,8 @@ def _p(a):
 class Context:
     """One bns_b200 context = one ClassifierGeneric + its per-worker Encoder copy on one GPU."""
 
-    def __init__(self, k, w=0, gaps=None, score=SCORE_LEX, canonicalize=True, api=API_STRING,
-                 entropy_cast=CAST_SATURATE, device=-1):
-        self.lib = load_library()
+    @staticmethod
+    def _config(k, w, gaps, score, canonicalize, api, entropy_cast, device):
         cfg = Config()
         cfg.k, cfg.w, cfg.score, cfg.canonicalize, cfg.api = k, w, score, int(bool(canonicalize)), api
         cfg.entropy_cast, cfg.device = entropy_cast, device
@@ -131,6 +136,12 @@ class Context:
             assert len(gaps) == k - 1, "gap vector must have k-1 entries"
             for i, g in enumerate(gaps):
                 cfg.gaps[i] = int(g)
+        return cfg
+
+    def __init__(self, k, w=0, gaps=None, score=SCORE_LEX, canonicalize=True, api=API_STRING,
+                 entropy_cast=CAST_SATURATE, device=-1):
+        self.lib = load_library()
+        cfg = self._config(k, w, gaps, score, canonicalize, api, entropy_cast, device)
         h = C.c_void_p()
         rc = self.lib.bns_b200_open(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -199,6 +210,35 @@ class Context:
         out = C.c_uint64()
         self._ck(self.lib.bns_b200_lookup_sectors(self.h, _p(keys), keys.size, C.byref(out)))
         return out.value
+
+    # ---- database construction on the device ----
+    def reconfigure(self, k, w=0, gaps=None, score=SCORE_LEX, canonicalize=True, api=API_STRING, entropy_cast=CAST_SATURATE):
+        cfg = self._config(k, w, gaps, score, canonicalize, api, entropy_cast, -1)
+        self._ck(self.lib.bns_b200_reconfigure(self.h, C.byref(cfg)))
+        self.k = k
+
+    def build_begin(self, max_kmers, taxids):
+        t = np.ascontiguousarray(taxids, np.uint32)
+        self._ck(self.lib.bns_b200_build_begin(self.h, int(max_kmers), _p(t), t.size))
+
+    def build_add_genome(self, bases, offsets, taxid):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        self._ck(self.lib.bns_b200_build_add_genome(self.h, _p(bases), _p(offsets), offsets.size - 1, int(taxid)))
+
+    def build_finish(self):
+        self._ck(self.lib.bns_b200_build_finish(self.h))
+
+    def table_dump(self):
+        """-> (keys sorted uint64, vals uint32)"""
+        n = C.c_uint64()
+        self._ck(self.lib.bns_b200_table_dump(self.h, None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, np.uint64)
+        vals = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.bns_b200_table_dump(self.h, _p(keys), _p(vals), n.value, C.byref(n)))
+        o = np.argsort(keys)
+        return keys[o], vals[o]
 
     # ---- taxonomy ----
     def load_taxonomy(self, child, parent):

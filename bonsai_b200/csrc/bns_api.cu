@@ -69,7 +69,8 @@ struct bns_b200_ctx {
     uint4 *d_val_info = nullptr, *d_node_info = nullptr;
     u32 n_nodes = 0, node_of_one = 0;
     // misc device state
-    unsigned long long *d_counters = nullptr;   // [0] classified [1] unclassified [2..7] scratch
+    unsigned long long *d_counters = nullptr;   // [0] classified [1] unclassified [2..7] scratch [8..11] build stats
+    bool building = false;
     u32 *d_status = nullptr;
     Slot slots[N_SLOTS];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -425,9 +426,9 @@ int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
         if((e = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if((e = cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if((e = cudaMalloc((void **)&ctx->d_status, sizeof(u32))) != cudaSuccess) return bail(e, "cudaMalloc");
-    cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long));
     cudaMemset(ctx->d_status, 0, sizeof(u32));
     *out = ctx;
     return BNS_OK;
@@ -634,6 +635,133 @@ int bns_b200_lookup_sectors(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, u
     unsigned long long h = 0;
     CK(cudaMemcpy(&h, ctx->d_counters + 4, sizeof h, cudaMemcpyDeviceToHost));
     *sectors_out = h;
+    return BNS_OK;
+}
+
+// ---- database construction on the device -----------------------------------------------------------------
+int bns_b200_reconfigure(bns_b200_t *ctx, const bns_b200_config *cfg) {
+    if(!ctx || !cfg) return BNS_E_INVAL;
+    const bns_b200_config old = ctx->cfg;
+    ctx->cfg = *cfg;
+    ctx->cfg.device = old.device;
+    const int rc = derive_encoder(ctx);
+    if(rc != BNS_OK) { ctx->cfg = old; derive_encoder(ctx); }
+    return rc;
+}
+
+int bns_b200_build_begin(bns_b200_t *ctx, uint64_t max_kmers, const uint32_t *taxids, uint32_t n_taxids) {
+    if(!ctx || !taxids || !n_taxids) return ctx ? ctx->fail(BNS_E_INVAL, "no taxids") : BNS_E_INVAL;
+    if(!ctx->tax_loaded) return ctx->fail(BNS_E_STATE, "load the taxonomy before building");
+    CK(cudaSetDevice(ctx->device));
+    // value dictionary = the taxids and all their ancestors (every lca result lives there), plus taxid 1
+    std::vector<u32> order(ctx->tax_child.size());
+    for(size_t i = 0; i < order.size(); ++i) order[i] = (u32)i;
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return ctx->tax_child[a] < ctx->tax_child[b]; });
+    auto parent_of = [&](u32 t, bool &found) -> u32 {
+        if(t == 1) { found = true; return 0; }
+        // last line for a taxid wins, as repeated kh_put + assignment does (util.h:773-776)
+        auto it = std::upper_bound(order.begin(), order.end(), t, [&](u32 v, u32 idx) { return v < ctx->tax_child[idx]; });
+        if(it == order.begin() || ctx->tax_child[*(it - 1)] != t) { found = false; return 0; }
+        found = true;
+        return ctx->tax_parent[*(it - 1)];
+    };
+    std::vector<u32> values;
+    values.push_back(1);
+    for(u32 i = 0; i < n_taxids; ++i) {
+        u32 t = taxids[i];
+        for(int guard = 0; t && guard < 4096; ++guard) {
+            values.push_back(t);
+            bool found;
+            t = parent_of(t, found);
+            if(!found) break;
+        }
+    }
+    std::sort(values.begin(), values.end());
+    values.erase(std::unique(values.begin(), values.end()), values.end());
+    free_table(ctx);
+    ctx->values = values;
+    int rc = upload_values(ctx);
+    if(rc == BNS_OK) rc = alloc_table(ctx, choose_bits(max_kmers, (u32)values.size()));
+    if(rc == BNS_OK) rc = finalize_taxonomy(ctx);
+    if(rc != BNS_OK) return rc;
+    CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->slots[0].st));
+    CK(cudaStreamSynchronize(ctx->slots[0].st));
+    ctx->building = true;
+    return BNS_OK;
+}
+
+int bns_b200_build_add_genome(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_records, uint32_t taxid) {
+    if(!ctx || !offsets || (n_records && !bases)) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!ctx->building) return ctx->fail(BNS_E_STATE, "bns_b200_build_begin first");
+    CK(cudaSetDevice(ctx->device));
+    const auto it = std::lower_bound(ctx->values.begin(), ctx->values.end(), taxid);
+    if(it == ctx->values.end() || *it != taxid) return ctx->fail(BNS_E_INVAL, "taxid %u was not announced to build_begin", taxid);
+    const u32 vid = (u32)(it - ctx->values.begin());
+    if(!n_records) return BNS_OK;
+    // Pieces: long records are cut so that many warps share a genome. Only where the encoder keeps no state across
+    // positions other than the window itself (FAM_U, FAM_K): piece i re-reads the W-1 elements before its first window.
+    const EncParams &P = ctx->enc;
+    const bool can_split = P.family == FAM_U || P.family == FAM_K;
+    const u64 SPLIT = 1 << 14, c = P.c, W = P.W;
+    std::vector<u64> se;
+    for(u64 r = 0; r < n_records; ++r) {
+        const u64 b = offsets[r], e = offsets[r + 1], L = e - b;
+        if(!can_split || L < c || L - c + 1 <= SPLIT) { se.push_back(b); se.push_back(e); continue; }
+        const u64 npos = L - c + 1;
+        for(u64 s = 0; s < npos; s += SPLIT) {
+            const u64 a = s >= W - 1 ? s - (W - 1) : 0, z = std::min(s + SPLIT, npos);
+            se.push_back(b + a); se.push_back(b + z + c - 1);
+        }
+    }
+    const u64 npieces = se.size() / 2, nb = offsets[n_records] - offsets[0];
+    Slot &s = ctx->slots[0];
+    int rc = ensure(s.d_bases, s.cap_bases, nb + 16);
+    if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, se.size() + 1);
+    if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+    CK(cudaMemcpyAsync(s.d_bases, bases + offsets[0], nb, cudaMemcpyHostToDevice, s.st));
+    CK(cudaMemcpyAsync(s.d_offsets, se.data(), se.size() * 8, cudaMemcpyHostToDevice, s.st));
+    const size_t smem = stream_smem_bytes(ctx->ring_cap, false);
+    CK(launch_build(ctx->enc, grid_for(ctx, npieces, 4), smem, s.st, s.d_bases - offsets[0], s.d_offsets, npieces, offsets[n_records],
+                    ctx->d_slots, ctx->bucket_bits, vid, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 8,
+                    ctx->ring_cap));
+    ++ctx->stats.kernel_launches;
+    ctx->stats.h2d_bytes += nb + se.size() * 8;
+    ctx->stats.bases_processed += nb;
+    CK(cudaStreamSynchronize(s.st));          // `se` and the caller's buffers may go away
+    return BNS_OK;
+}
+
+int bns_b200_build_finish(bns_b200_t *ctx) {
+    if(!ctx) return BNS_E_INVAL;
+    if(!ctx->building) return ctx->fail(BNS_E_STATE, "no build in progress");
+    CK(cudaSetDevice(ctx->device));
+    ctx->building = false;
+    unsigned long long h[4];
+    CK(cudaMemcpy(h, ctx->d_counters + 8, sizeof h, cudaMemcpyDeviceToHost));
+    if(h[0]) return ctx->fail(BNS_E_CAPACITY, "%llu k-mers found no slot: call build_begin with a larger max_kmers", h[0]);
+    ctx->n_displaced = 0;
+    ctx->tax_ready = true;
+    return refresh_table_stats(ctx);
+}
+
+int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out, uint64_t cap, uint64_t *n_out) {
+    if(!ctx || !n_out || (cap && (!keys_out || !vals_out))) return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
+    CK(cudaSetDevice(ctx->device));
+    *n_out = ctx->n_keys;
+    if(!cap) return BNS_OK;
+    if(cap < ctx->n_keys) return ctx->fail(BNS_E_CAPACITY, "table holds %llu keys", (unsigned long long)ctx->n_keys);
+    u64 *dk = nullptr; u32 *dv = nullptr;
+    cudaStream_t st = ctx->slots[0].st;
+    CK(cudaMalloc((void **)&dk, std::max<u64>(ctx->n_keys, 1) * 8));
+    CK(cudaMalloc((void **)&dv, std::max<u64>(ctx->n_keys, 1) * 4));
+    CK(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st));
+    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
+    ++ctx->stats.kernel_launches;
+    CK(cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(dk); cudaFree(dv);
     return BNS_OK;
 }
 

@@ -103,6 +103,22 @@ __device__ __host__ __forceinline__ u64 mix64(u64 x) {
     return x;
 }
 
+// modular inverse of the odd multiplier (Newton iteration), for unmix64
+__host__ __device__ constexpr u64 inv_odd(u64 a) {
+    u64 x = a;                       // correct to 3 bits
+    for(int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+__device__ __host__ __forceinline__ u64 unmix64(u64 x) {
+    constexpr u64 MI = inv_odd(0xd6e8feb86659fd93ull);
+    x ^= x >> 32;
+    x *= MI;
+    x ^= x >> 32;
+    x *= MI;
+    x ^= x >> 32;
+    return x;
+}
+
 __device__ __forceinline__ void ld_bucket(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {
     // one 32-byte sector per probe (LDG.E.256)
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"

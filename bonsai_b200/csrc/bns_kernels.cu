@@ -383,6 +383,78 @@ struct ClassifySink {
     }
 };
 
+// value -> dense id by binary search in the sorted distinct-value list
+__device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u32 v) {
+    u32 lo = 0, hi = n;
+    while(lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if(values[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && values[lo] == v) ? lo : VAL_MISS;
+}
+
+// Database construction on the device: every k-mer the encoder emits for a genome is inserted with the genome's value
+// id, or -- if the key is already present with another value -- merged with lca(tax, new, old), which is what
+// fill_set_genome + update_lca_map do (feature_min.h:68-83,205-228). lca is idempotent, commutative and associative on
+// a well-formed taxonomy, so concurrent CAS merges converge to the reference's sequential result.
+struct BuildSink {
+    u64 *slots;
+    u32 b, tag_shift, val_mask;
+    u32 vid;                           // value id of the genome being added
+    const uint4 *val_info, *node_info; // Euler intervals: {tin, tout, node, taxid} / {tin, tout, parent node, taxid}
+    const u32 *values;
+    u32 n_values, node_of_one;
+    unsigned long long *stats;         // [0] failed  [1] displaced  [3] new keys
+    u32 n_new, n_fail;                 // per lane
+
+    __device__ __forceinline__ u32 lca_id(u32 a_id, u32 b_id) const {     // lca(), util.h:634-663, on value ids
+        if(a_id == b_id) return a_id;
+        u32 a = val_info[a_id].z;
+        const u32 tb = val_info[b_id].x;
+        while(a) {
+            const uint4 na = node_info[a];
+            if(na.x <= tb && tb < na.y) break;
+            a = na.z;
+        }
+        if(!a) a = node_of_one;
+        return value_id(values, n_values, node_info[a].w);
+    }
+    __device__ __forceinline__ void insert(u64 key) {
+        const u64 h = mix64(key), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
+        for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
+            u64 *bk = slots + (((home + d) & bmask) << 2);
+            const u64 entry = tag | ((u64)d << tag_shift) | (1ull << (tag_shift - 1)) | vid;
+            for(int s = 0; s < 4; ++s) {
+                u64 cur = bk[s];
+                if(cur == ~0ull) {
+                    cur = atomicCAS((unsigned long long *)&bk[s], ~0ull, (unsigned long long)entry);
+                    if(cur == ~0ull) { ++n_new; return; }
+                }
+                if(((cur ^ entry) >> tag_shift) == 0) {                  // key present: update_lca_map's merge branch
+                    for(;;) {
+                        const u32 old = (u32)cur & val_mask;
+                        if(old == vid) return;
+                        const u32 m = lca_id(vid, old);
+                        if(m == old) return;
+                        if(m == VAL_MISS) { ++n_fail; return; }
+                        const u64 want = (cur & ~(u64)val_mask) | m;
+                        const u64 prev = atomicCAS((unsigned long long *)&bk[s], (unsigned long long)cur, (unsigned long long)want);
+                        if(prev == cur) return;
+                        cur = prev;                                      // value or overflow mark changed under us: retry
+                    }
+                }
+                if((u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant
+            }
+            if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (tag_shift - 1)));
+        }
+        ++n_fail;
+    }
+    __device__ __forceinline__ void consume(const WarpSmem &, const u64 (&x)[PPL], u32 mask, u32) {
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) if(mask >> i & 1u) insert(x[i]);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // window ring (QueueMap, qmap.h:79-96) over the elements a tile produced. `m` new elements were written to
 // S.rel/S.rsc[hist .. hist+m) by the caller. Produces the window minima for the new elements this lane owns
@@ -675,16 +747,6 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
     }
 }
 
-// value -> dense id by binary search in the sorted distinct-value list
-__device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u32 v) {
-    u32 lo = 0, hi = n;
-    while(lo < hi) {
-        const u32 mid = (lo + hi) >> 1;
-        if(values[mid] < v) lo = mid + 1; else hi = mid;
-    }
-    return (lo < n && values[lo] == v) ? lo : VAL_MISS;
-}
-
 // Bucketised open addressing, 4 x u64 slots per 32-byte bucket:
 //   slot = [ low (64-b) bits of mix64(key) | disp:4 | novf:1 | value id:(b-5) ],  empty = ~0.
 // A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 14);
@@ -792,6 +854,43 @@ bns_resolve_kernel(TaxView X, const u32 *__restrict__ values, u32 n_values, cons
     }
 }
 
+// bonsai build on the device: one warp per genome record (contig), every emitted k-mer goes to BuildSink::insert
+template <int FAM>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+bns_build_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
+                 u64 n_seqs, u64 total_bases, BuildSink proto, u32 ring_cap) {
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, false), ring_cap);
+    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    BuildSink sink = proto;
+    sink.n_new = sink.n_fail = 0;
+    for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_seqs; r += nwarps) {
+        const u64 b = offsets[2 * r], e = offsets[2 * r + 1];           // (start, end) pairs: pieces may overlap
+        encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+    }
+    const u32 nn = __reduce_add_sync(FULL, sink.n_new), nf = __reduce_add_sync(FULL, sink.n_fail);
+    if(lane == 0) {
+        if(nn) atomicAdd(&sink.stats[3], (unsigned long long)nn);
+        if(nf) atomicAdd(&sink.stats[0], (unsigned long long)nf);
+    }
+}
+
+// table -> (key, value) pairs: the home bucket is bucket - disp, the key is unmix64(home : remainder)
+__global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, const u32 *__restrict__ dict,
+                                u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, u64 cap,
+                                unsigned long long *__restrict__ counter) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_buckets * 4) return;
+    const u64 v = slots[i];
+    if(v == ~0ull) return;
+    const u32 tag_shift = b - DISP_BITS;
+    const u64 bucket = i >> 2, disp = (v >> tag_shift) & ((1u << DISP_BITS) - 1);
+    const u64 home = (bucket - disp) & (n_buckets - 1);
+    const u64 h = (home << (64 - b)) | (v >> b);
+    const u64 at = atomicAdd(counter, 1ull);
+    if(at < cap) { keys_out[at] = unmix64(h); vals_out[at] = dict[(u32)v & ((1u << (tag_shift - 1)) - 1)]; }
+}
+
 // independent 32-byte loads at uniformly random buckets: the random-access ceiling the lookup is measured against
 __global__ void bns_gather_kernel(const u64 *__restrict__ slots, u32 b, u64 n_loads, u64 seed,
                                   unsigned long long *__restrict__ sink_out) {
@@ -868,6 +967,26 @@ int encode_occupancy(const EncParams &P, size_t smem) {
     cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, smem);
     return nb;
+}
+cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
+                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 vid, const TaxView &X, const u32 *values,
+                         u32 n_values, unsigned long long *stats, u32 ring_cap) {
+    BuildSink sk;
+    sk.slots = slots; sk.b = b; sk.tag_shift = b - DISP_BITS; sk.val_mask = (1u << (b - DISP_BITS - 1)) - 1; sk.vid = vid;
+    sk.val_info = X.val_info; sk.node_info = X.node_info; sk.values = values; sk.n_values = n_values;
+    sk.node_of_one = X.node_of_one; sk.stats = stats; sk.n_new = sk.n_fail = 0;
+    void (*f)(const EncParams, const char *, const u64 *, u64, u64, BuildSink, u32) =
+        P.family == FAM_U ? bns_build_kernel<FAM_U> : P.family == FAM_K ? bns_build_kernel<FAM_K>
+        : P.family == FAM_R ? bns_build_kernel<FAM_R> : bns_build_kernel<FAM_NONE>;
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, sk, ring_cap);
+    return cudaGetLastError();
+}
+cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, const u32 *dict, u64 *keys_out, u32 *vals_out,
+                        u64 cap, unsigned long long *counter) {
+    const u64 n = n_buckets * 4;
+    bns_dump_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, dict, keys_out, vals_out, cap, counter);
+    return cudaGetLastError();
 }
 cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
                           u32 n_values, unsigned long long *stats) {

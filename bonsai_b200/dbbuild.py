@@ -86,3 +86,24 @@ def build_db(genomes, taxids, tax_child, tax_parent, k, w, gaps=None, score=capi
              entropy_cast=capi.CAST_SATURATE, device=-1):
     sets = genome_kmer_sets(genomes, k, w, gaps, score, canonicalize, entropy_cast, device)
     return merge_lca(sets, taxids, tax_child, tax_parent)
+
+
+def build_on_device(ctx, genomes, taxids, tax_child, tax_parent, k, w, gaps=None, score=capi.SCORE_LEX, canonicalize=True,
+                    entropy_cast=capi.CAST_SATURATE, max_kmers=None):
+    """`bonsai build` entirely on the GPU, into `ctx`'s own table: the context is switched to the database's encoder
+    (record overloads), every genome is streamed through bns_b200_build_add_genome (encode -> insert-or-LCA-merge in one
+    kernel), and the caller's classification encoder is restored by the caller with ctx.reconfigure(...)."""
+    ctx.load_taxonomy(tax_child, tax_parent)
+    ctx.reconfigure(k, w, gaps, score, canonicalize, capi.API_PATH, entropy_cast)
+    bound = max_kmers or max(1024, int(sum(int(o[-1] - o[0]) for _, o in genomes)))
+    while True:
+        ctx.build_begin(bound, taxids)
+        for (bases, offsets), t in zip(genomes, taxids):
+            ctx.build_add_genome(bases, offsets, t)
+        try:
+            ctx.build_finish()
+            return ctx.table_info()
+        except capi.BnsError as e:
+            if e.code != -6:
+                raise
+            bound *= 2

@@ -110,6 +110,21 @@ int bns_b200_lookup_batch(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uin
 /* number of 32-byte buckets (DRAM sectors) the probes of `keys` touch in total: the p-bar of SURVEY 8(d) */
 int bns_b200_lookup_sectors(bns_b200_t *ctx, const uint64_t *keys, uint64_t n, uint64_t *sectors_out);
 
+/* ---- database construction on the device: `bonsai build` ----------------------------------------------------
+ * fill_set_genome + update_lca_map (include/bonsai/feature_min.h:68-83,205-228): the k-mer / minimizer SET of every
+ * genome (encoder = this context's configuration, normally BNS_API_PATH) is inserted with the genome's taxid, or merged
+ * with lca(tax, taxid, old) where the key already exists. Needs the taxonomy. `taxids` announces every taxid that
+ * add_genome will use (their ancestors become the value dictionary); max_kmers bounds the distinct keys
+ * (BNS_E_CAPACITY from build_finish means: begin again with a larger bound). */
+int bns_b200_build_begin(bns_b200_t *ctx, uint64_t max_kmers, const uint32_t *taxids, uint32_t n_taxids);
+int bns_b200_build_add_genome(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_records, uint32_t taxid);
+int bns_b200_build_finish(bns_b200_t *ctx);
+/* the resident table as (key, value) pairs in no particular order; cap = 0 only reports the count in *n_out */
+int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out, uint64_t cap, uint64_t *n_out);
+/* change the Spacer / Encoder configuration of a context, keeping its table and taxonomy (a DB is minimised with one
+ * encoder and queried with another: bin/bonsai.cpp:152) */
+int bns_b200_reconfigure(bns_b200_t *ctx, const bns_b200_config *cfg);
+
 /* ---- taxonomy: khash_t(p) child -> parent ---------------------------------------------------------
  * build_parent_map, include/bonsai/util.h:766-785 (taxid 1 is forced to parent 0) */
 int bns_b200_load_taxonomy(bns_b200_t *ctx, const uint32_t *child, const uint32_t *parent, uint64_t n);

@@ -527,7 +527,7 @@ struct PinnedBatch {
         size_t ncap = std::max<size_t>(need, cap ? cap * 2 : 1 << 16);
         void *np = nullptr;
         if(bns_b200_host_alloc(&np, ncap * sizeof(T))) BNS_RUNTIME_ERROR("pinned host allocation failed");
-        if(used) std::memcpy(np, p, used * sizeof(T));
+        if(used && p) std::memcpy(np, p, used * sizeof(T));
         bns_b200_host_free(p);
         p = (T *)np; cap = ncap;
     }
