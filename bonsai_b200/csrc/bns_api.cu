@@ -741,7 +741,36 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
     if(h[0]) return ctx->fail(BNS_E_CAPACITY, "%llu k-mers found no slot: call build_begin with a larger max_kmers", h[0]);
     ctx->n_displaced = 0;
     ctx->tax_ready = true;
-    return refresh_table_stats(ctx);
+    int rc = refresh_table_stats(ctx);
+    if(rc != BNS_OK) return rc;
+    // The table was sized for the caller's bound; minimised sets are far smaller. Re-home the entries into a table of the
+    // right size (device to device) so that a small database stays L2-resident.
+    for(u32 want = choose_bits(ctx->n_keys, (u32)ctx->values.size()); want < ctx->bucket_bits; ++want) {
+        cudaStream_t st = ctx->slots[0].st;
+        const u64 n = ctx->n_keys;
+        u64 *dk = nullptr, *new_slots = nullptr;
+        u32 *dv = nullptr;
+        CK(cudaMalloc((void **)&dk, std::max<u64>(n, 1) * 8));
+        CK(cudaMalloc((void **)&dv, std::max<u64>(n, 1) * 4));
+        CK(cudaMalloc((void **)&new_slots, (1ull << want) * 32));
+        CK(cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st));
+        CK(cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st));
+        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_values, dk, dv, n, ctx->d_counters + 12));
+        CK(launch_insert(st, new_slots, want, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
+        ctx->stats.kernel_launches += 2;
+        unsigned long long h2[3];
+        CK(cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(dk); cudaFree(dv);
+        if(h2[0] || h2[2]) { cudaFree(new_slots); continue; }          // no room at this size: try one bit more
+        cudaFree(ctx->d_slots);
+        ctx->d_slots = new_slots;
+        ctx->bucket_bits = want;
+        ctx->n_buckets = 1ull << want;
+        ctx->n_displaced = h2[1];
+        return refresh_table_stats(ctx);
+    }
+    return BNS_OK;
 }
 
 int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out, uint64_t cap, uint64_t *n_out) {
