@@ -3,8 +3,6 @@
 // update_lca_map merge -> the DB file layout the reference intends), `dbwrite` / `dbcheck` (DB file tooling).
 #include <getopt.h>
 
-#include <map>
-#include <set>
 
 #include "../../../include/bonsai_b200/bonsai.hpp"
 
@@ -60,50 +58,12 @@ static int classify_main(int argc, char *argv[]) {
     return EXIT_SUCCESS;
 }
 
-// lca, util.h:634-663 over a std::map child -> parent
-static tax_t lca(const std::map<tax_t, tax_t> &pm, tax_t a, tax_t b) {
-    if(a == b) return a;
-    if(b == 0) return a;
-    if(a == 0) return b;
-    std::vector<tax_t> nodes;
-    while(a) {
-        nodes.push_back(a);
-        auto it = pm.find(a);
-        if(it == pm.end()) return tax_t(-1);
-        a = it->second;
-    }
-    while(b) {
-        if(std::find(nodes.begin(), nodes.end(), b) != nodes.end()) return b;
-        auto it = pm.find(b);
-        if(it == pm.end()) return tax_t(-1);
-        b = it->second;
-    }
-    return 1;
-}
-
 static int build_usage(const char *ex) {
     std::fprintf(stderr,
                  "Usage:\n%s build <opts> <dbpath> <tax_path> <taxid=genome.fa[.gz]> ...\nFlags:\n-k:\tk-mer length [31]\n"
                  "-w:\twindow size [k]\n-s:\tspacing string, e.g. 1x3,0x5 [unspaced]\n-e:\tminimise by entropy instead of Lex\n"
                  "-C:\tDo not canonicalize\n-z:\tgzip the database\n", ex);
     return EXIT_FAILURE;
-}
-
-// fill_set_genome + update_lca_map (feature_min.h:68-83,205-228) with the GPU encoder, then Database::write
-template <typename Score>
-static void build_sets(const Spacer &sp, bool canon, const std::vector<std::pair<tax_t, std::string>> &genomes,
-                       const std::map<tax_t, tax_t> &pm, std::map<u64, tax_t> &kc) {
-    Encoder<Score> enc(sp, canon);
-    for(const auto &g : genomes) {
-        std::set<u64> kmers;
-        enc.for_each([&](u64 x) { kmers.insert(x); }, g.second.c_str());
-        for(const u64 x : kmers) {
-            auto it = kc.find(x);
-            if(it == kc.end()) kc.emplace(x, g.first);
-            else if(it->second != g.first) it->second = lca(pm, g.first, it->second);
-        }
-        std::fprintf(stderr, "[build] %s (taxid %u): %zu distinct k-mers, database now %zu\n", g.second.c_str(), g.first, kmers.size(), kc.size());
-    }
 }
 
 static int build_main(int argc, char *argv[]) {
@@ -126,20 +86,47 @@ static int build_main(int argc, char *argv[]) {
         const spvec_t gaps = parse_spacing(spacing.c_str(), k);
         Spacer sp(k, w < 0 ? k : w, gaps);
         std::unique_ptr<TaxMap> tm(build_parent_map(argv[optind + 1]));
-        std::map<tax_t, tax_t> pm;
-        for(size_t i = 0; i < tm->size(); ++i) pm[tm->child[i]] = tm->parent[i];
         std::vector<std::pair<tax_t, std::string>> genomes;
         for(int i = optind + 2; i < argc; ++i) {
             const char *eq = std::strchr(argv[i], '=');
             if(!eq) { std::fprintf(stderr, "expected taxid=path, got %s\n", argv[i]); return EXIT_FAILURE; }
             genomes.emplace_back((tax_t)std::atoi(argv[i]), std::string(eq + 1));
         }
-        std::map<u64, tax_t> kc;
-        if(entropy) build_sets<score::Entropy>(sp, canon, genomes, pm, kc);
-        else build_sets<score::Lex>(sp, canon, genomes, pm, kc);
-        std::vector<u64> keys; std::vector<u32> vals;
-        keys.reserve(kc.size()); vals.reserve(kc.size());
-        for(const auto &kv : kc) { keys.push_back(kv.first); vals.push_back(kv.second); }
+        // fill_set_genome + update_lca_map (feature_min.h:68-83,205-228) on the device: every genome's records go through
+        // the encoder's record overloads and an insert-or-LCA-merge into the device table, in one kernel per genome.
+        auto h = detail::open_handle(sp, entropy ? BNS_SCORE_ENTROPY : BNS_SCORE_LEX, canon && sp.unspaced(), BNS_API_PATH);
+        detail::check(h->h, bns_b200_load_taxonomy(h->h, tm->child.data(), tm->parent.data(), tm->size()), "bns_b200_load_taxonomy");
+        std::vector<std::string> bases(genomes.size());
+        std::vector<std::vector<u64>> offs(genomes.size());
+        std::vector<tax_t> taxids;
+        u64 bound = 1024;
+        for(size_t g = 0; g < genomes.size(); ++g) {
+            detail::KSeq ks(genomes[g].second.c_str());
+            offs[g].push_back(0);
+            while(ks.read() >= 0) { bases[g] += ks.seq; offs[g].push_back(bases[g].size()); }
+            taxids.push_back(genomes[g].first);
+            bound += bases[g].size();
+        }
+        for(;; bound *= 2) {
+            detail::check(h->h, bns_b200_build_begin(h->h, bound, taxids.data(), (u32)taxids.size()), "bns_b200_build_begin");
+            for(size_t g = 0; g < genomes.size(); ++g)
+                detail::check(h->h, bns_b200_build_add_genome(h->h, bases[g].data(), offs[g].data(), offs[g].size() - 1, taxids[g]),
+                              "bns_b200_build_add_genome");
+            const int rc = bns_b200_build_finish(h->h);
+            if(rc == BNS_OK) break;
+            if(rc != BNS_E_CAPACITY) detail::check(h->h, rc, "bns_b200_build_finish");
+        }
+        u64 n = 0;
+        detail::check(h->h, bns_b200_table_dump(h->h, nullptr, nullptr, 0, &n), "bns_b200_table_dump");
+        std::vector<u64> keys(n); std::vector<u32> vals(n);
+        if(n) detail::check(h->h, bns_b200_table_dump(h->h, keys.data(), vals.data(), n, &n), "bns_b200_table_dump");
+        {   // deterministic file: insert in key order
+            std::vector<std::pair<u64, u32>> kv(n);
+            for(u64 i = 0; i < n; ++i) kv[i] = {keys[i], vals[i]};
+            std::sort(kv.begin(), kv.end());
+            for(u64 i = 0; i < n; ++i) { keys[i] = kv[i].first; vals[i] = kv[i].second; }
+        }
+        std::fprintf(stderr, "[build] %zu genomes -> %" PRIu64 " distinct k-mers\n", genomes.size(), n);
         Database db;
         db.assign(k, sp.w_, gaps, keys.data(), vals.data(), keys.size());
         db.write(argv[optind], gz);
