@@ -95,6 +95,14 @@ def workload_spec(name):
         return dict(db=dict(k=K, w=K, gaps=W.SPACED_GAPS, score=capi.SCORE_LEX, canon=False),
                     cls=dict(k=K, w=K, gaps=W.SPACED_GAPS, canon=False, api=capi.API_PATH), n_lookup=L_READ - 40 + 1,
                     label="synthetic 150bp reads, spaced seed k=31 comb=40 (for_each_uncanon_spaced), spaced 4-genome DB")
+    if name == "win50lex":       # Encoder-API-level windowed minimizers on the reads (for_each_canon_windowed, W = 20)
+        return dict(db=dict(k=K, w=K, gaps=None, score=capi.SCORE_LEX, canon=True),
+                    cls=dict(k=K, w=50, gaps=None, canon=True, api=capi.API_STRING), n_lookup=L_READ - 50 + 1,
+                    label="synthetic 150bp reads, Lex minimizers w=50 canonical on the reads (101 lookups/read), full 4-genome DB")
+    if name == "win50ent":       # rolling entropy minimizers (for_each_canon_unspaced_windowed_entropy_), tail flush
+        return dict(db=dict(k=K, w=50, gaps=None, score=capi.SCORE_ENTROPY, canon=True),
+                    cls=dict(k=K, w=50, gaps=None, canon=True, api=capi.API_STRING, score=capi.SCORE_ENTROPY), n_lookup=L_READ - 50 + 1,
+                    label="synthetic 150bp reads, entropy minimizers w=50 canonical on the reads, entropy-min 4-genome DB")
     if name == "stress":
         return dict(db=None, cls=dict(k=K, w=K, gaps=None, canon=True, api=capi.API_STRING), n_lookup=L_READ - K + 1,
                     label="synthetic 150bp reads vs synthetic random-stream DB (HBM-bound lookup stress, BASELINE config 5 scaled "
@@ -109,7 +117,7 @@ def build_database(ctx, spec, g):
     d, c = spec["db"], spec["cls"]
     genomes = [W.genome_records(g, gi) for gi in range(4)]
     dbbuild.build_on_device(ctx, genomes, W.GENOME_TAXIDS, tc, tp, d["k"], d["w"], d["gaps"], d["score"], d["canon"])
-    ctx.reconfigure(c["k"], c["w"], c["gaps"], capi.SCORE_LEX, c["canon"], c["api"])
+    ctx.reconfigure(c["k"], c["w"], c["gaps"], c.get("score", capi.SCORE_LEX), c["canon"], c["api"])
 
 
 def run_reference(args, spec):
@@ -197,7 +205,7 @@ def main():
 
     g = W.load_genomes()
     c = spec["cls"]
-    ctx = capi.Context(c["k"], c["w"], c["gaps"], capi.SCORE_LEX, c["canon"], c["api"], device=local_rank)
+    ctx = capi.Context(c["k"], c["w"], c["gaps"], c.get("score", capi.SCORE_LEX), c["canon"], c["api"], device=local_rank)
     # ---- database: built on rank 0, replicated with one broadcast ------------------------------------
     t_db0 = time.perf_counter()
     keys = vals = None
@@ -320,7 +328,7 @@ def main():
     ns = min(n, 50_000)
     samp_b = d_bases[: ns * L_READ].cpu().numpy()
     samp_o = d_offs[: ns + 1].cpu().numpy().astype(np.uint64)
-    with capi.Context(c["k"], c["w"], c["gaps"], capi.SCORE_LEX, c["canon"], c["api"], device=local_rank) as ectx:
+    with capi.Context(c["k"], c["w"], c["gaps"], c.get("score", capi.SCORE_LEX), c["canon"], c["api"], device=local_rank) as ectx:
         km, oo, cnt = ectx.encode(samp_b, samp_o)
         idx = np.repeat(oo[:-1], cnt) + (np.arange(int(cnt.sum()), dtype=np.uint64) - np.repeat(np.cumsum(cnt, dtype=np.uint64) - cnt, cnt))
         sample_kmers = km[idx.astype(np.int64)]
@@ -358,12 +366,12 @@ def main():
         nb = 20000
         sb, so = d_bases[: nb * L_READ].cpu().numpy(), d_offs[: nb + 1].cpu().numpy().astype(np.uint64)
         t0 = time.perf_counter()
-        cpu.classify(db, T, sb, so, c["k"], c["w"], c["gaps"], 0, c["canon"], c["api"], nthreads=nthreads)
+        cpu.classify(db, T, sb, so, c["k"], c["w"], c["gaps"], c.get("score", 0), c["canon"], c["api"], nthreads=nthreads)
         rate = nb / (time.perf_counter() - t0)
         nb = int(max(20000, min(n, rate * 10.0)))
         sb, so = d_bases[: nb * L_READ].cpu().numpy(), d_offs[: nb + 1].cpu().numpy().astype(np.uint64)
         t0 = time.perf_counter()
-        ct, _, _ = cpu.classify(db, T, sb, so, c["k"], c["w"], c["gaps"], 0, c["canon"], c["api"], nthreads=nthreads)
+        ct, _, _ = cpu.classify(db, T, sb, so, c["k"], c["w"], c["gaps"], c.get("score", 0), c["canon"], c["api"], nthreads=nthreads)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": nb / dt / 1e6, "unit": "Mreads/s", "cores": nthreads, "kind": cpu.kind,
                         "sample": "first %d reads of this run's batch, same DB and taxonomy" % nb,

@@ -170,9 +170,38 @@ static int dbcheck_main(int argc, char *argv[]) {
     return EXIT_SUCCESS;
 }
 
+// hist_main, bin/bonsai.cpp:351-374: how many k-mers each taxid owns, ascending by count (ties by taxid)   (host only)
+static int hist_main(int argc, char *argv[]) {
+    if(argc < 3 || !std::strcmp(argv[2], "-h") || !std::strcmp(argv[2], "--help")) {
+        std::fprintf(stderr, "Produces a histogram of how many kmers have been assigned to all taxids\n"
+                             "Usage: bonsai %s <database.db> [outfile (omit to emit to stdout)]\n", argv[1]);
+        return EXIT_FAILURE;
+    }
+    try {
+        Database db(argv[2]);
+        std::vector<tax_t> v;
+        for(u64 i = 0; i < db.n_buckets; ++i) if(db.exists(i)) v.push_back(db.vals[i]);
+        std::sort(v.begin(), v.end());
+        std::vector<std::pair<u32, tax_t>> structs;
+        for(size_t i = 0; i < v.size();) {
+            size_t j = i;
+            while(j < v.size() && v[j] == v[i]) ++j;
+            structs.emplace_back((u32)(j - i), v[i]);
+            i = j;
+        }
+        std::sort(structs.begin(), structs.end());
+        std::FILE *ofp = argc > 3 ? std::fopen(argv[3], "w") : stdout;
+        if(!ofp) BNS_RUNTIME_ERROR("cannot open output file");
+        std::fputs("Name\tCount\n", ofp);
+        for(const auto &e : structs) std::fprintf(ofp, "%u\t%u\n", e.second, e.first);
+        if(ofp != stdout) std::fclose(ofp);
+    } catch(const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+}
+
 static int usage(const char *ex) {
     std::fprintf(stderr, "Usage: %s <subcommand> [options...]. Use %s <subcommand> for more options.\n"
-                         "Subcommands:\nclassify\nbuild\ndbwrite\ndbcheck\n", ex, ex);
+                         "Subcommands:\nclassify\nbuild\nhist\ndbwrite\ndbcheck\n", ex, ex);
     return EXIT_FAILURE;
 }
 
@@ -181,6 +210,7 @@ int main(int argc, char *argv[]) {                          // bin/bonsai.cpp:52
     const std::string cmd(argv[1]);
     if(cmd == "classify") return classify_main(argc - 1, argv + 1);
     if(cmd == "build" || cmd == "phase2" || cmd == "p2") return build_main(argc - 1, argv + 1);
+    if(cmd == "hist") return hist_main(argc, argv);
     if(cmd == "dbwrite") return dbwrite_main(argc, argv);
     if(cmd == "dbcheck") return dbcheck_main(argc, argv);
     return usage(argv[0]);

@@ -67,3 +67,19 @@ def test_cli_usage(cli):
     assert r.returncode != 0 and "classify" in r.stderr
     r = subprocess.run([cli, "classify"], capture_output=True, text=True)
     assert r.returncode != 0 and "-k:\tEmit kraken-style output." in r.stderr
+
+
+def test_hist(cli, tmp_path):
+    keys = np.arange(1, 1001, dtype=np.uint64) * np.uint64(7919)
+    vals = np.where(np.arange(1000) % 10 == 0, 20, np.where(np.arange(1000) % 3 == 0, 11, 12)).astype(np.uint32)
+    pairs = tmp_path / "p.bin"
+    with open(pairs, "wb") as f:
+        f.write(struct.pack("<Q", keys.size)); f.write(keys.tobytes()); f.write(vals.tobytes())
+    db = tmp_path / "h.db"
+    subprocess.check_call([cli, "dbwrite", str(db), "31", "50", str(pairs)])
+    out = subprocess.check_output([cli, "hist", str(db)], text=True).splitlines()
+    assert out[0] == "Name\tCount"
+    rows = [tuple(map(int, l.split("\t"))) for l in out[1:]]
+    u, c = np.unique(vals, return_counts=True)
+    assert sorted(rows) == sorted(zip(u.tolist(), c.tolist()))
+    assert [r[1] for r in rows] == sorted(r[1] for r in rows)
