@@ -30,8 +30,8 @@ constexpr int VI_CAP = 512;                              // val_info records sta
 struct WarpSmem {
     u32 *codes;      // [NWORDS] 16 bases per word, first base in the top bits
     u32 *bad;        // [NWORDS] 16 invalid-bits per word (low half), first base in bit 15
-    u64 *rel;        // [ring_cap] window ring: elements
-    u64 *rsc;        // [ring_cap] window ring: scores
+    ulonglong2 *raw; // [ring_cap] window ring: (element, score) pairs, the last W-1 carried across tiles
+    ulonglong2 *work;// [ring_cap] sliding minima over 2^j elements (sparse-table levels, rebuilt per tile)
     u32 *ids;        // [AGG_CAP] distinct value ids      (ClassifySink)
     u32 *cnt;        // [AGG_CAP] their counts
     u32 *tin;        // [AGG_CAP] scratch for resolve
@@ -40,8 +40,8 @@ struct WarpSmem {
 
 __host__ __device__ inline size_t warp_smem_bytes(u32 ring_cap, bool classify) {
     size_t b = 2 * NWORDS * sizeof(u32);
-    b = (b + 7) & ~size_t(7);
-    b += 2 * (size_t)ring_cap * sizeof(u64);
+    b = (b + 15) & ~size_t(15);
+    b += 2 * (size_t)ring_cap * sizeof(ulonglong2);
     if(classify) b += 4 * AGG_CAP * sizeof(u32);
     return (b + 15) & ~size_t(15);
 }
@@ -50,10 +50,10 @@ __device__ inline WarpSmem carve(unsigned char *base, u32 ring_cap) {
     s.codes = (u32 *)base;
     s.bad = s.codes + NWORDS;
     size_t off = 2 * NWORDS * sizeof(u32);
-    off = (off + 7) & ~size_t(7);
-    s.rel = (u64 *)(base + off);
-    s.rsc = s.rel + ring_cap;
-    off += 2 * (size_t)ring_cap * sizeof(u64);
+    off = (off + 15) & ~size_t(15);
+    s.raw = (ulonglong2 *)(base + off);
+    s.work = s.raw + ring_cap;
+    off += 2 * (size_t)ring_cap * sizeof(ulonglong2);
     s.ids = (u32 *)(base + off);
     s.cnt = s.ids + AGG_CAP;
     s.tin = s.cnt + AGG_CAP;
@@ -457,24 +457,62 @@ struct BuildSink {
 
 // ---------------------------------------------------------------------------------------------
 // window ring (QueueMap, qmap.h:79-96) over the elements a tile produced. `m` new elements were written to
-// S.rel/S.rsc[hist .. hist+m) by the caller. Produces the window minima for the new elements this lane owns
+// S.raw[hist .. hist+m) by the caller. Produces the window minima for the new elements this lane owns
 // (indices j = PPL*lane + i) and rolls the ring forward. total_before = elements pushed before this tile.
 // ---------------------------------------------------------------------------------------------
+// (score, element) order of ElScore::operator< (qmap.h:23)
+__device__ __forceinline__ ulonglong2 pair_min(ulonglong2 a, ulonglong2 b) {
+    return (b.y < a.y || (b.y == a.y && b.x < a.x)) ? b : a;
+}
+// `m` new (element, score) pairs sit in S.raw[hist .. hist+m). Sliding minima over W elements in O(log W) passes:
+// level j holds min over the last 2^j elements; the window of W is the min of two overlapping windows of
+// t = 2^floor(log2 W). Only entries whose full window lies inside the buffer are used (g >= W-1 globally).
 __device__ __forceinline__ u32 window_outputs(const WarpSmem &S, u32 hist, u32 m, u64 total_before, u32 W, u32 lane,
                                               u64 (&o)[PPL]) {
+    const u32 have = hist + m;
+    if(m == 0) {                                       // warp-uniform: nothing new, nothing to emit
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) o[i] = KMER_NONE;
+        return 0;
+    }
+    // level 1: raw -> work
+    for(u32 g = lane; g < have; g += 32) {
+        ulonglong2 v = S.raw[g];
+        if(g >= 1) v = pair_min(v, S.raw[g - 1]);
+        S.work[g] = v;
+    }
+    __syncwarp();
+    u32 t = 2;
+    for(; t * 2 <= W; t *= 2) {                       // work[g] = min(work[g], work[g - t]) : window 2t, in place
+        // Rounds of 8 x 32 entries, from the top of the buffer downwards: a round reads only indices <= its own, so the
+        // rounds below it are still at the old level; inside a round every read precedes every write.
+        for(int base = (int)((have - 1) / 256) * 256; base >= 0; base -= 256) {
+            ulonglong2 v[8];
+#pragma unroll
+            for(int r = 0; r < 8; ++r) {
+                const u32 g = (u32)base + lane + 32 * r;
+                if(g < have) { v[r] = S.work[g]; if(g >= t) v[r] = pair_min(v[r], S.work[g - t]); }
+            }
+            __syncwarp();
+#pragma unroll
+            for(int r = 0; r < 8; ++r) {
+                const u32 g = (u32)base + lane + 32 * r;
+                if(g < have) S.work[g] = v[r];
+            }
+            __syncwarp();
+        }
+    }
     u32 mask = 0;
+    const u32 back = W - t;                            // second window starts `back` elements earlier (0 if W == t)
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         const u32 j = PPL * lane + i;
         o[i] = KMER_NONE;
         if(j < m && total_before + j + 1 >= W) {
-            const u32 end = hist + j;                 // inclusive
-            u64 be = S.rel[end], bs = S.rsc[end];
-            for(u32 t = 1; t < W; ++t) {
-                const u64 e = S.rel[end - t], s = S.rsc[end - t];
-                if(s < bs || (s == bs && e < be)) { be = e; bs = s; }     // ElScore::operator<, qmap.h:23
-            }
-            o[i] = be;
+            const u32 g = hist + j;
+            ulonglong2 v = S.work[g];
+            if(back) v = pair_min(v, S.work[g - back]);
+            o[i] = v.x;
             mask |= 1u << i;
         }
     }
@@ -488,10 +526,10 @@ __device__ __forceinline__ u32 roll_ring(const WarpSmem &S, u32 hist, u32 m, u32
     if(src) {
         for(u32 base = 0; base < keep; base += 32) {
             const u32 i = base + lane;
-            u64 e = 0, s = 0;
-            if(i < keep) { e = S.rel[src + i]; s = S.rsc[src + i]; }
+            ulonglong2 e = make_ulonglong2(0, 0);
+            if(i < keep) e = S.raw[src + i];
             __syncwarp();
-            if(i < keep) { S.rel[i] = e; S.rsc[i] = s; }
+            if(i < keep) S.raw[i] = e;
             __syncwarp();
         }
     }
@@ -617,7 +655,7 @@ __device__ __forceinline__ void encode_sequence_g(const EncParams &cP, const War
             u32 idx = hist + ex;
 #pragma unroll
             for(int i = 0; i < PPL; ++i)
-                if(emask >> i & 1u) { S.rel[idx] = x[i]; S.rsc[idx] = score_of(cP, x[i]); ++idx; }
+                if(emask >> i & 1u) { S.raw[idx] = make_ulonglong2(x[i], score_of(cP, x[i])); ++idx; }
         }
         __syncwarp();
         u64 o[PPL];
@@ -633,11 +671,9 @@ __device__ __forceinline__ void encode_sequence_g(const EncParams &cP, const War
     }
     // tail flush: a queue that never filled emits its minimum once (encoder.h:304-305,343-344)
     if(cP.tail_flush && W > 1 && total > 0 && total < W) {
-        u64 be = S.rel[0], bs = S.rsc[0];
-        for(u32 t = 1; t < (u32)total; ++t) {
-            const u64 e = S.rel[t], s = S.rsc[t];
-            if(s < bs || (s == bs && e < be)) { be = e; bs = s; }
-        }
+        ulonglong2 best = S.raw[0];
+        for(u32 t = 1; t < (u32)total; ++t) best = pair_min(best, S.raw[t]);
+        const u64 be = best.x;
         u64 o[PPL] = {cP.canon_emit ? canonical(be, k) : be, KMER_NONE, KMER_NONE, KMER_NONE};
         __syncwarp();
         sink.consume(S, o, lane == 0 ? 1u : 0u, lane);
