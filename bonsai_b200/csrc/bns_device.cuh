@@ -35,7 +35,7 @@ constexpr int MAX_SEG = 32;
 constexpr int TILE = 128;        // k-mer positions per warp tile (4 per lane, lane-contiguous)
 constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
-constexpr int AGG_CAP = 128;     // distinct taxa tracked per record in shared memory
+constexpr int AGG_CAP = 256;     // distinct taxa tracked per record in shared memory (covers any read up to k+255 bases)
 constexpr int DISP_BITS = 4;     // slot displacement field; disp == 2^DISP_BITS - 1 is reserved for the empty slot
 constexpr int MAX_DISP = (1 << DISP_BITS) - 2;
 

@@ -398,3 +398,74 @@ def test_device_build_matches_reference(capi, golden, genomes, name):
         dbbuild.build_on_device(ctx, small, H.GENOME_TAXIDS, c, p, spec["k"], spec["w"], spec["gaps"], spec["score"], spec["canon"])
         k2, v2 = ctx.table_dump()
     assert np.array_equal(k1, k2) and np.array_equal(v1, v2)
+
+
+def test_error_paths(capi):
+    """every failure is an error code + message, never a crash"""
+    with pytest.raises(capi.BnsError) as e:
+        capi.Context(0)
+    assert e.value.code == -1
+    with pytest.raises(capi.BnsError):
+        capi.Context(33)
+    with pytest.raises(capi.BnsError) as e:
+        capi.Context(31, 31, [300] + [0] * 29)             # comb beyond the supported span
+    assert "comb" in str(e.value)
+    with capi.Context(31) as ctx:
+        b, o = po.pack_reads(["ACGT" * 40])
+        with pytest.raises(capi.BnsError) as e:             # classify before any table
+            ctx.classify(b, o)
+        assert e.value.code == -4
+        ctx.load_pairs(np.array([1, 2, 3], np.uint64), np.array([5, 6, 7], np.uint32))
+        with pytest.raises(capi.BnsError) as e:             # table but no taxonomy
+            ctx.classify(b, o)
+        assert e.value.code == -4
+        # a cycle in the taxonomy is rejected
+        ctx.load_taxonomy(np.array([5, 6, 7], np.uint32), np.array([6, 7, 5], np.uint32))
+        with pytest.raises(capi.BnsError) as e:
+            ctx.classify(b, o)
+        assert e.value.code == -5
+        # lenient where the reference is UB: a value (7) whose parent is not a node, values missing from the taxonomy
+        ctx.load_taxonomy(np.array([5, 6], np.uint32), np.array([1, 5], np.uint32))
+        t, h, m = ctx.classify(b, o)
+        assert t.tolist() == [0] and h.tolist() == [0] and m.tolist() == [130]
+        with pytest.raises(capi.BnsError):                  # build_add_genome without build_begin
+            ctx.build_add_genome(b, o, 5)
+
+
+def test_many_distinct_taxa_and_big_taxonomy(capi, oracle):
+    """records with dozens of distinct taxa on a 300 k-node, 2 000-deep taxonomy (iterative Euler tour, lca climbs)"""
+    rng = np.random.default_rng(9)
+    n = 300_000
+    nodes = np.arange(1, n + 1, dtype=np.uint32) * 3 + 1            # taxids 4, 7, 10, ... plus the root 1
+    nodes[0] = 1
+    parent = np.zeros(n, np.uint32)
+    parent[0] = 1
+    # a 2 000-long spine, everything else hangs off random earlier nodes
+    for i in range(1, 2000):
+        parent[i] = nodes[i - 1]
+    parent[2000:] = nodes[(rng.random(n - 2000) * np.arange(2000, n)).astype(np.int64)]
+    T = oracle.tax_from_pairs(nodes, parent)
+    # DB: random 31-mers of a random sequence, values drawn from 5 000 taxa (some deep on the spine)
+    seq = "".join(rng.choice(list("ACGT"), 40_000))
+    km = np.unique(oracle.encode(seq, 31, 31))
+    pool = np.concatenate([nodes[1500:2000], rng.choice(nodes, 4500, replace=False)])
+    vals = pool[rng.integers(0, pool.size, km.size)].astype(np.uint32)
+    D = oracle.db_from_pairs(km, vals)
+    reads = [seq[s:s + int(rng.integers(100, 280))] for s in rng.integers(0, len(seq) - 400, 300)]
+    b, o = po.pack_reads(reads)
+    with capi.Context(31) as ctx:
+        ctx.load_pairs(km, vals)
+        ctx.load_taxonomy(nodes, parent)
+        t, h, m = ctx.classify(b, o)
+    et, eh, em = oracle.classify(D, T, b, o, 31, 31)
+    assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
+    assert len(set(t.tolist())) > 50
+    # more than AGG_CAP (256) distinct taxa in one record is reported, not mis-classified
+    long_read = seq[:3000]
+    b2, o2 = po.pack_reads([long_read])
+    with capi.Context(31) as ctx:
+        ctx.load_pairs(km, (np.arange(km.size) % 4000 + 1).astype(np.uint32) * 3 + 1)
+        ctx.load_taxonomy(nodes, parent)
+        with pytest.raises(capi.BnsError) as e:
+            ctx.classify(b2, o2)
+        assert e.value.code == -6
