@@ -419,6 +419,12 @@ int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
         return BNS_E_CUDA;
     };
     if((e = cudaSetDevice(dev)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    // Optional knob: BNS_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity. Measured on B200 it changes nothing:
+    // a sector miss fills its whole 128-byte line whatever the limit (profiles/micro/gather_variants_r01.txt).
+    if(const char *env = getenv("BNS_B200_L2_FETCH")) {
+        const long g = atol(env);
+        if(g == 32 || g == 64 || g == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g); cudaGetLastError(); }
+    }
     cudaDeviceProp prop;
     if((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     ctx->n_sm = prop.multiProcessorCount;
