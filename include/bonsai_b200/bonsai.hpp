@@ -117,9 +117,9 @@ inline std::shared_ptr<Handle> open_handle(const Spacer &sp, u32 score, bool can
     const spvec_t gaps = sp.sub1();
     std::copy(gaps.begin(), gaps.end(), cfg.gaps);
     cfg.score = score; cfg.canonicalize = canon; cfg.api = api; cfg.device = device;
-    // the reference's entropy score casts a negative double to u64: do what THIS host's reference build would do
-    volatile double probe = -5.5;
-    cfg.entropy_cast = ((u64)probe == ~u64(0)) ? BNS_CAST_SATURATE : BNS_CAST_WRAP;
+    // the reference's entropy score casts a negative double to u64 (UB): do what a `-march=native` build of the reference
+    // does on THIS host -- vcvttsd2usi saturates where AVX-512 exists, the cvttsd2si sequence wraps elsewhere
+    cfg.entropy_cast = __builtin_cpu_supports("avx512f") ? BNS_CAST_SATURATE : BNS_CAST_WRAP;
     auto ret = std::make_shared<Handle>();
     const int rc = bns_b200_open(&cfg, &ret->h);
     if(rc) BNS_RUNTIME_ERROR(std::string("bns_b200_open: ") + bns_b200_last_error(nullptr));
@@ -160,11 +160,27 @@ struct KSeq {
         if(!append) out.clear();
         const size_t before = out.size();
         bool got_any = false;
-        int c;
-        while((c = getc_()) >= 0) {
+        int c = -1;
+        for(;;) {
+            if(pos >= end) {
+                if(eof) break;
+                const int n = gzread(fp, buf.data(), (unsigned)buf.size());
+                if(n <= 0) { eof = true; break; }
+                pos = 0; end = (size_t)n;
+            }
             got_any = true;
-            if(delim == SEP_SPACE ? std::isspace(c) : c == '\n') break;
-            out.push_back((char)c);
+            const unsigned char *p = buf.data() + pos, *stop = buf.data() + end, *q;
+            if(delim == SEP_LINE) q = static_cast<const unsigned char *>(std::memchr(p, '\n', (size_t)(stop - p)));
+            else { q = p; while(q < stop && !std::isspace(*q)) ++q; if(q == stop) q = nullptr; }
+            if(q) {                                            // delimiter inside the buffer: take the run in one append
+                out.append(reinterpret_cast<const char *>(p), (size_t)(q - p));
+                c = *q;
+                pos = (size_t)(q - buf.data()) + 1;
+                break;
+            }
+            out.append(reinterpret_cast<const char *>(p), (size_t)(stop - p));
+            pos = end;
+            c = -1;
         }
         if(!got_any) return -1;
         if(delim == SEP_LINE && out.size() > before && out.back() == '\r') out.pop_back();
@@ -532,6 +548,10 @@ struct PinnedBatch {
         p = (T *)np; cap = ncap;
     }
     void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); }
+    void reserve(size_t bases_hint) {                   // pinned allocations are slow: size the ring once per dataset
+        grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 4 + (1 << 16));
+        grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 32 + 1024);
+    }
     void push(KSeq *k) {
         trim_readno(k->name);
         grow(bases, cap_bases, n_bases, n_bases + k->seq.size() + 16);
@@ -591,6 +611,7 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     constexpr int NB = 3;
     detail::PinnedBatch ring[NB];
+    for(auto &b : ring) b.reserve(chunk_size);
     int state[NB] = {0, 0, 0};                   // 0 free, 1 filled, 2 end of input
     std::mutex mu;
     std::condition_variable cv;

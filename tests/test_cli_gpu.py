@@ -117,3 +117,24 @@ def test_classify_paired(setup, oracle, genomes):
     exp, _, _ = oracle.classify_text(setup["dbo"], setup["tax"], bases, offs, names, 31, 31, emit_all=True, emit_fastq=False,
                                      emit_kraken=True, paired=True)
     assert r.stdout == exp
+
+
+def test_build_entropy_minimised(setup, oracle, genomes):
+    """`bonsai build -e -w 50`: the entropy-minimised DB (the reference's path-overload encoder with ent_score) -- also
+    checks that the C++ layer picks the cast mode a -march=native reference build would have on this host"""
+    d = setup["dir"]
+    args, dbo = [], oracle.db_new()
+    mode = po.CAST_SATURATE if po.host_has_avx512() else po.CAST_WRAP
+    for gi, taxid in enumerate(H.GENOME_TAXIDS):
+        b, off = H.genome_records(genomes, gi)
+        recs = [bytes(b[:150_000]), bytes(b[200_000:350_000])]
+        args.append("%d=%s" % (taxid, d / ("g%d.fa%s" % (gi, ".gz" if gi == 1 else ""))))
+        oracle.db_add_genome(dbo, setup["tax"], recs, taxid, 31, 50, None, po.SCORE_ENTROPY, True, cast_mode=mode)
+    db = d / "ent.db"
+    subprocess.check_call([setup["cli"], "build", "-k", "31", "-w", "50", "-e", str(db), str(setup["nodes"])] + args)
+    out = subprocess.check_output([setup["cli"], "dbcheck", str(db)], text=True)
+    k, v = oracle.db_pairs(dbo)
+    with np.errstate(over="ignore"):
+        assert "k=31 w=50" in out and "occupied=%d " % k.size in out
+        assert "key_xor=%016x" % int(np.bitwise_xor.reduce(k)) in out
+        assert "val_sum=%d" % int(v.sum(dtype=np.uint64)) in out
