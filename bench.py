@@ -147,11 +147,18 @@ def run_reference(args, spec):
     c = spec["cls"]
     # size the per-step sample for ~5 s of CPU work
     probe_b, probe_o, _ = H.make_reads(20000, seed=99, genomes=g)
-    t0 = time.perf_counter()
-    cpu.classify(db, T, probe_b, probe_o, c["k"], c["w"], c["gaps"], 0, c["canon"], c["api"], nthreads=nthreads)
-    rate = 20000 / (time.perf_counter() - t0)
-    n = int(max(20000, min(args.reads, rate * 5.0)))
-    bases, offs, _ = H.make_reads(n, seed=1234, genomes=g)
+    for _ in range(2):                                # the first call pays for thread start-up and cold caches
+        t0 = time.perf_counter()
+        cpu.classify(db, T, probe_b, probe_o, c["k"], c["w"], c["gaps"], 0, c["canon"], c["api"], nthreads=nthreads)
+        rate = 20000 / (time.perf_counter() - t0)
+    n = int(max(20000, min(args.reads, rate * 3.0, 4_000_000)))
+    parts, done = [], 0
+    while done < n:                                   # generated in slices: the numpy generator is memory-hungry
+        m = min(500_000, n - done)
+        parts.append(H.make_reads(m, seed=1234 + len(parts), genomes=g)[0])
+        done += m
+    bases = np.concatenate(parts)
+    offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L_READ)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
