@@ -80,8 +80,18 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, u32 lane, u32 &total) {
 // tile's first base sits at coordinate `shift` because loads are 16-byte aligned) and whether any staged
 // base is invalid. One LDG.128 per lane covers the whole tile (<= 398 bytes).
 // ---------------------------------------------------------------------------------------------
+// The 16-byte block lane `lane` stages for a tile starting at `a0` with `nbases` bases in range (zero outside).
+__device__ __forceinline__ uint4 load_tile_block(const char *a0, u32 nbases, const char *buf_end, u32 lane) {
+    const u32 shift = (u32)((uintptr_t)a0 & 15u);
+    const u32 nblk = (shift + nbases + 15) >> 4;
+    const char *p = a0 - shift + 16 * lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if(lane < nblk && p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return v;
+}
 __device__ __forceinline__ u32 stage_tile(const EncParams &cP, const WarpSmem &S, const char *seq, u64 p0, u64 L, u32 span,
-                                          const char *buf_end, u32 lane, bool &any_invalid, u32 &t_carry) {
+                                          const char *buf_end, u32 lane, bool &any_invalid, u32 &t_carry,
+                                          const uint4 *pre = nullptr) {
     const char *a0 = seq + p0;
     const u32 shift = (u32)((uintptr_t)a0 & 15u);
     const char *aligned = a0 - shift;
@@ -93,8 +103,8 @@ __device__ __forceinline__ u32 stage_tile(const EncParams &cP, const WarpSmem &S
     uint4 v = make_uint4(0, 0, 0, 0);
     u32 suspicious = 0;
     if(lane < nblk) {
-        const char *p = aligned + 16 * lane;
-        if(p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p));
+        if(pre) v = *pre;                                   // this tile was requested while the previous record ran
+        else { const char *p = aligned + 16 * lane; if(p < buf_end) v = __ldg(reinterpret_cast<const uint4 *>(p)); }
         suspicious = pack16_fast(v, codes);
     }
     // common case: every staged byte is one of ACGTacgt -> no invalid-mask work at all
@@ -543,7 +553,7 @@ __device__ __forceinline__ u32 roll_ring(const WarpSmem &S, u32 hist, u32 m, u32
 // ---------------------------------------------------------------------------------------------
 template <class Sink>
 __device__ __forceinline__ void encode_sequence_u(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L,
-                                                  const char *buf_end, Sink &sink, u32 lane) {
+                                                  const char *buf_end, Sink &sink, u32 lane, const uint4 *pre = nullptr) {
     const u32 k = cP.k;
     if(L < k) return;                                            // has_next_kmer(), encoder.h:418,594
     const u64 npos = L - k + 1;
@@ -553,7 +563,7 @@ __device__ __forceinline__ void encode_sequence_u(const EncParams &cP, const War
     u32 t_carry = 0;
     for(u64 p0 = 0; p0 < npos; p0 += TILE) {
         bool any_invalid;
-        const u32 shift = stage_tile(cP, S, seq, p0, L, span, buf_end, lane, any_invalid, t_carry);
+        const u32 shift = stage_tile(cP, S, seq, p0, L, span, buf_end, lane, any_invalid, t_carry, p0 == 0 ? pre : nullptr);
         const u32 q0 = shift + PPL * lane;
         const u64 left = npos - p0;
         const u32 nlive = left > (u64)PPL * lane ? (u32)min((u64)PPL, left - (u64)PPL * lane) : 0u;
@@ -683,8 +693,8 @@ __device__ __forceinline__ void encode_sequence_g(const EncParams &cP, const War
 
 template <int FAM, class Sink>
 __device__ __forceinline__ void encode_sequence(const EncParams &cP, const WarpSmem &S, const char *seq, u64 L,
-                                                const char *buf_end, Sink &sink, u32 lane) {
-    if(FAM == FAM_U) encode_sequence_u(cP, S, seq, L, buf_end, sink, lane);
+                                                const char *buf_end, Sink &sink, u32 lane, const uint4 *pre = nullptr) {
+    if(FAM == FAM_U) encode_sequence_u(cP, S, seq, L, buf_end, sink, lane, pre);
     else if(FAM == FAM_K || FAM == FAM_R) encode_sequence_g<FAM>(cP, S, seq, L, buf_end, sink, lane);
     // FAM_NONE: the string overload with a spaced seed emits nothing (encoder.h:437-440)
 }
@@ -759,11 +769,45 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
     sink.vi = staged ? s_vi : X.val_info;
     if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
-    for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_records; r += nwarps) {
+    const char *buf_end = bases + total_bases;
+    const u64 r_first = (u64)blockIdx.x * WARPS_PER_CTA + wid;
+    if(FAM == FAM_U && mates == 1) {
+        // Software pipeline over this warp's records: the offsets of record r+2*nwarps and the first tile of record
+        // r+nwarps are requested before record r is processed, so neither the offset fetch nor the read bytes (both
+        // stream from HBM) stall the warp when their turn comes.
+        const u32 span = TILE + P.k - 1;
+        u64 b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if(r_first < n_records) {
+            b0 = offsets[r_first]; e0 = offsets[r_first + 1];
+            v0 = load_tile_block(bases + b0, (u32)min((u64)span, e0 - b0), buf_end, lane);
+        }
+        if(r_first + nwarps < n_records) { b1 = offsets[r_first + nwarps]; e1 = offsets[r_first + nwarps + 1]; }
+        for(u64 r = r_first; r < n_records; r += nwarps) {
+            u64 b2 = 0, e2 = 0;
+            if(r + 2 * nwarps < n_records) { b2 = offsets[r + 2 * nwarps]; e2 = offsets[r + 2 * nwarps + 1]; }
+            uint4 v1 = make_uint4(0, 0, 0, 0);
+            if(r + nwarps < n_records) v1 = load_tile_block(bases + b1, (u32)min((u64)span, e1 - b1), buf_end, lane);
+            sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
+            encode_sequence<FAM>(P, S, bases + b0, e0 - b0, buf_end, sink, lane, &v0);
+            const u32 taxon = sink.resolve(S, X, lane);
+            if(lane == 0) {
+                if(mate1_out) mate1_out[r] = sink.n_hit + sink.n_miss;
+                taxon_out[r] = taxon;
+                if(nhit_out) nhit_out[r] = sink.n_hit;
+                if(nmiss_out) nmiss_out[r] = sink.n_miss;
+                if(sink.overflow) atomicOr(status, 2u);
+            }
+            if(taxon) ++n_cls; else ++n_uncls;
+            __syncwarp();
+            b0 = b1; e0 = e1; v0 = v1; b1 = b2; e1 = e2;
+        }
+    } else
+    for(u64 r = r_first; r < n_records; r += nwarps) {
         sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
         for(u32 mt = 0; mt < mates; ++mt) {
             const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
-            encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
+            encode_sequence<FAM>(P, S, bases + b, e - b, buf_end, sink, lane);
             // k-mers the first mate produced (classify_seq's first ambig_count term, classifier.h:232)
             if(mt == 0 && mate1_out && lane == 0) mate1_out[r] = sink.n_hit + sink.n_miss;
         }
