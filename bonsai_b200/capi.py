@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("BNS_B200_LIB") or os.path.join(HERE, "libbonsai_b200.so")
+LIB_PATH = os.environ.get("BNS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonsai_b200.so")
 
 SCORE_LEX, SCORE_ENTROPY = 0, 1
 API_STRING, API_PATH = 0, 1

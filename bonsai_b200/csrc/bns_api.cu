@@ -374,6 +374,7 @@ int check_status(bns_b200_ctx *ctx, u32 st) {
     if(st & 2u) return ctx->fail(BNS_E_CAPACITY, "a record hit more than %d distinct taxa", AGG_CAP);
     if(st & 1u) return ctx->fail(BNS_E_CAPACITY, "an output window was too small for the k-mers produced");
     if(st & 4u) return ctx->fail(BNS_E_INVAL, "a taxid passed to resolve is not a database value");
+    if(st & 8u) return ctx->fail(BNS_E_CAPACITY, "a record is longer than 2^32-2 bases");
     return BNS_OK;
 }
 
@@ -1001,10 +1002,9 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     u64 total_bases = 0;
     CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
-    const int occ = classify_occupancy(ctx->enc, d_taxa != nullptr, smem);
+    const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false);
     CK(cudaEventRecord(ctx->ev0, st));
-    CK(launch_classify(ctx->enc, grid_for(ctx, n_rec, occ), smem, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
+    CK(launch_classify(ctx->enc, pl, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
                        table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
                        (const u64 *)d_taxa_offsets, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
     CK(cudaEventRecord(ctx->ev1, st));
@@ -1031,8 +1031,6 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
     const u32 mates = paired ? 2 : 1;
     const u64 n_rec_total = n_reads / mates;
     if(!n_rec_total) return BNS_OK;
-    const size_t smem = stream_smem_bytes(ctx->ring_cap, true);
-    const int occ = classify_occupancy(ctx->enc, taxa_out != nullptr, smem);
     CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
     CK(cudaStreamSynchronize(ctx->slots[0].st));
     int slot_i = 0;
@@ -1058,7 +1056,8 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
         CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        CK(launch_classify(ctx->enc, grid_for(ctx, nq, occ), smem, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
+        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr);
+        CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
                            taxa_out ? s.d_taxa_offsets : nullptr, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap,
@@ -1079,7 +1078,7 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
     for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st));
     u32 status = 0;
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
-    return check_status(ctx, status & 2u);
+    return check_status(ctx, status & 10u);
 }
 
 int bns_b200_sync(bns_b200_t *ctx) {

@@ -1,0 +1,286 @@
+// bns_classify_u.cuh -- the lean kernel for what `bonsai classify` always runs (bin/bonsai.cpp:152: k == w, no spaced
+// seed): single-end records, every (canonical) k-mer of the record looked up, taxon by resolve_tree, no ordered hit list.
+// Included by bns_kernels.cu after the shared building blocks (ClassifySink, probe_displaced, the TMA staging helpers).
+//
+// Same algorithm and table as bns_classify_kernel<FAM_U,false>; what differs is the bookkeeping around the k-mers, which
+// was two thirds of the instructions there (ncu, profiles/ncu_r01e_classify.txt):
+//   * a warp takes a BATCH of 32 consecutive records: their offsets come in with one coalesced load (prefetched a batch
+//     ahead), each record's (start, length) reaches the warp by shuffle, and the 32 results leave with one coalesced store
+//     per output array;
+//   * the 2-bit words of the staged tile go from the lanes that packed them to the lanes that need them by SHFL, not
+//     through shared memory;
+//   * everything is 32-bit: the bucket arrives as eight u32 (LDG.256), the bucket address is one IMAD.WIDE, tags are
+//     funnel shifts;
+//   * the first distinct taxon of a record and its count live in (warp-uniform) registers; shared memory is touched
+//     only by records with >= 2 distinct taxa (resolve_tree's real work) -- 78 % of the classified reads have one;
+//   * displaced-key probes (home bucket overflowed at build time, ~0.6 % of lookups) run in one warp-level loop.
+#pragma once
+
+namespace bns {
+
+constexpr int RB = 32;                       // records per warp batch
+#ifndef BNS_CLASSIFY_U_MIN_CTAS
+#define BNS_CLASSIFY_U_MIN_CTAS 4
+#endif
+
+__device__ __forceinline__ void ld_bucket8(const void *p, u32 (&w)[8]) {
+    // one 32-byte sector per probe (LDG.E.256), as eight 32-bit words: {lo, hi} of slots 0..3
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+struct ProbeConst {                          // launch-uniform pieces of the slot format (bns_insert_kernel)
+    const char *slots;
+    u32 b, idx_shift;                        // bucket = h.hi >> idx_shift
+    u32 hm;                                  // bits of the low word that belong to {remainder, disp}
+    u32 novf;                                // "no key homed here was displaced" bit of slot 0
+    u32 val_mask;
+};
+
+// buckets after the home bucket for ONE key (rare). Returns the low word of the matching slot or ~tl ("no match").
+__device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 hl, u32 hh) {
+    const u32 b = Pc.b;
+    const u32 home = hh >> Pc.idx_shift, bmask = (b == 32) ? ~0u : ((1u << b) - 1);
+    const u32 th = __funnelshift_lc(hl, hh, b), tl0 = __funnelshift_lc(0u, hl, b);
+    const u32 tag_shift = b - DISP_BITS;
+    for(u32 d = 1; d <= (u32)MAX_DISP; ++d) {
+        u32 w[8];
+        ld_bucket8(Pc.slots + ((u64)((home + d) & bmask) << 5), w);
+        const u32 tl = tl0 | (d << tag_shift);
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+            if(w[2 * j + 1] == th && ((w[2 * j] ^ tl) & Pc.hm) == 0) return w[2 * j];
+        if((w[6] & w[7]) == ~0u) break;                               // a bucket with a free slot ends the run
+    }
+    return ~tl0;
+}
+
+template <bool CANON>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, BNS_CLASSIFY_U_MIN_CTAS)
+bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records,
+                      TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
+                      u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
+    __shared__ __align__(16) uint4 s_vi[VI_CAP];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
+    if(staged) tma_stage_val_info(s_vi, X.val_info, T.n_values * (u32)sizeof(uint4), &s_mbar);
+    WarpSmem S;                                                        // only the distinct-taxon lists are used here
+    S.ids = (u32 *)(g_smem + (size_t)wid * 4 * AGG_CAP * sizeof(u32));
+    S.cnt = S.ids + AGG_CAP; S.tin = S.cnt + AGG_CAP; S.tout = S.tin + AGG_CAP;
+    ClassifySink<false> sink;
+    sink.T = T;
+    sink.vi = staged ? s_vi : X.val_info;
+    sink.begin(nullptr);
+
+    ProbeConst Pc;
+    Pc.slots = (const char *)T.slots;
+    Pc.b = T.bucket_bits;
+    Pc.idx_shift = 32 - T.bucket_bits;
+    Pc.hm = ~0u << T.tag_shift;
+    Pc.novf = 1u << (T.tag_shift - 1);
+    Pc.val_mask = T.val_mask;
+    const u32 span = TILE + k - 1;
+    const u32 down = 64 - 2 * k;
+    const u32 kmask_lo = (u32)(~0ull >> down), kmask_hi = (u32)((~0ull >> down) >> 32);
+
+    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    const u64 n_batches = (n_records + RB - 1) / RB;
+    u64 bt = (u64)blockIdx.x * WARPS_PER_CTA + wid;
+    // lane j holds (start, length) of record j of the current batch (c*) and of the next one (n*)
+    u64 cb = 0, nb = 0;
+    u32 cl = 0, nl = 0;
+    auto fetch_offsets = [&](u64 batch, u64 &ob, u32 &ol) {
+        ob = 0; ol = 0;
+        const u64 r = batch * RB + lane;
+        if(batch < n_batches && r < n_records) {
+            ob = offsets[r];
+            const u64 len = offsets[r + 1] - ob;
+            ol = len < 0xffffffffull ? (u32)len : 0xffffffffu;
+        }
+    };
+    // the 16-byte block of a record's first tile this lane stages (zero outside the record)
+    auto first_block = [&](u64 rb, u32 rl) -> uint4 {
+        const char *a0 = bases + rb;
+        const u32 shift = (u32)((uintptr_t)a0 & 15u);
+        const u32 nblk = rl ? (shift + min(rl, span) + 15) >> 4 : 0u;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if(lane < nblk) v = __ldg(reinterpret_cast<const uint4 *>(a0 - shift) + lane);
+        return v;
+    };
+    fetch_offsets(bt, cb, cl);
+    fetch_offsets(bt + nwarps, nb, nl);
+    uint4 pre = first_block(__shfl_sync(FULL, cb, 0), __shfl_sync(FULL, cl, 0));
+    if(staged) mbar_wait(&s_mbar, 0);
+    u32 n_cls = 0, n_uncls = 0;
+
+    for(; bt < n_batches; bt += nwarps) {
+        u64 fb; u32 fl;
+        fetch_offsets(bt + 2 * nwarps, fb, fl);                        // arrives while this batch is processed
+        const u64 r0 = bt * RB;
+        const u32 nrec = (u32)min((u64)RB, n_records - r0);
+        u32 my_taxon = 0, my_hit = 0, my_miss = 0;
+        for(u32 j = 0; j < nrec; ++j) {
+            const u64 rb = __shfl_sync(FULL, cb, j);
+            const u32 L = __shfl_sync(FULL, cl, j);
+            // request the first tile of the record after this one before working on this one
+            uint4 pre_next;
+            {
+                const bool last = j + 1 == nrec;
+                const u64 xb = __shfl_sync(FULL, last ? nb : cb, last ? 0 : j + 1);
+                const u32 xl = __shfl_sync(FULL, last ? nl : cl, last ? 0 : j + 1);
+                pre_next = first_block(xb, xl);
+            }
+            // ---- per-record state: linear::counter with its first key in registers -----------------------------
+            u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
+            bool spilled = false;
+            if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
+            else if(L >= k) {
+                const u32 npos = L - k + 1;
+                for(u32 p0 = 0; p0 < npos; p0 += TILE) {
+                    // ---- stage: 16 bases per lane -> one 2-bit word per lane -----------------------------------
+                    const char *a0 = bases + rb + p0;
+                    const u32 shift = (u32)((uintptr_t)a0 & 15u);
+                    const u32 nblk = (shift + min(L - p0, span) + 15) >> 4;
+                    uint4 v = pre;
+                    if(p0) { v = make_uint4(0, 0, 0, 0); if(lane < nblk) v = __ldg(reinterpret_cast<const uint4 *>(a0 - shift) + lane); }
+                    u32 codes = 0, susp = 0;
+                    if(lane < nblk) susp = pack16_fast(v, codes);
+                    const bool slow = __any_sync(FULL, susp != 0);
+                    const u32 q0 = shift + PPL * lane, wi = q0 >> 4, s = (q0 & 15u) * 2u;
+                    const u32 w0 = __shfl_sync(FULL, codes, wi), w1 = __shfl_sync(FULL, codes, wi + 1),
+                              w2 = __shfl_sync(FULL, codes, wi + 2), w3 = __shfl_sync(FULL, codes, wi + 3);
+                    const u32 left = npos - p0;
+                    const u32 nlive = left > PPL * lane ? min((u32)PPL, left - PPL * lane) : 0u;
+                    u32 mask = (1u << nlive) - 1;
+                    if(slow) {                                         // some staged byte is not ACGTacgt (rare)
+                        u32 bad = 0, tm;
+                        if(lane < nblk) pack16(v, codes, bad, tm);
+                        const u32 b0 = __shfl_sync(FULL, bad, wi), b1 = __shfl_sync(FULL, bad, wi + 1),
+                                  b2 = __shfl_sync(FULL, bad, wi + 2), b3 = __shfl_sync(FULL, bad, wi + 3);
+                        const u64 B = ((u64)b0 << 48) | ((u64)b1 << 32) | ((u64)b2 << 16) | (u64)b3;   // coordinate 16*wi at bit 63
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i)
+                            if(((B << ((q0 & 15u) + i)) >> (64 - k)) != 0) mask &= ~(1u << i);
+                        n_emit += __reduce_add_sync(FULL, __popc(mask));
+                    } else n_emit += min(left, (u32)TILE);
+                    // ---- the lane's four k-mers (and reverse complements) out of one 96-bit window --------------
+                    const u32 A = __funnelshift_l(w1, w0, s), B_ = __funnelshift_l(w2, w1, s), C = __funnelshift_l(w3, w2, s);
+                    u32 R0 = 0, R1 = 0, R2 = 0;
+                    if(CANON) {
+                        R0 = __brev(C); R1 = __brev(B_); R2 = __brev(A);
+                        R0 = ~(((R0 >> 1) & 0x55555555u) | ((R0 & 0x55555555u) << 1));
+                        R1 = ~(((R1 >> 1) & 0x55555555u) | ((R1 & 0x55555555u) << 1));
+                        R2 = ~(((R2 >> 1) & 0x55555555u) | ((R2 & 0x55555555u) << 1));
+                    }
+                    u32 hl[PPL], hh[PPL], w[PPL][8];
+#pragma unroll
+                    for(int i = 0; i < PPL; ++i) {
+                        const u32 fh0 = __funnelshift_l(B_, A, 2 * i), fl0 = __funnelshift_l(C, B_, 2 * i);
+                        u32 xl, xh;                                                          // forward k-mer
+                        if(down < 32) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
+                        else { xl = fh0 >> (down - 32); xh = 0; }                            // k <= 16
+                        if(CANON) {
+                            const u32 rl = __funnelshift_r(R2, R1, 2 * i) & kmask_lo, rh = __funnelshift_r(R1, R0, 2 * i) & kmask_hi;
+                            const bool lt = xh < rh || (xh == rh && xl < rl);
+                            xl = lt ? xl : rl; xh = lt ? xh : rh;
+                        }
+                        // mix64 (bns_device.cuh) on 32-bit halves
+                        u64 x = ((u64)xh << 32) | (xl ^ xh);
+                        x *= 0xd6e8feb86659fd93ull;
+                        x ^= x >> 32;
+                        x *= 0xd6e8feb86659fd93ull;
+                        hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
+                        ld_bucket8(Pc.slots + ((u64)(hh[i] >> Pc.idx_shift) << 5), w[i]);
+                    }
+                    // ---- match: first slot whose high word equals the tag's, verified on the low word ------------
+                    u32 cand[PPL], okm = 0, more = 0;
+#pragma unroll
+                    for(int i = 0; i < PPL; ++i) {
+                        const u32 th = __funnelshift_lc(hl[i], hh[i], Pc.b), tl = __funnelshift_lc(0u, hl[i], Pc.b);
+                        u32 c = ~tl;
+                        c = w[i][7] == th ? w[i][6] : c;
+                        c = w[i][5] == th ? w[i][4] : c;
+                        c = w[i][3] == th ? w[i][2] : c;
+                        c = w[i][1] == th ? w[i][0] : c;                                       // slots fill in order: first match wins
+                        cand[i] = c;
+                        const bool ok = ((c ^ tl) & Pc.hm) == 0;
+                        if(ok) okm |= 1u << i;
+                        else if(!(w[i][0] & Pc.novf)) more |= 1u << i;
+                    }
+                    more &= mask;
+                    while(__any_sync(FULL, more != 0)) {               // keys displaced from a full home bucket (rare)
+                        if(more) {
+                            const u32 i = __ffs(more) - 1;
+                            more &= more - 1;
+                            const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
+                            const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
+                            const u32 c = probe_displaced32(Pc, l, h);
+                            if(c != ~__funnelshift_lc(0u, l, Pc.b)) {
+                                okm |= 1u << i;
+                                if(i == 0) cand[0] = c; else if(i == 1) cand[1] = c; else if(i == 2) cand[2] = c; else cand[3] = c;
+                            }
+                        }
+                    }
+                    // ---- hits -> per-record distinct-taxon counts (linear::counter::add, linear.h:229) -----------
+                    u32 todo = okm & mask;
+                    u32 bal = __ballot_sync(FULL, todo != 0);
+                    if(bal) {
+                        n_hit += __reduce_add_sync(FULL, __popc(todo));
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) cand[i] &= Pc.val_mask;
+                        do {
+                            const u32 leader = __ffs(bal) - 1;
+                            u32 fv = cand[3];
+                            if(todo & 4u) fv = cand[2];
+                            if(todo & 2u) fv = cand[1];
+                            if(todo & 1u) fv = cand[0];
+                            const u32 vv = __shfl_sync(FULL, fv, leader);
+                            u32 c = 0;
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i) if((todo >> i & 1u) && cand[i] == vv) { ++c; todo &= ~(1u << i); }
+                            const u32 total = __reduce_add_sync(FULL, c);
+                            if(nd == 0) { id0 = vv; cnt0 = total; nd = 1; }
+                            else if(!spilled && vv == id0) cnt0 += total;
+                            else {
+                                if(!spilled) {                         // second distinct taxon: move the list to shared memory
+                                    if(lane == 0) { S.ids[0] = id0; S.cnt[0] = cnt0; }
+                                    __syncwarp();
+                                    sink.n_distinct = 1;
+                                    spilled = true;
+                                }
+                                sink.add(S, vv, total, lane);
+                            }
+                            bal = __ballot_sync(FULL, todo != 0);
+                        } while(bal);
+                    }
+                }
+            }
+            // ---- resolve_tree (util.h:831-869) -------------------------------------------------------------------
+            u32 taxon = 0;
+            if(spilled) {
+                taxon = sink.resolve(S, X, lane);
+                if(sink.overflow && lane == 0) atomicOr(status, 2u);
+                sink.n_distinct = 0; sink.overflow = 0;
+                __syncwarp();
+            } else if(nd) taxon = sink.vi[id0].w;
+            if(lane == j) { my_taxon = taxon; my_hit = n_hit; my_miss = n_emit - n_hit; }
+            pre = pre_next;
+        }
+        // ---- one coalesced store per output array for the batch ------------------------------------------------------
+        if(lane < nrec) {
+            taxon_out[r0 + lane] = my_taxon;
+            if(nhit_out) nhit_out[r0 + lane] = my_hit;
+            if(nmiss_out) nmiss_out[r0 + lane] = my_miss;
+        }
+        const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
+        n_cls += cls; n_uncls += nrec - cls;
+        cb = nb; cl = nl; nb = fb; nl = fl;
+    }
+    if(lane == 0 && (n_cls | n_uncls)) {
+        atomicAdd(&counters[0], (unsigned long long)n_cls);
+        atomicAdd(&counters[1], (unsigned long long)n_uncls);
+    }
+}
+
+}  // namespace bns

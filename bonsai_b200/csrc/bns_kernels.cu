@@ -15,6 +15,7 @@
 // always runs, bin/bonsai.cpp:152) compiles to a lean kernel without the window / spaced-seed machinery.
 #include "bns_device.cuh"
 #include "bns_kernels.h"
+#include <algorithm>
 
 namespace bns {
 
@@ -989,6 +990,10 @@ __global__ void bns_gather_kernel(const u64 *__restrict__ slots, u32 b, u64 n_lo
     if(acc == 0x1234567u) *sink_out = acc;       // keep the loads alive
 }
 
+}  // namespace bns
+#include "bns_classify_u.cuh"
+namespace bns {
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (called from bns_api.cu)
 // ---------------------------------------------------------------------------------------------
@@ -1024,22 +1029,55 @@ cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_
                                              ring_cap, status);
     return cudaGetLastError();
 }
-cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
+// Which kernel a classify call runs and with what geometry. The lean kernel covers what `bonsai classify` runs (FAM_U,
+// single-end, no ordered hit list); everything else goes to the generic stream kernel.
+static bool lean_ok(const EncParams &P, u32 mates, bool taxa, bool mate1) {
+#ifdef BNS_NO_LEAN
+    return false;
+#endif
+    return P.family == FAM_U && mates == 1 && !taxa && !mate1;
+}
+typedef void (*classify_u_fn)(u32, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *, unsigned long long *, u32 *);
+static size_t lean_smem() { return (size_t)WARPS_PER_CTA * 4 * AGG_CAP * sizeof(u32); }
+
+ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1) {
+    ClassifyPlan pl;
+    pl.lean = lean_ok(P, mates, taxa, mate1);
+    int nb = 0;
+    if(pl.lean) {
+        classify_u_fn f = P.canon_elem ? bns_classify_u_kernel<true> : bns_classify_u_kernel<false>;
+        pl.smem = lean_smem();
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, pl.smem);
+        const u64 want = ((n_records + RB - 1) / RB + WARPS_PER_CTA - 1) / WARPS_PER_CTA;     // one batch per warp at least
+        pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
+    } else {
+        classify_fn f = pick_classify(P.family, taxa);
+        pl.smem = stream_smem_bytes(ring_cap, true);
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, pl.smem);
+        const u64 want = (n_records + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
+    }
+    pl.occupancy = nb;
+    return pl;
+}
+
+cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStream_t st, const char *bases, const u64 *offsets,
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status) {
+    if(pl.lean) {
+        classify_u_fn f = P.canon_elem ? bns_classify_u_kernel<true> : bns_classify_u_kernel<false>;
+        f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P.k, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
+                                                        counters, status);
+        return cudaGetLastError();
+    }
     classify_fn f = pick_classify(P.family, taxa_out != nullptr);
-    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
-                                             nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status);
+    f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
+                                                    nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status);
     return cudaGetLastError();
-}
-int classify_occupancy(const EncParams &P, bool taxa, size_t smem) {
-    int nb = 0;
-    classify_fn f = pick_classify(P.family, taxa);
-    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, smem);
-    return nb;
 }
 int encode_occupancy(const EncParams &P, size_t smem) {
     int nb = 0;

@@ -16,12 +16,13 @@ struct TableView;
 struct TaxView;
 
 size_t stream_smem_bytes(u32 ring_cap, bool classify);
-int classify_occupancy(const EncParams &P, bool taxa, size_t smem);
+struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false; int occupancy = 0; };
+ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1);
 int encode_occupancy(const EncParams &P, size_t smem);
 
 cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
                           u64 total_bases, u64 *kmers_out, const u64 *out_offsets, u32 *counts_out, u32 ring_cap, u32 *status);
-cudaError_t launch_classify(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
+cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
                             u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status);
