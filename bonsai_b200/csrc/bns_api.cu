@@ -1002,7 +1002,7 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     u64 total_bases = 0;
     CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false);
+    const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
     CK(cudaEventRecord(ctx->ev0, st));
     CK(launch_classify(ctx->enc, pl, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
                        table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
@@ -1056,7 +1056,8 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
         CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr);
+        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
+                                               n_hit_out || n_missing_out);
         CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,

@@ -55,14 +55,30 @@ __device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 hl, u3
     return ~tl0;
 }
 
-template <bool CANON>
+// 8 ASCII bases -> 16 bits of 2-bit codes (first base in the top bits); returns non-zero iff some byte is not ACGTacgt
+__device__ __forceinline__ u32 pack8_fast(uint2 v, u32 &codes16) {
+    u32 c0, c1;
+    const u32 d = pack4_fast(v.x, c0) | pack4_fast(v.y, c1);
+    codes16 = (c0 << 8) | c1;
+    return d;
+}
+__device__ __forceinline__ void pack8(uint2 v, u32 &codes16, u32 &bad8) {
+    u32 c0, c1, b0, b1, t0, t1;
+    pack4(v.x, c0, b0, t0); pack4(v.y, c1, b1, t1);
+    codes16 = (c0 << 8) | c1;
+    bad8 = (b0 << 4) | b1;
+}
+
+// KT: compile-time k (0 = use the runtime argument). COUNTS: per-record hit / missing counts are wanted.
+template <bool CANON, int KT, bool COUNTS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, BNS_CLASSIFY_U_MIN_CTAS)
-bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records,
+bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records,
                       TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
                       u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const u32 k = KT ? (u32)KT : k_rt;
     const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
     if(staged) tma_stage_val_info(s_vi, X.val_info, T.n_values * (u32)sizeof(uint4), &s_mbar);
     WarpSmem S;                                                        // only the distinct-taxon lists are used here
@@ -99,18 +115,18 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
             ol = len < 0xffffffffull ? (u32)len : 0xffffffffu;
         }
     };
-    // the 16-byte block of a record's first tile this lane stages (zero outside the record)
-    auto first_block = [&](u64 rb, u32 rl) -> uint4 {
+    // the 8-byte block of a tile this lane stages (zero outside the record): bases [rb, rb + min(rl, span))
+    auto tile_block = [&](u64 rb, u32 rl) -> uint2 {
         const char *a0 = bases + rb;
-        const u32 shift = (u32)((uintptr_t)a0 & 15u);
-        const u32 nblk = rl ? (shift + min(rl, span) + 15) >> 4 : 0u;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if(lane < nblk) v = __ldg(reinterpret_cast<const uint4 *>(a0 - shift) + lane);
+        const u32 shift = (u32)((uintptr_t)a0 & 7u);
+        const u32 nblk = rl ? (shift + min(rl, span) + 7) >> 3 : 0u;      // <= 22 for k <= 32
+        uint2 v = make_uint2(0, 0);
+        if(lane < nblk) v = __ldg(reinterpret_cast<const uint2 *>(a0 - shift) + lane);
         return v;
     };
     fetch_offsets(bt, cb, cl);
     fetch_offsets(bt + nwarps, nb, nl);
-    uint4 pre = first_block(__shfl_sync(FULL, cb, 0), __shfl_sync(FULL, cl, 0));
+    uint2 pre = tile_block(__shfl_sync(FULL, cb, 0), __shfl_sync(FULL, cl, 0));
     if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
 
@@ -124,12 +140,12 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
             const u64 rb = __shfl_sync(FULL, cb, j);
             const u32 L = __shfl_sync(FULL, cl, j);
             // request the first tile of the record after this one before working on this one
-            uint4 pre_next;
+            uint2 pre_next;
             {
                 const bool last = j + 1 == nrec;
                 const u64 xb = __shfl_sync(FULL, last ? nb : cb, last ? 0 : j + 1);
                 const u32 xl = __shfl_sync(FULL, last ? nl : cl, last ? 0 : j + 1);
-                pre_next = first_block(xb, xl);
+                pre_next = tile_block(xb, xl);
             }
             // ---- per-record state: linear::counter with its first key in registers -----------------------------
             u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
@@ -138,32 +154,33 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
             else if(L >= k) {
                 const u32 npos = L - k + 1;
                 for(u32 p0 = 0; p0 < npos; p0 += TILE) {
-                    // ---- stage: 16 bases per lane -> one 2-bit word per lane -----------------------------------
-                    const char *a0 = bases + rb + p0;
-                    const u32 shift = (u32)((uintptr_t)a0 & 15u);
-                    const u32 nblk = (shift + min(L - p0, span) + 15) >> 4;
-                    uint4 v = pre;
-                    if(p0) { v = make_uint4(0, 0, 0, 0); if(lane < nblk) v = __ldg(reinterpret_cast<const uint4 *>(a0 - shift) + lane); }
-                    u32 codes = 0, susp = 0;
-                    if(lane < nblk) susp = pack16_fast(v, codes);
-                    const bool slow = __any_sync(FULL, susp != 0);
-                    const u32 q0 = shift + PPL * lane, wi = q0 >> 4, s = (q0 & 15u) * 2u;
-                    const u32 w0 = __shfl_sync(FULL, codes, wi), w1 = __shfl_sync(FULL, codes, wi + 1),
-                              w2 = __shfl_sync(FULL, codes, wi + 2), w3 = __shfl_sync(FULL, codes, wi + 3);
+                    // ---- stage: 8 bases per lane -> 16 bits per lane -> one 16-base word per lane ----------------
+                    const uint2 v = p0 ? tile_block(rb + p0, L - p0) : pre;
+                    const u32 shift = (u32)((uintptr_t)(bases + rb + p0) & 7u);
+                    u32 c16;
+                    const u32 susp = pack8_fast(v, c16);                 // lanes past the tile hold zeros: masked below
+                    const u32 nblk = (shift + min(L - p0, span) + 7) >> 3;
+                    if(lane >= nblk) c16 = 0;
+                    const bool slow = __any_sync(FULL, susp != 0 && lane < nblk);
+                    const u32 word = (c16 << 16) | __shfl_down_sync(FULL, c16, 1);   // bases [8*lane, 8*lane+16) of the tile
+                    const u32 q0 = shift + PPL * lane, ci = q0 >> 3, s = (q0 & 7u) * 2u;
+                    const u32 w0 = __shfl_sync(FULL, word, ci), w1 = __shfl_sync(FULL, word, ci + 2),
+                              w2 = __shfl_sync(FULL, word, ci + 4), w3 = __shfl_sync(FULL, word, ci + 6);
                     const u32 left = npos - p0;
                     const u32 nlive = left > PPL * lane ? min((u32)PPL, left - PPL * lane) : 0u;
                     u32 mask = (1u << nlive) - 1;
                     if(slow) {                                         // some staged byte is not ACGTacgt (rare)
-                        u32 bad = 0, tm;
-                        if(lane < nblk) pack16(v, codes, bad, tm);
-                        const u32 b0 = __shfl_sync(FULL, bad, wi), b1 = __shfl_sync(FULL, bad, wi + 1),
-                                  b2 = __shfl_sync(FULL, bad, wi + 2), b3 = __shfl_sync(FULL, bad, wi + 3);
-                        const u64 B = ((u64)b0 << 48) | ((u64)b1 << 32) | ((u64)b2 << 16) | (u64)b3;   // coordinate 16*wi at bit 63
+                        u32 b8 = 0, cc;
+                        if(lane < nblk) pack8(v, cc, b8);
+                        const u32 bw = (b8 << 8) | __shfl_down_sync(FULL, b8, 1);    // invalid bits of the same 16 bases, first at bit 15
+                        const u32 b0 = __shfl_sync(FULL, bw, ci), b1 = __shfl_sync(FULL, bw, ci + 2),
+                                  b2 = __shfl_sync(FULL, bw, ci + 4), b3 = __shfl_sync(FULL, bw, ci + 6);
+                        const u64 B = ((u64)b0 << 48) | ((u64)b1 << 32) | ((u64)b2 << 16) | (u64)b3;   // coordinate 8*ci at bit 63
 #pragma unroll
                         for(int i = 0; i < PPL; ++i)
-                            if(((B << ((q0 & 15u) + i)) >> (64 - k)) != 0) mask &= ~(1u << i);
-                        n_emit += __reduce_add_sync(FULL, __popc(mask));
-                    } else n_emit += min(left, (u32)TILE);
+                            if(((B << ((q0 & 7u) + i)) >> (64 - k)) != 0) mask &= ~(1u << i);
+                        if(COUNTS) n_emit += __reduce_add_sync(FULL, __popc(mask));
+                    } else if(COUNTS) n_emit += min(left, (u32)TILE);
                     // ---- the lane's four k-mers (and reverse complements) out of one 96-bit window --------------
                     const u32 A = __funnelshift_l(w1, w0, s), B_ = __funnelshift_l(w2, w1, s), C = __funnelshift_l(w3, w2, s);
                     u32 R0 = 0, R1 = 0, R2 = 0;
@@ -178,7 +195,7 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
                     for(int i = 0; i < PPL; ++i) {
                         const u32 fh0 = __funnelshift_l(B_, A, 2 * i), fl0 = __funnelshift_l(C, B_, 2 * i);
                         u32 xl, xh;                                                          // forward k-mer
-                        if(down < 32) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
+                        if(KT ? (KT > 16) : (down < 32)) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
                         else { xl = fh0 >> (down - 32); xh = 0; }                            // k <= 16
                         if(CANON) {
                             const u32 rl = __funnelshift_r(R2, R1, 2 * i) & kmask_lo, rh = __funnelshift_r(R1, R0, 2 * i) & kmask_hi;
@@ -194,7 +211,7 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
                         ld_bucket8(Pc.slots + ((u64)(hh[i] >> Pc.idx_shift) << 5), w[i]);
                     }
                     // ---- match: first slot whose high word equals the tag's, verified on the low word ------------
-                    u32 cand[PPL], okm = 0, more = 0;
+                    u32 cand[PPL], nok = 0;                            // nok bit i: k-mer i is not in its home bucket
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
                         const u32 th = __funnelshift_lc(hl[i], hh[i], Pc.b), tl = __funnelshift_lc(0u, hl[i], Pc.b);
@@ -204,29 +221,34 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
                         c = w[i][3] == th ? w[i][2] : c;
                         c = w[i][1] == th ? w[i][0] : c;                                       // slots fill in order: first match wins
                         cand[i] = c;
-                        const bool ok = ((c ^ tl) & Pc.hm) == 0;
-                        if(ok) okm |= 1u << i;
-                        else if(!(w[i][0] & Pc.novf)) more |= 1u << i;
+                        nok += min((c ^ tl) & Pc.hm, 1u) << i;
                     }
-                    more &= mask;
-                    while(__any_sync(FULL, more != 0)) {               // keys displaced from a full home bucket (rare)
-                        if(more) {
-                            const u32 i = __ffs(more) - 1;
-                            more &= more - 1;
-                            const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
-                            const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
-                            const u32 c = probe_displaced32(Pc, l, h);
-                            if(c != ~__funnelshift_lc(0u, l, Pc.b)) {
-                                okm |= 1u << i;
-                                if(i == 0) cand[0] = c; else if(i == 1) cand[1] = c; else if(i == 2) cand[2] = c; else cand[3] = c;
+                    // keys displaced from a full home bucket (rare): cheap conservative test first -- did any of the 128 home
+                    // buckets overflow at all? -- then the exact one
+                    if(__any_sync(FULL, ((w[0][0] & w[1][0] & w[2][0] & w[3][0]) & Pc.novf) == 0)) {
+                        u32 more = 0;
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) if(!(w[i][0] & Pc.novf)) more |= 1u << i;
+                        more &= nok & mask;
+                        while(__any_sync(FULL, more != 0)) {
+                            if(more) {
+                                const u32 i = __ffs(more) - 1;
+                                more &= more - 1;
+                                const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
+                                const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
+                                const u32 c = probe_displaced32(Pc, l, h);
+                                if(c != ~__funnelshift_lc(0u, l, Pc.b)) {
+                                    nok &= ~(1u << i);
+                                    if(i == 0) cand[0] = c; else if(i == 1) cand[1] = c; else if(i == 2) cand[2] = c; else cand[3] = c;
+                                }
                             }
                         }
                     }
                     // ---- hits -> per-record distinct-taxon counts (linear::counter::add, linear.h:229) -----------
-                    u32 todo = okm & mask;
+                    u32 todo = ~nok & mask;
                     u32 bal = __ballot_sync(FULL, todo != 0);
                     if(bal) {
-                        n_hit += __reduce_add_sync(FULL, __popc(todo));
+                        if(COUNTS) n_hit += __reduce_add_sync(FULL, __popc(todo));
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) cand[i] &= Pc.val_mask;
                         do {
@@ -236,10 +258,10 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
                             if(todo & 2u) fv = cand[1];
                             if(todo & 1u) fv = cand[0];
                             const u32 vv = __shfl_sync(FULL, fv, leader);
-                            u32 c = 0;
-#pragma unroll
-                            for(int i = 0; i < PPL; ++i) if((todo >> i & 1u) && cand[i] == vv) { ++c; todo &= ~(1u << i); }
-                            const u32 total = __reduce_add_sync(FULL, c);
+                            u32 e = (cand[0] == vv ? 1u : 0u) | (cand[1] == vv ? 2u : 0u) | (cand[2] == vv ? 4u : 0u) | (cand[3] == vv ? 8u : 0u);
+                            e &= todo;
+                            todo ^= e;
+                            const u32 total = __reduce_add_sync(FULL, __popc(e));
                             if(nd == 0) { id0 = vv; cnt0 = total; nd = 1; }
                             else if(!spilled && vv == id0) cnt0 += total;
                             else {
@@ -264,14 +286,16 @@ bns_classify_u_kernel(u32 k, const char *__restrict__ bases, const u64 *__restri
                 sink.n_distinct = 0; sink.overflow = 0;
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
-            if(lane == j) { my_taxon = taxon; my_hit = n_hit; my_miss = n_emit - n_hit; }
+            if(lane == j) { my_taxon = taxon; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; } }
             pre = pre_next;
         }
         // ---- one coalesced store per output array for the batch ------------------------------------------------------
         if(lane < nrec) {
             taxon_out[r0 + lane] = my_taxon;
-            if(nhit_out) nhit_out[r0 + lane] = my_hit;
-            if(nmiss_out) nmiss_out[r0 + lane] = my_miss;
+            if(COUNTS) {
+                if(nhit_out) nhit_out[r0 + lane] = my_hit;
+                if(nmiss_out) nmiss_out[r0 + lane] = my_miss;
+            }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
         n_cls += cls; n_uncls += nrec - cls;

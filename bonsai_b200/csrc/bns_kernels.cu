@@ -1039,13 +1039,22 @@ static bool lean_ok(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 }
 typedef void (*classify_u_fn)(u32, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *, unsigned long long *, u32 *);
 static size_t lean_smem() { return (size_t)WARPS_PER_CTA * 4 * AGG_CAP * sizeof(u32); }
+template <bool CANON, bool COUNTS>
+static classify_u_fn pick_lean_k(u32 k) {
+    return k == 31 ? bns_classify_u_kernel<CANON, 31, COUNTS> : bns_classify_u_kernel<CANON, 0, COUNTS>;
+}
+static classify_u_fn pick_lean(const EncParams &P, bool counts) {
+    if(P.canon_elem) return counts ? pick_lean_k<true, true>(P.k) : pick_lean_k<true, false>(P.k);
+    return counts ? pick_lean_k<false, true>(P.k) : pick_lean_k<false, false>(P.k);
+}
 
-ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1) {
+ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
     ClassifyPlan pl;
     pl.lean = lean_ok(P, mates, taxa, mate1);
+    pl.counts = counts;
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = P.canon_elem ? bns_classify_u_kernel<true> : bns_classify_u_kernel<false>;
+        classify_u_fn f = pick_lean(P, counts);
         pl.smem = lean_smem();
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1069,7 +1078,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status) {
     if(pl.lean) {
-        classify_u_fn f = P.canon_elem ? bns_classify_u_kernel<true> : bns_classify_u_kernel<false>;
+        classify_u_fn f = pick_lean(P, pl.counts);
         f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P.k, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
                                                         counters, status);
         return cudaGetLastError();

@@ -16,8 +16,8 @@ struct TableView;
 struct TaxView;
 
 size_t stream_smem_bytes(u32 ring_cap, bool classify);
-struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false; int occupancy = 0; };
-ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1);
+struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true; int occupancy = 0; };
+ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts);
 int encode_occupancy(const EncParams &P, size_t smem);
 
 cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
