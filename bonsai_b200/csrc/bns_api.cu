@@ -204,7 +204,9 @@ int alloc_table(bns_b200_ctx *ctx, u32 b) {
 }
 
 u32 choose_bits(u64 n_keys, u32 n_values) {
-    u32 b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / TARGET_LOAD));
+    double small_load = TARGET_LOAD;
+    if(const char *e = getenv("BNS_B200_TARGET_LOAD")) { const double v = atof(e); if(v > 0.05 && v <= 3.0) small_load = v; }   // experiments
+    u32 b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / small_load));
     // Tables that cannot live in L2 anyway prefer density (more L2 hits, second probes mostly land in the same 128-byte
     // line): up to 1.75 entries per bucket there (measured on the 10.5 M-key DB: 512 Mreads/s at 1.25/bucket and 268 MB
     // against 400 at 0.63/bucket and 537 MB).

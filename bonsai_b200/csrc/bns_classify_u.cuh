@@ -19,6 +19,7 @@
 namespace bns {
 
 constexpr int RB = 32;                       // records per warp batch
+constexpr int LEAN_STAGE_BYTES = 2 * (RB + 2) * 8 + 2 * 32 * 8;      // per warp: offsets ring + first-tile ring
 #ifndef BNS_CLASSIFY_U_MIN_CTAS
 #define BNS_CLASSIFY_U_MIN_CTAS 4
 #endif
@@ -100,53 +101,87 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
     const u32 down = 64 - 2 * k;
     const u32 kmask_lo = (u32)(~0ull >> down), kmask_hi = (u32)((~0ull >> down) >> 32);
 
+    // Per-warp staging area in shared memory, filled by cp.async (LDGSTS): no registers are held across the HBM latency
+    // and -- unlike a register prefetch -- the wait is a cp.async group wait, not a scoreboard the compiler may share
+    // with other loads (ncu showed the register prefetch of v2 stalling a full DRAM latency per record for that reason).
+    //   s_off[2][RB+1]  offsets of the current / next batch of records
+    //   s_rd[2][32]     8 bytes per lane of the first tile of the current / next record
+    u64 *s_off = (u64 *)(g_smem + (size_t)WARPS_PER_CTA * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
+    uint2 *s_rd = (uint2 *)(s_off + 2 * (RB + 2));
+    s_rd[lane] = make_uint2(0x41414141u, 0x41414141u);                 // lanes past a tile read 'A's: code 0, never "suspicious"
+    s_rd[32 + lane] = make_uint2(0x41414141u, 0x41414141u);
+    __syncwarp();
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
     const u64 n_batches = (n_records + RB - 1) / RB;
     u64 bt = (u64)blockIdx.x * WARPS_PER_CTA + wid;
-    // lane j holds (start, length) of record j of the current batch (c*) and of the next one (n*)
-    u64 cb = 0, nb = 0;
-    u32 cl = 0, nl = 0;
-    auto fetch_offsets = [&](u64 batch, u64 &ob, u32 &ol) {
-        ob = 0; ol = 0;
+    auto async8 = [](void *dst, const void *src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    auto async_commit = [] { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto async_wait_all = [] { asm volatile("cp.async.wait_group 0;" ::: "memory"); };
+    // offsets[batch*RB .. batch*RB + RB] -> s_off[buf]
+    auto fetch_offsets = [&](u64 batch, u32 buf) {
         const u64 r = batch * RB + lane;
-        if(batch < n_batches && r < n_records) {
-            ob = offsets[r];
-            const u64 len = offsets[r + 1] - ob;
-            ol = len < 0xffffffffull ? (u32)len : 0xffffffffu;
+        if(batch < n_batches) {
+            if(r <= n_records) async8(s_off + buf * (RB + 2) + lane, offsets + r);
+            if(lane == 0 && r + RB <= n_records) async8(s_off + buf * (RB + 2) + RB, offsets + r + RB);
         }
     };
-    // the 8-byte block of a tile this lane stages (zero outside the record): bases [rb, rb + min(rl, span))
-    auto tile_block = [&](u64 rb, u32 rl) -> uint2 {
+    // the 8-byte block of a record's first tile this lane stages -> s_rd[buf]: bases [rb, rb + min(rl, span))
+    auto fetch_tile = [&](u64 rb, u32 rl, u32 buf) {
         const char *a0 = bases + rb;
         const u32 shift = (u32)((uintptr_t)a0 & 7u);
         const u32 nblk = rl ? (shift + min(rl, span) + 7) >> 3 : 0u;      // <= 22 for k <= 32
-        uint2 v = make_uint2(0, 0);
+        if(lane < nblk) async8(s_rd + buf * 32 + lane, a0 - shift + 8 * lane);
+        else s_rd[buf * 32 + lane] = make_uint2(0x41414141u, 0x41414141u);
+    };
+    // later tiles of a long record: plain loads (rare)
+    auto tile_block = [&](u64 rb, u32 rl) -> uint2 {
+        const char *a0 = bases + rb;
+        const u32 shift = (u32)((uintptr_t)a0 & 7u);
+        const u32 nblk = rl ? (shift + min(rl, span) + 7) >> 3 : 0u;
+        uint2 v = make_uint2(0x41414141u, 0x41414141u);
         if(lane < nblk) v = __ldg(reinterpret_cast<const uint2 *>(a0 - shift) + lane);
         return v;
     };
-    fetch_offsets(bt, cb, cl);
-    fetch_offsets(bt + nwarps, nb, nl);
-    uint2 pre = tile_block(__shfl_sync(FULL, cb, 0), __shfl_sync(FULL, cl, 0));
+    auto rec_len = [](u64 b, u64 e) -> u32 { const u64 len = e - b; return len < 0xffffffffull ? (u32)len : 0xffffffffu; };
+    u32 pb = 0;                                                        // offsets buffer of the current batch
+    fetch_offsets(bt, 0);
+    async_commit();
+    async_wait_all();
+    __syncwarp();
+    u64 rb = 0;                                                        // the record being processed (warp-uniform)
+    u32 L = 0;
+    if(bt < n_batches) { rb = s_off[0]; L = rec_len(rb, s_off[1]); }
+    u32 tb = 0;                                                        // tile buffer of the current record
+    fetch_tile(rb, L, 0);
+    async_commit();
     if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
 
     for(; bt < n_batches; bt += nwarps) {
-        u64 fb; u32 fl;
-        fetch_offsets(bt + 2 * nwarps, fb, fl);                        // arrives while this batch is processed
+        fetch_offsets(bt + nwarps, pb ^ 1);                            // lands while this batch is processed
+        async_commit();
         const u64 r0 = bt * RB;
         const u32 nrec = (u32)min((u64)RB, n_records - r0);
+        const bool have_next_batch = bt + nwarps < n_batches;
         u32 my_taxon = 0, my_hit = 0, my_miss = 0;
         for(u32 j = 0; j < nrec; ++j) {
-            const u64 rb = __shfl_sync(FULL, cb, j);
-            const u32 L = __shfl_sync(FULL, cl, j);
+            // this record's first tile (requested one record ago) and, from the second record on, the next batch's offsets
+            // (the newest group at j == 0 is the next batch's offsets, requested a moment ago: not needed yet)
+            if(j == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else async_wait_all();
+            __syncwarp();
+            const uint2 pre = s_rd[tb * 32 + lane];
             // request the first tile of the record after this one before working on this one
-            uint2 pre_next;
+            u64 xb = 0; u32 xl = 0;
             {
-                const bool last = j + 1 == nrec;
-                const u64 xb = __shfl_sync(FULL, last ? nb : cb, last ? 0 : j + 1);
-                const u32 xl = __shfl_sync(FULL, last ? nl : cl, last ? 0 : j + 1);
-                pre_next = tile_block(xb, xl);
+                const u64 *o = nullptr;
+                if(j + 1 < nrec) o = s_off + pb * (RB + 2) + j + 1;
+                else if(have_next_batch) o = s_off + (pb ^ 1) * (RB + 2);
+                if(o) { xb = o[0]; xl = rec_len(xb, o[1]); }
             }
+            fetch_tile(xb, xl, tb ^ 1);
+            async_commit();
             // ---- per-record state: linear::counter with its first key in registers -----------------------------
             u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
             bool spilled = false;
@@ -158,10 +193,8 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                     const uint2 v = p0 ? tile_block(rb + p0, L - p0) : pre;
                     const u32 shift = (u32)((uintptr_t)(bases + rb + p0) & 7u);
                     u32 c16;
-                    const u32 susp = pack8_fast(v, c16);                 // lanes past the tile hold zeros: masked below
-                    const u32 nblk = (shift + min(L - p0, span) + 7) >> 3;
-                    if(lane >= nblk) c16 = 0;
-                    const bool slow = __any_sync(FULL, susp != 0 && lane < nblk);
+                    const u32 susp = pack8_fast(v, c16);
+                    const bool slow = __any_sync(FULL, susp != 0);
                     const u32 word = (c16 << 16) | __shfl_down_sync(FULL, c16, 1);   // bases [8*lane, 8*lane+16) of the tile
                     const u32 q0 = shift + PPL * lane, ci = q0 >> 3, s = (q0 & 7u) * 2u;
                     const u32 w0 = __shfl_sync(FULL, word, ci), w1 = __shfl_sync(FULL, word, ci + 2),
@@ -170,8 +203,8 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                     const u32 nlive = left > PPL * lane ? min((u32)PPL, left - PPL * lane) : 0u;
                     u32 mask = (1u << nlive) - 1;
                     if(slow) {                                         // some staged byte is not ACGTacgt (rare)
-                        u32 b8 = 0, cc;
-                        if(lane < nblk) pack8(v, cc, b8);
+                        u32 b8, cc;
+                        pack8(v, cc, b8);
                         const u32 bw = (b8 << 8) | __shfl_down_sync(FULL, b8, 1);    // invalid bits of the same 16 bases, first at bit 15
                         const u32 b0 = __shfl_sync(FULL, bw, ci), b1 = __shfl_sync(FULL, bw, ci + 2),
                                   b2 = __shfl_sync(FULL, bw, ci + 4), b3 = __shfl_sync(FULL, bw, ci + 6);
@@ -193,13 +226,20 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                     u32 hl[PPL], hh[PPL], w[PPL][8];
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
-                        const u32 fh0 = __funnelshift_l(B_, A, 2 * i), fl0 = __funnelshift_l(C, B_, 2 * i);
-                        u32 xl, xh;                                                          // forward k-mer
-                        if(KT ? (KT > 16) : (down < 32)) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
-                        else { xl = fh0 >> (down - 32); xh = 0; }                            // k <= 16
+                        u32 xl, xh;                                                          // forward k-mer: window bits [2i, 2i+2k)
+                        if(KT == 31) {                                                       // ... = bits [2i, 2i+62): shifts fold
+                            if(i == 0) { xl = __funnelshift_r(B_, A, 2); xh = A >> 2; }
+                            else if(i == 1) { xl = B_; xh = A & 0x3fffffffu; }
+                            else { xl = __funnelshift_l(C, B_, 2 * i - 2); xh = __funnelshift_l(B_, A, 2 * i - 2) & 0x3fffffffu; }
+                        } else {
+                            const u32 fh0 = __funnelshift_l(B_, A, 2 * i), fl0 = __funnelshift_l(C, B_, 2 * i);
+                            if(down < 32) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
+                            else { xl = fh0 >> (down - 32); xh = 0; }                        // k <= 16
+                        }
                         if(CANON) {
                             const u32 rl = __funnelshift_r(R2, R1, 2 * i) & kmask_lo, rh = __funnelshift_r(R1, R0, 2 * i) & kmask_hi;
-                            const bool lt = xh < rh || (xh == rh && xl < rl);
+                            const u64 f64 = ((u64)xh << 32) | xl, r64 = ((u64)rh << 32) | rl;
+                            const bool lt = f64 < r64;
                             xl = lt ? xl : rl; xh = lt ? xh : rh;
                         }
                         // mix64 (bns_device.cuh) on 32-bit halves
@@ -287,7 +327,7 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
             if(lane == j) { my_taxon = taxon; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; } }
-            pre = pre_next;
+            rb = xb; L = xl; tb ^= 1;
         }
         // ---- one coalesced store per output array for the batch ------------------------------------------------------
         if(lane < nrec) {
@@ -299,7 +339,7 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
         n_cls += cls; n_uncls += nrec - cls;
-        cb = nb; cl = nl; nb = fb; nl = fl;
+        pb ^= 1;
     }
     if(lane == 0 && (n_cls | n_uncls)) {
         atomicAdd(&counters[0], (unsigned long long)n_cls);

@@ -1038,7 +1038,7 @@ static bool lean_ok(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     return P.family == FAM_U && mates == 1 && !taxa && !mate1;
 }
 typedef void (*classify_u_fn)(u32, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *, unsigned long long *, u32 *);
-static size_t lean_smem() { return (size_t)WARPS_PER_CTA * 4 * AGG_CAP * sizeof(u32); }
+static size_t lean_smem() { return (size_t)WARPS_PER_CTA * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
 template <bool CANON, bool COUNTS>
 static classify_u_fn pick_lean_k(u32 k) {
     return k == 31 ? bns_classify_u_kernel<CANON, 31, COUNTS> : bns_classify_u_kernel<CANON, 0, COUNTS>;
