@@ -61,7 +61,7 @@ struct bns_b200_ctx {
     // table
     u64 *d_slots = nullptr;
     u64 n_buckets = 0, n_keys = 0, n_displaced = 0, n_overflowed = 0;
-    u32 bucket_bits = 0, max_disp = 0;
+    u32 bucket_bits = 0, max_disp = 0, flag_count = 1;
     std::vector<u32> values;          // sorted distinct DB values (value id -> taxid)
     u32 *d_values = nullptr;
     // taxonomy
@@ -197,6 +197,7 @@ u32 bits_for(u64 n) { u32 b = 0; while((1ull << b) < n) ++b; return b; }
 int alloc_table(bns_b200_ctx *ctx, u32 b) {
     if(b > 32) return ctx->fail(BNS_E_NOMEM, "table would need 2^%u buckets", b);
     ctx->bucket_bits = b;
+    ctx->flag_count = flag_count_for(b, (u32)ctx->values.size());
     ctx->n_buckets = 1ull << b;
     CK(cudaMalloc((void **)&ctx->d_slots, ctx->n_buckets * 32));
     CK(cudaMemsetAsync(ctx->d_slots, 0xff, ctx->n_buckets * 32, ctx->slots[0].st));
@@ -227,7 +228,7 @@ int upload_values(bns_b200_ctx *ctx) {
 int refresh_table_stats(bns_b200_ctx *ctx) {
     cudaStream_t st = ctx->slots[0].st;
     CK(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
-    CK(launch_table_stats(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_counters + 2));
+    CK(launch_table_stats(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_counters + 2));
     ++ctx->stats.kernel_launches;
     unsigned long long h[3];
     CK(cudaMemcpyAsync(h, ctx->d_counters + 2, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -260,7 +261,7 @@ int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
             if(!n) break;
             cudaMemcpyAsync(d_keys + buf * CH, h_keys + buf * CH, n * sizeof(u64), cudaMemcpyHostToDevice, st);
             cudaMemcpyAsync(d_vals + buf * CH, h_vals + buf * CH, n * sizeof(u32), cudaMemcpyHostToDevice, st);
-            cudaError_t e = launch_insert(st, ctx->d_slots, ctx->bucket_bits, d_keys + buf * CH, d_vals + buf * CH, n,
+            cudaError_t e = launch_insert(st, ctx->d_slots, ctx->bucket_bits, ctx->flag_count, d_keys + buf * CH, d_vals + buf * CH, n,
                                           ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5);
             ++ctx->stats.kernel_launches;
             ctx->stats.h2d_bytes += n * 12;
@@ -351,7 +352,9 @@ TableView table_view(const bns_b200_ctx *ctx) {
     T.slots = ctx->d_slots;
     T.bucket_bits = ctx->bucket_bits;
     T.tag_shift = ctx->bucket_bits - DISP_BITS;
-    T.val_mask = (1u << (ctx->bucket_bits - DISP_BITS - 1)) - 1;
+    T.flag_shift = T.tag_shift - ctx->flag_count;
+    T.flag_mask = ctx->flag_count - 1;
+    T.val_mask = (1u << T.flag_shift) - 1;
     T.n_values = (u32)ctx->values.size();
     return T;
 }
@@ -582,7 +585,7 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         CK(cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), st));
         const u64 CH = 1ull << 28;
         for(u64 off = 0; off < n; off += CH) {
-            CK(launch_insert(st, ctx->d_slots, b, (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
+            CK(launch_insert(st, ctx->d_slots, b, ctx->flag_count, (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
                              ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5));
             ++ctx->stats.kernel_launches;
         }
@@ -600,7 +603,7 @@ int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info) {
     info->n_buckets = ctx->n_buckets;
     info->bytes = ctx->n_buckets * 32;
     info->bucket_bits = ctx->bucket_bits;
-    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - DISP_BITS - 1 : 0;
+    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - DISP_BITS - ctx->flag_count : 0;
     info->n_values = (u32)ctx->values.size();
     info->max_disp = ctx->max_disp;
     info->n_displaced = ctx->n_displaced;
@@ -736,7 +739,7 @@ int bns_b200_build_add_genome(bns_b200_t *ctx, const char *bases, const uint64_t
     CK(cudaMemcpyAsync(s.d_offsets, se.data(), se.size() * 8, cudaMemcpyHostToDevice, s.st));
     const size_t smem = stream_smem_bytes(ctx->ring_cap, false);
     CK(launch_build(ctx->enc, grid_for(ctx, npieces, 4), smem, s.st, s.d_bases - offsets[0], s.d_offsets, npieces, offsets[n_records],
-                    ctx->d_slots, ctx->bucket_bits, vid, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 8,
+                    ctx->d_slots, ctx->bucket_bits, ctx->flag_count, vid, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 8,
                     ctx->ring_cap));
     ++ctx->stats.kernel_launches;
     ctx->stats.h2d_bytes += nb + se.size() * 8;
@@ -769,8 +772,9 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         CK(cudaMalloc((void **)&new_slots, (1ull << want) * 32));
         CK(cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st));
         CK(cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st));
-        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_values, dk, dv, n, ctx->d_counters + 12));
-        CK(launch_insert(st, new_slots, want, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
+        const u32 want_flags = flag_count_for(want, (u32)ctx->values.size());
+        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_values, dk, dv, n, ctx->d_counters + 12));
+        CK(launch_insert(st, new_slots, want, want_flags, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
         ctx->stats.kernel_launches += 2;
         unsigned long long h2[3];
         CK(cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st));
@@ -780,6 +784,7 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         cudaFree(ctx->d_slots);
         ctx->d_slots = new_slots;
         ctx->bucket_bits = want;
+        ctx->flag_count = want_flags;
         ctx->n_buckets = 1ull << want;
         ctx->n_displaced = h2[1];
         return refresh_table_stats(ctx);
@@ -799,7 +804,7 @@ int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out,
     CK(cudaMalloc((void **)&dk, std::max<u64>(ctx->n_keys, 1) * 8));
     CK(cudaMalloc((void **)&dv, std::max<u64>(ctx->n_keys, 1) * 4));
     CK(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st));
-    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
+    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
     ++ctx->stats.kernel_launches;
     CK(cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st));
@@ -889,6 +894,7 @@ int bns_b200_db_export_header(const bns_b200_t *ctx_, bns_b200_db_header *hdr) {
     hdr->words[6] = ctx->n_displaced;
     hdr->words[7] = ctx->n_overflowed;
     hdr->words[8] = ctx->max_disp;
+    hdr->words[9] = ctx->flag_count;
     return BNS_OK;
 }
 
@@ -906,6 +912,7 @@ int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr
     ctx->max_disp = (u32)hdr->words[8];
     int rc = alloc_table(ctx, (u32)hdr->words[1]);
     if(rc != BNS_OK) return rc;
+    if(ctx->flag_count != (u32)hdr->words[9]) return ctx->fail(BNS_E_INVAL, "database header: overflow flag count mismatch");
     CK(cudaMalloc((void **)&ctx->d_values, std::max<size_t>(ctx->values.size(), 1) * sizeof(u32)));
     CK(cudaMalloc((void **)&ctx->d_val_info, std::max<size_t>(ctx->values.size(), 1) * sizeof(uint4)));
     CK(cudaMalloc((void **)&ctx->d_node_info, std::max<u32>(ctx->n_nodes, 1) * sizeof(uint4)));

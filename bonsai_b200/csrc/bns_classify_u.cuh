@@ -34,7 +34,8 @@ struct ProbeConst {                          // launch-uniform pieces of the slo
     const char *slots;
     u32 b, idx_shift;                        // bucket = h.hi >> idx_shift
     u32 hm;                                  // bits of the low word that belong to {remainder, disp}
-    u32 novf;                                // "no key homed here was displaced" bit of slot 0
+    u32 flags_all;                           // the overflow flags of slot 0 (all set = no key homed here was displaced)
+    u32 flag_shift, flag_mask;               // a key's flag: bit flag_shift + (hl & flag_mask)
     u32 val_mask;
 };
 
@@ -95,7 +96,8 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
     Pc.b = T.bucket_bits;
     Pc.idx_shift = 32 - T.bucket_bits;
     Pc.hm = ~0u << T.tag_shift;
-    Pc.novf = 1u << (T.tag_shift - 1);
+    Pc.flags_all = ((1u << T.tag_shift) - 1) & ~T.val_mask;
+    Pc.flag_shift = T.flag_shift; Pc.flag_mask = T.flag_mask;
     Pc.val_mask = T.val_mask;
     const u32 span = TILE + k - 1;
     const u32 down = 64 - 2 * k;
@@ -265,10 +267,10 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                     }
                     // keys displaced from a full home bucket (rare): cheap conservative test first -- did any of the 128 home
                     // buckets overflow at all? -- then the exact one
-                    if(__any_sync(FULL, ((w[0][0] & w[1][0] & w[2][0] & w[3][0]) & Pc.novf) == 0)) {
+                    if(__any_sync(FULL, ((w[0][0] & w[1][0] & w[2][0] & w[3][0]) & Pc.flags_all) != Pc.flags_all)) {
                         u32 more = 0;
 #pragma unroll
-                        for(int i = 0; i < PPL; ++i) if(!(w[i][0] & Pc.novf)) more |= 1u << i;
+                        for(int i = 0; i < PPL; ++i) if(!((w[i][0] >> (Pc.flag_shift + (hl[i] & Pc.flag_mask))) & 1u)) more |= 1u << i;
                         more &= nok & mask;
                         while(__any_sync(FULL, more != 0)) {
                             if(more) {

@@ -56,10 +56,23 @@ struct EncParams {
 struct TableView {
     const u64 *slots;            // n_buckets * 4 u64
     u32 bucket_bits;             // b: bucket = h >> (64-b)
-    u32 tag_shift;               // b - DISP_BITS: bits below it are {novf, val}
-    u32 val_mask;                // (1 << (b - DISP_BITS - 1)) - 1
+    u32 tag_shift;               // b - DISP_BITS: bits below it are {overflow flags, val}
+    u32 val_mask;                // (1 << flag_shift) - 1
     u32 n_values;
+    u32 flag_shift;              // tag_shift - F: the F overflow flags of slot 0 sit at [flag_shift, tag_shift)
+    u32 flag_mask;               // F - 1 (F is a power of two): a key's flag is bit flag_shift + (low word of mix64 & flag_mask)
 };
+
+// Overflow flags. A key that found its home bucket full is stored in a later bucket and CLEARS, in slot 0 of the home
+// bucket, the one of F flag bits its hash selects (an empty slot is all ones and so reads "nothing displaced"). A lookup
+// that misses in the home bucket goes on to the next bucket only if ITS flag is cleared, so a miss costs one sector
+// unless a displaced key shares both its home bucket and its flag. F is what the value field leaves free, at most 8.
+__host__ __device__ inline u32 flag_count_for(u32 b, u32 n_values) {
+    u32 vb = 1;
+    while((1u << vb) < n_values) ++vb;
+    const u32 avail = b - DISP_BITS > vb ? b - DISP_BITS - vb : 1u;
+    return avail >= 8 ? 8u : avail >= 4 ? 4u : avail >= 2 ? 2u : 1u;
+}
 
 struct TaxView {
     // one 16-byte record per distinct DB value: {tin, tout, node, taxid}

@@ -250,7 +250,7 @@ __device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], 
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         val[i] = match4_home(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
-        if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.tag_shift - 1)) & 1u)) more |= 1u << i;
+        if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.flag_shift + ((u32)h[i] & T.flag_mask))) & 1u)) more |= 1u << i;
     }
     if(more) {                                                    // rare (~1 % of lookups at <= 1.25 entries/bucket)
 #pragma unroll
@@ -410,7 +410,7 @@ __device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u
 // a well-formed taxonomy, so concurrent CAS merges converge to the reference's sequential result.
 struct BuildSink {
     u64 *slots;
-    u32 b, tag_shift, val_mask;
+    u32 b, tag_shift, val_mask, flag_shift, flag_mask;
     u32 vid;                           // value id of the genome being added
     const uint4 *val_info, *node_info; // Euler intervals: {tin, tout, node, taxid} / {tin, tout, parent node, taxid}
     const u32 *values;
@@ -434,7 +434,7 @@ struct BuildSink {
         const u64 h = mix64(key), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
         for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
             u64 *bk = slots + (((home + d) & bmask) << 2);
-            const u64 entry = tag | ((u64)d << tag_shift) | (1ull << (tag_shift - 1)) | vid;
+            const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << tag_shift) - 1) & ~(u64)val_mask) | vid;
             for(int s = 0; s < 4; ++s) {
                 u64 cur = bk[s];
                 if(cur == ~0ull) {
@@ -456,7 +456,7 @@ struct BuildSink {
                 }
                 if((u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant
             }
-            if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (tag_shift - 1)));
+            if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + ((u32)h & flag_mask))));
         }
         ++n_fail;
     }
@@ -829,10 +829,11 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
 }
 
 // Bucketised open addressing, 4 x u64 slots per 32-byte bucket:
-//   slot = [ low (64-b) bits of mix64(key) | disp:4 | novf:1 | value id:(b-5) ],  empty = ~0.
+//   slot = [ low (64-b) bits of mix64(key) | disp:4 | overflow flags:F | value id:(b-4-F) ],  empty = ~0.
 // A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 14);
-// the home bucket's slot 0 then gets its novf bit CLEARED so that misses stop after one sector otherwise.
-__global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__restrict__ keys,
+// the home bucket's slot 0 then gets the key's overflow flag CLEARED (flag_count_for, bns_device.cuh) so that misses
+// stop after one sector otherwise.
+__global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, u32 F, const u64 *__restrict__ keys,
                                   const u32 *__restrict__ vals, u64 n, const u32 *__restrict__ values, u32 n_values,
                                   unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,11 +843,11 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__r
     if(vid == VAL_MISS) { atomicAdd(&stats[2], 1ull); return; }
     const u64 h = mix64(key);
     const u64 home = h >> (64 - b), bmask = (1ull << b) - 1;
-    const u32 tag_shift = b - DISP_BITS;
+    const u32 tag_shift = b - DISP_BITS, flag_shift = tag_shift - F;
     const u64 tag = h << b;
     for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
         u64 *bk = slots + (((home + d) & bmask) << 2);
-        const u64 entry = tag | ((u64)d << tag_shift) | (1ull << (tag_shift - 1)) | vid;
+        const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << F) - 1) << flag_shift) | vid;
         for(int s = 0; s < 4; ++s) {
             u64 cur = bk[s];
             if(cur == ~0ull) {
@@ -858,12 +859,12 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, const u64 *__r
             // build; the host rebuilds with one more bucket bit, which re-draws every upper word.
             if((u32)(cur >> 32) == (u32)(entry >> 32)) { atomicAdd(&stats[0], 1ull); return; }
         }
-        if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (tag_shift - 1)));
+        if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + ((u32)h & (F - 1)))));
     }
     atomicAdd(&stats[0], 1ull);
 }
 
-__global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b,
+__global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, u32 F,
                                        unsigned long long *__restrict__ out /* [0] entries [1] ovf buckets [2] max disp */) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_buckets) return;
@@ -874,7 +875,8 @@ __global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buck
         if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & ((1u << DISP_BITS) - 1))); }
     }
     if(cnt) atomicAdd(&out[0], (unsigned long long)cnt);
-    if(cnt == 4 && !((slots[4 * i] >> (tag_shift - 1)) & 1ull)) atomicAdd(&out[1], 1ull);
+    const u64 flags = ((1ull << F) - 1) << (tag_shift - F);
+    if(cnt == 4 && (slots[4 * i] & flags) != flags) atomicAdd(&out[1], 1ull);
     if(md) atomicMax(&out[2], (unsigned long long)md);
 }
 
@@ -886,7 +888,7 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
     u64 a, b, c, d;
     ld_bucket(T.slots + ((h >> (64 - T.bucket_bits)) << 2), a, b, c, d);
     u32 v = match4_home(T, h << T.bucket_bits, a, b, c, d);
-    if(v == VAL_MISS && !(((u32)a >> (T.tag_shift - 1)) & 1u)) v = probe_displaced(T, h);
+    if(v == VAL_MISS && !(((u32)a >> (T.flag_shift + ((u32)h & T.flag_mask))) & 1u)) v = probe_displaced(T, h);
     found_out[i] = v != VAL_MISS;
     vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
 }
@@ -902,7 +904,7 @@ __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u6
             ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
             ++touched;
             if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
-            if(d == 0 ? (((a >> (T.tag_shift - 1)) & 1ull) != 0) : (e == ~0ull)) break;
+            if(d == 0 ? (((a >> (T.flag_shift + ((u32)h & T.flag_mask))) & 1ull) != 0) : (e == ~0ull)) break;
         }
     }
     touched = __reduce_add_sync(FULL, touched);
@@ -957,7 +959,7 @@ bns_build_kernel(const __grid_constant__ EncParams P, const char *__restrict__ b
 }
 
 // table -> (key, value) pairs: the home bucket is bucket - disp, the key is unmix64(home : remainder)
-__global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, const u32 *__restrict__ dict,
+__global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, u32 F, const u32 *__restrict__ dict,
                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, u64 cap,
                                 unsigned long long *__restrict__ counter) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -969,7 +971,7 @@ __global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, u3
     const u64 home = (bucket - disp) & (n_buckets - 1);
     const u64 h = (home << (64 - b)) | (v >> b);
     const u64 at = atomicAdd(counter, 1ull);
-    if(at < cap) { keys_out[at] = unmix64(h); vals_out[at] = dict[(u32)v & ((1u << (tag_shift - 1)) - 1)]; }
+    if(at < cap) { keys_out[at] = unmix64(h); vals_out[at] = dict[(u32)v & ((1u << (tag_shift - F)) - 1)]; }
 }
 
 // independent 32-byte loads at uniformly random buckets: the random-access ceiling the lookup is measured against
@@ -1096,10 +1098,11 @@ int encode_occupancy(const EncParams &P, size_t smem) {
     return nb;
 }
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
-                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 vid, const TaxView &X, const u32 *values,
+                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 F, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap) {
     BuildSink sk;
-    sk.slots = slots; sk.b = b; sk.tag_shift = b - DISP_BITS; sk.val_mask = (1u << (b - DISP_BITS - 1)) - 1; sk.vid = vid;
+    sk.slots = slots; sk.b = b; sk.tag_shift = b - DISP_BITS; sk.flag_shift = sk.tag_shift - F; sk.flag_mask = F - 1;
+    sk.val_mask = (1u << sk.flag_shift) - 1; sk.vid = vid;
     sk.val_info = X.val_info; sk.node_info = X.node_info; sk.values = values; sk.n_values = n_values;
     sk.node_of_one = X.node_of_one; sk.stats = stats; sk.n_new = sk.n_fail = 0;
     void (*f)(const EncParams, const char *, const u64 *, u64, u64, BuildSink, u32) =
@@ -1109,20 +1112,20 @@ cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t
     f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, sk, ring_cap);
     return cudaGetLastError();
 }
-cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, const u32 *dict, u64 *keys_out, u32 *vals_out,
+cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, const u32 *dict, u64 *keys_out, u32 *vals_out,
                         u64 cap, unsigned long long *counter) {
     const u64 n = n_buckets * 4;
-    bns_dump_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, dict, keys_out, vals_out, cap, counter);
+    bns_dump_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, F, dict, keys_out, vals_out, cap, counter);
     return cudaGetLastError();
 }
-cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, u32 F, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
                           u32 n_values, unsigned long long *stats) {
     if(!n) return cudaSuccess;
-    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, b, keys, vals, n, values, n_values, stats);
+    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, b, F, keys, vals, n, values, n_values, stats);
     return cudaGetLastError();
 }
-cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, unsigned long long *out) {
-    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, out);
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, unsigned long long *out) {
+    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, F, out);
     return cudaGetLastError();
 }
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,

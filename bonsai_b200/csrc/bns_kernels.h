@@ -27,13 +27,13 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status);
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
-                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 vid, const TaxView &X, const u32 *values,
+                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 F, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap);
-cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, const u32 *dict, u64 *keys_out, u32 *vals_out,
+cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, const u32 *dict, u64 *keys_out, u32 *vals_out,
                         u64 cap, unsigned long long *counter);
-cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, u32 F, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
                           u32 n_values, unsigned long long *stats);
-cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, unsigned long long *out);
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, unsigned long long *out);
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
                           uint8_t *found_out);
 cudaError_t launch_sectors(cudaStream_t st, const TableView &T, const u64 *keys, u64 n, unsigned long long *total);
