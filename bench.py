@@ -352,7 +352,8 @@ def main():
             traffic = prof["dram_bytes_per_read"] * n
     except (OSError, KeyError, ValueError):
         pass
-    roofline = {"bound": "hbm", "kernel": "bns_classify_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    lean = c["w"] == c["k"] and not c["gaps"]       # what launch_classify picks for FAM_U, single-end, no hit list
+    roofline = {"bound": "hbm", "kernel": "bns_classify_u_kernel" if lean else "bns_classify_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_read": bytes_per_read, "lookups_per_read": lookups_per_read, "sectors_per_lookup": pbar,
                 "kernel_ms": kernel_ms, "table_bytes": tinfo["bytes"],

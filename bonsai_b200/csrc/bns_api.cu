@@ -211,7 +211,9 @@ u32 choose_bits(u64 n_keys, u32 n_values) {
     // Tables that cannot live in L2 anyway prefer density (more L2 hits, second probes mostly land in the same 128-byte
     // line): up to 1.75 entries per bucket there (measured on the 10.5 M-key DB: 512 Mreads/s at 1.25/bucket and 268 MB
     // against 400 at 0.63/bucket and 537 MB).
-    if((32ull << b) > (64ull << 20)) b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / TARGET_LOAD_BIG));
+    double big_load = TARGET_LOAD_BIG;
+    if(const char *e = getenv("BNS_B200_TARGET_LOAD_BIG")) { const double v = atof(e); if(v > 0.05 && v <= 3.5) big_load = v; }   // experiments
+    if((32ull << b) > (64ull << 20)) b = bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / big_load));
     b = std::max(b, 12u);
     b = std::max(b, bits_for(std::max<u32>(n_values, 1)) + (u32)DISP_BITS + 1u);
     return b;

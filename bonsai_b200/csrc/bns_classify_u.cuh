@@ -20,9 +20,13 @@ namespace bns {
 
 constexpr int RB = 32;                       // records per warp batch
 constexpr int LEAN_STAGE_BYTES = 2 * (RB + 2) * 8 + 2 * 32 * 8;      // per warp: offsets ring + first-tile ring
-#ifndef BNS_CLASSIFY_U_MIN_CTAS
-#define BNS_CLASSIFY_U_MIN_CTAS 4
+#ifndef BNS_LEAN_WARPS
+#define BNS_LEAN_WARPS 8
 #endif
+#ifndef BNS_CLASSIFY_U_MIN_CTAS
+#define BNS_CLASSIFY_U_MIN_CTAS 3
+#endif
+constexpr int LEAN_WARPS = BNS_LEAN_WARPS;   // warps per CTA of the lean kernel
 
 __device__ __forceinline__ void ld_bucket8(const void *p, u32 (&w)[8]) {
     // one 32-byte sector per probe (LDG.E.256), as eight 32-bit words: {lo, hi} of slots 0..3
@@ -73,7 +77,7 @@ __device__ __forceinline__ void pack8(uint2 v, u32 &codes16, u32 &bad8) {
 
 // KT: compile-time k (0 = use the runtime argument). COUNTS: per-record hit / missing counts are wanted.
 template <bool CANON, int KT, bool COUNTS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, BNS_CLASSIFY_U_MIN_CTAS)
+__global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records,
                       TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
                       u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
@@ -108,14 +112,14 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
     // with other loads (ncu showed the register prefetch of v2 stalling a full DRAM latency per record for that reason).
     //   s_off[2][RB+1]  offsets of the current / next batch of records
     //   s_rd[2][32]     8 bytes per lane of the first tile of the current / next record
-    u64 *s_off = (u64 *)(g_smem + (size_t)WARPS_PER_CTA * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
+    u64 *s_off = (u64 *)(g_smem + (size_t)LEAN_WARPS * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
     uint2 *s_rd = (uint2 *)(s_off + 2 * (RB + 2));
     s_rd[lane] = make_uint2(0x41414141u, 0x41414141u);                 // lanes past a tile read 'A's: code 0, never "suspicious"
     s_rd[32 + lane] = make_uint2(0x41414141u, 0x41414141u);
     __syncwarp();
-    const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
+    const u64 nwarps = (u64)gridDim.x * LEAN_WARPS;
     const u64 n_batches = (n_records + RB - 1) / RB;
-    u64 bt = (u64)blockIdx.x * WARPS_PER_CTA + wid;
+    u64 bt = (u64)blockIdx.x * LEAN_WARPS + wid;
     auto async8 = [](void *dst, const void *src) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     };
@@ -159,7 +163,6 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
     fetch_tile(rb, L, 0);
     async_commit();
     if(staged) mbar_wait(&s_mbar, 0);
-    u32 n_cls = 0, n_uncls = 0;
 
     for(; bt < n_batches; bt += nwarps) {
         fetch_offsets(bt + nwarps, pb ^ 1);                            // lands while this batch is processed
@@ -340,12 +343,11 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
             }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
-        n_cls += cls; n_uncls += nrec - cls;
+        if(lane == 0) {                                                // classified_[2] (classifier.h:138,238), once per batch
+            atomicAdd(&counters[0], (unsigned long long)cls);
+            atomicAdd(&counters[1], (unsigned long long)(nrec - cls));
+        }
         pb ^= 1;
-    }
-    if(lane == 0 && (n_cls | n_uncls)) {
-        atomicAdd(&counters[0], (unsigned long long)n_cls);
-        atomicAdd(&counters[1], (unsigned long long)n_uncls);
     }
 }
 

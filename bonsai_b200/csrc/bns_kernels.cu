@@ -1040,7 +1040,7 @@ static bool lean_ok(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     return P.family == FAM_U && mates == 1 && !taxa && !mate1;
 }
 typedef void (*classify_u_fn)(u32, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *, unsigned long long *, u32 *);
-static size_t lean_smem() { return (size_t)WARPS_PER_CTA * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
+static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
 template <bool CANON, bool COUNTS>
 static classify_u_fn pick_lean_k(u32 k) {
     return k == 31 ? bns_classify_u_kernel<CANON, 31, COUNTS> : bns_classify_u_kernel<CANON, 0, COUNTS>;
@@ -1060,8 +1060,8 @@ ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_rec
         pl.smem = lean_smem();
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, pl.smem);
-        const u64 want = ((n_records + RB - 1) / RB + WARPS_PER_CTA - 1) / WARPS_PER_CTA;     // one batch per warp at least
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, LEAN_WARPS * 32, pl.smem);
+        const u64 want = ((n_records + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;           // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
     } else {
         classify_fn f = pick_classify(P.family, taxa);
@@ -1081,7 +1081,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status) {
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.counts);
-        f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P.k, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
+        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P.k, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
                                                         counters, status);
         return cudaGetLastError();
     }
