@@ -35,6 +35,8 @@ struct Slot {
     u64 *d_taxa_offsets = nullptr; size_t cap_taxa_offsets = 0;
     u64 *d_kmers = nullptr;        size_t cap_kmers = 0;
     u64 *d_out_offsets = nullptr;  size_t cap_out_offsets = 0;
+    u32 *d_defer = nullptr;        size_t cap_defer = 0;     // records the lean windowed kernel leaves to the generic one
+    unsigned long long *d_defer_cnt = nullptr;
 };
 
 template <class T>
@@ -443,6 +445,10 @@ int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
     ctx->n_sm = prop.multiProcessorCount;
     for(int i = 0; i < N_SLOTS; ++i)
         if((e = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for(int i = 0; i < N_SLOTS; ++i) {
+        if((e = cudaMalloc((void **)&ctx->slots[i].d_defer_cnt, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+        cudaMemset(ctx->slots[i].d_defer_cnt, 0, sizeof(unsigned long long));
+    }
     if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -470,6 +476,8 @@ void bns_b200_close(bns_b200_t *ctx) {
         if(s.d_taxa_offsets) cudaFree(s.d_taxa_offsets);
         if(s.d_kmers) cudaFree(s.d_kmers);
         if(s.d_out_offsets) cudaFree(s.d_out_offsets);
+        if(s.d_defer) cudaFree(s.d_defer);
+        if(s.d_defer_cnt) cudaFree(s.d_defer_cnt);
         if(s.st) cudaStreamDestroy(s.st);
     }
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1014,12 +1022,20 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
+    Slot &s0 = ctx->slots[0];
+    if(pl.lean && pl.lean_mode != LEAN_U) {
+        rc = ensure(s0.d_defer, s0.cap_defer, n_rec);
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        CK(cudaMemsetAsync(s0.d_defer_cnt, 0, sizeof(unsigned long long), st));
+    }
+    int nl = 1;
     CK(cudaEventRecord(ctx->ev0, st));
     CK(launch_classify(ctx->enc, pl, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
                        table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
-                       (const u64 *)d_taxa_offsets, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status));
+                       (const u64 *)d_taxa_offsets, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status,
+                       s0.d_defer, s0.d_defer_cnt, &nl));
     CK(cudaEventRecord(ctx->ev1, st));
-    ++ctx->stats.kernel_launches;
+    ctx->stats.kernel_launches += nl;
     ctx->stats.reads_processed += n_reads;
     ctx->stats.bases_processed += total_bases;
     return BNS_OK;
@@ -1063,18 +1079,21 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
             rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
             if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
         }
+        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
+                                               n_hit_out || n_missing_out);
+        if(rc == BNS_OK && pl.lean && pl.lean_mode != LEAN_U) rc = ensure(s.d_defer, s.cap_defer, nq);
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        if(pl.lean && pl.lean_mode != LEAN_U) CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
         CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
-                                               n_hit_out || n_missing_out);
+        int nl = 1;
         CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
                            taxa_out ? s.d_taxa_offsets : nullptr, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap,
-                           ctx->d_counters, ctx->d_status));
-        ++ctx->stats.kernel_launches;
+                           ctx->d_counters, ctx->d_status, s.d_defer, s.d_defer_cnt, &nl));
+        ctx->stats.kernel_launches += nl;
         CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_hit_out) CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));

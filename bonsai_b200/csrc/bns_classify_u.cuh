@@ -75,16 +75,110 @@ __device__ __forceinline__ void pack8(uint2 v, u32 &codes16, u32 &bad8) {
     bad8 = (b0 << 4) | b1;
 }
 
-// KT: compile-time k (0 = use the runtime argument). COUNTS: per-record hit / missing counts are wanted.
-template <bool CANON, int KT, bool COUNTS>
+// ---------------------------------------------------------------------------------------------
+// Windowed minimizers without shared memory (single-tile records: at most TILE window elements).
+// An element is the 128-bit key (score, k-mer) of ElScore::operator< (qmap.h:23); lane l holds elements 4l..4l+3.
+// The minimum over the last W elements at element g = 4l+i is the minimum of
+//   a suffix of lane l+f's four elements, the lane minima of lanes l+f+1 .. l-1, and a prefix of lane l's own elements,
+// with f = floor((i-W+1)/4). Lane minima over runs of lanes come from a doubling table built with SHFL.UP; a run of c
+// lanes is assembled from the set bits of c while the table is built, so no level is kept.
+// ---------------------------------------------------------------------------------------------
+
+struct WKey { u32 sh, sl, eh, el; };                                   // score (hi, lo), element (hi, lo)
+__device__ __forceinline__ WKey wk_make(u64 score, u32 eh, u32 el) { WKey k; k.sh = (u32)(score >> 32); k.sl = (u32)score; k.eh = eh; k.el = el; return k; }
+__device__ __forceinline__ WKey wk_inf() { WKey k; k.sh = k.sl = k.eh = k.el = ~0u; return k; }
+__device__ __forceinline__ WKey wk_min(const WKey &a, const WKey &b) {
+    const u64 as = ((u64)a.sh << 32) | a.sl, bs = ((u64)b.sh << 32) | b.sl, ae = ((u64)a.eh << 32) | a.el, be = ((u64)b.eh << 32) | b.el;
+    const bool lt = bs < as || (bs == as && be < ae);
+    WKey r;
+    r.sh = lt ? b.sh : a.sh; r.sl = lt ? b.sl : a.sl; r.eh = lt ? b.eh : a.eh; r.el = lt ? b.el : a.el;
+    return r;
+}
+__device__ __forceinline__ WKey wk_shfl_up(const WKey &a, u32 d) {
+    WKey r;
+    r.sh = __shfl_up_sync(FULL, a.sh, d); r.sl = __shfl_up_sync(FULL, a.sl, d);
+    r.eh = __shfl_up_sync(FULL, a.eh, d); r.el = __shfl_up_sync(FULL, a.el, d);
+    return r;
+}
+__device__ __forceinline__ WKey wk_shfl_xor(const WKey &a, u32 d) {
+    WKey r;
+    r.sh = __shfl_xor_sync(FULL, a.sh, d); r.sl = __shfl_xor_sync(FULL, a.sl, d);
+    r.eh = __shfl_xor_sync(FULL, a.eh, d); r.el = __shfl_xor_sync(FULL, a.el, d);
+    return r;
+}
+// e[0..3]: this lane's elements (wk_inf() past the m-th). o[i] = minimum over elements [g-W+1, g], g = 4*lane+i.
+// Returns the mask of i with W-1 <= g < m (the windows QueueMap::next_value returns an element for, qmap.h:79-87).
+__device__ __forceinline__ u32 window_min_tile(const WKey (&e)[PPL], u32 m, u32 W, u32 lane, WKey (&o)[PPL]) {
+    WKey P[PPL], S[PPL];
+    P[0] = e[0]; P[1] = wk_min(P[0], e[1]); P[2] = wk_min(P[1], e[2]); P[3] = wk_min(P[2], e[3]);
+    S[3] = e[3]; S[2] = wk_min(e[2], S[3]); S[1] = wk_min(e[1], S[2]); S[0] = P[3];
+    int f[PPL]; u32 c[PPL], off[PPL];
+    u32 call = 0;
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) {
+        const int t = i - (int)W + 1;                                  // window start relative to 4*lane (<= 0)
+        f[i] = t >= 0 ? 0 : -(int)(((u32)(-t) + 3u) >> 2);              // floor(t / 4)
+        off[i] = (u32)(t - 4 * f[i]);                                  // first element's index inside lane l+f
+        c[i] = f[i] < 0 ? (u32)(-f[i] - 1) : 0u;                        // whole lanes between the two partial ones
+        call |= c[i];
+    }
+    WKey R[PPL];
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) R[i] = wk_inf();
+    WKey U = S[0];                                                     // level j: minimum of the lane minima of lanes l-2^j+1 .. l
+#pragma unroll
+    for(int j = 0; j < 5; ++j) {
+        if((call >> j) == 0) break;                                    // warp-uniform (W is)
+#pragma unroll
+        for(int i = 0; i < PPL; ++i)
+            if((c[i] >> j) & 1u) R[i] = wk_min(R[i], wk_shfl_up(U, 1u + (c[i] & ((1u << j) - 1u))));
+        if((call >> (j + 1)) != 0) U = wk_min(U, wk_shfl_up(U, 1u << j));
+    }
+    u32 mask = 0;
+#pragma unroll
+    for(int i = 0; i < PPL; ++i) {
+        const u32 g = PPL * lane + i;
+        if(f[i] < 0) {
+            const WKey sel = off[i] == 0 ? S[0] : off[i] == 1 ? S[1] : off[i] == 2 ? S[2] : S[3];
+            o[i] = wk_min(wk_min(wk_shfl_up(sel, (u32)(-f[i])), R[i]), P[i]);
+        } else {                                                       // W <= i+1: the window lies inside this lane
+            WKey a = e[i];
+#pragma unroll
+            for(int q = 0; q < PPL; ++q) if(q < i && (u32)q >= off[i]) a = wk_min(a, e[q]);
+            o[i] = a;
+        }
+        if(g + 1 >= W && g < m) mask |= 1u << i;
+    }
+    return mask;
+}
+
+// score of a window element; same values as score_of() (bns_kernels.cu). With the saturating cast every k-mer that holds
+// two different bases has H + 0.001 <= -0.138 (k <= 32), so kmer / (H + 0.001) <= -1.44 for kmer >= 2 (and kmer = 1 is
+// A..AC, |H + 0.001| < 1): the cast gives ~0 without any floating point. Homopolymers (H = 0) go the exact way.
+__device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask) {
+    if(cP.score_kind == SC_LEX) return lex_score(x);
+    if(cP.score_kind == SC_ENT_ROLL && !cP.cast_wrap && ((x ^ (x >> 2)) & (kmask >> 2)) != 0) return ~0ull;
+    return score_of(cP, x);
+}
+
+// MODE: LEAN_U every (canonical if CANON) k-mer                      encoder.h:240-272 (+ :218-232)
+//       LEAN_K canonical k-mer at every position, invalid -> 0, windowed  encoder.h:211-217,622-628   (CANON must be true)
+//       LEAN_R valid forward k-mers, windowed over the compacted sequence, tail flush, canonical on emit if CANON
+//                                                                   encoder.h:273-353
+// KT: compile-time k (0 = use P.k). COUNTS: per-record hit / missing counts are wanted.
+// Windowed modes handle records of at most TILE window elements here; longer ones (and the 32-T restart quirk of
+// encoder.h:283) are appended to defer_idx and done by the generic stream kernel right after this one.
+template <int MODE, bool CANON, int KT, bool COUNTS>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
-bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__restrict__ offsets, u64 n_records,
-                      TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
-                      u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
+bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
+                      u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
+                      u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status,
+                      u32 *__restrict__ defer_idx, unsigned long long *__restrict__ defer_cnt) {
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
-    const u32 k = KT ? (u32)KT : k_rt;
+    const u32 k = KT ? (u32)KT : P.k;
+    constexpr bool CANON_ELEM = MODE == LEAN_K || (MODE == LEAN_U && CANON);
     const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
     if(staged) tma_stage_val_info(s_vi, X.val_info, T.n_values * (u32)sizeof(uint4), &s_mbar);
     WarpSmem S;                                                        // only the distinct-taxon lists are used here
@@ -106,6 +200,8 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
     const u32 span = TILE + k - 1;
     const u32 down = 64 - 2 * k;
     const u32 kmask_lo = (u32)(~0ull >> down), kmask_hi = (u32)((~0ull >> down) >> 32);
+    const u64 kmask = ~0ull >> down;
+    const u32 W = P.W;
 
     // Per-warp staging area in shared memory, filled by cp.async (LDGSTS): no registers are held across the HBM latency
     // and -- unlike a register prefetch -- the wait is a cp.async group wait, not a scoreboard the compiler may share
@@ -170,7 +266,7 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
         const u64 r0 = bt * RB;
         const u32 nrec = (u32)min((u64)RB, n_records - r0);
         const bool have_next_batch = bt + nwarps < n_batches;
-        u32 my_taxon = 0, my_hit = 0, my_miss = 0;
+        u32 my_taxon = 0, my_hit = 0, my_miss = 0, my_def = 0;
         for(u32 j = 0; j < nrec; ++j) {
             // this record's first tile (requested one record ago) and, from the second record on, the next batch's offsets
             // (the newest group at j == 0 is the next batch's offsets, requested a moment ago: not needed yet)
@@ -190,7 +286,9 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
             // ---- per-record state: linear::counter with its first key in registers -----------------------------
             u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
             bool spilled = false;
+            bool deferred = false;
             if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
+            else if(MODE != LEAN_U && L >= k && L - k + 1 > (u32)TILE) deferred = true;   // more than one tile of window elements
             else if(L >= k) {
                 const u32 npos = L - k + 1;
                 for(u32 p0 = 0; p0 < npos; p0 += TILE) {
@@ -217,18 +315,26 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
 #pragma unroll
                         for(int i = 0; i < PPL; ++i)
                             if(((B << ((q0 & 7u) + i)) >> (64 - k)) != 0) mask &= ~(1u << i);
-                        if(COUNTS) n_emit += __reduce_add_sync(FULL, __popc(mask));
-                    } else if(COUNTS) n_emit += min(left, (u32)TILE);
+                        if(COUNTS && MODE == LEAN_U) n_emit += __reduce_add_sync(FULL, __popc(mask));
+                    } else if(COUNTS && MODE == LEAN_U) n_emit += min(left, (u32)TILE);
                     // ---- the lane's four k-mers (and reverse complements) out of one 96-bit window --------------
                     const u32 A = __funnelshift_l(w1, w0, s), B_ = __funnelshift_l(w2, w1, s), C = __funnelshift_l(w3, w2, s);
+                    if(MODE == LEAN_R && P.t_restart) {
+                        // for_each_uncanon_unspaced_windowed tests the 64-bit word against ~0 before masking (encoder.h:283):
+                        // 32 consecutive T restart the rolling state. Leave such records to the generic kernel.
+                        bool run = false;
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) run |= (__funnelshift_l(B_, A, 2 * i) & __funnelshift_l(C, B_, 2 * i)) == ~0u;
+                        if(__any_sync(FULL, run && lane * PPL < left)) { deferred = true; break; }
+                    }
                     u32 R0 = 0, R1 = 0, R2 = 0;
-                    if(CANON) {
+                    if(CANON_ELEM) {
                         R0 = __brev(C); R1 = __brev(B_); R2 = __brev(A);
                         R0 = ~(((R0 >> 1) & 0x55555555u) | ((R0 & 0x55555555u) << 1));
                         R1 = ~(((R1 >> 1) & 0x55555555u) | ((R1 & 0x55555555u) << 1));
                         R2 = ~(((R2 >> 1) & 0x55555555u) | ((R2 & 0x55555555u) << 1));
                     }
-                    u32 hl[PPL], hh[PPL], w[PPL][8];
+                    u32 xls[PPL], xhs[PPL];
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
                         u32 xl, xh;                                                          // forward k-mer: window bits [2i, 2i+2k)
@@ -239,14 +345,67 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                         } else {
                             const u32 fh0 = __funnelshift_l(B_, A, 2 * i), fl0 = __funnelshift_l(C, B_, 2 * i);
                             if(down < 32) { xl = __funnelshift_r(fl0, fh0, down); xh = fh0 >> down; }
-                            else { xl = fh0 >> (down - 32); xh = 0; }                        // k <= 16
+                            else { xl = fh0 >> ((down - 32) & 31u); xh = 0; }                      // k <= 16
                         }
-                        if(CANON) {
+                        if(CANON_ELEM) {
                             const u32 rl = __funnelshift_r(R2, R1, 2 * i) & kmask_lo, rh = __funnelshift_r(R1, R0, 2 * i) & kmask_hi;
                             const u64 f64 = ((u64)xh << 32) | xl, r64 = ((u64)rh << 32) | rl;
                             const bool lt = f64 < r64;
                             xl = lt ? xl : rl; xh = lt ? xh : rh;
                         }
+                        xls[i] = xl; xhs[i] = xh;
+                    }
+                    if(MODE != LEAN_U) {
+                        // ---- window elements -> minimizers (QueueMap, qmap.h:79-96) ---------------------------------
+                        const u32 livem = (1u << nlive) - 1;                 // positions inside the record
+                        WKey e[PPL], o[PPL];
+                        u32 m = npos;                                        // elements pushed
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) {
+                            if(MODE == LEAN_K && !(mask >> i & 1u)) { xls[i] = 0; xhs[i] = 0; }   // invalid -> ~0 -> canonical 0 (encoder.h:622-628)
+                            const bool on = MODE == LEAN_K ? (livem >> i & 1u) : (mask >> i & 1u);
+                            e[i] = on ? wk_make(score_lean(P, ((u64)xhs[i] << 32) | xls[i], kmask), xhs[i], xls[i]) : wk_inf();
+                        }
+                        if(MODE == LEAN_R && slow) {                         // only valid k-mers push: compact them (rare)
+                            u32 tot;
+                            u32 idx = warp_excl_scan(__popc(mask), lane, tot);
+                            uint4 *scratch = (uint4 *)S.ids;                 // TILE x 16 bytes: the distinct-taxon lists are idle here
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i) if(mask >> i & 1u) scratch[idx++] = make_uint4(e[i].sh, e[i].sl, e[i].eh, e[i].el);
+                            __syncwarp();
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i) {
+                                const u32 g = PPL * lane + i;
+                                e[i] = wk_inf();
+                                if(g < tot) { const uint4 t4 = scratch[g]; e[i].sh = t4.x; e[i].sl = t4.y; e[i].eh = t4.z; e[i].el = t4.w; }
+                            }
+                            __syncwarp();
+                            m = tot;
+                        }
+                        mask = window_min_tile(e, m, W, lane, o);
+                        if(MODE == LEAN_R && P.tail_flush && m > 0 && m < W) {
+                            // a queue that never filled emits its minimum once (encoder.h:304-305,343-344)
+                            WKey a = wk_min(wk_min(e[0], e[1]), wk_min(e[2], e[3]));
+#pragma unroll
+                            for(int d = 16; d; d >>= 1) a = wk_min(a, wk_shfl_xor(a, d));
+                            o[0] = a;
+                            mask = lane == 0 ? 1u : 0u;
+                        }
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) {
+                            xls[i] = o[i].el; xhs[i] = o[i].eh;
+                            if(P.filter_none && (xls[i] & xhs[i]) == ~0u) mask &= ~(1u << i);      // `!= ENCODE_OVERFLOW`
+                            if(MODE == LEAN_R && CANON) {                                          // canonical on emit (encoder.h:347-353)
+                                const u64 cx = canonical(((u64)xhs[i] << 32) | xls[i], k);
+                                xls[i] = (u32)cx; xhs[i] = (u32)(cx >> 32);
+                            }
+                        }
+                        if(COUNTS) n_emit += __reduce_add_sync(FULL, __popc(mask));
+                    }
+                    u32 hl[PPL], hh[PPL], w[PPL][8];
+#pragma unroll
+                    for(int i = 0; i < PPL; ++i) {
+                        const u32 xl = xls[i], xh = xhs[i];
                         // mix64 (bns_device.cuh) on 32-bit halves
                         u64 x = ((u64)xh << 32) | (xl ^ xh);
                         x *= 0xd6e8feb86659fd93ull;
@@ -323,6 +482,11 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                     }
                 }
             }
+            if(MODE != LEAN_U && deferred) {                           // the generic kernel redoes this record from scratch
+                if(lane == 0) defer_idx[atomicAdd(defer_cnt, 1ull)] = (u32)(r0 + j);
+                nd = 0; n_hit = 0; n_emit = 0;
+                if(spilled) { spilled = false; sink.n_distinct = 0; sink.overflow = 0; }
+            }
             // ---- resolve_tree (util.h:831-869) -------------------------------------------------------------------
             u32 taxon = 0;
             if(spilled) {
@@ -331,7 +495,7 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
                 sink.n_distinct = 0; sink.overflow = 0;
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
-            if(lane == j) { my_taxon = taxon; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; } }
+            if(lane == j) { my_taxon = taxon; my_def = deferred; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; } }
             rb = xb; L = xl; tb ^= 1;
         }
         // ---- one coalesced store per output array for the batch ------------------------------------------------------
@@ -343,9 +507,10 @@ bns_classify_u_kernel(u32 k_rt, const char *__restrict__ bases, const u64 *__res
             }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
+        const u32 ndef = MODE == LEAN_U ? 0u : __popc(__ballot_sync(FULL, lane < nrec && my_def != 0));
         if(lane == 0) {                                                // classified_[2] (classifier.h:138,238), once per batch
             atomicAdd(&counters[0], (unsigned long long)cls);
-            atomicAdd(&counters[1], (unsigned long long)(nrec - cls));
+            atomicAdd(&counters[1], (unsigned long long)(nrec - cls - ndef));
         }
         pb ^= 1;
     }

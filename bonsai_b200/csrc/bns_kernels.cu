@@ -757,7 +757,9 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
                     u64 n_records, u32 mates, u64 total_bases, TableView T, TaxView X,
                     u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out, u32 *__restrict__ nmiss_out,
                     u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 *__restrict__ mate1_out, u32 ring_cap,
-                    unsigned long long *__restrict__ counters, u32 *__restrict__ status) {
+                    unsigned long long *__restrict__ counters, u32 *__restrict__ status,
+                    const u32 *__restrict__ rec_list, const unsigned long long *__restrict__ rec_count) {
+    // rec_list != nullptr: only the *rec_count records it names (what the lean kernel left for this one)
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
@@ -772,7 +774,7 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
     u32 n_cls = 0, n_uncls = 0;
     const char *buf_end = bases + total_bases;
     const u64 r_first = (u64)blockIdx.x * WARPS_PER_CTA + wid;
-    if(FAM == FAM_U && mates == 1) {
+    if(FAM == FAM_U && mates == 1 && !rec_list) {
         // Software pipeline over this warp's records: the offsets of record r+2*nwarps and the first tile of record
         // r+nwarps are requested before record r is processed, so neither the offset fetch nor the read bytes (both
         // stream from HBM) stall the warp when their turn comes.
@@ -803,8 +805,10 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
             __syncwarp();
             b0 = b1; e0 = e1; v0 = v1; b1 = b2; e1 = e2;
         }
-    } else
-    for(u64 r = r_first; r < n_records; r += nwarps) {
+    } else {
+    const u64 n_loop = rec_list ? (u64)*rec_count : n_records;
+    for(u64 it = r_first; it < n_loop; it += nwarps) {
+        const u64 r = rec_list ? (u64)rec_list[it] : it;
         sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
         for(u32 mt = 0; mt < mates; ++mt) {
             const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
@@ -821,6 +825,7 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
         }
         if(taxon) ++n_cls; else ++n_uncls;
         __syncwarp();
+    }
     }
     if(lane == 0 && (n_cls | n_uncls)) {
         atomicAdd(&counters[0], (unsigned long long)n_cls);
@@ -1003,7 +1008,7 @@ size_t stream_smem_bytes(u32 ring_cap, bool classify) { return WARPS_PER_CTA * w
 
 typedef void (*encode_fn)(const EncParams, const char *, const u64 *, u64, u64, u64 *, const u64 *, u32 *, u32, u32 *);
 typedef void (*classify_fn)(const EncParams, const char *, const u64 *, u64, u32, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                            u32 *, const u64 *, u32 *, u32, unsigned long long *, u32 *);
+                            u32 *, const u64 *, u32 *, u32, unsigned long long *, u32 *, const u32 *, const unsigned long long *);
 
 static encode_fn pick_encode(u32 fam) {
     switch(fam) {
@@ -1031,63 +1036,90 @@ cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_
                                              ring_cap, status);
     return cudaGetLastError();
 }
-// Which kernel a classify call runs and with what geometry. The lean kernel covers what `bonsai classify` runs (FAM_U,
-// single-end, no ordered hit list); everything else goes to the generic stream kernel.
-static bool lean_ok(const EncParams &P, u32 mates, bool taxa, bool mate1) {
+// Which kernel a classify call runs and with what geometry. The lean kernel covers single-end records without an ordered
+// hit list for every unspaced encoder: what `bonsai classify` runs (FAM_U) and the windowed minimizer modes (FAM_K
+// canonical, FAM_R); everything else (spaced seeds, paired records, hit lists) goes to the generic stream kernel.
+static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 #ifdef BNS_NO_LEAN
-    return false;
+    return -1;
 #endif
-    return P.family == FAM_U && mates == 1 && !taxa && !mate1;
+    if(mates != 1 || taxa || mate1) return -1;
+    if(P.family == FAM_U) return LEAN_U;
+    const bool unspaced = P.c == P.k;
+    if(!unspaced || P.W > (u32)TILE) return -1;
+    if(P.family == FAM_K && P.canon_elem) return LEAN_K;
+    if(P.family == FAM_R) return LEAN_R;
+    return -1;
 }
-typedef void (*classify_u_fn)(u32, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *, unsigned long long *, u32 *);
+typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
+                              unsigned long long *, u32 *, u32 *, unsigned long long *);
 static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
-template <bool CANON, bool COUNTS>
+template <int MODE, bool CANON, bool COUNTS>
 static classify_u_fn pick_lean_k(u32 k) {
-    return k == 31 ? bns_classify_u_kernel<CANON, 31, COUNTS> : bns_classify_u_kernel<CANON, 0, COUNTS>;
+    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS>;
 }
-static classify_u_fn pick_lean(const EncParams &P, bool counts) {
-    if(P.canon_elem) return counts ? pick_lean_k<true, true>(P.k) : pick_lean_k<true, false>(P.k);
-    return counts ? pick_lean_k<false, true>(P.k) : pick_lean_k<false, false>(P.k);
+static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts) {
+    if(mode == LEAN_K) return pick_lean_k<LEAN_K, true, true>(P.k);
+    if(mode == LEAN_R) return P.canon_emit ? pick_lean_k<LEAN_R, true, true>(P.k) : pick_lean_k<LEAN_R, false, true>(P.k);
+    if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true>(P.k) : pick_lean_k<LEAN_U, true, false>(P.k);
+    return counts ? pick_lean_k<LEAN_U, false, true>(P.k) : pick_lean_k<LEAN_U, false, false>(P.k);
 }
 
 ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
     ClassifyPlan pl;
-    pl.lean = lean_ok(P, mates, taxa, mate1);
+    pl.lean_mode = lean_mode(P, mates, taxa, mate1);
+    pl.lean = pl.lean_mode >= 0;
     pl.counts = counts;
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, counts);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, counts);
         pl.smem = lean_smem();
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, LEAN_WARPS * 32, pl.smem);
         const u64 want = ((n_records + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;           // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
-    } else {
+    }
+    if(!pl.lean || pl.lean_mode != LEAN_U) {                          // the generic kernel: everything, or the deferred records
+        int ng = 0;
         classify_fn f = pick_classify(P.family, taxa);
-        pl.smem = stream_smem_bytes(ring_cap, true);
-        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, WARPS_PER_CTA * 32, pl.smem);
+        pl.gen_smem = stream_smem_bytes(ring_cap, true);
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.gen_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ng, f, WARPS_PER_CTA * 32, pl.gen_smem);
         const u64 want = (n_records + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
+        pl.gen_grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (ng > 0 ? ng : 1)));
+        if(!pl.lean) { nb = ng; pl.grid = pl.gen_grid; pl.smem = pl.gen_smem; }
     }
     pl.occupancy = nb;
     return pl;
 }
 
+// defer_idx / defer_cnt: device scratch of n_records u32 and one zeroed counter (windowed lean modes only)
 cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStream_t st, const char *bases, const u64 *offsets,
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
-                            u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status) {
+                            u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched) {
+    if(n_launched) *n_launched = 1;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.counts);
-        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P.k, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
-                                                        counters, status);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts);
+        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
+                                                    counters, status, defer_idx, defer_cnt);
+        cudaError_t e = cudaGetLastError();
+        if(e != cudaSuccess || pl.lean_mode == LEAN_U) return e;
+        // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel
+        // reads the count on the device and returns at once. Sized small: deferred records are rare and long.
+        classify_fn g = pick_classify(P.family, false);
+        g<<<pl.gen_grid, WARPS_PER_CTA * 32, pl.gen_smem, st>>>(P, bases, offsets, n_records, 1u, total_bases, T, X, taxon_out,
+                                                               nhit_out, nmiss_out, nullptr, nullptr, nullptr, ring_cap, counters,
+                                                               status, defer_idx, defer_cnt);
+        if(n_launched) *n_launched = 2;
         return cudaGetLastError();
     }
     classify_fn f = pick_classify(P.family, taxa_out != nullptr);
     f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
-                                                    nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status);
+                                                    nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status,
+                                                    nullptr, nullptr);
     return cudaGetLastError();
 }
 int encode_occupancy(const EncParams &P, size_t smem) {

@@ -16,7 +16,8 @@ struct TableView;
 struct TaxView;
 
 size_t stream_smem_bytes(u32 ring_cap, bool classify);
-struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true; int occupancy = 0; };
+enum LeanMode : int { LEAN_U = 0, LEAN_K = 1, LEAN_R = 2 };   // what bns_classify_u_kernel runs as (bns_classify_u.cuh)
+struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0; };
 ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts);
 int encode_occupancy(const EncParams &P, size_t smem);
 
@@ -25,7 +26,8 @@ cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_
 cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_records,
                             u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
-                            u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status);
+                            u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched);
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
                          u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 F, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap);
