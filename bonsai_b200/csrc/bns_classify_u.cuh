@@ -84,32 +84,42 @@ __device__ __forceinline__ void pack8(uint2 v, u32 &codes16, u32 &bad8) {
 // lanes is assembled from the set bits of c while the table is built, so no level is kept.
 // ---------------------------------------------------------------------------------------------
 
-struct WKey { u32 sh, sl, eh, el; };                                   // score (hi, lo), element (hi, lo)
-__device__ __forceinline__ WKey wk_make(u64 score, u32 eh, u32 el) { WKey k; k.sh = (u32)(score >> 32); k.sl = (u32)score; k.eh = eh; k.el = el; return k; }
-__device__ __forceinline__ WKey wk_inf() { WKey k; k.sh = k.sl = k.eh = k.el = ~0u; return k; }
-__device__ __forceinline__ WKey wk_min(const WKey &a, const WKey &b) {
-    const u64 as = ((u64)a.sh << 32) | a.sl, bs = ((u64)b.sh << 32) | b.sl, ae = ((u64)a.eh << 32) | a.el, be = ((u64)b.eh << 32) | b.el;
-    const bool lt = bs < as || (bs == as && be < ae);
-    WKey r;
-    r.sh = lt ? b.sh : a.sh; r.sl = lt ? b.sl : a.sl; r.eh = lt ? b.eh : a.eh; r.el = lt ? b.el : a.el;
+// NW = 4: (score hi, score lo, element hi, element lo);  NW = 2: one 64-bit key (hi, lo) when the order of the pairs is the
+// order of a single word: the Lex score is a bijection of the k-mer (the k-mer is recovered with lex_unscore), and with
+// the saturating cast the entropy scores are non-decreasing in the k-mer (LEAN_KEY_ELEM, see pick_lean()).
+template <int NW> struct WKey { u32 w[NW]; };
+template <int NW> __device__ __forceinline__ WKey<NW> wk_inf() { WKey<NW> k; for(int i = 0; i < NW; ++i) k.w[i] = ~0u; return k; }
+template <int NW> __device__ __forceinline__ WKey<NW> wk_min(const WKey<NW> &a, const WKey<NW> &b) {
+    bool lt;
+    const u64 a0 = ((u64)a.w[0] << 32) | a.w[1], b0 = ((u64)b.w[0] << 32) | b.w[1];
+    if(NW == 2) lt = b0 < a0;
+    else {
+        const u64 a1 = ((u64)a.w[NW - 2] << 32) | a.w[NW - 1], b1 = ((u64)b.w[NW - 2] << 32) | b.w[NW - 1];
+        lt = b0 < a0 || (b0 == a0 && b1 < a1);
+    }
+    WKey<NW> r;
+#pragma unroll
+    for(int i = 0; i < NW; ++i) r.w[i] = lt ? b.w[i] : a.w[i];
     return r;
 }
-__device__ __forceinline__ WKey wk_shfl_up(const WKey &a, u32 d) {
-    WKey r;
-    r.sh = __shfl_up_sync(FULL, a.sh, d); r.sl = __shfl_up_sync(FULL, a.sl, d);
-    r.eh = __shfl_up_sync(FULL, a.eh, d); r.el = __shfl_up_sync(FULL, a.el, d);
+template <int NW> __device__ __forceinline__ WKey<NW> wk_shfl_up(const WKey<NW> &a, u32 d) {
+    WKey<NW> r;
+#pragma unroll
+    for(int i = 0; i < NW; ++i) r.w[i] = __shfl_up_sync(FULL, a.w[i], d);
     return r;
 }
-__device__ __forceinline__ WKey wk_shfl_xor(const WKey &a, u32 d) {
-    WKey r;
-    r.sh = __shfl_xor_sync(FULL, a.sh, d); r.sl = __shfl_xor_sync(FULL, a.sl, d);
-    r.eh = __shfl_xor_sync(FULL, a.eh, d); r.el = __shfl_xor_sync(FULL, a.el, d);
+template <int NW> __device__ __forceinline__ WKey<NW> wk_shfl_xor(const WKey<NW> &a, u32 d) {
+    WKey<NW> r;
+#pragma unroll
+    for(int i = 0; i < NW; ++i) r.w[i] = __shfl_xor_sync(FULL, a.w[i], d);
     return r;
 }
 // e[0..3]: this lane's elements (wk_inf() past the m-th). o[i] = minimum over elements [g-W+1, g], g = 4*lane+i.
 // Returns the mask of i with W-1 <= g < m (the windows QueueMap::next_value returns an element for, qmap.h:79-87).
-__device__ __forceinline__ u32 window_min_tile(const WKey (&e)[PPL], u32 m, u32 W, u32 lane, WKey (&o)[PPL]) {
-    WKey P[PPL], S[PPL];
+template <int NW>
+__device__ __forceinline__ u32 window_min_tile(const WKey<NW> (&e)[PPL], u32 m, u32 W, u32 lane, WKey<NW> (&o)[PPL]) {
+    typedef WKey<NW> K;
+    K P[PPL], S[PPL];
     P[0] = e[0]; P[1] = wk_min(P[0], e[1]); P[2] = wk_min(P[1], e[2]); P[3] = wk_min(P[2], e[3]);
     S[3] = e[3]; S[2] = wk_min(e[2], S[3]); S[1] = wk_min(e[1], S[2]); S[0] = P[3];
     int f[PPL]; u32 c[PPL], off[PPL];
@@ -122,10 +132,17 @@ __device__ __forceinline__ u32 window_min_tile(const WKey (&e)[PPL], u32 m, u32 
         c[i] = f[i] < 0 ? (u32)(-f[i] - 1) : 0u;                        // whole lanes between the two partial ones
         call |= c[i];
     }
-    WKey R[PPL];
+    // the partial first lane: a suffix of lane l+f's elements
+    K R[PPL];
 #pragma unroll
-    for(int i = 0; i < PPL; ++i) R[i] = wk_inf();
-    WKey U = S[0];                                                     // level j: minimum of the lane minima of lanes l-2^j+1 .. l
+    for(int i = 0; i < PPL; ++i) {
+        R[i] = wk_inf<NW>();
+        if(f[i] < 0) {
+            const K sel = off[i] == 0 ? S[0] : off[i] == 1 ? S[1] : off[i] == 2 ? S[2] : S[3];
+            R[i] = wk_shfl_up(sel, (u32)(-f[i]));
+        }
+    }
+    K U = S[0];                                                        // level j: minimum of the lane minima of lanes l-2^j+1 .. l
 #pragma unroll
     for(int j = 0; j < 5; ++j) {
         if((call >> j) == 0) break;                                    // warp-uniform (W is)
@@ -138,11 +155,9 @@ __device__ __forceinline__ u32 window_min_tile(const WKey (&e)[PPL], u32 m, u32 
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         const u32 g = PPL * lane + i;
-        if(f[i] < 0) {
-            const WKey sel = off[i] == 0 ? S[0] : off[i] == 1 ? S[1] : off[i] == 2 ? S[2] : S[3];
-            o[i] = wk_min(wk_min(wk_shfl_up(sel, (u32)(-f[i])), R[i]), P[i]);
-        } else {                                                       // W <= i+1: the window lies inside this lane
-            WKey a = e[i];
+        if(f[i] < 0) o[i] = wk_min(R[i], P[i]);
+        else {                                                         // W <= i+1: the window lies inside this lane
+            K a = e[i];
 #pragma unroll
             for(int q = 0; q < PPL; ++q) if(q < i && (u32)q >= off[i]) a = wk_min(a, e[q]);
             o[i] = a;
@@ -150,6 +165,14 @@ __device__ __forceinline__ u32 window_min_tile(const WKey (&e)[PPL], u32 m, u32 
         if(g + 1 >= W && g < m) mask |= 1u << i;
     }
     return mask;
+}
+
+// inverse of lex_score (bns_device.cuh): xor, rotate and an odd multiply are all invertible
+__device__ __forceinline__ u64 lex_unscore(u64 s) {
+    constexpr u64 MI = inv_odd(0x9a98567ed20c127dull);
+    s ^= 0x691a9d706391077aull;
+    s = (s >> 31) | (s << 33);
+    return (s * MI) ^ 0x533f8c2151b20f97ull;
 }
 
 // score of a window element; same values as score_of() (bns_kernels.cu). With the saturating cast every k-mer that holds
@@ -168,7 +191,9 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
 // KT: compile-time k (0 = use P.k). COUNTS: per-record hit / missing counts are wanted.
 // Windowed modes handle records of at most TILE window elements here; longer ones (and the 32-T restart quirk of
 // encoder.h:283) are appended to defer_idx and done by the generic stream kernel right after this one.
-template <int MODE, bool CANON, int KT, bool COUNTS>
+// KEY (windowed modes): how a window element is ordered -- LEAN_KEY_PAIR (score, k-mer) in full, LEAN_KEY_LEX the Lex score
+// alone, LEAN_KEY_ELEM the k-mer alone (scores non-decreasing in the k-mer); chosen by pick_lean().
+template <int MODE, bool CANON, int KT, bool COUNTS, int KEY>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
@@ -358,34 +383,45 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     if(MODE != LEAN_U) {
                         // ---- window elements -> minimizers (QueueMap, qmap.h:79-96) ---------------------------------
                         const u32 livem = (1u << nlive) - 1;                 // positions inside the record
-                        WKey e[PPL], o[PPL];
+                        constexpr int NW = KEY == LEAN_KEY_PAIR ? 4 : 2;
+                        WKey<NW> e[PPL], o[PPL];
                         u32 m = npos;                                        // elements pushed
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) {
                             if(MODE == LEAN_K && !(mask >> i & 1u)) { xls[i] = 0; xhs[i] = 0; }   // invalid -> ~0 -> canonical 0 (encoder.h:622-628)
                             const bool on = MODE == LEAN_K ? (livem >> i & 1u) : (mask >> i & 1u);
-                            e[i] = on ? wk_make(score_lean(P, ((u64)xhs[i] << 32) | xls[i], kmask), xhs[i], xls[i]) : wk_inf();
+                            e[i] = wk_inf<NW>();
+                            if(on) {
+                                const u64 xe = ((u64)xhs[i] << 32) | xls[i];
+                                if(KEY == LEAN_KEY_ELEM) { e[i].w[0] = xhs[i]; e[i].w[1] = xls[i]; }
+                                else {
+                                    const u64 sc = KEY == LEAN_KEY_LEX ? lex_score(xe) : score_lean(P, xe, kmask);
+                                    e[i].w[0] = (u32)(sc >> 32); e[i].w[1] = (u32)sc;
+                                    if(KEY == LEAN_KEY_PAIR) { e[i].w[NW - 2] = xhs[i]; e[i].w[NW - 1] = xls[i]; }
+                                }
+                            }
                         }
                         if(MODE == LEAN_R && slow) {                         // only valid k-mers push: compact them (rare)
                             u32 tot;
                             u32 idx = warp_excl_scan(__popc(mask), lane, tot);
                             uint4 *scratch = (uint4 *)S.ids;                 // TILE x 16 bytes: the distinct-taxon lists are idle here
 #pragma unroll
-                            for(int i = 0; i < PPL; ++i) if(mask >> i & 1u) scratch[idx++] = make_uint4(e[i].sh, e[i].sl, e[i].eh, e[i].el);
+                            for(int i = 0; i < PPL; ++i)
+                                if(mask >> i & 1u) scratch[idx++] = make_uint4(e[i].w[0], e[i].w[1], e[i].w[NW - 2], e[i].w[NW - 1]);
                             __syncwarp();
 #pragma unroll
                             for(int i = 0; i < PPL; ++i) {
                                 const u32 g = PPL * lane + i;
-                                e[i] = wk_inf();
-                                if(g < tot) { const uint4 t4 = scratch[g]; e[i].sh = t4.x; e[i].sl = t4.y; e[i].eh = t4.z; e[i].el = t4.w; }
+                                e[i] = wk_inf<NW>();
+                                if(g < tot) { const uint4 t4 = scratch[g]; e[i].w[0] = t4.x; e[i].w[1] = t4.y; e[i].w[NW - 2] = t4.z; e[i].w[NW - 1] = t4.w; }
                             }
                             __syncwarp();
                             m = tot;
                         }
-                        mask = window_min_tile(e, m, W, lane, o);
+                        mask = window_min_tile<NW>(e, m, W, lane, o);
                         if(MODE == LEAN_R && P.tail_flush && m > 0 && m < W) {
                             // a queue that never filled emits its minimum once (encoder.h:304-305,343-344)
-                            WKey a = wk_min(wk_min(e[0], e[1]), wk_min(e[2], e[3]));
+                            WKey<NW> a = wk_min(wk_min(e[0], e[1]), wk_min(e[2], e[3]));
 #pragma unroll
                             for(int d = 16; d; d >>= 1) a = wk_min(a, wk_shfl_xor(a, d));
                             o[0] = a;
@@ -393,7 +429,10 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         }
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) {
-                            xls[i] = o[i].el; xhs[i] = o[i].eh;
+                            if(KEY == LEAN_KEY_LEX) {
+                                const u64 xe = lex_unscore(((u64)o[i].w[0] << 32) | o[i].w[1]);
+                                xls[i] = (u32)xe; xhs[i] = (u32)(xe >> 32);
+                            } else { xls[i] = o[i].w[NW - 1]; xhs[i] = o[i].w[NW - 2]; }
                             if(P.filter_none && (xls[i] & xhs[i]) == ~0u) mask &= ~(1u << i);      // `!= ENCODE_OVERFLOW`
                             if(MODE == LEAN_R && CANON) {                                          // canonical on emit (encoder.h:347-353)
                                 const u64 cx = canonical(((u64)xhs[i] << 32) | xls[i], k);

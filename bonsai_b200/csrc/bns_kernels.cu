@@ -1054,15 +1054,32 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
                               unsigned long long *, u32 *, u32 *, unsigned long long *);
 static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
-template <int MODE, bool CANON, bool COUNTS>
+template <int MODE, bool CANON, bool COUNTS, int KEY>
 static classify_u_fn pick_lean_k(u32 k) {
-    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS>;
+    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY>;
+}
+template <int MODE, bool CANON>
+static classify_u_fn pick_lean_key(u32 k, int key) {
+    if(key == LEAN_KEY_LEX) return pick_lean_k<MODE, CANON, true, LEAN_KEY_LEX>(k);
+    if(key == LEAN_KEY_ELEM) return pick_lean_k<MODE, CANON, true, LEAN_KEY_ELEM>(k);
+    return pick_lean_k<MODE, CANON, true, LEAN_KEY_PAIR>(k);
+}
+// How the (score, k-mer) pairs of a window can be ordered by one 64-bit word (bit-identical minima):
+//  * Lex: the score is a bijection of the k-mer (ties in score are ties in k-mer).
+//  * entropy scores under the saturating cast: every k-mer but the all-A one scores ~0 once kmer / 0.001 >= 2^64 for the
+//    other homopolymers, i.e. (4^k-1)/3 * 1000 >= 2^64, k >= 28 (rolling entropy), and for every k when the entropy is
+//    the NOT_FULL constant (kmer / -0.9999 <= -1 for kmer >= 1); the all-A k-mer is 0 and scores 0: the pair order is
+//    the k-mer order.
+static int lean_key(const EncParams &P) {
+    if(P.score_kind == SC_LEX) return LEAN_KEY_LEX;
+    if(!P.cast_wrap && (P.score_kind == SC_ENT_NOTFULL || (P.score_kind == SC_ENT_ROLL && P.k >= 28))) return LEAN_KEY_ELEM;
+    return LEAN_KEY_PAIR;
 }
 static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts) {
-    if(mode == LEAN_K) return pick_lean_k<LEAN_K, true, true>(P.k);
-    if(mode == LEAN_R) return P.canon_emit ? pick_lean_k<LEAN_R, true, true>(P.k) : pick_lean_k<LEAN_R, false, true>(P.k);
-    if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true>(P.k) : pick_lean_k<LEAN_U, true, false>(P.k);
-    return counts ? pick_lean_k<LEAN_U, false, true>(P.k) : pick_lean_k<LEAN_U, false, false>(P.k);
+    if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P));
+    if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P)) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P));
+    if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k) : pick_lean_k<LEAN_U, true, false, 0>(P.k);
+    return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k) : pick_lean_k<LEAN_U, false, false, 0>(P.k);
 }
 
 ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
