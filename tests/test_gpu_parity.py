@@ -469,3 +469,63 @@ def test_many_distinct_taxa_and_big_taxonomy(capi, oracle):
         with pytest.raises(capi.BnsError) as e:
             ctx.classify(b2, o2)
         assert e.value.code == -6
+
+
+@pytest.mark.parametrize("mode", ["lex_canon", "lex_nocanon", "ent_canon_sat", "ent_canon_wrap", "ent_nocanon_sat",
+                                  "path_ent_canon", "lex_canon_w33", "ent_canon_k21_w60"])
+def test_classify_lean_windowed_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, mode):
+    """The lean kernel's windowed modes (shuffle-only sliding minima; counts, no hit list) against the oracle on reads
+    that exercise its corners: reads shorter than the window (tail flush), empty reads, N (compaction / k-mer 0), runs of
+    >= 32 T (the encoder.h:283 restart: deferred to the generic kernel) and multi-tile records (deferred as well)."""
+    cfg = {
+        "lex_canon":         dict(k=31, w=50, score=po.SCORE_LEX, canon=True, api=po.API_STRING, cast=po.CAST_SATURATE),
+        "lex_nocanon":       dict(k=31, w=50, score=po.SCORE_LEX, canon=False, api=po.API_STRING, cast=po.CAST_SATURATE),
+        "ent_canon_sat":     dict(k=31, w=50, score=po.SCORE_ENTROPY, canon=True, api=po.API_STRING, cast=po.CAST_SATURATE),
+        "ent_canon_wrap":    dict(k=31, w=50, score=po.SCORE_ENTROPY, canon=True, api=po.API_STRING, cast=po.CAST_WRAP),
+        "ent_nocanon_sat":   dict(k=31, w=50, score=po.SCORE_ENTROPY, canon=False, api=po.API_STRING, cast=po.CAST_SATURATE),
+        "path_ent_canon":    dict(k=31, w=50, score=po.SCORE_ENTROPY, canon=True, api=po.API_PATH, cast=po.CAST_SATURATE),
+        "lex_canon_w33":     dict(k=31, w=33, score=po.SCORE_LEX, canon=True, api=po.API_STRING, cast=po.CAST_SATURATE),
+        "ent_canon_k21_w60": dict(k=21, w=60, score=po.SCORE_ENTROPY, canon=True, api=po.API_STRING, cast=po.CAST_SATURATE),
+    }[mode]
+    k, w = cfg["k"], cfg["w"]
+    rng = np.random.default_rng(11)
+    bases, offs, _ = H.make_reads(1500, seed=21, ragged=True)
+    reads = [bytes(bases[int(offs[i]):int(offs[i + 1])]) for i in range(offs.size - 1)]
+    fixed, foffs, _ = H.make_reads(1500, seed=22)
+    reads += [bytes(fixed[int(foffs[i]):int(foffs[i + 1])]) for i in range(foffs.size - 1)]
+    g = genomes["bases"]
+    for j in range(40):                                   # T runs of 30..70 inside genome reads; homopolymers; many N
+        s = int(rng.integers(0, g.size - 400))
+        r = bytearray(g[s:s + 150].tobytes())
+        p, n = int(rng.integers(0, 80)), int(rng.integers(30, 71))
+        r[p:p + n] = (b"T" if j % 4 else b"A") * n
+        if j % 5 == 0:
+            r[int(rng.integers(0, 150))] = ord("N")
+        reads.append(bytes(r[:150]))
+    for j in range(12):                                   # multi-tile records
+        s = int(rng.integers(0, g.size - 3000))
+        reads.append(bytes(g[s:s + int(rng.integers(160 + k, 2500))]))
+    reads += [b"T" * 150, b"A" * 150, b"ACGT" * 40, b"N" * 150, b"", b"ACGTN" * 30]
+    b, o = po.pack_reads(reads)
+    dbname = "lex_k31_w31" if k == 31 else None
+    if dbname:
+        db = dbcache.get(dbname)
+    else:                                                 # a k=21 DB of the first genome only
+        db = oracle.db_new()
+        oracle.db_add_genome(db, toy_tax, H.genome_records(genomes, 0), H.GENOME_TAXIDS[0], k, k)
+    keys, vals, flags, nb, _ = oracle.db_arrays(db)
+    c, p = H.toy_tax_arrays()
+    with capi.Context(k, w, None, cfg["score"], cfg["canon"], cfg["api"], entropy_cast=cfg["cast"]) as ctx:
+        ctx.load_table(keys, vals, flags, nb)
+        ctx.load_taxonomy(c, p)
+        got = ctx.classify(b, o)                          # counts, no hit list: the lean kernel
+        got_taxon_only, _, _ = ctx.classify(b, o, want_counts=False)
+        full = ctx.classify(b, o, want_taxa=True)         # the generic kernel (ordered hit lists)
+    exp = oracle.classify(db, toy_tax, b, o, k, w, None, cfg["score"], cfg["canon"], cfg["api"], cast_mode=cfg["cast"])
+    for name, a, bb in zip(("taxon", "nhit", "nmiss"), exp, got):
+        bad = np.nonzero(a != bb)[0]
+        assert bad.size == 0, "%s differs for %d records, first %d (len %d): oracle %d gpu %d" % (
+            name, bad.size, bad[0], len(reads[bad[0]]), a[bad[0]], bb[bad[0]])
+    assert np.array_equal(got_taxon_only, exp[0])
+    for a, bb in zip(exp, full[:3]):
+        assert np.array_equal(a, bb)
