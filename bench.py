@@ -202,7 +202,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        from bonsai_b200 import sharding
+        numa = sharding.bind_to_gpu_numa(local_rank)      # before any pinned buffer exists
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         build.build()
@@ -393,7 +396,8 @@ def main():
             "config": {"workload": spec["label"], "name": args.workload, "reads_per_gpu_per_step": n, "read_len": L_READ, "k": K,
                        "db_keys": tinfo["n_keys"], "db_table_mb": tinfo["bytes"] / 1e6, "parallelism": "reads sharded x%d, DB replicated" % world,
                        "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no explicit flush" % (n * L_READ / 1e9),
-                       "synthetic_genomes": bool(g["synthetic_genomes"]), "db_build_s": t_db, "db_broadcast_ms": bcast_ms},
+                       "synthetic_genomes": bool(g["synthetic_genomes"]), "db_build_s": t_db, "db_broadcast_ms": bcast_ms,
+                       "numa_node_rank0": numa},
             "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": int(n * L_READ + 8 * (n + 1)),
                     "d2h_bytes_per_step": int(4 * n), "steps": args.e2e_steps, "taxids_match_device_path": same},
             "gpu_launches": int(gpu_launches),

@@ -74,6 +74,7 @@ struct bns_b200_ctx {
     // misc device state
     unsigned long long *d_counters = nullptr;   // [0] classified [1] unclassified [2..7] scratch [8..11] build stats
     bool building = false;
+    bool timed = false;               // ev0/ev1 have been recorded
     u32 *d_status = nullptr;
     Slot slots[N_SLOTS];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1017,10 +1018,9 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     const u64 n_rec = n_reads / mates;
     if(!n_rec) return BNS_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // total bases = offsets[n_reads] lives on the device; the kernel only uses it to bound the 16-byte staging loads
-    u64 total_bases = 0;
-    CK(cudaMemcpyAsync(&total_bases, d_offsets + n_reads, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // Fully asynchronous: nothing is read back. The total base count (offsets[n_reads]) lives on the device; the generic
+    // kernel, which bounds its staging loads with it, reads it there (sentinel ~0), the lean kernel does not need it.
+    const u64 total_bases = ~0ull;
     const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
     Slot &s0 = ctx->slots[0];
     if(pl.lean && pl.lean_mode != LEAN_U) {
@@ -1036,8 +1036,8 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
                        s0.d_defer, s0.d_defer_cnt, &nl));
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += nl;
-    ctx->stats.reads_processed += n_reads;
-    ctx->stats.bases_processed += total_bases;
+    ctx->stats.reads_processed += n_reads;          // bases_processed is not known on the host for device-resident calls
+    ctx->timed = true;
     return BNS_OK;
 }
 
@@ -1128,8 +1128,10 @@ int bns_b200_stats_get(const bns_b200_t *ctx_, bns_b200_stats *out) {
     ctx->stats.n_classified = h[0];
     ctx->stats.n_unclassified = h[1];
     float ms = 0.f;
-    if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
-    else cudaGetLastError();
+    if(ctx->timed) {
+        if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+        else cudaGetLastError();
+    }
     *out = ctx->stats;
     return BNS_OK;
 }
@@ -1161,6 +1163,7 @@ int bns_b200_bench_gather(bns_b200_t *ctx, uint64_t n_loads, uint64_t seed, doub
     CK(cudaEventRecord(ctx->ev0, st));
     CK(launch_gather(ctx->n_sm * 8, st, ctx->d_slots, ctx->bucket_bits, n_loads, seed, ctx->d_counters + 7));
     CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
     ++ctx->stats.kernel_launches;
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;

@@ -772,7 +772,9 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
     sink.vi = staged ? s_vi : X.val_info;
     if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
-    const char *buf_end = bases + total_bases;
+    // total_bases == ~0: the caller's offsets live on the device only (bns_b200_classify_device); the bound of the
+    // 16-byte staging loads is the last offset
+    const char *buf_end = bases + (total_bases == ~0ull ? offsets[n_records * mates] : total_bases);
     const u64 r_first = (u64)blockIdx.x * WARPS_PER_CTA + wid;
     if(FAM == FAM_U && mates == 1 && !rec_list) {
         // Software pipeline over this warp's records: the offsets of record r+2*nwarps and the first tile of record

@@ -46,3 +46,35 @@ def replicate_db(ctx, dist, rank, root=0, device=None, as_tensor=None, header_de
     if rank != root:
         ctx.db_commit()
     return moved
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host buffer is allocated, so that
+    the ring buffers the H2D copies read from are local to the GPU's PCIe root (first-touch placement). With one process
+    per GPU on a two-socket box this keeps every rank's staging traffic off the inter-socket link. Returns the node or
+    None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
