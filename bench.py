@@ -394,7 +394,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": spec["label"], "name": args.workload, "reads_per_gpu_per_step": n, "read_len": L_READ, "k": K,
-                       "db_keys": tinfo["n_keys"], "db_table_mb": tinfo["bytes"] / 1e6, "parallelism": "reads sharded x%d, DB replicated" % world,
+                       "db_keys": tinfo["n_keys"], "db_table_mb": tinfo["bytes"] / 1e6,
+                       "db_layout": "minimizer" if tinfo.get("layout") else "hash", "parallelism": "reads sharded x%d, DB replicated" % world,
                        "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no explicit flush" % (n * L_READ / 1e9),
                        "synthetic_genomes": bool(g["synthetic_genomes"]), "db_build_s": t_db, "db_broadcast_ms": bcast_ms,
                        "numa_node_rank0": numa},

@@ -64,6 +64,8 @@ struct bns_b200_ctx {
     u64 *d_slots = nullptr;
     u64 n_buckets = 0, n_keys = 0, n_displaced = 0, n_overflowed = 0;
     u32 bucket_bits = 0, max_disp = 0, flag_count = 1;
+    u32 layout = LAYOUT_HASH, fmt_bits = 0, table_k = 0, disp_bits = DISP_BITS;
+    bool no_minimizer = false;        // a LAYOUT_MINIMIZER build of this key set failed (skewed minimizers): use LAYOUT_HASH
     std::vector<u32> values;          // sorted distinct DB values (value id -> taxid)
     u32 *d_values = nullptr;
     // taxonomy
@@ -197,11 +199,45 @@ void free_table(bns_b200_ctx *ctx) {
 
 u32 bits_for(u64 n) { u32 b = 0; while((1ull << b) < n) ++b; return b; }
 
-int alloc_table(bns_b200_ctx *ctx, u32 b) {
+// LAYOUT_MINIMIZER (bns_device.cuh) is OPT-IN for now: BNS_B200_LAYOUT=minimizer. It needs room in the slot for the longer
+// remainder -- 23 <= k <= 31, fmt_bits = loc_fmt_bits(k, b) in [value bits + displacement bits + 1, 28] -- and a key set
+// without heavily repeated 16-mers (a build that finds no room is redone in the hash layout). Measured on the 2^28-key
+// stress table: DRAM traffic per read 5.7x lower, throughput 0.99x (1 key/bucket) to 1.23x (0.5
+// keys/bucket) of the hash layout: the probe rounds for keys that overflow their line are instruction-bound.
+bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
+    const char *e = getenv("BNS_B200_LAYOUT");
+    if(ctx->no_minimizer || (e && !strcmp(e, "hash"))) return false;
+    const u32 k = ctx->cfg.k;
+    if(k < 23 || k > 31 || b < 8 || b > 32) return false;
+    if(b - 2 > LOC_MB) return false;
+    const int fmt = (int)loc_fmt_bits(k, b);
+    const u32 vb = bits_for(std::max<u32>((u32)ctx->values.size(), 2));
+    if(fmt > 28 || fmt < (int)(vb + DISP_BITS_LOC + 1)) return false;
+    return e && !strcmp(e, "minimizer");
+}
+TableFmt table_fmt(const bns_b200_ctx *ctx) {
+    TableFmt f;
+    f.b = ctx->bucket_bits; f.fmt_bits = ctx->fmt_bits; f.F = ctx->flag_count; f.layout = ctx->layout; f.kt = ctx->table_k;
+    f.disp_bits = ctx->disp_bits;
+    return f;
+}
+TableFmt fmt_for(const bns_b200_ctx *ctx, u32 b, bool minimizer) {
+    TableFmt f;
+    f.b = b; f.layout = minimizer ? LAYOUT_MINIMIZER : LAYOUT_HASH; f.kt = ctx->cfg.k;
+    f.fmt_bits = minimizer ? loc_fmt_bits(ctx->cfg.k, b) : b;
+    f.disp_bits = minimizer ? DISP_BITS_LOC : DISP_BITS;
+    f.F = flag_count_for(f.fmt_bits, f.disp_bits, (u32)ctx->values.size());
+    return f;
+}
+void adopt_fmt(bns_b200_ctx *ctx, const TableFmt &f) {
+    ctx->bucket_bits = f.b; ctx->fmt_bits = f.fmt_bits; ctx->flag_count = f.F; ctx->layout = f.layout; ctx->table_k = f.kt;
+    ctx->disp_bits = f.disp_bits;
+    ctx->n_buckets = 1ull << f.b;
+}
+
+int alloc_table(bns_b200_ctx *ctx, u32 b, int force_layout = -1) {
     if(b > 32) return ctx->fail(BNS_E_NOMEM, "table would need 2^%u buckets", b);
-    ctx->bucket_bits = b;
-    ctx->flag_count = flag_count_for(b, (u32)ctx->values.size());
-    ctx->n_buckets = 1ull << b;
+    adopt_fmt(ctx, fmt_for(ctx, b, force_layout >= 0 ? force_layout == (int)LAYOUT_MINIMIZER : want_minimizer_layout(ctx, b)));
     CK(cudaMalloc((void **)&ctx->d_slots, ctx->n_buckets * 32));
     CK(cudaMemsetAsync(ctx->d_slots, 0xff, ctx->n_buckets * 32, ctx->slots[0].st));
     return BNS_OK;
@@ -233,7 +269,7 @@ int upload_values(bns_b200_ctx *ctx) {
 int refresh_table_stats(bns_b200_ctx *ctx) {
     cudaStream_t st = ctx->slots[0].st;
     CK(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
-    CK(launch_table_stats(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_counters + 2));
+    CK(launch_table_stats(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_counters + 2));
     ++ctx->stats.kernel_launches;
     unsigned long long h[3];
     CK(cudaMemcpyAsync(h, ctx->d_counters + 2, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -266,7 +302,7 @@ int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
             if(!n) break;
             cudaMemcpyAsync(d_keys + buf * CH, h_keys + buf * CH, n * sizeof(u64), cudaMemcpyHostToDevice, st);
             cudaMemcpyAsync(d_vals + buf * CH, h_vals + buf * CH, n * sizeof(u32), cudaMemcpyHostToDevice, st);
-            cudaError_t e = launch_insert(st, ctx->d_slots, ctx->bucket_bits, ctx->flag_count, d_keys + buf * CH, d_vals + buf * CH, n,
+            cudaError_t e = launch_insert(st, ctx->d_slots, table_fmt(ctx), d_keys + buf * CH, d_vals + buf * CH, n,
                                           ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5);
             ++ctx->stats.kernel_launches;
             ctx->stats.h2d_bytes += n * 12;
@@ -356,7 +392,8 @@ TableView table_view(const bns_b200_ctx *ctx) {
     TableView T;
     T.slots = ctx->d_slots;
     T.bucket_bits = ctx->bucket_bits;
-    T.tag_shift = ctx->bucket_bits - DISP_BITS;
+    T.fmt = table_fmt(ctx);
+    T.tag_shift = ctx->fmt_bits - ctx->disp_bits;
     T.flag_shift = T.tag_shift - ctx->flag_count;
     T.flag_mask = ctx->flag_count - 1;
     T.val_mask = (1u << T.flag_shift) - 1;
@@ -506,6 +543,7 @@ uint64_t bns_b200_encode_bound(const bns_b200_t *ctx, uint64_t len) {
 int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, const uint32_t *flags, uint64_t n_buckets) {
     if(!ctx || (n_buckets && (!keys || !vals || !flags))) return ctx ? ctx->fail(BNS_E_INVAL, "null khash arrays") : BNS_E_INVAL;
     CK(cudaSetDevice(ctx->device));
+    ctx->no_minimizer = false;
     auto occupied = [&](u64 i) { return ((flags[i >> 4] >> ((i & 0xfu) << 1)) & 3u) == 0; };   // !__ac_iseither, khash64.h:171
     u64 n_keys = 0;
     std::vector<u32> values;
@@ -549,13 +587,16 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
         }, st);
         if(rc != BNS_OK) return rc;
         if(st[0] == 0) return finish_table(ctx, st);
-        // some key found no room within MAX_DISP buckets of home: grow and rebuild
+        // some key found no room within MAX_DISP buckets of home: grow and rebuild (a minimizer-layout build that fails --
+        // skewed minimizers -- is redone in the hash layout at the same size first)
+        if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
 
 int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *vals, uint64_t n) {
     if(!ctx || (n && (!keys || !vals))) return ctx ? ctx->fail(BNS_E_INVAL, "null key/value arrays") : BNS_E_INVAL;
     CK(cudaSetDevice(ctx->device));
+    ctx->no_minimizer = false;
     std::vector<u32> values(vals, vals + n);
     std::sort(values.begin(), values.end());
     values.erase(std::unique(values.begin(), values.end()), values.end());
@@ -576,6 +617,7 @@ int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
         }, st);
         if(rc != BNS_OK) return rc;
         if(st[0] == 0) return finish_table(ctx, st);
+        if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
 
@@ -583,6 +625,7 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
                                const uint32_t *values, uint32_t n_values) {
     if(!ctx || !values || !n_values || (n && (!d_keys || !d_vals))) return ctx ? ctx->fail(BNS_E_INVAL, "bad arguments") : BNS_E_INVAL;
     CK(cudaSetDevice(ctx->device));
+    ctx->no_minimizer = false;
     std::vector<u32> vs(values, values + n_values);
     std::sort(vs.begin(), vs.end());
     vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
@@ -596,7 +639,7 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         CK(cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), st));
         const u64 CH = 1ull << 28;
         for(u64 off = 0; off < n; off += CH) {
-            CK(launch_insert(st, ctx->d_slots, b, ctx->flag_count, (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
+            CK(launch_insert(st, ctx->d_slots, table_fmt(ctx), (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
                              ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5));
             ++ctx->stats.kernel_launches;
         }
@@ -604,6 +647,7 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         CK(cudaMemcpyAsync(h, ctx->d_counters + 5, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if(h[0] == 0) return finish_table(ctx, h);
+        if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
 
@@ -614,7 +658,9 @@ int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info) {
     info->n_buckets = ctx->n_buckets;
     info->bytes = ctx->n_buckets * 32;
     info->bucket_bits = ctx->bucket_bits;
-    info->val_bits = ctx->bucket_bits ? ctx->bucket_bits - DISP_BITS - ctx->flag_count : 0;
+    info->val_bits = ctx->bucket_bits ? ctx->fmt_bits - ctx->disp_bits - ctx->flag_count : 0;
+    info->layout = ctx->layout;
+    info->disp_bits = ctx->disp_bits;
     info->n_values = (u32)ctx->values.size();
     info->max_disp = ctx->max_disp;
     info->n_displaced = ctx->n_displaced;
@@ -709,7 +755,7 @@ int bns_b200_build_begin(bns_b200_t *ctx, uint64_t max_kmers, const uint32_t *ta
     free_table(ctx);
     ctx->values = values;
     int rc = upload_values(ctx);
-    if(rc == BNS_OK) rc = alloc_table(ctx, choose_bits(max_kmers, (u32)values.size()));
+    if(rc == BNS_OK) rc = alloc_table(ctx, choose_bits(max_kmers, (u32)values.size()), (int)LAYOUT_HASH);
     if(rc == BNS_OK) rc = finalize_taxonomy(ctx);
     if(rc != BNS_OK) return rc;
     CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->slots[0].st));
@@ -750,7 +796,7 @@ int bns_b200_build_add_genome(bns_b200_t *ctx, const char *bases, const uint64_t
     CK(cudaMemcpyAsync(s.d_offsets, se.data(), se.size() * 8, cudaMemcpyHostToDevice, s.st));
     const size_t smem = stream_smem_bytes(ctx->ring_cap, false);
     CK(launch_build(ctx->enc, grid_for(ctx, npieces, 4), smem, s.st, s.d_bases - offsets[0], s.d_offsets, npieces, offsets[n_records],
-                    ctx->d_slots, ctx->bucket_bits, ctx->flag_count, vid, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 8,
+                    ctx->d_slots, table_fmt(ctx), vid, tax_view(ctx), ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 8,
                     ctx->ring_cap));
     ++ctx->stats.kernel_launches;
     ctx->stats.h2d_bytes += nb + se.size() * 8;
@@ -771,9 +817,15 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
     ctx->tax_ready = true;
     int rc = refresh_table_stats(ctx);
     if(rc != BNS_OK) return rc;
-    // The table was sized for the caller's bound; minimised sets are far smaller. Re-home the entries into a table of the
-    // right size (device to device) so that a small database stays L2-resident.
-    for(u32 want = choose_bits(ctx->n_keys, (u32)ctx->values.size()); want < ctx->bucket_bits; ++want) {
+    // The table was sized for the caller's bound and built in the hash layout; minimised sets are far smaller. Re-home the
+    // entries (device to device) into a table of the right size -- so that a small database stays L2-resident -- and of the
+    // layout that size calls for (a minimizer-layout attempt that finds no room is redone in the hash layout).
+    ctx->no_minimizer = false;
+    u32 want = std::min(choose_bits(ctx->n_keys, (u32)ctx->values.size()), ctx->bucket_bits);
+    while(want <= ctx->bucket_bits) {
+        const bool mini = want_minimizer_layout(ctx, want);
+        if(want == ctx->bucket_bits && !mini) break;                     // already there
+        const TableFmt nf = fmt_for(ctx, want, mini);
         cudaStream_t st = ctx->slots[0].st;
         const u64 n = ctx->n_keys;
         u64 *dk = nullptr, *new_slots = nullptr;
@@ -783,20 +835,22 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         CK(cudaMalloc((void **)&new_slots, (1ull << want) * 32));
         CK(cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st));
         CK(cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st));
-        const u32 want_flags = flag_count_for(want, (u32)ctx->values.size());
-        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_values, dk, dv, n, ctx->d_counters + 12));
-        CK(launch_insert(st, new_slots, want, want_flags, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
+        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, n, ctx->d_counters + 12));
+        CK(launch_insert(st, new_slots, nf, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
         ctx->stats.kernel_launches += 2;
         unsigned long long h2[3];
         CK(cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaFree(dk); cudaFree(dv);
-        if(h2[0] || h2[2]) { cudaFree(new_slots); continue; }          // no room at this size: try one bit more
+        if(h2[0] || h2[2]) {                                              // no room
+            cudaFree(new_slots);
+            if(mini) ctx->no_minimizer = true;                            // same size, hash layout
+            else ++want;
+            continue;
+        }
         cudaFree(ctx->d_slots);
         ctx->d_slots = new_slots;
-        ctx->bucket_bits = want;
-        ctx->flag_count = want_flags;
-        ctx->n_buckets = 1ull << want;
+        adopt_fmt(ctx, nf);
         ctx->n_displaced = h2[1];
         return refresh_table_stats(ctx);
     }
@@ -815,7 +869,7 @@ int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out,
     CK(cudaMalloc((void **)&dk, std::max<u64>(ctx->n_keys, 1) * 8));
     CK(cudaMalloc((void **)&dv, std::max<u64>(ctx->n_keys, 1) * 4));
     CK(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st));
-    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, ctx->bucket_bits, ctx->flag_count, ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
+    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
     ++ctx->stats.kernel_launches;
     CK(cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st));
@@ -906,6 +960,10 @@ int bns_b200_db_export_header(const bns_b200_t *ctx_, bns_b200_db_header *hdr) {
     hdr->words[7] = ctx->n_overflowed;
     hdr->words[8] = ctx->max_disp;
     hdr->words[9] = ctx->flag_count;
+    hdr->words[10] = ctx->layout;
+    hdr->words[11] = ctx->fmt_bits;
+    hdr->words[12] = ctx->table_k;
+    hdr->words[13] = ctx->disp_bits;
     return BNS_OK;
 }
 
@@ -921,9 +979,14 @@ int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr
     ctx->node_of_one = (u32)hdr->words[4];
     ctx->n_keys = hdr->words[5]; ctx->n_displaced = hdr->words[6]; ctx->n_overflowed = hdr->words[7];
     ctx->max_disp = (u32)hdr->words[8];
-    int rc = alloc_table(ctx, (u32)hdr->words[1]);
+    int rc = alloc_table(ctx, (u32)hdr->words[1], (int)hdr->words[10]);
     if(rc != BNS_OK) return rc;
-    if(ctx->flag_count != (u32)hdr->words[9]) return ctx->fail(BNS_E_INVAL, "database header: overflow flag count mismatch");
+    // the slot format is the sender's (this context may be configured for another k)
+    ctx->fmt_bits = (u32)hdr->words[11]; ctx->table_k = (u32)hdr->words[12];
+    ctx->disp_bits = hdr->words[13] ? (u32)hdr->words[13] : (u32)DISP_BITS;
+    ctx->flag_count = (u32)hdr->words[9];
+    if(!ctx->flag_count || (ctx->flag_count & (ctx->flag_count - 1)) || ctx->fmt_bits < ctx->disp_bits + ctx->flag_count)
+        return ctx->fail(BNS_E_INVAL, "database header: bad slot format");
     CK(cudaMalloc((void **)&ctx->d_values, std::max<size_t>(ctx->values.size(), 1) * sizeof(u32)));
     CK(cudaMalloc((void **)&ctx->d_val_info, std::max<size_t>(ctx->values.size(), 1) * sizeof(uint4)));
     CK(cudaMalloc((void **)&ctx->d_node_info, std::max<u32>(ctx->n_nodes, 1) * sizeof(uint4)));
@@ -1021,7 +1084,7 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     // Fully asynchronous: nothing is read back. The total base count (offsets[n_reads]) lives on the device; the generic
     // kernel, which bounds its staging loads with it, reads it there (sentinel ~0), the lean kernel does not need it.
     const u64 total_bases = ~0ull;
-    const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
+    const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
     Slot &s0 = ctx->slots[0];
     if(pl.lean && pl.lean_mode != LEAN_U) {
         rc = ensure(s0.d_defer, s0.cap_defer, n_rec);
@@ -1079,7 +1142,7 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
             rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
             if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
         }
-        const ClassifyPlan pl = plan_classify(ctx->enc, ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
+        const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
                                                n_hit_out || n_missing_out);
         if(rc == BNS_OK && pl.lean && pl.lean_mode != LEAN_U) rc = ensure(s.d_defer, s.cap_defer, nq);
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");

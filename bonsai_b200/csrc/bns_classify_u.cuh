@@ -36,23 +36,23 @@ __device__ __forceinline__ void ld_bucket8(const void *p, u32 (&w)[8]) {
 
 struct ProbeConst {                          // launch-uniform pieces of the slot format (bns_insert_kernel)
     const char *slots;
-    u32 b, idx_shift;                        // bucket = h.hi >> idx_shift
+    u32 b, idx_shift;                        // bucket = h.hi >> idx_shift (LAYOUT_HASH)
+    u32 tag_shift, fmt_bits, max_disp, layout;
     u32 hm;                                  // bits of the low word that belong to {remainder, disp}
     u32 flags_all;                           // the overflow flags of slot 0 (all set = no key homed here was displaced)
     u32 flag_shift, flag_mask;               // a key's flag: bit flag_shift + (hl & flag_mask)
     u32 val_mask;
 };
 
-// buckets after the home bucket for ONE key (rare). Returns the low word of the matching slot or ~tl ("no match").
-__device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 hl, u32 hh) {
+// buckets after the home bucket for ONE key (rare). (th, tl0): the left-aligned remainder. Returns the low word of the
+// matching slot or ~tl0 ("no match").
+__device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 home, u32 th, u32 tl0) {
     const u32 b = Pc.b;
-    const u32 home = hh >> Pc.idx_shift, bmask = (b == 32) ? ~0u : ((1u << b) - 1);
-    const u32 th = __funnelshift_lc(hl, hh, b), tl0 = __funnelshift_lc(0u, hl, b);
-    const u32 tag_shift = b - DISP_BITS;
-    for(u32 d = 1; d <= (u32)MAX_DISP; ++d) {
+    const u32 bmask = (b == 32) ? ~0u : ((1u << b) - 1);
+    for(u32 d = 1; d <= Pc.max_disp; ++d) {
         u32 w[8];
-        ld_bucket8(Pc.slots + ((u64)((home + d) & bmask) << 5), w);
-        const u32 tl = tl0 | (d << tag_shift);
+        ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, home, d, bmask) << 5), w);
+        const u32 tl = tl0 | (d << Pc.tag_shift);
 #pragma unroll
         for(int j = 0; j < 4; ++j)
             if(w[2 * j + 1] == th && ((w[2 * j] ^ tl) & Pc.hm) == 0) return w[2 * j];
@@ -193,7 +193,8 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
 // encoder.h:283) are appended to defer_idx and done by the generic stream kernel right after this one.
 // KEY (windowed modes): how a window element is ordered -- LEAN_KEY_PAIR (score, k-mer) in full, LEAN_KEY_LEX the Lex score
 // alone, LEAN_KEY_ELEM the k-mer alone (scores non-decreasing in the k-mer); chosen by pick_lean().
-template <int MODE, bool CANON, int KT, bool COUNTS, int KEY>
+// LOC: the table is in LAYOUT_MINIMIZER (bns_device.cuh): bucket and remainder come from loc_encode instead of mix64.
+template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
@@ -219,6 +220,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     Pc.b = T.bucket_bits;
     Pc.idx_shift = 32 - T.bucket_bits;
     Pc.hm = ~0u << T.tag_shift;
+    Pc.tag_shift = T.tag_shift; Pc.fmt_bits = T.fmt.fmt_bits; Pc.max_disp = T.fmt.max_disp(); Pc.layout = T.fmt.layout;
     Pc.flags_all = ((1u << T.tag_shift) - 1) & ~T.val_mask;
     Pc.flag_shift = T.flag_shift; Pc.flag_mask = T.flag_mask;
     Pc.val_mask = T.val_mask;
@@ -360,6 +362,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         R2 = ~(((R2 >> 1) & 0x55555555u) | ((R2 & 0x55555555u) << 1));
                     }
                     u32 xls[PPL], xhs[PPL];
+                    u32 fwdm = 0xfu;                                   // bit i: k-mer i is used as read (not reverse-complemented)
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
                         u32 xl, xh;                                                          // forward k-mer: window bits [2i, 2i+2k)
@@ -377,6 +380,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             const u64 f64 = ((u64)xh << 32) | xl, r64 = ((u64)rh << 32) | rl;
                             const bool lt = f64 < r64;
                             xl = lt ? xl : rl; xh = lt ? xh : rh;
+                            if(LOC && !lt) fwdm &= ~(1u << i);
                         }
                         xls[i] = xl; xhs[i] = xh;
                     }
@@ -441,28 +445,88 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         }
                         if(COUNTS) n_emit += __reduce_add_sync(FULL, __popc(mask));
                     }
-                    u32 hl[PPL], hh[PPL], w[PPL][8];
+                    // (bucket, left-aligned remainder) of the four keys. LAYOUT_HASH carries mix64 as (hl, hh) and derives
+                    // bucket and tag words from it; LAYOUT_MINIMIZER carries the tag words in (hl, hh) and the bucket in hb.
+                    u32 hl[PPL], hh[PPL], hb[PPL], w[PPL][8];
+                    // LAYOUT_MINIMIZER, all four k-mers of every lane at once (records of at most 120 k-mers per tile: lanes 0..29
+                    // own k-mers, and lane l's 19 16-mers come from lanes l..l+2): each lane mixes the canonical 16-mers at
+                    // offsets 0..3 and 8..11 of its window, two SHFL.DOWN steps bring in the other twelve, and the minimum of
+                    // (27-bit mixed value : position) over each k-mer's 16 positions is a chain of 32-bit VIMNMX.
+                    const bool loc_fast = LOC && MODE == LEAN_U && KT == 31 && left <= 120u;   // the offsets below are those of k = 31
+                    if(loc_fast) {
+                        u32 key[19];                                   // mixed canonical 16-mers at window offsets 0..18
+#pragma unroll
+                        for(int i = 0; i < 4; ++i) {
+                            const u32 fa = __funnelshift_l(B_, A, 2 * i), fb = __funnelshift_l(B_, A, 16 + 2 * i);
+                            key[i] = nmix(min(fa, rc16(fa)), LOC_MB) >> 5;
+                            key[8 + i] = nmix(min(fb, rc16(fb)), LOC_MB) >> 5;
+                        }
+#pragma unroll
+                        for(int i = 0; i < 4; ++i) {
+                            key[4 + i] = __shfl_down_sync(FULL, key[i], 1);
+                            key[12 + i] = __shfl_down_sync(FULL, key[8 + i], 1);
+                            if(i < 3) key[16 + i] = __shfl_down_sync(FULL, key[8 + i], 2);
+                        }
+#pragma unroll
+                        for(int j = 0; j < 19; ++j) key[j] = (key[j] << 5) | (u32)j;         // leftmost wins ties; ^31: rightmost
+                        u32 coreL = key[3], coreR = key[3] ^ 31u;
+#pragma unroll
+                        for(int j = 4; j <= 15; ++j) { coreL = min(coreL, key[j]); coreR = min(coreR, key[j] ^ 31u); }
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) {
+                            u32 mL = coreL, mR = coreR;
+#pragma unroll
+                            for(int j = 0; j < 19; ++j)
+                                if(j >= i && j <= i + 15 && (j < 3 || j > 15)) { mL = min(mL, key[j]); mR = min(mR, key[j] ^ 31u); }
+                            // the k-mer's canonical string reads left to right when it is the read's strand, else right to left
+                            const bool fw = (fwdm >> i) & 1u;
+                            const u32 js = fw ? (mL & 31u) : (31u - (mR & 31u));             // winning window offset, 0..18
+                            const u32 bo2 = 2 * js;
+                            const u32 f16 = __funnelshift_l(bo2 < 32 ? B_ : C, bo2 < 32 ? A : B_, bo2 & 31u);
+                            const u32 r16 = rc16(f16), mh = nmix(min(f16, r16), LOC_MB);
+                            const u32 pr = js - (u32)i;                                      // position in the read's k-mer
+                            const TableHash t = loc_pack(((u64)xhs[i] << 32) | xls[i], k, Pc.b, mh, fw ? pr : (k - LOC_L) - pr,
+                                                         fw ? (r16 < f16) : (f16 < r16));
+                            hb[i] = (u32)t.home; hh[i] = (u32)(t.tag >> 32); hl[i] = (u32)t.tag;
+                            ld_bucket8(Pc.slots + ((u64)hb[i] << 5), w[i]);
+                        }
+                    } else {
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
                         const u32 xl = xls[i], xh = xhs[i];
-                        // mix64 (bns_device.cuh) on 32-bit halves
-                        u64 x = ((u64)xh << 32) | (xl ^ xh);
-                        x *= 0xd6e8feb86659fd93ull;
-                        x ^= x >> 32;
-                        x *= 0xd6e8feb86659fd93ull;
-                        hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
-                        ld_bucket8(Pc.slots + ((u64)(hh[i] >> Pc.idx_shift) << 5), w[i]);
+                        if(LOC) {
+                            const TableHash t = loc_encode(((u64)xh << 32) | xl, k, Pc.b);
+                            hb[i] = (u32)t.home; hh[i] = (u32)(t.tag >> 32); hl[i] = (u32)t.tag;
+                        } else {
+                            // mix64 (bns_device.cuh) on 32-bit halves
+                            u64 x = ((u64)xh << 32) | (xl ^ xh);
+                            x *= 0xd6e8feb86659fd93ull;
+                            x ^= x >> 32;
+                            x *= 0xd6e8feb86659fd93ull;
+                            hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
+                            hb[i] = hh[i] >> Pc.idx_shift;
+                        }
+                        ld_bucket8(Pc.slots + ((u64)hb[i] << 5), w[i]);
                     }
-                    // ---- match: first slot whose high word equals the tag's, verified on the low word ------------
+                    }
+                    // ---- match: first slot whose high word equals the tag's, verified on the low word (LAYOUT_HASH keeps
+                    // upper words unique within a bucket; LAYOUT_MINIMIZER compares every slot in full) ----------------
                     u32 cand[PPL], nok = 0;                            // nok bit i: k-mer i is not in its home bucket
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
-                        const u32 th = __funnelshift_lc(hl[i], hh[i], Pc.b), tl = __funnelshift_lc(0u, hl[i], Pc.b);
+                        const u32 th = LOC ? hh[i] : __funnelshift_lc(hl[i], hh[i], Pc.b);
+                        const u32 tl = LOC ? hl[i] : __funnelshift_lc(0u, hl[i], Pc.b);
                         u32 c = ~tl;
-                        c = w[i][7] == th ? w[i][6] : c;
-                        c = w[i][5] == th ? w[i][4] : c;
-                        c = w[i][3] == th ? w[i][2] : c;
-                        c = w[i][1] == th ? w[i][0] : c;                                       // slots fill in order: first match wins
+                        if(LOC) {
+#pragma unroll
+                            for(int j = 3; j >= 0; --j)
+                                if((((w[i][2 * j] ^ tl) & Pc.hm) | (w[i][2 * j + 1] ^ th)) == 0) c = w[i][2 * j];
+                        } else {
+                            c = w[i][7] == th ? w[i][6] : c;
+                            c = w[i][5] == th ? w[i][4] : c;
+                            c = w[i][3] == th ? w[i][2] : c;
+                            c = w[i][1] == th ? w[i][0] : c;                                   // slots fill in order: first match wins
+                        }
                         cand[i] = c;
                         nok += min((c ^ tl) & Pc.hm, 1u) << i;
                     }
@@ -471,16 +535,43 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     if(__any_sync(FULL, ((w[0][0] & w[1][0] & w[2][0] & w[3][0]) & Pc.flags_all) != Pc.flags_all)) {
                         u32 more = 0;
 #pragma unroll
-                        for(int i = 0; i < PPL; ++i) if(!((w[i][0] >> (Pc.flag_shift + (hl[i] & Pc.flag_mask))) & 1u)) more |= 1u << i;
+                        for(int i = 0; i < PPL; ++i) {
+                            const u32 fsel = LOC ? (hl[i] >> Pc.fmt_bits) : hl[i];
+                            if(!((w[i][0] >> (Pc.flag_shift + (fsel & Pc.flag_mask))) & 1u)) more |= 1u << i;
+                        }
                         more &= nok & mask;
+                        if(LOC) {
+                            // LAYOUT_MINIMIZER fills lines in bursts (whole minimizer runs), displaced keys are common and sit
+                            // a few buckets on: all pending keys of the warp step through their probe sequences together,
+                            // four loads per lane in flight, instead of one key at a time.
+                            const u32 bmask = (Pc.b == 32) ? ~0u : ((1u << Pc.b) - 1);
+                            for(u32 d = 1; d <= Pc.max_disp && __any_sync(FULL, more != 0); ++d) {
+#pragma unroll
+                                for(int i = 0; i < PPL; ++i)
+                                    if(more >> i & 1u) ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, hb[i], d, bmask) << 5), w[i]);
+#pragma unroll
+                                for(int i = 0; i < PPL; ++i)
+                                    if(more >> i & 1u) {
+                                        const u32 tl = hl[i] | (d << Pc.tag_shift);
+                                        u32 c = ~hl[i];
+#pragma unroll
+                                        for(int j = 3; j >= 0; --j)
+                                            if((((w[i][2 * j] ^ tl) & Pc.hm) | (w[i][2 * j + 1] ^ hh[i])) == 0) c = w[i][2 * j];
+                                        if(c != ~hl[i]) { cand[i] = c; nok &= ~(1u << i); more &= ~(1u << i); }
+                                        else if((w[i][6] & w[i][7]) == ~0u) more &= ~(1u << i);   // a bucket with a free slot ends the run
+                                    }
+                            }
+                        } else
                         while(__any_sync(FULL, more != 0)) {
                             if(more) {
                                 const u32 i = __ffs(more) - 1;
                                 more &= more - 1;
                                 const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
                                 const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
-                                const u32 c = probe_displaced32(Pc, l, h);
-                                if(c != ~__funnelshift_lc(0u, l, Pc.b)) {
+                                const u32 hm = i == 0 ? hb[0] : i == 1 ? hb[1] : i == 2 ? hb[2] : hb[3];
+                                const u32 th = LOC ? h : __funnelshift_lc(l, h, Pc.b), tl0 = LOC ? l : __funnelshift_lc(0u, l, Pc.b);
+                                const u32 c = probe_displaced32(Pc, hm, th, tl0);
+                                if(c != ~tl0) {
                                     nok &= ~(1u << i);
                                     if(i == 0) cand[0] = c; else if(i == 1) cand[1] = c; else if(i == 2) cand[2] = c; else cand[3] = c;
                                 }

@@ -36,8 +36,8 @@ constexpr int TILE = 128;        // k-mer positions per warp tile (4 per lane, l
 constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
 constexpr int AGG_CAP = 256;     // distinct taxa tracked per record in shared memory (covers any read up to k+255 bases)
-constexpr int DISP_BITS = 4;     // slot displacement field; disp == 2^DISP_BITS - 1 is reserved for the empty slot
-constexpr int MAX_DISP = (1 << DISP_BITS) - 2;
+constexpr int DISP_BITS = 4;     // slot displacement field of LAYOUT_HASH; disp == 2^bits - 1 is reserved for the empty slot
+constexpr int DISP_BITS_LOC = 7; // LAYOUT_MINIMIZER: lines fill unevenly (whole minimizer runs land in one), longer runs of full buckets
 
 struct EncParams {
     u32 k, c, W;                 // W = w_ - c_ + 1  (QueueMap size, encoder.h:142)
@@ -53,24 +53,49 @@ struct EncParams {
     double plogp[33];            // n/k * log(n/k) evaluated by the HOST libm (entropy.h:44-48)
 };
 
+// How a key becomes (home bucket, remainder). Both are bijections key <-> (bucket, remainder), so hits and misses are exact.
+//   LAYOUT_HASH      bucket = top b bits of mix64(key), remainder = the other 64-b bits. Consecutive k-mers of a read land
+//                    in unrelated DRAM lines: one line per lookup once the table exceeds L2.
+//   LAYOUT_MINIMIZER (23 <= k <= 31) the 128-byte LINE is chosen by the k-mer's canonical 16-mer minimizer, the 32-byte
+//                    sector inside it by the minimizer's position mod 4; the remainder spells the k-mer relative to its
+//                    minimizer (loc_encode). ~(k-14)/2 consecutive k-mers of a read share a minimizer and so a line:
+//                    the line one lookup brings into L2 serves the next ones.
+enum TableLayout : u32 { LAYOUT_HASH = 0, LAYOUT_MINIMIZER = 1 };
+constexpr u32 LOC_L = 16;        // minimizer length: a k-mer holds k-15 <= 16 of them for k <= 31, so a full run of consecutive
+                                 // k-mers sharing one minimizer fits the 16 slots of a line, four per sector
+constexpr u32 LOC_MB = 2 * LOC_L; // bits of a minimizer
+
+struct TableFmt {
+    u32 b;                       // bucket bits: 2^b buckets of 32 bytes
+    u32 fmt_bits;                // 64 - (bits of the remainder): b for LAYOUT_HASH, loc_fmt_bits(k, b) for LAYOUT_MINIMIZER
+    u32 F;                       // overflow flags per bucket (power of two)
+    u32 layout;
+    u32 kt;                      // k of the keys (LAYOUT_MINIMIZER spells keys as k-mers)
+    u32 disp_bits;               // width of the displacement field
+    __host__ __device__ u32 tag_shift() const { return fmt_bits - disp_bits; }
+    __host__ __device__ u32 flag_shift() const { return fmt_bits - disp_bits - F; }
+    __host__ __device__ u32 max_disp() const { return (1u << disp_bits) - 2u; }
+};
+
 struct TableView {
     const u64 *slots;            // n_buckets * 4 u64
-    u32 bucket_bits;             // b: bucket = h >> (64-b)
-    u32 tag_shift;               // b - DISP_BITS: bits below it are {overflow flags, val}
+    u32 bucket_bits;             // b: 2^b buckets
+    u32 tag_shift;               // fmt_bits - disp_bits: bits below it are {overflow flags, val}
     u32 val_mask;                // (1 << flag_shift) - 1
     u32 n_values;
     u32 flag_shift;              // tag_shift - F: the F overflow flags of slot 0 sit at [flag_shift, tag_shift)
-    u32 flag_mask;               // F - 1 (F is a power of two): a key's flag is bit flag_shift + (low word of mix64 & flag_mask)
+    u32 flag_mask;               // F - 1 (F is a power of two): a key's flag is bit flag_shift + (flag selector & flag_mask)
+    TableFmt fmt;
 };
 
 // Overflow flags. A key that found its home bucket full is stored in a later bucket and CLEARS, in slot 0 of the home
 // bucket, the one of F flag bits its hash selects (an empty slot is all ones and so reads "nothing displaced"). A lookup
 // that misses in the home bucket goes on to the next bucket only if ITS flag is cleared, so a miss costs one sector
 // unless a displaced key shares both its home bucket and its flag. F is what the value field leaves free, at most 8.
-__host__ __device__ inline u32 flag_count_for(u32 b, u32 n_values) {
+__host__ __device__ inline u32 flag_count_for(u32 fmt_bits, u32 disp_bits, u32 n_values) {
     u32 vb = 1;
     while((1u << vb) < n_values) ++vb;
-    const u32 avail = b - DISP_BITS > vb ? b - DISP_BITS - vb : 1u;
+    const u32 avail = fmt_bits - disp_bits > vb ? fmt_bits - disp_bits - vb : 1u;
     return avail >= 8 ? 8u : avail >= 4 ? 4u : avail >= 2 ? 2u : 1u;
 }
 
@@ -130,6 +155,115 @@ __device__ __host__ __forceinline__ u64 unmix64(u64 x) {
     x *= MI;
     x ^= x >> 32;
     return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LAYOUT_MINIMIZER: key <-> (bucket, remainder)
+// ---------------------------------------------------------------------------------------------
+// bijections on n-bit values (odd multiplies and xorshifts by >= n/2 are invertible mod 2^n)
+__host__ __device__ __forceinline__ u32 nmix(u32 x, u32 n) {
+    const u32 m = n >= 32 ? ~0u : ((1u << n) - 1), h = (n + 1) >> 1;
+    x = (x * 0x9e3779b1u) & m; x ^= x >> h;
+    x = (x * 0x85ebca6bu) & m; x ^= x >> h;
+    return x;
+}
+__host__ __device__ __forceinline__ u32 nunmix(u32 x, u32 n) {
+    const u32 m = n >= 32 ? ~0u : ((1u << n) - 1), h = (n + 1) >> 1;
+    x ^= x >> h; x = (x * (u32)inv_odd(0x85ebca6bu)) & m;
+    x ^= x >> h; x = (x * (u32)inv_odd(0x9e3779b1u)) & m;
+    return x;
+}
+// reverse complement of a 16-mer held in 32 bits
+__host__ __device__ __forceinline__ u32 rc16(u32 x) {
+#ifdef __CUDA_ARCH__
+    u32 r = __brev(x);
+#else
+    u32 r = x;
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    r = ((r >> 2) & 0x33333333u) | ((r & 0x33333333u) << 2);
+    r = ((r >> 4) & 0x0f0f0f0fu) | ((r & 0x0f0f0f0fu) << 4);
+    r = ((r >> 8) & 0x00ff00ffu) | ((r & 0x00ff00ffu) << 8);
+    r = (r >> 16) | (r << 16);
+#endif
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);     // bit-reversed pairs back in order
+    return ~r;
+}
+// remainder bits of a LAYOUT_MINIMIZER slot: [minimizer hash below the line bits | position >> 2 | orientation | flank hash]
+__host__ __device__ __forceinline__ u32 loc_rembits(u32 k, u32 b) { return (LOC_MB - (b - 2)) + 2 + 1 + 2 * (k - LOC_L); }
+__host__ __device__ __forceinline__ u32 loc_fmt_bits(u32 k, u32 b) { return 64 - loc_rembits(k, b); }
+struct TableHash { u64 home; u64 tag; u32 fsel; };                // home bucket, left-aligned remainder, overflow-flag selector
+
+// (bucket, remainder) of k-mer s once its minimizer is known: mh = nmix(canonical 16-mer, 32), at position bp of s,
+// bo = the 16-mer stands in s as the reverse complement of its canonical form
+__host__ __device__ __forceinline__ TableHash loc_pack(u64 s, u32 k, u32 b, u32 mh, u32 bp, u32 bo) {
+    const u32 nf = 2 * (k - LOC_L), bl = b - 2;
+    const u32 nr = 2 * (k - LOC_L - bp);                                   // bits right of the minimizer
+    const u64 left = bp ? (s >> (2 * (k - bp))) : 0ull, right = nr ? (s & ((1ull << nr) - 1)) : 0ull;
+    const u32 fm = nmix((u32)((left << nr) | right), nf);
+    // the sector inside the line: the minimizer's position mod 4. The k-mers of one run have consecutive positions, so a run
+    // spreads evenly over the line's four sectors instead of overflowing one of them by chance.
+    const u32 sec = bp & 3u;
+    // the minimum of k-15 hashes is small: its top bits would crowd the keys into a few lines. The line comes from a
+    // second bijection of the winning hash.
+    const u32 li = nmix(mh ^ 0x2545f491u, LOC_MB);
+    const u32 line = li >> (LOC_MB - bl), mrest = bl >= LOC_MB ? 0u : (li & ((1u << (LOC_MB - bl)) - 1));
+    const u64 rem = ((((u64)mrest << 2 | (bp >> 2)) << 1 | bo) << nf) | fm;
+    TableHash t;
+    t.home = ((u64)line << 2) | sec;
+    t.tag = rem << (64 - loc_rembits(k, b));
+    t.fsel = fm;
+    return t;
+}
+// the order of the minimizer: the top 27 bits of the mixed canonical 16-mer (so that value and position sort as one
+// 32-bit word in the classify kernel), LEFTMOST position of the k-mer on ties
+__host__ __device__ inline TableHash loc_encode(u64 s, u32 k, u32 b) {
+    const u32 J = k - LOC_L + 1;
+    u32 best = ~0u, best27 = ~0u, bp = 0, bo = 0;
+    for(u32 p = 0; p < J; ++p) {
+        const u32 f = (u32)(s >> (2 * (k - LOC_L - p)));                     // position 0 = the first (most significant) base
+        const u32 r = rc16(f), c = f < r ? f : r, mh = nmix(c, LOC_MB);
+        if((mh >> 5) < best27) { best27 = mh >> 5; best = mh; bp = p; bo = r < f; }
+    }
+    return loc_pack(s, k, b, best, bp, bo);
+}
+// inverse: home bucket + left-aligned remainder -> key
+__host__ __device__ inline u64 loc_decode(u64 home, u64 tag, u32 k, u32 b) {
+    const u32 nf = 2 * (k - LOC_L), bl = b - 2;
+    const u64 rem = tag >> (64 - loc_rembits(k, b));
+    const u32 fm = (u32)(rem & (nf >= 32 ? 0xffffffffull : ((1ull << nf) - 1)));
+    const u32 bo = (u32)(rem >> nf) & 1u, bp = ((u32)(rem >> (nf + 1)) & 3u) << 2 | ((u32)home & 3u);
+    const u32 mrest = (u32)(rem >> (nf + 3));
+    const u32 li = bl >= LOC_MB ? (u32)(home >> 2) : (((u32)(home >> 2) << (LOC_MB - bl)) | mrest);
+    const u32 mh = nunmix(li, LOC_MB) ^ 0x2545f491u;
+    const u32 c = nunmix(mh, LOC_MB), f = bo ? rc16(c) : c;
+    const u32 fl = nunmix(fm, nf);
+    const u32 nr = 2 * (k - LOC_L - bp);
+    const u64 left = nr >= 32 ? 0ull : ((u64)fl >> nr), right = nr ? ((u64)fl & ((1ull << nr) - 1)) : 0ull;
+    return (((left << LOC_MB) | f) << nr) | right;
+}
+// the d-th bucket of a key's probe sequence: the next buckets (LAYOUT_HASH); the other sectors of the home LINE first, then
+// the following lines (LAYOUT_MINIMIZER: a displaced key stays in the line its minimizer run already brought into L2)
+__host__ __device__ __forceinline__ u64 probe_bucket(u32 layout, u64 home, u32 d, u64 bmask) {
+    if(layout == LAYOUT_MINIMIZER) return (((((home >> 2) + (d >> 2)) << 2) | ((home + d) & 3ull))) & bmask;
+    return (home + d) & bmask;
+}
+// ... and back: the home bucket of an entry found in `bucket` with displacement d
+__host__ __device__ __forceinline__ u64 probe_home(u32 layout, u64 bucket, u32 d, u64 bmask) {
+    if(layout == LAYOUT_MINIMIZER) return (((((bucket >> 2) - (d >> 2)) << 2) | ((bucket - d) & 3ull))) & bmask;
+    return (bucket - d) & bmask;
+}
+// key -> (home bucket, remainder) of either layout. Keys that are not k-mers of the table's k cannot be in a
+// LAYOUT_MINIMIZER table: `possible` is false and the caller reports a miss.
+__host__ __device__ inline TableHash table_hash(const TableFmt &f, u64 key, bool &possible) {
+    possible = true;
+    if(f.layout == LAYOUT_MINIMIZER) {
+        if(f.kt < 32 && (key >> (2 * f.kt)) != 0) { possible = false; key &= (1ull << (2 * f.kt)) - 1; }
+        return loc_encode(key, f.kt, f.b);
+    }
+    const u64 h = mix64(key);
+    TableHash t;
+    t.home = h >> (64 - f.b); t.tag = h << f.b; t.fsel = (u32)h;
+    return t;
 }
 
 __device__ __forceinline__ void ld_bucket(const u64 *p, u64 &a, u64 &b, u64 &c, u64 &d) {

@@ -213,12 +213,12 @@ __device__ __forceinline__ u32 match4(const TableView &T, u64 tag, u64 s0, u64 s
     return (d0 && d1 && d2 && d3) ? VAL_MISS : (v & T.val_mask);
 }
 // buckets after the home bucket (rare: the home bucket overflowed when the table was built)
-__device__ __noinline__ u32 probe_displaced(const TableView T, u64 h) {
+__device__ __noinline__ u32 probe_displaced(const TableView T, u64 home, u64 tag) {
     const u32 b = T.bucket_bits;
-    const u64 bmask = (1ull << b) - 1, home = h >> (64 - b), tag = h << b;
-    for(u32 d = 1; d <= (u32)MAX_DISP; ++d) {
+    const u64 bmask = (1ull << b) - 1;
+    for(u32 d = 1; d <= T.fmt.max_disp(); ++d) {
         u64 a, bb, c, e;
-        ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
+        ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, bmask) << 2), a, bb, c, e);
         const u32 v = match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e);
         if(v != VAL_MISS || e == ~0ull) return v;
     }
@@ -237,24 +237,30 @@ __device__ __forceinline__ u32 match4_home(const TableView &T, u64 tag, u64 s0, 
 // kh_get + kh_val for PPL keys per lane: all home-bucket sectors are requested before any is inspected. Lanes / slots
 // without a live k-mer probe anyway (their result is masked by the caller): no predication, no register init.
 __device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 (&val)[PPL]) {
-    const u32 b = T.bucket_bits;
-    u64 h[PPL], s[PPL][4];
+    TableHash h[PPL];
+    u64 s[PPL][4];
+    u32 imposs = 0;
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
-        h[i] = mix64(x[i]);
-        ld_bucket(T.slots + ((h[i] >> (64 - b)) << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
+        bool possible;
+        h[i] = table_hash(T.fmt, x[i], possible);
+        if(!possible) imposs |= 1u << i;
+        ld_bucket(T.slots + (h[i].home << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
     }
     // The overflow mark is a CLEARED bit in slot 0 of a full home bucket (an empty slot is all ones, so an empty or
     // part-filled bucket reads "no overflow"): a miss costs one sector unless a key homed there was displaced.
     u32 more = 0;
+    const bool exact = T.fmt.layout != LAYOUT_HASH;               // only LAYOUT_HASH keeps upper words unique in a bucket
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
-        val[i] = match4_home(T, h[i] << b, s[i][0], s[i][1], s[i][2], s[i][3]);
-        if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.flag_shift + ((u32)h[i] & T.flag_mask))) & 1u)) more |= 1u << i;
+        val[i] = exact ? match4(T, h[i].tag, s[i][0], s[i][1], s[i][2], s[i][3])
+                       : match4_home(T, h[i].tag, s[i][0], s[i][1], s[i][2], s[i][3]);
+        if(imposs >> i & 1u) val[i] = VAL_MISS;
+        else if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.flag_shift + (h[i].fsel & T.flag_mask))) & 1u)) more |= 1u << i;
     }
-    if(more) {                                                    // rare (~1 % of lookups at <= 1.25 entries/bucket)
+    if(more) {                                                    // rare
 #pragma unroll
-        for(int i = 0; i < PPL; ++i) if(more >> i & 1u) val[i] = probe_displaced(T, h[i]);
+        for(int i = 0; i < PPL; ++i) if(more >> i & 1u) val[i] = probe_displaced(T, h[i].home, h[i].tag);
     }
 }
 
@@ -411,6 +417,7 @@ __device__ __forceinline__ u32 value_id(const u32 *__restrict__ values, u32 n, u
 struct BuildSink {
     u64 *slots;
     u32 b, tag_shift, val_mask, flag_shift, flag_mask;
+    TableFmt fmt;
     u32 vid;                           // value id of the genome being added
     const uint4 *val_info, *node_info; // Euler intervals: {tin, tout, node, taxid} / {tin, tout, parent node, taxid}
     const u32 *values;
@@ -431,9 +438,12 @@ struct BuildSink {
         return value_id(values, n_values, node_info[a].w);
     }
     __device__ __forceinline__ void insert(u64 key) {
-        const u64 h = mix64(key), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
-        for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
-            u64 *bk = slots + (((home + d) & bmask) << 2);
+        bool possible;
+        const TableHash th = table_hash(fmt, key, possible);
+        if(!possible) { ++n_fail; return; }
+        const u64 home = th.home, bmask = (1ull << b) - 1, tag = th.tag;
+        for(u32 d = 0; d <= fmt.max_disp(); ++d) {
+            u64 *bk = slots + (probe_bucket(fmt.layout, home, d, bmask) << 2);
             const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << tag_shift) - 1) & ~(u64)val_mask) | vid;
             for(int s = 0; s < 4; ++s) {
                 u64 cur = bk[s];
@@ -454,9 +464,9 @@ struct BuildSink {
                         cur = prev;                                      // value or overflow mark changed under us: retry
                     }
                 }
-                if((u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant
+                if(fmt.layout == LAYOUT_HASH && (u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant
             }
-            if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + ((u32)h & flag_mask))));
+            if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + (th.fsel & flag_mask))));
         }
         ++n_fail;
     }
@@ -840,7 +850,7 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
 // A key lives in its home bucket (disp 0) or, if that was full, in the first later bucket with room (disp <= 14);
 // the home bucket's slot 0 then gets the key's overflow flag CLEARED (flag_count_for, bns_device.cuh) so that misses
 // stop after one sector otherwise.
-__global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, u32 F, const u64 *__restrict__ keys,
+__global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u64 *__restrict__ keys,
                                   const u32 *__restrict__ vals, u64 n, const u32 *__restrict__ values, u32 n_values,
                                   unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -848,12 +858,15 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, u32 F, const u
     const u64 key = keys[i];
     const u32 vid = value_id(values, n_values, vals[i]);
     if(vid == VAL_MISS) { atomicAdd(&stats[2], 1ull); return; }
-    const u64 h = mix64(key);
-    const u64 home = h >> (64 - b), bmask = (1ull << b) - 1;
-    const u32 tag_shift = b - DISP_BITS, flag_shift = tag_shift - F;
-    const u64 tag = h << b;
-    for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
-        u64 *bk = slots + (((home + d) & bmask) << 2);
+    bool possible;
+    const TableHash th = table_hash(fmt, key, possible);
+    if(!possible) { atomicAdd(&stats[0], 1ull); return; }
+    const u32 b = fmt.b, F = fmt.F;
+    const u64 home = th.home, bmask = (1ull << b) - 1;
+    const u32 tag_shift = fmt.tag_shift(), flag_shift = fmt.flag_shift();
+    const u64 tag = th.tag;
+    for(u32 d = 0; d <= fmt.max_disp(); ++d) {
+        u64 *bk = slots + (probe_bucket(fmt.layout, home, d, bmask) << 2);
         const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << F) - 1) << flag_shift) | vid;
         for(int s = 0; s < 4; ++s) {
             u64 cur = bk[s];
@@ -864,22 +877,22 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, u32 b, u32 F, const u
             if(((cur ^ entry) >> tag_shift) == 0) return;          // same key already present: first value stays
             // invariant for match4_home: upper words are unique within a bucket. A clash (2^-32 per pair) fails the
             // build; the host rebuilds with one more bucket bit, which re-draws every upper word.
-            if((u32)(cur >> 32) == (u32)(entry >> 32)) { atomicAdd(&stats[0], 1ull); return; }
+            if(fmt.layout == LAYOUT_HASH && (u32)(cur >> 32) == (u32)(entry >> 32)) { atomicAdd(&stats[0], 1ull); return; }
         }
-        if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + ((u32)h & (F - 1)))));
+        if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + (th.fsel & (F - 1)))));
     }
     atomicAdd(&stats[0], 1ull);
 }
 
-__global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, u32 F,
+__global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, TableFmt fmt,
                                        unsigned long long *__restrict__ out /* [0] entries [1] ovf buckets [2] max disp */) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_buckets) return;
-    const u32 tag_shift = b - DISP_BITS;
+    const u32 tag_shift = fmt.tag_shift(), F = fmt.F;
     u32 cnt = 0, md = 0;
     for(int s = 0; s < 4; ++s) {
         const u64 v = slots[4 * i + s];
-        if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & ((1u << DISP_BITS) - 1))); }
+        if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & ((1u << fmt.disp_bits) - 1))); }
     }
     if(cnt) atomicAdd(&out[0], (unsigned long long)cnt);
     const u64 flags = ((1ull << F) - 1) << (tag_shift - F);
@@ -891,11 +904,13 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
                                   u32 *__restrict__ vals_out, uint8_t *__restrict__ found_out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    const u64 h = mix64(keys[i]);
+    bool possible;
+    const TableHash h = table_hash(T.fmt, keys[i], possible);
     u64 a, b, c, d;
-    ld_bucket(T.slots + ((h >> (64 - T.bucket_bits)) << 2), a, b, c, d);
-    u32 v = match4_home(T, h << T.bucket_bits, a, b, c, d);
-    if(v == VAL_MISS && !(((u32)a >> (T.flag_shift + ((u32)h & T.flag_mask))) & 1u)) v = probe_displaced(T, h);
+    ld_bucket(T.slots + (h.home << 2), a, b, c, d);
+    u32 v = T.fmt.layout != LAYOUT_HASH ? match4(T, h.tag, a, b, c, d) : match4_home(T, h.tag, a, b, c, d);
+    if(!possible) v = VAL_MISS;
+    else if(v == VAL_MISS && !(((u32)a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) v = probe_displaced(T, h.home, h.tag);
     found_out[i] = v != VAL_MISS;
     vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
 }
@@ -905,13 +920,15 @@ __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u6
     u32 touched = 0;
     if(i < n) {
         const u32 b = T.bucket_bits;
-        const u64 h = mix64(keys[i]), home = h >> (64 - b), bmask = (1ull << b) - 1, tag = h << b;
-        for(u32 d = 0; d <= (u32)MAX_DISP; ++d) {
+        bool possible;
+        const TableHash h = table_hash(T.fmt, keys[i], possible);
+        const u64 home = h.home, bmask = (1ull << b) - 1, tag = h.tag;
+        for(u32 d = 0; d <= T.fmt.max_disp(); ++d) {
             u64 a, bb, c, e;
-            ld_bucket(T.slots + (((home + d) & bmask) << 2), a, bb, c, e);
+            ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, bmask) << 2), a, bb, c, e);
             ++touched;
             if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
-            if(d == 0 ? (((a >> (T.flag_shift + ((u32)h & T.flag_mask))) & 1ull) != 0) : (e == ~0ull)) break;
+            if(d == 0 ? (((a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1ull) != 0) : (e == ~0ull)) break;
         }
     }
     touched = __reduce_add_sync(FULL, touched);
@@ -966,19 +983,21 @@ bns_build_kernel(const __grid_constant__ EncParams P, const char *__restrict__ b
 }
 
 // table -> (key, value) pairs: the home bucket is bucket - disp, the key is unmix64(home : remainder)
-__global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, u32 b, u32 F, const u32 *__restrict__ dict,
+__global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, TableFmt fmt, const u32 *__restrict__ dict,
                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, u64 cap,
                                 unsigned long long *__restrict__ counter) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_buckets * 4) return;
     const u64 v = slots[i];
     if(v == ~0ull) return;
-    const u32 tag_shift = b - DISP_BITS;
-    const u64 bucket = i >> 2, disp = (v >> tag_shift) & ((1u << DISP_BITS) - 1);
-    const u64 home = (bucket - disp) & (n_buckets - 1);
-    const u64 h = (home << (64 - b)) | (v >> b);
+    const u32 tag_shift = fmt.tag_shift(), b = fmt.b;
+    const u64 bucket = i >> 2, disp = (v >> tag_shift) & ((1u << fmt.disp_bits) - 1);
+    const u64 home = probe_home(fmt.layout, bucket, (u32)disp, n_buckets - 1);
+    const u64 rem_mask = ~0ull << fmt.fmt_bits;                    // the remainder, left-aligned
+    const u64 key = fmt.layout == LAYOUT_MINIMIZER ? loc_decode(home, v & rem_mask, fmt.kt, b)
+                                                   : unmix64((home << (64 - b)) | (v >> b));
     const u64 at = atomicAdd(counter, 1ull);
-    if(at < cap) { keys_out[at] = unmix64(h); vals_out[at] = dict[(u32)v & ((1u << (tag_shift - F)) - 1)]; }
+    if(at < cap) { keys_out[at] = key; vals_out[at] = dict[(u32)v & ((1u << fmt.flag_shift()) - 1)]; }
 }
 
 // independent 32-byte loads at uniformly random buckets: the random-access ceiling the lookup is measured against
@@ -1057,14 +1076,15 @@ typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, T
                               unsigned long long *, u32 *, u32 *, unsigned long long *);
 static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
 template <int MODE, bool CANON, bool COUNTS, int KEY>
-static classify_u_fn pick_lean_k(u32 k) {
-    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY>;
+static classify_u_fn pick_lean_k(u32 k, bool loc) {
+    if(loc) return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, true> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, true>;
+    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, false> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, false>;
 }
 template <int MODE, bool CANON>
-static classify_u_fn pick_lean_key(u32 k, int key) {
-    if(key == LEAN_KEY_LEX) return pick_lean_k<MODE, CANON, true, LEAN_KEY_LEX>(k);
-    if(key == LEAN_KEY_ELEM) return pick_lean_k<MODE, CANON, true, LEAN_KEY_ELEM>(k);
-    return pick_lean_k<MODE, CANON, true, LEAN_KEY_PAIR>(k);
+static classify_u_fn pick_lean_key(u32 k, int key, bool loc) {
+    if(key == LEAN_KEY_LEX) return pick_lean_k<MODE, CANON, true, LEAN_KEY_LEX>(k, loc);
+    if(key == LEAN_KEY_ELEM) return pick_lean_k<MODE, CANON, true, LEAN_KEY_ELEM>(k, loc);
+    return pick_lean_k<MODE, CANON, true, LEAN_KEY_PAIR>(k, loc);
 }
 // How the (score, k-mer) pairs of a window can be ordered by one 64-bit word (bit-identical minima):
 //  * Lex: the score is a bijection of the k-mer (ties in score are ties in k-mer).
@@ -1077,21 +1097,24 @@ static int lean_key(const EncParams &P) {
     if(!P.cast_wrap && (P.score_kind == SC_ENT_NOTFULL || (P.score_kind == SC_ENT_ROLL && P.k >= 28))) return LEAN_KEY_ELEM;
     return LEAN_KEY_PAIR;
 }
-static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts) {
-    if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P));
-    if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P)) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P));
-    if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k) : pick_lean_k<LEAN_U, true, false, 0>(P.k);
-    return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k) : pick_lean_k<LEAN_U, false, false, 0>(P.k);
+static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc) {
+    if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P), loc);
+    if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P), loc) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P), loc);
+    if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc);
+    return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, false, false, 0>(P.k, loc);
 }
 
-ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
+ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
     ClassifyPlan pl;
     pl.lean_mode = lean_mode(P, mates, taxa, mate1);
+    // the lean kernel spells LAYOUT_MINIMIZER keys as k-mers of ITS k: a table of another k goes through the generic probe
+    pl.loc = T.fmt.layout == LAYOUT_MINIMIZER;
+    if(pl.loc && T.fmt.kt != P.k) pl.lean_mode = -1;
     pl.lean = pl.lean_mode >= 0;
     pl.counts = counts;
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, counts);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, counts, pl.loc);
         pl.smem = lean_smem();
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1121,7 +1144,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched) {
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
         f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
                                                     counters, status, defer_idx, defer_cnt);
         cudaError_t e = cudaGetLastError();
@@ -1149,10 +1172,11 @@ int encode_occupancy(const EncParams &P, size_t smem) {
     return nb;
 }
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
-                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 F, u32 vid, const TaxView &X, const u32 *values,
+                         u64 n_seqs, u64 total_bases, u64 *slots, const TableFmt &fmt, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap) {
     BuildSink sk;
-    sk.slots = slots; sk.b = b; sk.tag_shift = b - DISP_BITS; sk.flag_shift = sk.tag_shift - F; sk.flag_mask = F - 1;
+    sk.fmt = fmt;
+    sk.slots = slots; sk.b = fmt.b; sk.tag_shift = fmt.tag_shift(); sk.flag_shift = fmt.flag_shift(); sk.flag_mask = fmt.F - 1;
     sk.val_mask = (1u << sk.flag_shift) - 1; sk.vid = vid;
     sk.val_info = X.val_info; sk.node_info = X.node_info; sk.values = values; sk.n_values = n_values;
     sk.node_of_one = X.node_of_one; sk.stats = stats; sk.n_new = sk.n_fail = 0;
@@ -1163,20 +1187,20 @@ cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t
     f<<<grid, WARPS_PER_CTA * 32, smem, st>>>(P, bases, offsets, n_seqs, total_bases, sk, ring_cap);
     return cudaGetLastError();
 }
-cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, const u32 *dict, u64 *keys_out, u32 *vals_out,
+cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, const u32 *dict, u64 *keys_out, u32 *vals_out,
                         u64 cap, unsigned long long *counter) {
     const u64 n = n_buckets * 4;
-    bns_dump_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, F, dict, keys_out, vals_out, cap, counter);
+    bns_dump_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, n_buckets, fmt, dict, keys_out, vals_out, cap, counter);
     return cudaGetLastError();
 }
-cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, u32 F, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, const TableFmt &fmt, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
                           u32 n_values, unsigned long long *stats) {
     if(!n) return cudaSuccess;
-    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, b, F, keys, vals, n, values, n_values, stats);
+    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, fmt, keys, vals, n, values, n_values, stats);
     return cudaGetLastError();
 }
-cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, unsigned long long *out) {
-    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, b, F, out);
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, unsigned long long *out) {
+    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, fmt, out);
     return cudaGetLastError();
 }
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,

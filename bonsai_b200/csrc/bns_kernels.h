@@ -14,12 +14,13 @@ constexpr int WARPS_PER_CTA = 8;
 struct EncParams;
 struct TableView;
 struct TaxView;
+struct TableFmt;
 
 size_t stream_smem_bytes(u32 ring_cap, bool classify);
 enum LeanMode : int { LEAN_U = 0, LEAN_K = 1, LEAN_R = 2 };   // what bns_classify_u_kernel runs as (bns_classify_u.cuh)
 enum LeanKey : int { LEAN_KEY_PAIR = 0, LEAN_KEY_LEX = 1, LEAN_KEY_ELEM = 2 };   // how window elements are ordered
-struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0; };
-ClassifyPlan plan_classify(const EncParams &P, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts);
+struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true, loc = false; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0; };
+ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts);
 int encode_occupancy(const EncParams &P, size_t smem);
 
 cudaError_t launch_encode(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets, u64 n_seqs,
@@ -30,13 +31,13 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
                             u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched);
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
-                         u64 n_seqs, u64 total_bases, u64 *slots, u32 b, u32 F, u32 vid, const TaxView &X, const u32 *values,
+                         u64 n_seqs, u64 total_bases, u64 *slots, const TableFmt &fmt, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap);
-cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, const u32 *dict, u64 *keys_out, u32 *vals_out,
+cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, const u32 *dict, u64 *keys_out, u32 *vals_out,
                         u64 cap, unsigned long long *counter);
-cudaError_t launch_insert(cudaStream_t st, u64 *slots, u32 b, u32 F, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
+cudaError_t launch_insert(cudaStream_t st, u64 *slots, const TableFmt &fmt, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
                           u32 n_values, unsigned long long *stats);
-cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, u32 b, u32 F, unsigned long long *out);
+cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, unsigned long long *out);
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
                           uint8_t *found_out);
 cudaError_t launch_sectors(cudaStream_t st, const TableView &T, const u64 *keys, u64 n, unsigned long long *total);

@@ -69,6 +69,8 @@ typedef struct bns_b200_table_info {
     uint32_t bucket_bits, val_bits, n_values, max_disp;
     uint64_t n_displaced;       /* entries not in their home bucket */
     uint64_t n_overflowed;      /* home buckets with the overflow mark */
+    uint32_t layout;            /* 0 hash (bucket = mix64), 1 minimizer (128-byte line by the k-mer's 15-mer minimizer) */
+    uint32_t disp_bits;         /* width of the slot's displacement field */
 } bns_b200_table_info;
 
 typedef struct bns_b200_stats {

@@ -11,7 +11,7 @@ for spec in "$@"; do
 import json
 try:
     d=json.load(open("gpurun_out/wl_${TAG}_$n.json")); r=d["roofline"]
-    print("[$spec]", "value %.1f"%d["value"], "e2e %.1f"%d["e2e"]["value"], "kernel_ms %.3f"%r["kernel_ms"], "frac %.3f"%r["frac"], "pbar %.4f"%r["sectors_per_lookup"], "tableMB %.0f"%d["config"]["db_table_mb"], "gatherfrac %.3f"%r["frac_of_random_gather"], "uncls", d["n_unclassified"], "match", d["e2e"]["taxids_match_device_path"], d["config"].get("stress_reads_classified_as_expected"))
+    print("[$spec]", d["config"].get("db_layout"), "value %.1f"%d["value"], "e2e %.1f"%d["e2e"]["value"], "kernel_ms %.3f"%r["kernel_ms"], "frac %.3f"%r["frac"], "pbar %.4f"%r["sectors_per_lookup"], "tableMB %.0f"%d["config"]["db_table_mb"], "gatherfrac %.3f"%r["frac_of_random_gather"], "uncls", d["n_unclassified"], "match", d["e2e"]["taxids_match_device_path"], d["config"].get("stress_reads_classified_as_expected"))
 except Exception as e:
     print("[$spec] FAILED", e); print(open("gpurun_out/wl_${TAG}_$n.err").read()[-1500:])
 P
