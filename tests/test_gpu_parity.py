@@ -529,3 +529,71 @@ def test_classify_lean_windowed_vs_oracle(capi, oracle, dbcache, toy_tax, genome
     assert np.array_equal(got_taxon_only, exp[0])
     for a, bb in zip(exp, full[:3]):
         assert np.array_equal(a, bb)
+
+
+def test_minimizer_layout_vs_oracle(capi, oracle, toy_tax, monkeypatch):
+    """The opt-in minimizer-bucketed table layout (line by the k-mer's canonical 16-mer minimizer, structured remainder): same
+    kh_get results, same dump, same classification as the oracle, through the lean kernel (fast warp-level encode), the
+    generic kernel (hit lists) and the windowed modes (per-key encode); and a key set of another k falls back cleanly."""
+    import torch
+    from bonsai_b200 import workload as W
+    monkeypatch.setenv("BNS_B200_LAYOUT", "minimizer")
+    dev = torch.device("cuda", 0)
+    n_keys = (1 << 19) + 777
+    stream, d_keys, d_vals = W.make_stress_db(n_keys, seed=15, device=dev)
+    d_bases, d_offs, from_db = W.make_stress_reads(stream, 12000, seed=16, device=dev)
+    keys = d_keys.cpu().numpy().astype(np.uint64)
+    vals = d_vals.cpu().numpy().astype(np.uint32)
+    uk, ui = np.unique(keys, return_index=True)
+    D = oracle.db_from_pairs(uk, vals[ui])
+    # reads: the stress reads plus ragged / N / long ones
+    rb, ro, _ = H.make_reads(1500, seed=23, ragged=True)
+    reads = [bytes(rb[int(ro[i]):int(ro[i + 1])]) for i in range(ro.size - 1)]
+    sb, so = d_bases.cpu().numpy(), d_offs.cpu().numpy().astype(np.uint64)
+    reads += [bytes(sb[int(so[i]):int(so[i + 1])]) for i in range(so.size - 1)]
+    st = np.frombuffer(b"ACGT", np.uint8)[stream[:20000].cpu().numpy()]      # the key stream, as bases: long all-hit records
+    for j in range(8):
+        s0 = 1000 * j
+        reads.append(bytes(st[s0:s0 + 700 + 37 * j]))
+    b, o = po.pack_reads(reads)
+    c, p = H.toy_tax_arrays()
+    with capi.Context(31, 31) as ctx:
+        ctx.load_pairs_device(d_keys.data_ptr(), d_vals.data_ptr(), n_keys, W.STRESS_VALUES)
+        ctx.load_taxonomy(c, p)
+        info = ctx.table_info()
+        assert info["layout"] == 1, "the minimizer layout was not taken"
+        gv, gf = ctx.lookup(keys)
+        assert gf.all() and np.array_equal(gv, vals)
+        rng = np.random.default_rng(3)
+        probe = rng.integers(0, 1 << 62, 200000, dtype=np.uint64)
+        pv, pf = ctx.lookup(probe)
+        present = np.isin(probe, uk)
+        assert np.array_equal(pf, present)
+        dk, dv = ctx.table_dump()
+        order = np.argsort(dk)
+        assert np.array_equal(dk[order], uk) and np.array_equal(dv[order], vals[ui])
+        exp = oracle.classify(D, toy_tax, b, o, 31, 31, want_taxa=True)
+        got = ctx.classify(b, o)                                  # lean kernel, fast encode
+        for a, bb in zip(exp[:3], got):
+            assert np.array_equal(a, bb)
+        full = ctx.classify(b, o, want_taxa=True)                 # generic kernel
+        for a, bb in zip(exp[:3], full[:3]):
+            assert np.array_equal(a, bb)
+        assert all(np.array_equal(a, bb) for a, bb in zip(exp[3], full[3]))
+        # windowed minimizers on the reads against the same table (lean windowed kernel, per-key encode)
+        ctx.reconfigure(31, 50, None, capi.SCORE_LEX, True, capi.API_STRING)
+        expw = oracle.classify(D, toy_tax, b, o, 31, 50)
+        gotw = ctx.classify(b, o)
+        for a, bb in zip(expw, gotw):
+            assert np.array_equal(a, bb)
+        # a shorter k against the k=31 table: keys that are not 31-mers of the table cannot be there
+        ctx.reconfigure(25, 25, None, capi.SCORE_LEX, True, capi.API_STRING)
+        t25, h25, m25 = ctx.classify(b, o)
+        e25 = oracle.classify(D, toy_tax, b, o, 25, 25)
+        for a, bb in zip(e25, (t25, h25, m25)):
+            assert np.array_equal(a, bb)
+    # k = 21 is outside the layout's range: the hash layout is used
+    with capi.Context(21, 21) as ctx:
+        ctx.load_pairs(uk[:1000] & np.uint64((1 << 42) - 1), vals[ui][:1000])
+        assert ctx.table_info()["layout"] == 0
+    oracle.db_free(D)
