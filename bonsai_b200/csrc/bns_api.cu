@@ -1086,7 +1086,7 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     const u64 total_bases = ~0ull;
     const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
     Slot &s0 = ctx->slots[0];
-    if(pl.lean && pl.lean_mode != LEAN_U) {
+    if(pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R)) {
         rc = ensure(s0.d_defer, s0.cap_defer, n_rec);
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
         CK(cudaMemsetAsync(s0.d_defer_cnt, 0, sizeof(unsigned long long), st));
@@ -1144,9 +1144,9 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         }
         const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
                                                n_hit_out || n_missing_out);
-        if(rc == BNS_OK && pl.lean && pl.lean_mode != LEAN_U) rc = ensure(s.d_defer, s.cap_defer, nq);
+        if(rc == BNS_OK && pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R)) rc = ensure(s.d_defer, s.cap_defer, nq);
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
-        if(pl.lean && pl.lean_mode != LEAN_U) CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));
+        if(pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R)) CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
         CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));

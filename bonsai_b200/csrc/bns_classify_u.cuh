@@ -188,6 +188,7 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
 //       LEAN_K canonical k-mer at every position, invalid -> 0, windowed  encoder.h:211-217,622-628   (CANON must be true)
 //       LEAN_R valid forward k-mers, windowed over the compacted sequence, tail flush, canonical on emit if CANON
 //                                                                   encoder.h:273-353
+//       LEAN_S every valid spaced k-mer (comb of at most 45 bases, window of one)        encoder.h:233-239,547-592,616-621
 // KT: compile-time k (0 = use P.k). COUNTS: per-record hit / missing counts are wanted.
 // Windowed modes handle records of at most TILE window elements here; longer ones (and the 32-T restart quirk of
 // encoder.h:283) are appended to defer_idx and done by the generic stream kernel right after this one.
@@ -224,11 +225,15 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     Pc.flags_all = ((1u << T.tag_shift) - 1) & ~T.val_mask;
     Pc.flag_shift = T.flag_shift; Pc.flag_mask = T.flag_mask;
     Pc.val_mask = T.val_mask;
-    const u32 span = TILE + k - 1;
+    const u32 c = MODE == LEAN_S ? P.c : k;                            // bases a k-mer spans (the comb)
+    const u32 span = TILE + c - 1;
     const u32 down = 64 - 2 * k;
     const u32 kmask_lo = (u32)(~0ull >> down), kmask_hi = (u32)((~0ull >> down) >> 32);
     const u64 kmask = ~0ull >> down;
     const u32 W = P.W;
+    u64 comb = 0;                                                      // LEAN_S: the comb's bases, first base at bit c-1
+    if(MODE == LEAN_S)
+        for(u32 sg = 0; sg < P.n_seg; ++sg) comb |= ((1ull << P.seg_len[sg]) - 1) << (c - P.seg_off[sg] - P.seg_len[sg]);
 
     // Per-warp staging area in shared memory, filled by cp.async (LDGSTS): no registers are held across the HBM latency
     // and -- unlike a register prefetch -- the wait is a cp.async group wait, not a scoreboard the compiler may share
@@ -315,9 +320,9 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             bool spilled = false;
             bool deferred = false;
             if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
-            else if(MODE != LEAN_U && L >= k && L - k + 1 > (u32)TILE) deferred = true;   // more than one tile of window elements
-            else if(L >= k) {
-                const u32 npos = L - k + 1;
+            else if((MODE == LEAN_K || MODE == LEAN_R) && L >= k && L - k + 1 > (u32)TILE) deferred = true;   // more than one tile of window elements
+            else if(L >= c) {
+                const u32 npos = L - c + 1;
                 for(u32 p0 = 0; p0 < npos; p0 += TILE) {
                     // ---- stage: 8 bases per lane -> 16 bits per lane -> one 16-base word per lane ----------------
                     const uint2 v = p0 ? tile_block(rb + p0, L - p0) : pre;
@@ -341,9 +346,10 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         const u64 B = ((u64)b0 << 48) | ((u64)b1 << 32) | ((u64)b2 << 16) | (u64)b3;   // coordinate 8*ci at bit 63
 #pragma unroll
                         for(int i = 0; i < PPL; ++i)
-                            if(((B << ((q0 & 7u) + i)) >> (64 - k)) != 0) mask &= ~(1u << i);
-                        if(COUNTS && MODE == LEAN_U) n_emit += __reduce_add_sync(FULL, __popc(mask));
-                    } else if(COUNTS && MODE == LEAN_U) n_emit += min(left, (u32)TILE);
+                            if(MODE == LEAN_S ? ((((B << ((q0 & 7u) + i)) >> (64 - c)) & comb) != 0)
+                                              : (((B << ((q0 & 7u) + i)) >> (64 - k)) != 0)) mask &= ~(1u << i);
+                        if(COUNTS && (MODE == LEAN_U || MODE == LEAN_S)) n_emit += __reduce_add_sync(FULL, __popc(mask));
+                    } else if(COUNTS && (MODE == LEAN_U || MODE == LEAN_S)) n_emit += min(left, (u32)TILE);
                     // ---- the lane's four k-mers (and reverse complements) out of one 96-bit window --------------
                     const u32 A = __funnelshift_l(w1, w0, s), B_ = __funnelshift_l(w2, w1, s), C = __funnelshift_l(w3, w2, s);
                     if(MODE == LEAN_R && P.t_restart) {
@@ -363,6 +369,26 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     }
                     u32 xls[PPL], xhs[PPL];
                     u32 fwdm = 0xfu;                                   // bit i: k-mer i is used as read (not reverse-complemented)
+                    if(MODE == LEAN_S) {
+                        // Encoder::kmer(pos) (encoder.h:547-592) for the lane's four positions at once: per contiguous run of the
+                        // comb, the run's bases plus three more come out of the 96-bit window as one 64-bit word; position i's piece
+                        // is that word shifted by 2(3-i).
+                        u64 xs[PPL] = {0, 0, 0, 0};
+                        for(u32 sg = 0; sg < P.n_seg; ++sg) {
+                            const u32 off = P.seg_off[sg], len = P.seg_len[sg];              // len <= 29 (checked by the dispatcher)
+                            const u32 bo = 2 * off, wi = bo >> 5, sb = bo & 31u;
+                            const u32 x0 = wi == 0 ? A : wi == 1 ? B_ : C, x1 = wi == 0 ? B_ : wi == 1 ? C : 0u, x2 = wi == 0 ? C : 0u;
+                            const u64 V = ((((u64)__funnelshift_l(x1, x0, sb)) << 32) | __funnelshift_l(x2, x1, sb)) >> (58 - 2 * len);
+                            const u64 pm = (1ull << (2 * len)) - 1;
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i) xs[i] = (xs[i] << (2 * len)) | ((V >> (6 - 2 * i)) & pm);
+                        }
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) {
+                            xls[i] = (u32)xs[i]; xhs[i] = (u32)(xs[i] >> 32);
+                            if(P.filter_none && xs[i] == ~0ull) mask &= ~(1u << i);          // `!= ENCODE_OVERFLOW` (k = 32, all T)
+                        }
+                    } else
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
                         u32 xl, xh;                                                          // forward k-mer: window bits [2i, 2i+2k)
@@ -384,7 +410,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         }
                         xls[i] = xl; xhs[i] = xh;
                     }
-                    if(MODE != LEAN_U) {
+                    if(MODE == LEAN_K || MODE == LEAN_R) {
                         // ---- window elements -> minimizers (QueueMap, qmap.h:79-96) ---------------------------------
                         const u32 livem = (1u << nlive) - 1;                 // positions inside the record
                         constexpr int NW = KEY == LEAN_KEY_PAIR ? 4 : 2;
@@ -612,7 +638,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     }
                 }
             }
-            if(MODE != LEAN_U && deferred) {                           // the generic kernel redoes this record from scratch
+            if((MODE == LEAN_K || MODE == LEAN_R) && deferred) {                           // the generic kernel redoes this record from scratch
                 if(lane == 0) defer_idx[atomicAdd(defer_cnt, 1ull)] = (u32)(r0 + j);
                 nd = 0; n_hit = 0; n_emit = 0;
                 if(spilled) { spilled = false; sink.n_distinct = 0; sink.overflow = 0; }
@@ -637,7 +663,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
-        const u32 ndef = MODE == LEAN_U ? 0u : __popc(__ballot_sync(FULL, lane < nrec && my_def != 0));
+        const u32 ndef = (MODE == LEAN_U || MODE == LEAN_S) ? 0u : __popc(__ballot_sync(FULL, lane < nrec && my_def != 0));
         if(lane == 0) {                                                // classified_[2] (classifier.h:138,238), once per batch
             atomicAdd(&counters[0], (unsigned long long)cls);
             atomicAdd(&counters[1], (unsigned long long)(nrec - cls - ndef));

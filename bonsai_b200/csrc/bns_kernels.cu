@@ -1067,7 +1067,12 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     if(mates != 1 || taxa || mate1) return -1;
     if(P.family == FAM_U) return LEAN_U;
     const bool unspaced = P.c == P.k;
-    if(!unspaced || P.W > (u32)TILE) return -1;
+    if(!unspaced) {                                                   // spaced seed, window of one, comb inside the lane's 48-base window
+        if(P.family != FAM_K || P.canon_elem || P.W != 1 || P.c > 45) return -1;
+        for(u32 s = 0; s < P.n_seg; ++s) if(P.seg_len[s] > 29) return -1;
+        return LEAN_S;
+    }
+    if(P.W > (u32)TILE) return -1;
     if(P.family == FAM_K && P.canon_elem) return LEAN_K;
     if(P.family == FAM_R) return LEAN_R;
     return -1;
@@ -1098,6 +1103,7 @@ static int lean_key(const EncParams &P) {
     return LEAN_KEY_PAIR;
 }
 static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc) {
+    if(mode == LEAN_S) return pick_lean_k<LEAN_S, false, true, 0>(P.k, loc);
     if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P), loc);
     if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P), loc) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P), loc);
     if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc);
@@ -1122,7 +1128,7 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
         const u64 want = ((n_records + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;           // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
     }
-    if(!pl.lean || pl.lean_mode != LEAN_U) {                          // the generic kernel: everything, or the deferred records
+    if(!pl.lean || pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R) { // the generic kernel: everything, or the deferred records
         int ng = 0;
         classify_fn f = pick_classify(P.family, taxa);
         pl.gen_smem = stream_smem_bytes(ring_cap, true);
@@ -1148,7 +1154,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
         f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
                                                     counters, status, defer_idx, defer_cnt);
         cudaError_t e = cudaGetLastError();
-        if(e != cudaSuccess || pl.lean_mode == LEAN_U) return e;
+        if(e != cudaSuccess || pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) return e;
         // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel
         // reads the count on the device and returns at once. Sized small: deferred records are rare and long.
         classify_fn g = pick_classify(P.family, false);

@@ -221,9 +221,11 @@ def test_classify_golden(capi, golden, gpu_dbs, reads2000, cname):
     assert nhit.tolist() == spec["nhit"]
     assert nmiss.tolist() == spec["nmiss"]
     assert hashlib.md5(np.concatenate(lists).tobytes()).hexdigest() == spec["taxa_md5"]
-    # the lean call (taxon only) agrees
+    # the lean kernel (no hit list; with and without counts) agrees
     t2, _, _ = ctx.classify(bases, offs, want_counts=False)
     assert np.array_equal(t2, taxon)
+    t3, h3, m3 = ctx.classify(bases, offs)
+    assert np.array_equal(t3, taxon) and h3.tolist() == spec["nhit"] and m3.tolist() == spec["nmiss"]
     st = ctx.stats()
     assert st["kernel_launches"] > 0
 
