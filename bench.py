@@ -314,11 +314,16 @@ def main():
 
     step_host()
     barrier()
+    st0 = ctx.stats()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    st1 = ctx.stats()
+    # bytes the library actually moved per step (it does not ship the offsets of fixed-length batches)
+    h2d_step = (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.e2e_steps
+    d2h_step = (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.e2e_steps
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -399,8 +404,8 @@ def main():
                        "l2": "inputs (%.1f GB/step) exceed the 126 MB L2; no explicit flush" % (n * L_READ / 1e9),
                        "synthetic_genomes": bool(g["synthetic_genomes"]), "db_build_s": t_db, "db_broadcast_ms": bcast_ms,
                        "numa_node_rank0": numa},
-            "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": int(n * L_READ + 8 * (n + 1)),
-                    "d2h_bytes_per_step": int(4 * n), "steps": args.e2e_steps, "taxids_match_device_path": same},
+            "e2e": {"value": e2e_value, "unit": "Mreads/s", "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step), "steps": args.e2e_steps, "taxids_match_device_path": same},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

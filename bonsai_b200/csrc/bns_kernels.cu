@@ -1078,7 +1078,7 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     return -1;
 }
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                              unsigned long long *, u32 *, u32 *, unsigned long long *);
+                              unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64);
 static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
 template <int MODE, bool CANON, bool COUNTS, int KEY>
 static classify_u_fn pick_lean_k(u32 k, bool loc) {
@@ -1152,7 +1152,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
         f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
-                                                    counters, status, defer_idx, defer_cnt);
+                                                    counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base);
         cudaError_t e = cudaGetLastError();
         if(e != cudaSuccess || pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) return e;
         // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel

@@ -19,7 +19,9 @@ struct TableFmt;
 size_t stream_smem_bytes(u32 ring_cap, bool classify);
 enum LeanMode : int { LEAN_U = 0, LEAN_K = 1, LEAN_R = 2, LEAN_S = 3 };   // what bns_classify_u_kernel runs as (bns_classify_u.cuh)
 enum LeanKey : int { LEAN_KEY_PAIR = 0, LEAN_KEY_LEX = 1, LEAN_KEY_ELEM = 2 };   // how window elements are ordered
-struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true, loc = false; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0; };
+struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true, loc = false; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0;
+                      u32 fixed_len = 0; u64 fixed_base = 0;   // set by the caller: all records have fixed_len bases, offsets are not on the device
+                    };
 ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts);
 int encode_occupancy(const EncParams &P, size_t smem);
 

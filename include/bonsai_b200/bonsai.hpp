@@ -506,21 +506,27 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
                     int is_paired, std::string &cks) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
+    // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
+    // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
+    const bool need_taxa = (c.output_flag_ & KRAKEN) != 0;
     std::vector<u64> toffs(1, 0);
-    toffs.reserve(nrec + 1);
-    for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
-    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(nrec), taxa(toffs.back() + 1);
+    if(need_taxa) {
+        toffs.reserve(nrec + 1);
+        for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
+    }
+    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(is_paired ? nrec : 0), taxa(need_taxa ? toffs.back() + 1 : 0);
     bns_b200_t *h = c.h_->h;
     check(h, bns_b200_classify_batch_ex(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
-                                        taxa.data(), toffs.data(), mate1.data()), "bns_b200_classify_batch");
+                                        need_taxa ? taxa.data() : nullptr, need_taxa ? toffs.data() : nullptr,
+                                        is_paired ? mate1.data() : nullptr), "bns_b200_classify_batch");
     const u32 comb = c.sp_.c_;
     for(unsigned r = 0; r < nrec; ++r) {
         const ReadView *b = views + r * inc;
         // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
-        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)mate1[r]);
+        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
         if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
         if(c.get_emit_all() || taxon[r]) {
-            const tax_t *tx = taxa.data() + toffs[r];
+            const tax_t *tx = need_taxa ? taxa.data() + toffs[r] : nullptr;
             if(c.output_flag_ & FASTQ)
                 append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, cks, c.get_emit_kraken(), is_paired);
             else if(c.output_flag_ & KRAKEN)
