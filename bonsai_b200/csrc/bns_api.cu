@@ -209,7 +209,7 @@ bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
     if(ctx->no_minimizer || (e && !strcmp(e, "hash"))) return false;
     const u32 k = ctx->cfg.k;
     if(k < 23 || k > 31 || b < 8 || b > 32) return false;
-    if(b - 2 > LOC_MB) return false;
+    if(b - LOC_GB > LOC_MB) return false;
     const int fmt = (int)loc_fmt_bits(k, b);
     const u32 vb = bits_for(std::max<u32>((u32)ctx->values.size(), 2));
     if(fmt > 28 || fmt < (int)(vb + DISP_BITS_LOC + 1)) return false;

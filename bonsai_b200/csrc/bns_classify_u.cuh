@@ -51,7 +51,7 @@ __device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 home, 
     const u32 bmask = (b == 32) ? ~0u : ((1u << b) - 1);
     for(u32 d = 1; d <= Pc.max_disp; ++d) {
         u32 w[8];
-        ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, home, d, bmask) << 5), w);
+        ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, home, d, Pc.b) << 5), w);
         const u32 tl = tl0 | (d << Pc.tag_shift);
 #pragma unroll
         for(int j = 0; j < 4; ++j)
@@ -573,28 +573,6 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             if(!((w[i][0] >> (Pc.flag_shift + (fsel & Pc.flag_mask))) & 1u)) more |= 1u << i;
                         }
                         more &= nok & mask;
-                        if(LOC) {
-                            // LAYOUT_MINIMIZER fills lines in bursts (whole minimizer runs), displaced keys are common and sit
-                            // a few buckets on: all pending keys of the warp step through their probe sequences together,
-                            // four loads per lane in flight, instead of one key at a time.
-                            const u32 bmask = (Pc.b == 32) ? ~0u : ((1u << Pc.b) - 1);
-                            for(u32 d = 1; d <= Pc.max_disp && __any_sync(FULL, more != 0); ++d) {
-#pragma unroll
-                                for(int i = 0; i < PPL; ++i)
-                                    if(more >> i & 1u) ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, hb[i], d, bmask) << 5), w[i]);
-#pragma unroll
-                                for(int i = 0; i < PPL; ++i)
-                                    if(more >> i & 1u) {
-                                        const u32 tl = hl[i] | (d << Pc.tag_shift);
-                                        u32 c = ~hl[i];
-#pragma unroll
-                                        for(int j = 3; j >= 0; --j)
-                                            if((((w[i][2 * j] ^ tl) & Pc.hm) | (w[i][2 * j + 1] ^ hh[i])) == 0) c = w[i][2 * j];
-                                        if(c != ~hl[i]) { cand[i] = c; nok &= ~(1u << i); more &= ~(1u << i); }
-                                        else if((w[i][6] & w[i][7]) == ~0u) more &= ~(1u << i);   // a bucket with a free slot ends the run
-                                    }
-                            }
-                        } else
                         while(__any_sync(FULL, more != 0)) {
                             if(more) {
                                 const u32 i = __ffs(more) - 1;

@@ -64,6 +64,8 @@ enum TableLayout : u32 { LAYOUT_HASH = 0, LAYOUT_MINIMIZER = 1 };
 constexpr u32 LOC_L = 16;        // minimizer length: a k-mer holds k-15 <= 16 of them for k <= 31, so a full run of consecutive
                                  // k-mers sharing one minimizer fits the 16 slots of a line, four per sector
 constexpr u32 LOC_MB = 2 * LOC_L; // bits of a minimizer
+constexpr u32 LOC_GB = 3;         // a minimizer's home is a GROUP of 2^3 buckets (two adjacent 128-byte lines, 32 slots): the bucket
+                                 // inside it is the minimizer's position mod 8, so one run of <= 16 k-mers puts <= 2 keys in a bucket
 
 struct TableFmt {
     u32 b;                       // bucket bits: 2^b buckets of 32 bytes
@@ -188,28 +190,28 @@ __host__ __device__ __forceinline__ u32 rc16(u32 x) {
     r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);     // bit-reversed pairs back in order
     return ~r;
 }
-// remainder bits of a LAYOUT_MINIMIZER slot: [minimizer hash below the line bits | position >> 2 | orientation | flank hash]
-__host__ __device__ __forceinline__ u32 loc_rembits(u32 k, u32 b) { return (LOC_MB - (b - 2)) + 2 + 1 + 2 * (k - LOC_L); }
+// remainder bits of a LAYOUT_MINIMIZER slot: [minimizer hash below the group bits | position >> 3 | orientation | flank hash]
+__host__ __device__ __forceinline__ u32 loc_rembits(u32 k, u32 b) { return (LOC_MB - (b - LOC_GB)) + 1 + 1 + 2 * (k - LOC_L); }
 __host__ __device__ __forceinline__ u32 loc_fmt_bits(u32 k, u32 b) { return 64 - loc_rembits(k, b); }
 struct TableHash { u64 home; u64 tag; u32 fsel; };                // home bucket, left-aligned remainder, overflow-flag selector
 
 // (bucket, remainder) of k-mer s once its minimizer is known: mh = nmix(canonical 16-mer, 32), at position bp of s,
 // bo = the 16-mer stands in s as the reverse complement of its canonical form
 __host__ __device__ __forceinline__ TableHash loc_pack(u64 s, u32 k, u32 b, u32 mh, u32 bp, u32 bo) {
-    const u32 nf = 2 * (k - LOC_L), bl = b - 2;
+    const u32 nf = 2 * (k - LOC_L), bl = b - LOC_GB;
     const u32 nr = 2 * (k - LOC_L - bp);                                   // bits right of the minimizer
     const u64 left = bp ? (s >> (2 * (k - bp))) : 0ull, right = nr ? (s & ((1ull << nr) - 1)) : 0ull;
     const u32 fm = nmix((u32)((left << nr) | right), nf);
-    // the sector inside the line: the minimizer's position mod 4. The k-mers of one run have consecutive positions, so a run
-    // spreads evenly over the line's four sectors instead of overflowing one of them by chance.
-    const u32 sec = bp & 3u;
+    // the bucket inside the group: the minimizer's position mod 8. The k-mers of one run have consecutive positions, so a
+    // run spreads evenly over the group's eight buckets instead of overflowing one of them by chance.
+    const u32 sec = bp & ((1u << LOC_GB) - 1);
     // the minimum of k-15 hashes is small: its top bits would crowd the keys into a few lines. The line comes from a
     // second bijection of the winning hash.
     const u32 li = nmix(mh ^ 0x2545f491u, LOC_MB);
     const u32 line = li >> (LOC_MB - bl), mrest = bl >= LOC_MB ? 0u : (li & ((1u << (LOC_MB - bl)) - 1));
-    const u64 rem = ((((u64)mrest << 2 | (bp >> 2)) << 1 | bo) << nf) | fm;
+    const u64 rem = ((((u64)mrest << 1 | (bp >> LOC_GB)) << 1 | bo) << nf) | fm;
     TableHash t;
-    t.home = ((u64)line << 2) | sec;
+    t.home = ((u64)line << LOC_GB) | sec;
     t.tag = rem << (64 - loc_rembits(k, b));
     t.fsel = fm;
     return t;
@@ -228,12 +230,12 @@ __host__ __device__ inline TableHash loc_encode(u64 s, u32 k, u32 b) {
 }
 // inverse: home bucket + left-aligned remainder -> key
 __host__ __device__ inline u64 loc_decode(u64 home, u64 tag, u32 k, u32 b) {
-    const u32 nf = 2 * (k - LOC_L), bl = b - 2;
+    const u32 nf = 2 * (k - LOC_L), bl = b - LOC_GB;
     const u64 rem = tag >> (64 - loc_rembits(k, b));
     const u32 fm = (u32)(rem & (nf >= 32 ? 0xffffffffull : ((1ull << nf) - 1)));
-    const u32 bo = (u32)(rem >> nf) & 1u, bp = ((u32)(rem >> (nf + 1)) & 3u) << 2 | ((u32)home & 3u);
-    const u32 mrest = (u32)(rem >> (nf + 3));
-    const u32 li = bl >= LOC_MB ? (u32)(home >> 2) : (((u32)(home >> 2) << (LOC_MB - bl)) | mrest);
+    const u32 bo = (u32)(rem >> nf) & 1u, bp = ((u32)(rem >> (nf + 1)) & 1u) << LOC_GB | ((u32)home & ((1u << LOC_GB) - 1));
+    const u32 mrest = (u32)(rem >> (nf + 2));
+    const u32 li = bl >= LOC_MB ? (u32)(home >> LOC_GB) : (((u32)(home >> LOC_GB) << (LOC_MB - bl)) | mrest);
     const u32 mh = nunmix(li, LOC_MB) ^ 0x2545f491u;
     const u32 c = nunmix(mh, LOC_MB), f = bo ? rc16(c) : c;
     const u32 fl = nunmix(fm, nf);
@@ -241,15 +243,27 @@ __host__ __device__ inline u64 loc_decode(u64 home, u64 tag, u32 k, u32 b) {
     const u64 left = nr >= 32 ? 0ull : ((u64)fl >> nr), right = nr ? ((u64)fl & ((1ull << nr) - 1)) : 0ull;
     return (((left << LOC_MB) | f) << nr) | right;
 }
-// the d-th bucket of a key's probe sequence: the next buckets (LAYOUT_HASH); the other sectors of the home LINE first, then
-// the following lines (LAYOUT_MINIMIZER: a displaced key stays in the line its minimizer run already brought into L2)
-__host__ __device__ __forceinline__ u64 probe_bucket(u32 layout, u64 home, u32 d, u64 bmask) {
-    if(layout == LAYOUT_MINIMIZER) return (((((home >> 2) + (d >> 2)) << 2) | ((home + d) & 3ull))) & bmask;
+// the d-th bucket of a key's probe sequence. LAYOUT_HASH: the next buckets. LAYOUT_MINIMIZER: the home bucket, its neighbour
+// in the group (same pair of lines, already in L2), then a run of buckets starting at a scrambled image of the home bucket:
+// keys that overflow a crowded group (two or three minimizer runs in one) scatter instead of piling into the next group,
+// so probe sequences stay short.
+__host__ __device__ __forceinline__ u64 probe_bucket(u32 layout, u64 home, u32 d, u32 b) {
+    const u64 bmask = b >= 64 ? ~0ull : ((1ull << b) - 1);
+    if(layout == LAYOUT_MINIMIZER) {
+        const u64 gm = (1ull << LOC_GB) - 1;
+        if(d < 2) return (home & ~gm) | ((home + d) & gm);
+        return ((u64)nmix((u32)home, b) + (d - 2)) & bmask;
+    }
     return (home + d) & bmask;
 }
 // ... and back: the home bucket of an entry found in `bucket` with displacement d
-__host__ __device__ __forceinline__ u64 probe_home(u32 layout, u64 bucket, u32 d, u64 bmask) {
-    if(layout == LAYOUT_MINIMIZER) return (((((bucket >> 2) - (d >> 2)) << 2) | ((bucket - d) & 3ull))) & bmask;
+__host__ __device__ __forceinline__ u64 probe_home(u32 layout, u64 bucket, u32 d, u32 b) {
+    const u64 bmask = b >= 64 ? ~0ull : ((1ull << b) - 1);
+    if(layout == LAYOUT_MINIMIZER) {
+        const u64 gm = (1ull << LOC_GB) - 1;
+        if(d < 2) return (bucket & ~gm) | ((bucket - d) & gm);
+        return (u64)nunmix((u32)((bucket - (d - 2)) & bmask), b);
+    }
     return (bucket - d) & bmask;
 }
 // key -> (home bucket, remainder) of either layout. Keys that are not k-mers of the table's k cannot be in a

@@ -218,7 +218,7 @@ __device__ __noinline__ u32 probe_displaced(const TableView T, u64 home, u64 tag
     const u64 bmask = (1ull << b) - 1;
     for(u32 d = 1; d <= T.fmt.max_disp(); ++d) {
         u64 a, bb, c, e;
-        ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, bmask) << 2), a, bb, c, e);
+        ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, T.fmt.b) << 2), a, bb, c, e);
         const u32 v = match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e);
         if(v != VAL_MISS || e == ~0ull) return v;
     }
@@ -443,7 +443,7 @@ struct BuildSink {
         if(!possible) { ++n_fail; return; }
         const u64 home = th.home, bmask = (1ull << b) - 1, tag = th.tag;
         for(u32 d = 0; d <= fmt.max_disp(); ++d) {
-            u64 *bk = slots + (probe_bucket(fmt.layout, home, d, bmask) << 2);
+            u64 *bk = slots + (probe_bucket(fmt.layout, home, d, fmt.b) << 2);
             const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << tag_shift) - 1) & ~(u64)val_mask) | vid;
             for(int s = 0; s < 4; ++s) {
                 u64 cur = bk[s];
@@ -866,7 +866,7 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u
     const u32 tag_shift = fmt.tag_shift(), flag_shift = fmt.flag_shift();
     const u64 tag = th.tag;
     for(u32 d = 0; d <= fmt.max_disp(); ++d) {
-        u64 *bk = slots + (probe_bucket(fmt.layout, home, d, bmask) << 2);
+        u64 *bk = slots + (probe_bucket(fmt.layout, home, d, fmt.b) << 2);
         const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << F) - 1) << flag_shift) | vid;
         for(int s = 0; s < 4; ++s) {
             u64 cur = bk[s];
@@ -925,7 +925,7 @@ __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u6
         const u64 home = h.home, bmask = (1ull << b) - 1, tag = h.tag;
         for(u32 d = 0; d <= T.fmt.max_disp(); ++d) {
             u64 a, bb, c, e;
-            ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, bmask) << 2), a, bb, c, e);
+            ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, T.fmt.b) << 2), a, bb, c, e);
             ++touched;
             if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
             if(d == 0 ? (((a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1ull) != 0) : (e == ~0ull)) break;
@@ -992,7 +992,7 @@ __global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, Ta
     if(v == ~0ull) return;
     const u32 tag_shift = fmt.tag_shift(), b = fmt.b;
     const u64 bucket = i >> 2, disp = (v >> tag_shift) & ((1u << fmt.disp_bits) - 1);
-    const u64 home = probe_home(fmt.layout, bucket, (u32)disp, n_buckets - 1);
+    const u64 home = probe_home(fmt.layout, bucket, (u32)disp, fmt.b);
     const u64 rem_mask = ~0ull << fmt.fmt_bits;                    // the remainder, left-aligned
     const u64 key = fmt.layout == LAYOUT_MINIMIZER ? loc_decode(home, v & rem_mask, fmt.kt, b)
                                                    : unmix64((home << (64 - b)) | (v >> b));

@@ -14,7 +14,7 @@ int main() {
     int failures = 0;
     for(u32 k : {23u, 25u, 27u, 31u})
         for(u32 b : {12u, 16u, 20u, 24u, 27u, 29u, 31u}) {
-            if(b - 2 > LOC_MB) continue;
+            if(b - LOC_GB > LOC_MB) continue;
             const int fmt = (int)loc_fmt_bits(k, b);
             if(fmt > 28 || fmt < 8) continue;
             const u64 mask = (1ull << (2 * k)) - 1;
@@ -29,32 +29,27 @@ int main() {
                 const u64 y = loc_decode(t.home, t.tag, k, b);
                 if(y != x || (t.home >> b) != 0 || (t.tag & ((1ull << (64 - rembits)) - 1)) != 0) ++bad;
                 // probe sequence and its inverse
-                const u64 bmask = (1ull << b) - 1;
                 for(u32 d : {0u, 1u, 3u, 4u, 9u, 61u})
-                    if(probe_home(LAYOUT_MINIMIZER, probe_bucket(LAYOUT_MINIMIZER, t.home, d, bmask), d, bmask) != t.home) ++bad;
+                    if(probe_home(LAYOUT_MINIMIZER, probe_bucket(LAYOUT_MINIMIZER, t.home, d, b), d, b) != t.home) ++bad;
             }
             printf("k=%u b=%u fmt=%d bad=%zu\n", k, b, fmt, bad);
             failures += bad != 0;
         }
-    // a k-mer and its reverse complement are the same key only through the caller's canonicalisation; locality: distinct
-    // consecutive lines touched by the 120 canonical 31-mers of a random 150 bp read
+    // locality: distinct 128-byte lines holding the home buckets of the 120 canonical 31-mers of a random 150 bp read
     const u32 k = 31, b = 28;
     double tot = 0;
     const int R = 500;
     for(int r = 0; r < R; ++r) {
         u64 f = 0;
         const u64 mask = (1ull << 62) - 1;
-        u64 prev = ~0ull;
-        int nl = 0;
+        u64 lines[120];
+        int n = 0;
         for(int i = 0; i < 150; ++i) {
             f = ((f << 2) | (rng() & 3)) & mask;
-            if(i >= 30) {
-                const u64 c = std::min(f, revcomp(f, 31));
-                const u64 ln = loc_encode(c, k, b).home >> 2;
-                if(ln != prev) { ++nl; prev = ln; }
-            }
+            if(i >= 30) lines[n++] = loc_encode(std::min(f, revcomp(f, 31)), k, b).home >> 2;      // line = 4 buckets
         }
-        tot += nl;
+        std::sort(lines, lines + n);
+        tot += std::unique(lines, lines + n) - lines;
     }
     printf("lines_per_read=%.2f\n", tot / R);
     return failures ? 1 : 0;

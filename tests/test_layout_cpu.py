@@ -22,4 +22,4 @@ def test_minimizer_layout_bijection(tmp_path):
     checked = [ln for ln in lines if ln.startswith("k=")]
     assert len(checked) >= 10 and all(ln.endswith("bad=0") for ln in checked), r.stdout
     lpr = float([ln for ln in lines if ln.startswith("lines_per_read=")][0].split("=")[1])
-    assert lpr < 20.0          # 120 consecutive 31-mers of a read touch ~15 lines instead of 120
+    assert lpr < 45.0          # the 120 consecutive 31-mers of a read have their homes in ~30 lines (15 groups of two) instead of 120
