@@ -199,11 +199,12 @@ void free_table(bns_b200_ctx *ctx) {
 
 u32 bits_for(u64 n) { u32 b = 0; while((1ull << b) < n) ++b; return b; }
 
-// LAYOUT_MINIMIZER (bns_device.cuh) is OPT-IN for now: BNS_B200_LAYOUT=minimizer. It needs room in the slot for the longer
-// remainder -- 23 <= k <= 31, fmt_bits = loc_fmt_bits(k, b) in [value bits + displacement bits + 1, 28] -- and a key set
-// without heavily repeated 16-mers (a build that finds no room is redone in the hash layout). Measured on the 2^28-key
-// stress table: DRAM traffic per read 5.7x lower, throughput 0.99x (1 key/bucket) to 1.23x (0.5
-// keys/bucket) of the hash layout: the probe rounds for keys that overflow their line are instruction-bound.
+// LAYOUT_MINIMIZER (bns_device.cuh) is taken for tables far beyond L2 (>= 1 GiB: one DRAM line per lookup in the hash
+// layout) of unspaced k-mers, 23 <= k <= 31, when the slot has room for the longer remainder (fmt_bits = loc_fmt_bits(k, b)
+// in [value bits + displacement bits + 1, 28]). It suits key sets whose minimizers are spread out: a build that finds no
+// room, or that had to displace more than a tenth of the keys (heavily repeated 16-mers: real genomes at small scale), is
+// redone in the hash layout. BNS_B200_LAYOUT=hash|minimizer overrides the size rule and the displacement check.
+// Measured: 2^28-key stress table 283 -> 446 Mreads/s at equal memory, DRAM traffic per read 5.7x lower.
 bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
     const char *e = getenv("BNS_B200_LAYOUT");
     if(ctx->no_minimizer || (e && !strcmp(e, "hash"))) return false;
@@ -213,7 +214,14 @@ bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
     const int fmt = (int)loc_fmt_bits(k, b);
     const u32 vb = bits_for(std::max<u32>((u32)ctx->values.size(), 2));
     if(fmt > 28 || fmt < (int)(vb + DISP_BITS_LOC + 1)) return false;
-    return e && !strcmp(e, "minimizer");
+    if(e && !strcmp(e, "minimizer")) return true;
+    return ctx->unspaced && (32ull << b) >= (1ull << 30);
+}
+// a minimizer-layout build that displaced too many keys probes too long: better off in the hash layout
+bool minimizer_build_too_crowded(const bns_b200_ctx *ctx) {
+    const char *e = getenv("BNS_B200_LAYOUT");
+    if(ctx->layout != LAYOUT_MINIMIZER || (e && !strcmp(e, "minimizer"))) return false;
+    return ctx->n_displaced * 10 > ctx->n_keys;
 }
 TableFmt table_fmt(const bns_b200_ctx *ctx) {
     TableFmt f;
@@ -586,7 +594,12 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
             return n;
         }, st);
         if(rc != BNS_OK) return rc;
-        if(st[0] == 0) return finish_table(ctx, st);
+        if(st[0] == 0) {
+            rc = finish_table(ctx, st);
+            if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
+            ctx->no_minimizer = true; --b;                            // same size, hash layout
+            continue;
+        }
         // some key found no room within MAX_DISP buckets of home: grow and rebuild (a minimizer-layout build that fails --
         // skewed minimizers -- is redone in the hash layout at the same size first)
         if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
@@ -616,7 +629,12 @@ int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
             return m;
         }, st);
         if(rc != BNS_OK) return rc;
-        if(st[0] == 0) return finish_table(ctx, st);
+        if(st[0] == 0) {
+            rc = finish_table(ctx, st);
+            if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
+            ctx->no_minimizer = true; --b;                            // same size, hash layout
+            continue;
+        }
         if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
@@ -646,7 +664,12 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         unsigned long long h[3];
         CK(cudaMemcpyAsync(h, ctx->d_counters + 5, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if(h[0] == 0) return finish_table(ctx, h);
+        if(h[0] == 0) {
+            rc = finish_table(ctx, h);
+            if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
+            ctx->no_minimizer = true; --b;                            // same size, hash layout
+            continue;
+        }
         if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
@@ -824,7 +847,7 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
     u32 want = std::min(choose_bits(ctx->n_keys, (u32)ctx->values.size()), ctx->bucket_bits);
     while(want <= ctx->bucket_bits) {
         const bool mini = want_minimizer_layout(ctx, want);
-        if(want == ctx->bucket_bits && !mini) break;                     // already there
+        if(want == ctx->bucket_bits && !mini && ctx->layout == LAYOUT_HASH) break;   // already there
         const TableFmt nf = fmt_for(ctx, want, mini);
         cudaStream_t st = ctx->slots[0].st;
         const u64 n = ctx->n_keys;
@@ -852,7 +875,9 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         ctx->d_slots = new_slots;
         adopt_fmt(ctx, nf);
         ctx->n_displaced = h2[1];
-        return refresh_table_stats(ctx);
+        rc = refresh_table_stats(ctx);
+        if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
+        ctx->no_minimizer = true;                                         // same size, hash layout
     }
     return BNS_OK;
 }

@@ -537,9 +537,8 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             x ^= x >> 32;
                             x *= 0xd6e8feb86659fd93ull;
                             hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
-                            hb[i] = hh[i] >> Pc.idx_shift;
                         }
-                        ld_bucket8(Pc.slots + ((u64)hb[i] << 5), w[i]);
+                        ld_bucket8(Pc.slots + ((u64)(LOC ? hb[i] : hh[i] >> Pc.idx_shift) << 5), w[i]);
                     }
                     }
                     // ---- match: first slot whose high word equals the tag's, verified on the low word (LAYOUT_HASH keeps
@@ -579,7 +578,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                                 more &= more - 1;
                                 const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
                                 const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
-                                const u32 hm = i == 0 ? hb[0] : i == 1 ? hb[1] : i == 2 ? hb[2] : hb[3];
+                                const u32 hm = LOC ? (i == 0 ? hb[0] : i == 1 ? hb[1] : i == 2 ? hb[2] : hb[3]) : (h >> Pc.idx_shift);
                                 const u32 th = LOC ? h : __funnelshift_lc(l, h, Pc.b), tl0 = LOC ? l : __funnelshift_lc(0u, l, Pc.b);
                                 const u32 c = probe_displaced32(Pc, hm, th, tl0);
                                 if(c != ~tl0) {

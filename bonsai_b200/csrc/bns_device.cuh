@@ -37,7 +37,7 @@ constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
 constexpr int AGG_CAP = 256;     // distinct taxa tracked per record in shared memory (covers any read up to k+255 bases)
 constexpr int DISP_BITS = 4;     // slot displacement field of LAYOUT_HASH; disp == 2^bits - 1 is reserved for the empty slot
-constexpr int DISP_BITS_LOC = 7; // LAYOUT_MINIMIZER: lines fill unevenly (whole minimizer runs land in one), longer runs of full buckets
+constexpr int DISP_BITS_LOC = 8; // LAYOUT_MINIMIZER: lines fill unevenly (whole minimizer runs land in one), longer runs of full buckets
 
 struct EncParams {
     u32 k, c, W;                 // W = w_ - c_ + 1  (QueueMap size, encoder.h:142)
