@@ -202,9 +202,9 @@ u32 bits_for(u64 n) { u32 b = 0; while((1ull << b) < n) ++b; return b; }
 // LAYOUT_MINIMIZER (bns_device.cuh) is taken for tables far beyond L2 (>= 1 GiB: one DRAM line per lookup in the hash
 // layout) of unspaced k-mers, 23 <= k <= 31, when the slot has room for the longer remainder (fmt_bits = loc_fmt_bits(k, b)
 // in [value bits + displacement bits + 1, 28]). It suits key sets whose minimizers are spread out: a build that finds no
-// room, or that had to displace more than a tenth of the keys (heavily repeated 16-mers: real genomes at small scale), is
+// room, or that had to displace more than a sixth of the keys (heavily repeated 16-mers: real genomes at small scale), is
 // redone in the hash layout. BNS_B200_LAYOUT=hash|minimizer overrides the size rule and the displacement check.
-// Measured: 2^28-key stress table 283 -> 446 Mreads/s at equal memory, DRAM traffic per read 5.7x lower.
+// Measured: stress tables of 2^28 / 2^30 keys 283 -> 446 / 278 -> 397 Mreads/s at equal memory.
 bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
     const char *e = getenv("BNS_B200_LAYOUT");
     if(ctx->no_minimizer || (e && !strcmp(e, "hash"))) return false;
@@ -221,7 +221,7 @@ bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
 bool minimizer_build_too_crowded(const bns_b200_ctx *ctx) {
     const char *e = getenv("BNS_B200_LAYOUT");
     if(ctx->layout != LAYOUT_MINIMIZER || (e && !strcmp(e, "minimizer"))) return false;
-    return ctx->n_displaced * 10 > ctx->n_keys;
+    return ctx->n_displaced * 6 > ctx->n_keys;                    // measured: 10 % displaced is still 1.43x the hash layout at 2^30 keys
 }
 TableFmt table_fmt(const bns_b200_ctx *ctx) {
     TableFmt f;
@@ -664,6 +664,9 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         unsigned long long h[3];
         CK(cudaMemcpyAsync(h, ctx->d_counters + 5, sizeof h, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if(getenv("BNS_B200_VERBOSE"))
+            fprintf(stderr, "[bns_b200] table build: 2^%u buckets, layout %u, no room for %llu keys, %llu displaced of %llu\n", b, ctx->layout, h[0], h[1],
+                    (unsigned long long)n);
         if(h[0] == 0) {
             rc = finish_table(ctx, h);
             if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
