@@ -9,7 +9,7 @@ if [ "$2" != "notests" ]; then
 fi
 timeout 600 python bench.py --steps 30 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 1 --reads 4000000 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:bns_classify -s 3 -c 1 -f -o gpurun_out/prof_$TAG \
   python bench.py --steps 2 --warmup 1 --reads 4000000 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
