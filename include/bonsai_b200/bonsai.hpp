@@ -520,19 +520,31 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
                                         need_taxa ? taxa.data() : nullptr, need_taxa ? toffs.data() : nullptr,
                                         is_paired ? mate1.data() : nullptr), "bns_b200_classify_batch");
     const u32 comb = c.sp_.c_;
-    for(unsigned r = 0; r < nrec; ++r) {
-        const ReadView *b = views + r * inc;
-        // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
-        u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
-        if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
-        if(c.get_emit_all() || taxon[r]) {
-            const tax_t *tx = need_taxa ? taxa.data() + toffs[r] : nullptr;
-            if(c.output_flag_ & FASTQ)
-                append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, cks, c.get_emit_kraken(), is_paired);
-            else if(c.output_flag_ & KRAKEN)
-                append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], *b, cks);
+    // classify_seq's epilogue (text) per record. The reference formats on its worker threads (-p, kt_for_helper,
+    // classifier.h:254-266); here -p threads format contiguous slices of the batch and the slices are joined in order.
+    auto format_range = [&](unsigned r_lo, unsigned r_hi, std::string &out) {
+        for(unsigned r = r_lo; r < r_hi; ++r) {
+            const ReadView *b = views + r * inc;
+            // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
+            u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
+            if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
+            if(c.get_emit_all() || taxon[r]) {
+                const tax_t *tx = need_taxa ? taxa.data() + toffs[r] : nullptr;
+                if(c.output_flag_ & FASTQ)
+                    append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, out, c.get_emit_kraken(), is_paired);
+                else if(c.output_flag_ & KRAKEN)
+                    append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], *b, out);
+            }
         }
-    }
+    };
+    const unsigned nthreads = std::max(1u, std::min<unsigned>(c.nt_, nrec / 256 + 1));
+    if(nthreads == 1) { format_range(0, nrec, cks); return; }
+    std::vector<std::string> parts(nthreads);
+    std::vector<std::thread> pool;
+    for(unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] { format_range((unsigned)((u64)nrec * t / nthreads), (unsigned)((u64)nrec * (t + 1) / nthreads), parts[t]); });
+    for(auto &th : pool) th.join();
+    for(auto &part : parts) cks += part;
 }
 
 // A batch parsed straight into PINNED host memory (bns_b200_host_alloc): the library DMAs from it without staging.
@@ -541,6 +553,7 @@ struct PinnedBatch {
     u64 *offs = nullptr; size_t cap_offs = 0, n = 0;
     std::vector<std::string> names, quals;
     std::vector<char> has_qual;
+    bool keep_qual = true;             // qualities are only printed by the FASTQ-style output
     PinnedBatch() = default;
     PinnedBatch(const PinnedBatch &) = delete;
     ~PinnedBatch() { bns_b200_host_free(bases); bns_b200_host_free(offs); }
@@ -567,8 +580,8 @@ struct PinnedBatch {
         n_bases += k->seq.size();
         offs[++n] = n_bases;
         names.push_back(k->name);
-        has_qual.push_back(!k->qual.empty());
-        quals.push_back(k->qual);
+        has_qual.push_back(keep_qual && !k->qual.empty());
+        if(keep_qual) quals.push_back(k->qual); else quals.emplace_back();
     }
 };
 // bseq_read (kseq_declare.h:112-145) into a pinned batch: records until >= chunk_size bases and an even count
@@ -617,7 +630,7 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     constexpr int NB = 3;
     detail::PinnedBatch ring[NB];
-    for(auto &b : ring) b.reserve(chunk_size);
+    for(auto &b : ring) { b.reserve(chunk_size); b.keep_qual = c.get_emit_fastq() != 0; }
     int state[NB] = {0, 0, 0};                   // 0 free, 1 filled, 2 end of input
     std::mutex mu;
     std::condition_variable cv;

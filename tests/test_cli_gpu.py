@@ -56,7 +56,8 @@ def test_build_matches_oracle(setup, oracle):
         assert "val_sum=%d" % int(v.sum(dtype=np.uint64)) in out
 
 
-@pytest.mark.parametrize("mode", ["kraken_all", "kraken_classified_only", "fastq_all", "fastq_kraken", "kraken_nocanon"])
+@pytest.mark.parametrize("mode", ["kraken_all", "kraken_classified_only", "fastq_all", "fastq_kraken", "kraken_nocanon",
+                                  "kraken_all_p4", "fastq_all_p4"])
 def test_classify_text(setup, oracle, genomes, mode):
     g = genomes
     rng = np.random.default_rng(3)
@@ -79,14 +80,19 @@ def test_classify_text(setup, oracle, genomes, mode):
     use_q = mode != "kraken_classified_only"
     write_fastq(fq, names, seqs, quals if use_q else None)
     flags = {"kraken_all": ["-a"], "kraken_classified_only": [], "fastq_all": ["-a", "-f", "-K"], "fastq_kraken": ["-a", "-f", "-k"],
-             "kraken_nocanon": ["-a", "-C"]}[mode]
+             "kraken_nocanon": ["-a", "-C"],
+             # one big chunk, four formatter threads (the lean kernel for the FASTQ-style output without run lists)
+             "kraken_all_p4": ["-a", "-p", "4"], "fastq_all_p4": ["-a", "-f", "-K", "-p", "4"]}[mode]
+    chunk = "100000000" if mode.endswith("_p4") else "20000"
     kw = {"kraken_all": dict(emit_all=True, emit_fastq=False, emit_kraken=True),
           "kraken_classified_only": dict(emit_all=False, emit_fastq=False, emit_kraken=True),
           "fastq_all": dict(emit_all=True, emit_fastq=True, emit_kraken=False),
           "fastq_kraken": dict(emit_all=True, emit_fastq=True, emit_kraken=True),
-          "kraken_nocanon": dict(emit_all=True, emit_fastq=False, emit_kraken=True, canon=False)}[mode]
+          "kraken_nocanon": dict(emit_all=True, emit_fastq=False, emit_kraken=True, canon=False),
+          "kraken_all_p4": dict(emit_all=True, emit_fastq=False, emit_kraken=True),
+          "fastq_all_p4": dict(emit_all=True, emit_fastq=True, emit_kraken=False)}[mode]
     outp = setup["dir"] / ("out_%s.txt" % mode)
-    r = subprocess.run([setup["cli"], "classify"] + flags + ["-c", "20000", "-o", str(outp), str(setup["db"]), str(setup["nodes"]), str(fq)],
+    r = subprocess.run([setup["cli"], "classify"] + flags + ["-c", chunk, "-o", str(outp), str(setup["db"]), str(setup["nodes"]), str(fq)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     bases, offs = po.pack_reads(seqs)
