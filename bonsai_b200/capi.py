@@ -24,7 +24,7 @@ SYMBOLS = [
     "bns_b200_load_taxonomy_file", "bns_b200_resolve_batch", "bns_b200_build_begin", "bns_b200_build_add_genome",
     "bns_b200_build_finish", "bns_b200_table_dump", "bns_b200_reconfigure", "bns_b200_db_export_header",
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
-    "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
+    "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_batch_runs", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
 ]
 
@@ -108,6 +108,7 @@ def load_library(path=None):
     lib.bns_b200_encode_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, vp]
     lib.bns_b200_classify_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp]
     lib.bns_b200_classify_batch_ex.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.bns_b200_classify_batch_runs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.POINTER(C.c_uint64)]
     lib.bns_b200_classify_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.bns_b200_sync.argtypes = [vp]
     lib.bns_b200_stats_get.argtypes = [vp, C.POINTER(Stats)]
@@ -324,6 +325,28 @@ class Context:
             lists = [taxa[int(toffs[i]):int(toffs[i]) + int(nhit[i])].copy() for i in range(nrec)]
             return taxon, nhit, nmiss, lists
         return taxon, nhit, nmiss
+
+    def classify_runs(self, bases, offsets, paired=False, cap=None):
+        """bns_b200_classify_batch_runs: (taxon, nhit, nmiss, [per record array of (taxid, run length) rows])"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = offsets.size - 1
+        inc = 2 if paired else 1
+        nrec = n // inc
+        taxon = np.zeros(nrec, np.uint32); nhit = np.zeros(nrec, np.uint32); nmiss = np.zeros(nrec, np.uint32)
+        if cap is None:
+            cap = int((offsets[nrec * inc] - offsets[0])) + 2 * nrec + 1
+        runs = np.zeros(max(cap, 1), np.uint64)
+        pos = np.zeros(nrec, np.uint64); nruns = np.zeros(nrec, np.uint32)
+        total = C.c_uint64(0)
+        self._ck(self.lib.bns_b200_classify_batch_runs(self.h, _p(bases), _p(offsets), n, int(paired), _p(taxon), _p(nhit),
+                                                       _p(nmiss), None, _p(runs), cap, _p(pos), _p(nruns), C.byref(total)))
+        out = []
+        for r in range(nrec):
+            w = runs[int(pos[r]):int(pos[r]) + int(nruns[r])]
+            out.append(np.stack([(w >> np.uint64(32)).astype(np.uint32), (w & np.uint64(0xffffffff)).astype(np.uint32)], axis=1))
+        assert int(total.value) == int(nruns.sum())
+        return taxon, nhit, nmiss, out
 
     def classify_into(self, bases_ptr, offsets_ptr, n_reads, taxon_ptr, nhit_ptr=None, nmiss_ptr=None, paired=False):
         """bns_b200_classify_batch on raw HOST pointers (e.g. pinned buffers): blocks until outputs are written."""

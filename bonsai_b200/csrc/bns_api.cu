@@ -36,6 +36,9 @@ struct Slot {
     u64 *d_kmers = nullptr;        size_t cap_kmers = 0;
     u64 *d_out_offsets = nullptr;  size_t cap_out_offsets = 0;
     u32 *d_defer = nullptr;        size_t cap_defer = 0;     // records the lean windowed kernel leaves to the generic one
+    u64 *d_runs = nullptr;         size_t cap_runs = 0;      // run-length encoded hit lists (classify_batch_runs)
+    u64 *d_run_pos = nullptr;      size_t cap_run_pos = 0;
+    u32 *d_nruns = nullptr;        size_t cap_nruns = 0;
     unsigned long long *d_defer_cnt = nullptr;
 };
 
@@ -523,6 +526,9 @@ void bns_b200_close(bns_b200_t *ctx) {
         if(s.d_kmers) cudaFree(s.d_kmers);
         if(s.d_out_offsets) cudaFree(s.d_out_offsets);
         if(s.d_defer) cudaFree(s.d_defer);
+        if(s.d_runs) cudaFree(s.d_runs);
+        if(s.d_run_pos) cudaFree(s.d_run_pos);
+        if(s.d_nruns) cudaFree(s.d_nruns);
         if(s.d_defer_cnt) cudaFree(s.d_defer_cnt);
         if(s.st) cudaStreamDestroy(s.st);
     }
@@ -1207,6 +1213,107 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         slot_i = (slot_i + 1) % N_SLOTS;
     }
     for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st));
+    u32 status = 0;
+    CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
+    return check_status(ctx, status & 10u);
+}
+
+// classify_seqs with the hit lists run-length encoded on the device. Chunks are pipelined over the stream slots like
+// classify_batch_ex; a chunk's runs are fetched (their count is only known once its kernels are done) while the next chunk's
+// copies and kernels are already queued.
+int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                                 uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
+                                 uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,
+                                 uint64_t *n_runs_total_out) {
+    if(!ctx || !offsets || !taxon_out || !n_hit_out || !run_pos_out || !n_runs_out || !n_runs_total_out || (runs_cap && !runs_out))
+        return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = classify_ready(ctx);
+    if(rc != BNS_OK) return rc;
+    *n_runs_total_out = 0;
+    const u32 mates = paired ? 2 : 1;
+    const u64 n_rec_total = n_reads / mates;
+    if(!n_rec_total) return BNS_OK;
+    CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
+    CK(cudaStreamSynchronize(ctx->slots[0].st));
+    struct Pending { bool live = false; u64 q0 = 0, nq = 0; } pend[N_SLOTS];
+    u64 used = 0;
+    std::vector<u64> h_toffs;
+    // fetch the runs of the chunk a slot holds: count first, then exactly that many entries
+    auto finalize = [&](int si) -> int {
+        Pending &pd = pend[si];
+        if(!pd.live) return BNS_OK;
+        pd.live = false;
+        Slot &s = ctx->slots[si];
+        unsigned long long total = 0;
+        CK(cudaMemcpyAsync(&total, s.d_defer_cnt, sizeof total, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+        if(used + total > runs_cap) return ctx->fail(BNS_E_CAPACITY, "the run buffer holds %llu entries, more were produced", (unsigned long long)runs_cap);
+        if(total) CK(cudaMemcpyAsync(runs_out + used, s.d_runs, total * 8, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(run_pos_out + pd.q0, s.d_run_pos, pd.nq * 8, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(n_runs_out + pd.q0, s.d_nruns, pd.nq * 4, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+        for(u64 r = 0; r < pd.nq; ++r) run_pos_out[pd.q0 + r] += used;      // chunk-relative -> position in runs_out
+        ctx->stats.d2h_bytes += total * 8 + pd.nq * 12;
+        used += total;
+        return BNS_OK;
+    };
+    int slot_i = 0;
+    u64 q0 = 0;
+    while(q0 < n_rec_total) {
+        u64 q1 = q0;
+        while(q1 < n_rec_total && (q1 - q0) * mates < CHUNK_READS &&
+              (q1 == q0 || offsets[(q1 + 1) * mates] - offsets[q0 * mates] <= CHUNK_BASES)) ++q1;
+        const u64 r0 = q0 * mates, r1 = q1 * mates, nr = r1 - r0, nq = q1 - q0;
+        const u64 nb = offsets[r1] - offsets[r0];
+        rc = finalize(slot_i);                                             // the chunk this slot carried three chunks ago
+        if(rc != BNS_OK) return rc;
+        Slot &s = ctx->slots[slot_i];
+        CK(cudaStreamSynchronize(s.st));
+        // hit-list windows of the chunk on the device: one slot per k-mer position plus two, like the reference's vector
+        h_toffs.resize(nq + 1);
+        h_toffs[0] = 0;
+        for(u64 q = 0; q < nq; ++q) h_toffs[q + 1] = h_toffs[q] + (offsets[(q0 + q + 1) * mates] - offsets[(q0 + q) * mates]) + 2;
+        const u64 nt = h_toffs[nq];
+        rc = ensure(s.d_bases, s.cap_bases, nb + 16);
+        if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 4 * nq);
+        if(rc == BNS_OK) rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_runs, s.cap_runs, nt + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_run_pos, s.cap_run_pos, nq);
+        if(rc == BNS_OK) rc = ensure(s.d_nruns, s.cap_nruns, nq);
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, true, mate1_kmers_out != nullptr, true);
+        CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));     // the run counter of this chunk
+        CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        CK(cudaMemcpyAsync(s.d_taxa_offsets, h_toffs.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        CK(cudaStreamSynchronize(s.st));                                   // h_toffs is reused by the next chunk
+        int nl = 1;
+        CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
+                           table_view(ctx), tax_view(ctx), s.d_out, s.d_out + nq, s.d_out + 2 * nq, s.d_taxa, s.d_taxa_offsets,
+                           mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status,
+                           nullptr, nullptr, &nl));
+        CK(launch_rle(s.st, s.d_taxa, s.d_taxa_offsets, s.d_out + nq, nq, s.d_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns));
+        ctx->stats.kernel_launches += nl + 1;
+        CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(mate1_kmers_out) CK(cudaMemcpyAsync(mate1_kmers_out + q0, s.d_out + 3 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        ctx->stats.h2d_bytes += nb + 8 * (nr + 1) + 8 * (nq + 1);
+        ctx->stats.d2h_bytes += nq * 4 * (2 + (n_missing_out != nullptr) + (mate1_kmers_out != nullptr));
+        ctx->stats.reads_processed += nr;
+        ctx->stats.bases_processed += nb;
+        pend[slot_i].live = true; pend[slot_i].q0 = q0; pend[slot_i].nq = nq;
+        q0 = q1;
+        slot_i = (slot_i + 1) % N_SLOTS;
+    }
+    for(int i = 0; i < N_SLOTS; ++i) {                                      // in chunk order: positions in runs_out follow the records
+        rc = finalize((slot_i + i) % N_SLOTS);
+        if(rc != BNS_OK) return rc;
+    }
+    *n_runs_total_out = used;
     u32 status = 0;
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
     return check_status(ctx, status & 10u);

@@ -1000,6 +1000,43 @@ __global__ void bns_dump_kernel(const u64 *__restrict__ slots, u64 n_buckets, Ta
     if(at < cap) { keys_out[at] = key; vals_out[at] = dict[(u32)v & ((1u << fmt.flag_shift()) - 1)]; }
 }
 
+// Run-length encoding of the ordered per-k-mer hit list of each record (what append_taxa_runs prints, classifier.h:46-61):
+// one thread per record counts its runs, reserves that many entries of the chunk's run buffer with one atomic per warp
+// and writes (taxid << 32 | run length) words. The verbose output then costs 8 bytes per RUN over PCIe instead of 4 bytes
+// per k-mer window slot.
+__global__ void bns_rle_kernel(const u32 *__restrict__ taxa, const u64 *__restrict__ taxa_offsets, const u32 *__restrict__ nhit,
+                               u64 n_records, u64 *__restrict__ runs, unsigned long long *__restrict__ total,
+                               u64 *__restrict__ run_pos, u32 *__restrict__ n_runs) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
+    u32 n = 0, nr = 0;
+    const u32 *t = nullptr;
+    if(r < n_records) {
+        n = nhit[r];
+        t = taxa + taxa_offsets[r];
+        for(u32 i = 0; i < n; ++i) nr += (i == 0 || t[i] != t[i - 1]);
+    }
+    // one reservation per warp
+    u32 incl = nr;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) { const u32 y = __shfl_up_sync(FULL, incl, d); if(lane >= (u32)d) incl += y; }
+    const u32 wtot = __shfl_sync(FULL, incl, 31);
+    unsigned long long base = 0;
+    if(lane == 31 && wtot) base = atomicAdd(total, (unsigned long long)wtot);
+    base = __shfl_sync(FULL, base, 31);
+    if(r >= n_records) return;
+    u64 at = base + (incl - nr);
+    run_pos[r] = at;
+    n_runs[r] = nr;
+    u32 last = 0, run = 0;
+    for(u32 i = 0; i < n; ++i) {
+        const u32 v = t[i];
+        if(i && v != last) { runs[at++] = ((u64)last << 32) | run; run = 0; }
+        last = v; ++run;
+    }
+    if(n) runs[at] = ((u64)last << 32) | run;
+}
+
 // independent 32-byte loads at uniformly random buckets: the random-access ceiling the lookup is measured against
 __global__ void bns_gather_kernel(const u64 *__restrict__ slots, u32 b, u64 n_loads, u64 seed,
                                   unsigned long long *__restrict__ sink_out) {
@@ -1224,6 +1261,12 @@ cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u3
                            const uint16_t *counts, const u64 *offsets, u64 n_lists, u32 *taxon_out, u32 *status) {
     const size_t smem = WARPS_PER_CTA * warp_smem_bytes(0, true);
     bns_resolve_kernel<<<grid, WARPS_PER_CTA * 32, smem, st>>>(X, values, n_values, taxa, counts, offsets, n_lists, taxon_out, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_rle(cudaStream_t st, const u32 *taxa, const u64 *taxa_offsets, const u32 *nhit, u64 n_records, u64 *runs,
+                       unsigned long long *total, u64 *run_pos, u32 *n_runs) {
+    if(!n_records) return cudaSuccess;
+    bns_rle_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(taxa, taxa_offsets, nhit, n_records, runs, total, run_pos, n_runs);
     return cudaGetLastError();
 }
 cudaError_t launch_gather(int grid, cudaStream_t st, const u64 *slots, u32 b, u64 n_loads, u64 seed, unsigned long long *sink) {

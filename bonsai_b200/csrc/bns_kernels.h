@@ -45,6 +45,8 @@ cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, 
 cudaError_t launch_sectors(cudaStream_t st, const TableView &T, const u64 *keys, u64 n, unsigned long long *total);
 cudaError_t launch_resolve(int grid, cudaStream_t st, const TaxView &X, const u32 *values, u32 n_values, const u32 *taxa,
                            const uint16_t *counts, const u64 *offsets, u64 n_lists, u32 *taxon_out, u32 *status);
+cudaError_t launch_rle(cudaStream_t st, const u32 *taxa, const u64 *taxa_offsets, const u32 *nhit, u64 n_records, u64 *runs,
+                       unsigned long long *total, u64 *run_pos, u32 *n_runs);
 cudaError_t launch_gather(int grid, cudaStream_t st, const u64 *slots, u32 b, u64 n_loads, u64 seed, unsigned long long *sink);
 
 }  // namespace bns

@@ -42,12 +42,21 @@ static int classify_main(int argc, char *argv[]) {
     }
     if(argc - optind < 3) return classify_usage(argv[0]);
     try {
+        const bool verbose = std::getenv("BNS_B200_VERBOSE") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         Database db(argv[optind]);
+        const double t1 = now();
         // bin/bonsai.cpp:152: always score::Lex with window = k, whatever the DB was minimised with
         Classifier c(db, db.s_, (u8)db.k_, (u16)db.k_, num_threads, emit_all, emit_fastq, emit_kraken, canonicalize);
+        const double t2 = now();
         std::unique_ptr<TaxMap> taxmap(build_parent_map(argv[optind + 1]));
         const char *fq2 = (argc - optind >= 4) ? argv[optind + 3] : nullptr;
+        const double t3 = now();
         process_dataset(c, taxmap.get(), argv[optind + 2], fq2, ofp, (unsigned)chunk_size, (unsigned)per_set);
+        if(verbose)
+            std::fprintf(stderr, "[bonsai classify] database file %.2f s, classifier (device open + table load) %.2f s, taxonomy %.2f s, "
+                         "dataset %.2f s\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
         std::fprintf(stderr, "Successfully finished classify_main. classified %" PRIu64 ", unclassified %" PRIu64 "\n",
                      c.n_classified(), c.n_unclassified());
     } catch(const std::exception &e) {

@@ -167,6 +167,14 @@ int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *
 int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                                uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
                                uint32_t *taxa_out, const uint64_t *taxa_offsets, uint32_t *mate1_kmers_out);
+/* The ordered hit list run-length encoded on the device (what the Kraken-style run lists print, classifier.h:46-61):
+ * record r's runs are runs_out[run_pos_out[r] .. + n_runs_out[r]), each (taxid << 32 | run length), in k-mer order.
+ * runs_cap entries are available in runs_out (BNS_E_CAPACITY if more were produced: the number of hits is an upper
+ * bound); *n_runs_total_out receives the number written. 8 bytes per run cross PCIe instead of 4 per window slot. */
+int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
+                                 uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
+                                 uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,
+                                 uint64_t *n_runs_total_out);
 /* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). */
 int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
                              uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cinttypes>
 #include <cstdint>
 #include <cstdio>
@@ -27,6 +28,9 @@
 #include <thread>
 #include <stdexcept>
 #include <string>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
 
@@ -448,7 +452,11 @@ struct ClassifierGeneric {
 using Classifier = ClassifierGeneric<score::Lex>;
 
 namespace detail {
-struct ReadView { const char *name, *seq, *qual; int l_seq; };          // what the emitters need of a bseq1_t
+struct ReadView {                                                     // what the emitters need of a bseq1_t
+    const char *name, *seq, *qual; int l_seq;
+    int l_name = -1;                                                  // < 0: name is NUL-terminated
+    void put_name(std::string &s) const { if(l_name < 0) s += name; else s.append(name, (size_t)l_name); }
+};
 inline void put_u(std::string &s, u32 x) { char b[16]; s.append(b, std::snprintf(b, sizeof b, "%u", x)); }
 inline void put_i(std::string &s, long x) { char b[32]; s.append(b, std::snprintf(b, sizeof b, "%ld", x)); }
 inline void append_taxa_run(tax_t last, u32 run, std::string &s) {                // classifier.h:30-43
@@ -466,33 +474,41 @@ inline void append_taxa_runs(tax_t taxon, const tax_t *taxa, u32 n, std::string 
         s.back() = '\n';
     } else s.append("0:0\n", 4);
 }
+// the same line from run-length encoded hits, (taxid << 32 | run length) words in k-mer order (bns_b200_classify_batch_runs)
+inline void append_taxa_runs_rle(tax_t taxon, const u64 *runs, u32 n_runs, std::string &s) {
+    if(taxon) {
+        for(u32 i = 0; i != n_runs; ++i) append_taxa_run((tax_t)(runs[i] >> 32), (u32)runs[i], s);
+        s.back() = '\n';
+    } else s.append("0:0\n", 4);
+}
 inline void append_counts(u32 count, char ch, std::string &s) {                   // :63-70
     if(count) { s.push_back(ch); s.push_back(':'); put_u(s, count); s.push_back('\t'); }
 }
 inline void append_kraken_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
-                                         const ReadView &bs, std::string &s) {     // :112-129
+                                         const ReadView &bs, std::string &s, const u64 *runs = nullptr, u32 n_runs = 0) {     // :112-129
     s.push_back(taxon ? 'C' : 'U'); s.push_back('\t');
-    s += bs.name; s.push_back('\t');
+    bs.put_name(s); s.push_back('\t');
     put_u(s, taxon); s.push_back('\t');
     put_i(s, bs.l_seq); s.push_back('\t');
     append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
-    append_taxa_runs(taxon, taxa, ntaxa, s);
+    if(runs) append_taxa_runs_rle(taxon, runs, n_runs, s); else append_taxa_runs(taxon, taxa, ntaxa, s);
 }
 inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxon, u32 ambig, u32 missing,
-                                        const ReadView *bs, std::string &s, int verbose, int is_paired) {   // :72-108
-    s += bs->name; s.push_back(' ');
+                                        const ReadView *bs, std::string &s, int verbose, int is_paired,
+                                        const u64 *runs = nullptr, u32 n_runs = 0) {   // :72-108
+    bs->put_name(s); s.push_back(' ');
     const size_t cms = s.size();
     s.push_back(taxon == 0 ? 'U' : 'C'); s.push_back('\t');
     put_u(s, taxon); s.push_back('\t');
     put_i(s, bs->l_seq); s.push_back('\t');
     append_counts(missing, 'M', s); append_counts(ambig, 'A', s);
-    if(verbose) append_taxa_runs(taxon, taxa, ntaxa, s); else s.back() = '\n';
+    if(verbose) { if(runs) append_taxa_runs_rle(taxon, runs, n_runs, s); else append_taxa_runs(taxon, taxa, ntaxa, s); } else s.back() = '\n';
     const std::string cm = s.substr(cms);      // the reference keeps raw pointers here and breaks on realloc
     s.append(bs->seq, bs->l_seq); s.append("\n+\n", 3);
     s.append(bs->qual ? bs->qual : bs->seq, bs->l_seq); s.push_back('\n');
     if(is_paired) {
         const ReadView *b2 = bs + 1;
-        s += b2->name; s.push_back(' ');
+        b2->put_name(s); s.push_back(' ');
         s += cm; s.push_back('\n');
         s.append(b2->seq, b2->l_seq); s.append("\n+\n", 3);
         s.append(b2->qual ? b2->qual : b2->seq, b2->l_seq); s.push_back('\n');
@@ -509,16 +525,27 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
     // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
     const bool need_taxa = (c.output_flag_ & KRAKEN) != 0;
-    std::vector<u64> toffs(1, 0);
-    if(need_taxa) {
-        toffs.reserve(nrec + 1);
-        for(unsigned r = 0; r < nrec; ++r) toffs.push_back(toffs.back() + (offs[(r + 1) * inc] - offs[r * inc]) + 2);
-    }
-    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(is_paired ? nrec : 0), taxa(need_taxa ? toffs.back() + 1 : 0);
+    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(is_paired ? nrec : 0), nruns(need_taxa ? nrec : 0);
+    std::vector<u64> run_pos(need_taxa ? nrec : 0);
+    std::unique_ptr<u64[]> runs;
     bns_b200_t *h = c.h_->h;
-    check(h, bns_b200_classify_batch_ex(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
-                                        need_taxa ? taxa.data() : nullptr, need_taxa ? toffs.data() : nullptr,
-                                        is_paired ? mate1.data() : nullptr), "bns_b200_classify_batch");
+    if(need_taxa) {
+        // run lists: encoded on the device, 8 bytes per run back instead of 4 per k-mer window slot. The number of runs is
+        // not known beforehand: a buffer for a few runs per record first, one for every possible hit if that was too small.
+        u64 windows = 0;
+        for(unsigned r = 0; r < nrec; ++r) windows += (offs[(r + 1) * inc] - offs[r * inc]) + 2;
+        u64 cap = std::min<u64>(windows, (u64)nrec * 8 + 4096), total = 0;
+        for(;;) {
+            runs.reset(new u64[cap ? cap : 1]);
+            const int rc = bns_b200_classify_batch_runs(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
+                                                        is_paired ? mate1.data() : nullptr, runs.get(), cap, run_pos.data(), nruns.data(), &total);
+            if(rc == BNS_E_CAPACITY && cap < windows) { cap = windows; continue; }
+            check(h, rc, "bns_b200_classify_batch_runs");
+            break;
+        }
+    } else
+        check(h, bns_b200_classify_batch_ex(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
+                                            nullptr, nullptr, is_paired ? mate1.data() : nullptr), "bns_b200_classify_batch");
     const u32 comb = c.sp_.c_;
     // classify_seq's epilogue (text) per record. The reference formats on its worker threads (-p, kt_for_helper,
     // classifier.h:254-266); here -p threads format contiguous slices of the batch and the slices are joined in order.
@@ -529,11 +556,12 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
             u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
             if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
             if(c.get_emit_all() || taxon[r]) {
-                const tax_t *tx = need_taxa ? taxa.data() + toffs[r] : nullptr;
+                const u64 *rn = need_taxa ? runs.get() + run_pos[r] : nullptr;
+                const u32 nrn = need_taxa ? nruns[r] : 0;
                 if(c.output_flag_ & FASTQ)
-                    append_fastq_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], b, out, c.get_emit_kraken(), is_paired);
+                    append_fastq_classification(nullptr, nhit[r], taxon[r], ambig, nmiss[r], b, out, c.get_emit_kraken(), is_paired, rn, nrn);
                 else if(c.output_flag_ & KRAKEN)
-                    append_kraken_classification(tx, nhit[r], taxon[r], ambig, nmiss[r], *b, out);
+                    append_kraken_classification(nullptr, nhit[r], taxon[r], ambig, nmiss[r], *b, out, rn, nrn);
             }
         }
     };
@@ -547,6 +575,8 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     for(auto &part : parts) cks += part;
 }
 
+// one record of a mapped plain file (parallel ingest, below): offsets into the mapping
+struct RecRef { u64 name_off, seq_off, qual_off; u32 name_len, seq_len; };
 // A batch parsed straight into PINNED host memory (bns_b200_host_alloc): the library DMAs from it without staging.
 struct PinnedBatch {
     char *bases = nullptr; size_t cap_bases = 0, n_bases = 0;
@@ -554,6 +584,8 @@ struct PinnedBatch {
     std::vector<std::string> names, quals;
     std::vector<char> has_qual;
     bool keep_qual = true;             // qualities are only printed by the FASTQ-style output
+    std::vector<RecRef> refs;   // parallel-ingest batches: names / qualities stay in the file mapping `map`
+    const char *map = nullptr;
     PinnedBatch() = default;
     PinnedBatch(const PinnedBatch &) = delete;
     ~PinnedBatch() { bns_b200_host_free(bases); bns_b200_host_free(offs); }
@@ -566,7 +598,7 @@ struct PinnedBatch {
         bns_b200_host_free(p);
         p = (T *)np; cap = ncap;
     }
-    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); }
+    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = nullptr; }
     void reserve(size_t bases_hint) {                   // pinned allocations are slow: size the ring once per dataset
         grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 4 + (1 << 16));
         grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 32 + 1024);
@@ -584,6 +616,158 @@ struct PinnedBatch {
         if(keep_qual) quals.push_back(k->qual); else quals.emplace_back();
     }
 };
+// ---- parallel ingest of plain (uncompressed) files in the simple form ---------------------------------------------
+// kseq is a byte-at-a-time state machine: ~2 M reads/s on one thread, two orders of magnitude below the GPU. A plain file
+// whose records are exactly 4 lines (FASTQ: @header / sequence / + / quality of the same length) or 2 lines (FASTA:
+// >header / sequence) is mapped and indexed by -p threads instead, window by window; names and qualities stay in the
+// mapping, sequences are copied into the pinned batch in parallel. kseq semantics are kept for such records (name = header
+// up to the first white space, trim_readno). Anything else (gzip, multi-line records, empty lines, CR) takes the kseq path.
+struct MappedFile {
+    const char *p = nullptr; size_t n = 0; int fd = -1;
+    explicit MappedFile(const char *path) {
+        fd = ::open(path, O_RDONLY);
+        if(fd < 0) return;
+        struct stat st;
+        if(::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 4) { ::close(fd); fd = -1; return; }
+        void *m = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if(m == MAP_FAILED) { ::close(fd); fd = -1; return; }
+        p = (const char *)m; n = (size_t)st.st_size;
+        ::madvise(m, n, MADV_SEQUENTIAL);
+    }
+    MappedFile(const MappedFile &) = delete;
+    ~MappedFile() { if(p) ::munmap((void *)p, n); if(fd >= 0) ::close(fd); }
+    bool simple_candidate() const { return p && (p[0] == '@' || p[0] == '>') && !((unsigned char)p[0] == 0x1f && (unsigned char)p[1] == 0x8b); }
+};
+// end of the line starting at x (offset of its newline, or n)
+inline size_t line_end(const char *p, size_t x, size_t n) {
+    const void *q = x < n ? std::memchr(p + x, '\n', n - x) : nullptr;
+    return q ? (size_t)((const char *)q - p) : n;
+}
+// first record start at or after x (x = 0 or any offset): a line starting with the header character whose record parses
+inline size_t next_record_start(const char *p, size_t x, size_t n, bool fastq) {
+    size_t ls = x;
+    if(x) { ls = line_end(p, x - 1, n) + 1; }                              // the line start at or after x
+    for(int tries = 0; ls < n && tries < 8; ++tries) {
+        if(p[ls] == (fastq ? '@' : '>')) {
+            if(!fastq) return ls;
+            const size_t e1 = line_end(p, ls, n), e2 = line_end(p, e1 + 1, n);
+            if(e2 + 1 < n && p[e2 + 1] == '+') {
+                const size_t e3 = line_end(p, e2 + 1, n), e4 = line_end(p, e3 + 1, n);
+                if(e4 - (e3 + 1) == e2 - (e1 + 1)) return ls;
+            }
+        }
+        ls = line_end(p, ls, n) + 1;
+    }
+    return n;                                                              // none found nearby: the caller gives up the fast path
+}
+// records of [lo, hi) (both record starts or n). Returns false on anything outside the simple form.
+inline bool index_range(const char *p, size_t lo, size_t hi, size_t n, bool fastq, std::vector<RecRef> &out) {
+    size_t x = lo;
+    while(x < hi) {
+        if(p[x] != (fastq ? '@' : '>')) return false;
+        const size_t e1 = line_end(p, x, n);
+        if(e1 >= n) return false;
+        size_t ne = x + 1;
+        while(ne < e1 && !std::isspace((unsigned char)p[ne])) ++ne;
+        RecRef r;
+        r.name_off = x + 1; r.name_len = (u32)(ne - (x + 1));
+        if(r.name_len > 2 && p[ne - 2] == '/' && std::isdigit((unsigned char)p[ne - 1])) r.name_len -= 2;   // trim_readno
+        const size_t e2 = line_end(p, e1 + 1, n);
+        if(e2 - (e1 + 1) > 0x7fffffffull) return false;
+        r.seq_off = e1 + 1; r.seq_len = (u32)(e2 - (e1 + 1));
+        if(r.seq_len == 0 || std::memchr(p + x, '\r', e2 - x)) return false;
+        if(std::memchr(p + r.seq_off, '>', r.seq_len) || std::memchr(p + r.seq_off, '@', r.seq_len) || std::memchr(p + r.seq_off, '+', r.seq_len))
+            return false;                                                  // kseq would end the sequence there
+        r.qual_off = ~0ull;
+        size_t next = e2 + 1;
+        if(fastq) {
+            if(e2 + 1 >= n || p[e2 + 1] != '+') return false;
+            const size_t e3 = line_end(p, e2 + 1, n);
+            if(e3 >= n) return false;
+            const size_t e4 = line_end(p, e3 + 1, n);
+            if(e4 - (e3 + 1) != r.seq_len) return false;
+            r.qual_off = e3 + 1;
+            next = e4 + 1;
+        }
+        out.push_back(r);
+        x = next;
+    }
+    return x == hi || (x == n + 1 && hi == n);                            // a last line without a newline ends at n
+}
+struct SimpleFile {
+    MappedFile map;
+    bool fastq = false, ok = false;
+    size_t cursor = 0;                     // next unindexed byte (a record start)
+    std::vector<RecRef> recs;              // the current window
+    size_t next_rec = 0;
+    unsigned nthreads;
+    size_t window;
+    SimpleFile(const char *path, unsigned nt) : map(path), nthreads(std::max(1u, nt)) {
+        const char *e = std::getenv("BNS_B200_FASTQ_WINDOW");              // bytes per indexing window (tests use a small one)
+        window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)1 << 30);
+        if(!map.simple_candidate()) return;
+        fastq = map.p[0] == '@';
+        ok = true;
+    }
+    // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
+    // kseq must take over)
+    bool refill() {
+        recs.clear(); next_rec = 0;
+        if(!ok || cursor >= map.n) return false;
+        const char *p = map.p;
+        const size_t n = map.n, lo = cursor;
+        size_t hi = n;
+        if(n - lo > window) { hi = next_record_start(p, lo + window, n, fastq); }
+        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, (hi - lo) / (1u << 20) + 1));
+        std::vector<size_t> cut(T + 1);
+        cut[0] = lo; cut[T] = hi;
+        for(unsigned t = 1; t < T; ++t) cut[t] = next_record_start(p, lo + (hi - lo) / T * t, n, fastq);
+        for(unsigned t = 1; t <= T; ++t) if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+        std::vector<std::vector<RecRef>> part(T);
+        std::vector<char> good(T, 1);
+        std::vector<std::thread> pool;
+        for(unsigned t = 0; t < T; ++t)
+            pool.emplace_back([&, t] { good[t] = index_range(p, cut[t], cut[t + 1], n, fastq, part[t]); });
+        for(auto &th : pool) th.join();
+        for(unsigned t = 0; t < T; ++t) {
+            if(!good[t]) { ok = false; recs.clear(); return false; }     // leave `cursor` at the window start for kseq
+            recs.insert(recs.end(), part[t].begin(), part[t].end());
+        }
+        cursor = hi;
+        return !recs.empty();
+    }
+};
+// the next batch out of the index: records until >= chunk_size bases and an even count (bseq_read's rule)
+inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f) {
+    b.clear();
+    b.refs.clear();
+    b.map = f.map.p;
+    u64 size = 0;
+    for(;;) {
+        if(f.next_rec >= f.recs.size() && !f.refill()) break;
+        const RecRef &r = f.recs[f.next_rec++];
+        b.refs.push_back(r);
+        size += r.seq_len;
+        if((long)size >= chunk_size && (b.refs.size() & 1) == 0) break;
+    }
+    const size_t n = b.refs.size();
+    if(!n) return false;
+    PinnedBatch::grow(b.bases, b.cap_bases, 0, size + 16);
+    PinnedBatch::grow(b.offs, b.cap_offs, 0, n + 2);
+    b.offs[0] = 0;
+    for(size_t i = 0; i < n; ++i) b.offs[i + 1] = b.offs[i] + b.refs[i].seq_len;
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(f.nthreads, n / 8192 + 1));
+    auto copy = [&](size_t lo, size_t hi) { for(size_t i = lo; i < hi; ++i) std::memcpy(b.bases + b.offs[i], f.map.p + b.refs[i].seq_off, b.refs[i].seq_len); };
+    if(T == 1) copy(0, n);
+    else {
+        std::vector<std::thread> pool;
+        for(unsigned t = 0; t < T; ++t) pool.emplace_back(copy, n * t / T, n * (t + 1) / T);
+        for(auto &th : pool) th.join();
+    }
+    b.n = n; b.n_bases = size;
+    return true;
+}
+
 // bseq_read (kseq_declare.h:112-145) into a pinned batch: records until >= chunk_size bases and an even count
 inline bool read_pinned(int chunk_size, PinnedBatch &b, KSeq *ks, KSeq *ks2) {
     b.clear();
@@ -627,6 +811,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     detail::KSeq ks1(fq1);
     std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
+    // single plain files in the simple 4-line / 2-line form are indexed by the -p threads (detail::SimpleFile)
+    std::unique_ptr<detail::SimpleFile> simple(fq2 ? nullptr : new detail::SimpleFile(fq1, c.nt_));
+    if(simple && !simple->ok) simple.reset();
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     constexpr int NB = 3;
     detail::PinnedBatch ring[NB];
@@ -639,7 +826,15 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
         try {
             for(int i = 0;; i = (i + 1) % NB) {
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
-                const bool got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
+                bool got = false;
+                if(simple) {
+                    got = detail::fill_pinned((int)chunk_size, ring[i], *simple);
+                    if(!got && !simple->ok && simple->cursor < simple->map.n) {      // left the simple form: kseq from there on
+                        gzseek(ks1.fp, (z_off_t)simple->cursor, SEEK_SET);
+                        simple.reset();
+                    }
+                }
+                if(!got && !simple) got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
                 { std::lock_guard<std::mutex> lk(mu); state[i] = got ? 1 : 2; }
                 cv.notify_all();
                 if(!got) return;
@@ -665,19 +860,38 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     bool first = true;
     std::string failure;
     std::vector<detail::ReadView> views;
+    const bool verbose = std::getenv("BNS_B200_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_wait = 0, t_classify = 0, t_write = 0;
+    size_t n_batches = 0;
     for(int i = 0;; i = (i + 1) % NB) {
+        const double tw = now();
         { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] != 0; }); }
+        t_wait += now() - tw;
         if(state[i] == 2) break;
         detail::PinnedBatch &b = ring[i];
+        ++n_batches;
         try {
             if(failure.empty()) {
                 views.resize(b.n);
+                if(b.map)
+                    for(size_t r = 0; r < b.n; ++r) {
+                        const detail::RecRef &ref = b.refs[r];
+                        views[r] = detail::ReadView{b.map + ref.name_off, b.bases + b.offs[r],
+                                                    b.keep_qual && ref.qual_off != ~0ull ? b.map + ref.qual_off : nullptr,
+                                                    (int)ref.seq_len, (int)ref.name_len};
+                    }
+                else
                 for(size_t r = 0; r < b.n; ++r)
                     views[r] = detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
                                                 (int)(b.offs[r + 1] - b.offs[r])};
+                const double tc = now();
                 detail::classify_views(c, b.bases, b.offs, views.data(), (unsigned)b.n, is_paired, cks);
+                const double tf = now();
+                t_classify += tf - tc;
                 if(first) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
                 if(cks.size() > (1ull << 16)) flush();
+                t_write += now() - tf;
             }
         } catch(const std::exception &e) { failure = e.what(); }
         { std::lock_guard<std::mutex> lk(mu); state[i] = 0; }
@@ -688,6 +902,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!failure.empty()) BNS_RUNTIME_ERROR(failure);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
     flush();
+    if(verbose)
+        std::fprintf(stderr, "[process_dataset] %zu batches: waiting for the reader %.2f s, classify + format %.2f s, write %.2f s\n",
+                     n_batches, t_wait, t_classify, t_write);
 }
 
 }  // namespace bns

@@ -83,3 +83,17 @@ def test_hist(cli, tmp_path):
     u, c = np.unique(vals, return_counts=True)
     assert sorted(rows) == sorted(zip(u.tolist(), c.tolist()))
     assert [r[1] for r in rows] == sorted(r[1] for r in rows)
+
+
+def test_parallel_ingest_index_matches_kseq(tmp_path):
+    """detail::SimpleFile (parallel index of plain 4-line FASTQ / 2-line FASTA, hand-over to kseq elsewhere) yields the same
+    records as the kseq state machine: tests/host/ingest_index.cpp, host code only."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = str(tmp_path / "ingest_index")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "ingest_index.cpp")
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, src, "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 15, r.stdout

@@ -57,7 +57,7 @@ def test_build_matches_oracle(setup, oracle):
 
 
 @pytest.mark.parametrize("mode", ["kraken_all", "kraken_classified_only", "fastq_all", "fastq_kraken", "kraken_nocanon",
-                                  "kraken_all_p4", "fastq_all_p4"])
+                                  "kraken_all_p4", "fastq_all_p4", "kraken_all_plain_p4", "fastq_all_plain_p3"])
 def test_classify_text(setup, oracle, genomes, mode):
     g = genomes
     rng = np.random.default_rng(3)
@@ -76,13 +76,15 @@ def test_classify_text(setup, oracle, genomes, mode):
         seqs.append(s.decode())
         names.append("read%d/1" % i if i % 2 else "read%d" % i)
     quals = ["".join(chr(33 + (j * 7 + i) % 40) for j in range(len(s))) for i, s in enumerate(seqs)]
-    fq = setup["dir"] / ("reads_%s.fq.gz" % mode)
+    # *_plain_*: an uncompressed file goes through the parallel index (several small windows) instead of kseq
+    fq = setup["dir"] / ("reads_%s.fq%s" % (mode, "" if "_plain_" in mode else ".gz"))
     use_q = mode != "kraken_classified_only"
     write_fastq(fq, names, seqs, quals if use_q else None)
     flags = {"kraken_all": ["-a"], "kraken_classified_only": [], "fastq_all": ["-a", "-f", "-K"], "fastq_kraken": ["-a", "-f", "-k"],
              "kraken_nocanon": ["-a", "-C"],
              # one big chunk, four formatter threads (the lean kernel for the FASTQ-style output without run lists)
-             "kraken_all_p4": ["-a", "-p", "4"], "fastq_all_p4": ["-a", "-f", "-K", "-p", "4"]}[mode]
+             "kraken_all_p4": ["-a", "-p", "4"], "fastq_all_p4": ["-a", "-f", "-K", "-p", "4"],
+             "kraken_all_plain_p4": ["-a", "-p", "4"], "fastq_all_plain_p3": ["-a", "-f", "-K", "-p", "3"]}[mode]
     chunk = "100000000" if mode.endswith("_p4") else "20000"
     kw = {"kraken_all": dict(emit_all=True, emit_fastq=False, emit_kraken=True),
           "kraken_classified_only": dict(emit_all=False, emit_fastq=False, emit_kraken=True),
@@ -90,10 +92,12 @@ def test_classify_text(setup, oracle, genomes, mode):
           "fastq_kraken": dict(emit_all=True, emit_fastq=True, emit_kraken=True),
           "kraken_nocanon": dict(emit_all=True, emit_fastq=False, emit_kraken=True, canon=False),
           "kraken_all_p4": dict(emit_all=True, emit_fastq=False, emit_kraken=True),
-          "fastq_all_p4": dict(emit_all=True, emit_fastq=True, emit_kraken=False)}[mode]
+          "fastq_all_p4": dict(emit_all=True, emit_fastq=True, emit_kraken=False),
+          "kraken_all_plain_p4": dict(emit_all=True, emit_fastq=False, emit_kraken=True),
+          "fastq_all_plain_p3": dict(emit_all=True, emit_fastq=True, emit_kraken=False)}[mode]
     outp = setup["dir"] / ("out_%s.txt" % mode)
     r = subprocess.run([setup["cli"], "classify"] + flags + ["-c", chunk, "-o", str(outp), str(setup["db"]), str(setup["nodes"]), str(fq)],
-                       capture_output=True, text=True)
+                       capture_output=True, text=True, env=dict(os.environ, BNS_B200_FASTQ_WINDOW="60000"))
     assert r.returncode == 0, r.stderr
     bases, offs = po.pack_reads(seqs)
     trimmed = [n[:-2] if n.endswith("/1") else n for n in names]          # trim_readno

@@ -230,6 +230,27 @@ def test_classify_golden(capi, golden, gpu_dbs, reads2000, cname):
     assert st["kernel_launches"] > 0
 
 
+def test_classify_runs_match_hit_lists(capi, golden, gpu_dbs, reads2000):
+    """bns_b200_classify_batch_runs: the device-side run-length encoding of the ordered hit lists equals the encoding of
+    the lists bns_b200_classify_batch returns (single-end and paired), and too small a run buffer is reported."""
+    bases, offs, _ = reads2000
+    ctx = gpu_dbs("config1_lex_w31")
+    for paired in (False, True):
+        taxon, nhit, nmiss, lists = ctx.classify(bases, offs, paired=paired, want_taxa=True)
+        t2, h2, m2, runs = ctx.classify_runs(bases, offs, paired=paired)
+        assert np.array_equal(t2, taxon) and np.array_equal(h2, nhit) and np.array_equal(m2, nmiss)
+        for lst, rn in zip(lists, runs):
+            if lst.size == 0:
+                assert rn.shape[0] == 0
+                continue
+            cut = np.flatnonzero(np.diff(lst.astype(np.int64)) != 0) + 1
+            starts = np.concatenate([[0], cut])
+            lens = np.diff(np.concatenate([starts, [lst.size]]))
+            assert np.array_equal(rn[:, 0], lst[starts]) and np.array_equal(rn[:, 1], lens.astype(np.uint32))
+    with pytest.raises(capi.BnsError):
+        ctx.classify_runs(bases, offs, cap=10)
+
+
 def test_classify_phix_and_paired(capi, golden, gpu_dbs, reads2000, genomes):
     ctx = gpu_dbs("config1_lex_w31")
     pb, poff = po.pack_reads([bytes(genomes["phix"])])
