@@ -200,7 +200,11 @@ __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
                       u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status,
-                      u32 *__restrict__ defer_idx, unsigned long long *__restrict__ defer_cnt, u32 fixed_len, u64 fixed_base) {
+                      u32 *__restrict__ defer_idx, unsigned long long *__restrict__ defer_cnt, u32 fixed_len, u64 fixed_base,
+                      u32 mates, u32 *__restrict__ mate1_out) {
+    // n_records counts SEQUENCES here: a record is `mates` (1 or 2) consecutive sequences sharing one taxon counter
+    // (classify_seq encodes the second mate into the same counter, classifier.h:233-236); a batch of 32 sequences holds
+    // whole records. mate1_out: k-mers the first mate produced (classifier.h:232's first ambig_count term).
     // fixed_len != 0: every record has that many bases and record r starts at fixed_base + r * fixed_len; `offsets` is
     // not read (the host did not even copy it: 8 of the 158 bytes per 150 bp read that cross PCIe)
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
@@ -305,8 +309,13 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
         const u64 r0 = bt * RB;
         const u32 nrec = (u32)min((u64)RB, n_records - r0);
         const bool have_next_batch = bt + nwarps < n_batches;
-        u32 my_taxon = 0, my_hit = 0, my_miss = 0, my_def = 0;
+        u32 my_taxon = 0, my_hit = 0, my_miss = 0, my_def = 0, my_m1 = 0;
+        // ---- per-record state: linear::counter with its first key in registers --------------------------------------
+        u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
+        bool spilled = false, deferred = false;
+        const u32 msh = mates - 1;                                     // record of sequence j: j >> msh
         for(u32 j = 0; j < nrec; ++j) {
+            const bool first_mate = (j & msh) == 0, last_mate = (j & msh) == msh;
             // this record's first tile (requested one record ago) and, from the second record on, the next batch's offsets
             // (the newest group at j == 0 is the next batch's offsets, requested a moment ago: not needed yet)
             if(j == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else async_wait_all();
@@ -322,11 +331,9 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             }
             fetch_tile(xb, xl, tb ^ 1);
             async_commit();
-            // ---- per-record state: linear::counter with its first key in registers -----------------------------
-            u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
-            bool spilled = false;
-            bool deferred = false;
+            if(first_mate) { nd = 0; id0 = 0; cnt0 = 0; n_hit = 0; n_emit = 0; deferred = false; }
             if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
+            else if(deferred) {}                                       // the first mate already sent the record to the generic kernel
             else if((MODE == LEAN_K || MODE == LEAN_R) && L >= k && L - k + 1 > (u32)TILE) deferred = true;   // more than one tile of window elements
             else if(L >= c) {
                 const u32 npos = L - c + 1;
@@ -441,7 +448,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         if(MODE == LEAN_R && slow) {                         // only valid k-mers push: compact them (rare)
                             u32 tot;
                             u32 idx = warp_excl_scan(__popc(mask), lane, tot);
-                            uint4 *scratch = (uint4 *)S.ids;                 // TILE x 16 bytes: the distinct-taxon lists are idle here
+                            uint4 *scratch = (uint4 *)S.tin;                 // TILE x 16 bytes = tin + tout: only resolve() uses them (ids / cnt may hold mate 1's list)
 #pragma unroll
                             for(int i = 0; i < PPL; ++i)
                                 if(mask >> i & 1u) scratch[idx++] = make_uint4(e[i].w[0], e[i].w[1], e[i].w[NW - 2], e[i].w[NW - 1]);
@@ -622,8 +629,13 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     }
                 }
             }
+            if(first_mate && !last_mate) {                              // between the mates of a pair
+                if(lane == (j >> msh)) my_m1 = n_emit;
+                rb = xb; L = xl; tb ^= 1;
+                continue;
+            }
             if((MODE == LEAN_K || MODE == LEAN_R) && deferred) {                           // the generic kernel redoes this record from scratch
-                if(lane == 0) defer_idx[atomicAdd(defer_cnt, 1ull)] = (u32)(r0 + j);
+                if(lane == 0) defer_idx[atomicAdd(defer_cnt, 1ull)] = (u32)((r0 + j) >> msh);
                 nd = 0; n_hit = 0; n_emit = 0;
                 if(spilled) { spilled = false; sink.n_distinct = 0; sink.overflow = 0; }
             }
@@ -635,22 +647,26 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                 sink.n_distinct = 0; sink.overflow = 0;
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
-            if(lane == j) { my_taxon = taxon; my_def = deferred; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; } }
+            if(lane == (j >> msh)) { my_taxon = taxon; my_def = deferred; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; if(msh == 0) my_m1 = n_emit; } }
+            spilled = false;
             rb = xb; L = xl; tb ^= 1;
         }
         // ---- one coalesced store per output array for the batch ------------------------------------------------------
-        if(lane < nrec) {
-            taxon_out[r0 + lane] = my_taxon;
+        const u32 nout = nrec >> msh;                                  // records of the batch
+        const u64 o0 = r0 >> msh;
+        if(lane < nout) {
+            taxon_out[o0 + lane] = my_taxon;
             if(COUNTS) {
-                if(nhit_out) nhit_out[r0 + lane] = my_hit;
-                if(nmiss_out) nmiss_out[r0 + lane] = my_miss;
+                if(nhit_out) nhit_out[o0 + lane] = my_hit;
+                if(nmiss_out) nmiss_out[o0 + lane] = my_miss;
+                if(mate1_out) mate1_out[o0 + lane] = my_m1;
             }
         }
-        const u32 cls = __popc(__ballot_sync(FULL, lane < nrec && my_taxon != 0));
-        const u32 ndef = (MODE == LEAN_U || MODE == LEAN_S) ? 0u : __popc(__ballot_sync(FULL, lane < nrec && my_def != 0));
+        const u32 cls = __popc(__ballot_sync(FULL, lane < nout && my_taxon != 0));
+        const u32 ndef = (MODE == LEAN_U || MODE == LEAN_S) ? 0u : __popc(__ballot_sync(FULL, lane < nout && my_def != 0));
         if(lane == 0) {                                                // classified_[2] (classifier.h:138,238), once per batch
             atomicAdd(&counters[0], (unsigned long long)cls);
-            atomicAdd(&counters[1], (unsigned long long)(nrec - cls - ndef));
+            atomicAdd(&counters[1], (unsigned long long)(nout - cls - ndef));
         }
         pb ^= 1;
     }

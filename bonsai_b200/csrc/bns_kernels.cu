@@ -1101,7 +1101,8 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 #ifdef BNS_NO_LEAN
     return -1;
 #endif
-    if(mates != 1 || taxa || mate1) return -1;
+    (void)mate1;
+    if(mates > 2 || taxa) return -1;                                  // pairs share the batch machinery: two sequences per record
     if(P.family == FAM_U) return LEAN_U;
     const bool unspaced = P.c == P.k;
     if(!unspaced) {                                                   // spaced seed, window of one, comb inside the lane's 48-base window
@@ -1115,7 +1116,7 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     return -1;
 }
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                              unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64);
+                              unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64, u32, u32 *);
 static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
 template <int MODE, bool CANON, bool COUNTS, int KEY>
 static classify_u_fn pick_lean_k(u32 k, bool loc) {
@@ -1154,15 +1155,15 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     pl.loc = T.fmt.layout == LAYOUT_MINIMIZER;
     if(pl.loc && T.fmt.kt != P.k) pl.lean_mode = -1;
     pl.lean = pl.lean_mode >= 0;
-    pl.counts = counts;
+    pl.counts = counts || mates == 2 || mate1;                        // the pair bookkeeping lives in the COUNTS variants
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, counts, pl.loc);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
         pl.smem = lean_smem();
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, LEAN_WARPS * 32, pl.smem);
-        const u64 want = ((n_records + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;           // one batch per warp at least
+        const u64 want = ((n_records * mates + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;   // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
     }
     if(!pl.lean || pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R) { // the generic kernel: everything, or the deferred records
@@ -1188,15 +1189,15 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
-        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records, T, X, taxon_out, nhit_out, nmiss_out,
-                                                    counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base);
+        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,
+                                                    counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base, mates, mate1_out);
         cudaError_t e = cudaGetLastError();
         if(e != cudaSuccess || pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) return e;
         // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel
         // reads the count on the device and returns at once. Sized small: deferred records are rare and long.
         classify_fn g = pick_classify(P.family, false);
-        g<<<pl.gen_grid, WARPS_PER_CTA * 32, pl.gen_smem, st>>>(P, bases, offsets, n_records, 1u, total_bases, T, X, taxon_out,
-                                                               nhit_out, nmiss_out, nullptr, nullptr, nullptr, ring_cap, counters,
+        g<<<pl.gen_grid, WARPS_PER_CTA * 32, pl.gen_smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out,
+                                                               nhit_out, nmiss_out, nullptr, nullptr, mate1_out, ring_cap, counters,
                                                                status, defer_idx, defer_cnt);
         if(n_launched) *n_launched = 2;
         return cudaGetLastError();

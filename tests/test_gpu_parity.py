@@ -285,6 +285,12 @@ def test_classify_ragged_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, geno
     got = ctx.classify(b, o)
     for a, bb in zip(exp, got):
         assert np.array_equal(a, bb)
+    # the ragged reads as mate pairs (lean kernel, two sequences per record)
+    ne = ((offs.size - 1) // 2) * 2
+    expp = oracle.classify(db, toy_tax, bases[:int(offs[ne])], offs[:ne + 1], 31, 31, paired=True)
+    gotp = ctx.classify(bases[:int(offs[ne])], offs[:ne + 1], paired=True)
+    for a, bb in zip(expp, gotp):
+        assert np.array_equal(a, bb)
     # empty batch
     t, h, m = ctx.classify(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert t.size == 0
@@ -544,6 +550,14 @@ def test_classify_lean_windowed_vs_oracle(capi, oracle, dbcache, toy_tax, genome
         got = ctx.classify(b, o)                          # counts, no hit list: the lean kernel
         got_taxon_only, _, _ = ctx.classify(b, o, want_counts=False)
         full = ctx.classify(b, o, want_taxa=True)         # the generic kernel (ordered hit lists)
+        # the same reads as mate pairs (two sequences per record in the lean kernel; a deferred mate defers the pair)
+        ne = (len(reads) // 2) * 2
+        pb_, po_ = po.pack_reads(reads[:ne])
+        got_pair = ctx.classify(pb_, po_, paired=True)
+    exp_pair = oracle.classify(db, toy_tax, pb_, po_, k, w, None, cfg["score"], cfg["canon"], cfg["api"], cast_mode=cfg["cast"], paired=True)
+    for name, a, bb in zip(("taxon", "nhit", "nmiss"), exp_pair, got_pair):
+        bad = np.nonzero(a != bb)[0]
+        assert bad.size == 0, "paired %s differs for %d records, first %d: oracle %d gpu %d" % (name, bad.size, bad[0], a[bad[0]], bb[bad[0]])
     exp = oracle.classify(db, toy_tax, b, o, k, w, None, cfg["score"], cfg["canon"], cfg["api"], cast_mode=cfg["cast"])
     for name, a, bb in zip(("taxon", "nhit", "nmiss"), exp, got):
         bad = np.nonzero(a != bb)[0]
