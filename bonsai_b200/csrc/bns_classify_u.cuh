@@ -1,5 +1,6 @@
-// bns_classify_u.cuh -- the lean kernel for what `bonsai classify` always runs (bin/bonsai.cpp:152: k == w, no spaced
-// seed): single-end records, every (canonical) k-mer of the record looked up, taxon by resolve_tree, no ordered hit list.
+// bns_classify_u.cuh -- the lean kernel: what `bonsai classify` always runs (bin/bonsai.cpp:152: k == w, no spaced seed: every
+// (canonical) k-mer of the record looked up, taxon by resolve_tree) plus the windowed-minimizer and spaced-seed encoders,
+// for single-end records and mate pairs, without the ordered hit list.
 // Included by bns_kernels.cu after the shared building blocks (ClassifySink, probe_displaced, the TMA staging helpers).
 //
 // Same algorithm and table as bns_classify_kernel<FAM_U,false>; what differs is the bookkeeping around the k-mers, which
@@ -313,7 +314,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
         // ---- per-record state: linear::counter with its first key in registers --------------------------------------
         u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
         bool spilled = false, deferred = false;
-        const u32 msh = mates - 1;                                     // record of sequence j: j >> msh
+        const u32 msh = COUNTS ? mates - 1 : 0u;                       // record of sequence j: j >> msh (pairs always run a COUNTS variant)
         for(u32 j = 0; j < nrec; ++j) {
             const bool first_mate = (j & msh) == 0, last_mate = (j & msh) == msh;
             // this record's first tile (requested one record ago) and, from the second record on, the next batch's offsets
