@@ -3,18 +3,22 @@
 // for single-end records and mate pairs, without the ordered hit list.
 // Included by bns_kernels.cu after the shared building blocks (ClassifySink, probe_displaced, the TMA staging helpers).
 //
-// Same algorithm and table as bns_classify_kernel<FAM_U,false>; what differs is the bookkeeping around the k-mers, which
-// was two thirds of the instructions there (ncu, profiles/ncu_r01e_classify.txt):
-//   * a warp takes a BATCH of 32 consecutive records: their offsets come in with one coalesced load (prefetched a batch
-//     ahead), each record's (start, length) reaches the warp by shuffle, and the 32 results leave with one coalesced store
-//     per output array;
-//   * the 2-bit words of the staged tile go from the lanes that packed them to the lanes that need them by SHFL, not
-//     through shared memory;
+// Same algorithm and table as the generic stream kernel bns_classify_kernel; what differs is the bookkeeping around the
+// k-mers, which was two thirds of the instructions there (ncu, profiles/ncu_r01d_classify.txt vs ncu_r01g_classify.txt):
+//   * a warp takes a BATCH of 32 consecutive sequences: their offsets arrive in shared memory by cp.async one batch ahead
+//     (or are generated, for fixed-length batches), the first 8-byte blocks of the next sequence one sequence ahead, and
+//     the batch's results leave with one coalesced store per output array and one atomic pair;
+//   * bases are packed 8 per lane; the 2-bit words go from the lanes that packed them to the lanes that need them by SHFL,
+//     not through shared memory; the lane's four k-mers and their reverse complements come out of one 96-bit window;
 //   * everything is 32-bit: the bucket arrives as eight u32 (LDG.256), the bucket address is one IMAD.WIDE, tags are
 //     funnel shifts;
 //   * the first distinct taxon of a record and its count live in (warp-uniform) registers; shared memory is touched
 //     only by records with >= 2 distinct taxa (resolve_tree's real work) -- 78 % of the classified reads have one;
-//   * displaced-key probes (home bucket overflowed at build time, ~0.6 % of lookups) run in one warp-level loop.
+//   * displaced-key probes (home bucket overflowed at build time: the key's overflow flag is cleared there) run in one
+//     warp-level loop behind a one-vote conservative test;
+//   * window minima (LEAN_K / LEAN_R) are computed with shuffles only, on one 64-bit word per element where that is exact;
+//   * LAYOUT_MINIMIZER tables: the minimizers of all four k-mers of a lane come from 19 mixed 16-mers (8 computed, 11 by
+//     SHFL.DOWN) and 32-bit min chains.
 #pragma once
 
 namespace bns {
