@@ -151,7 +151,9 @@ def run_reference(args, spec):
         t0 = time.perf_counter()
         cpu.classify(db, T, probe_b, probe_o, c["k"], c["w"], c["gaps"], 0, c["canon"], c["api"], nthreads=nthreads)
         rate = 20000 / (time.perf_counter() - t0)
-    n = int(max(20000, min(args.reads, rate * 3.0, 4_000_000)))
+    # per-step sample: the whole --steps K --warmup W run should end within a few minutes whatever K is (~2 min of CPU work)
+    per_step_s = min(3.0, max(0.2, 120.0 / max(args.steps + args.warmup, 1)))
+    n = int(max(20000, min(args.reads, rate * per_step_s, 4_000_000)))
     parts, done = [], 0
     while done < n:                                   # generated in slices: the numpy generator is memory-hungry
         m = min(500_000, n - done)
