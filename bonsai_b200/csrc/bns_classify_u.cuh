@@ -544,10 +544,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             hb[i] = (u32)t.home; hh[i] = (u32)(t.tag >> 32); hl[i] = (u32)t.tag;
                         } else {
                             // mix64 (bns_device.cuh) on 32-bit halves
-                            u64 x = ((u64)xh << 32) | (xl ^ xh);
-                            x *= 0xd6e8feb86659fd93ull;
-                            x ^= x >> 32;
-                            x *= 0xd6e8feb86659fd93ull;
+                            const u64 x = (((u64)xh << 32) | xl) * 0xd6e8feb86659fd93ull;
                             hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
                         }
                         ld_bucket8(Pc.slots + ((u64)(LOC ? hb[i] : hh[i] >> Pc.idx_shift) << 5), w[i]);
