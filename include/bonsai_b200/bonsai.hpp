@@ -585,7 +585,8 @@ struct PinnedBatch {
     std::vector<char> has_qual;
     bool keep_qual = true;             // qualities are only printed by the FASTQ-style output
     std::vector<RecRef> refs;   // parallel-ingest batches: names / qualities stay in the file mapping `map`
-    const char *map = nullptr;
+    const char *map = nullptr, *map2 = nullptr;                        // map2: the mates' file (records at odd indices)
+    const char *map_of(size_t i) const { return (map2 && (i & 1)) ? map2 : map; }
     PinnedBatch() = default;
     PinnedBatch(const PinnedBatch &) = delete;
     ~PinnedBatch() { bns_b200_host_free(bases); bns_b200_host_free(offs); }
@@ -598,7 +599,7 @@ struct PinnedBatch {
         bns_b200_host_free(p);
         p = (T *)np; cap = ncap;
     }
-    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = nullptr; }
+    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = map2 = nullptr; }
     void reserve(size_t bases_hint) {                   // pinned allocations are slow: size the ring once per dataset
         grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 4 + (1 << 16));
         grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 32 + 1024);
@@ -709,6 +710,8 @@ struct SimpleFile {
         fastq = map.p[0] == '@';
         ok = true;
     }
+    // where kseq must continue: the first record not handed out yet
+    size_t resume_offset() const { return next_rec < recs.size() ? (size_t)recs[next_rec].name_off - 1 : cursor; }
     // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
     // kseq must take over)
     bool refill() {
@@ -738,16 +741,24 @@ struct SimpleFile {
     }
 };
 // the next batch out of the index: records until >= chunk_size bases and an even count (bseq_read's rule)
-inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f) {
+// (f2: the mates' file; records are interleaved r1, r2, r1, r2 ... like bseq_read does, mates of file 2 at the odd indices)
+inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f, SimpleFile *f2 = nullptr) {
     b.clear();
     b.refs.clear();
     b.map = f.map.p;
+    b.map2 = f2 ? f2->map.p : nullptr;
     u64 size = 0;
+    auto have = [](SimpleFile &x) { return x.next_rec < x.recs.size() || x.refill(); };
     for(;;) {
-        if(f.next_rec >= f.recs.size() && !f.refill()) break;
+        if(!have(f) || (f2 && !have(*f2))) break;                     // either file is out of indexed records: the caller hands over to kseq
         const RecRef &r = f.recs[f.next_rec++];
         b.refs.push_back(r);
         size += r.seq_len;
+        if(f2) {
+            const RecRef &r2 = f2->recs[f2->next_rec++];
+            b.refs.push_back(r2);
+            size += r2.seq_len;
+        }
         if((long)size >= chunk_size && (b.refs.size() & 1) == 0) break;
     }
     const size_t n = b.refs.size();
@@ -757,7 +768,9 @@ inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f) {
     b.offs[0] = 0;
     for(size_t i = 0; i < n; ++i) b.offs[i + 1] = b.offs[i] + b.refs[i].seq_len;
     const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(f.nthreads, n / 8192 + 1));
-    auto copy = [&](size_t lo, size_t hi) { for(size_t i = lo; i < hi; ++i) std::memcpy(b.bases + b.offs[i], f.map.p + b.refs[i].seq_off, b.refs[i].seq_len); };
+    auto copy = [&](size_t lo, size_t hi) {
+        for(size_t i = lo; i < hi; ++i) std::memcpy(b.bases + b.offs[i], b.map_of(i) + b.refs[i].seq_off, b.refs[i].seq_len);
+    };
     if(T == 1) copy(0, n);
     else {
         std::vector<std::thread> pool;
@@ -811,9 +824,11 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     detail::KSeq ks1(fq1);
     std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
-    // single plain files in the simple 4-line / 2-line form are indexed by the -p threads (detail::SimpleFile)
-    std::unique_ptr<detail::SimpleFile> simple(fq2 ? nullptr : new detail::SimpleFile(fq1, c.nt_));
-    if(simple && !simple->ok) simple.reset();
+    // plain files in the simple 4-line / 2-line form are indexed by the -p threads (detail::SimpleFile); with mates, both
+    // files must qualify
+    std::unique_ptr<detail::SimpleFile> simple(new detail::SimpleFile(fq1, c.nt_)), simple2(fq2 ? new detail::SimpleFile(fq2, c.nt_) : nullptr);
+    if(!simple->ok || (simple2 && !simple2->ok)) { simple.reset(); simple2.reset(); }
+    bool use_index = simple != nullptr;          // the mappings stay alive to the end: batches in flight point into them
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     constexpr int NB = 3;
     detail::PinnedBatch ring[NB];
@@ -827,14 +842,17 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
             for(int i = 0;; i = (i + 1) % NB) {
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
                 bool got = false;
-                if(simple) {
-                    got = detail::fill_pinned((int)chunk_size, ring[i], *simple);
-                    if(!got && !simple->ok && simple->cursor < simple->map.n) {      // left the simple form: kseq from there on
-                        gzseek(ks1.fp, (z_off_t)simple->cursor, SEEK_SET);
-                        simple.reset();
+                if(use_index) {
+                    got = detail::fill_pinned((int)chunk_size, ring[i], *simple, simple2.get());
+                    if(!got) {
+                        // out of indexed records: a file left the simple form, or ended (kseq then reports unequal mate
+                        // files the way bseq_read does). kseq takes over at the first record the index did not hand out.
+                        gzseek(ks1.fp, (z_off_t)simple->resume_offset(), SEEK_SET);
+                        if(simple2) gzseek(ks2->fp, (z_off_t)simple2->resume_offset(), SEEK_SET);
+                        use_index = false;
                     }
                 }
-                if(!got && !simple) got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
+                if(!got && !use_index) got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
                 { std::lock_guard<std::mutex> lk(mu); state[i] = got ? 1 : 2; }
                 cv.notify_all();
                 if(!got) return;
@@ -877,8 +895,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                 if(b.map)
                     for(size_t r = 0; r < b.n; ++r) {
                         const detail::RecRef &ref = b.refs[r];
-                        views[r] = detail::ReadView{b.map + ref.name_off, b.bases + b.offs[r],
-                                                    b.keep_qual && ref.qual_off != ~0ull ? b.map + ref.qual_off : nullptr,
+                        const char *mp = b.map_of(r);
+                        views[r] = detail::ReadView{mp + ref.name_off, b.bases + b.offs[r],
+                                                    b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
                                                     (int)ref.seq_len, (int)ref.name_len};
                     }
                 else

@@ -148,3 +148,29 @@ def test_build_entropy_minimised(setup, oracle, genomes):
         assert "k=31 w=50" in out and "occupied=%d " % k.size in out
         assert "key_xor=%016x" % int(np.bitwise_xor.reduce(k)) in out
         assert "val_sum=%d" % int(v.sum(dtype=np.uint64)) in out
+
+
+def test_classify_paired_plain_equals_gz(setup, genomes):
+    """Mate files through the parallel index (plain FASTQ, small windows, 4 threads) give the bytes the kseq path gives
+    for the same files gzipped -- including the hand-over when the second file ends early (bseq_read's warning)."""
+    b, _ = H.genome_records(genomes, 1)
+    rng = np.random.default_rng(18)
+    s1, s2, n1, n2 = [], [], [], []
+    for i in range(900):
+        st = int(rng.integers(0, 140_000))
+        s1.append(b[st:st + int(rng.integers(40, 160))].tobytes().decode())
+        s2.append(b[st + 200:st + 200 + int(rng.integers(40, 160))].tobytes().decode())
+        n1.append("q%d/1" % i); n2.append("q%d/2" % i)
+    q1 = ["I" * len(s) for s in s1]; q2 = ["@" + "F" * (len(s) - 1) for s in s2]
+    outs = {}
+    for kind in ("plain", "gz"):
+        ext = ".fq" if kind == "plain" else ".fq.gz"
+        f1, f2 = setup["dir"] / ("pp1" + ext), setup["dir"] / ("pp2" + ext)
+        write_fastq(f1, n1, s1, q1); write_fastq(f2, n2[:880], s2[:880], q2[:880])       # the mates' file is 20 records short
+        r = subprocess.run([setup["cli"], "classify", "-a", "-f", "-k", "-p", "4", "-c", "30000", str(setup["db"]), str(setup["nodes"]), str(f1), str(f2)],
+                           capture_output=True, env=dict(os.environ, BNS_B200_FASTQ_WINDOW="40000"))
+        assert r.returncode == 0, r.stderr
+        assert b"the 2nd file has fewer sequences" in r.stderr
+        outs[kind] = r.stdout
+    # 9 lines per pair: the second mate's header repeats the classification line INCLUDING its newline (classifier.h:99-104)
+    assert outs["plain"] == outs["gz"] and outs["plain"].count(b"\n") == 880 * 9
