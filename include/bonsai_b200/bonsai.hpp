@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -586,6 +587,7 @@ struct PinnedBatch {
     bool keep_qual = true;             // qualities are only printed by the FASTQ-style output
     std::vector<RecRef> refs;   // parallel-ingest batches: names / qualities stay in the file mapping `map`
     const char *map = nullptr, *map2 = nullptr;                        // map2: the mates' file (records at odd indices)
+    std::shared_ptr<char> keep, keep2;                                 // gzip input: the inflated windows `map` / `map2` point into
     const char *map_of(size_t i) const { return (map2 && (i & 1)) ? map2 : map; }
     PinnedBatch() = default;
     PinnedBatch(const PinnedBatch &) = delete;
@@ -599,7 +601,7 @@ struct PinnedBatch {
         bns_b200_host_free(p);
         p = (T *)np; cap = ncap;
     }
-    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = map2 = nullptr; }
+    void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = map2 = nullptr; keep.reset(); keep2.reset(); }
     void reserve(size_t bases_hint) {                   // pinned allocations are slow: size the ring once per dataset
         grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 4 + (1 << 16));
         grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 32 + 1024);
@@ -695,36 +697,134 @@ inline bool index_range(const char *p, size_t lo, size_t hi, size_t n, bool fast
     }
     return x == hi || (x == n + 1 && hi == n);                            // a last line without a newline ends at n
 }
+// gzip input in the same simple form: one decompressor thread per file inflates the stream window after window (zlib is a
+// serial format; this takes inflate off the parser's thread and lets two mate files inflate side by side). A window is cut at
+// its last complete record, the tail is carried into the headroom in front of the next window, and the window is indexed by
+// the -p threads exactly like a stretch of a mapped plain file. Window buffers are recycled through a pool and stay alive
+// while a batch in flight points into them (PinnedBatch::keep).
+struct GzWindows {
+    static constexpr size_t HEAD = 1u << 20;                              // room for the previous window's tail
+    struct Chunk { std::shared_ptr<char> buf; size_t n = 0; u64 off = 0; bool eof = false; };   // data at buf + HEAD; off: uncompressed offset
+    struct Pool {
+        std::mutex mu; std::vector<char *> idle;
+        ~Pool() { for(char *p : idle) delete[] p; }
+    };
+    gzFile fp = nullptr;
+    size_t wsz;
+    std::shared_ptr<Pool> pool{std::make_shared<Pool>()};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Chunk> q;
+    bool done = false, quit = false;
+    std::thread th;
+    GzWindows(const char *path, size_t window) : wsz(window) {
+        fp = gzopen(path, "rb");
+        if(!fp) return;
+        gzbuffer(fp, 1 << 20);
+        th = std::thread([this] { run(); });
+    }
+    GzWindows(const GzWindows &) = delete;
+    ~GzWindows() { stop(); if(fp) gzclose(fp); }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        if(th.joinable()) th.join();
+    }
+    std::shared_ptr<char> acquire() {
+        char *p = nullptr;
+        { std::lock_guard<std::mutex> lk(pool->mu); if(!pool->idle.empty()) { p = pool->idle.back(); pool->idle.pop_back(); } }
+        if(!p) p = new char[HEAD + wsz];
+        std::shared_ptr<Pool> pl = pool;
+        return std::shared_ptr<char>(p, [pl](char *x) { std::lock_guard<std::mutex> lk(pl->mu); pl->idle.push_back(x); });
+    }
+    void run() {
+        u64 off = 0;
+        for(;;) {
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return q.size() < 2 || quit; }); if(quit) return; }
+            Chunk c;
+            c.buf = acquire(); c.off = off;
+            while(c.n < wsz) {                                            // a short or failed read ends the stream, as in KSeq::getc_
+                const int r = gzread(fp, c.buf.get() + HEAD + c.n, (unsigned)std::min<size_t>(wsz - c.n, 1u << 30));
+                if(r <= 0) { c.eof = true; break; }
+                c.n += (size_t)r;
+            }
+            off += c.n;
+            const bool last = c.eof;
+            { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(c)); if(last) done = true; }
+            cv.notify_all();
+            if(last) return;
+        }
+    }
+    bool next(Chunk &out) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !q.empty() || done || quit; });
+        if(q.empty()) return false;
+        out = std::move(q.front()); q.pop_front();
+        lk.unlock();
+        cv.notify_all();
+        return true;
+    }
+};
+// the start of the first record that is not complete inside p[0, n) (n itself when the text ends on a record end); 0 when no
+// record boundary is found near the end
+inline size_t last_complete_record_end(const char *p, size_t n, bool fastq) {
+    for(const size_t back : {(size_t)1 << 16, GzWindows::HEAD}) {
+        size_t s = next_record_start(p, n > back ? n - back : 0, n, fastq);
+        if(s >= n) continue;
+        for(;;) {
+            const size_t e1 = line_end(p, s, n); if(e1 >= n) break;
+            size_t e = line_end(p, e1 + 1, n); if(e >= n) break;
+            if(fastq) {
+                e = line_end(p, e + 1, n); if(e >= n) break;
+                e = line_end(p, e + 1, n); if(e >= n) break;
+            }
+            s = e + 1;
+            if(s >= n) break;
+        }
+        return s;
+    }
+    return 0;
+}
 struct SimpleFile {
     MappedFile map;
     bool fastq = false, ok = false;
-    size_t cursor = 0;                     // next unindexed byte (a record start)
-    std::vector<RecRef> recs;              // the current window
+    size_t cursor = 0;                     // next unindexed byte of the (uncompressed) stream, a record start
+    std::vector<RecRef> recs;              // the current window; offsets are relative to text()
     size_t next_rec = 0;
     unsigned nthreads;
     size_t window;
+    // gzip input
+    std::unique_ptr<GzWindows> gz;
+    std::shared_ptr<char> hold;            // the current window's buffer
+    const char *gz_text = nullptr;
+    u64 gz_base = 0;                       // uncompressed offset of gz_text[0]
+    std::string carry;
+    bool gz_first = true;
     SimpleFile(const char *path, unsigned nt) : map(path), nthreads(std::max(1u, nt)) {
         const char *e = std::getenv("BNS_B200_FASTQ_WINDOW");              // bytes per indexing window (tests use a small one)
         window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)1 << 30);
+        if(map.p && (unsigned char)map.p[0] == 0x1f && (unsigned char)map.p[1] == 0x8b) {
+            const char *g = std::getenv("BNS_B200_GZ_WINDOW");             // inflated bytes per window
+            gz.reset(new GzWindows(path, g && std::atoll(g) > 0 ? (size_t)std::atoll(g) : ((size_t)64 << 20)));
+            ok = gz->fp != nullptr;        // whether the text is in the simple form shows at the first window
+            return;
+        }
         if(!map.simple_candidate()) return;
         fastq = map.p[0] == '@';
         ok = true;
     }
-    // where kseq must continue: the first record not handed out yet
-    size_t resume_offset() const { return next_rec < recs.size() ? (size_t)recs[next_rec].name_off - 1 : cursor; }
-    // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
-    // kseq must take over)
-    bool refill() {
-        recs.clear(); next_rec = 0;
-        if(!ok || cursor >= map.n) return false;
-        const char *p = map.p;
-        const size_t n = map.n, lo = cursor;
-        size_t hi = n;
-        if(n - lo > window) { hi = next_record_start(p, lo + window, n, fastq); }
+    const char *text() const { return gz ? gz_text : map.p; }
+    void stop() { if(gz) gz->stop(); }
+    // where kseq must continue (an offset into the uncompressed stream): the first record not handed out yet
+    size_t resume_offset() const {
+        return next_rec < recs.size() ? (size_t)(gz ? gz_base : 0) + (size_t)recs[next_rec].name_off - 1 : cursor;
+    }
+    // records of p[lo, hi) on the -p threads; n: end of the text
+    bool index_parallel(const char *p, size_t lo, size_t hi, size_t n) {
         const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, (hi - lo) / (1u << 20) + 1));
         std::vector<size_t> cut(T + 1);
         cut[0] = lo; cut[T] = hi;
-        for(unsigned t = 1; t < T; ++t) cut[t] = next_record_start(p, lo + (hi - lo) / T * t, n, fastq);
+        for(unsigned t = 1; t < T; ++t) cut[t] = std::min(hi, next_record_start(p, lo + (hi - lo) / T * t, n, fastq));
         for(unsigned t = 1; t <= T; ++t) if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
         std::vector<std::vector<RecRef>> part(T);
         std::vector<char> good(T, 1);
@@ -733,10 +833,50 @@ struct SimpleFile {
             pool.emplace_back([&, t] { good[t] = index_range(p, cut[t], cut[t + 1], n, fastq, part[t]); });
         for(auto &th : pool) th.join();
         for(unsigned t = 0; t < T; ++t) {
-            if(!good[t]) { ok = false; recs.clear(); return false; }     // leave `cursor` at the window start for kseq
+            if(!good[t]) { recs.clear(); return false; }
             recs.insert(recs.end(), part[t].begin(), part[t].end());
         }
+        return true;
+    }
+    // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
+    // kseq must take over)
+    bool refill() {
+        recs.clear(); next_rec = 0;
+        if(gz) return refill_gz();
+        if(!ok || cursor >= map.n) return false;
+        const char *p = map.p;
+        const size_t n = map.n, lo = cursor;
+        size_t hi = n;
+        if(n - lo > window) { hi = next_record_start(p, lo + window, n, fastq); }
+        if(!index_parallel(p, lo, hi, n)) { ok = false; return false; }   // leave `cursor` at the window start for kseq
         cursor = hi;
+        return !recs.empty();
+    }
+    bool refill_gz() {
+        if(!ok) return false;
+        GzWindows::Chunk ch;
+        if(!gz->next(ch)) return false;                                    // the stream has ended
+        const size_t cl = carry.size();
+        char *t = ch.buf.get() + GzWindows::HEAD - cl;
+        if(cl) std::memcpy(t, carry.data(), cl);
+        carry.clear();
+        const size_t n = cl + ch.n;
+        hold = ch.buf; gz_text = t;
+        gz_base = ch.off - cl; cursor = (size_t)gz_base;
+        if(n == 0) return false;
+        if(gz_first) {
+            gz_first = false;
+            if(t[0] != '@' && t[0] != '>') { ok = false; return false; }
+            fastq = t[0] == '@';
+        }
+        size_t hi = n;
+        if(!ch.eof) {
+            hi = last_complete_record_end(t, n, fastq);
+            if(hi == 0 || n - hi > GzWindows::HEAD) { ok = false; return false; }   // no boundary / a record beyond the headroom
+            carry.assign(t + hi, n - hi);
+        }
+        if(!index_parallel(t, 0, hi, hi)) { ok = false; carry.clear(); return false; }
+        cursor = (size_t)gz_base + hi;
         return !recs.empty();
     }
 };
@@ -745,11 +885,12 @@ struct SimpleFile {
 inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f, SimpleFile *f2 = nullptr) {
     b.clear();
     b.refs.clear();
-    b.map = f.map.p;
-    b.map2 = f2 ? f2->map.p : nullptr;
     u64 size = 0;
     auto have = [](SimpleFile &x) { return x.next_rec < x.recs.size() || x.refill(); };
+    // a batch points into ONE window per file: with gzip input it ends where a window does
+    auto at_window_end = [](SimpleFile &x) { return x.gz && x.next_rec >= x.recs.size(); };
     for(;;) {
+        if(!b.refs.empty() && (at_window_end(f) || (f2 && at_window_end(*f2)))) break;
         if(!have(f) || (f2 && !have(*f2))) break;                     // either file is out of indexed records: the caller hands over to kseq
         const RecRef &r = f.recs[f.next_rec++];
         b.refs.push_back(r);
@@ -763,6 +904,9 @@ inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f, SimpleFil
     }
     const size_t n = b.refs.size();
     if(!n) return false;
+    b.map = f.text(); b.keep = f.hold;
+    b.map2 = f2 ? f2->text() : nullptr;
+    if(f2) b.keep2 = f2->hold;
     PinnedBatch::grow(b.bases, b.cap_bases, 0, size + 16);
     PinnedBatch::grow(b.offs, b.cap_offs, 0, n + 2);
     b.offs[0] = 0;
@@ -824,10 +968,11 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     detail::KSeq ks1(fq1);
     std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
-    // plain files in the simple 4-line / 2-line form are indexed by the -p threads (detail::SimpleFile); with mates, both
-    // files must qualify
+    // plain or gzip files in the simple 4-line / 2-line form are indexed by the -p threads (detail::SimpleFile; gzip streams
+    // are inflated by one thread per file, detail::GzWindows); with mates, both files must qualify
     std::unique_ptr<detail::SimpleFile> simple(new detail::SimpleFile(fq1, c.nt_)), simple2(fq2 ? new detail::SimpleFile(fq2, c.nt_) : nullptr);
-    if(!simple->ok || (simple2 && !simple2->ok)) { simple.reset(); simple2.reset(); }
+    const char *ingest = std::getenv("BNS_B200_INGEST");                  // "kseq": the single-threaded reader for everything
+    if(!simple->ok || (simple2 && !simple2->ok) || (ingest && !std::strcmp(ingest, "kseq"))) { simple.reset(); simple2.reset(); }
     bool use_index = simple != nullptr;          // the mappings stay alive to the end: batches in flight point into them
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     constexpr int NB = 3;
@@ -849,6 +994,8 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                         // files the way bseq_read does). kseq takes over at the first record the index did not hand out.
                         gzseek(ks1.fp, (z_off_t)simple->resume_offset(), SEEK_SET);
                         if(simple2) gzseek(ks2->fp, (z_off_t)simple2->resume_offset(), SEEK_SET);
+                        simple->stop();
+                        if(simple2) simple2->stop();
                         use_index = false;
                     }
                 }

@@ -1,11 +1,17 @@
 // Host-side check of the parallel plain-file ingest (include/bonsai_b200/bonsai.hpp, detail::SimpleFile) against the
 // kseq state machine of the same header: same records, and a clean hand-over to kseq where a file leaves the simple form.
+// The same for gzip input (detail::GzWindows: decompressor thread, windows cut at record ends, tails carried over), and
+// detail::fill_pinned over single and mate files (plain and gzip) against the kseq records, batch by batch.
 // Built with g++ -lz by tests/test_cli_cpu.py; argv[1] = directory to write the test files into.
 #include <cstdio>
 #include <random>
 #include <string>
 #include <vector>
 #include "../../include/bonsai_b200/bonsai.hpp"
+
+// the pinned allocator of the C ABI, stood in for by malloc: this test never touches the device library
+extern "C" int bns_b200_host_alloc(void **p, size_t n) { *p = std::malloc(n); return *p ? 0 : -1; }
+extern "C" int bns_b200_host_free(void *p) { std::free(p); return 0; }
 
 using namespace bns;
 struct Rec { std::string name, seq, qual; bool operator==(const Rec &o) const { return name == o.name && seq == o.seq && qual == o.qual; } };
@@ -25,17 +31,63 @@ static std::vector<Rec> by_index(const std::string &path, unsigned nt, bool *use
     if(f.ok) {
         while(f.refill())
             for(const auto &r : f.recs)
-                out.push_back(Rec{std::string(f.map.p + r.name_off, r.name_len), std::string(f.map.p + r.seq_off, r.seq_len),
-                                  r.qual_off == ~0ull ? std::string() : std::string(f.map.p + r.qual_off, r.seq_len)});
-        if(f.ok || f.cursor >= f.map.n) return out;
+                out.push_back(Rec{std::string(f.text() + r.name_off, r.name_len), std::string(f.text() + r.seq_off, r.seq_len),
+                                  r.qual_off == ~0ull ? std::string() : std::string(f.text() + r.qual_off, r.seq_len)});
+        if(f.ok) return out;
         *fell_back = true;
-        auto rest = by_kseq(path, f.cursor);
+        auto rest = by_kseq(path, f.resume_offset());
         out.insert(out.end(), rest.begin(), rest.end());
         return out;
     }
     return by_kseq(path);
 }
 static void write(const std::string &path, const std::string &txt) { FILE *f = fopen(path.c_str(), "wb"); fwrite(txt.data(), 1, txt.size(), f); fclose(f); }
+static void write_gz(const std::string &path, const std::string &txt, size_t members = 1) {
+    // `members` > 1: concatenated gzip members (what bgzip / `cat a.gz b.gz` produce); gzread reads through them
+    FILE *out = fopen(path.c_str(), "wb"); fclose(out);
+    for(size_t m = 0; m < members; ++m) {
+        gzFile g = gzopen(path.c_str(), "ab1");
+        const size_t lo = txt.size() * m / members, hi = txt.size() * (m + 1) / members;
+        for(size_t x = lo; x < hi;) { const int r = gzwrite(g, txt.data() + x, (unsigned)std::min<size_t>(hi - x, 1u << 20)); x += (size_t)r; }
+        gzclose(g);
+    }
+}
+// process_dataset's reader, batch by batch: fill_pinned while the index serves, read_pinned (kseq) after the hand-over
+static std::vector<Rec> by_batches(const std::string &p1, const std::string *p2, unsigned nt, int chunk, size_t *n_batches) {
+    std::vector<Rec> out;
+    detail::KSeq ks1(p1.c_str());
+    std::unique_ptr<detail::KSeq> ks2(p2 ? new detail::KSeq(p2->c_str()) : nullptr);
+    std::unique_ptr<detail::SimpleFile> f1(new detail::SimpleFile(p1.c_str(), nt)), f2(p2 ? new detail::SimpleFile(p2->c_str(), nt) : nullptr);
+    bool use_index = f1->ok && (!f2 || f2->ok);
+    detail::PinnedBatch ring[3];                                       // batches stay alive for two more rounds, like the ring in flight
+    std::vector<std::vector<Rec>> pending(3);
+    *n_batches = 0;
+    for(int i = 0;; i = (i + 1) % 3) {
+        detail::PinnedBatch &b = ring[i];
+        bool got = false;
+        if(use_index) {
+            got = detail::fill_pinned(chunk, b, *f1, f2.get());
+            if(!got) {
+                gzseek(ks1.fp, (z_off_t)f1->resume_offset(), SEEK_SET);
+                if(f2) gzseek(ks2->fp, (z_off_t)f2->resume_offset(), SEEK_SET);
+                f1->stop(); if(f2) f2->stop();
+                use_index = false;
+            }
+        }
+        if(!got && !use_index) got = detail::read_pinned(chunk, b, &ks1, ks2.get());
+        if(!got) break;
+        ++*n_batches;
+        for(size_t r = 0; r < b.n; ++r) {
+            const std::string seq(b.bases + b.offs[r], b.offs[r + 1] - b.offs[r]);
+            if(b.map) {
+                const detail::RecRef &ref = b.refs[r];
+                const char *mp = b.map_of(r);
+                out.push_back(Rec{std::string(mp + ref.name_off, ref.name_len), seq, ref.qual_off == ~0ull ? std::string() : std::string(mp + ref.qual_off, ref.seq_len)});
+            } else out.push_back(Rec{b.names[r], seq, b.quals[r]});
+        }
+    }
+    return out;
+}
 
 int main(int argc, char **argv) {
     const std::string dir = argc > 1 ? argv[1] : "/tmp";
@@ -89,6 +141,59 @@ int main(int argc, char **argv) {
             const bool ok = same && used == c.expect_index && fell == c.expect_fallback;
             printf("%s nt=%u records=%zu/%zu index=%d fallback=%d %s\n", c.name, nt, got.size(), ref.size(), (int)used, (int)fell, ok ? "ok" : "MISMATCH");
             failures += !ok;
+        }
+    }
+    // gzip input: the same texts, compressed (single- and multi-member), small inflate windows
+    setenv("BNS_B200_GZ_WINDOW", "300000", 1);
+    for(auto &c : cases) {
+        for(size_t members : {(size_t)1, (size_t)5}) {
+            const std::string path = dir + "/" + c.name + "_m" + std::to_string(members) + ".gz";
+            write_gz(path, c.txt, members);
+            const auto ref = by_kseq(path);
+            for(unsigned nt : {1u, 4u}) {
+                bool used = false, fell = false;
+                const auto got = by_index(path, nt, &used, &fell);
+                const bool same = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin());
+                const bool ok = same && used == c.expect_index && fell == c.expect_fallback;
+                printf("gz %s members=%zu nt=%u records=%zu/%zu index=%d fallback=%d %s\n", c.name, members, nt, got.size(), ref.size(), (int)used, (int)fell, ok ? "ok" : "MISMATCH");
+                failures += !ok;
+            }
+        }
+    }
+    // batches (fill_pinned / read_pinned), single and mate files; mates of different line lengths so that their windows do not line up;
+    // the second mate file of the last pairing is one record short (bseq_read stops there)
+    {
+        std::string m1, m2, m2short, m2multi;
+        for(int i = 0; i < 15000; ++i) {
+            const int n1 = 30 + rng() % 200, n2 = 80 + rng() % 300;
+            m1 += "@p" + std::to_string(i) + "/1\n" + seq(n1) + "\n+\n" + qual(n1, i) + "\n";
+            const std::string r2 = "@p" + std::to_string(i) + "/2\n" + seq(n2) + "\n+\n" + qual(n2, i) + "\n";
+            m2 += r2;
+            if(i + 1 < 15000) m2short += r2;
+            m2multi += i == 9000 ? "@p9000/2\nACGT\nACGT\n+\nIIIIIIII\n" : r2;
+        }
+        struct Pairing { const char *name; std::string a, b; bool gz_a, gz_b; };
+        std::vector<Pairing> pairings = {{"single_plain", m1, "", false, false}, {"single_gz", m1, "", true, false},
+                                         {"pair_plain", m1, m2, false, false}, {"pair_gz", m1, m2, true, true}, {"pair_mixed", m1, m2, false, true},
+                                         {"pair_gz_short", m1, m2short, true, true}, {"pair_gz_multiline", m1, m2multi, true, true}};
+        for(auto &pr : pairings) {
+            const std::string pa = dir + "/" + pr.name + "_1" + (pr.gz_a ? ".gz" : ".fq"), pb = dir + "/" + pr.name + "_2" + (pr.gz_b ? ".gz" : ".fq");
+            pr.gz_a ? write_gz(pa, pr.a) : write(pa, pr.a);
+            const bool paired = !pr.b.empty();
+            if(paired) { pr.gz_b ? write_gz(pb, pr.b) : write(pb, pr.b); }
+            std::vector<Rec> ref;
+            {
+                const auto ra = by_kseq(pa);
+                if(!paired) ref = ra;
+                else { const auto rb = by_kseq(pb); for(size_t i = 0; i < std::min(ra.size(), rb.size()); ++i) { ref.push_back(ra[i]); ref.push_back(rb[i]); } }
+            }
+            for(int chunk : {1 << 16, 1 << 22}) {
+                size_t nb = 0;
+                const auto got = by_batches(pa, paired ? &pb : nullptr, 4, chunk, &nb);
+                const bool ok = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin());
+                printf("batches %s chunk=%d records=%zu/%zu batches=%zu %s\n", pr.name, chunk, got.size(), ref.size(), nb, ok ? "ok" : "MISMATCH");
+                failures += !ok;
+            }
         }
     }
     return failures ? 1 : 0;

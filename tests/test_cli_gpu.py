@@ -151,8 +151,9 @@ def test_build_entropy_minimised(setup, oracle, genomes):
 
 
 def test_classify_paired_plain_equals_gz(setup, genomes):
-    """Mate files through the parallel index (plain FASTQ, small windows, 4 threads) give the bytes the kseq path gives
-    for the same files gzipped -- including the hand-over when the second file ends early (bseq_read's warning)."""
+    """Mate files through the parallel index (plain FASTQ with small windows, gzip with small and with default inflate
+    windows, 4 threads) give the bytes the kseq path gives for the same files -- including the hand-over when the second
+    file ends early (bseq_read's warning)."""
     b, _ = H.genome_records(genomes, 1)
     rng = np.random.default_rng(18)
     s1, s2, n1, n2 = [], [], [], []
@@ -163,14 +164,17 @@ def test_classify_paired_plain_equals_gz(setup, genomes):
         n1.append("q%d/1" % i); n2.append("q%d/2" % i)
     q1 = ["I" * len(s) for s in s1]; q2 = ["@" + "F" * (len(s) - 1) for s in s2]
     outs = {}
-    for kind in ("plain", "gz"):
-        ext = ".fq" if kind == "plain" else ".fq.gz"
+    kinds = {"plain": (".fq", {"BNS_B200_FASTQ_WINDOW": "40000"}), "gz_kseq": (".fq.gz", {"BNS_B200_INGEST": "kseq"}),
+             "gz_windows": (".fq.gz", {"BNS_B200_GZ_WINDOW": "50000"}), "gz": (".fq.gz", {})}
+    for kind, (ext, env) in kinds.items():
         f1, f2 = setup["dir"] / ("pp1" + ext), setup["dir"] / ("pp2" + ext)
         write_fastq(f1, n1, s1, q1); write_fastq(f2, n2[:880], s2[:880], q2[:880])       # the mates' file is 20 records short
         r = subprocess.run([setup["cli"], "classify", "-a", "-f", "-k", "-p", "4", "-c", "30000", str(setup["db"]), str(setup["nodes"]), str(f1), str(f2)],
-                           capture_output=True, env=dict(os.environ, BNS_B200_FASTQ_WINDOW="40000"))
+                           capture_output=True, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stderr
         assert b"the 2nd file has fewer sequences" in r.stderr
         outs[kind] = r.stdout
     # 9 lines per pair: the second mate's header repeats the classification line INCLUDING its newline (classifier.h:99-104)
-    assert outs["plain"] == outs["gz"] and outs["plain"].count(b"\n") == 880 * 9
+    assert outs["gz_kseq"].count(b"\n") == 880 * 9
+    for kind in kinds:
+        assert outs[kind] == outs["gz_kseq"], kind
