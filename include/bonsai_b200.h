@@ -137,8 +137,9 @@ int bns_b200_resolve_batch(bns_b200_t *ctx, const uint32_t *taxa, const uint16_t
                            uint64_t n_lists, uint32_t *taxon_out);
 
 /* ---- replication: one broadcast at load ------------------------------------------------
- * Rank 0 loads table + taxonomy, every rank calls db_blob_size, non-root ranks db_blob_alloc, then the host
- * plumbing broadcasts the device segments (NCCL / torch.distributed) and every rank calls db_blob_commit. */
+ * Rank 0 loads table + taxonomy and exports the 128-byte header; the host plumbing broadcasts it, non-root ranks
+ * allocate from it (db_alloc_from_header), every rank lists its device segments (db_segments), the plumbing
+ * broadcasts each segment (NCCL / torch.distributed) and non-root ranks call db_commit. */
 typedef struct bns_b200_db_header { uint64_t words[16]; } bns_b200_db_header;
 int bns_b200_db_export_header(const bns_b200_t *ctx, bns_b200_db_header *hdr);
 int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr);
