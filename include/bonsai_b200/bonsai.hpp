@@ -800,6 +800,7 @@ struct SimpleFile {
     u64 gz_base = 0;                       // uncompressed offset of gz_text[0]
     std::string carry;
     bool gz_first = true;
+    bool at_end = false;                   // the whole stream has been indexed
     SimpleFile(const char *path, unsigned nt) : map(path), nthreads(std::max(1u, nt)) {
         const char *e = std::getenv("BNS_B200_FASTQ_WINDOW");              // bytes per indexing window (tests use a small one)
         window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)1 << 30);
@@ -818,6 +819,12 @@ struct SimpleFile {
     // where kseq must continue (an offset into the uncompressed stream): the first record not handed out yet
     size_t resume_offset() const {
         return next_rec < recs.size() ? (size_t)(gz ? gz_base : 0) + (size_t)recs[next_rec].name_off - 1 : cursor;
+    }
+    // every record of the file has been handed out and the file kept the simple form to its end (looks one window ahead)
+    bool drained() {
+        if(next_rec < recs.size() || !ok) return false;
+        if(!at_end) refill();
+        return ok && at_end && recs.empty();
     }
     // records of p[lo, hi) on the -p threads; n: end of the text
     bool index_parallel(const char *p, size_t lo, size_t hi, size_t n) {
@@ -843,7 +850,8 @@ struct SimpleFile {
     bool refill() {
         recs.clear(); next_rec = 0;
         if(gz) return refill_gz();
-        if(!ok || cursor >= map.n) return false;
+        if(!ok) return false;
+        if(cursor >= map.n) { at_end = true; return false; }
         const char *p = map.p;
         const size_t n = map.n, lo = cursor;
         size_t hi = n;
@@ -855,7 +863,7 @@ struct SimpleFile {
     bool refill_gz() {
         if(!ok) return false;
         GzWindows::Chunk ch;
-        if(!gz->next(ch)) return false;                                    // the stream has ended
+        if(!gz->next(ch)) { at_end = true; return false; }                 // the stream has ended
         const size_t cl = carry.size();
         char *t = ch.buf.get() + GzWindows::HEAD - cl;
         if(cl) std::memcpy(t, carry.data(), cl);
@@ -863,7 +871,7 @@ struct SimpleFile {
         const size_t n = cl + ch.n;
         hold = ch.buf; gz_text = t;
         gz_base = ch.off - cl; cursor = (size_t)gz_base;
-        if(n == 0) return false;
+        if(n == 0) { at_end = true; return false; }
         if(gz_first) {
             gz_first = false;
             if(t[0] != '@' && t[0] != '>') { ok = false; return false; }
@@ -989,9 +997,16 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                 bool got = false;
                 if(use_index) {
                     got = detail::fill_pinned((int)chunk_size, ring[i], *simple, simple2.get());
+                    if(!got && simple->drained() && (!simple2 || simple2->drained())) {
+                        // the index served the input to its end (a gzip stream would inflate once more to seek there)
+                        use_index = false;
+                        { std::lock_guard<std::mutex> lk(mu); state[i] = 2; }
+                        cv.notify_all();
+                        return;
+                    }
                     if(!got) {
-                        // out of indexed records: a file left the simple form, or ended (kseq then reports unequal mate
-                        // files the way bseq_read does). kseq takes over at the first record the index did not hand out.
+                        // out of indexed records: a file left the simple form, or one mate file ended before the other (kseq
+                        // then reports it the way bseq_read does). kseq takes over at the first record the index did not hand out.
                         gzseek(ks1.fp, (z_off_t)simple->resume_offset(), SEEK_SET);
                         if(simple2) gzseek(ks2->fp, (z_off_t)simple2->resume_offset(), SEEK_SET);
                         simple->stop();

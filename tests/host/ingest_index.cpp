@@ -53,7 +53,7 @@ static void write_gz(const std::string &path, const std::string &txt, size_t mem
     }
 }
 // process_dataset's reader, batch by batch: fill_pinned while the index serves, read_pinned (kseq) after the hand-over
-static std::vector<Rec> by_batches(const std::string &p1, const std::string *p2, unsigned nt, int chunk, size_t *n_batches) {
+static std::vector<Rec> by_batches(const std::string &p1, const std::string *p2, unsigned nt, int chunk, size_t *n_batches, size_t *n_handovers) {
     std::vector<Rec> out;
     detail::KSeq ks1(p1.c_str());
     std::unique_ptr<detail::KSeq> ks2(p2 ? new detail::KSeq(p2->c_str()) : nullptr);
@@ -61,13 +61,15 @@ static std::vector<Rec> by_batches(const std::string &p1, const std::string *p2,
     bool use_index = f1->ok && (!f2 || f2->ok);
     detail::PinnedBatch ring[3];                                       // batches stay alive for two more rounds, like the ring in flight
     std::vector<std::vector<Rec>> pending(3);
-    *n_batches = 0;
+    *n_batches = 0; *n_handovers = 0;
     for(int i = 0;; i = (i + 1) % 3) {
         detail::PinnedBatch &b = ring[i];
         bool got = false;
         if(use_index) {
             got = detail::fill_pinned(chunk, b, *f1, f2.get());
+            if(!got && f1->drained() && (!f2 || f2->drained())) break;
             if(!got) {
+                ++*n_handovers;
                 gzseek(ks1.fp, (z_off_t)f1->resume_offset(), SEEK_SET);
                 if(f2) gzseek(ks2->fp, (z_off_t)f2->resume_offset(), SEEK_SET);
                 f1->stop(); if(f2) f2->stop();
@@ -172,10 +174,11 @@ int main(int argc, char **argv) {
             if(i + 1 < 15000) m2short += r2;
             m2multi += i == 9000 ? "@p9000/2\nACGT\nACGT\n+\nIIIIIIII\n" : r2;
         }
-        struct Pairing { const char *name; std::string a, b; bool gz_a, gz_b; };
-        std::vector<Pairing> pairings = {{"single_plain", m1, "", false, false}, {"single_gz", m1, "", true, false},
-                                         {"pair_plain", m1, m2, false, false}, {"pair_gz", m1, m2, true, true}, {"pair_mixed", m1, m2, false, true},
-                                         {"pair_gz_short", m1, m2short, true, true}, {"pair_gz_multiline", m1, m2multi, true, true}};
+        struct Pairing { const char *name; std::string a, b; bool gz_a, gz_b; size_t handovers; };   // handovers: kseq takes over (not at a clean end)
+        std::vector<Pairing> pairings = {{"single_plain", m1, "", false, false, 0}, {"single_gz", m1, "", true, false, 0},
+                                         {"pair_plain", m1, m2, false, false, 0}, {"pair_gz", m1, m2, true, true, 0}, {"pair_mixed", m1, m2, false, true, 0},
+                                         {"pair_gz_short", m1, m2short, true, true, 1}, {"pair_short_gz", m2short, m1, true, true, 1},
+                                         {"pair_gz_multiline", m1, m2multi, true, true, 1}};
         for(auto &pr : pairings) {
             const std::string pa = dir + "/" + pr.name + "_1" + (pr.gz_a ? ".gz" : ".fq"), pb = dir + "/" + pr.name + "_2" + (pr.gz_b ? ".gz" : ".fq");
             pr.gz_a ? write_gz(pa, pr.a) : write(pa, pr.a);
@@ -188,10 +191,10 @@ int main(int argc, char **argv) {
                 else { const auto rb = by_kseq(pb); for(size_t i = 0; i < std::min(ra.size(), rb.size()); ++i) { ref.push_back(ra[i]); ref.push_back(rb[i]); } }
             }
             for(int chunk : {1 << 16, 1 << 22}) {
-                size_t nb = 0;
-                const auto got = by_batches(pa, paired ? &pb : nullptr, 4, chunk, &nb);
-                const bool ok = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin());
-                printf("batches %s chunk=%d records=%zu/%zu batches=%zu %s\n", pr.name, chunk, got.size(), ref.size(), nb, ok ? "ok" : "MISMATCH");
+                size_t nb = 0, nh = 0;
+                const auto got = by_batches(pa, paired ? &pb : nullptr, 4, chunk, &nb, &nh);
+                const bool ok = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin()) && nh == pr.handovers;
+                printf("batches %s chunk=%d records=%zu/%zu batches=%zu handovers=%zu %s\n", pr.name, chunk, got.size(), ref.size(), nb, nh, ok ? "ok" : "MISMATCH");
                 failures += !ok;
             }
         }
