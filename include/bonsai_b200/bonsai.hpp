@@ -715,13 +715,19 @@ struct GzWindows {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Chunk> q;
-    bool done = false, quit = false;
+    bool done = false, quit = false, failed = false;
     std::thread th;
     GzWindows(const char *path, size_t window) : wsz(window) {
         fp = gzopen(path, "rb");
         if(!fp) return;
         gzbuffer(fp, 1 << 20);
-        th = std::thread([this] { run(); });
+        th = std::thread([this] {
+            try { run(); }
+            catch(...) {                                                   // out of memory for a window: end the stream here, the
+                { std::lock_guard<std::mutex> lk(mu); done = true; failed = true; }   // consumer hands the rest to kseq
+                cv.notify_all();
+            }
+        });
     }
     GzWindows(const GzWindows &) = delete;
     ~GzWindows() { stop(); if(fp) gzclose(fp); }
@@ -863,7 +869,10 @@ struct SimpleFile {
     bool refill_gz() {
         if(!ok) return false;
         GzWindows::Chunk ch;
-        if(!gz->next(ch)) { at_end = true; return false; }                 // the stream has ended
+        if(!gz->next(ch)) {                                                // the stream has ended
+            if(gz->failed) { ok = false; carry.clear(); return false; }    // (not cleanly: kseq continues at `cursor`)
+            at_end = true; return false;
+        }
         const size_t cl = carry.size();
         char *t = ch.buf.get() + GzWindows::HEAD - cl;
         if(cl) std::memcpy(t, carry.data(), cl);
