@@ -717,12 +717,38 @@ struct GzWindows {
     std::deque<Chunk> q;
     bool done = false, quit = false, failed = false;
     std::thread th;
-    GzWindows(const char *path, size_t window) : wsz(window) {
+    // BGZF (bgzip / htslib): a gzip file of independent blocks of <= 64 KiB whose headers carry their size (extra subfield
+    // "BC"), so the blocks of a window inflate in parallel on the -p threads, straight out of the file mapping. Anything
+    // unexpected (another kind of member, a block that does not inflate to its size and checksum) ends the indexed stream
+    // there and kseq / gzread take over.
+    const unsigned char *mp = nullptr;
+    size_t mn = 0;
+    unsigned nthreads = 1;
+    bool bgzf = false;
+    static u32 le32(const unsigned char *p) { return p[0] | (u32)p[1] << 8 | (u32)p[2] << 16 | (u32)p[3] << 24; }
+    static bool bgzf_block(const unsigned char *p, size_t avail, size_t *total, size_t *data_off, u32 *isize) {
+        if(avail < 28 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || p[3] != 4) return false;     // FEXTRA and nothing else
+        const size_t xlen = p[10] | (size_t)p[11] << 8;
+        if(12 + xlen + 8 > avail) return false;
+        size_t bs = 0;
+        for(size_t x = 12; x + 4 <= 12 + xlen;) {
+            const size_t slen = p[x + 2] | (size_t)p[x + 3] << 8;
+            if(p[x] == 'B' && p[x + 1] == 'C' && slen == 2 && x + 6 <= 12 + xlen) bs = (p[x + 4] | (size_t)p[x + 5] << 8) + 1;
+            x += 4 + slen;
+        }
+        if(bs < 12 + xlen + 8 || bs > avail) return false;
+        *total = bs; *data_off = 12 + xlen; *isize = le32(p + bs - 4);
+        return *isize <= 65536;
+    }
+    GzWindows(const char *path, size_t window, const char *mapped = nullptr, size_t mapped_n = 0, unsigned nt = 1)
+        : wsz(window), mp((const unsigned char *)mapped), mn(mapped_n), nthreads(std::max(1u, nt)) {
         fp = gzopen(path, "rb");
         if(!fp) return;
         gzbuffer(fp, 1 << 20);
+        size_t t, d; u32 isz;
+        bgzf = mp && wsz >= (1u << 17) && bgzf_block(mp, mn, &t, &d, &isz);
         th = std::thread([this] {
-            try { run(); }
+            try { if(bgzf) run_bgzf(); else run(); }
             catch(...) {                                                   // out of memory for a window: end the stream here, the
                 { std::lock_guard<std::mutex> lk(mu); done = true; failed = true; }   // consumer hands the rest to kseq
                 cv.notify_all();
@@ -757,6 +783,68 @@ struct GzWindows {
             off += c.n;
             const bool last = c.eof;
             { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(c)); if(last) done = true; }
+            cv.notify_all();
+            if(last) return;
+        }
+    }
+    void run_bgzf() {
+        struct Blk { size_t in, in_len, out; u32 isize, crc; };
+        std::vector<Blk> blks;
+        size_t pos = 0;
+        u64 off = 0;
+        for(;;) {
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return q.size() < 2 || quit; }); if(quit) return; }
+            Chunk c;
+            c.buf = acquire(); c.off = off;
+            blks.clear();
+            size_t out = 0;
+            bool bad = false;
+            while(pos < mn) {                                             // the blocks of this window
+                size_t total, doff; u32 isz;
+                if(!bgzf_block(mp + pos, mn - pos, &total, &doff, &isz)) { bad = true; break; }
+                if(out + isz > wsz) break;
+                blks.push_back(Blk{pos + doff, total - doff - 8, out, isz, le32(mp + pos + total - 8)});
+                out += isz; pos += total;
+            }
+            const size_t nb = blks.size();
+            const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, nb / 16 + 1));
+            std::vector<size_t> first_bad(T, nb);
+            char *dst = c.buf.get() + HEAD;
+            auto work = [&](unsigned t) {
+                const size_t lo = nb * t / T, hi = nb * (t + 1) / T;
+                z_stream zs;
+                std::memset(&zs, 0, sizeof zs);
+                if(inflateInit2(&zs, -15) != Z_OK) { first_bad[t] = lo; return; }
+                for(size_t i = lo; i < hi; ++i) {
+                    const Blk &b = blks[i];
+                    if(b.isize == 0) continue;                            // the empty end-of-file block
+                    inflateReset(&zs);
+                    zs.next_in = (Bytef *)(mp + b.in); zs.avail_in = (uInt)b.in_len;
+                    zs.next_out = (Bytef *)(dst + b.out); zs.avail_out = b.isize;
+                    const int r = inflate(&zs, Z_FINISH);
+                    if(r != Z_STREAM_END || zs.avail_out != 0 || (u32)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)(dst + b.out), b.isize) != b.crc) {
+                        first_bad[t] = i; break;
+                    }
+                }
+                inflateEnd(&zs);
+            };
+            if(T == 1) work(0);
+            else {
+                std::vector<std::thread> pool;
+                for(unsigned t = 0; t < T; ++t) pool.emplace_back(work, t);
+                for(auto &w : pool) w.join();
+            }
+            const size_t fb = *std::min_element(first_bad.begin(), first_bad.end());
+            if(fb < nb) { bad = true; out = blks[fb].out; }
+            c.n = out; off += out;
+            c.eof = !bad && pos >= mn;
+            const bool last = c.eof || bad;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if(c.n || c.eof) q.push_back(std::move(c));
+                if(bad) failed = true;
+                if(last) done = true;
+            }
             cv.notify_all();
             if(last) return;
         }
@@ -812,7 +900,7 @@ struct SimpleFile {
         window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)1 << 30);
         if(map.p && (unsigned char)map.p[0] == 0x1f && (unsigned char)map.p[1] == 0x8b) {
             const char *g = std::getenv("BNS_B200_GZ_WINDOW");             // inflated bytes per window
-            gz.reset(new GzWindows(path, g && std::atoll(g) > 0 ? (size_t)std::atoll(g) : ((size_t)64 << 20)));
+            gz.reset(new GzWindows(path, g && std::atoll(g) > 0 ? (size_t)std::atoll(g) : ((size_t)64 << 20), map.p, map.n, nthreads));
             ok = gz->fp != nullptr;        // whether the text is in the simple form shows at the first window
             return;
         }
@@ -880,7 +968,7 @@ struct SimpleFile {
         const size_t n = cl + ch.n;
         hold = ch.buf; gz_text = t;
         gz_base = ch.off - cl; cursor = (size_t)gz_base;
-        if(n == 0) { at_end = true; return false; }
+        if(n == 0) { if(ch.eof) at_end = true; else ok = false; return false; }
         if(gz_first) {
             gz_first = false;
             if(t[0] != '@' && t[0] != '>') { ok = false; return false; }

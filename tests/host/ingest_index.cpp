@@ -52,6 +52,39 @@ static void write_gz(const std::string &path, const std::string &txt, size_t mem
         gzclose(g);
     }
 }
+// BGZF as bgzip writes it: independent gzip members of <= 64 KiB with a "BC" extra subfield holding the block size, closed by an empty
+// block. `plain_member_at`: block index at which an ordinary gzip member (no extra field) is spliced in instead -- still a valid
+// gzip file for gzread, but not BGZF from there on.
+static void write_bgzf(const std::string &path, const std::string &txt, size_t plain_member_at = ~(size_t)0) {
+    FILE *out = fopen(path.c_str(), "wb");
+    const size_t BS = 0xff00;
+    std::vector<unsigned char> comp(BS + 1024);
+    size_t blk = 0;
+    for(size_t x = 0;; x += BS, ++blk) {
+        const size_t len = x < txt.size() ? std::min(BS, txt.size() - x) : 0;
+        if(blk == plain_member_at && len) {
+            fclose(out);
+            gzFile g = gzopen(path.c_str(), "ab6"); gzwrite(g, txt.data() + x, (unsigned)len); gzclose(g);
+            out = fopen(path.c_str(), "ab");
+            continue;
+        }
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = (Bytef *)(len ? txt.data() + x : ""); zs.avail_in = (uInt)len;
+        zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
+        deflate(&zs, Z_FINISH);
+        const size_t clen = comp.size() - zs.avail_out;
+        deflateEnd(&zs);
+        const unsigned bsize = (unsigned)(clen + 25);                    // total block size - 1
+        const unsigned char hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (unsigned char)(bsize & 0xff), (unsigned char)(bsize >> 8)};
+        const unsigned long crc = crc32(crc32(0L, Z_NULL, 0), (const Bytef *)txt.data() + (len ? x : 0), (uInt)len);
+        const unsigned char tail[8] = {(unsigned char)crc, (unsigned char)(crc >> 8), (unsigned char)(crc >> 16), (unsigned char)(crc >> 24),
+                                       (unsigned char)len, (unsigned char)(len >> 8), (unsigned char)(len >> 16), (unsigned char)(len >> 24)};
+        fwrite(hdr, 1, 18, out); fwrite(comp.data(), 1, clen, out); fwrite(tail, 1, 8, out);
+        if(!len) break;                                                   // that was the end-of-file block
+    }
+    fclose(out);
+}
 // process_dataset's reader, batch by batch: fill_pinned while the index serves, read_pinned (kseq) after the hand-over
 static std::vector<Rec> by_batches(const std::string &p1, const std::string *p2, unsigned nt, int chunk, size_t *n_batches, size_t *n_handovers) {
     std::vector<Rec> out;
@@ -162,6 +195,23 @@ int main(int argc, char **argv) {
             }
         }
     }
+    // BGZF: blocks inflate in parallel out of the mapping; a file that stops being BGZF half way is finished by kseq / gzread
+    for(auto &c : cases) {
+        for(int spliced = 0; spliced < 2; ++spliced) {
+            const std::string path = dir + "/" + c.name + (spliced ? "_spliced" : "") + ".bgz";
+            write_bgzf(path, c.txt, spliced ? 20 : ~(size_t)0);
+            { detail::SimpleFile probe(path.c_str(), 2); if(!probe.gz || !probe.gz->bgzf) { printf("bgzf %s not detected MISMATCH\n", c.name); ++failures; } }
+            const auto ref = by_kseq(path);
+            for(unsigned nt : {1u, 4u}) {
+                bool used = false, fell = false;
+                const auto got = by_index(path, nt, &used, &fell);
+                const bool same = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin());
+                const bool ok = same && used == c.expect_index && fell == (c.expect_fallback || spliced);
+                printf("bgzf %s spliced=%d nt=%u records=%zu/%zu index=%d fallback=%d %s\n", c.name, spliced, nt, got.size(), ref.size(), (int)used, (int)fell, ok ? "ok" : "MISMATCH");
+                failures += !ok;
+            }
+        }
+    }
     // batches (fill_pinned / read_pinned), single and mate files; mates of different line lengths so that their windows do not line up;
     // the second mate file of the last pairing is one record short (bseq_read stops there)
     {
@@ -174,16 +224,18 @@ int main(int argc, char **argv) {
             if(i + 1 < 15000) m2short += r2;
             m2multi += i == 9000 ? "@p9000/2\nACGT\nACGT\n+\nIIIIIIII\n" : r2;
         }
-        struct Pairing { const char *name; std::string a, b; bool gz_a, gz_b; size_t handovers; };   // handovers: kseq takes over (not at a clean end)
+        struct Pairing { const char *name; std::string a, b; int gz_a, gz_b; size_t handovers; };   // 0 plain, 1 gzip, 2 BGZF   // handovers: kseq takes over (not at a clean end)
         std::vector<Pairing> pairings = {{"single_plain", m1, "", false, false, 0}, {"single_gz", m1, "", true, false, 0},
                                          {"pair_plain", m1, m2, false, false, 0}, {"pair_gz", m1, m2, true, true, 0}, {"pair_mixed", m1, m2, false, true, 0},
                                          {"pair_gz_short", m1, m2short, true, true, 1}, {"pair_short_gz", m2short, m1, true, true, 1},
-                                         {"pair_gz_multiline", m1, m2multi, true, true, 1}};
+                                         {"pair_gz_multiline", m1, m2multi, true, true, 1},
+                                         {"single_bgzf", m1, "", 2, 0, 0}, {"pair_bgzf", m1, m2, 2, 2, 0}, {"pair_bgzf_gz_short", m1, m2short, 2, 1, 1}};
         for(auto &pr : pairings) {
             const std::string pa = dir + "/" + pr.name + "_1" + (pr.gz_a ? ".gz" : ".fq"), pb = dir + "/" + pr.name + "_2" + (pr.gz_b ? ".gz" : ".fq");
-            pr.gz_a ? write_gz(pa, pr.a) : write(pa, pr.a);
+            auto put = [](int kind, const std::string &path, const std::string &txt) { kind == 2 ? write_bgzf(path, txt) : kind == 1 ? write_gz(path, txt) : write(path, txt); };
+            put(pr.gz_a, pa, pr.a);
             const bool paired = !pr.b.empty();
-            if(paired) { pr.gz_b ? write_gz(pb, pr.b) : write(pb, pr.b); }
+            if(paired) put(pr.gz_b, pb, pr.b);
             std::vector<Rec> ref;
             {
                 const auto ra = by_kseq(pa);

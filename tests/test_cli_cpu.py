@@ -86,8 +86,8 @@ def test_hist(cli, tmp_path):
 
 
 def test_parallel_ingest_index_matches_kseq(tmp_path):
-    """detail::SimpleFile (parallel index of plain or gzip 4-line FASTQ / 2-line FASTA, hand-over to kseq elsewhere) yields the
-    same records as the kseq state machine, window by window and batch by batch (single and mate files):
+    """detail::SimpleFile (parallel index of plain, gzip or BGZF 4-line FASTQ / 2-line FASTA, hand-over to kseq elsewhere) yields
+    the same records as the kseq state machine, window by window and batch by batch (single and mate files):
     tests/host/ingest_index.cpp, host code only."""
     import shutil
     import subprocess
@@ -97,4 +97,4 @@ def test_parallel_ingest_index_matches_kseq(tmp_path):
     r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, src, "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 51, r.stdout
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 77, r.stdout

@@ -36,7 +36,27 @@ def setup(tmp_path_factory, oracle, genomes):
     return dict(cli=cli, dir=d, nodes=nodes, db=db, dbo=dbo, tax=tax)
 
 
+def bgzf_bytes(data, block=0xff00):
+    """`data` as bgzip writes it: independent gzip members with a "BC" extra subfield (block size - 1), then an empty block."""
+    import struct
+    import zlib
+    out = bytearray()
+    for x in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if x is None else data[x:x + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
+        out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    return bytes(out)
+
+
 def write_fastq(path, names, seqs, quals=None):
+    if str(path).endswith(".bgz"):
+        txt = "".join(">%s extra\n%s\n" % (n, s) if quals is None else "@%s extra\n%s\n+\n%s\n" % (n, s, quals[i])
+                      for i, (n, s) in enumerate(zip(names, seqs)))
+        with open(path, "wb") as f:
+            f.write(bgzf_bytes(txt.encode(), block=3000))
+        return
     op = gzip.open if str(path).endswith(".gz") else open
     with op(path, "wt") as f:
         for i, (n, s) in enumerate(zip(names, seqs)):
@@ -152,7 +172,7 @@ def test_build_entropy_minimised(setup, oracle, genomes):
 
 def test_classify_paired_plain_equals_gz(setup, genomes):
     """Mate files through the parallel index (plain FASTQ with small windows, gzip with small and with default inflate
-    windows, 4 threads) give the bytes the kseq path gives for the same files -- including the hand-over when the second
+    windows, BGZF, 4 threads) give the bytes the kseq path gives for the same files -- including the hand-over when the second
     file ends early (bseq_read's warning)."""
     b, _ = H.genome_records(genomes, 1)
     rng = np.random.default_rng(18)
@@ -165,7 +185,8 @@ def test_classify_paired_plain_equals_gz(setup, genomes):
     q1 = ["I" * len(s) for s in s1]; q2 = ["@" + "F" * (len(s) - 1) for s in s2]
     outs = {}
     kinds = {"plain": (".fq", {"BNS_B200_FASTQ_WINDOW": "40000"}), "gz_kseq": (".fq.gz", {"BNS_B200_INGEST": "kseq"}),
-             "gz_windows": (".fq.gz", {"BNS_B200_GZ_WINDOW": "50000"}), "gz": (".fq.gz", {})}
+             "gz_windows": (".fq.gz", {"BNS_B200_GZ_WINDOW": "50000"}), "gz": (".fq.gz", {}),
+             "bgzf": (".fq.bgz", {"BNS_B200_GZ_WINDOW": "140000"})}          # blocks inflated in parallel out of the mapping
     for kind, (ext, env) in kinds.items():
         f1, f2 = setup["dir"] / ("pp1" + ext), setup["dir"] / ("pp2" + ext)
         write_fastq(f1, n1, s1, q1); write_fastq(f2, n2[:880], s2[:880], q2[:880])       # the mates' file is 20 records short
