@@ -4,6 +4,7 @@ The genome fixture (tests/golden/genomes4.npz) is DERIVED data: the four archaea
 reference ships as test/GCF_*.fna.gz plus phiX (test/phix.fa), 2-bit packed by
 tests/golden/make_golden.py (all five are pure upper-case ACGT). Nothing here reads /root/reference.
 """
+import gzip
 import os
 
 import numpy as np
@@ -134,3 +135,33 @@ def digest(kmers):
         x = np.bitwise_xor.reduce(km * np.uint64(0x9E3779B97F4A7C15) + idx) if n else np.uint64(0)
         s = km.sum(dtype=np.uint64) if n else np.uint64(0)
     return int(n), int(x), int(s)
+
+
+def bgzf_bytes(data, block=0xff00):
+    """`data` as bgzip writes it: independent gzip members with a "BC" extra subfield (block size - 1), then an empty block."""
+    import struct
+    import zlib
+    out = bytearray()
+    for x in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if x is None else data[x:x + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
+        out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    return bytes(out)
+
+
+def write_fastq(path, names, seqs, quals=None):
+    if str(path).endswith(".bgz"):
+        txt = "".join(">%s extra\n%s\n" % (n, s) if quals is None else "@%s extra\n%s\n+\n%s\n" % (n, s, quals[i])
+                      for i, (n, s) in enumerate(zip(names, seqs)))
+        with open(path, "wb") as f:
+            f.write(bgzf_bytes(txt.encode(), block=3000))
+        return
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "wt") as f:
+        for i, (n, s) in enumerate(zip(names, seqs)):
+            if quals is None:
+                f.write(">%s extra\n%s\n" % (n, s))
+            else:
+                f.write("@%s extra\n%s\n+\n%s\n" % (n, s, quals[i]))

@@ -98,3 +98,60 @@ def test_parallel_ingest_index_matches_kseq(tmp_path):
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 77, r.stdout
+
+
+def test_cli_host_pipeline_ingest_kinds(tmp_path, cli):
+    """`bonsai classify`'s host pipeline end to end without a device: the CLI source is linked against a DUMMY ABI
+    (tests/host/abi_stub.cpp: results are an arbitrary function of each record's bases) and must print byte-identical
+    text whichever way the same records are read -- kseq, or the parallel index over plain, gzip and BGZF files, at several
+    window / batch sizes and thread counts, single and mate files (the mates' file 7 records short), Kraken and FASTQ text."""
+    import hashlib
+    import shutil
+    from helpers import write_fastq
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = str(tmp_path / "bonsai_stub")
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, os.path.join(root, "bonsai_b200", "csrc", "cli", "bonsai_main.cpp"),
+                        os.path.join(here, "host", "abi_stub.cpp"), "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    d = tmp_path
+    keys = np.arange(1, 100, dtype=np.uint64)
+    with open(d / "pairs.bin", "wb") as f:
+        f.write(struct.pack("<Q", keys.size)); f.write(keys.tobytes()); f.write(np.full(keys.size, 11, np.uint32).tobytes())
+    subprocess.check_call([cli, "dbwrite", str(d / "t.db"), "31", "31", str(d / "pairs.bin")])
+    (d / "nodes.dmp").write_text("1\t|\t1\t|\n2\t|\t1\t|\n10\t|\t2\t|\n11\t|\t10\t|\n12\t|\t10\t|\n")
+    rng = np.random.default_rng(3)
+
+    def mk(n, tag):
+        names = ["read%d/%s" % (i, tag) for i in range(n)]
+        seqs, quals = [], []
+        for l in rng.integers(20, 260, n):
+            seqs.append(np.frombuffer(b"ACGTN", np.uint8)[rng.choice(5, p=[.245, .245, .245, .245, .02], size=int(l))].tobytes().decode())
+            quals.append(rng.integers(33, 93, int(l), dtype=np.uint8).tobytes().decode())
+        return names, seqs, quals
+    a, b = mk(9000, "1"), mk(8993, "2")
+    for ext in (".fq", ".fq.gz", ".fq.bgz"):
+        write_fastq(d / ("r1" + ext), *a); write_fastq(d / ("r2" + ext), *b)
+    for ext in (".fa", ".fa.gz", ".fa.bgz"):
+        write_fastq(d / ("s" + ext), a[0], a[1])
+
+    def run(env, flags, *files):
+        r = subprocess.run([exe, "classify"] + flags + [str(d / "t.db"), str(d / "nodes.dmp")] + [str(d / f) for f in files],
+                           capture_output=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        return hashlib.md5(r.stdout).hexdigest(), r.stdout.count(b"\n"), r.stderr
+
+    kinds = [({"BNS_B200_INGEST": "kseq"}, ".gz", "50000"), ({"BNS_B200_FASTQ_WINDOW": "150000"}, "", "50000"), ({}, "", "3000000"),
+             ({}, ".gz", "50000"), ({"BNS_B200_GZ_WINDOW": "100000"}, ".gz", "50000"), ({"BNS_B200_GZ_WINDOW": "140000"}, ".bgz", "50000"),
+             ({}, ".bgz", "400000")]
+    for flags, per_record in ((["-a", "-p", "4"], 1), (["-a", "-f", "-k", "-p", "3"], 4), (["-p", "5"], None)):
+        single = [run(env, flags + ["-c", c], "r1.fq" + ext) for env, ext, c in kinds]
+        assert len({x[0] for x in single}) == 1, (flags, single)
+        assert per_record is None or single[0][1] == 9000 * per_record
+        paired = [run(env, flags + ["-c", c], "r1.fq" + ext, "r2.fq" + ext) for env, ext, c in kinds]
+        paired.append(run({"BNS_B200_GZ_WINDOW": "140000"}, flags + ["-c", "50000"], "r1.fq", "r2.fq.bgz"))
+        assert len({x[0] for x in paired}) == 1, (flags, paired)
+        assert all(b"the 2nd file has fewer sequences" in x[2] for x in paired)
+    fasta = [run(env, ["-a", "-f", "-k", "-p", "4", "-c", c], "s.fa" + ext) for env, ext, c in kinds]
+    assert len({x[0] for x in fasta}) == 1 and fasta[0][1] == 9000 * 4

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import helpers as H
+from helpers import write_fastq
 from oracle import pyoracle as po
 
 pytestmark = pytest.mark.gpu
@@ -34,36 +35,6 @@ def setup(tmp_path_factory, oracle, genomes):
     db = d / "four.db"
     subprocess.check_call([cli, "build", "-k", "31", str(db), str(nodes)] + args)
     return dict(cli=cli, dir=d, nodes=nodes, db=db, dbo=dbo, tax=tax)
-
-
-def bgzf_bytes(data, block=0xff00):
-    """`data` as bgzip writes it: independent gzip members with a "BC" extra subfield (block size - 1), then an empty block."""
-    import struct
-    import zlib
-    out = bytearray()
-    for x in list(range(0, len(data), block)) + [None]:
-        chunk = b"" if x is None else data[x:x + block]
-        co = zlib.compressobj(6, zlib.DEFLATED, -15)
-        comp = co.compress(chunk) + co.flush()
-        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
-        out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
-    return bytes(out)
-
-
-def write_fastq(path, names, seqs, quals=None):
-    if str(path).endswith(".bgz"):
-        txt = "".join(">%s extra\n%s\n" % (n, s) if quals is None else "@%s extra\n%s\n+\n%s\n" % (n, s, quals[i])
-                      for i, (n, s) in enumerate(zip(names, seqs)))
-        with open(path, "wb") as f:
-            f.write(bgzf_bytes(txt.encode(), block=3000))
-        return
-    op = gzip.open if str(path).endswith(".gz") else open
-    with op(path, "wt") as f:
-        for i, (n, s) in enumerate(zip(names, seqs)):
-            if quals is None:
-                f.write(">%s extra\n%s\n" % (n, s))
-            else:
-                f.write("@%s extra\n%s\n+\n%s\n" % (n, s, quals[i]))
 
 
 def test_build_matches_oracle(setup, oracle):
