@@ -1124,15 +1124,41 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
         }
     });
     std::string cks;
-    auto flush = [&]() {
-        std::fflush(out);
-        size_t put = 0;
-        while(put < cks.size()) {
-            const ssize_t r = ::write(fn, cks.data() + put, cks.size() - put);
-            if(r <= 0) BNS_RUNTIME_ERROR("write failed");
-            put += (size_t)r;
+    // text leaves through a writer thread (at most two buffers queued), so write(2) overlaps the next batch
+    std::fflush(out);
+    std::mutex wmu;
+    std::condition_variable wcv;
+    std::deque<std::string> wq;
+    bool wdone = false;
+    std::string werr;
+    std::thread writer([&]() {
+        for(;;) {
+            std::string s;
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return !wq.empty() || wdone; });
+                if(wq.empty()) return;
+                s = std::move(wq.front()); wq.pop_front();
+            }
+            wcv.notify_all();
+            if(!werr.empty()) continue;                                    // after a failed write: drain and drop
+            size_t put = 0;
+            while(put < s.size()) {
+                const ssize_t r = ::write(fn, s.data() + put, s.size() - put);
+                if(r <= 0) { std::lock_guard<std::mutex> lk(wmu); werr = "write failed"; break; }
+                put += (size_t)r;
+            }
         }
+    });
+    auto flush = [&]() {
+        if(cks.empty()) return;
+        std::unique_lock<std::mutex> lk(wmu);
+        wcv.wait(lk, [&] { return wq.size() < 2; });
+        if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
+        wq.push_back(std::move(cks));
         cks.clear();
+        lk.unlock();
+        wcv.notify_all();
     };
     bool first = true;
     std::string failure;
@@ -1176,12 +1202,16 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
         cv.notify_all();
     }
     reader.join();
+    if(failure.empty()) { try { flush(); } catch(const std::exception &e) { failure = e.what(); } }
+    { std::lock_guard<std::mutex> lk(wmu); wdone = true; }
+    wcv.notify_all();
+    writer.join();
     if(!reader_error.empty()) BNS_RUNTIME_ERROR(reader_error);
     if(!failure.empty()) BNS_RUNTIME_ERROR(failure);
+    if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
-    flush();
     if(verbose)
-        std::fprintf(stderr, "[process_dataset] %zu batches: waiting for the reader %.2f s, classify + format %.2f s, write %.2f s\n",
+        std::fprintf(stderr, "[process_dataset] %zu batches: waiting for the reader %.2f s, classify + format %.2f s, waiting for the writer %.2f s\n",
                      n_batches, t_wait, t_classify, t_write);
 }
 
