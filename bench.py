@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -286,10 +286,20 @@ def main():
         b.record(stream)
     t_end.record(stream)
     barrier()
-    clk = clocks.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     gpu_launches = ctx.stats()["kernel_launches"] - launches0
+    # a timed region shorter than two nvidia-smi periods (small --steps): keep the same kernel running, untimed, until two
+    # clock samples under this load exist (at most 1 s), and say so
+    clocks_extended = False
+    if clocks.proc is not None and len(clocks.rows) < 2:
+        clocks_extended = True
+        t_ext = time.perf_counter()
+        while len(clocks.rows) < 2 and time.perf_counter() - t_ext < 1.0:
+            step_device()
+            torch.cuda.synchronize()
+    clk = clocks.stop()
+    clk["sampled_past_timed_region"] = clocks_extended
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
