@@ -71,9 +71,14 @@ class ClockSampler:
             if len(r) < 8:
                 continue
             try:
-                sm.append(float(r[1])); mx = float(r[2]); pw.append(float(r[3]))
+                clk, clk_max = float(r[1]), float(r[2])
             except ValueError:
                 continue
+            sm.append(clk); mx = clk_max
+            try:
+                pw.append(float(r[3]))
+            except ValueError:                       # power.draw can read [N/A]: the clocks of the row still count
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
