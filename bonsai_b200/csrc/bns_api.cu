@@ -14,6 +14,7 @@
 
 #include "../../include/bonsai_b200.h"
 #include "bns_device.cuh"
+#include "bns_host_util.h"
 #include "bns_kernels.h"
 
 using namespace bns;
@@ -560,29 +561,7 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
     ctx->no_minimizer = false;
     auto occupied = [&](u64 i) { return ((flags[i >> 4] >> ((i & 0xfu) << 1)) & 3u) == 0; };   // !__ac_iseither, khash64.h:171
     u64 n_keys = 0;
-    std::vector<u32> values;
-    {
-        std::vector<u32> tmp;
-        tmp.reserve(1 << 16);
-        for(u64 i = 0; i < n_buckets; ++i)
-            if(occupied(i)) {
-                ++n_keys;
-                tmp.push_back(vals[i]);
-                if(tmp.size() >= (1u << 22)) {
-                    std::sort(tmp.begin(), tmp.end());
-                    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                    std::vector<u32> merged;
-                    std::set_union(values.begin(), values.end(), tmp.begin(), tmp.end(), std::back_inserter(merged));
-                    values.swap(merged);
-                    tmp.clear();
-                }
-            }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        std::vector<u32> merged;
-        std::set_union(values.begin(), values.end(), tmp.begin(), tmp.end(), std::back_inserter(merged));
-        values.swap(merged);
-    }
+    const std::vector<u32> values = distinct_values_khash(vals, flags, n_buckets, &n_keys);   // the value dictionary (bns_host_util.h)
     for(u32 b = choose_bits(n_keys, (u32)values.size());; ++b) {
         free_table(ctx);
         ctx->values = values;
@@ -616,9 +595,7 @@ int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
     if(!ctx || (n && (!keys || !vals))) return ctx ? ctx->fail(BNS_E_INVAL, "null key/value arrays") : BNS_E_INVAL;
     CK(cudaSetDevice(ctx->device));
     ctx->no_minimizer = false;
-    std::vector<u32> values(vals, vals + n);
-    std::sort(values.begin(), values.end());
-    values.erase(std::unique(values.begin(), values.end()), values.end());
+    const std::vector<u32> values = distinct_values(vals, n);
     for(u32 b = choose_bits(n, (u32)values.size());; ++b) {
         free_table(ctx);
         ctx->values = values;

@@ -59,3 +59,17 @@ def test_no_oracle_in_product():
                 txt = open(os.path.join(dp, fn)).read()
                 for b in banned:
                     assert b not in txt, (fn, b)
+
+
+def test_value_dictionary_host_code(tmp_path):
+    """The loader's distinct-value pass (bonsai_b200/csrc/bns_host_util.h: bitmap for values < 2^24, sort-merge above) against
+    sort + unique over khash arrays with empty / deleted / occupied buckets: tests/host/distinct_values.cpp, host code only."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = str(tmp_path / "distinct_values")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "distinct_values.cpp")
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 9, r.stdout
