@@ -560,8 +560,9 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
     CK(cudaSetDevice(ctx->device));
     ctx->no_minimizer = false;
     auto occupied = [&](u64 i) { return ((flags[i >> 4] >> ((i & 0xfu) << 1)) & 3u) == 0; };   // !__ac_iseither, khash64.h:171
-    u64 n_keys = 0;
-    const std::vector<u32> values = distinct_values_khash(vals, flags, n_buckets, &n_keys);   // the value dictionary (bns_host_util.h)
+    uint64_t n_occupied = 0;
+    const std::vector<u32> values = distinct_values_khash(vals, flags, n_buckets, &n_occupied);   // the value dictionary (bns_host_util.h)
+    const u64 n_keys = n_occupied;
     for(u32 b = choose_bits(n_keys, (u32)values.size());; ++b) {
         free_table(ctx);
         ctx->values = values;
