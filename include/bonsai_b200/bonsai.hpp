@@ -437,7 +437,7 @@ struct ClassifierGeneric {
     // classifier.h:155-166; `map` = the database whose raw khash arrays go to the device
     ClassifierGeneric(const Database &map, const spvec_t &spaces, u8 k, u16 wsz, int num_threads = 16, bool emit_all = true,
                       bool emit_fastq = true, bool emit_kraken = false, bool canonicalize = true)
-        : sp_(k, wsz, spaces), enc_(sp_, canonicalize), nt_(num_threads > 0 ? (u16)num_threads : (u16)1), output_flag_(0) {
+        : sp_(k, wsz, spaces), enc_(sp_, canonicalize), nt_(num_threads > 0 ? (u16)num_threads : (u16)std::max(1u, std::thread::hardware_concurrency())), output_flag_(0) {
         set_emit_all(emit_all); set_emit_fastq(emit_fastq); set_emit_kraken(emit_kraken);
         h_ = detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING);
         detail::check(h_->h, bns_b200_load_table(h_->h, map.keys.data(), map.vals.data(), map.flags.data(), map.n_buckets),
