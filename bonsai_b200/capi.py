@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BNS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbonsai_b200.so")
 
 SCORE_LEX, SCORE_ENTROPY = 0, 1
-API_STRING, API_PATH = 0, 1
+API_STRING, API_PATH, API_ITER = 0, 1, 2
 CAST_SATURATE, CAST_WRAP = 0, 1
 MAX_K = 32
 

@@ -116,7 +116,7 @@ thread_local std::string g_open_err;
 int derive_encoder(bns_b200_ctx *ctx) {
     const bns_b200_config &cf = ctx->cfg;
     if(cf.k < 1 || cf.k > BNS_MAX_K) return ctx->fail(BNS_E_INVAL, "k must be in [1,32], got %u", cf.k);
-    if(cf.score > BNS_SCORE_ENTROPY || cf.api > BNS_API_PATH || cf.entropy_cast > BNS_CAST_WRAP)
+    if(cf.score > BNS_SCORE_ENTROPY || cf.api > BNS_API_ITER || cf.entropy_cast > BNS_CAST_WRAP)
         return ctx->fail(BNS_E_INVAL, "bad score/api/entropy_cast selector");
     EncParams &P = ctx->enc;
     memset(&P, 0, sizeof P);
@@ -127,7 +127,7 @@ int derive_encoder(bns_b200_ctx *ctx) {
     if(c > (u32)CMAX) return ctx->fail(BNS_E_INVAL, "comb size %u exceeds the supported maximum %d", c, CMAX);
     const u32 w = std::max<int>((int)c, (int)cf.w);
     ctx->c = c; ctx->w = w; ctx->unspaced = unspaced; ctx->unwindowed = (k == w);
-    ctx->canon = cf.canonicalize && unspaced;                      // encoder.h:148-150
+    ctx->canon = cf.canonicalize && (unspaced || cf.api == BNS_API_ITER);   // encoder.h:148-150 (the iterator calls do not look at it)
     ctx->W = w - c + 1;
     P.k = k; P.c = c; P.W = ctx->W;
     P.cast_wrap = cf.entropy_cast == BNS_CAST_WRAP;
@@ -158,7 +158,11 @@ int derive_encoder(bns_b200_ctx *ctx) {
     const bool ent = cf.score == BNS_SCORE_ENTROPY;
     const bool windowed = !ctx->unwindowed;
     P.score_kind = SC_LEX;
-    if(cf.api == BNS_API_STRING) {
+    if(cf.api == BNS_API_ITER) {
+        // next_canonicalized_minimizer / next_minimizer call by call (encoder.h:616-628): kmer(pos) elements, every window
+        // result kept
+        P.family = FAM_K; P.canon_elem = ctx->canon ? 1 : 0; P.filter_none = 0; P.score_kind = ent ? SC_ENT_NOTFULL : SC_LEX;
+    } else if(cf.api == BNS_API_STRING) {
         if(ctx->canon) {
             if(!windowed) { P.family = FAM_U; P.canon_elem = 1; }
             else if(ent) { P.family = FAM_R; P.score_kind = SC_ENT_ROLL; P.canon_emit = 1; P.tail_flush = 1; }
@@ -736,6 +740,7 @@ int bns_b200_reconfigure(bns_b200_t *ctx, const bns_b200_config *cfg) {
 int bns_b200_build_begin(bns_b200_t *ctx, uint64_t max_kmers, const uint32_t *taxids, uint32_t n_taxids) {
     if(!ctx || !taxids || !n_taxids) return ctx ? ctx->fail(BNS_E_INVAL, "no taxids") : BNS_E_INVAL;
     if(!ctx->tax_loaded) return ctx->fail(BNS_E_STATE, "load the taxonomy before building");
+    if(ctx->cfg.api == BNS_API_ITER) return ctx->fail(BNS_E_INVAL, "BNS_API_ITER is an encode-only configuration");
     CK(cudaSetDevice(ctx->device));
     // value dictionary = the taxids and all their ancestors (every lca result lives there), plus taxid 1
     std::vector<u32> order(ctx->tax_child.size());
@@ -1078,6 +1083,7 @@ int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *of
 
 // ---- classify --------------------------------------------------------------------------------------
 static int classify_ready(bns_b200_t *ctx) {
+    if(ctx->cfg.api == BNS_API_ITER) return ctx->fail(BNS_E_INVAL, "BNS_API_ITER is an encode-only configuration");
     if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded");
     return finalize_taxonomy(ctx);
 }

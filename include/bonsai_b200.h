@@ -42,7 +42,14 @@ enum { BNS_SCORE_LEX = 0, BNS_SCORE_ENTROPY = 1 };
  *                   spaced seeds emit nothing there -- reference quirk)
  *   BNS_API_PATH    Encoder::for_each_canon / for_each_uncanon on one record, encoder.h:448-464 (what the
  *                   database builder uses; spaced seeds work: for_each_uncanon_spaced, encoder.h:233) */
-enum { BNS_API_STRING = 0, BNS_API_PATH = 1 };
+/*   BNS_API_ITER    the call-by-call surface: assign(), then next_canonicalized_minimizer() (canonicalize != 0) or
+ *                   next_minimizer() (== next_kmer() when the window is the comb) once per position while
+ *                   has_next_kmer(), encoder.h:201-206,594-628. Nothing is filtered: the stream holds the value of every
+ *                   call from the first full window on (the W-1 calls before it return ENCODE_OVERFLOW by
+ *                   construction, qmap.h:79-87), ENCODE_OVERFLOW included where an invalid k-mer wins its window.
+ *                   `canonicalize` is taken as given here, also for spaced seeds (next_canonicalized_minimizer does not
+ *                   look at canonicalize_). Encode only: the classify and build calls refuse this configuration. */
+enum { BNS_API_STRING = 0, BNS_API_PATH = 1, BNS_API_ITER = 2 };
 /* The entropy score casts a negative double to u64 (encoder.h:337, :55-58), which is UB; an x86-64 build of
  * the reference saturates (AVX-512 vcvttsd2usi) or wraps (cvttsd2si sequence) depending on -march. */
 enum { BNS_CAST_SATURATE = 0, BNS_CAST_WRAP = 1 };

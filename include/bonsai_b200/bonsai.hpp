@@ -233,6 +233,30 @@ class Encoder {
         if(!p) p = detail::open_handle(sp_, ScoreType::id, canonicalize_, path_api ? BNS_API_PATH : BNS_API_STRING);
         return p.get();
     }
+    // call-by-call state (assign / next_*)
+    const char *s_ = nullptr;
+    u64 l_ = 0, pos_ = 0;
+    int iter_kind_ = -1;                               // 0 next_kmer, 1 next_minimizer, 2 next_canonicalized_minimizer
+    std::vector<u64> iter_;                            // iter_[p]: what call number p returns
+    std::shared_ptr<detail::Handle> iter_h_[3];
+    u64 iter_value(int kind) {
+        if(!has_next_kmer()) return ENCODE_OVERFLOW;   // the reference only asserts here
+        if(iter_kind_ != kind) {
+            if(pos_ != 0) BNS_RUNTIME_ERROR("Encoder: one kind of next_*() call per assigned string");
+            // next_kmer is the window-of-one case of next_minimizer: the same comb with w = c
+            const Spacer sp = kind == 0 ? Spacer(sp_.k_, 0, sp_.sub1()) : sp_;
+            if(!iter_h_[kind]) iter_h_[kind] = detail::open_handle(sp, ScoreType::id, kind == 2, BNS_API_ITER);
+            bns_b200_t *h = iter_h_[kind]->h;
+            const u64 npos = l_ - sp_.c_ + 1, lead = std::min<u64>(npos, sp.w_ - sp.c_);   // calls before the first full window
+            iter_.assign(npos + 1, ENCODE_OVERFLOW);
+            const u64 offs[2] = {0, l_}, ooffs[2] = {0, npos - lead + 1};
+            u32 count = 0;
+            detail::check(h, bns_b200_encode_batch(h, s_, offs, 1, iter_.data() + lead, ooffs, &count), "bns_b200_encode_batch");
+            if(count != npos - lead) BNS_RUNTIME_ERROR("Encoder: unexpected stream length from the device");
+            iter_kind_ = kind;
+        }
+        return iter_[pos_++];
+    }
     template <typename F>
     void run(const F &fn, const char *str, u64 l, bool path_api) {
         bns_b200_t *h = get(path_api)->h;
@@ -260,6 +284,16 @@ public:
         detail::KSeq ks(path);
         while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
     }
+    // ---- the call-by-call surface, encoder.h:201-206,594-628 ---------------------------------------------------------
+    // assign() borrows the string. The first next_*() call after it computes the value of that call for EVERY position of
+    // the string on the device (one BNS_API_ITER encode: nothing filtered, ENCODE_OVERFLOW where the reference returns it --
+    // an invalid base under the comb, a window that is not full yet, an invalid k-mer winning its window) and the calls
+    // hand them out one by one. One kind of call per assigned string (the reference shares pos_ and qmap_ between them).
+    void assign(const char *s, u64 l) { s_ = s; l_ = l; pos_ = 0; iter_kind_ = -1; }
+    int has_next_kmer() const { return (pos_ + sp_.c_ - 1) < l_; }                       // encoder.h:594-597
+    u64 next_kmer() { return iter_value(0); }                                            // kmer(pos_++), :601-604
+    u64 next_minimizer() { return iter_value(1); }                                       // :616-621
+    u64 next_canonicalized_minimizer() { return iter_value(2); }                         // :622-628
     // batched form of the string overload: fn(sequence index, kmer)
     template <typename F> void for_each_batch(const F &fn, const char *bases, const u64 *offsets, u64 n) {
         bns_b200_t *h = get(false)->h;

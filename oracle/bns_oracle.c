@@ -372,7 +372,18 @@ void bo_for_each(const bo_spacer *sp, int score, int canon, int api, int cast_mo
     circus_init(&e.ent, sp->k);
     /* assign(), encoder.h:201-206, then for_each(), :416-442 */
     if(!enc_has_next(&e)) { qmap_free(&e.q); return; }
-    if(api == BO_API_STRING) {
+    if(api == BO_API_ITER) {
+        /* next_canonicalized_minimizer (encoder.h:622-628; canonicalises whatever canonicalize_ says) or next_minimizer
+         * (:616-621), one call per position; the calls made before the window fills return ~0 and are not reported */
+        const uint64_t wsz = (uint64_t)sp->w - sp->c + 1;
+        uint64_t calls = 0;
+        while(enc_has_next(&e)) {
+            uint64_t nk = enc_kmer(&e, e.pos++);
+            if(canon) nk = bo_canonical(nk, sp->k);
+            const uint64_t m = qmap_next(&e.q, nk, enc_score(&e, nk));
+            if(++calls >= wsz) fn(m, ctx);
+        }
+    } else if(api == BO_API_STRING) {
         if(e.canon) {
             if(sp->unwindowed) {
                 if(sp->unspaced) fe_unspaced_unwindowed(&e, 1, fn, ctx);

@@ -24,7 +24,10 @@ extern "C" {
 enum { BO_SCORE_LEX = 0, BO_SCORE_ENTROPY = 1 };
 /* api 0: Encoder::for_each(fn, str, l) dispatch (encoder.h:416-442) -- what classify_seq calls
  * api 1: the path/kseq overloads applied to one record (encoder.h:448-464) -- what the DB builder calls */
-enum { BO_API_STRING = 0, BO_API_PATH = 1 };
+/* api 2: the call-by-call surface (encoder.h:201-206,594-628): assign(), then next_canonicalized_minimizer() (canon) or
+ *        next_minimizer() once per position while has_next_kmer(); every return value from the first full window on is
+ *        reported, ENCODE_OVERFLOW included (the W-1 calls before it return ENCODE_OVERFLOW by construction) */
+enum { BO_API_STRING = 0, BO_API_PATH = 1, BO_API_ITER = 2 };
 /* (u64) of an out-of-range double is UB in C++; x86-64 gives one of two behaviours:
  * SATURATE = AVX-512 vcvttsd2usi, WRAP = pre-AVX-512 cvttsd2si sequence. */
 enum { BO_CAST_SATURATE = 0, BO_CAST_WRAP = 1 };

@@ -17,7 +17,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SCORE_LEX, SCORE_ENTROPY = 0, 1
-API_STRING, API_PATH = 0, 1
+API_STRING, API_PATH, API_ITER = 0, 1, 2
 CAST_SATURATE, CAST_WRAP = 0, 1
 
 _u16p = C.POINTER(C.c_uint16)

@@ -39,10 +39,20 @@ spvec_t make_gaps(unsigned k, const uint16_t *gaps) {
 // api: 0 = string overload for_each(fn, str, l)        (what classify_seq calls)
 //      1 = path-overload semantics on one record: canon ? for_each_canon : for_each_uncanon
 //          (encoder.h:448-464; what the DB builder uses; spaced seeds work here)
+//      2 = call by call: assign(), then next_canonicalized_minimizer() / next_minimizer() while has_next_kmer()
+//          (encoder.h:201-206,594-628); the values from the first full window on, nothing filtered
 template<typename Score, typename F>
-void run_encoder(Encoder<Score> &enc, int api, const char *seq, uint64_t len, const F &fn) {
+void run_encoder(Encoder<Score> &enc, int api, const char *seq, uint64_t len, const F &fn, int iter_canon = 0) {
     if(api == 0) {
         enc.for_each(fn, seq, len);
+    } else if(api == 2) {
+        enc.assign(seq, len);
+        const uint64_t wsz = (uint64_t)enc.sp_.w_ - enc.sp_.c_ + 1;
+        uint64_t calls = 0;
+        while(enc.has_next_kmer()) {
+            const u64 m = iter_canon ? enc.next_canonicalized_minimizer() : enc.next_minimizer();
+            if(++calls >= wsz) fn(m);
+        }
     } else {
         enc.assign(seq, len);
         if(!enc.has_next_kmer()) return;
@@ -67,7 +77,7 @@ int64_t encode_impl(unsigned k, unsigned w, const uint16_t *gaps, int canon, int
     run_encoder(enc, api, seq, len, [&](u64 km) {
         if(n < cap) out[n] = km;
         ++n;
-    });
+    }, canon);
     return (int64_t)n;
 }
 

@@ -634,3 +634,107 @@ def test_minimizer_layout_vs_oracle(capi, oracle, toy_tax, monkeypatch):
         ctx.load_pairs(uk[:1000] & np.uint64((1 << 42) - 1), vals[ui][:1000])
         assert ctx.table_info()["layout"] == 0
     oracle.db_free(D)
+
+
+# ---- the call-by-call Encoder surface (BNS_API_ITER) ---------------------------------------------------------------
+def test_iterator_surface_golden_and_fuzz(capi, oracle):
+    """assign / has_next_kmer / next_minimizer / next_canonicalized_minimizer (encoder.h:201-206,594-628) as one unfiltered
+    stream per sequence: against the vectors of the unmodified reference (tests/golden/golden_iter.json, saturating cast) and,
+    batched and in both cast modes, against the oracle on seeded random sequences (N runs, T runs, multi-tile lengths)."""
+    import json
+    import os
+    with open(os.path.join(H.GOLDEN, "golden_iter.json")) as f:
+        gold = json.load(f)
+    ctxs = {}
+
+    def ctx_for(k, w, gaps, score, canon, cast):
+        key = (k, w, tuple(gaps or ()), score, canon, cast)
+        if key not in ctxs:
+            ctxs[key] = capi.Context(k, w, gaps, score, bool(canon), capi.API_ITER, cast)
+        return ctxs[key]
+    for c in gold["cases"]:
+        b, o = po.pack_reads([c["seq"].encode()])
+        got = ctx_for(c["k"], c["w"], c["gaps"], c["score"], c["canon"], capi.CAST_SATURATE).encode_lists(b, o)[0]
+        assert hx(got) == c["values"], {k: c[k] for k in ("k", "w", "gaps", "score", "canon", "seq")}
+    rng = random.Random(4321)
+    six = [0] * 30
+    for i, g in ((2, 1), (7, 2), (11, 1), (15, 1), (20, 3), (25, 1)):
+        six[i] = g
+    for k, w, gaps in ((31, 0, None), (31, 50, None), (31, 0, six), (31, 70, six), (21, 33, None), (32, 45, None), (13, 200, None)):
+        seqs = []
+        for _ in range(60):
+            L = rng.choice([0, 5, k, 64, 150, 151, 400, 1100])
+            s = "".join(rng.choice(rng.choice(["ACGT", "ACGTN", "ACGTacgt", "T"])) for _ in range(L))
+            if L > 60 and rng.random() < 0.3:
+                p0 = rng.randrange(L - 40)
+                s = s[:p0] + "T" * 40 + s[p0 + 40:]
+            seqs.append(s.encode())
+        b, o = po.pack_reads(seqs)
+        for score in (0, 1):
+            for canon in (0, 1):
+                for cast, ocast in ((capi.CAST_SATURATE, po.CAST_SATURATE), (capi.CAST_WRAP, po.CAST_WRAP)):
+                    if score == 0 and cast == capi.CAST_WRAP:
+                        continue
+                    got = ctx_for(k, w, gaps, score, canon, cast).encode_lists(b, o)
+                    for sq, g in zip(seqs, got):
+                        exp = oracle.encode(sq, k, w, gaps, score, canon, po.API_ITER, cast_mode=ocast)
+                        assert np.array_equal(g, exp), dict(k=k, w=w, gaps=gaps, score=score, canon=canon, cast=cast, seq=sq)
+    # an encode-only configuration: classify refuses it
+    c0 = ctx_for(31, 0, None, 0, 1, capi.CAST_SATURATE)
+    c0.load_pairs(np.array([1, 2, 3], np.uint64), np.array([11, 11, 12], np.uint32))
+    tc, tp = H.toy_tax_arrays()
+    c0.load_taxonomy(tc, tp)
+    b, o = po.pack_reads([b"ACGT" * 40])
+    with pytest.raises(capi.BnsError):
+        c0.classify(b, o)
+    for c in ctxs.values():
+        c.close()
+
+
+def test_cpp_encoder_surface(capi, oracle, tmp_path):
+    """The C++ mirror of the reference's Encoder (include/bonsai_b200/bonsai.hpp): for_each(fn, str, l), the record overloads and
+    assign / has_next_kmer / next_kmer / next_minimizer / next_canonicalized_minimizer, compiled into tests/host/encoder_api.cpp
+    and linked against the library, against streams the oracle computes here."""
+    import os
+    import shutil
+    import subprocess
+    from bonsai_b200 import build
+    here = os.path.dirname(os.path.abspath(__file__))
+    libdir = os.path.dirname(build.build())
+    exe = str(tmp_path / "encoder_api")
+    r = subprocess.run([shutil.which("g++") or "/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, os.path.join(here, "host", "encoder_api.cpp"),
+                        "-L" + libdir, "-lbonsai_b200", "-lz", "-lpthread", "-Wl,-rpath," + libdir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    cast = oracle.host_cast_mode()                     # the mirror picks the cast of THIS host's CPU, as a native build of the reference would
+    BF = (1 << 64) - 1
+    rng = random.Random(99)
+    gapped = [1, 2] + [0] * 28
+    lines = []
+    for k, w, gaps in ((31, 31, None), (31, 50, None), (31, 31, gapped), (31, 60, gapped), (16, 24, None)):
+        cc, ww = oracle.spacer(k, w, gaps)[:2]
+        for trial in range(6):
+            L = rng.choice([0, 20, 34, 150, 300])
+            seq = "".join(rng.choice("ACGT" if trial % 3 else "ACGTN") for _ in range(L))
+            if trial == 0:
+                seq = "ACATGCTAGCATGCTGACTGACTGATCGATCGTA"                                     # test/encoding.cpp:17
+            npos = max(0, len(seq) - cc + 1)
+            for score in (0, 1):
+                for canon in (0, 1):
+                    for kind in range(5):
+                        if kind == 0:
+                            exp = [int(x) for x in oracle.encode(seq, k, w, gaps, score, canon, po.API_STRING, cast_mode=cast)]
+                        elif kind == 1:
+                            exp = [int(x) for x in oracle.encode(seq, k, w, gaps, score, canon, po.API_PATH, cast_mode=cast)]
+                        elif kind == 2:                                                         # kmer(pos) for every position
+                            exp = [int(x) for x in oracle.encode(seq, k, 0, gaps, score, 0, po.API_ITER, cast_mode=cast)]
+                        else:                                                                   # W - 1 calls before the first full window
+                            v = [int(x) for x in oracle.encode(seq, k, w, gaps, score, int(kind == 4), po.API_ITER, cast_mode=cast)]
+                            exp = [BF] * min(npos, ww - cc) + v
+                        if kind >= 2:
+                            assert len(exp) == npos
+                        lines.append("%d %d %d %d %d %s %s %d %s" % (kind, k, w, score, canon, ",".join(map(str, gaps)) if gaps else "-", seq or "-", len(exp),
+                                                                     " ".join("%x" % x for x in exp)))
+    cases = tmp_path / "cases.txt"
+    cases.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([exe, str(cases)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and ("%d cases, 0 failures" % len(lines)) in r.stdout, r.stdout[-3000:]

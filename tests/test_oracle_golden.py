@@ -195,3 +195,35 @@ def test_text(oracle, golden, dbcache, toy_tax, reads2000, genomes):
     pb, poff = po.pack_reads([bytes(genomes["phix"])])
     txt, _, _ = oracle.classify_text(db, toy_tax, pb, poff, ["phix"], 31, 31)
     assert txt.decode() == golden["text"]["phix_kraken"] == "U\tphix\t0\t5386\tM:5356\t0:0\n"
+
+
+def test_iterator_surface_golden(oracle):
+    """assign / has_next_kmer / next_minimizer / next_canonicalized_minimizer call by call (encoder.h:201-206,594-628):
+    the restatement against vectors produced by the unmodified reference headers (tests/golden/make_golden_iter.py)."""
+    import json
+    import os
+    with open(os.path.join(H.GOLDEN, "golden_iter.json")) as f:
+        gold = json.load(f)
+    assert gold["cast"] == "saturate" and len(gold["cases"]) == 224
+    for c in gold["cases"]:
+        got = oracle.encode(c["seq"], c["k"], c["w"], c["gaps"], c["score"], c["canon"], po.API_ITER, cast_mode=po.CAST_SATURATE)
+        assert ["%x" % int(x) for x in got] == c["values"], {k: c[k] for k in ("k", "w", "gaps", "score", "canon", "seq")}
+        # one value per call from the first full window on: l - w + 1 of them (has_next_kmer counts positions l - c + 1)
+        cc, ww = oracle.spacer(c["k"], c["w"], c["gaps"])[:2]
+        assert len(got) == max(0, len(c["seq"]) - ww + 1)
+
+
+def test_iterator_surface_reference_pins(oracle):
+    """test/encoding.cpp:17-47: the first next_kmer() / next_minimizer() of a 34-base string under the {1,2,0...} comb spells
+    the string with its skipped bases dashed out (Spacer::to_string)."""
+    test = "ACATGCTAGCATGCTGACTGACTGATCGATCGTA"
+    gaps = [1, 2] + [0] * 28
+    first = oracle.encode(test, 31, 31, gaps, canon=False, api=po.API_ITER)
+    assert first.size == 1
+    offs = np.concatenate([[0], np.cumsum(np.array(gaps) + 1)])
+    spelled = ["-"] * 34
+    for j, o in enumerate(offs):
+        spelled[int(o)] = "ACGT"[(int(first[0]) >> (2 * (30 - j))) & 3]
+    expect = list(test)
+    expect[1] = expect[3] = expect[4] = "-"
+    assert spelled == expect

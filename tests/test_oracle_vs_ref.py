@@ -37,7 +37,7 @@ def test_encode_fuzz(oracle, variant):
             seq = seq[:p] + rng.choice("ACGT") * 35 + seq[p + 35:]
         for score in (0, 1):
             for canon in (0, 1):
-                for api in (0, 1):
+                for api in (0, 1, 2):                        # 2: next_minimizer / next_canonicalized_minimizer call by call
                     a = R.encode(seq, k, w, gaps, score, canon, api)
                     b = oracle.encode(seq, k, w, gaps, score, canon, api, cast_mode=R.cast_mode)
                     assert np.array_equal(a, b), dict(k=k, w=w, gaps=gaps, score=score, canon=canon, api=api, seq=seq)
