@@ -492,8 +492,17 @@ struct ReadView {                                                     // what th
     int l_name = -1;                                                  // < 0: name is NUL-terminated
     void put_name(std::string &s) const { if(l_name < 0) s += name; else s.append(name, (size_t)l_name); }
 };
-inline void put_u(std::string &s, u32 x) { char b[16]; s.append(b, std::snprintf(b, sizeof b, "%u", x)); }
-inline void put_i(std::string &s, long x) { char b[32]; s.append(b, std::snprintf(b, sizeof b, "%ld", x)); }
+// decimal text without snprintf (a Kraken line holds a dozen numbers; this is most of the formatter's time)
+inline void put_u64(std::string &s, u64 x) {
+    char b[24];
+    int at = 24;
+    do { b[--at] = (char)('0' + x % 10); x /= 10; } while(x);
+    s.append(b + at, (size_t)(24 - at));
+}
+inline void put_u(std::string &s, u32 x) { put_u64(s, x); }
+inline void put_i(std::string &s, long x) {
+    if(x < 0) { s.push_back('-'); put_u64(s, (u64)0 - (u64)x); } else put_u64(s, (u64)x);
+}
 inline void append_taxa_run(tax_t last, u32 run, std::string &s) {                // classifier.h:30-43
     if(last == 0) s.push_back('U'); else if(last == (tax_t)-1) s.push_back('A'); else put_u(s, last);
     s.push_back(':'); put_u(s, run); s.push_back('\t');

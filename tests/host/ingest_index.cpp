@@ -130,6 +130,22 @@ int main(int argc, char **argv) {
     auto seq = [&](int n) { std::string s(n, 'A'); for(auto &c : s) c = "ACGTN"[rng() % 100 < 2 ? 4 : rng() % 4]; return s; };
     auto qual = [&](int n, int i) { std::string q(n, 'I'); for(auto &c : q) c = (char)(33 + rng() % 60); if(i % 7 == 0) q[0] = '@'; if(i % 11 == 0) q[0] = '+'; return q; };
     int failures = 0;
+    {   // the emitters' decimal formatting against printf
+        std::vector<long> vals = {0, 1, 9, 10, 11, 99, 100, 101, 150, 999, 1000, 65535, 65536, 999999, 1000000, 2147483647L, 2147483648L, 4294967295L,
+                                  -1, -9, -10, -150, -2147483648L, 9223372036854775807L, -9223372036854775807L - 1};
+        for(int i = 0; i < 2000; ++i) vals.push_back((long)(rng() >> (rng() % 64)) * ((rng() & 1) ? 1 : -1));
+        bool ok = true;
+        for(long v : vals) {
+            char b[32];
+            std::string a, c;
+            detail::put_i(a, v);
+            snprintf(b, sizeof b, "%ld", v);
+            ok = ok && a == b;
+            if(v >= 0 && v <= 4294967295L) { detail::put_u(c, (u32)v); snprintf(b, sizeof b, "%u", (u32)v); ok = ok && c == b; }
+        }
+        printf("decimal formatting of %zu values %s\n", vals.size(), ok ? "ok" : "MISMATCH");
+        failures += !ok;
+    }
     struct Case { const char *name; std::string txt; bool expect_index, expect_fallback; };
     std::vector<Case> cases;
     {   // plain 4-line FASTQ, names with comments / tabs / read numbers, quality lines starting with @ and +, no final newline
