@@ -143,12 +143,27 @@ struct KSeq {
     bool eof = false;
     int last_char = 0;
     std::string name, comment, seq, qual;
+    std::FILE *pfp = nullptr;                              // .xz / .bz2 / .zst: read through `xz|bzip2|zstd -dc`, encoder.h:511-524
+    bool owns_fp = true;
     explicit KSeq(const char *path) : buf(1 << 18) {
-        fp = gzopen(path, "rb");
-        if(!fp) BNS_RUNTIME_ERROR(std::string("Could not open file at ") + path);
+        const std::string p(path);
+        auto ends = [&](const char *suf) { const size_t n = std::strlen(suf); return p.size() >= n && p.compare(p.size() - n, n, suf) == 0; };
+        const char *tool = ends(".xz") ? "xz" : ends(".bz2") ? "bzip2" : ends(".zst") ? "zstd" : nullptr;
+        if(tool) {
+            std::string quoted = "'";
+            for(char ch : p) { if(ch == '\'') quoted += "'\\''"; else quoted.push_back(ch); }
+            quoted.push_back('\'');
+            const std::string cmd = std::string(tool) + " -dc -- " + quoted;
+            pfp = ::popen(cmd.c_str(), "r");
+            if(!pfp) BNS_RUNTIME_ERROR(std::string("Failed to open popen call: ") + cmd);
+            fp = gzdopen(::dup(::fileno(pfp)), "rb");
+        } else fp = gzopen(path, "rb");
+        if(!fp) { if(pfp) ::pclose(pfp); BNS_RUNTIME_ERROR(std::string("Could not open file at ") + path); }
         gzbuffer(fp, 1 << 18);
     }
-    ~KSeq() { if(fp) gzclose(fp); }
+    explicit KSeq(gzFile borrowed) : fp(borrowed), buf(1 << 18), owns_fp(false) {}     // for_each(fn, gzFile): the caller closes it
+    KSeq(const KSeq &) = delete;
+    ~KSeq() { if(fp && owns_fp) gzclose(fp); if(pfp) ::pclose(pfp); }
     int getc_() {
         if(pos >= end) {
             if(eof) return -1;
@@ -233,6 +248,20 @@ class Encoder {
         if(!p) p = detail::open_handle(sp_, ScoreType::id, canonicalize_, path_api ? BNS_API_PATH : BNS_API_STRING);
         return p.get();
     }
+    std::shared_ptr<detail::Handle> forced_[2];        // record-overload contexts with canonicalisation forced off / on
+    template <typename F> void for_each_as(const F &fn, const char *path, bool canon) {
+        if(canon == canonicalize_) { for_each(fn, path); return; }
+        auto &p = forced_[canon];
+        if(!p) p = detail::open_handle(sp_, ScoreType::id, canon, BNS_API_PATH);
+        detail::KSeq ks(path);
+        while(ks.read() >= 0) {
+            const u64 l = ks.seq.size(), offs[2] = {0, l}, bound = bns_b200_encode_bound(p->h, l), ooffs[2] = {0, bound};
+            kmers_.resize(bound + 1);
+            u32 count = 0;
+            detail::check(p->h, bns_b200_encode_batch(p->h, ks.seq.data(), offs, 1, kmers_.data(), ooffs, &count), "bns_b200_encode_batch");
+            for(u32 i = 0; i < count; ++i) fn(kmers_[i]);
+        }
+    }
     // call-by-call state (assign / next_*)
     const char *s_ = nullptr;
     u64 l_ = 0, pos_ = 0;
@@ -279,11 +308,23 @@ public:
     template <typename F> void for_each(const F &fn, const char *str, u64 l) { run(fn, str, l, false); }
     // for_each_canon / for_each_uncanon on one record, encoder.h:448-464
     template <typename F> void for_each_record(const F &fn, const char *str, u64 l) { run(fn, str, l, true); }
-    // for_each(fn, path), encoder.h:511-530: every record of a FASTA/FASTQ(.gz) file through the record overloads
+    // for_each(fn, path), encoder.h:511-530: every record of a FASTA/FASTQ(.gz/.xz/.bz2/.zst) file through the record overloads
     template <typename F> void for_each(const F &fn, const char *path) {
         detail::KSeq ks(path);
         while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
     }
+    template <typename F> void for_each(const F &fn, const std::string &path) { for_each(fn, path.c_str()); }      // :507-510
+    template <typename F> void for_each(const F &fn, gzFile fp) {                                                  // :497-506
+        detail::KSeq ks(fp);
+        while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
+    }
+    // every file of a list, encoder.h:531-545
+    template <typename F> void for_each(const F &fn, const std::vector<std::string> &paths) { for(const auto &p : paths) for_each(fn, p.c_str()); }
+    // for_each_canon / for_each_uncanon over a file, encoder.h:448-496: the canonical / uncanonical bodies whatever canonicalize_
+    // says. (A spaced seed stays uncanonical here, as the constructor decided; the reference would canonicalise it in
+    // for_each_canon, which nothing on the classify path does.)
+    template <typename F> void for_each_canon(const F &fn, const char *path) { for_each_as(fn, path, true); }
+    template <typename F> void for_each_uncanon(const F &fn, const char *path) { for_each_as(fn, path, false); }
     // ---- the call-by-call surface, encoder.h:201-206,594-628 ---------------------------------------------------------
     // assign() borrows the string. The first next_*() call after it computes the value of that call for EVERY position of
     // the string on the device (one BNS_API_ITER encode: nothing filtered, ENCODE_OVERFLOW where the reference returns it --

@@ -194,6 +194,18 @@ int main(int argc, char **argv) {
             failures += !ok;
         }
     }
+    // .xz / .bz2 through `xz|bzip2 -dc` (encoder.h:511-524), where those tools exist: the same records; never the index
+    for(const char *tool : {"xz", "bzip2"}) {
+        const std::string ext = tool[0] == 'x' ? ".xz" : ".bz2", plain = dir + "/fastq_simple.txt", comp = dir + "/popen it's.fq" + ext;
+        const std::string cmd = std::string(tool) + " -c '" + plain + "' > '" + dir + "/popen it'\\''s.fq" + ext + "' 2>/dev/null";
+        if(std::system(cmd.c_str()) != 0) { printf("%s not available: skipped ok\n", tool); continue; }
+        const auto ref = by_kseq(plain);
+        bool used = true, fell = true;
+        const auto got = by_index(comp, 4, &used, &fell);
+        const bool ok = got.size() == ref.size() && std::equal(got.begin(), got.end(), ref.begin()) && !used && !fell;
+        printf("popen %s records=%zu/%zu %s\n", tool, got.size(), ref.size(), ok ? "ok" : "MISMATCH");
+        failures += !ok;
+    }
     // gzip input: the same texts, compressed (single- and multi-member), small inflate windows
     setenv("BNS_B200_GZ_WINDOW", "300000", 1);
     for(auto &c : cases) {

@@ -97,7 +97,7 @@ def test_parallel_ingest_index_matches_kseq(tmp_path):
     r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, src, "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 78, r.stdout
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 80, r.stdout
 
 
 def test_cli_host_pipeline_ingest_kinds(tmp_path, cli):
