@@ -249,18 +249,41 @@ class Encoder {
         return p.get();
     }
     std::shared_ptr<detail::Handle> forced_[2];        // record-overload contexts with canonicalisation forced off / on
-    template <typename F> void for_each_as(const F &fn, const char *path, bool canon) {
-        if(canon == canonicalize_) { for_each(fn, path); return; }
-        auto &p = forced_[canon];
-        if(!p) p = detail::open_handle(sp_, ScoreType::id, canon, BNS_API_PATH);
-        detail::KSeq ks(path);
+    // every record of a file through the record overloads on context `h`: records are gathered into batches of ~32 MB of bases
+    // (one device call each instead of one per record) and fn sees the k-mers record by record, in file order
+    template <typename F> void for_each_records_of(const F &fn, detail::KSeq &ks, bns_b200_t *h) {
+        const char *e = std::getenv("BNS_B200_ENCODE_BATCH");                          // bases per batch (tests use a small one)
+        const size_t BATCH_BASES = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)32 << 20);
+        std::string bases;
+        std::vector<u64> offs(1, 0), ooffs(1, 0);
+        std::vector<u32> counts;
+        auto flush = [&]() {
+            const u64 n = offs.size() - 1;
+            if(!n) return;
+            kmers_.resize(ooffs.back() + 1);
+            counts.assign(n, 0);
+            detail::check(h, bns_b200_encode_batch(h, bases.data(), offs.data(), n, kmers_.data(), ooffs.data(), counts.data()), "bns_b200_encode_batch");
+            for(u64 i = 0; i < n; ++i) for(u32 j = 0; j < counts[i]; ++j) fn(kmers_[ooffs[i] + j]);
+            bases.clear(); offs.assign(1, 0); ooffs.assign(1, 0);
+        };
         while(ks.read() >= 0) {
-            const u64 l = ks.seq.size(), offs[2] = {0, l}, bound = bns_b200_encode_bound(p->h, l), ooffs[2] = {0, bound};
-            kmers_.resize(bound + 1);
-            u32 count = 0;
-            detail::check(p->h, bns_b200_encode_batch(p->h, ks.seq.data(), offs, 1, kmers_.data(), ooffs, &count), "bns_b200_encode_batch");
-            for(u32 i = 0; i < count; ++i) fn(kmers_[i]);
+            bases += ks.seq;
+            offs.push_back(bases.size());
+            ooffs.push_back(ooffs.back() + bns_b200_encode_bound(h, ks.seq.size()));
+            if(bases.size() >= BATCH_BASES) flush();
         }
+        flush();
+    }
+    template <typename F> void for_each_as(const F &fn, const char *path, bool canon) {
+        detail::Handle *hd;
+        if(canon == canonicalize_) hd = get(true);
+        else {
+            auto &p = forced_[canon];
+            if(!p) p = detail::open_handle(sp_, ScoreType::id, canon, BNS_API_PATH);
+            hd = p.get();
+        }
+        detail::KSeq ks(path);
+        for_each_records_of(fn, ks, hd->h);
     }
     // call-by-call state (assign / next_*)
     const char *s_ = nullptr;
@@ -311,12 +334,12 @@ public:
     // for_each(fn, path), encoder.h:511-530: every record of a FASTA/FASTQ(.gz/.xz/.bz2/.zst) file through the record overloads
     template <typename F> void for_each(const F &fn, const char *path) {
         detail::KSeq ks(path);
-        while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
+        for_each_records_of(fn, ks, get(true)->h);
     }
     template <typename F> void for_each(const F &fn, const std::string &path) { for_each(fn, path.c_str()); }      // :507-510
     template <typename F> void for_each(const F &fn, gzFile fp) {                                                  // :497-506
         detail::KSeq ks(fp);
-        while(ks.read() >= 0) run(fn, ks.seq.data(), ks.seq.size(), true);
+        for_each_records_of(fn, ks, get(true)->h);
     }
     // every file of a list, encoder.h:531-545
     template <typename F> void for_each(const F &fn, const std::vector<std::string> &paths) { for(const auto &p : paths) for_each(fn, p.c_str()); }

@@ -9,19 +9,30 @@
 #include <vector>
 #include <algorithm>
 #include "../../include/bonsai_b200.h"
-struct bns_b200_ctx { uint64_t ncls = 0, nun = 0; uint32_t k = 31; };
+struct bns_b200_ctx { uint64_t ncls = 0, nun = 0; uint32_t k = 31, canon = 0, api = 0; };
 static uint64_t hsh(const char *p, size_t n) { uint64_t h = 1469598103934665603ull; for(size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull; return h; }
 extern "C" {
 const char *bns_b200_last_error(const bns_b200_t *) { return "stub"; }
-int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) { *out = new bns_b200_ctx; (*out)->k = cfg->k; return 0; }
+int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) { *out = new bns_b200_ctx; (*out)->k = cfg->k; (*out)->canon = cfg->canonicalize; (*out)->api = cfg->api; return 0; }
 void bns_b200_close(bns_b200_t *c) { delete c; }
 int bns_b200_load_table(bns_b200_t *, const uint64_t *, const uint32_t *, const uint32_t *, uint64_t) { return 0; }
 int bns_b200_load_taxonomy(bns_b200_t *, const uint32_t *, const uint32_t *, uint64_t) { return 0; }
 int bns_b200_stats_get(const bns_b200_t *c, bns_b200_stats *s) { memset(s, 0, sizeof *s); s->n_classified = c->ncls; s->n_unclassified = c->nun; return 0; }
 int bns_b200_host_alloc(void **p, size_t n) { *p = malloc(n); return *p ? 0 : -3; }
 int bns_b200_host_free(void *p) { free(p); return 0; }
-uint64_t bns_b200_encode_bound(const bns_b200_t *, uint64_t len) { return len; }
-int bns_b200_encode_batch(bns_b200_t *, const char *, const uint64_t *, uint64_t, uint64_t *, const uint64_t *, uint32_t *) { return -2; }
+uint64_t bns_b200_encode_bound(const bns_b200_t *c, uint64_t len) { return len >= c->k ? len - c->k + 1 : 0; }
+// not an encoder: one arbitrary word per position (a hash of the k bases there, the canonicalize flag and the API selector) for the
+// record-overload configurations, so that the mirror's batching and context selection can be checked; the other selectors refuse
+int bns_b200_encode_batch(bns_b200_t *c, const char *bases, const uint64_t *offs, uint64_t n, uint64_t *out, const uint64_t *ooffs, uint32_t *counts) {
+    if(c->api != BNS_API_PATH) return -2;
+    for(uint64_t r = 0; r < n; ++r) {
+        const uint64_t len = offs[r + 1] - offs[r], m = len >= c->k ? len - c->k + 1 : 0;
+        if(m > ooffs[r + 1] - ooffs[r]) return BNS_E_CAPACITY;
+        for(uint64_t p = 0; p < m; ++p) out[ooffs[r] + p] = hsh(bases + offs[r] + p, c->k) * 2 + c->canon;
+        counts[r] = (uint32_t)m;
+    }
+    return 0;
+}
 int bns_b200_build_begin(bns_b200_t *, uint64_t, const uint32_t *, uint32_t) { return -2; }
 int bns_b200_build_add_genome(bns_b200_t *, const char *, const uint64_t *, uint64_t, uint32_t) { return -2; }
 int bns_b200_build_finish(bns_b200_t *) { return -2; }

@@ -169,3 +169,17 @@ def test_cpp_encoder_surface_compiles(tmp_path):
     (tmp_path / "cases.txt").write_text("2 31 31 0 0 - %s 0\n3 5 9 0 0 1,0,2,0 - 0\n" % ("ACGT" * 10))
     r = subprocess.run([exe, str(tmp_path / "cases.txt")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert "2 cases, 1 failures" in r.stdout and "exception" in r.stdout, r.stdout     # the dummy ABI has no encoder; an empty string needs none
+
+
+def test_cpp_encoder_file_overloads_batching(tmp_path):
+    """Encoder::for_each over a path / std::string / gzFile / list and for_each_canon / for_each_uncanon gather the records of a
+    file into batches; against the dummy ABI, every batch size must hand fn what record-by-record calls do, in file order, from
+    plain / gzip / xz files and with the canonical context forced either way: tests/host/encoder_files.cpp, host code only."""
+    import shutil
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "encoder_files")
+    r = subprocess.run([shutil.which("g++") or "/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(here, "host", "encoder_files.cpp"),
+                        os.path.join(here, "host", "abi_stub.cpp"), "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") >= 48, r.stdout
