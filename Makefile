@@ -5,7 +5,7 @@ PKG  := bonsai_b200
 CSRC := $(PKG)/csrc
 LIB  := $(PKG)/libbonsai_b200.so
 CLI  := $(PKG)/bin/bonsai
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -shared
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -shared -ldl
 
 all: $(LIB) $(CLI)
 

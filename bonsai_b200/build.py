@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libbonsai_b200.so")
 SOURCES = ["bns_kernels.cu", "bns_api.cu"]
 DEPS = SOURCES + ["bns_device.cuh", "bns_classify_u.cuh", "bns_kernels.h", "bns_host_util.h", os.path.join("..", "..", "include", "bonsai_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-ldl"]
 
 
 def nvcc_path():

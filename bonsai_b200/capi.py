@@ -26,13 +26,14 @@ SYMBOLS = [
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
     "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_batch_runs", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
+    "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi",
 ]
 
 
 class Config(C.Structure):
     _fields_ = [("k", C.c_uint32), ("w", C.c_uint32), ("gaps", C.c_uint16 * MAX_K), ("score", C.c_uint32),
                 ("canonicalize", C.c_uint32), ("api", C.c_uint32), ("entropy_cast", C.c_uint32),
-                ("device", C.c_int32), ("reserved", C.c_uint32 * 7)]
+                ("device", C.c_int32), ("n_gpus", C.c_uint32), ("reserved", C.c_uint32 * 6)]
 
 
 class TableInfo(C.Structure):
@@ -116,6 +117,10 @@ def load_library(path=None):
     lib.bns_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.bns_b200_host_free.argtypes = [vp]
     lib.bns_b200_bench_gather.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
+    lib.bns_b200_open_multi.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(C.c_int)]
+    lib.bns_b200_replicate.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.bns_b200_close_multi.argtypes = [C.POINTER(vp), C.c_int]
+    lib.bns_b200_close_multi.restype = None
     if path is None:
         _lib = lib
     return lib
@@ -149,6 +154,12 @@ class Context:
             raise BnsError(rc, self.lib.bns_b200_last_error(None).decode())
         self.h = h
         self.k = k
+
+    @classmethod
+    def _adopt(cls, handle, k):
+        self = cls.__new__(cls)
+        self.lib, self.h, self.k = load_library(), handle, k
+        return self
 
     def _ck(self, rc):
         if rc != 0:
@@ -374,3 +385,28 @@ class Context:
         ms = C.c_double()
         self._ck(self.lib.bns_b200_bench_gather(self.h, n_loads, seed, C.byref(ms)))
         return ms.value
+
+
+def open_multi(n_gpus, k, w=0, gaps=None, score=SCORE_LEX, canonicalize=True, api=API_STRING, entropy_cast=CAST_SATURATE, devices=None):
+    """bns_b200_open_multi: one Context per GPU of this process (n_gpus = 0: every visible device)."""
+    lib = load_library()
+    cfg = Context._config(k, w, gaps, score, canonicalize, api, entropy_cast, -1)
+    hs = (C.c_void_p * 64)()
+    n = C.c_int()
+    devs = None
+    if devices is not None:
+        devs = (C.c_int * len(devices))(*devices)
+        n_gpus = len(devices)
+    rc = lib.bns_b200_open_multi(C.byref(cfg), n_gpus, devs, hs, C.byref(n))
+    if rc != 0:
+        raise BnsError(rc, lib.bns_b200_last_error(None).decode())
+    return [Context._adopt(C.c_void_p(hs[i]), k) for i in range(n.value)]
+
+
+def replicate(ctxs, root=0):
+    """bns_b200_replicate: the database of ctxs[root] into every other context (NCCL broadcast inside the library)."""
+    lib = load_library()
+    hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = lib.bns_b200_replicate(hs, len(ctxs), root)
+    if rc != 0:
+        raise BnsError(rc, lib.bns_b200_last_error(ctxs[root].h).decode())

@@ -12,6 +12,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "../../include/bonsai_b200.h"
 #include "bns_device.cuh"
 #include "bns_host_util.h"
@@ -272,6 +275,15 @@ u32 choose_bits(u64 n_keys, u32 n_values) {
     b = std::max(b, 12u);
     b = std::max(b, bits_for(std::max<u32>(n_values, 1)) + (u32)DISP_BITS + 1u);
     return b;
+}
+
+// tables that will take the minimizer layout: entries per 32-byte bucket from BNS_B200_LOC_LOAD when set (experiments)
+u32 layout_bits(const bns_b200_ctx *ctx, u32 b, u64 n_keys) {
+    const char *e = getenv("BNS_B200_LOC_LOAD");
+    if(!e || !want_minimizer_layout(ctx, b)) return b;
+    const double v = atof(e);
+    if(!(v > 0.05 && v <= 3.0)) return b;
+    return std::max(12u, bits_for((u64)std::ceil((double)std::max<u64>(n_keys, 1) / v)));
 }
 
 int upload_values(bns_b200_ctx *ctx) {
@@ -567,7 +579,8 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
     uint64_t n_occupied = 0;
     const std::vector<u32> values = distinct_values_khash(vals, flags, n_buckets, &n_occupied);   // the value dictionary (bns_host_util.h)
     const u64 n_keys = n_occupied;
-    for(u32 b = choose_bits(n_keys, (u32)values.size());; ++b) {
+    ctx->values = values;
+    for(u32 b = layout_bits(ctx, choose_bits(n_keys, (u32)values.size()), n_keys);; ++b) {
         free_table(ctx);
         ctx->values = values;
         int rc = upload_values(ctx);
@@ -601,7 +614,8 @@ int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
     CK(cudaSetDevice(ctx->device));
     ctx->no_minimizer = false;
     const std::vector<u32> values = distinct_values(vals, n);
-    for(u32 b = choose_bits(n, (u32)values.size());; ++b) {
+    ctx->values = values;
+    for(u32 b = layout_bits(ctx, choose_bits(n, (u32)values.size()), n);; ++b) {
         free_table(ctx);
         ctx->values = values;
         int rc = upload_values(ctx);
@@ -636,7 +650,8 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
     std::sort(vs.begin(), vs.end());
     vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
     cudaStream_t st = ctx->slots[0].st;
-    for(u32 b = choose_bits(n, (u32)vs.size());; ++b) {
+    ctx->values = vs;
+    for(u32 b = layout_bits(ctx, choose_bits(n, (u32)vs.size()), n);; ++b) {
         free_table(ctx);
         ctx->values = vs;
         int rc = upload_values(ctx);
@@ -1031,6 +1046,132 @@ int bns_b200_db_commit(bns_b200_t *ctx) {
         CK(cudaMemcpy(ctx->values.data(), ctx->d_values, ctx->values.size() * sizeof(u32), cudaMemcpyDeviceToHost));
     ctx->tax_ready = true;
     ctx->tax_loaded = true;
+    return BNS_OK;
+}
+
+// ---- several GPUs in one process ------------------------------------------------------------------------
+// NCCL is bound at the first replicate call (dlopen of libnccl.so.2, prototypes from <nccl.h>): a process that drives one
+// GPU never loads it, and a host process that already carries an NCCL (torch.distributed) shares that copy instead of
+// mapping a second one under the same soname.
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for(const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if(a.lib) break;
+        }
+        if(!a.lib) return a;
+        a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
+        a.ok = a.CommInitAll && a.CommDestroy && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+int bns_b200_open_multi(const bns_b200_config *cfg, int n_gpus, const int *devices, bns_b200_t **out, int *n_out) {
+    if(!cfg || !out || n_gpus < 0) return BNS_E_INVAL;
+    if(n_out) *n_out = 0;
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_open_err = "no usable CUDA device";
+        return BNS_E_CUDA;
+    }
+    int n = n_gpus ? n_gpus : (cfg->n_gpus ? (int)cfg->n_gpus : ndev);
+    if(n > ndev && !devices) { g_open_err = "more GPUs requested than visible"; return BNS_E_INVAL; }
+    for(int i = 0; i < n; ++i) out[i] = nullptr;
+    for(int i = 0; i < n; ++i) {
+        bns_b200_config c = *cfg;
+        c.device = devices ? devices[i] : i;
+        const int rc = bns_b200_open(&c, &out[i]);
+        if(rc != BNS_OK) {
+            for(int j = 0; j < i; ++j) { bns_b200_close(out[j]); out[j] = nullptr; }
+            return rc;
+        }
+    }
+    if(n_out) *n_out = n;
+    return BNS_OK;
+}
+
+void bns_b200_close_multi(bns_b200_t **handles, int n) {
+    if(!handles) return;
+    for(int i = 0; i < n; ++i) { bns_b200_close(handles[i]); handles[i] = nullptr; }
+}
+
+int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
+    if(!handles || n < 1 || root < 0 || root >= n || !handles[root]) return BNS_E_INVAL;
+    bns_b200_ctx *ctx = handles[root];                                     // errors are reported on the root context
+    for(int i = 0; i < n; ++i) {
+        if(!handles[i]) return ctx->fail(BNS_E_INVAL, "null context in the replica list");
+        for(int j = 0; j < i; ++j)
+            if(handles[j]->device == handles[i]->device) return ctx->fail(BNS_E_INVAL, "two contexts of the replica list share device %d", handles[i]->device);
+    }
+    if(!ctx->d_slots) return ctx->fail(BNS_E_STATE, "no table loaded on the root context");
+    if(n == 1) return BNS_OK;
+    bns_b200_db_header hdr;
+    int rc = bns_b200_db_export_header(ctx, &hdr);
+    if(rc != BNS_OK) return rc;
+    for(int i = 0; i < n; ++i)
+        if(i != root && (rc = bns_b200_db_alloc_from_header(handles[i], &hdr)) != BNS_OK)
+            return ctx->fail(rc, "replica %d: %s", i, handles[i]->err.c_str());
+    NcclApi &nc = nccl_api();
+    if(!nc.ok) return ctx->fail(BNS_E_CUDA, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+    std::vector<ncclComm_t> comms((size_t)n, nullptr);
+    std::vector<int> devs((size_t)n);
+    for(int i = 0; i < n; ++i) devs[(size_t)i] = handles[i]->device;
+    ncclResult_t nr = nc.CommInitAll(comms.data(), n, devs.data());
+    if(nr != ncclSuccess) return ctx->fail(BNS_E_CUDA, "ncclCommInitAll: %s", nc.GetErrorString(nr));
+    auto done = [&](int code) {
+        for(int i = 0; i < n; ++i) if(comms[(size_t)i]) nc.CommDestroy(comms[(size_t)i]);
+        return code;
+    };
+    std::vector<void *> ptrs((size_t)n * 4);
+    uint64_t bytes[4] = {0, 0, 0, 0};
+    for(int i = 0; i < n; ++i) {
+        uint64_t b[4]; int ns = 0;
+        rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 4], b, 4, &ns);
+        if(rc != BNS_OK || ns != 4) return done(ctx->fail(BNS_E_STATE, "replica %d has no segments", i));
+        if(i == root) for(int s = 0; s < 4; ++s) bytes[s] = b[s];
+    }
+    for(int s = 0; s < 4 && nr == ncclSuccess; ++s) {                       // one broadcast per segment, every rank of it in one group
+        if(!bytes[s]) continue;
+        nc.GroupStart();
+        for(int i = 0; i < n; ++i) {
+            cudaSetDevice(handles[i]->device);
+            const ncclResult_t r = nc.Broadcast(ptrs[(size_t)root * 4 + s], ptrs[(size_t)i * 4 + s], (size_t)bytes[s], ncclChar, root,
+                                                comms[(size_t)i], handles[i]->slots[0].st);
+            if(r != ncclSuccess) nr = r;
+        }
+        const ncclResult_t r = nc.GroupEnd();
+        if(r != ncclSuccess) nr = r;
+    }
+    if(nr != ncclSuccess) return done(ctx->fail(BNS_E_CUDA, "ncclBroadcast: %s", nc.GetErrorString(nr)));
+    for(int i = 0; i < n; ++i) {
+        cudaSetDevice(handles[i]->device);
+        const cudaError_t e = cudaStreamSynchronize(handles[i]->slots[0].st);
+        if(e != cudaSuccess) return done(ctx->cuda_fail(e, "replication stream"));
+    }
+    done(0);
+    for(int i = 0; i < n; ++i)
+        if(i != root && (rc = bns_b200_db_commit(handles[i])) != BNS_OK) return ctx->fail(rc, "replica %d: %s", i, handles[i]->err.c_str());
+    cudaSetDevice(ctx->device);
     return BNS_OK;
 }
 

@@ -33,6 +33,7 @@ constexpr int LEAN_STAGE_BYTES = 2 * (RB + 2) * 8 + 2 * 32 * 8;      // per warp
 #endif
 constexpr int LEAN_WARPS = BNS_LEAN_WARPS;   // warps per CTA of the lean kernel
 
+
 __device__ __forceinline__ void ld_bucket8(const void *p, u32 (&w)[8]) {
     // one 32-byte sector per probe (LDG.E.256), as eight 32-bit words: {lo, hi} of slots 0..3
     asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -49,19 +50,36 @@ struct ProbeConst {                          // launch-uniform pieces of the slo
     u32 val_mask;
 };
 
-// buckets after the home bucket for ONE key (rare). (th, tl0): the left-aligned remainder. Returns the low word of the
-// matching slot or ~tl0 ("no match").
+// buckets after the home bucket for ONE key of a LAYOUT_HASH table (rare). (th, tl0): the left-aligned remainder. Returns the
+// low word of the matching slot or ~tl0 ("no match").
 __device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 home, u32 th, u32 tl0) {
     const u32 b = Pc.b;
     const u32 bmask = (b == 32) ? ~0u : ((1u << b) - 1);
     for(u32 d = 1; d <= Pc.max_disp; ++d) {
         u32 w[8];
-        ld_bucket8(Pc.slots + (probe_bucket(Pc.layout, home, d, Pc.b) << 5), w);
+        ld_bucket8(Pc.slots + ((u64)((home + d) & bmask) << 5), w);
         const u32 tl = tl0 | (d << Pc.tag_shift);
 #pragma unroll
         for(int j = 0; j < 4; ++j)
             if(w[2 * j + 1] == th && ((w[2 * j] ^ tl) & Pc.hm) == 0) return w[2 * j];
         if((w[6] & w[7]) == ~0u) break;                               // a bucket with a free slot ends the run
+    }
+    return ~tl0;
+}
+// the overflow chain of ONE key of a LAYOUT_MINIMIZER table: 64-byte units from a scrambled image of the home unit on
+__device__ __forceinline__ u32 probe_chain_loc(const ProbeConst Pc, u32 home, u32 th, u32 tl0) {
+    const u32 ub = Pc.b - 1, umask = (1u << ub) - 1;
+    const u32 u0 = nmix(home >> 1, ub);
+    for(u32 d = 1; d <= Pc.max_disp; ++d) {
+        u32 w[16];
+        const char *up = Pc.slots + ((u64)((u0 + (d - 1)) & umask) << 6);
+        ld_bucket8(up, *reinterpret_cast<u32 (*)[8]>(&w[0]));
+        ld_bucket8(up + 32, *reinterpret_cast<u32 (*)[8]>(&w[8]));
+        const u32 tl = tl0 | (d << Pc.tag_shift);
+#pragma unroll
+        for(int j = 0; j < 8; ++j)
+            if(w[2 * j + 1] == th && ((w[2 * j] ^ tl) & Pc.hm) == 0) return w[2 * j];
+        if((w[14] & w[15]) == ~0u) break;                             // a unit with a free slot ends the run
     }
     return ~tl0;
 }
@@ -490,21 +508,22 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         }
                         if(COUNTS) n_emit += __reduce_add_sync(FULL, __popc(mask));
                     }
-                    // (bucket, left-aligned remainder) of the four keys. LAYOUT_HASH carries mix64 as (hl, hh) and derives
-                    // bucket and tag words from it; LAYOUT_MINIMIZER carries the tag words in (hl, hh) and the bucket in hb.
-                    u32 hl[PPL], hh[PPL], hb[PPL], w[PPL][8];
-                    // LAYOUT_MINIMIZER, all four k-mers of every lane at once (records of at most 120 k-mers per tile: lanes 0..29
-                    // own k-mers, and lane l's 19 16-mers come from lanes l..l+2): each lane mixes the canonical 16-mers at
-                    // offsets 0..3 and 8..11 of its window, two SHFL.DOWN steps bring in the other twelve, and the minimum of
-                    // (27-bit mixed value : position) over each k-mer's 16 positions is a chain of 32-bit VIMNMX.
-                    const bool loc_fast = LOC && MODE == LEAN_U && KT == 31 && left <= 120u;   // the offsets below are those of k = 31
+                    u32 cand[PPL], nok = 0;                            // nok bit i: k-mer i was not found
+                    if(LOC) {
+                    // ---- LAYOUT_MINIMIZER: (home unit, left-aligned remainder) of the four keys --------------------------
+                    u32 hb[PPL], th[PPL], tl[PPL];
+                    // All four k-mers of every lane at once (records of at most 120 k-mers per tile: lanes 0..29 own k-mers, and
+                    // lane l's 19 16-mers come from lanes l..l+2): each lane hashes the canonical 16-mers at offsets 0..3 and
+                    // 8..11 of its window, two SHFL.DOWN steps bring in the other eleven, and the minimum of (27-bit hash :
+                    // position) over each k-mer's 16 positions is a chain of 32-bit VIMNMX.
+                    const bool loc_fast = MODE == LEAN_U && KT == 31 && left <= 120u;   // the offsets below are those of k = 31
                     if(loc_fast) {
-                        u32 key[19];                                   // mixed canonical 16-mers at window offsets 0..18
+                        u32 key[19];                                   // hashed canonical 16-mers at window offsets 0..18
 #pragma unroll
                         for(int i = 0; i < 4; ++i) {
                             const u32 fa = __funnelshift_l(B_, A, 2 * i), fb = __funnelshift_l(B_, A, 16 + 2 * i);
-                            key[i] = nmix(min(fa, rc16(fa)), LOC_MB) >> 5;
-                            key[8 + i] = nmix(min(fb, rc16(fb)), LOC_MB) >> 5;
+                            key[i] = loc_hash(min(fa, rc16(fa))) & ~31u;
+                            key[8 + i] = loc_hash(min(fb, rc16(fb))) & ~31u;
                         }
 #pragma unroll
                         for(int i = 0; i < 4; ++i) {
@@ -513,61 +532,116 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             if(i < 3) key[16 + i] = __shfl_down_sync(FULL, key[8 + i], 2);
                         }
 #pragma unroll
-                        for(int j = 0; j < 19; ++j) key[j] = (key[j] << 5) | (u32)j;         // leftmost wins ties; ^31: rightmost
+                        for(int j = 0; j < 19; ++j) key[j] |= (u32)j;                        // leftmost wins ties; ^31: rightmost
                         u32 coreL = key[3], coreR = key[3] ^ 31u;
 #pragma unroll
                         for(int j = 4; j <= 15; ++j) { coreL = min(coreL, key[j]); coreR = min(coreR, key[j] ^ 31u); }
+                        const u32 bl = Pc.b - LOC_GB, lmask = (1u << bl) - 1, xmask = ~((1u << (bl - 1)) - 1);
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) {
                             u32 mL = coreL, mR = coreR;
 #pragma unroll
                             for(int j = 0; j < 19; ++j)
                                 if(j >= i && j <= i + 15 && (j < 3 || j > 15)) { mL = min(mL, key[j]); mR = min(mR, key[j] ^ 31u); }
-                            // the k-mer's canonical string reads left to right when it is the read's strand, else right to left
+                            // the k-mer's canonical string reads left to right when it is the read's strand, else right to left:
+                            // window offset js of the winner -> position bp in the canonical k-mer
                             const bool fw = (fwdm >> i) & 1u;
-                            const u32 js = fw ? (mL & 31u) : (31u - (mR & 31u));             // winning window offset, 0..18
-                            const u32 bo2 = 2 * js;
-                            const u32 f16 = __funnelshift_l(bo2 < 32 ? B_ : C, bo2 < 32 ? A : B_, bo2 & 31u);
-                            const u32 r16 = rc16(f16), mh = nmix(min(f16, r16), LOC_MB);
-                            const u32 pr = js - (u32)i;                                      // position in the read's k-mer
-                            const TableHash t = loc_pack(((u64)xhs[i] << 32) | xls[i], k, Pc.b, mh, fw ? pr : (k - LOC_L) - pr,
-                                                         fw ? (r16 < f16) : (f16 < r16));
-                            hb[i] = (u32)t.home; hh[i] = (u32)(t.tag >> 32); hl[i] = (u32)t.tag;
-                            ld_bucket8(Pc.slots + ((u64)hb[i] << 5), w[i]);
+                            const u32 bp = fw ? (mL & 31u) - (u32)i : (mR & 31u) + (u32)i - 16u;   // = 15 - ((31 - (mR & 31)) - i)
+                            const u32 xl = xls[i], xh = xhs[i];
+                            const u32 m16 = __funnelshift_r(xl, xh, 30u - 2u * bp);            // the minimizer as it stands in the canonical k-mer
+                            const u32 r16 = rc16(m16), pl = loc_place(loc_hash(min(m16, r16)));
+                            hb[i] = ((pl & lmask) << LOC_GB) | ((bp & 3u) << 1);
+                            tl[i] = ((pl >> 1) & xmask) | (r16 < m16 ? 0x80000000u : 0u);
+                            th[i] = (__funnelshift_l(xh << 2, xl, 2u * bp) << 2) | (bp >> 2);   // the other 15 bases (right : left) | position >> 2
                         }
                     } else {
 #pragma unroll
-                    for(int i = 0; i < PPL; ++i) {
-                        const u32 xl = xls[i], xh = xhs[i];
-                        if(LOC) {
-                            const TableHash t = loc_encode(((u64)xh << 32) | xl, k, Pc.b);
-                            hb[i] = (u32)t.home; hh[i] = (u32)(t.tag >> 32); hl[i] = (u32)t.tag;
-                        } else {
-                            // mix64 (bns_device.cuh) on 32-bit halves
-                            const u64 x = (((u64)xh << 32) | xl) * 0xd6e8feb86659fd93ull;
-                            hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
+                        for(int i = 0; i < PPL; ++i) {
+                            const TableHash t = loc_encode(((u64)xhs[i] << 32) | xls[i], k, Pc.b);
+                            hb[i] = (u32)t.home; th[i] = (u32)(t.tag >> 32); tl[i] = (u32)t.tag;
                         }
-                        ld_bucket8(Pc.slots + ((u64)(LOC ? hb[i] : hh[i] >> Pc.idx_shift) << 5), w[i]);
                     }
+                    // ---- probe: the 64-byte home unit of two k-mers at a time (four LDG.256 in flight per lane; the lane's four
+                    // k-mers mostly share their group, so the second pair finds its lines in L2 or on their way) -------------
+                    u32 more = 0;                                      // bit i: k-mer i must follow its overflow chain
+#pragma unroll
+                    for(int rnd = 0; rnd < 2; ++rnd) {
+                        u32 w[2][16];
+#pragma unroll
+                        for(int j = 0; j < 2; ++j) {
+                            const char *up = Pc.slots + ((u64)hb[2 * rnd + j] << 5);
+                            ld_bucket8(up, *reinterpret_cast<u32 (*)[8]>(&w[j][0]));
+                            ld_bucket8(up + 32, *reinterpret_cast<u32 (*)[8]>(&w[j][8]));
+                        }
+#pragma unroll
+                        for(int j = 0; j < 2; ++j) {
+                            const int i = 2 * rnd + j;
+                            // first slot whose high word is the key's, verified on the low word; two entries of a unit sharing
+                            // their high word (2^-30 per pair) send the lane through the exact loop
+                            u32 c = ~tl[i];
+#pragma unroll
+                            for(int sl = 7; sl >= 0; --sl) c = w[j][2 * sl + 1] == th[i] ? w[j][2 * sl] : c;
+                            if(((c ^ tl[i]) & Pc.hm) != 0 && c != ~tl[i]) {
+                                c = ~tl[i];
+#pragma unroll
+                                for(int sl = 7; sl >= 0; --sl)
+                                    if(w[j][2 * sl + 1] == th[i] && ((w[j][2 * sl] ^ tl[i]) & Pc.hm) == 0) c = w[j][2 * sl];
+                            }
+                            cand[i] = c;
+                            const u32 miss = min((c ^ tl[i]) & Pc.hm, 1u);
+                            nok |= miss << i;
+                            // the key's overflow flag in slot 0 of the unit: cleared = a key homed here lives further down the chain
+                            more |= (miss & ~(w[j][0] >> (Pc.flag_shift + ((th[i] >> 2) & Pc.flag_mask)))) << i;
+                        }
                     }
-                    // ---- match: first slot whose high word equals the tag's, verified on the low word (LAYOUT_HASH keeps
-                    // upper words unique within a bucket; LAYOUT_MINIMIZER compares every slot in full) ----------------
-                    u32 cand[PPL], nok = 0;                            // nok bit i: k-mer i is not in its home bucket
+                    more &= mask;
+                    // ---- overflow chains (a few keys per record): compacted over the warp, one key per lane ------------------
+                    if(__any_sync(FULL, more != 0)) {
+                        u32 tot;
+                        const u32 at0 = warp_excl_scan(__popc(more), lane, tot);
+                        uint4 *q = (uint4 *)S.tin;                     // TILE x 16 bytes = tin + tout: only resolve() uses them
+                        u32 at = at0;
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i) if(more >> i & 1u) q[at++] = make_uint4(hb[i], th[i], tl[i], 0u);
+                        __syncwarp();
+                        for(u32 base = 0; base < tot; base += 32) {
+                            const u32 t = base + lane;
+                            if(t < tot) {
+                                const uint4 e = q[t];
+                                q[t].w = probe_chain_loc(Pc, e.x, e.y, e.z);
+                            }
+                        }
+                        __syncwarp();
+                        at = at0;
+#pragma unroll
+                        for(int i = 0; i < PPL; ++i)
+                            if(more >> i & 1u) {
+                                const u32 c = q[at++].w;
+                                if(c != ~tl[i]) { nok &= ~(1u << i); cand[i] = c; }
+                            }
+                        __syncwarp();
+                    }
+                    } else {
+                    // ---- LAYOUT_HASH: mix64 as (hl, hh); bucket and tag words derive from it ---------------------------------
+                    u32 hl[PPL], hh[PPL], w[PPL][8];
 #pragma unroll
                     for(int i = 0; i < PPL; ++i) {
-                        const u32 th = LOC ? hh[i] : __funnelshift_lc(hl[i], hh[i], Pc.b);
-                        const u32 tl = LOC ? hl[i] : __funnelshift_lc(0u, hl[i], Pc.b);
+                        // mix64 (bns_device.cuh) on 32-bit halves
+                        const u64 x = (((u64)xhs[i] << 32) | xls[i]) * 0xd6e8feb86659fd93ull;
+                        hh[i] = (u32)(x >> 32); hl[i] = (u32)x ^ hh[i];
+                        ld_bucket8(Pc.slots + ((u64)(hh[i] >> Pc.idx_shift) << 5), w[i]);
+                    }
+                    // ---- match: first slot whose high word equals the tag's, verified on the low word (upper words are unique
+                    // within a bucket) ------------------------------------------------------------------------------------------
+#pragma unroll
+                    for(int i = 0; i < PPL; ++i) {
+                        const u32 th = __funnelshift_lc(hl[i], hh[i], Pc.b);
+                        const u32 tl = __funnelshift_lc(0u, hl[i], Pc.b);
                         u32 c = ~tl;
-                        if(LOC) {
-#pragma unroll
-                            for(int j = 3; j >= 0; --j)
-                                if((((w[i][2 * j] ^ tl) & Pc.hm) | (w[i][2 * j + 1] ^ th)) == 0) c = w[i][2 * j];
-                        } else {
-                            c = w[i][7] == th ? w[i][6] : c;
-                            c = w[i][5] == th ? w[i][4] : c;
-                            c = w[i][3] == th ? w[i][2] : c;
-                            c = w[i][1] == th ? w[i][0] : c;                                   // slots fill in order: first match wins
-                        }
+                        c = w[i][7] == th ? w[i][6] : c;
+                        c = w[i][5] == th ? w[i][4] : c;
+                        c = w[i][3] == th ? w[i][2] : c;
+                        c = w[i][1] == th ? w[i][0] : c;                                   // slots fill in order: first match wins
                         cand[i] = c;
                         nok += min((c ^ tl) & Pc.hm, 1u) << i;
                     }
@@ -576,10 +650,8 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     if(__any_sync(FULL, ((w[0][0] & w[1][0] & w[2][0] & w[3][0]) & Pc.flags_all) != Pc.flags_all)) {
                         u32 more = 0;
 #pragma unroll
-                        for(int i = 0; i < PPL; ++i) {
-                            const u32 fsel = LOC ? (hl[i] >> Pc.fmt_bits) : hl[i];
-                            if(!((w[i][0] >> (Pc.flag_shift + (fsel & Pc.flag_mask))) & 1u)) more |= 1u << i;
-                        }
+                        for(int i = 0; i < PPL; ++i)
+                            if(!((w[i][0] >> (Pc.flag_shift + (hl[i] & Pc.flag_mask))) & 1u)) more |= 1u << i;
                         more &= nok & mask;
                         while(__any_sync(FULL, more != 0)) {
                             if(more) {
@@ -587,15 +659,15 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                                 more &= more - 1;
                                 const u32 l = i == 0 ? hl[0] : i == 1 ? hl[1] : i == 2 ? hl[2] : hl[3];
                                 const u32 h = i == 0 ? hh[0] : i == 1 ? hh[1] : i == 2 ? hh[2] : hh[3];
-                                const u32 hm = LOC ? (i == 0 ? hb[0] : i == 1 ? hb[1] : i == 2 ? hb[2] : hb[3]) : (h >> Pc.idx_shift);
-                                const u32 th = LOC ? h : __funnelshift_lc(l, h, Pc.b), tl0 = LOC ? l : __funnelshift_lc(0u, l, Pc.b);
-                                const u32 c = probe_displaced32(Pc, hm, th, tl0);
+                                const u32 th = __funnelshift_lc(l, h, Pc.b), tl0 = __funnelshift_lc(0u, l, Pc.b);
+                                const u32 c = probe_displaced32(Pc, h >> Pc.idx_shift, th, tl0);
                                 if(c != ~tl0) {
                                     nok &= ~(1u << i);
                                     if(i == 0) cand[0] = c; else if(i == 1) cand[1] = c; else if(i == 2) cand[2] = c; else cand[3] = c;
                                 }
                             }
                         }
+                    }
                     }
                     // ---- hits -> per-record distinct-taxon counts (linear::counter::add, linear.h:229) -----------
                     u32 todo = ~nok & mask;

@@ -37,7 +37,7 @@ constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
 constexpr int AGG_CAP = 256;     // distinct taxa tracked per record in shared memory (covers any read up to k+255 bases)
 constexpr int DISP_BITS = 4;     // slot displacement field of LAYOUT_HASH; disp == 2^bits - 1 is reserved for the empty slot
-constexpr int DISP_BITS_LOC = 8; // LAYOUT_MINIMIZER: lines fill unevenly (whole minimizer runs land in one), longer runs of full buckets
+constexpr int DISP_BITS_LOC = 6; // LAYOUT_MINIMIZER: probes are 64-byte units; chains of up to 62 units
 
 struct EncParams {
     u32 k, c, W;                 // W = w_ - c_ + 1  (QueueMap size, encoder.h:142)
@@ -55,17 +55,20 @@ struct EncParams {
 
 // How a key becomes (home bucket, remainder). Both are bijections key <-> (bucket, remainder), so hits and misses are exact.
 //   LAYOUT_HASH      bucket = top b bits of mix64(key), remainder = the other 64-b bits. Consecutive k-mers of a read land
-//                    in unrelated DRAM lines: one line per lookup once the table exceeds L2.
-//   LAYOUT_MINIMIZER (23 <= k <= 31) the 128-byte LINE is chosen by the k-mer's canonical 16-mer minimizer, the 32-byte
-//                    sector inside it by the minimizer's position mod 4; the remainder spells the k-mer relative to its
-//                    minimizer (loc_encode). ~(k-14)/2 consecutive k-mers of a read share a minimizer and so a line:
-//                    the line one lookup brings into L2 serves the next ones.
+//                    in unrelated DRAM lines: one line per lookup once the table exceeds L2. A probe is one 32-byte bucket.
+//   LAYOUT_MINIMIZER (23 <= k <= 31) a probe is a 64-byte UNIT of two adjacent buckets (8 slots). The home unit lies in a
+//                    GROUP of four units (256 bytes, two 128-byte lines) chosen by the k-mer's canonical 16-mer minimizer, the
+//                    unit inside the group by the minimizer's position mod 4; the remainder spells the k-mer relative to
+//                    its minimizer (loc_pack). ~(k-14)/2 consecutive k-mers of a read share a minimizer and so a group:
+//                    the lines one lookup brings into L2 serve the next ones (~30 lines per 150 bp read instead of 120).
+//                    (A variant that stored a unit as a sector of eight high words followed by a sector of eight low words --
+//                    one LDG.256 to find the candidate, one LDG.32 for its low word, 8F overflow flags per unit -- measured
+//                    10 % slower on the 2^28-key stress table: profiles/ncu_r02_loc3_soa.txt.)
 enum TableLayout : u32 { LAYOUT_HASH = 0, LAYOUT_MINIMIZER = 1 };
 constexpr u32 LOC_L = 16;        // minimizer length: a k-mer holds k-15 <= 16 of them for k <= 31, so a full run of consecutive
-                                 // k-mers sharing one minimizer fits the 16 slots of a line, four per sector
+                                 // k-mers sharing one minimizer puts at most 4 keys into each unit of its group
 constexpr u32 LOC_MB = 2 * LOC_L; // bits of a minimizer
-constexpr u32 LOC_GB = 3;         // a minimizer's home is a GROUP of 2^3 buckets (two adjacent 128-byte lines, 32 slots): the bucket
-                                 // inside it is the minimizer's position mod 8, so one run of <= 16 k-mers puts <= 2 keys in a bucket
+constexpr u32 LOC_GB = 3;         // a group is 2^3 buckets = four 64-byte units
 
 struct TableFmt {
     u32 b;                       // bucket bits: 2^b buckets of 32 bytes
@@ -77,6 +80,7 @@ struct TableFmt {
     __host__ __device__ u32 tag_shift() const { return fmt_bits - disp_bits; }
     __host__ __device__ u32 flag_shift() const { return fmt_bits - disp_bits - F; }
     __host__ __device__ u32 max_disp() const { return (1u << disp_bits) - 2u; }
+    __host__ __device__ u32 unit_slots() const { return layout == LAYOUT_MINIMIZER ? 8u : 4u; }   // slots one probe covers
 };
 
 struct TableView {
@@ -187,69 +191,70 @@ __host__ __device__ __forceinline__ u32 rc16(u32 x) {
     r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);     // bit-reversed pairs back in order
     return ~r;
 }
-// remainder bits of a LAYOUT_MINIMIZER slot: [minimizer hash below the group bits | position >> 3 | orientation | flank hash]
-__host__ __device__ __forceinline__ u32 loc_rembits(u32 k, u32 b) { return (LOC_MB - (b - LOC_GB)) + 1 + 1 + 2 * (k - LOC_L); }
+// The minimizer's two hashes, both bijections on 32 bits and one instruction pair each:
+//   loc_hash   orders the canonical 16-mers of a k-mer (its top 27 bits; the xor keeps poly-A from being everybody's minimum);
+//   loc_place  folds the well-mixed high half into the low half: the GROUP is the low bits of loc_place(loc_hash(c)) -- the
+//              minimum of 16 hashes is small in its top bits, which would crowd the keys into few groups -- and the bits above
+//              them go into the remainder.
+__host__ __device__ __forceinline__ u32 loc_hash(u32 c) { return (c ^ 0x5bd1e995u) * 0x9e3779b1u; }
+__host__ __device__ __forceinline__ u32 loc_unhash(u32 h) { return (h * (u32)inv_odd(0x9e3779b1u)) ^ 0x5bd1e995u; }
+__host__ __device__ __forceinline__ u32 loc_place(u32 h) { return h ^ (h >> 16); }                 // its own inverse
+// remainder bits of a LAYOUT_MINIMIZER slot: [the other k-16 bases | position >> 2 | orientation | group hash above the group bits]
+__host__ __device__ __forceinline__ u32 loc_rembits(u32 k, u32 b) { return 2 * (k - LOC_L) + 2 + 1 + (LOC_MB - (b - LOC_GB)); }
 __host__ __device__ __forceinline__ u32 loc_fmt_bits(u32 k, u32 b) { return 64 - loc_rembits(k, b); }
 struct TableHash { u64 home; u64 tag; u32 fsel; };                // home bucket, left-aligned remainder, overflow-flag selector
 
-// (bucket, remainder) of k-mer s once its minimizer is known: mh = nmix(canonical 16-mer, 32), at position bp of s,
-// bo = the 16-mer stands in s as the reverse complement of its canonical form
-__host__ __device__ __forceinline__ TableHash loc_pack(u64 s, u32 k, u32 b, u32 mh, u32 bp, u32 bo) {
+// (bucket, remainder) of the 2k-bit k-mer s once its minimizer is known: h = loc_hash(canonical 16-mer), at position bp of s
+// (0 = the first, most significant base), bo = the 16-mer stands in s as the reverse complement of its canonical form.
+// The other k-16 bases are taken as s rotated left by bp bases with the minimizer dropped: (right part : left part) -- two
+// shifts on 32-bit halves in the classify kernel.
+__host__ __device__ __forceinline__ TableHash loc_pack(u64 s, u32 k, u32 b, u32 h, u32 bp, u32 bo) {
     const u32 nf = 2 * (k - LOC_L), bl = b - LOC_GB;
-    const u32 nr = 2 * (k - LOC_L - bp);                                   // bits right of the minimizer
-    const u64 left = bp ? (s >> (2 * (k - bp))) : 0ull, right = nr ? (s & ((1ull << nr) - 1)) : 0ull;
-    const u32 fm = nmix((u32)((left << nr) | right), nf);
-    // the bucket inside the group: the minimizer's position mod 8. The k-mers of one run have consecutive positions, so a
-    // run spreads evenly over the group's eight buckets instead of overflowing one of them by chance.
-    const u32 sec = bp & ((1u << LOC_GB) - 1);
-    // the minimum of k-15 hashes is small: its top bits would crowd the keys into a few lines. The line comes from a
-    // second bijection of the winning hash.
-    const u32 li = nmix(mh ^ 0x2545f491u, LOC_MB);
-    const u32 line = li >> (LOC_MB - bl), mrest = bl >= LOC_MB ? 0u : (li & ((1u << (LOC_MB - bl)) - 1));
-    const u64 rem = ((((u64)mrest << 1 | (bp >> LOC_GB)) << 1 | bo) << nf) | fm;
+    const u64 fmask = (1ull << nf) - 1;
+    const u64 flank = ((s << (2 * bp)) & fmask) | (bp ? (s >> (2 * (k - bp))) : 0ull);
+    const u32 p = loc_place(h);
+    const u32 line = bl >= LOC_MB ? p : (p & ((1u << bl) - 1)), mrest = bl >= LOC_MB ? 0u : (p >> bl);
+    const u64 rem = ((((flank << 2) | (bp >> 2)) << 1 | bo) << (LOC_MB - bl)) | mrest;
     TableHash t;
-    t.home = ((u64)line << LOC_GB) | sec;
+    t.home = ((u64)line << LOC_GB) | ((bp & 3u) << 1);            // the unit's first (even) bucket
     t.tag = rem << (64 - loc_rembits(k, b));
-    t.fsel = fm;
+    t.fsel = (u32)(t.tag >> 34);                                   // k = 31: the other 15 bases
     return t;
 }
-// the order of the minimizer: the top 27 bits of the mixed canonical 16-mer (so that value and position sort as one
-// 32-bit word in the classify kernel), LEFTMOST position of the k-mer on ties
+// the order of the minimizer: the top 27 bits of loc_hash of the canonical 16-mer (value and position sort as one 32-bit
+// word in the classify kernel), LEFTMOST position of the k-mer on ties
 __host__ __device__ inline TableHash loc_encode(u64 s, u32 k, u32 b) {
     const u32 J = k - LOC_L + 1;
     u32 best = ~0u, best27 = ~0u, bp = 0, bo = 0;
     for(u32 p = 0; p < J; ++p) {
         const u32 f = (u32)(s >> (2 * (k - LOC_L - p)));                     // position 0 = the first (most significant) base
-        const u32 r = rc16(f), c = f < r ? f : r, mh = nmix(c, LOC_MB);
+        const u32 r = rc16(f), c = f < r ? f : r, mh = loc_hash(c);
         if((mh >> 5) < best27) { best27 = mh >> 5; best = mh; bp = p; bo = r < f; }
     }
     return loc_pack(s, k, b, best, bp, bo);
 }
-// inverse: home bucket + left-aligned remainder -> key
+// inverse: home bucket (any bucket of the unit) + left-aligned remainder -> key
 __host__ __device__ inline u64 loc_decode(u64 home, u64 tag, u32 k, u32 b) {
-    const u32 nf = 2 * (k - LOC_L), bl = b - LOC_GB;
+    const u32 bl = b - LOC_GB;
     const u64 rem = tag >> (64 - loc_rembits(k, b));
-    const u32 fm = (u32)(rem & (nf >= 32 ? 0xffffffffull : ((1ull << nf) - 1)));
-    const u32 bo = (u32)(rem >> nf) & 1u, bp = ((u32)(rem >> (nf + 1)) & 1u) << LOC_GB | ((u32)home & ((1u << LOC_GB) - 1));
-    const u32 mrest = (u32)(rem >> (nf + 2));
-    const u32 li = bl >= LOC_MB ? (u32)(home >> LOC_GB) : (((u32)(home >> LOC_GB) << (LOC_MB - bl)) | mrest);
-    const u32 mh = nunmix(li, LOC_MB) ^ 0x2545f491u;
-    const u32 c = nunmix(mh, LOC_MB), f = bo ? rc16(c) : c;
-    const u32 fl = nunmix(fm, nf);
-    const u32 nr = 2 * (k - LOC_L - bp);
-    const u64 left = nr >= 32 ? 0ull : ((u64)fl >> nr), right = nr ? ((u64)fl & ((1ull << nr) - 1)) : 0ull;
-    return (((left << LOC_MB) | f) << nr) | right;
+    const u32 mrest = bl >= LOC_MB ? 0u : (u32)(rem & ((1ull << (LOC_MB - bl)) - 1));
+    const u64 up = rem >> (LOC_MB - bl);
+    const u32 bo = (u32)up & 1u, bp = (((u32)(up >> 1) & 3u) << 2) | (((u32)home >> 1) & 3u);
+    const u64 flank = up >> 3;
+    const u32 p = bl >= LOC_MB ? (u32)(home >> LOC_GB) : ((mrest << bl) | (u32)(home >> LOC_GB));
+    const u32 c = loc_unhash(loc_place(p)), m = bo ? rc16(c) : c;
+    const u32 nr = 2 * (k - LOC_L - bp);                                     // bits right of the minimizer
+    const u64 left = bp ? (flank & ((1ull << (2 * bp)) - 1)) : 0ull, right = flank >> (2 * bp);
+    return (bp ? (left << (2 * (k - bp))) : 0ull) | ((u64)m << nr) | right;
 }
-// the d-th bucket of a key's probe sequence. LAYOUT_HASH: the next buckets. LAYOUT_MINIMIZER: the home bucket, its neighbour
-// in the group (same pair of lines, already in L2), then a run of buckets starting at a scrambled image of the home bucket:
-// keys that overflow a crowded group (two or three minimizer runs in one) scatter instead of piling into the next group,
-// so probe sequences stay short.
+// the d-th probe of a key, as the index of its first bucket. LAYOUT_HASH: the next buckets. LAYOUT_MINIMIZER: the home unit,
+// then a run of units starting at a scrambled image of the home unit: keys that overflow a crowded group scatter instead of
+// piling into the next group, so probe sequences stay short.
 __host__ __device__ __forceinline__ u64 probe_bucket(u32 layout, u64 home, u32 d, u32 b) {
     const u64 bmask = b >= 64 ? ~0ull : ((1ull << b) - 1);
     if(layout == LAYOUT_MINIMIZER) {
-        const u64 gm = (1ull << LOC_GB) - 1;
-        if(d < 2) return (home & ~gm) | ((home + d) & gm);
-        return ((u64)nmix((u32)home, b) + (d - 2)) & bmask;
+        if(d == 0) return home & ~1ull;
+        return (((u64)nmix((u32)(home >> 1), b - 1) + (d - 1)) << 1) & bmask;
     }
     return (home + d) & bmask;
 }
@@ -257,9 +262,8 @@ __host__ __device__ __forceinline__ u64 probe_bucket(u32 layout, u64 home, u32 d
 __host__ __device__ __forceinline__ u64 probe_home(u32 layout, u64 bucket, u32 d, u32 b) {
     const u64 bmask = b >= 64 ? ~0ull : ((1ull << b) - 1);
     if(layout == LAYOUT_MINIMIZER) {
-        const u64 gm = (1ull << LOC_GB) - 1;
-        if(d < 2) return (bucket & ~gm) | ((bucket - d) & gm);
-        return (u64)nunmix((u32)((bucket - (d - 2)) & bmask), b);
+        if(d == 0) return bucket & ~1ull;
+        return (u64)nunmix((u32)((((bucket >> 1) - (d - 1)) & (bmask >> 1))), b - 1) << 1;
     }
     return (bucket - d) & bmask;
 }

@@ -212,15 +212,29 @@ __device__ __forceinline__ u32 match4(const TableView &T, u64 tag, u64 s0, u64 s
     if(d3 == 0) v = (u32)s3;
     return (d0 && d1 && d2 && d3) ? VAL_MISS : (v & T.val_mask);
 }
-// buckets after the home bucket (rare: the home bucket overflowed when the table was built)
+// One probe of a key covers T.fmt.unit_slots() slots: one 32-byte bucket (LAYOUT_HASH) or a 64-byte unit of two
+// (LAYOUT_MINIMIZER). Exact test of every slot of the probe at `bucket`. flagw: the low word of the probe's first slot (the
+// overflow flags); last_free: the probe's last slot is empty.
+__device__ __forceinline__ u32 match_probe(const TableView &T, u64 bucket, u64 tag, u32 &flagw, bool &last_free) {
+    u64 a, b, c, d;
+    ld_bucket(T.slots + (bucket << 2), a, b, c, d);
+    flagw = (u32)a;
+    last_free = d == ~0ull;
+    u32 v = match4(T, tag, a, b, c, d);
+    if(T.fmt.layout == LAYOUT_MINIMIZER) {
+        ld_bucket(T.slots + (bucket << 2) + 4, a, b, c, d);
+        last_free = d == ~0ull;
+        const u32 v2 = match4(T, tag, a, b, c, d);
+        if(v == VAL_MISS) v = v2;
+    }
+    return v;
+}
+// probes after the home probe (rare: the home probe was full when the table was built)
 __device__ __noinline__ u32 probe_displaced(const TableView T, u64 home, u64 tag) {
-    const u32 b = T.bucket_bits;
-    const u64 bmask = (1ull << b) - 1;
     for(u32 d = 1; d <= T.fmt.max_disp(); ++d) {
-        u64 a, bb, c, e;
-        ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, T.fmt.b) << 2), a, bb, c, e);
-        const u32 v = match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e);
-        if(v != VAL_MISS || e == ~0ull) return v;
+        u32 fw; bool last_free;
+        const u32 v = match_probe(T, probe_bucket(T.fmt.layout, home, d, T.fmt.b), tag | ((u64)d << T.tag_shift), fw, last_free);
+        if(v != VAL_MISS || last_free) return v;                   // a probe with a free slot ends the run
     }
     return VAL_MISS;
 }
@@ -234,29 +248,39 @@ __device__ __forceinline__ u32 match4_home(const TableView &T, u64 tag, u64 s0, 
     const bool ok = (m0 | m1 | m2 | m3) && (((cand ^ tl) & hm) == 0);            // an empty slot (disp 15) never passes
     return ok ? (cand & T.val_mask) : VAL_MISS;
 }
+// kh_get + kh_val for one key (generic kernels: lookup, the stream kernels of LAYOUT_MINIMIZER tables)
+__device__ __forceinline__ u32 probe_key(const TableView &T, u64 key) {
+    bool possible;
+    const TableHash h = table_hash(T.fmt, key, possible);
+    if(!possible) return VAL_MISS;
+    u32 fw; bool last_free;
+    const u32 v = match_probe(T, probe_bucket(T.fmt.layout, h.home, 0, T.fmt.b), h.tag, fw, last_free);
+    // The overflow mark is a CLEARED bit in slot 0 of a full home probe (an empty slot is all ones, so an empty or
+    // part-filled one reads "no overflow"): a miss costs one probe unless a key homed there was displaced.
+    if(v == VAL_MISS && !((fw >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) return probe_displaced(T, h.home, h.tag);
+    return v;
+}
 // kh_get + kh_val for PPL keys per lane: all home-bucket sectors are requested before any is inspected. Lanes / slots
 // without a live k-mer probe anyway (their result is masked by the caller): no predication, no register init.
 __device__ __forceinline__ void probe4(const TableView &T, const u64 (&x)[PPL], u32 (&val)[PPL]) {
+    if(T.fmt.layout != LAYOUT_HASH) {                             // 64-byte probes: key by key (the lean kernel has the fast path)
+#pragma unroll
+        for(int i = 0; i < PPL; ++i) val[i] = probe_key(T, x[i]);
+        return;
+    }
     TableHash h[PPL];
     u64 s[PPL][4];
-    u32 imposs = 0;
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
         bool possible;
         h[i] = table_hash(T.fmt, x[i], possible);
-        if(!possible) imposs |= 1u << i;
         ld_bucket(T.slots + (h[i].home << 2), s[i][0], s[i][1], s[i][2], s[i][3]);
     }
-    // The overflow mark is a CLEARED bit in slot 0 of a full home bucket (an empty slot is all ones, so an empty or
-    // part-filled bucket reads "no overflow"): a miss costs one sector unless a key homed there was displaced.
     u32 more = 0;
-    const bool exact = T.fmt.layout != LAYOUT_HASH;               // only LAYOUT_HASH keeps upper words unique in a bucket
 #pragma unroll
     for(int i = 0; i < PPL; ++i) {
-        val[i] = exact ? match4(T, h[i].tag, s[i][0], s[i][1], s[i][2], s[i][3])
-                       : match4_home(T, h[i].tag, s[i][0], s[i][1], s[i][2], s[i][3]);
-        if(imposs >> i & 1u) val[i] = VAL_MISS;
-        else if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.flag_shift + (h[i].fsel & T.flag_mask))) & 1u)) more |= 1u << i;
+        val[i] = match4_home(T, h[i].tag, s[i][0], s[i][1], s[i][2], s[i][3]);
+        if(val[i] == VAL_MISS && !(((u32)s[i][0] >> (T.flag_shift + (h[i].fsel & T.flag_mask))) & 1u)) more |= 1u << i;
     }
     if(more) {                                                    // rare
 #pragma unroll
@@ -440,8 +464,8 @@ struct BuildSink {
     __device__ __forceinline__ void insert(u64 key) {
         bool possible;
         const TableHash th = table_hash(fmt, key, possible);
-        if(!possible) { ++n_fail; return; }
-        const u64 home = th.home, bmask = (1ull << b) - 1, tag = th.tag;
+        if(!possible || fmt.layout != LAYOUT_HASH) { ++n_fail; return; }   // databases are built in LAYOUT_HASH and re-homed (build_finish)
+        const u64 home = th.home, tag = th.tag;
         for(u32 d = 0; d <= fmt.max_disp(); ++d) {
             u64 *bk = slots + (probe_bucket(fmt.layout, home, d, fmt.b) << 2);
             const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << tag_shift) - 1) & ~(u64)val_mask) | vid;
@@ -861,14 +885,15 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u
     bool possible;
     const TableHash th = table_hash(fmt, key, possible);
     if(!possible) { atomicAdd(&stats[0], 1ull); return; }
-    const u32 b = fmt.b, F = fmt.F;
-    const u64 home = th.home, bmask = (1ull << b) - 1;
+    const u32 F = fmt.F;
+    const u64 home = th.home;
     const u32 tag_shift = fmt.tag_shift(), flag_shift = fmt.flag_shift();
     const u64 tag = th.tag;
     for(u32 d = 0; d <= fmt.max_disp(); ++d) {
         u64 *bk = slots + (probe_bucket(fmt.layout, home, d, fmt.b) << 2);
         const u64 entry = tag | ((u64)d << tag_shift) | (((1ull << F) - 1) << flag_shift) | vid;
-        for(int s = 0; s < 4; ++s) {
+        const int ns = (int)fmt.unit_slots();
+        for(int s = 0; s < ns; ++s) {
             u64 cur = bk[s];
             if(cur == ~0ull) {
                 cur = atomicCAS((unsigned long long *)&bk[s], ~0ull, (unsigned long long)entry);
@@ -885,18 +910,21 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u
 }
 
 __global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, TableFmt fmt,
-                                       unsigned long long *__restrict__ out /* [0] entries [1] ovf buckets [2] max disp */) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n_buckets) return;
+                                       unsigned long long *__restrict__ out /* [0] entries [1] overflowed probes [2] max disp */) {
+    const u64 ns = fmt.unit_slots();
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;        // one thread per probe unit
+    if(i >= n_buckets * 4 / ns) return;
     const u32 tag_shift = fmt.tag_shift(), F = fmt.F;
     u32 cnt = 0, md = 0;
-    for(int s = 0; s < 4; ++s) {
-        const u64 v = slots[4 * i + s];
+    bool flagged = false;
+    const u64 flags = ((1ull << F) - 1) << (tag_shift - F);
+    for(u64 s = 0; s < ns; ++s) {
+        const u64 v = slots[ns * i + s];
         if(v != ~0ull) { ++cnt; md = max(md, (u32)((v >> tag_shift) & ((1u << fmt.disp_bits) - 1))); }
     }
+    flagged = cnt == ns && (slots[ns * i] & flags) != flags;
     if(cnt) atomicAdd(&out[0], (unsigned long long)cnt);
-    const u64 flags = ((1ull << F) - 1) << (tag_shift - F);
-    if(cnt == 4 && (slots[4 * i] & flags) != flags) atomicAdd(&out[1], 1ull);
+    if(flagged) atomicAdd(&out[1], 1ull);
     if(md) atomicMax(&out[2], (unsigned long long)md);
 }
 
@@ -904,31 +932,33 @@ __global__ void bns_lookup_kernel(TableView T, const u32 *__restrict__ dict, con
                                   u32 *__restrict__ vals_out, uint8_t *__restrict__ found_out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    bool possible;
-    const TableHash h = table_hash(T.fmt, keys[i], possible);
-    u64 a, b, c, d;
-    ld_bucket(T.slots + (h.home << 2), a, b, c, d);
-    u32 v = T.fmt.layout != LAYOUT_HASH ? match4(T, h.tag, a, b, c, d) : match4_home(T, h.tag, a, b, c, d);
-    if(!possible) v = VAL_MISS;
-    else if(v == VAL_MISS && !(((u32)a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) v = probe_displaced(T, h.home, h.tag);
+    u32 v;
+    if(T.fmt.layout == LAYOUT_HASH) {                              // the home-bucket test the classify kernels use
+        bool possible;
+        const TableHash h = table_hash(T.fmt, keys[i], possible);
+        u64 a, b, c, d;
+        ld_bucket(T.slots + (h.home << 2), a, b, c, d);
+        v = match4_home(T, h.tag, a, b, c, d);
+        if(v == VAL_MISS && !(((u32)a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) v = probe_displaced(T, h.home, h.tag);
+    } else v = probe_key(T, keys[i]);
     found_out[i] = v != VAL_MISS;
     vals_out[i] = v != VAL_MISS ? dict[v] : 0u;
 }
 
+// 32-byte sectors the probes of `keys` touch (a LAYOUT_MINIMIZER probe is two adjacent ones)
 __global__ void bns_sectors_kernel(TableView T, const u64 *__restrict__ keys, u64 n, unsigned long long *__restrict__ total) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 touched = 0;
     if(i < n) {
-        const u32 b = T.bucket_bits;
         bool possible;
         const TableHash h = table_hash(T.fmt, keys[i], possible);
-        const u64 home = h.home, bmask = (1ull << b) - 1, tag = h.tag;
+        const u32 per = T.fmt.unit_slots() / 4;
         for(u32 d = 0; d <= T.fmt.max_disp(); ++d) {
-            u64 a, bb, c, e;
-            ld_bucket(T.slots + (probe_bucket(T.fmt.layout, home, d, T.fmt.b) << 2), a, bb, c, e);
-            ++touched;
-            if(match4(T, tag | ((u64)d << T.tag_shift), a, bb, c, e) != VAL_MISS) break;
-            if(d == 0 ? (((a >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1ull) != 0) : (e == ~0ull)) break;
+            u32 fw; bool last_free;
+            const u32 v = match_probe(T, probe_bucket(T.fmt.layout, h.home, d, T.fmt.b), h.tag | ((u64)d << T.tag_shift), fw, last_free);
+            touched += per;
+            if(v != VAL_MISS) break;
+            if(d == 0 ? (((fw >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u) != 0) : last_free) break;
         }
     }
     touched = __reduce_add_sync(FULL, touched);
@@ -1244,7 +1274,8 @@ cudaError_t launch_insert(cudaStream_t st, u64 *slots, const TableFmt &fmt, cons
     return cudaGetLastError();
 }
 cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, unsigned long long *out) {
-    bns_table_stats_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(slots, n_buckets, fmt, out);
+    const u64 n_units = n_buckets * 4 / fmt.unit_slots();
+    bns_table_stats_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, st>>>(slots, n_buckets, fmt, out);
     return cudaGetLastError();
 }
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,

@@ -14,19 +14,22 @@ static int classify_usage(const char *ex) {
                  "-o:\tRedirect output to path instead of stdout.\n-c:\tSet chunk size [1048576 bases]\n"
                  "-a:\tEmit all records, not just classified.\n-p:\tSet number of threads. Default: 1.\n"
                  "-k:\tEmit kraken-style output.\n-K:\tDo not emit kraken-style output.\n-f:\tEmit fastq-style output.\n"
-                 "-F:\tDo not emit fastq-style output.\n-C:\tDo not canonicalize.\n-S:\tSet records per worker set (ignored: one GPU call per chunk)\n",
+                 "-F:\tDo not emit fastq-style output.\n-C:\tDo not canonicalize.\n-S:\tSet records per worker set (ignored: one GPU call per chunk)\n"
+                 "--gpus N:\tShard the reads over N GPUs (database replicated once over NVLink). Default: 1.\n",
                  ex);
     return EXIT_FAILURE;
 }
 
 // classify_main, bin/bonsai.cpp:107-163
 static int classify_main(int argc, char *argv[]) {
-    int co, num_threads(1), emit_kraken(1), emit_fastq(0), emit_all(0), chunk_size(1 << 20), per_set(32);
+    int co, num_threads(1), emit_kraken(1), emit_fastq(0), emit_all(0), chunk_size(1 << 20), per_set(32), n_gpus(1);
     bool canonicalize(true);
     std::FILE *ofp(stdout);
     if(argc < 4) return classify_usage(argv[0]);
-    while((co = getopt(argc, argv, "Cc:p:o:S:afFkKh?")) >= 0) {
+    static const struct option long_opts[] = {{"gpus", required_argument, nullptr, 1000}, {nullptr, 0, nullptr, 0}};
+    while((co = getopt_long(argc, argv, "Cc:p:o:S:afFkKh?", long_opts, nullptr)) >= 0) {
         switch(co) {
+            case 1000: n_gpus = std::atoi(optarg); break;
             case 'h': case '?': return classify_usage(argv[0]);
             case 'a': emit_all = 1; break;
             case 'C': canonicalize = false; break;
@@ -49,6 +52,7 @@ static int classify_main(int argc, char *argv[]) {
         const double t1 = now();
         // bin/bonsai.cpp:152: always score::Lex with window = k, whatever the DB was minimised with
         Classifier c(db, db.s_, (u8)db.k_, (u16)db.k_, num_threads, emit_all, emit_fastq, emit_kraken, canonicalize);
+        if(n_gpus > 1) c.set_gpus(n_gpus);       // replicas are made once the taxonomy is loaded (process_dataset)
         const double t2 = now();
         std::unique_ptr<TaxMap> taxmap(build_parent_map(argv[optind + 1]));
         const char *fq2 = (argc - optind >= 4) ? argv[optind + 3] : nullptr;

@@ -64,7 +64,8 @@ typedef struct bns_b200_config {
     uint32_t api;               /* BNS_API_* */
     uint32_t entropy_cast;      /* BNS_CAST_* */
     int32_t  device;            /* CUDA ordinal, -1 = current device */
-    uint32_t reserved[7];
+    uint32_t n_gpus;            /* bns_b200_open_multi: contexts to open when its n_gpus argument is 0 (0 = every visible device) */
+    uint32_t reserved[6];
 } bns_b200_config;
 
 typedef struct bns_b200_ctx bns_b200_t;
@@ -153,6 +154,17 @@ int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr
 /* device segments that make up the database: fills up to `cap` (ptr, bytes) pairs, returns the count in *n */
 int bns_b200_db_segments(const bns_b200_t *ctx, void **dev_ptrs, uint64_t *bytes, int cap, int *n);
 int bns_b200_db_commit(bns_b200_t *ctx);
+
+/* ---- several GPUs in ONE process (reads dealt chunk by chunk to the GPUs, database replicated once) ------
+ * open_multi opens one context per device (devices == NULL: ordinals 0..n_gpus-1; n_gpus == 0: cfg->n_gpus, and if that is 0
+ * too every visible device) with the same Spacer / Encoder configuration; out[] receives n contexts and *n_out their count.
+ * replicate copies the database (table + taxonomy) of handles[root] into the other contexts: ncclCommInitAll over their
+ * devices and ONE ncclBroadcast per device segment (slots, value dictionary, val_info, node_info) over NVLink. After it
+ * every context classifies on its own; each is driven by one host thread at a time (process_dataset, classifier.h:296,
+ * deals its chunks round-robin). There is no per-batch collective. */
+int bns_b200_open_multi(const bns_b200_config *cfg, int n_gpus, const int *devices, bns_b200_t **out, int *n_out);
+int bns_b200_replicate(bns_b200_t *const *handles, int n, int root);
+void bns_b200_close_multi(bns_b200_t **handles, int n);
 
 /* ---- Encoder<Score>::for_each(fn, str, len) over a batch -- encoder.h:416 ------------------------------
  * bases: all sequences concatenated (ASCII); offsets[n+1]. Sequence r's k-mers are written in emission order

@@ -28,6 +28,8 @@
 #include <mutex>
 #include <thread>
 #include <stdexcept>
+#include <map>
+#include <type_traits>
 #include <string>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -396,7 +398,7 @@ inline TaxMap *build_parent_map(const char *fn) {                   // util.h:76
 //   u32 k, u32 w, (k-1) x u8 gaps, u64 n_buckets, u64 n_occupied, u64 size, u64 upper_bound,
 //   u32 flags[max(1, n_buckets/16)], u64 keys[n_buckets], u32 vals[n_buckets]          (little endian, no padding)
 // i.e. the raw khash_t(c) arrays (Wang64 hash, triangular probing, 2 flag bits per bucket, khash64.h:169-263).
-struct Database {
+struct DatabaseImpl {
     u32 k_ = 0, w_ = 0;
     spvec_t s_;                                  // gaps (before the Spacer's +1)
     u64 n_buckets = 0, n_occupied = 0, size = 0, upper_bound = 0;
@@ -411,8 +413,8 @@ struct Database {
         return key + (key << 31);
     }
     bool exists(u64 i) const { return ((flags[i >> 4] >> ((i & 0xfU) << 1)) & 3u) == 0; }
-    Database() = default;
-    explicit Database(const char *path) {        // database.h:33-56 (with the fread / popen defects of App. B-1 not reproduced)
+    DatabaseImpl() = default;
+    explicit DatabaseImpl(const char *path) {    // database.h:33-56 (with the fread / popen defects of App. B-1 not reproduced)
         gzFile fp = gzopen(path, "rb");
         if(!fp) BNS_RUNTIME_ERROR(std::string("Could not open database at ") + path);
         auto rd = [&](void *p, size_t n) {
@@ -484,6 +486,25 @@ struct Database {
         std::fclose(fp);
     }
 };
+// The raw khash_t(c) as the reference declares it (struct kh_c_s, khash64.h:213-219, khint_t = u64): what Database<T>::db_
+// points to and what ClassifierGeneric's constructor takes (classifier.h:155). Here it is a VIEW of the vectors above.
+struct kh_c_t { u64 n_buckets, size, n_occupied, upper_bound; u32 *flags; u64 *keys; u32 *vals; };
+// Database<khash_t(c)> (database.h:17): the reference's spelling. T must be kh_c_t; db_ views the arrays of this object.
+template <typename T = kh_c_t>
+struct Database : DatabaseImpl {
+    static_assert(std::is_same<T, kh_c_t>::value, "Database<T>: only khash_t(c) databases exist on the classify path");
+    kh_c_t view_{};
+    T *db_ = nullptr;
+    void sync() {                                // after the arrays changed (assign)
+        view_ = kh_c_t{n_buckets, size, n_occupied, upper_bound, flags.data(), keys.data(), vals.data()};
+        db_ = &view_;
+    }
+    Database() { sync(); }
+    explicit Database(const char *path) : DatabaseImpl(path) { sync(); }
+    Database(const Database &o) : DatabaseImpl(o) { sync(); }
+    Database &operator=(const Database &o) { DatabaseImpl::operator=(o); sync(); return *this; }
+    void assign(u32 k, u32 w, const spvec_t &gaps, const u64 *ks, const u32 *vs, u64 n) { DatabaseImpl::assign(k, w, gaps, ks, vs, n); sync(); }
+};
 
 // ---- reads -----------------------------------------------------------------------------------------------------
 struct bseq1_t {                                  // kseq_declare.h:40-44 (strings own their storage here)
@@ -525,6 +546,8 @@ struct ClassifierGeneric {
     u32 nt_ : 16;
     u32 output_flag_ : 16;
     std::shared_ptr<detail::Handle> h_;
+    std::vector<std::shared_ptr<detail::Handle>> replicas_;      // contexts on GPUs 1 .. n-1 holding a copy of the database (set_gpus)
+    int n_gpus_ = 1;
     bool tax_loaded_ = false;
     void set_emit_all(bool s) { if(s) output_flag_ |= EMIT_ALL; else output_flag_ &= ~EMIT_ALL; }
     void set_emit_kraken(bool s) { if(s) output_flag_ |= KRAKEN; else output_flag_ &= ~KRAKEN; }
@@ -533,20 +556,56 @@ struct ClassifierGeneric {
     int get_emit_kraken() const { return output_flag_ & KRAKEN; }
     int get_emit_fastq() const { return output_flag_ & FASTQ; }
     // classifier.h:155-166; `map` = the database whose raw khash arrays go to the device
-    ClassifierGeneric(const Database &map, const spvec_t &spaces, u8 k, u16 wsz, int num_threads = 16, bool emit_all = true,
+    ClassifierGeneric(const DatabaseImpl &map, const spvec_t &spaces, u8 k, u16 wsz, int num_threads = 16, bool emit_all = true,
                       bool emit_fastq = true, bool emit_kraken = false, bool canonicalize = true)
         : sp_(k, wsz, spaces), enc_(sp_, canonicalize), nt_(num_threads > 0 ? (u16)num_threads : (u16)std::max(1u, std::thread::hardware_concurrency())), output_flag_(0) {
         set_emit_all(emit_all); set_emit_fastq(emit_fastq); set_emit_kraken(emit_kraken);
-        h_ = detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING);
+        h_ = detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING, 0);
         detail::check(h_->h, bns_b200_load_table(h_->h, map.keys.data(), map.vals.data(), map.flags.data(), map.n_buckets),
                       "bns_b200_load_table");
+    }
+    // the reference's own argument list: the raw khash_t(c) (classifier.h:155; kh_c_t below)
+    ClassifierGeneric(const kh_c_t *map, const spvec_t &spaces, u8 k, u16 wsz, int num_threads = 16, bool emit_all = true,
+                      bool emit_fastq = true, bool emit_kraken = false, bool canonicalize = true)
+        : sp_(k, wsz, spaces), enc_(sp_, canonicalize), nt_(num_threads > 0 ? (u16)num_threads : (u16)std::max(1u, std::thread::hardware_concurrency())), output_flag_(0) {
+        set_emit_all(emit_all); set_emit_fastq(emit_fastq); set_emit_kraken(emit_kraken);
+        h_ = detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING, 0);
+        detail::check(h_->h, bns_b200_load_table(h_->h, map->keys, map->vals, map->flags, map->n_buckets), "bns_b200_load_table");
+    }
+    // Reads shard over n GPUs of this process: GPU 0 holds the table; the others receive a copy with one NCCL
+    // broadcast per segment (bns_b200_replicate) once the taxonomy is there, and process_dataset deals its chunks round-robin.
+    void set_gpus(int n) {
+        if(n < 1) BNS_RUNTIME_ERROR("set_gpus: need at least one GPU");
+        if(!replicas_.empty() && n != n_gpus_) BNS_RUNTIME_ERROR("set_gpus: replicas already exist");
+        n_gpus_ = n;
+        if(tax_loaded_) replicate();
+    }
+    int n_gpus() const { return n_gpus_; }
+    bns_b200_t *gpu(int g) const { return g == 0 ? h_->h : replicas_[(size_t)g - 1]->h; }
+    void replicate() {
+        if(n_gpus_ <= 1 || !replicas_.empty()) return;
+        std::vector<bns_b200_t *> all(1, h_->h);
+        for(int g = 1; g < n_gpus_; ++g) {
+            replicas_.push_back(detail::open_handle(sp_, ScoreType::id, enc_.canonicalize(), BNS_API_STRING, g));
+            all.push_back(replicas_.back()->h);
+        }
+        detail::check(h_->h, bns_b200_replicate(all.data(), n_gpus_, 0), "bns_b200_replicate");
     }
     void load_taxonomy(const TaxMap *t) {
         detail::check(h_->h, bns_b200_load_taxonomy(h_->h, t->child.data(), t->parent.data(), t->size()), "bns_b200_load_taxonomy");
         tax_loaded_ = true;
+        replicate();
     }
-    u64 n_classified() const { bns_b200_stats s; bns_b200_stats_get(h_->h, &s); return s.n_classified; }      // classifier.h:170
-    u64 n_unclassified() const { bns_b200_stats s; bns_b200_stats_get(h_->h, &s); return s.n_unclassified; }  // :171
+    u64 n_classified() const {                                    // classifier.h:170
+        u64 n = 0;
+        for(int g = 0; g < (replicas_.empty() ? 1 : n_gpus_); ++g) { bns_b200_stats s; bns_b200_stats_get(gpu(g), &s); n += s.n_classified; }
+        return n;
+    }
+    u64 n_unclassified() const {                                  // :171
+        u64 n = 0;
+        for(int g = 0; g < (replicas_.empty() ? 1 : n_gpus_); ++g) { bns_b200_stats s; bns_b200_stats_get(gpu(g), &s); n += s.n_unclassified; }
+        return n;
+    }
 };
 using Classifier = ClassifierGeneric<score::Lex>;
 
@@ -627,16 +686,16 @@ inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxo
 // (classifier.h:232-246). `views` has one entry per read (mates interleaved).
 template <typename ScoreType>
 void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ReadView *views, unsigned n_reads,
-                    int is_paired, std::string &cks) {
+                    int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
+    if(!h) h = c.h_->h;                                               // the context (GPU) this batch runs on
     // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
     // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
     const bool need_taxa = (c.output_flag_ & KRAKEN) != 0;
     std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(is_paired ? nrec : 0), nruns(need_taxa ? nrec : 0);
     std::vector<u64> run_pos(need_taxa ? nrec : 0);
     std::unique_ptr<u64[]> runs;
-    bns_b200_t *h = c.h_->h;
     if(need_taxa) {
         // run lists: encoded on the device, 8 bytes per run back instead of 4 per k-mer window slot. The number of runs is
         // not known beforehand: a buffer for a few runs per record first, one for every possible hit if that was too small.
@@ -673,7 +732,7 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
             }
         }
     };
-    const unsigned nthreads = std::max(1u, std::min<unsigned>(c.nt_, nrec / 256 + 1));
+    const unsigned nthreads = std::max(1u, std::min<unsigned>(max_threads ? max_threads : c.nt_, nrec / 256 + 1));
     if(nthreads == 1) { format_range(0, nrec, cks); return; }
     std::vector<std::string> parts(nthreads);
     std::vector<std::thread> pool;
@@ -1153,27 +1212,81 @@ inline bool read_pinned(int chunk_size, PinnedBatch &b, KSeq *ks, KSeq *ks2) {
 
 // classify_seqs, classifier.h:269-289: classify `chunk_size` reads (mates interleaved when is_paired) and append each
 // record's text to cks in read order. per_set / the thread pool of the reference have no role here: the batch is one
-// GPU call.
+// GPU call (a caller that loops over single reads pays one device round trip per call: batch them).
 template <typename ScoreType>
 void classify_seqs(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, bseq1_t *bs, std::string &cks,
                    const unsigned chunk_size, const unsigned /*per_set*/, const int is_paired) {
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     const unsigned inc = is_paired ? 2 : 1, n = (chunk_size / inc) * inc;
     if(!n) return;
-    std::string bases;
-    std::vector<u64> offs(1, 0);
+    // the batch goes to the device from a pinned staging buffer kept per thread (no pageable copy inside the library)
+    thread_local detail::PinnedBatch stage;
+    size_t total = 0;
+    for(unsigned i = 0; i < n; ++i) total += bs[i].seq.size();
+    stage.clear();
+    detail::PinnedBatch::grow(stage.bases, stage.cap_bases, 0, total + 16);
+    detail::PinnedBatch::grow(stage.offs, stage.cap_offs, 0, (size_t)n + 2);
+    stage.offs[0] = 0;
+    for(unsigned i = 0; i < n; ++i) {
+        std::memcpy(stage.bases + stage.offs[i], bs[i].seq.data(), bs[i].seq.size());
+        stage.offs[i + 1] = stage.offs[i] + bs[i].seq.size();
+    }
     std::vector<detail::ReadView> views(n);
-    for(unsigned i = 0; i < n; ++i) { bases += bs[i].seq; offs.push_back(bases.size()); }
     for(unsigned i = 0; i < n; ++i)
-        views[i] = detail::ReadView{bs[i].name.c_str(), bases.data() + offs[i], bs[i].qual.empty() ? nullptr : bs[i].qual.c_str(), bs[i].l_seq};
-    const size_t before = cks.size();
-    detail::classify_views(c, bases.data(), offs.data(), views.data(), n, is_paired, cks);
-    (void)before;
+        views[i] = detail::ReadView{bs[i].name.c_str(), stage.bases + stage.offs[i], bs[i].qual.empty() ? nullptr : bs[i].qual.c_str(), bs[i].l_seq};
+    detail::classify_views(c, stage.bases, stage.offs, views.data(), n, is_paired, cks);
 }
 
-// process_dataset, classifier.h:296-337. Ingest is overlapped with the GPU: a reader thread parses FASTA/FASTQ(.gz)
-// records into a ring of pinned host batches while the caller's thread classifies the previous batch (the library DMAs
-// straight from the pinned buffer on its copy stream) and formats its text.
+}  // namespace bns
+// ---- the reference's spelling of the same calls -------------------------------------------------------------------------
+// classify_main (bin/bonsai.cpp:107-163) is written against khash_t(c) / khash_t(p), ks::string and ForPool. These shims let
+// such a caller compile against this header unchanged: khash_t(c) is the raw table view above, khash_t(p) the parent map,
+// ks::string a growable byte buffer with the members classify_seqs / process_dataset use, ForPool a thread count (the GPU
+// call needs no pool). They are only defined when the real headers are not part of the translation unit.
+#ifndef khash_t
+#define khash_t(name) ::bns::kh_##name##_t
+#define BNS_B200_KHASH_SHIM 1
+#endif
+#ifndef kh_destroy
+#define kh_destroy(name, h) ::bns::kh_destroy_##name(h)
+#endif
+namespace ks {
+#ifndef BNS_B200_NO_KS_SHIM
+class string {                                    // kspp/ks.h: the subset on the classify path
+    std::string s_;
+public:
+    explicit string(size_t reserve = 0) { s_.reserve(reserve); }
+    const char *data() const { return s_.data(); }
+    size_t size() const { return s_.size(); }
+    void clear() { s_.clear(); }
+    void resize(size_t n) { s_.reserve(n); }      // classify_seqs sizes the buffer before filling it (classifier.h:277)
+    void terminate() {}
+    int putsn_(const char *p, size_t n) { s_.append(p, n); return (int)n; }
+    int write(int fd) const {
+        size_t put = 0;
+        while(put < s_.size()) { const ssize_t r = ::write(fd, s_.data() + put, s_.size() - put); if(r <= 0) return -1; put += (size_t)r; }
+        return (int)put;
+    }
+    std::string &str() { return s_; }
+};
+#endif
+}  // namespace ks
+namespace bns {
+using kh_p_t = TaxMap;
+inline void kh_destroy_p(kh_p_t *t) { delete t; }
+inline void kh_destroy_c(kh_c_t *) {}              // a Database owns its arrays
+struct ForPool { int nt_; explicit ForPool(int nthreads = 1) : nt_(nthreads) {} };   // util.h ForPool: kt_forpool handle
+// classify_seqs with the reference's own parameter list (classifier.h:269); the pool is accepted and not needed
+template <typename ScoreType>
+void classify_seqs(ClassifierGeneric<ScoreType> &c, const kh_p_t *taxmap, bseq1_t *bs, ks::string &cks,
+                   const unsigned chunk_size, const unsigned per_set, const int is_paired, ForPool &) {
+    classify_seqs(c, taxmap, bs, cks.str(), chunk_size, per_set, is_paired);
+}
+
+// process_dataset, classifier.h:296-337, as a pipeline: a reader thread parses FASTA/FASTQ(.gz) records into a ring of
+// pinned host batches; one worker thread per GPU (ClassifierGeneric::set_gpus) takes the batches dealt to it round-robin
+// -- batch s goes to GPU s mod n, SURVEY 8e -- classifies it on its own context (the library DMAs straight from the pinned
+// buffer on that context's streams) and formats its text; a writer thread emits the texts in batch order.
 template <typename ScoreType>
 void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, const char *fq1, const char *fq2, std::FILE *out,
                      unsigned chunk_size, unsigned /*per_set*/) {
@@ -1187,16 +1300,20 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!simple->ok || (simple2 && !simple2->ok) || (ingest && !std::strcmp(ingest, "kseq"))) { simple.reset(); simple2.reset(); }
     bool use_index = simple != nullptr;          // the mappings stay alive to the end: batches in flight point into them
     const int fn = fileno(out), is_paired = fq2 != nullptr;
-    constexpr int NB = 3;
-    detail::PinnedBatch ring[NB];
+    const int G = c.replicas_.empty() ? 1 : c.n_gpus();
+    const int NB = 2 * G + 1;
+    std::vector<detail::PinnedBatch> ring((size_t)NB);
     for(auto &b : ring) { b.reserve(chunk_size); b.keep_qual = c.get_emit_fastq() != 0; }
-    int state[NB] = {0, 0, 0};                   // 0 free, 1 filled, 2 end of input
+    std::vector<int> state((size_t)NB, 0);       // 0 free, 1 filled
+    std::vector<u64> seq_of((size_t)NB, ~0ull);
+    u64 end_seq = ~0ull;                         // batches [0, end_seq) exist
     std::mutex mu;
     std::condition_variable cv;
     std::string reader_error;
     std::thread reader([&]() {
         try {
-            for(int i = 0;; i = (i + 1) % NB) {
+            for(u64 sq = 0;; ++sq) {
+                const size_t i = (size_t)(sq % (u64)NB);
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
                 bool got = false;
                 if(use_index) {
@@ -1204,7 +1321,7 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                     if(!got && simple->drained() && (!simple2 || simple2->drained())) {
                         // the index served the input to its end (a gzip stream would inflate once more to seek there)
                         use_index = false;
-                        { std::lock_guard<std::mutex> lk(mu); state[i] = 2; }
+                        { std::lock_guard<std::mutex> lk(mu); end_seq = sq; }
                         cv.notify_all();
                         return;
                     }
@@ -1219,98 +1336,102 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                     }
                 }
                 if(!got && !use_index) got = detail::read_pinned((int)chunk_size, ring[i], &ks1, ks2.get());
-                { std::lock_guard<std::mutex> lk(mu); state[i] = got ? 1 : 2; }
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if(got) { state[i] = 1; seq_of[i] = sq; } else end_seq = sq;
+                }
                 cv.notify_all();
                 if(!got) return;
             }
         } catch(const std::exception &e) {
             std::lock_guard<std::mutex> lk(mu);
             reader_error = e.what();
-            for(int &s : state) s = 2;
+            if(end_seq == ~0ull) { u64 mx = 0; for(size_t i = 0; i < (size_t)NB; ++i) if(state[i] == 1) mx = std::max(mx, seq_of[i] + 1); end_seq = mx; }
             cv.notify_all();
         }
     });
-    std::string cks;
-    // text leaves through a writer thread (at most two buffers queued), so write(2) overlaps the next batch
+    // text leaves through a writer thread, in batch order, so write(2) overlaps the next batches
     std::fflush(out);
     std::mutex wmu;
     std::condition_variable wcv;
-    std::deque<std::string> wq;
-    bool wdone = false;
+    std::map<u64, std::string> wq;               // finished texts by batch number (at most NB: a worker holds its ring slot until it has queued its text)
+    u64 w_end = ~0ull;                           // set once the last batch number is known
     std::string werr;
     std::thread writer([&]() {
-        for(;;) {
-            std::string s;
+        for(u64 next = 0;; ++next) {
+            std::string t;
             {
                 std::unique_lock<std::mutex> lk(wmu);
-                wcv.wait(lk, [&] { return !wq.empty() || wdone; });
-                if(wq.empty()) return;
-                s = std::move(wq.front()); wq.pop_front();
+                wcv.wait(lk, [&] { return wq.count(next) || next >= w_end; });
+                if(!wq.count(next)) return;
+                t = std::move(wq[next]); wq.erase(next);
             }
-            wcv.notify_all();
             if(!werr.empty()) continue;                                    // after a failed write: drain and drop
             size_t put = 0;
-            while(put < s.size()) {
-                const ssize_t r = ::write(fn, s.data() + put, s.size() - put);
+            while(put < t.size()) {
+                const ssize_t r = ::write(fn, t.data() + put, t.size() - put);
                 if(r <= 0) { std::lock_guard<std::mutex> lk(wmu); werr = "write failed"; break; }
                 put += (size_t)r;
             }
         }
     });
-    auto flush = [&]() {
-        if(cks.empty()) return;
-        std::unique_lock<std::mutex> lk(wmu);
-        wcv.wait(lk, [&] { return wq.size() < 2; });
-        if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
-        wq.push_back(std::move(cks));
-        cks.clear();
-        lk.unlock();
-        wcv.notify_all();
-    };
-    bool first = true;
+    std::atomic<bool> first(true);
     std::string failure;
-    std::vector<detail::ReadView> views;
     const bool verbose = std::getenv("BNS_B200_VERBOSE") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_wait = 0, t_classify = 0, t_write = 0;
-    size_t n_batches = 0;
-    for(int i = 0;; i = (i + 1) % NB) {
-        const double tw = now();
-        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] != 0; }); }
-        t_wait += now() - tw;
-        if(state[i] == 2) break;
-        detail::PinnedBatch &b = ring[i];
-        ++n_batches;
-        try {
-            if(failure.empty()) {
-                views.resize(b.n);
-                if(b.map)
-                    for(size_t r = 0; r < b.n; ++r) {
-                        const detail::RecRef &ref = b.refs[r];
-                        const char *mp = b.map_of(r);
-                        views[r] = detail::ReadView{mp + ref.name_off, b.bases + b.offs[r],
-                                                    b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
-                                                    (int)ref.seq_len, (int)ref.name_len};
-                    }
-                else
-                for(size_t r = 0; r < b.n; ++r)
-                    views[r] = detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
-                                                (int)(b.offs[r + 1] - b.offs[r])};
-                const double tc = now();
-                detail::classify_views(c, b.bases, b.offs, views.data(), (unsigned)b.n, is_paired, cks);
-                const double tf = now();
-                t_classify += tf - tc;
-                if(first) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
-                if(cks.size() > (1ull << 16)) flush();
-                t_write += now() - tf;
+    std::vector<double> t_wait((size_t)G, 0.), t_classify((size_t)G, 0.);
+    std::vector<size_t> n_batches((size_t)G, 0);
+    const unsigned fmt_threads = std::max(1u, (unsigned)c.nt_ / (unsigned)G);
+    auto work = [&](int g) {
+        std::vector<detail::ReadView> views;
+        bns_b200_t *h = c.gpu(g);
+        for(u64 sq = (u64)g;; sq += (u64)G) {
+            const size_t i = (size_t)(sq % (u64)NB);
+            const double tw = now();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return (state[i] == 1 && seq_of[i] == sq) || sq >= end_seq; });
+                if(!(state[i] == 1 && seq_of[i] == sq)) return;
             }
-        } catch(const std::exception &e) { failure = e.what(); }
-        { std::lock_guard<std::mutex> lk(mu); state[i] = 0; }
-        cv.notify_all();
-    }
+            t_wait[(size_t)g] += now() - tw;
+            detail::PinnedBatch &b = ring[i];
+            ++n_batches[(size_t)g];
+            std::string text;
+            bool failed;
+            { std::lock_guard<std::mutex> lk(mu); failed = !failure.empty(); }
+            try {
+                if(!failed) {
+                    views.resize(b.n);
+                    if(b.map)
+                        for(size_t r = 0; r < b.n; ++r) {
+                            const detail::RecRef &ref = b.refs[r];
+                            const char *mp = b.map_of(r);
+                            views[r] = detail::ReadView{mp + ref.name_off, b.bases + b.offs[r],
+                                                        b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
+                                                        (int)ref.seq_len, (int)ref.name_len};
+                        }
+                    else
+                        for(size_t r = 0; r < b.n; ++r)
+                            views[r] = detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
+                                                        (int)(b.offs[r + 1] - b.offs[r])};
+                    const double tc = now();
+                    detail::classify_views(c, b.bases, b.offs, views.data(), (unsigned)b.n, is_paired, text, h, fmt_threads);
+                    t_classify[(size_t)g] += now() - tc;
+                    if(sq == 0) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
+                }
+            } catch(const std::exception &e) { std::lock_guard<std::mutex> lk(mu); if(failure.empty()) failure = e.what(); }
+            { std::lock_guard<std::mutex> lk(wmu); wq[sq] = std::move(text); }
+            wcv.notify_all();
+            { std::lock_guard<std::mutex> lk(mu); state[i] = 0; }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> workers;
+    for(int g = 1; g < G; ++g) workers.emplace_back(work, g);
+    work(0);                                                               // GPU 0 on the caller's thread
+    for(auto &t : workers) t.join();
     reader.join();
-    if(failure.empty()) { try { flush(); } catch(const std::exception &e) { failure = e.what(); } }
-    { std::lock_guard<std::mutex> lk(wmu); wdone = true; }
+    { std::lock_guard<std::mutex> lk(wmu); w_end = end_seq; }
     wcv.notify_all();
     writer.join();
     if(!reader_error.empty()) BNS_RUNTIME_ERROR(reader_error);
@@ -1318,8 +1439,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
     if(verbose)
-        std::fprintf(stderr, "[process_dataset] %zu batches: waiting for the reader %.2f s, classify + format %.2f s, waiting for the writer %.2f s\n",
-                     n_batches, t_wait, t_classify, t_write);
+        for(int g = 0; g < G; ++g)
+            std::fprintf(stderr, "[process_dataset] gpu %d: %zu batches, waiting for the reader %.2f s, classify + format %.2f s\n",
+                         g, n_batches[(size_t)g], t_wait[(size_t)g], t_classify[(size_t)g]);
 }
 
 }  // namespace bns

@@ -16,6 +16,7 @@ const char *bns_b200_last_error(const bns_b200_t *) { return "stub"; }
 int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) { *out = new bns_b200_ctx; (*out)->k = cfg->k; (*out)->canon = cfg->canonicalize; (*out)->api = cfg->api; return 0; }
 void bns_b200_close(bns_b200_t *c) { delete c; }
 int bns_b200_load_table(bns_b200_t *, const uint64_t *, const uint32_t *, const uint32_t *, uint64_t) { return 0; }
+int bns_b200_replicate(bns_b200_t *const *, int, int) { return 0; }        // every dummy context already "holds" the database
 int bns_b200_load_taxonomy(bns_b200_t *, const uint32_t *, const uint32_t *, uint64_t) { return 0; }
 int bns_b200_stats_get(const bns_b200_t *c, bns_b200_stats *s) { memset(s, 0, sizeof *s); s->n_classified = c->ncls; s->n_unclassified = c->nun; return 0; }
 int bns_b200_host_alloc(void **p, size_t n) { *p = malloc(n); return *p ? 0 : -3; }

@@ -12,16 +12,17 @@ sys.path.insert(0, ROOT)
 
 def test_clock_sampler_reduction():
     import bench
-    cs = bench.ClockSampler(0)
-    assert cs.stop()["sm_mhz"] is None                       # never started: says so instead of inventing a clock
-    cs.proc = type("P", (), {"terminate": lambda s: None, "wait": lambda s, timeout=None: 0, "kill": lambda s: None})()
-    cs.rows = [["0", "1965", "1965", "350.1", "Not Active", "Not Active", "Not Active", "Active"],
-               ["0", "1950", "1965", "360.2", "Not Active", "Not Active", "Not Active", "Not Active"],
-               ["0", "1965", "1965", "[N/A]", "Not Active", "Not Active", "Not Active", "Not Active"],      # no power reading: the clocks still count
-               ["garbage"]]
-    r = cs.stop()
-    assert r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1965.0 and r["samples"] == 3
+    cs = bench.ClockSampler(0)                                # no device here: neither NVML nor nvidia-smi delivers a sample
+    cs.stop()
+    assert cs.window(0.0, 1e18)["sm_mhz"] is None and cs.window(0.0, 1e18)["samples"] == 0      # says so instead of inventing a clock
+    # (host time, SM MHz, max SM MHz, watts or None, NVML clocks-event-reasons bits): only samples inside the window count
+    cs.rows = [(9.0, 600.0, 1965.0, 90.0, 0x8),               # before the timed region (an idle clock and a slowdown that is not ours)
+               (10.0, 1965.0, 1965.0, 350.1, 0x4), (10.5, 1950.0, 1965.0, 360.2, 0x0), (11.0, 1965.0, 1965.0, None, 0x1),
+               (12.5, 800.0, 1965.0, 100.0, 0x40)]            # after it
+    r = cs.window(10.0, 11.0)
+    assert r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1965.0 and r["samples"] == 3 and r["inside_timed_region"]
     assert r["reasons"] == ["sw_power_cap"] and r["power_w_max"] == 360.2
+    assert cs.window(9.0, 12.5)["reasons"] == ["hw_slowdown", "hw_thermal_slowdown", "sw_power_cap"]
 
 
 def _check_reference_line(line, n_gpus):

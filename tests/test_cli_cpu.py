@@ -155,6 +155,12 @@ def test_cli_host_pipeline_ingest_kinds(tmp_path, cli):
         assert all(b"the 2nd file has fewer sequences" in x[2] for x in paired)
     fasta = [run(env, ["-a", "-f", "-k", "-p", "4", "-c", c], "s.fa" + ext) for env, ext, c in kinds]
     assert len({x[0] for x in fasta}) == 1 and fasta[0][1] == 9000 * 4
+    # --gpus N: the batches are dealt round-robin to N worker contexts and the text is reassembled in batch order
+    one = run({}, ["-a", "-p", "4", "-c", "50000"], "r1.fq", "r2.fq")
+    for g in ("2", "3", "5"):
+        many = run({}, ["-a", "-p", "4", "-c", "50000", "--gpus", g], "r1.fq", "r2.fq")
+        assert many[0] == one[0] and many[1] == one[1], g
+        assert many[2].split(b"classified")[-2:] == one[2].split(b"classified")[-2:]      # the counters add up over the contexts
 
 
 def test_cpp_encoder_surface_compiles(tmp_path):
