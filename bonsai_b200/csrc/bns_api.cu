@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include "../../include/bonsai_b200.h"
@@ -279,6 +280,11 @@ u32 choose_bits(u64 n_keys, u32 n_values) {
 
 // tables that will take the minimizer layout: entries per 32-byte bucket from BNS_B200_LOC_LOAD when set (experiments)
 u32 layout_bits(const bns_b200_ctx *ctx, u32 b, u64 n_keys) {
+    if(const char *f = getenv("BNS_B200_LAYOUT"))                     // forced: small tables grow until the slot format has room
+        if(!strcmp(f, "minimizer") && ctx->cfg.k >= 23 && ctx->cfg.k <= 31) {
+            const u32 vb = bits_for(std::max<u32>((u32)ctx->values.size(), 2));
+            while(b < 32 && (int)loc_fmt_bits(ctx->cfg.k, b) < (int)(vb + DISP_BITS_LOC + 1)) ++b;
+        }
     const char *e = getenv("BNS_B200_LOC_LOAD");
     if(!e || !want_minimizer_layout(ctx, b)) return b;
     const double v = atof(e);
@@ -1067,6 +1073,8 @@ struct NcclApi {
 NcclApi &nccl_api() {
     static NcclApi api = [] {
         NcclApi a;
+        // NCCL prints its warnings to stdout unless told otherwise: stdout is where `bonsai classify` writes its records
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         for(const char *name : {"libnccl.so.2", "libnccl.so"}) {
             a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
             if(a.lib) break;
@@ -1133,6 +1141,13 @@ int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
             return ctx->fail(rc, "replica %d: %s", i, handles[i]->err.c_str());
     NcclApi &nc = nccl_api();
     if(!nc.ok) return ctx->fail(BNS_E_CUDA, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+    // NCCL announces itself on stdout ("NCCL version ..."), which is where `bonsai classify` writes its records: while NCCL
+    // runs, file descriptor 1 is the process's stderr
+    struct StdoutGuard {
+        int saved;
+        StdoutGuard() { fflush(stdout); saved = dup(1); if(saved >= 0) dup2(2, 1); }
+        ~StdoutGuard() { if(saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); } }
+    } stdout_guard;
     std::vector<ncclComm_t> comms((size_t)n, nullptr);
     std::vector<int> devs((size_t)n);
     for(int i = 0; i < n; ++i) devs[(size_t)i] = handles[i]->device;
@@ -1344,8 +1359,9 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
 }
 
 // classify_seqs with the hit lists run-length encoded on the device. Chunks are pipelined over the stream slots like
-// classify_batch_ex; a chunk's runs are fetched (their count is only known once its kernels are done) while the next chunk's
-// copies and kernels are already queued.
+// classify_batch_ex; a chunk's runs are fetched (their count is only known once its kernel is done) while the next chunk's
+// copies and kernels are already queued. What `bonsai classify` runs (every k-mer, no window) produces the runs in the lean
+// kernel itself; the other encoders go through the ordered hit list of the generic kernel and bns_rle_kernel.
 int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
                                  uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,
@@ -1361,9 +1377,18 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
     if(!n_rec_total) return BNS_OK;
     CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
     CK(cudaStreamSynchronize(ctx->slots[0].st));
+    // a call that fails for want of room in runs_out must leave classified_[] as it found them (the caller calls again)
+    unsigned long long counters0[2];
+    CK(cudaMemcpy(counters0, ctx->d_counters, sizeof counters0, cudaMemcpyDeviceToHost));
     struct Pending { bool live = false; u64 q0 = 0, nq = 0; } pend[N_SLOTS];
     u64 used = 0;
     std::vector<u64> h_toffs;
+    auto no_room = [&](u64 need) -> int {
+        for(int i = 0; i < N_SLOTS; ++i) cudaStreamSynchronize(ctx->slots[i].st);
+        cudaMemcpy(ctx->d_counters, counters0, sizeof counters0, cudaMemcpyHostToDevice);
+        *n_runs_total_out = need;                                          // a lower bound on what the call needs
+        return ctx->fail(BNS_E_CAPACITY, "the run buffer holds %llu entries, at least %llu are needed", (unsigned long long)runs_cap, (unsigned long long)need);
+    };
     // fetch the runs of the chunk a slot holds: count first, then exactly that many entries
     auto finalize = [&](int si) -> int {
         Pending &pd = pend[si];
@@ -1373,7 +1398,7 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
         unsigned long long total = 0;
         CK(cudaMemcpyAsync(&total, s.d_defer_cnt, sizeof total, cudaMemcpyDeviceToHost, s.st));
         CK(cudaStreamSynchronize(s.st));
-        if(used + total > runs_cap) return ctx->fail(BNS_E_CAPACITY, "the run buffer holds %llu entries, more were produced", (unsigned long long)runs_cap);
+        if(used + total > runs_cap) return no_room(used + total);
         if(total) CK(cudaMemcpyAsync(runs_out + used, s.d_runs, total * 8, cudaMemcpyDeviceToHost, s.st));
         CK(cudaMemcpyAsync(run_pos_out + pd.q0, s.d_run_pos, pd.nq * 8, cudaMemcpyDeviceToHost, s.st));
         CK(cudaMemcpyAsync(n_runs_out + pd.q0, s.d_nruns, pd.nq * 4, cudaMemcpyDeviceToHost, s.st));
@@ -1395,38 +1420,50 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
         if(rc != BNS_OK) return rc;
         Slot &s = ctx->slots[slot_i];
         CK(cudaStreamSynchronize(s.st));
-        // hit-list windows of the chunk on the device: one slot per k-mer position plus two, like the reference's vector
-        h_toffs.resize(nq + 1);
-        h_toffs[0] = 0;
-        for(u64 q = 0; q < nq; ++q) h_toffs[q + 1] = h_toffs[q] + (offsets[(q0 + q + 1) * mates] - offsets[(q0 + q) * mates]) + 2;
-        const u64 nt = h_toffs[nq];
+        ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, true, mate1_kmers_out != nullptr, true, true);
+        // one run-buffer entry per k-mer position plus two per record bounds the hits, as the reference's vector does
+        const u64 nt = nb + 2 * nq;
         rc = ensure(s.d_bases, s.cap_bases, nb + 16);
         if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
         if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 4 * nq);
-        if(rc == BNS_OK) rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
-        if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
-        if(rc == BNS_OK) rc = ensure(s.d_runs, s.cap_runs, nt + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_runs, s.cap_runs, nt + 1 + runs_slack(pl));
         if(rc == BNS_OK) rc = ensure(s.d_run_pos, s.cap_run_pos, nq);
         if(rc == BNS_OK) rc = ensure(s.d_nruns, s.cap_nruns, nq);
+        if(rc == BNS_OK && !pl.runs) {
+            rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
+            if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
+        }
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
-        const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, true, mate1_kmers_out != nullptr, true);
+        if(pl.runs && nb % nr == 0 && nb / nr < 0xffffffffull) {              // fixed-length batch: offsets stay on the host
+            const u64 flen = nb / nr;
+            bool fixed = flen > 0;
+            for(u64 r = r0; fixed && r < r1; ++r) fixed = offsets[r + 1] - offsets[r] == flen;
+            if(fixed) { pl.fixed_len = (u32)flen; pl.fixed_base = offsets[r0]; }
+        }
         CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));     // the run counter of this chunk
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
-        CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        CK(cudaMemcpyAsync(s.d_taxa_offsets, h_toffs.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        CK(cudaStreamSynchronize(s.st));                                   // h_toffs is reused by the next chunk
+        if(!pl.fixed_len) CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        if(!pl.runs) {
+            // hit-list windows of the chunk on the device: one slot per k-mer position plus two
+            h_toffs.resize(nq + 1);
+            h_toffs[0] = 0;
+            for(u64 q = 0; q < nq; ++q) h_toffs[q + 1] = h_toffs[q] + (offsets[(q0 + q + 1) * mates] - offsets[(q0 + q) * mates]) + 2;
+            CK(cudaMemcpyAsync(s.d_taxa_offsets, h_toffs.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
+            CK(cudaStreamSynchronize(s.st));                               // h_toffs is reused by the next chunk
+        }
         int nl = 1;
+        const RunsOut ro{s.d_runs, s.cap_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns};
         CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
-                           table_view(ctx), tax_view(ctx), s.d_out, s.d_out + nq, s.d_out + 2 * nq, s.d_taxa, s.d_taxa_offsets,
-                           mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status,
-                           nullptr, nullptr, &nl));
-        CK(launch_rle(s.st, s.d_taxa, s.d_taxa_offsets, s.d_out + nq, nq, s.d_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns));
-        ctx->stats.kernel_launches += nl + 1;
+                           table_view(ctx), tax_view(ctx), s.d_out, s.d_out + nq, s.d_out + 2 * nq, pl.runs ? nullptr : s.d_taxa,
+                           pl.runs ? nullptr : s.d_taxa_offsets, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap, ctx->d_counters,
+                           ctx->d_status, nullptr, nullptr, &nl, &ro));
+        if(!pl.runs) { CK(launch_rle(s.st, s.d_taxa, s.d_taxa_offsets, s.d_out + nq, nq, s.d_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns)); ++nl; }
+        ctx->stats.kernel_launches += nl;
         CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
         CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(mate1_kmers_out) CK(cudaMemcpyAsync(mate1_kmers_out + q0, s.d_out + 3 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
-        ctx->stats.h2d_bytes += nb + 8 * (nr + 1) + 8 * (nq + 1);
+        ctx->stats.h2d_bytes += nb + (pl.fixed_len ? 0 : 8 * (nr + 1)) + (pl.runs ? 0 : 8 * (nq + 1));
         ctx->stats.d2h_bytes += nq * 4 * (2 + (n_missing_out != nullptr) + (mate1_kmers_out != nullptr));
         ctx->stats.reads_processed += nr;
         ctx->stats.bases_processed += nb;
@@ -1441,7 +1478,7 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
     *n_runs_total_out = used;
     u32 status = 0;
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
-    return check_status(ctx, status & 10u);
+    return check_status(ctx, status & 11u);
 }
 
 int bns_b200_sync(bns_b200_t *ctx) {

@@ -25,6 +25,8 @@ namespace bns {
 
 constexpr int RB = 32;                       // records per warp batch
 constexpr int LEAN_STAGE_BYTES = 2 * (RB + 2) * 8 + 2 * 32 * 8;      // per warp: offsets ring + first-tile ring
+constexpr int RUNBUF = 128;                  // run-list variants: runs of one record buffered per warp before they are placed
+constexpr u32 RUN_BLOCK = 256;               // ... into stretches of the chunk's run buffer a warp reserves with one atomic each
 #ifndef BNS_LEAN_WARPS
 #define BNS_LEAN_WARPS 8
 #endif
@@ -218,13 +220,18 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
 // KEY (windowed modes): how a window element is ordered -- LEAN_KEY_PAIR (score, k-mer) in full, LEAN_KEY_LEX the Lex score
 // alone, LEAN_KEY_ELEM the k-mer alone (scores non-decreasing in the k-mer); chosen by pick_lean().
 // LOC: the table is in LAYOUT_MINIMIZER (bns_device.cuh): bucket and remainder come from loc_encode instead of mix64.
-template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC>
+// RUNS: the ordered hit list of every record leaves run-length encoded (what the Kraken-style text prints, classifier.h:46-61):
+// (taxid << 32 | run length) words at runs_out[run_pos_out[r] .. + n_runs_out[r]). A record's runs are gathered in shared
+// memory and placed into a stretch of runs_out the warp reserved with one atomic per RUN_BLOCK entries (runs_total = entries
+// handed out so far, gaps included).
+template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC, bool RUNS>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
                       u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status,
                       u32 *__restrict__ defer_idx, unsigned long long *__restrict__ defer_cnt, u32 fixed_len, u64 fixed_base,
-                      u32 mates, u32 *__restrict__ mate1_out) {
+                      u32 mates, u32 *__restrict__ mate1_out, u64 *__restrict__ runs_out, u64 runs_cap,
+                      unsigned long long *__restrict__ runs_total, u64 *__restrict__ run_pos_out, u32 *__restrict__ n_runs_out) {
     // n_records counts SEQUENCES here: a record is `mates` (1 or 2) consecutive sequences sharing one taxon counter
     // (classify_seq encodes the second mate into the same counter, classifier.h:233-236); a batch of 32 sequences holds
     // whole records. mate1_out: k-mers the first mate produced (classifier.h:232's first ambig_count term).
@@ -271,6 +278,27 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     //   s_rd[2][32]     8 bytes per lane of the first tile of the current / next record
     u64 *s_off = (u64 *)(g_smem + (size_t)LEAN_WARPS * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
     uint2 *s_rd = (uint2 *)(s_off + 2 * (RB + 2));
+    // run lists: this warp's record buffer, its reserved stretch of runs_out, and the run that is still open
+    u64 *s_run = (u64 *)(g_smem + (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES) + (size_t)wid * RUNBUF * sizeof(u64));
+    u64 blk_pos = 0;
+    u32 blk_left = 0, run_val = VAL_MISS, run_len = 0, n_runs_rec = 0;
+    bool run_direct = false;                                          // this record's runs go straight to runs_out[blk_pos ...]
+    u64 my_rpos = 0; u32 my_nruns = 0;
+    auto put_run = [&](u32 widx, u32 val, u32 len) {                   // run number widx of the current record
+        const u64 e = ((u64)sink.vi[val].w << 32) | len;
+        if(!run_direct) s_run[widx] = e;
+        else if(blk_pos + widx < runs_cap) runs_out[blk_pos + widx] = e;
+    };
+    auto reserve_runs = [&](u32 need) {                                // make the warp's stretch hold `need` more entries
+        if(need > blk_left) {
+            const u32 take = max(need, RUN_BLOCK);
+            unsigned long long base = 0;
+            if(lane == 0) base = atomicAdd(runs_total, (unsigned long long)take);
+            blk_pos = __shfl_sync(FULL, base, 0);
+            blk_left = take;
+            if(blk_pos + take > runs_cap && lane == 0) atomicOr(status, 1u);
+        }
+    };
     s_rd[lane] = make_uint2(0x41414141u, 0x41414141u);                 // lanes past a tile read 'A's: code 0, never "suspicious"
     s_rd[32 + lane] = make_uint2(0x41414141u, 0x41414141u);
     __syncwarp();
@@ -355,6 +383,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             fetch_tile(xb, xl, tb ^ 1);
             async_commit();
             if(first_mate) { nd = 0; id0 = 0; cnt0 = 0; n_hit = 0; n_emit = 0; deferred = false; }
+            if(RUNS && first_mate) { run_val = VAL_MISS; run_len = 0; n_runs_rec = 0; run_direct = false; }
             if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
             else if(deferred) {}                                       // the first mate already sent the record to the generic kernel
             else if((MODE == LEAN_K || MODE == LEAN_R) && L >= k && L - k + 1 > (u32)TILE) deferred = true;   // more than one tile of window elements
@@ -676,6 +705,62 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         if(COUNTS) n_hit += __reduce_add_sync(FULL, __popc(todo));
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) cand[i] &= Pc.val_mask;
+                        if(RUNS) {
+                            // The tile's hits in k-mer order (lane-major). A hit starts a run when no hit precedes it in the record
+                            // or its value differs from the previous hit's; every start closes the run before it.
+                            u32 firstv = VAL_MISS, prevv = VAL_MISS, inner = 0;
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i)
+                                if(todo >> i & 1u) {
+                                    if(prevv == VAL_MISS) firstv = cand[i]; else if(cand[i] != prevv) inner |= 1u << i;
+                                    prevv = cand[i];
+                                }
+                            const u32 lower = bal & ((1u << lane) - 1);                    // lanes before this one that hold hits
+                            u32 pv = __shfl_sync(FULL, prevv, (31 - __clz(lower)) & 31);   // value of the last hit before this lane
+                            if(lower == 0) pv = run_val;
+                            u32 starts = inner;
+                            if(todo && (pv == VAL_MISS || firstv != pv)) starts |= todo & (0u - todo);
+                            const u32 m = __popc(todo), ns = __popc(starts);
+                            u32 tot;
+                            const u32 ex = warp_excl_scan(m | (ns << 16), lane, tot);
+                            const u32 hbase = ex & 0xffffu, sbase = ex >> 16, H = tot & 0xffffu, SX = tot >> 16;
+                            const bool carry = run_val != VAL_MISS;
+                            // more runs than the record buffer holds (long reads): from here on straight into a reserved stretch
+                            if(!run_direct && n_runs_rec + SX + 1 > (u32)RUNBUF) {
+                                const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
+                                reserve_runs(n_runs_rec + rest);
+                                for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                                run_direct = true;
+                            }
+                            u32 last_idx = 0, last_val = 0;                               // this lane's last start
+                            {
+                                u32 rank = 0;
+#pragma unroll
+                                for(int i = 0; i < PPL; ++i)
+                                    if(todo >> i & 1u) { if(starts >> i & 1u) { last_idx = hbase + rank; last_val = cand[i]; } ++rank; }
+                            }
+                            const u32 sl = __ballot_sync(FULL, ns != 0), slower = sl & ((1u << lane) - 1);
+                            int open_start = (int)__shfl_sync(FULL, last_idx, (31 - __clz(slower)) & 31);   // where the run open before this lane began
+                            if(slower == 0) open_start = -(int)run_len;
+                            u32 open_val = pv, rank = 0, srank = 0;
+#pragma unroll
+                            for(int i = 0; i < PPL; ++i)
+                                if(todo >> i & 1u) {
+                                    if(starts >> i & 1u) {
+                                        const u32 t = sbase + srank;                      // the t-th start of the tile
+                                        if(carry || t > 0) put_run(n_runs_rec + t - (carry ? 0u : 1u), open_val, (u32)((int)(hbase + rank) - open_start));
+                                        open_val = cand[i]; open_start = (int)(hbase + rank); ++srank;
+                                    }
+                                    ++rank;
+                                }
+                            if(SX) {
+                                const u32 top = 31 - __clz(sl);
+                                run_val = __shfl_sync(FULL, last_val, top);
+                                run_len = H - __shfl_sync(FULL, last_idx, top);
+                                n_runs_rec += SX - (carry ? 0u : 1u);
+                            } else run_len += H;
+                            __syncwarp();
+                        }
                         do {
                             const u32 leader = __ffs(bal) - 1;
                             u32 fv = cand[3];
@@ -722,6 +807,26 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
             if(lane == (j >> msh)) { my_taxon = taxon; my_def = deferred; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; if(msh == 0) my_m1 = n_emit; } }
+            if(RUNS) {
+                // the run still open ends with the record; then the record's runs take their place in the warp's stretch
+                if(run_val != VAL_MISS) {
+                    if(!run_direct && n_runs_rec + 1 > (u32)RUNBUF) {
+                        reserve_runs(n_runs_rec + 1);
+                        for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                        run_direct = true;
+                    }
+                    if(lane == 0) put_run(n_runs_rec, run_val, run_len);
+                    ++n_runs_rec;
+                    __syncwarp();
+                }
+                if(!run_direct) {
+                    reserve_runs(n_runs_rec);
+                    for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                    __syncwarp();
+                }
+                if(lane == (j >> msh)) { my_rpos = blk_pos; my_nruns = n_runs_rec; }
+                blk_pos += n_runs_rec; blk_left -= n_runs_rec;
+            }
             spilled = false;
             rb = xb; L = xl; tb ^= 1;
         }
@@ -735,6 +840,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                 if(nmiss_out) nmiss_out[o0 + lane] = my_miss;
                 if(mate1_out) mate1_out[o0 + lane] = my_m1;
             }
+            if(RUNS) { run_pos_out[o0 + lane] = my_rpos; n_runs_out[o0 + lane] = my_nruns; }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nout && my_taxon != 0));
         const u32 ndef = (MODE == LEAN_U || MODE == LEAN_S) ? 0u : __popc(__ballot_sync(FULL, lane < nout && my_def != 0));

@@ -1146,12 +1146,15 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
     return -1;
 }
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                              unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64, u32, u32 *);
-static size_t lean_smem() { return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES); }
-template <int MODE, bool CANON, bool COUNTS, int KEY>
+                              unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64, u32, u32 *,
+                              u64 *, u64, unsigned long long *, u64 *, u32 *);
+static size_t lean_smem(bool runs) {
+    return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES + (runs ? RUNBUF * sizeof(u64) : 0));
+}
+template <int MODE, bool CANON, bool COUNTS, int KEY, bool RUNS = false>
 static classify_u_fn pick_lean_k(u32 k, bool loc) {
-    if(loc) return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, true> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, true>;
-    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, false> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, false>;
+    if(loc) return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, true, RUNS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, true, RUNS>;
+    return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, false, RUNS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, false, RUNS>;
 }
 template <int MODE, bool CANON>
 static classify_u_fn pick_lean_key(u32 k, int key, bool loc) {
@@ -1170,26 +1173,31 @@ static int lean_key(const EncParams &P) {
     if(!P.cast_wrap && (P.score_kind == SC_ENT_NOTFULL || (P.score_kind == SC_ENT_ROLL && P.k >= 28))) return LEAN_KEY_ELEM;
     return LEAN_KEY_PAIR;
 }
-static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc) {
+static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false) {
     if(mode == LEAN_S) return pick_lean_k<LEAN_S, false, true, 0>(P.k, loc);
     if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P), loc);
     if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P), loc) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P), loc);
+    if(runs) return P.canon_elem ? pick_lean_k<LEAN_U, true, true, 0, true>(P.k, loc) : pick_lean_k<LEAN_U, false, true, 0, true>(P.k, loc);
     if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc);
     return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, false, false, 0>(P.k, loc);
 }
 
-ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts) {
+ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts, bool runs) {
     ClassifyPlan pl;
-    pl.lean_mode = lean_mode(P, mates, taxa, mate1);
+    // run lists come out of the lean kernel for what `bonsai classify` runs (every k-mer, no window); the other encoders keep the
+    // ordered hit list of the generic kernel, run-length encoded by bns_rle_kernel
+    pl.lean_mode = lean_mode(P, mates, taxa && !runs, mate1);
+    if(runs && pl.lean_mode != LEAN_U) pl.lean_mode = lean_mode(P, mates, true, mate1);
     // the lean kernel spells LAYOUT_MINIMIZER keys as k-mers of ITS k: a table of another k goes through the generic probe
     pl.loc = T.fmt.layout == LAYOUT_MINIMIZER;
     if(pl.loc && T.fmt.kt != P.k) pl.lean_mode = -1;
     pl.lean = pl.lean_mode >= 0;
-    pl.counts = counts || mates == 2 || mate1;                        // the pair bookkeeping lives in the COUNTS variants
+    pl.runs = runs && pl.lean_mode == LEAN_U;
+    pl.counts = counts || mates == 2 || mate1 || runs;                // the pair bookkeeping lives in the COUNTS variants
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
-        pl.smem = lean_smem();
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs);
+        pl.smem = lean_smem(pl.runs);
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, LEAN_WARPS * 32, pl.smem);
@@ -1215,12 +1223,14 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
-                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched) {
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro) {
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs);
         f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,
-                                                    counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base, mates, mate1_out);
+                                                    counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base, mates, mate1_out,
+                                                    pl.runs ? ro->runs : nullptr, pl.runs ? ro->cap : 0, pl.runs ? ro->total : nullptr,
+                                                    pl.runs ? ro->run_pos : nullptr, pl.runs ? ro->n_runs : nullptr);
         cudaError_t e = cudaGetLastError();
         if(e != cudaSuccess || pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) return e;
         // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel
@@ -1238,6 +1248,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                                                     nullptr, nullptr);
     return cudaGetLastError();
 }
+u64 runs_slack(const ClassifyPlan &pl) { return pl.runs ? (u64)pl.grid * LEAN_WARPS * RUN_BLOCK : 0; }
 int encode_occupancy(const EncParams &P, size_t smem) {
     int nb = 0;
     encode_fn f = pick_encode(P.family);

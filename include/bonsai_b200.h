@@ -189,8 +189,11 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
                                uint32_t *taxa_out, const uint64_t *taxa_offsets, uint32_t *mate1_kmers_out);
 /* The ordered hit list run-length encoded on the device (what the Kraken-style run lists print, classifier.h:46-61):
  * record r's runs are runs_out[run_pos_out[r] .. + n_runs_out[r]), each (taxid << 32 | run length), in k-mer order.
- * runs_cap entries are available in runs_out (BNS_E_CAPACITY if more were produced: the number of hits is an upper
- * bound); *n_runs_total_out receives the number written. 8 bytes per run cross PCIe instead of 4 per window slot. */
+ * runs_cap entries are available in runs_out; *n_runs_total_out receives the entries used (the runs of a chunk may leave
+ * small unused stretches between records; every record's runs are contiguous at run_pos_out[r]). BNS_E_CAPACITY if the runs
+ * do not fit: nothing is counted (classified / unclassified stay as they were), *n_runs_total_out holds a lower bound on the
+ * entries needed, and the call can be repeated with a larger buffer (bases + 2 entries per record + 2^21 always suffice).
+ * 8 bytes per run cross PCIe instead of 4 per window slot. */
 int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
                                  uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,

@@ -549,6 +549,7 @@ struct ClassifierGeneric {
     std::vector<std::shared_ptr<detail::Handle>> replicas_;      // contexts on GPUs 1 .. n-1 holding a copy of the database (set_gpus)
     int n_gpus_ = 1;
     bool tax_loaded_ = false;
+    std::atomic<u32> runs_per_record_hint_{4};                   // run-buffer entries per record the batches so far needed (classify_views)
     void set_emit_all(bool s) { if(s) output_flag_ |= EMIT_ALL; else output_flag_ &= ~EMIT_ALL; }
     void set_emit_kraken(bool s) { if(s) output_flag_ |= KRAKEN; else output_flag_ &= ~KRAKEN; }
     void set_emit_fastq(bool s) { if(s) output_flag_ |= FASTQ; else output_flag_ &= ~FASTQ; }
@@ -698,18 +699,23 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     std::unique_ptr<u64[]> runs;
     if(need_taxa) {
         // run lists: encoded on the device, 8 bytes per run back instead of 4 per k-mer window slot. The number of runs is
-        // not known beforehand: a buffer for a few runs per record first, one for every possible hit if that was too small.
+        // not known beforehand: the buffer is sized from what earlier batches of this classifier needed (entries per record,
+        // carried in the classifier), and a call that does not fit reports how much it needs and has counted nothing.
         u64 windows = 0;
         for(unsigned r = 0; r < nrec; ++r) windows += (offs[(r + 1) * inc] - offs[r * inc]) + 2;
-        u64 cap = std::min<u64>(windows, (u64)nrec * 8 + 4096), total = 0;
+        const u64 bound = windows + ((u64)1 << 21);                       // always enough (bonsai_b200.h)
+        u64 cap = std::min<u64>(bound, (u64)nrec * c.runs_per_record_hint_.load() + ((u64)1 << 20)), total = 0;
         for(;;) {
             runs.reset(new u64[cap ? cap : 1]);
             const int rc = bns_b200_classify_batch_runs(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
                                                         is_paired ? mate1.data() : nullptr, runs.get(), cap, run_pos.data(), nruns.data(), &total);
-            if(rc == BNS_E_CAPACITY && cap < windows) { cap = windows; continue; }
+            if(rc == BNS_E_CAPACITY && cap < bound) { cap = std::min<u64>(bound, std::max<u64>(cap * 2, total + total / 2)); continue; }
             check(h, rc, "bns_b200_classify_batch_runs");
             break;
         }
+        const u32 per = (u32)std::min<u64>(1u << 20, total / nrec + 2);
+        u32 seen = c.runs_per_record_hint_.load();
+        while(per > seen && !c.runs_per_record_hint_.compare_exchange_weak(seen, per)) {}
     } else
         check(h, bns_b200_classify_batch_ex(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
                                             nullptr, nullptr, is_paired ? mate1.data() : nullptr), "bns_b200_classify_batch");

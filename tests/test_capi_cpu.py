@@ -73,3 +73,12 @@ def test_value_dictionary_host_code(tmp_path):
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 9, r.stdout
+
+
+def test_bns_repack_layout():
+    """repack (python/bns.cpp:130-150): list entry `kind` lands at flat positions kind * pairs + [0, pairs) of a (pairs, len) array"""
+    import numpy as np
+    from bonsai_b200 import bns
+    r = bns.repack([np.arange(3, dtype=np.float32), 10 + np.arange(3, dtype=np.float32)], 3)
+    assert r.shape == (3, 2) and r.dtype == np.float32
+    assert r.reshape(-1).tolist() == [0, 1, 2, 10, 11, 12]

@@ -251,6 +251,56 @@ def test_classify_runs_match_hit_lists(capi, golden, gpu_dbs, reads2000):
         ctx.classify_runs(bases, offs, cap=10)
 
 
+def _rle(lst):
+    if lst.size == 0:
+        return np.zeros((0, 2), np.uint32)
+    starts = np.concatenate([[0], np.flatnonzero(np.diff(lst.astype(np.int64)) != 0) + 1])
+    lens = np.diff(np.concatenate([starts, [lst.size]]))
+    return np.stack([lst[starts], lens.astype(np.uint32)], axis=1)
+
+
+@pytest.mark.parametrize("layout", ["hash", "minimizer"])
+def test_classify_runs_long_records_many_runs(capi, oracle, toy_tax, genomes, monkeypatch, layout):
+    """Run lists out of the lean kernel where one record holds far more runs than its per-warp buffer (k-mers of a 6 kb
+    stretch valued 11 / 12 / 13 by position, so nearly every hit starts a run), runs that continue across tiles and across
+    the mates of a pair, records without hits and empty records between them -- against the oracle's ordered hit lists."""
+    monkeypatch.setenv("BNS_B200_LAYOUT", layout)
+    b, _ = H.genome_records(genomes, 0)
+    region = b[10_000:16_000]
+    lut = np.zeros(256, np.uint64)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    c = lut[region]
+    n = c.size - 30
+    f = np.zeros(n, np.uint64); r = np.zeros(n, np.uint64)
+    for j in range(31):
+        f = (f << np.uint64(2)) | c[j:j + n]
+        r = r | ((np.uint64(3) - c[j:j + n]) << np.uint64(2 * j))
+    km = np.minimum(f, r)
+    keys, first = np.unique(km, return_index=True)
+    pos = first                                               # value by the position of the k-mer's first occurrence
+    vals = np.where(pos % 7 < 3, 11, np.where(pos % 7 < 5, 12, 13)).astype(np.uint32)
+    vals[(pos // 400) % 3 == 1] = 12                          # and stretches of equal values: long runs across tile borders
+    dbo = oracle.db_from_pairs(keys, vals)
+    rng = np.random.default_rng(5)
+    reads = [bytes(region), b"", bytes(region[100:250]), bytes(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 300)]),
+             bytes(region[2000:2900]), bytes(region[3000:3100]), bytes(region[:31]), bytes(region[5:35])]
+    reads += [bytes(region[s:s + int(l)]) for s, l in zip(rng.integers(0, 5000, 200), rng.integers(0, 700, 200))]
+    bases, offs = po.pack_reads(reads)
+    tc, tp = H.toy_tax_arrays()
+    with capi.Context(31, 31) as ctx:
+        ctx.load_pairs(keys, vals)
+        ctx.load_taxonomy(tc, tp)
+        assert ctx.table_info()["layout"] == (1 if layout == "minimizer" else 0)
+        for paired in (False, True):
+            et, eh, em, lists = oracle.classify(dbo, toy_tax, bases, offs, 31, 31, paired=paired, want_taxa=True)
+            t, h, m, runs = ctx.classify_runs(bases, offs, paired=paired)
+            assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
+            assert max(len(x) for x in runs) > 1000            # the long record really overflows the per-warp buffer
+            for lst, rn in zip(lists, runs):
+                assert np.array_equal(rn, _rle(lst))
+
+
 def test_classify_phix_and_paired(capi, golden, gpu_dbs, reads2000, genomes):
     ctx = gpu_dbs("config1_lex_w31")
     pb, poff = po.pack_reads([bytes(genomes["phix"])])
@@ -398,6 +448,14 @@ def test_bns_python_surface(capi, oracle, genomes, tmp_path):
     assert len(lists) == 2 and all(np.array_equal(a, b) for a, b in zip(lists, exp))
     assert np.array_equal(bns.from_fasta(str(p), 31, unique=True), np.unique(np.concatenate(
         [oracle.encode(x, 31, 31, None, 0, True, po.API_PATH) for x in (s[:300], s[300:650])])))
+    # seqdict (python/bns.cpp:175-199): the reference maps every record name to the k-mers of the whole file; per_record=True
+    # gives each its own
+    whole = np.concatenate([oracle.encode(x, 31, 31, None, 0, True, po.API_PATH) for x in (s[:300], s[300:650])])
+    d = bns.seqdict(str(p), 31)
+    assert list(d) == ["a", "b"] and all(np.array_equal(v, whole) for v in d.values())
+    d = bns.seqdict(str(p), 31, per_record=True)
+    assert np.array_equal(d["a"], oracle.encode(s[:300], 31, 31, None, 0, True, po.API_PATH))
+    assert np.array_equal(d["b"], oracle.encode(s[300:650], 31, 31, None, 0, True, po.API_PATH))
 
 
 @pytest.mark.parametrize("name", ["lex_k31_w31", "ent_k31_w50", "spaced_k31_c40"])

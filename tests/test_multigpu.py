@@ -89,7 +89,7 @@ def test_cli_gpus_matches_single(tmp_path, oracle, genomes):
                            capture_output=True)
         assert r.returncode == 0, r.stderr.decode()
         outs[g] = (r.stdout, r.stderr.decode().strip().splitlines()[-1])
-    assert outs[1][0] == outs[2][0] and outs[1][0].count(b"\n") == 30000
+    assert outs[1][0] == outs[2][0] and outs[1][0].count(b"\n") == 30000, (outs[2][0][:400], outs[2][1])
     assert outs[1][1] == outs[2][1]                       # "classified N, unclassified M" adds up over the GPUs
 
 
