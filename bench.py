@@ -407,7 +407,7 @@ def h2d_ceiling(env, nbytes=1 << 30, reps=6):
     return env.world * nbytes * reps / (ms * 1e-3) / 1e9
 
 
-def run_workload(env, name, n, steps, warmup, e2e_steps, n_check, with_cpu_baseline):
+def run_workload(env, name, n, steps, warmup, e2e_steps, n_check, with_cpu_baseline, with_runs=False):
     """One workload end to end: database (built on rank 0, replicated), reads, device-timed steps, e2e steps, roofline, oracle
     check. Returns the record (meaningful on rank 0; collectives are entered by every rank)."""
     torch, dist, capi, W, args = env.torch, env.dist, env.capi, env.W, env.args
@@ -528,6 +528,41 @@ def run_workload(env, name, n, steps, warmup, e2e_steps, n_check, with_cpu_basel
                "d2h_bytes_per_step": int(d2h_step), "steps": e2e_steps,
                "h2d_gbs": world * h2d_step * e2e_steps / e2e_s / 1e9,
                "taxids_match_device_path": bool(np.array_equal(h_taxon.numpy().astype(np.uint32), taxon_dev))}
+        # the same call with Kraken run lists (bns_b200_classify_batch_runs: runs produced by the lean kernel itself)
+        if with_runs:
+            import ctypes as C
+            nr = min(n, 4_000_000)
+            h_hit = torch.empty(nr, dtype=torch.int32, pin_memory=True)
+            h_pos = torch.empty(nr, dtype=torch.int64, pin_memory=True)
+            h_nruns = torch.empty(nr, dtype=torch.int32, pin_memory=True)
+            cap = nr * 24 + (1 << 21)
+            h_runs = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+            total = C.c_uint64(0)
+
+            def step_runs():
+                ctx._ck(ctx.lib.bns_b200_classify_batch_runs(ctx.h, h_bases.data_ptr(), h_offs.data_ptr(), nr, 0, h_taxon.data_ptr(), h_hit.data_ptr(),
+                                                             None, None, h_runs.data_ptr(), cap, h_pos.data_ptr(), h_nruns.data_ptr(), C.byref(total)))
+            try:
+                step_runs()
+                env.barrier()
+                s0 = ctx.stats()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    step_runs()
+                dt = env.max_over_ranks(time.perf_counter() - t0)
+                s1 = ctx.stats()
+                pos, cnt, rr = h_pos.numpy(), h_nruns.numpy(), h_runs.numpy()
+                # spot check: the taxids agree with the device path and sampled records' run lengths add up to their hit counts
+                ok = bool(np.array_equal(h_taxon.numpy()[:nr].astype(np.uint32), taxon_dev[:nr]))
+                sample = range(0, nr, max(1, nr // 5000))
+                ok = ok and all(int((rr[pos[i]:pos[i] + cnt[i]] & 0xffffffff).sum()) == int(h_hit[i]) for i in sample)
+                e2e["runs"] = {"e2e_mreads_s": world * nr * 3 / dt / 1e6, "reads_per_step": nr,
+                               "device_mreads_s": world * nr * 3 / ((s1["kernel_ms_total"] - s0["kernel_ms_total"]) * 1e-3) / 1e6,
+                               "runs_per_read": float(cnt.sum()) / nr, "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) // 3),
+                               "consistent_with_taxon_path": ok}
+            except capi.BnsError as ex:
+                e2e["runs"] = {"error": str(ex)}
+            del h_hit, h_pos, h_nruns, h_runs
         del h_bases, h_offs, h_taxon
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
@@ -642,7 +677,7 @@ def main():
     env = Env(args)
     main_rec = run_workload(env, args.workload, args.reads, args.steps, args.warmup, args.e2e_steps,
                             0 if not args.no_cpu_baseline and args.workload != "stress" and env.world == 1 else args.check_reads,
-                            with_cpu_baseline=not args.no_cpu_baseline)
+                            with_cpu_baseline=not args.no_cpu_baseline, with_runs=args.workload != "stress")
     ceiling = h2d_ceiling(env)
     subs = {}
     if args.workload == "config2" and not args.no_sub:

@@ -26,7 +26,7 @@ SYMBOLS = [
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
     "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_batch_runs", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
-    "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi",
+    "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi", "bns_b200_device_status",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library(path=None):
     lib.bns_b200_classify_batch_runs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.POINTER(C.c_uint64)]
     lib.bns_b200_classify_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.bns_b200_sync.argtypes = [vp]
+    lib.bns_b200_device_status.argtypes = [vp]
     lib.bns_b200_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.bns_b200_stats_reset.argtypes = [vp]
     lib.bns_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -372,6 +373,10 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.bns_b200_sync(self.h))
+
+    def device_status(self):
+        """raises what the asynchronous device-pointer calls latched (bns_b200_device_status)"""
+        self._ck(self.lib.bns_b200_device_status(self.h))
 
     def stats(self):
         s = Stats()

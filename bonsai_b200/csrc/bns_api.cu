@@ -44,7 +44,9 @@ struct Slot {
     u64 *d_runs = nullptr;         size_t cap_runs = 0;      // run-length encoded hit lists (classify_batch_runs)
     u64 *d_run_pos = nullptr;      size_t cap_run_pos = 0;
     u32 *d_nruns = nullptr;        size_t cap_nruns = 0;
-    unsigned long long *d_defer_cnt = nullptr;
+    unsigned long long *d_defer_cnt = nullptr;                // [0] records left to the second pass  [1] run-buffer entries handed out
+    cudaEvent_t ka = nullptr, kb = nullptr;                   // around the kernels of the chunk in flight (stats.kernel_ms_total)
+    bool k_timed = false;
 };
 
 template <class T>
@@ -86,6 +88,7 @@ struct bns_b200_ctx {
     bool building = false;
     bool timed = false;               // ev0/ev1 have been recorded
     u32 *d_status = nullptr;
+    u32 *d_big = nullptr; size_t cap_big = 0;   // global-memory taxon lists of the second classify pass (databases of > 256 values)
     Slot slots[N_SLOTS];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bns_b200_stats stats{};
@@ -451,8 +454,17 @@ int finish_table(bns_b200_ctx *ctx, const unsigned long long *h_stats) {
     return rc;
 }
 
+// device time of the kernels a slot ran for its last chunk (the slot's stream must be idle)
+void collect_kernel_time(bns_b200_ctx *ctx, Slot &s) {
+    if(!s.k_timed) return;
+    s.k_timed = false;
+    float ms = 0.f;
+    if(cudaEventElapsedTime(&ms, s.ka, s.kb) == cudaSuccess) { ctx->stats.kernel_ms_total += ms; ctx->stats.last_kernel_ms = ms; }
+    else cudaGetLastError();
+}
+
 int check_status(bns_b200_ctx *ctx, u32 st) {
-    if(st & 2u) return ctx->fail(BNS_E_CAPACITY, "a record hit more than %d distinct taxa", AGG_CAP);
+    if(st & 2u) return ctx->fail(BNS_E_CAPACITY, "a record hit more than 65536 distinct taxa");
     if(st & 1u) return ctx->fail(BNS_E_CAPACITY, "an output window was too small for the k-mers produced");
     if(st & 4u) return ctx->fail(BNS_E_INVAL, "a taxid passed to resolve is not a database value");
     if(st & 8u) return ctx->fail(BNS_E_CAPACITY, "a record is longer than 2^32-2 bases");
@@ -518,8 +530,9 @@ int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
     for(int i = 0; i < N_SLOTS; ++i)
         if((e = cudaStreamCreateWithFlags(&ctx->slots[i].st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for(int i = 0; i < N_SLOTS; ++i) {
-        if((e = cudaMalloc((void **)&ctx->slots[i].d_defer_cnt, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-        cudaMemset(ctx->slots[i].d_defer_cnt, 0, sizeof(unsigned long long));
+        if((e = cudaMalloc((void **)&ctx->slots[i].d_defer_cnt, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+        cudaMemset(ctx->slots[i].d_defer_cnt, 0, 2 * sizeof(unsigned long long));
+        if((e = cudaEventCreate(&ctx->slots[i].ka)) != cudaSuccess || (e = cudaEventCreate(&ctx->slots[i].kb)) != cudaSuccess) return bail(e, "cudaEventCreate");
     }
     if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -540,6 +553,7 @@ void bns_b200_close(bns_b200_t *ctx) {
     if(ctx->d_node_info) cudaFree(ctx->d_node_info);
     if(ctx->d_counters) cudaFree(ctx->d_counters);
     if(ctx->d_status) cudaFree(ctx->d_status);
+    if(ctx->d_big) cudaFree(ctx->d_big);
     for(auto &s : ctx->slots) {
         if(s.d_bases) cudaFree(s.d_bases);
         if(s.d_offsets) cudaFree(s.d_offsets);
@@ -553,6 +567,8 @@ void bns_b200_close(bns_b200_t *ctx) {
         if(s.d_run_pos) cudaFree(s.d_run_pos);
         if(s.d_nruns) cudaFree(s.d_nruns);
         if(s.d_defer_cnt) cudaFree(s.d_defer_cnt);
+        if(s.ka) cudaEventDestroy(s.ka);
+        if(s.kb) cudaEventDestroy(s.kb);
         if(s.st) cudaStreamDestroy(s.st);
     }
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -848,6 +864,8 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
     ctx->building = false;
     unsigned long long h[4];
     CK(cudaMemcpy(h, ctx->d_counters + 8, sizeof h, cudaMemcpyDeviceToHost));
+    if(h[2]) return ctx->fail(BNS_E_TAXONOMY, "%llu k-mers could not be merged: an lca of two genomes' taxids is not an ancestor of either "
+                              "in the loaded taxonomy (malformed nodes file?)", h[2]);
     if(h[0]) return ctx->fail(BNS_E_CAPACITY, "%llu k-mers found no slot: call build_begin with a larger max_kmers", h[0]);
     ctx->n_displaced = 0;
     ctx->tax_ready = true;
@@ -866,18 +884,24 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         const u64 n = ctx->n_keys;
         u64 *dk = nullptr, *new_slots = nullptr;
         u32 *dv = nullptr;
-        CK(cudaMalloc((void **)&dk, std::max<u64>(n, 1) * 8));
-        CK(cudaMalloc((void **)&dv, std::max<u64>(n, 1) * 4));
-        CK(cudaMalloc((void **)&new_slots, (1ull << want) * 32));
-        CK(cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st));
-        CK(cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st));
-        CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, n, ctx->d_counters + 12));
-        CK(launch_insert(st, new_slots, nf, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
-        ctx->stats.kernel_launches += 2;
         unsigned long long h2[3];
-        CK(cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        cudaFree(dk); cudaFree(dv);
+        auto rehome = [&]() -> cudaError_t {
+            cudaError_t e;
+            if((e = cudaMalloc((void **)&dk, std::max<u64>(n, 1) * 8)) != cudaSuccess) return e;
+            if((e = cudaMalloc((void **)&dv, std::max<u64>(n, 1) * 4)) != cudaSuccess) return e;
+            if((e = cudaMalloc((void **)&new_slots, (1ull << want) * 32)) != cudaSuccess) return e;
+            if((e = cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st)) != cudaSuccess) return e;
+            if((e = cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+            if((e = launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, n, ctx->d_counters + 12)) != cudaSuccess) return e;
+            if((e = launch_insert(st, new_slots, nf, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13)) != cudaSuccess) return e;
+            ctx->stats.kernel_launches += 2;
+            if((e = cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            return cudaStreamSynchronize(st);
+        };
+        const cudaError_t re = rehome();
+        if(dk) cudaFree(dk);
+        if(dv) cudaFree(dv);
+        if(re != cudaSuccess) { if(new_slots) cudaFree(new_slots); return ctx->cuda_fail(re, "re-homing the built table"); }
         if(h2[0] || h2[2]) {                                              // no room
             cudaFree(new_slots);
             if(mini) ctx->no_minimizer = true;                            // same size, hash layout
@@ -904,15 +928,21 @@ int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out,
     if(cap < ctx->n_keys) return ctx->fail(BNS_E_CAPACITY, "table holds %llu keys", (unsigned long long)ctx->n_keys);
     u64 *dk = nullptr; u32 *dv = nullptr;
     cudaStream_t st = ctx->slots[0].st;
-    CK(cudaMalloc((void **)&dk, std::max<u64>(ctx->n_keys, 1) * 8));
-    CK(cudaMalloc((void **)&dv, std::max<u64>(ctx->n_keys, 1) * 4));
-    CK(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st));
-    CK(launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12));
-    ++ctx->stats.kernel_launches;
-    CK(cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    cudaFree(dk); cudaFree(dv);
+    auto dump = [&]() -> cudaError_t {
+        cudaError_t e;
+        if((e = cudaMalloc((void **)&dk, std::max<u64>(ctx->n_keys, 1) * 8)) != cudaSuccess) return e;
+        if((e = cudaMalloc((void **)&dv, std::max<u64>(ctx->n_keys, 1) * 4)) != cudaSuccess) return e;
+        if((e = cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if((e = launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12)) != cudaSuccess) return e;
+        ++ctx->stats.kernel_launches;
+        if((e = cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if((e = cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(st);
+    };
+    const cudaError_t de = dump();
+    if(dk) cudaFree(dk);
+    if(dv) cudaFree(dv);
+    if(de != cudaSuccess) return ctx->cuda_fail(de, "table dump");
     return BNS_OK;
 }
 
@@ -1139,6 +1169,36 @@ int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
     for(int i = 0; i < n; ++i)
         if(i != root && (rc = bns_b200_db_alloc_from_header(handles[i], &hdr)) != BNS_OK)
             return ctx->fail(rc, "replica %d: %s", i, handles[i]->err.c_str());
+    // BNS_B200_REPLICATE=p2p: peer copies (cudaMemcpyPeerAsync over NVLink) instead of NCCL. ncclCommInitAll costs seconds of
+    // topology discovery per process, which a short `bonsai classify --gpus N` run feels; the broadcast itself is milliseconds.
+    if(const char *how = getenv("BNS_B200_REPLICATE")) {
+        if(!strcmp(how, "p2p")) {
+            std::vector<void *> ptrs((size_t)n * 4);
+            uint64_t bytes[4] = {0, 0, 0, 0};
+            for(int i = 0; i < n; ++i) {
+                uint64_t b[4]; int ns = 0;
+                rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 4], b, 4, &ns);
+                if(rc != BNS_OK || ns != 4) return ctx->fail(BNS_E_STATE, "replica %d has no segments", i);
+                if(i == root) for(int s = 0; s < 4; ++s) bytes[s] = b[s];
+            }
+            for(int i = 0; i < n; ++i) {
+                if(i == root) continue;
+                for(int s = 0; s < 4; ++s)
+                    if(bytes[s]) {
+                        const cudaError_t e = cudaMemcpyPeerAsync(ptrs[(size_t)i * 4 + s], handles[i]->device, ptrs[(size_t)root * 4 + s], ctx->device,
+                                                                  (size_t)bytes[s], ctx->slots[0].st);
+                        if(e != cudaSuccess) return ctx->cuda_fail(e, "cudaMemcpyPeerAsync");
+                    }
+            }
+            cudaSetDevice(ctx->device);
+            const cudaError_t e = cudaStreamSynchronize(ctx->slots[0].st);
+            if(e != cudaSuccess) return ctx->cuda_fail(e, "replication stream");
+            for(int i = 0; i < n; ++i)
+                if(i != root && (rc = bns_b200_db_commit(handles[i])) != BNS_OK) return ctx->fail(rc, "replica %d: %s", i, handles[i]->err.c_str());
+            cudaSetDevice(ctx->device);
+            return BNS_OK;
+        }
+    }
     NcclApi &nc = nccl_api();
     if(!nc.ok) return ctx->fail(BNS_E_CUDA, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
     // NCCL announces itself on stdout ("NCCL version ..."), which is where `bonsai classify` writes its records: while NCCL
@@ -1260,8 +1320,9 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     const u64 total_bases = ~0ull;
     const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec, mates, d_taxa != nullptr, false, d_n_hit || d_n_missing);
     Slot &s0 = ctx->slots[0];
-    if(pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R)) {
+    if(pl.second_pass) {
         rc = ensure(s0.d_defer, s0.cap_defer, n_rec);
+        if(rc == BNS_OK) rc = ensure(ctx->d_big, ctx->cap_big, pass2_scratch_words(pl));
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
         CK(cudaMemsetAsync(s0.d_defer_cnt, 0, sizeof(unsigned long long), st));
     }
@@ -1270,7 +1331,7 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     CK(launch_classify(ctx->enc, pl, st, d_bases, (const u64 *)d_offsets, n_rec, mates, total_bases,
                        table_view(ctx), tax_view(ctx), d_taxon, d_n_hit, d_n_missing, d_taxa,
                        (const u64 *)d_taxa_offsets, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status,
-                       s0.d_defer, s0.d_defer_cnt, &nl));
+                       s0.d_defer, s0.d_defer_cnt, &nl, nullptr, ctx->d_big));
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->stats.kernel_launches += nl;
     ctx->stats.reads_processed += n_reads;          // bases_processed is not known on the host for device-resident calls
@@ -1307,6 +1368,7 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         const u64 nb = offsets[r1] - offsets[r0];
         Slot &s = ctx->slots[slot_i];
         CK(cudaStreamSynchronize(s.st));
+        collect_kernel_time(ctx, s);
         rc = ensure(s.d_bases, s.cap_bases, nb + 16);
         if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
         if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 4 * nq);
@@ -1319,9 +1381,15 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, taxa_out != nullptr, mate1_kmers_out != nullptr,
                                          n_hit_out || n_missing_out);
         const bool windowed_lean = pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R);
-        if(rc == BNS_OK && windowed_lean) rc = ensure(s.d_defer, s.cap_defer, nq);
+        if(rc == BNS_OK && pl.second_pass) rc = ensure(s.d_defer, s.cap_defer, nq);
+        if(rc == BNS_OK && pl.second_pass) {
+            // the scratch is shared by the slots: the pass that uses it is stream-ordered behind the previous chunk's only when
+            // it does not move, so it is sized once for the largest plan before any chunk is in flight
+            if(pass2_scratch_words(pl) > ctx->cap_big) { for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st)); }
+            rc = ensure(ctx->d_big, ctx->cap_big, pass2_scratch_words(pl));
+        }
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
-        if(windowed_lean) CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));
+        if(pl.second_pass) CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));
         // Fixed-length batches (every read of a sequencing run has the same length): the offsets are an arithmetic
         // progression the kernel generates itself; they do not cross PCIe (5 % of the bytes of a 150 bp read).
         if(pl.lean && !windowed_lean && nb % nr == 0 && nb / nr < 0xffffffffull) {
@@ -1334,11 +1402,14 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         if(!pl.fixed_len) CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(taxa_out) CK(cudaMemcpyAsync(s.d_taxa_offsets, taxa_offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, s.st));
         int nl = 1;
+        CK(cudaEventRecord(s.ka, s.st));
         CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
                            n_missing_out ? s.d_out + 2 * nq : nullptr, taxa_out ? s.d_taxa - taxa_offsets[q0] : nullptr,
                            taxa_out ? s.d_taxa_offsets : nullptr, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap,
-                           ctx->d_counters, ctx->d_status, s.d_defer, s.d_defer_cnt, &nl));
+                           ctx->d_counters, ctx->d_status, s.d_defer, s.d_defer_cnt, &nl, nullptr, ctx->d_big));
+        CK(cudaEventRecord(s.kb, s.st));
+        s.k_timed = true;
         ctx->stats.kernel_launches += nl;
         CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
         if(n_hit_out) CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
@@ -1352,10 +1423,10 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         q0 = q1;
         slot_i = (slot_i + 1) % N_SLOTS;
     }
-    for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st));
+    for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); collect_kernel_time(ctx, ctx->slots[i]); }
     u32 status = 0;
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
-    return check_status(ctx, status & 10u);
+    return check_status(ctx, status & 11u);
 }
 
 // classify_seqs with the hit lists run-length encoded on the device. Chunks are pipelined over the stream slots like
@@ -1396,8 +1467,9 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
         pd.live = false;
         Slot &s = ctx->slots[si];
         unsigned long long total = 0;
-        CK(cudaMemcpyAsync(&total, s.d_defer_cnt, sizeof total, cudaMemcpyDeviceToHost, s.st));
+        CK(cudaMemcpyAsync(&total, s.d_defer_cnt + 1, sizeof total, cudaMemcpyDeviceToHost, s.st));
         CK(cudaStreamSynchronize(s.st));
+        collect_kernel_time(ctx, s);
         if(used + total > runs_cap) return no_room(used + total);
         if(total) CK(cudaMemcpyAsync(runs_out + used, s.d_runs, total * 8, cudaMemcpyDeviceToHost, s.st));
         CK(cudaMemcpyAsync(run_pos_out + pd.q0, s.d_run_pos, pd.nq * 8, cudaMemcpyDeviceToHost, s.st));
@@ -1433,6 +1505,11 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
             rc = ensure(s.d_taxa, s.cap_taxa, nt + 1);
             if(rc == BNS_OK) rc = ensure(s.d_taxa_offsets, s.cap_taxa_offsets, nq + 1);
         }
+        if(rc == BNS_OK && pl.second_pass) rc = ensure(s.d_defer, s.cap_defer, nq);
+        if(rc == BNS_OK && pl.second_pass) {
+            if(pass2_scratch_words(pl) > ctx->cap_big) { for(int i = 0; i < N_SLOTS; ++i) CK(cudaStreamSynchronize(ctx->slots[i].st)); }
+            rc = ensure(ctx->d_big, ctx->cap_big, pass2_scratch_words(pl));
+        }
         if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
         if(pl.runs && nb % nr == 0 && nb / nr < 0xffffffffull) {              // fixed-length batch: offsets stay on the host
             const u64 flen = nb / nr;
@@ -1440,7 +1517,7 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
             for(u64 r = r0; fixed && r < r1; ++r) fixed = offsets[r + 1] - offsets[r] == flen;
             if(fixed) { pl.fixed_len = (u32)flen; pl.fixed_base = offsets[r0]; }
         }
-        CK(cudaMemsetAsync(s.d_defer_cnt, 0, sizeof(unsigned long long), s.st));     // the run counter of this chunk
+        CK(cudaMemsetAsync(s.d_defer_cnt, 0, 2 * sizeof(unsigned long long), s.st)); // second-pass list and run counter of this chunk
         CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
         if(!pl.fixed_len) CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st));
         if(!pl.runs) {
@@ -1452,12 +1529,15 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
             CK(cudaStreamSynchronize(s.st));                               // h_toffs is reused by the next chunk
         }
         int nl = 1;
-        const RunsOut ro{s.d_runs, s.cap_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns};
+        const RunsOut ro{s.d_runs, s.cap_runs, s.d_defer_cnt + 1, s.d_run_pos, s.d_nruns};
+        CK(cudaEventRecord(s.ka, s.st));
         CK(launch_classify(ctx->enc, pl, s.st, s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
                            table_view(ctx), tax_view(ctx), s.d_out, s.d_out + nq, s.d_out + 2 * nq, pl.runs ? nullptr : s.d_taxa,
                            pl.runs ? nullptr : s.d_taxa_offsets, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap, ctx->d_counters,
-                           ctx->d_status, nullptr, nullptr, &nl, &ro));
-        if(!pl.runs) { CK(launch_rle(s.st, s.d_taxa, s.d_taxa_offsets, s.d_out + nq, nq, s.d_runs, s.d_defer_cnt, s.d_run_pos, s.d_nruns)); ++nl; }
+                           ctx->d_status, s.d_defer, s.d_defer_cnt, &nl, &ro, ctx->d_big));
+        if(!pl.runs) { CK(launch_rle(s.st, s.d_taxa, s.d_taxa_offsets, s.d_out + nq, nq, s.d_runs, s.d_defer_cnt + 1, s.d_run_pos, s.d_nruns)); ++nl; }
+        CK(cudaEventRecord(s.kb, s.st));
+        s.k_timed = true;
         ctx->stats.kernel_launches += nl;
         CK(cudaMemcpyAsync(taxon_out + q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
         CK(cudaMemcpyAsync(n_hit_out + q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
@@ -1478,6 +1558,16 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
     *n_runs_total_out = used;
     u32 status = 0;
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
+    return check_status(ctx, status & 11u);
+}
+
+int bns_b200_device_status(bns_b200_t *ctx) {
+    if(!ctx) return BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    u32 status = 0;
+    CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->d_status, 0, 4));
     return check_status(ctx, status & 11u);
 }
 

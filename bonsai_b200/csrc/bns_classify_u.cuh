@@ -801,8 +801,12 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             // ---- resolve_tree (util.h:831-869) -------------------------------------------------------------------
             u32 taxon = 0;
             if(spilled) {
-                taxon = sink.resolve(S, X, lane);
-                if(sink.overflow && lane == 0) atomicOr(status, 2u);
+                if(sink.overflow) {
+                    // more distinct taxa than the shared-memory lists hold (only a database of more than AGG_CAP values can do
+                    // that): the second pass redoes the record with its lists in global memory
+                    if(defer_idx) { if(lane == 0) defer_idx[atomicAdd(defer_cnt, 1ull)] = (u32)((r0 + j) >> msh); deferred = true; }
+                    else if(lane == 0) atomicOr(status, 2u);
+                } else taxon = sink.resolve(S, X, lane);
                 sink.n_distinct = 0; sink.overflow = 0;
                 __syncwarp();
             } else if(nd) taxon = sink.vi[id0].w;
@@ -843,7 +847,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             if(RUNS) { run_pos_out[o0 + lane] = my_rpos; n_runs_out[o0 + lane] = my_nruns; }
         }
         const u32 cls = __popc(__ballot_sync(FULL, lane < nout && my_taxon != 0));
-        const u32 ndef = (MODE == LEAN_U || MODE == LEAN_S) ? 0u : __popc(__ballot_sync(FULL, lane < nout && my_def != 0));
+        const u32 ndef = __popc(__ballot_sync(FULL, lane < nout && my_def != 0));
         if(lane == 0) {                                                // classified_[2] (classifier.h:138,238), once per batch
             atomicAdd(&counters[0], (unsigned long long)cls);
             atomicAdd(&counters[1], (unsigned long long)(nout - cls - ndef));

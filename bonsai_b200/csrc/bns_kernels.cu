@@ -312,8 +312,13 @@ struct ClassifySink {
     const uint4 *vi;  // val_info: shared-memory copy (TMA-staged) when it fits, else global
     u32 *taxa_out;    // ordered hit list of this record (raw taxids) when TAXA
     u32 n_distinct, n_hit, n_miss, overflow;   // warp-uniform
+    u32 cap = AGG_CAP;                         // entries the distinct-taxon lists hold (AGG_CAP in shared memory; more in the overflow pass)
+    u64 taxa_cap = 0;                          // entries of this record's hit-list window (the caller sized it)
+    u32 taxa_short = 0;                        // ... and whether it was too small
 
-    __device__ __forceinline__ void begin(u32 *taxa) { taxa_out = taxa; n_distinct = n_hit = n_miss = overflow = 0; }
+    __device__ __forceinline__ void begin(u32 *taxa, u64 tcap = ~0ull) {
+        taxa_out = taxa; taxa_cap = tcap; n_distinct = n_hit = n_miss = overflow = taxa_short = 0;
+    }
 
     // linear::counter::add of `total` hits of value id v
     __device__ __forceinline__ void add(const WarpSmem &S, u32 v, u32 total, u32 lane) {
@@ -324,7 +329,7 @@ struct ClassifySink {
             if(bm) { found = (int)(base + __ffs(bm) - 1); break; }
         }
         if(found < 0) {
-            if(n_distinct < AGG_CAP) {
+            if(n_distinct < cap) {
                 if(lane == 0) { S.ids[n_distinct] = v; S.cnt[n_distinct] = total; }
                 ++n_distinct;
             } else overflow = 1;
@@ -346,7 +351,8 @@ struct ClassifySink {
             u32 dummy;
             u32 idx = n_hit + warp_excl_scan(__popc(todo), lane, dummy);
 #pragma unroll
-            for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) taxa_out[idx++] = vi[val[i]].w;
+            for(int i = 0; i < PPL; ++i) if(todo >> i & 1u) { if(idx < taxa_cap) taxa_out[idx] = vi[val[i]].w; ++idx; }
+            if((u64)n_hit + hits_total > taxa_cap) taxa_short = 1;
         }
         n_hit += hits_total;
         n_miss += (both & 0xffffu) - hits_total;
@@ -446,8 +452,8 @@ struct BuildSink {
     const uint4 *val_info, *node_info; // Euler intervals: {tin, tout, node, taxid} / {tin, tout, parent node, taxid}
     const u32 *values;
     u32 n_values, node_of_one;
-    unsigned long long *stats;         // [0] failed  [1] displaced  [3] new keys
-    u32 n_new, n_fail;                 // per lane
+    unsigned long long *stats;         // [0] no room  [1] displaced  [2] bad taxonomy / value (lca outside the dictionary, upper-word clash)  [3] new keys
+    u32 n_new, n_fail, n_bad;          // per lane
 
     __device__ __forceinline__ u32 lca_id(u32 a_id, u32 b_id) const {     // lca(), util.h:634-663, on value ids
         if(a_id == b_id) return a_id;
@@ -481,14 +487,14 @@ struct BuildSink {
                         if(old == vid) return;
                         const u32 m = lca_id(vid, old);
                         if(m == old) return;
-                        if(m == VAL_MISS) { ++n_fail; return; }
+                        if(m == VAL_MISS) { ++n_bad; return; }
                         const u64 want = (cur & ~(u64)val_mask) | m;
                         const u64 prev = atomicCAS((unsigned long long *)&bk[s], (unsigned long long)cur, (unsigned long long)want);
                         if(prev == cur) return;
                         cur = prev;                                      // value or overflow mark changed under us: retry
                     }
                 }
-                if(fmt.layout == LAYOUT_HASH && (u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant
+                if(fmt.layout == LAYOUT_HASH && (u32)(cur >> 32) == (u32)(entry >> 32)) { ++n_fail; return; }   // unique-upper-word invariant: a larger table re-draws the words
             }
             if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + (th.fsel & flag_mask))));
         }
@@ -792,18 +798,27 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
                     u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out, u32 *__restrict__ nmiss_out,
                     u32 *__restrict__ taxa_out, const u64 *__restrict__ taxa_offsets, u32 *__restrict__ mate1_out, u32 ring_cap,
                     unsigned long long *__restrict__ counters, u32 *__restrict__ status,
-                    const u32 *__restrict__ rec_list, const unsigned long long *__restrict__ rec_count) {
-    // rec_list != nullptr: only the *rec_count records it names (what the lean kernel left for this one)
+                    const u32 *__restrict__ rec_list, const unsigned long long *__restrict__ rec_count,
+                    u32 *__restrict__ ovf_idx, unsigned long long *__restrict__ ovf_cnt, u32 *__restrict__ big_scratch, u32 big_cap) {
+    // rec_list != nullptr: only the *rec_count records it names (what the first pass left for this one: windowed records of
+    // more than one tile, 32-T restarts, records with more than AGG_CAP distinct taxa). ovf_idx != nullptr (first pass): a
+    // record whose distinct-taxon list overflows shared memory is appended there instead of failing the call; the pass over
+    // rec_list keeps its lists in big_scratch (global memory, big_cap entries per list).
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
     const u32 lane = lane_id(), wid = threadIdx.x >> 5;
     const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
     if(staged) tma_stage_val_info(s_vi, X.val_info, T.n_values * (u32)sizeof(uint4), &s_mbar);
-    const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, true), ring_cap);
+    WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, true), ring_cap);
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
     ClassifySink<TAXA> sink;
     sink.T = T;
     sink.vi = staged ? s_vi : X.val_info;
+    if(big_scratch) {
+        S.ids = big_scratch + ((size_t)blockIdx.x * WARPS_PER_CTA + wid) * 4 * big_cap;
+        S.cnt = S.ids + big_cap; S.tin = S.cnt + big_cap; S.tout = S.tin + big_cap;
+        sink.cap = big_cap;
+    }
     if(staged) mbar_wait(&s_mbar, 0);
     u32 n_cls = 0, n_uncls = 0;
     // total_bases == ~0: the caller's offsets live on the device only (bns_b200_classify_device); the bound of the
@@ -827,7 +842,7 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
             if(r + 2 * nwarps < n_records) { b2 = offsets[r + 2 * nwarps]; e2 = offsets[r + 2 * nwarps + 1]; }
             uint4 v1 = make_uint4(0, 0, 0, 0);
             if(r + nwarps < n_records) v1 = load_tile_block(bases + b1, (u32)min((u64)span, e1 - b1), buf_end, lane);
-            sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
+            sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr, TAXA ? taxa_offsets[r + 1] - taxa_offsets[r] : 0ull);
             encode_sequence<FAM>(P, S, bases + b0, e0 - b0, buf_end, sink, lane, &v0);
             const u32 taxon = sink.resolve(S, X, lane);
             if(lane == 0) {
@@ -835,9 +850,10 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
                 taxon_out[r] = taxon;
                 if(nhit_out) nhit_out[r] = sink.n_hit;
                 if(nmiss_out) nmiss_out[r] = sink.n_miss;
-                if(sink.overflow) atomicOr(status, 2u);
+                if(sink.overflow) { if(ovf_idx) ovf_idx[atomicAdd(ovf_cnt, 1ull)] = (u32)r; else atomicOr(status, 2u); }
+                if(TAXA && sink.taxa_short) atomicOr(status, 1u);
             }
-            if(taxon) ++n_cls; else ++n_uncls;
+            if(sink.overflow && ovf_idx) {} else if(taxon) ++n_cls; else ++n_uncls;
             __syncwarp();
             b0 = b1; e0 = e1; v0 = v1; b1 = b2; e1 = e2;
         }
@@ -845,7 +861,7 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
     const u64 n_loop = rec_list ? (u64)*rec_count : n_records;
     for(u64 it = r_first; it < n_loop; it += nwarps) {
         const u64 r = rec_list ? (u64)rec_list[it] : it;
-        sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr);
+        sink.begin(TAXA ? taxa_out + taxa_offsets[r] : nullptr, TAXA ? taxa_offsets[r + 1] - taxa_offsets[r] : 0ull);
         for(u32 mt = 0; mt < mates; ++mt) {
             const u64 b = offsets[r * mates + mt], e = offsets[r * mates + mt + 1];
             encode_sequence<FAM>(P, S, bases + b, e - b, buf_end, sink, lane);
@@ -857,9 +873,10 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
             taxon_out[r] = taxon;
             if(nhit_out) nhit_out[r] = sink.n_hit;
             if(nmiss_out) nmiss_out[r] = sink.n_miss;
-            if(sink.overflow) atomicOr(status, 2u);
+            if(sink.overflow) { if(ovf_idx) ovf_idx[atomicAdd(ovf_cnt, 1ull)] = (u32)r; else atomicOr(status, 2u); }
+            if(TAXA && sink.taxa_short) atomicOr(status, 1u);
         }
-        if(taxon) ++n_cls; else ++n_uncls;
+        if(sink.overflow && ovf_idx) {} else if(taxon) ++n_cls; else ++n_uncls;
         __syncwarp();
     }
     }
@@ -1000,15 +1017,16 @@ bns_build_kernel(const __grid_constant__ EncParams P, const char *__restrict__ b
     const WarpSmem S = carve(g_smem + wid * warp_smem_bytes(ring_cap, false), ring_cap);
     const u64 nwarps = (u64)gridDim.x * WARPS_PER_CTA;
     BuildSink sink = proto;
-    sink.n_new = sink.n_fail = 0;
+    sink.n_new = sink.n_fail = sink.n_bad = 0;
     for(u64 r = (u64)blockIdx.x * WARPS_PER_CTA + wid; r < n_seqs; r += nwarps) {
         const u64 b = offsets[2 * r], e = offsets[2 * r + 1];           // (start, end) pairs: pieces may overlap
         encode_sequence<FAM>(P, S, bases + b, e - b, bases + total_bases, sink, lane);
     }
-    const u32 nn = __reduce_add_sync(FULL, sink.n_new), nf = __reduce_add_sync(FULL, sink.n_fail);
+    const u32 nn = __reduce_add_sync(FULL, sink.n_new), nf = __reduce_add_sync(FULL, sink.n_fail), nbad = __reduce_add_sync(FULL, sink.n_bad);
     if(lane == 0) {
         if(nn) atomicAdd(&sink.stats[3], (unsigned long long)nn);
         if(nf) atomicAdd(&sink.stats[0], (unsigned long long)nf);
+        if(nbad) atomicAdd(&sink.stats[2], (unsigned long long)nbad);
     }
 }
 
@@ -1096,7 +1114,8 @@ size_t stream_smem_bytes(u32 ring_cap, bool classify) { return WARPS_PER_CTA * w
 
 typedef void (*encode_fn)(const EncParams, const char *, const u64 *, u64, u64, u64 *, const u64 *, u32 *, u32, u32 *);
 typedef void (*classify_fn)(const EncParams, const char *, const u64 *, u64, u32, u64, TableView, TaxView, u32 *, u32 *, u32 *,
-                            u32 *, const u64 *, u32 *, u32, unsigned long long *, u32 *, const u32 *, const unsigned long long *);
+                            u32 *, const u64 *, u32 *, u32, unsigned long long *, u32 *, const u32 *, const unsigned long long *,
+                            u32 *, unsigned long long *, u32 *, u32);
 
 static encode_fn pick_encode(u32 fam) {
     switch(fam) {
@@ -1204,7 +1223,12 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
         const u64 want = ((n_records * mates + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;   // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
     }
-    if(!pl.lean || pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R) { // the generic kernel: everything, or the deferred records
+    // A second pass of the generic kernel takes what the first leaves: windowed records of more than one tile and 32-T restarts
+    // (lean windowed modes), and -- only possible when the database holds more than AGG_CAP distinct values -- records that hit
+    // more distinct taxa than the shared-memory lists hold; it keeps its lists in global memory.
+    pl.big_cap = T.n_values > (u32)AGG_CAP ? std::min<u32>((T.n_values + 31u) & ~31u, 1u << 16) : 0u;
+    pl.second_pass = (pl.lean && (pl.lean_mode == LEAN_K || pl.lean_mode == LEAN_R)) || pl.big_cap != 0;
+    if(!pl.lean || pl.second_pass) {                                   // the generic kernel: everything, or the deferred records
         int ng = 0;
         classify_fn f = pick_classify(P.family, taxa);
         pl.gen_smem = stream_smem_bytes(ring_cap, true);
@@ -1213,6 +1237,7 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
         const u64 want = (n_records + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         pl.gen_grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (ng > 0 ? ng : 1)));
         if(!pl.lean) { nb = ng; pl.grid = pl.gen_grid; pl.smem = pl.gen_smem; }
+        pl.pass2_grid = pl.big_cap ? std::min(pl.gen_grid, 32) : pl.gen_grid;
     }
     pl.occupancy = nb;
     return pl;
@@ -1223,7 +1248,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
-                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro) {
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro, u32 *big_scratch) {
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs);
@@ -1232,22 +1257,25 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                                                     pl.runs ? ro->runs : nullptr, pl.runs ? ro->cap : 0, pl.runs ? ro->total : nullptr,
                                                     pl.runs ? ro->run_pos : nullptr, pl.runs ? ro->n_runs : nullptr);
         cudaError_t e = cudaGetLastError();
-        if(e != cudaSuccess || pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) return e;
-        // records the lean kernel left (more than one tile of window elements, 32-T restarts): usually none, the kernel
-        // reads the count on the device and returns at once. Sized small: deferred records are rare and long.
-        classify_fn g = pick_classify(P.family, false);
-        g<<<pl.gen_grid, WARPS_PER_CTA * 32, pl.gen_smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out,
-                                                               nhit_out, nmiss_out, nullptr, nullptr, mate1_out, ring_cap, counters,
-                                                               status, defer_idx, defer_cnt);
-        if(n_launched) *n_launched = 2;
-        return cudaGetLastError();
+        if(e != cudaSuccess || !pl.second_pass) return e;
+    } else {
+        classify_fn f = pick_classify(P.family, taxa_out != nullptr);
+        f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
+                                                        nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status,
+                                                        nullptr, nullptr, pl.second_pass ? defer_idx : nullptr, defer_cnt, nullptr, 0u);
+        cudaError_t e = cudaGetLastError();
+        if(e != cudaSuccess || !pl.second_pass) return e;
     }
-    classify_fn f = pick_classify(P.family, taxa_out != nullptr);
-    f<<<pl.grid, WARPS_PER_CTA * 32, pl.smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out, nhit_out,
-                                                    nmiss_out, taxa_out, taxa_offsets, mate1_out, ring_cap, counters, status,
-                                                    nullptr, nullptr);
+    // the records the first pass left: usually none, the kernel reads the count on the device and returns at once
+    classify_fn g = pick_classify(P.family, !pl.lean && taxa_out != nullptr);
+    g<<<pl.pass2_grid, WARPS_PER_CTA * 32, pl.gen_smem, st>>>(P, bases, offsets, n_records, mates, total_bases, T, X, taxon_out,
+                                                             nhit_out, nmiss_out, pl.lean ? nullptr : taxa_out, pl.lean ? nullptr : taxa_offsets,
+                                                             mate1_out, ring_cap, counters, status, defer_idx, defer_cnt, nullptr, nullptr,
+                                                             pl.big_cap ? big_scratch : nullptr, pl.big_cap);
+    if(n_launched) *n_launched = 2;
     return cudaGetLastError();
 }
+size_t pass2_scratch_words(const ClassifyPlan &pl) { return pl.big_cap ? (size_t)pl.pass2_grid * WARPS_PER_CTA * 4 * pl.big_cap : 0; }
 u64 runs_slack(const ClassifyPlan &pl) { return pl.runs ? (u64)pl.grid * LEAN_WARPS * RUN_BLOCK : 0; }
 int encode_occupancy(const EncParams &P, size_t smem) {
     int nb = 0;
@@ -1264,7 +1292,7 @@ cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t
     sk.slots = slots; sk.b = fmt.b; sk.tag_shift = fmt.tag_shift(); sk.flag_shift = fmt.flag_shift(); sk.flag_mask = fmt.F - 1;
     sk.val_mask = (1u << sk.flag_shift) - 1; sk.vid = vid;
     sk.val_info = X.val_info; sk.node_info = X.node_info; sk.values = values; sk.n_values = n_values;
-    sk.node_of_one = X.node_of_one; sk.stats = stats; sk.n_new = sk.n_fail = 0;
+    sk.node_of_one = X.node_of_one; sk.stats = stats; sk.n_new = sk.n_fail = sk.n_bad = 0;
     void (*f)(const EncParams, const char *, const u64 *, u64, u64, BuildSink, u32) =
         P.family == FAM_U ? bns_build_kernel<FAM_U> : P.family == FAM_K ? bns_build_kernel<FAM_K>
         : P.family == FAM_R ? bns_build_kernel<FAM_R> : bns_build_kernel<FAM_NONE>;

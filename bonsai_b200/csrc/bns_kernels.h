@@ -21,6 +21,7 @@ enum LeanMode : int { LEAN_U = 0, LEAN_K = 1, LEAN_R = 2, LEAN_S = 3 };   // wha
 enum LeanKey : int { LEAN_KEY_PAIR = 0, LEAN_KEY_LEX = 1, LEAN_KEY_ELEM = 2 };   // how window elements are ordered
 struct RunsOut { u64 *runs; u64 cap; unsigned long long *total; u64 *run_pos; u32 *n_runs; };   // run-list outputs of the lean kernel
 struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true, loc = false, runs = false; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0;
+                      bool second_pass = false; int pass2_grid = 1; u32 big_cap = 0;   // the pass over the records the first kernel left (bns_kernels.cu)
                       u32 fixed_len = 0; u64 fixed_base = 0;   // set by the caller: all records have fixed_len bases, offsets are not on the device
                     };
 ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts,
@@ -35,7 +36,9 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
-                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro = nullptr);
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro = nullptr, u32 *big_scratch = nullptr);
+// u32 words of global scratch the second pass needs (0 unless the database holds more than AGG_CAP distinct values)
+size_t pass2_scratch_words(const ClassifyPlan &pl);
 cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t st, const char *bases, const u64 *offsets,
                          u64 n_seqs, u64 total_bases, u64 *slots, const TableFmt &fmt, u32 vid, const TaxView &X, const u32 *values,
                          u32 n_values, unsigned long long *stats, u32 ring_cap);

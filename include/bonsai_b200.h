@@ -198,11 +198,15 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
                                  uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,
                                  uint64_t *n_runs_total_out);
-/* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). */
+/* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). Window of record r in
+ * d_taxa: at least (bases of the record) + 2 entries. Nothing is read back: conditions the host-pointer calls report as
+ * BNS_E_CAPACITY (a record of 2^32-1 bases or more, more than 65536 distinct taxa in one record) are latched on the device
+ * and returned -- and cleared -- by bns_b200_device_status(), which waits for the context's device to go idle. */
 int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
                              uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,
                              uint32_t *d_taxa, const uint64_t *d_taxa_offsets, void *stream);
 
+int bns_b200_device_status(bns_b200_t *ctx);
 int bns_b200_sync(bns_b200_t *ctx);
 int bns_b200_stats_get(const bns_b200_t *ctx, bns_b200_stats *out);
 int bns_b200_stats_reset(bns_b200_t *ctx);

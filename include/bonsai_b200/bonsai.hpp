@@ -239,7 +239,7 @@ struct KSeq {
 
 // ---- Encoder ---------------------------------------------------------------------------------------------------
 // Encoder<Score>: borrows the string, calls fn(kmer) synchronously and in stream order (encoder.h:416). Not
-// thread-safe, one copy per worker (classifier.h:258). Copies share the device context.
+// thread-safe, one copy per worker (classifier.h:258); a copy opens device contexts of its own.
 template <typename ScoreType = score::Lex>
 class Encoder {
     std::shared_ptr<detail::Handle> str_, path_;       // lazily opened contexts for the two overload families
@@ -326,6 +326,17 @@ public:
     Spacer sp_;
     static constexpr u64 ENCODE_OVERFLOW = ~u64(0);
     Encoder(const Spacer &sp, bool canonicalize = true) : canonicalize_(canonicalize && sp.unspaced()), sp_(sp) {}   // encoder.h:148-150
+    // A copy is another worker's encoder (classifier.h:258): it opens its own device contexts at its first use instead of
+    // sharing the original's (a context runs one call at a time).
+    Encoder(const Encoder &o) : canonicalize_(o.canonicalize_), sp_(o.sp_) {}
+    Encoder &operator=(const Encoder &o) {
+        if(this != &o) {
+            str_.reset(); path_.reset(); forced_[0].reset(); forced_[1].reset();
+            for(auto &h : iter_h_) h.reset();
+            canonicalize_ = o.canonicalize_; sp_ = o.sp_; s_ = nullptr; l_ = pos_ = 0; iter_kind_ = -1;
+        }
+        return *this;
+    }
     explicit Encoder(unsigned k, bool canonicalize = true) : Encoder(Spacer(k), canonicalize) {}
     bool canonicalize() const { return canonicalize_; }
     u32 k() const { return sp_.k_; }

@@ -301,6 +301,53 @@ def test_classify_runs_long_records_many_runs(capi, oracle, toy_tax, genomes, mo
                 assert np.array_equal(rn, _rle(lst))
 
 
+def test_records_with_more_distinct_taxa_than_shared_memory_holds(capi, oracle, genomes):
+    """linear::counter has no limit on distinct taxa (linear.h:229); the kernels keep 256 per record in shared memory. A
+    database of 900 values and records that hit up to 900 of them: the second pass (lists in global memory) must give the
+    reference's answer for every entry point -- taxon only, counts, hit lists, run lists, pairs, a windowed encoder."""
+    b, _ = H.genome_records(genomes, 1)
+    region = b[50_000:50_930]
+    lut = np.zeros(256, np.uint64)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    c = lut[region]
+    n = c.size - 30
+    f = np.zeros(n, np.uint64); r = np.zeros(n, np.uint64)
+    for j in range(31):
+        f = (f << np.uint64(2)) | c[j:j + n]
+        r = r | ((np.uint64(3) - c[j:j + n]) << np.uint64(2 * j))
+    keys, first = np.unique(np.minimum(f, r), return_index=True)
+    vals = (1000 + first).astype(np.uint32)                       # one taxon per k-mer position
+    tc = np.concatenate([[1], 50 + np.arange(7), 1000 + np.arange(n)]).astype(np.uint32)
+    tp = np.concatenate([[1], np.ones(7), 50 + (np.arange(n) % 7)]).astype(np.uint32)
+    T = oracle.tax_from_pairs(tc, tp)
+    dbo = oracle.db_from_pairs(keys, vals)
+    reads = [bytes(region), bytes(region[:400]), bytes(region[:150]), b"", bytes(region[300:930]), bytes(region[100:420])] * 3
+    reads.append(bytes(region[:286]))                             # 256 hits: just fits
+    reads.append(bytes(region[:287]))                             # 257: the first that does not
+    bases, offs = po.pack_reads(reads)
+    with capi.Context(31, 31) as ctx:
+        ctx.load_pairs(keys, vals)
+        ctx.load_taxonomy(tc, tp)
+        for paired in (False, True):
+            et, eh, em, lists = oracle.classify(dbo, T, bases, offs, 31, 31, paired=paired, want_taxa=True)
+            assert eh.max() > 256
+            t, h, m = ctx.classify(bases, offs, paired=paired)
+            assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
+            t, h, m, gl = ctx.classify(bases, offs, paired=paired, want_taxa=True)
+            assert np.array_equal(t, et) and all(np.array_equal(a, x) for a, x in zip(lists, gl))
+            t, h, m, runs = ctx.classify_runs(bases, offs, paired=paired)
+            assert np.array_equal(t, et) and np.array_equal(h, eh) and all(np.array_equal(rn, _rle(x)) for rn, x in zip(runs, lists))
+        st = ctx.stats()
+        assert st["n_classified"] + st["n_unclassified"] == 3 * (len(reads) + len(reads) // 2)    # every record counted exactly once
+    with capi.Context(31, 40) as ctx:                             # windowed (lean LEAN_K + second pass)
+        ctx.load_pairs(keys, vals)
+        ctx.load_taxonomy(tc, tp)
+        et, eh, em = oracle.classify(dbo, T, bases, offs, 31, 40)
+        t, h, m = ctx.classify(bases, offs)
+        assert eh.max() > 256 and np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
+
+
 def test_classify_phix_and_paired(capi, golden, gpu_dbs, reads2000, genomes):
     ctx = gpu_dbs("config1_lex_w31")
     pb, poff = po.pack_reads([bytes(genomes["phix"])])
@@ -547,15 +594,17 @@ def test_many_distinct_taxa_and_big_taxonomy(capi, oracle):
     et, eh, em = oracle.classify(D, T, b, o, 31, 31)
     assert np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
     assert len(set(t.tolist())) > 50
-    # more than AGG_CAP (256) distinct taxa in one record is reported, not mis-classified
+    # more than 256 distinct taxa in one record (what shared memory holds): the second pass, lists in global memory
     long_read = seq[:3000]
-    b2, o2 = po.pack_reads([long_read])
+    b2, o2 = po.pack_reads([long_read, seq[5000:5600], long_read[::-1]])
+    vals2 = (np.arange(km.size) % 4000 + 1).astype(np.uint32) * 3 + 1
+    D2 = oracle.db_from_pairs(km, vals2)
     with capi.Context(31) as ctx:
-        ctx.load_pairs(km, (np.arange(km.size) % 4000 + 1).astype(np.uint32) * 3 + 1)
+        ctx.load_pairs(km, vals2)
         ctx.load_taxonomy(nodes, parent)
-        with pytest.raises(capi.BnsError) as e:
-            ctx.classify(b2, o2)
-        assert e.value.code == -6
+        t, h, m = ctx.classify(b2, o2)
+    et, eh, em = oracle.classify(D2, T, b2, o2, 31, 31)
+    assert eh[0] > 2000 and np.array_equal(t, et) and np.array_equal(h, eh) and np.array_equal(m, em)
 
 
 @pytest.mark.parametrize("mode", ["lex_canon", "lex_nocanon", "ent_canon_sat", "ent_canon_wrap", "ent_nocanon_sat",
