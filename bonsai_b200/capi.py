@@ -39,7 +39,8 @@ class Config(C.Structure):
 class TableInfo(C.Structure):
     _fields_ = [("n_keys", C.c_uint64), ("n_buckets", C.c_uint64), ("bytes", C.c_uint64),
                 ("bucket_bits", C.c_uint32), ("val_bits", C.c_uint32), ("n_values", C.c_uint32), ("max_disp", C.c_uint32),
-                ("n_displaced", C.c_uint64), ("n_overflowed", C.c_uint64), ("layout", C.c_uint32), ("disp_bits", C.c_uint32)]
+                ("n_displaced", C.c_uint64), ("n_overflowed", C.c_uint64), ("layout", C.c_uint32), ("disp_bits", C.c_uint32),
+                ("n_stash", C.c_uint64)]
 
 
 class Stats(C.Structure):

@@ -76,6 +76,9 @@ struct bns_b200_ctx {
     u32 bucket_bits = 0, max_disp = 0, flag_count = 1;
     u32 layout = LAYOUT_HASH, fmt_bits = 0, table_k = 0, disp_bits = DISP_BITS;
     bool no_minimizer = false;        // a LAYOUT_MINIMIZER build of this key set failed (skewed minimizers): use LAYOUT_HASH
+    // LAYOUT_MINIMIZER: keys whose chain was full (a few per thousand on real genomes) in a small LAYOUT_HASH table
+    u64 *d_stash = nullptr; u32 stash_bits = 0, stash_flags = 1; u64 n_stash = 0;
+    u64 *d_fail_k = nullptr; u32 *d_fail_v = nullptr;          // the insert kernel's list of keys that found no room
     std::vector<u32> values;          // sorted distinct DB values (value id -> taxid)
     u32 *d_values = nullptr;
     // taxonomy
@@ -203,9 +206,13 @@ int grid_for(bns_b200_ctx *ctx, u64 n_units, int occ) {
     return (int)std::max<u64>(1, std::min(want, cap));
 }
 
+constexpr u64 FAIL_CAP = 1ull << 21;           // keys a minimizer-layout build may send to the stash
+
 void free_table(bns_b200_ctx *ctx) {
     if(ctx->d_slots) cudaFree(ctx->d_slots);
     if(ctx->d_values) cudaFree(ctx->d_values);
+    if(ctx->d_stash) cudaFree(ctx->d_stash);
+    ctx->d_stash = nullptr; ctx->n_stash = 0; ctx->stash_bits = 0;
     ctx->d_slots = nullptr; ctx->d_values = nullptr;
     ctx->n_buckets = ctx->n_keys = 0; ctx->bucket_bits = 0;
     ctx->values.clear();
@@ -236,7 +243,13 @@ bool want_minimizer_layout(const bns_b200_ctx *ctx, u32 b) {
 bool minimizer_build_too_crowded(const bns_b200_ctx *ctx) {
     const char *e = getenv("BNS_B200_LAYOUT");
     if(ctx->layout != LAYOUT_MINIMIZER || (e && !strcmp(e, "minimizer"))) return false;
-    return ctx->n_displaced * 6 > ctx->n_keys;                    // measured: 10 % displaced is still 1.43x the hash layout at 2^30 keys
+    return ctx->n_displaced * 4 > ctx->n_keys;                    // measured: 10 % displaced is still 1.43x the hash layout at 2^30 keys
+}
+TableFmt stash_fmt(const bns_b200_ctx *ctx) {
+    TableFmt f;
+    f.b = ctx->stash_bits; f.fmt_bits = ctx->stash_bits; f.F = ctx->stash_flags; f.layout = LAYOUT_HASH; f.kt = ctx->table_k;
+    f.disp_bits = DISP_BITS;
+    return f;
 }
 TableFmt table_fmt(const bns_b200_ctx *ctx) {
     TableFmt f;
@@ -311,10 +324,11 @@ int refresh_table_stats(bns_b200_ctx *ctx) {
     unsigned long long h[3];
     CK(cudaMemcpyAsync(h, ctx->d_counters + 2, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->n_keys = h[0]; ctx->n_overflowed = h[1]; ctx->max_disp = (u32)h[2];
+    ctx->n_keys = h[0] + ctx->n_stash; ctx->n_overflowed = h[1]; ctx->max_disp = (u32)h[2];
     return BNS_OK;
 }
 
+int ensure_fail_list(bns_b200_ctx *ctx);
 // Insert host pairs through a pinned staging buffer; `next` fills up to cap pairs and returns how many.
 template <class Next>
 int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
@@ -323,6 +337,7 @@ int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
     u32 *h_vals = nullptr, *d_vals = nullptr;
     cudaStream_t st = ctx->slots[0].st;
     int rc = BNS_OK;
+    if(ctx->layout == LAYOUT_MINIMIZER && (rc = ensure_fail_list(ctx)) != BNS_OK) return rc;
     if(cudaMallocHost((void **)&h_keys, 2 * CH * sizeof(u64)) != cudaSuccess ||
        cudaMallocHost((void **)&h_vals, 2 * CH * sizeof(u32)) != cudaSuccess ||
        cudaMalloc((void **)&d_keys, 2 * CH * sizeof(u64)) != cudaSuccess ||
@@ -340,7 +355,8 @@ int insert_stream(bns_b200_ctx *ctx, Next next, unsigned long long *h_stats) {
             cudaMemcpyAsync(d_keys + buf * CH, h_keys + buf * CH, n * sizeof(u64), cudaMemcpyHostToDevice, st);
             cudaMemcpyAsync(d_vals + buf * CH, h_vals + buf * CH, n * sizeof(u32), cudaMemcpyHostToDevice, st);
             cudaError_t e = launch_insert(st, ctx->d_slots, table_fmt(ctx), d_keys + buf * CH, d_vals + buf * CH, n,
-                                          ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5);
+                                          ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5,
+                                          ctx->layout == LAYOUT_MINIMIZER ? ctx->d_fail_k : nullptr, ctx->d_fail_v, FAIL_CAP);
             ++ctx->stats.kernel_launches;
             ctx->stats.h2d_bytes += n * 12;
             if(e != cudaSuccess) { rc = ctx->cuda_fail(e, "insert kernel"); break; }
@@ -435,6 +451,8 @@ TableView table_view(const bns_b200_ctx *ctx) {
     T.flag_mask = ctx->flag_count - 1;
     T.val_mask = (1u << T.flag_shift) - 1;
     T.n_values = (u32)ctx->values.size();
+    T.stash = ctx->d_stash;
+    T.sfmt = stash_fmt(ctx);
     return T;
 }
 TaxView tax_view(const bns_b200_ctx *ctx) {
@@ -444,6 +462,39 @@ TaxView tax_view(const bns_b200_ctx *ctx) {
     X.n_nodes = ctx->n_nodes;
     X.node_of_one = ctx->node_of_one;
     return X;
+}
+
+// the insert kernels listed the keys that found no room (d_fail_k / d_fail_v): a minimizer-layout table keeps them in a small
+// LAYOUT_HASH stash when they are few (at most 1/16 of the keys); st[0] becomes 0 when that worked
+int ensure_fail_list(bns_b200_ctx *ctx) {
+    if(ctx->d_fail_k) return BNS_OK;
+    CK(cudaMalloc((void **)&ctx->d_fail_k, FAIL_CAP * sizeof(u64)));
+    CK(cudaMalloc((void **)&ctx->d_fail_v, FAIL_CAP * sizeof(u32)));
+    return BNS_OK;
+}
+int settle_failures(bns_b200_ctx *ctx, unsigned long long *st, u64 n_keys, int layout = -1) {
+    if(ctx->d_stash) { cudaFree(ctx->d_stash); ctx->d_stash = nullptr; }
+    ctx->n_stash = 0; ctx->stash_bits = 0;
+    if(layout < 0) layout = (int)ctx->layout;
+    if(!st[0] || layout != (int)LAYOUT_MINIMIZER || !ctx->d_fail_k || st[0] > FAIL_CAP || st[0] * 16 > n_keys) return BNS_OK;
+    cudaStream_t s0 = ctx->slots[0].st;
+    const u64 nf = st[0];
+    for(u32 bs = std::max(choose_bits(nf, (u32)ctx->values.size()), 10u); bs <= 30; ++bs) {
+        ctx->stash_bits = bs;
+        ctx->stash_flags = flag_count_for(bs, DISP_BITS, (u32)ctx->values.size());
+        CK(cudaMalloc((void **)&ctx->d_stash, (32ull << bs)));
+        CK(cudaMemsetAsync(ctx->d_stash, 0xff, (32ull << bs), s0));
+        CK(cudaMemsetAsync(ctx->d_counters + 13, 0, 3 * sizeof(unsigned long long), s0));
+        CK(launch_insert(s0, ctx->d_stash, stash_fmt(ctx), ctx->d_fail_k, ctx->d_fail_v, nf, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13));
+        ++ctx->stats.kernel_launches;
+        unsigned long long h[3];
+        CK(cudaMemcpyAsync(h, ctx->d_counters + 13, sizeof h, cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        if(h[0] == 0 && h[2] == 0) { ctx->n_stash = nf; st[0] = 0; return BNS_OK; }
+        cudaFree(ctx->d_stash); ctx->d_stash = nullptr;
+    }
+    ctx->stash_bits = 0;
+    return BNS_OK;
 }
 
 int finish_table(bns_b200_ctx *ctx, const unsigned long long *h_stats) {
@@ -619,6 +670,7 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
             return n;
         }, st);
         if(rc != BNS_OK) return rc;
+        if((rc = settle_failures(ctx, st, n_keys)) != BNS_OK) return rc;
         if(st[0] == 0) {
             rc = finish_table(ctx, st);
             if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
@@ -626,7 +678,7 @@ int bns_b200_load_table(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
             continue;
         }
         // some key found no room within MAX_DISP buckets of home: grow and rebuild (a minimizer-layout build that fails --
-        // skewed minimizers -- is redone in the hash layout at the same size first)
+        // skewed minimizers beyond what the stash takes -- is redone in the hash layout at the same size first)
         if(ctx->layout == LAYOUT_MINIMIZER) { ctx->no_minimizer = true; --b; }
     }
 }
@@ -653,6 +705,7 @@ int bns_b200_load_pairs(bns_b200_t *ctx, const uint64_t *keys, const uint32_t *v
             return m;
         }, st);
         if(rc != BNS_OK) return rc;
+        if((rc = settle_failures(ctx, st, n)) != BNS_OK) return rc;
         if(st[0] == 0) {
             rc = finish_table(ctx, st);
             if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
@@ -680,10 +733,12 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         if(rc == BNS_OK) rc = alloc_table(ctx, b);
         if(rc != BNS_OK) return rc;
         CK(cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), st));
+        if(ctx->layout == LAYOUT_MINIMIZER && (rc = ensure_fail_list(ctx)) != BNS_OK) return rc;
         const u64 CH = 1ull << 28;
         for(u64 off = 0; off < n; off += CH) {
             CK(launch_insert(st, ctx->d_slots, table_fmt(ctx), (const u64 *)d_keys + off, d_vals + off, std::min(CH, n - off),
-                             ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5));
+                             ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 5,
+                             ctx->layout == LAYOUT_MINIMIZER ? ctx->d_fail_k : nullptr, ctx->d_fail_v, FAIL_CAP));
             ++ctx->stats.kernel_launches;
         }
         unsigned long long h[3];
@@ -692,6 +747,7 @@ int bns_b200_load_pairs_device(bns_b200_t *ctx, const uint64_t *d_keys, const ui
         if(getenv("BNS_B200_VERBOSE"))
             fprintf(stderr, "[bns_b200] table build: 2^%u buckets, layout %u, no room for %llu keys, %llu displaced of %llu\n", b, ctx->layout, h[0], h[1],
                     (unsigned long long)n);
+        if((rc = settle_failures(ctx, h, n)) != BNS_OK) return rc;
         if(h[0] == 0) {
             rc = finish_table(ctx, h);
             if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
@@ -716,6 +772,7 @@ int bns_b200_table_info_get(const bns_b200_t *ctx, bns_b200_table_info *info) {
     info->max_disp = ctx->max_disp;
     info->n_displaced = ctx->n_displaced;
     info->n_overflowed = ctx->n_overflowed;
+    info->n_stash = ctx->n_stash;
     return BNS_OK;
 }
 
@@ -876,32 +933,44 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
     // layout that size calls for (a minimizer-layout attempt that finds no room is redone in the hash layout).
     ctx->no_minimizer = false;
     u32 want = std::min(choose_bits(ctx->n_keys, (u32)ctx->values.size()), ctx->bucket_bits);
-    while(want <= ctx->bucket_bits) {
+    const u32 built_bits = ctx->bucket_bits;
+    cudaStream_t st = ctx->slots[0].st;
+    const u64 n = ctx->n_keys;
+    u64 *dk = nullptr;
+    u32 *dv = nullptr;
+    bool dumped = false;
+    auto cleanup = [&](int code) { if(dk) cudaFree(dk); if(dv) cudaFree(dv); return code; };
+    while(want <= built_bits) {
         const bool mini = want_minimizer_layout(ctx, want);
-        if(want == ctx->bucket_bits && !mini && ctx->layout == LAYOUT_HASH) break;   // already there
+        if(!dumped && want == ctx->bucket_bits && !mini && ctx->layout == LAYOUT_HASH) break;   // already there
+        if(!dumped) {                                                     // the built table as pairs, once, for every attempt below
+            cudaError_t e;
+            if((e = cudaMalloc((void **)&dk, std::max<u64>(n, 1) * 8)) != cudaSuccess || (e = cudaMalloc((void **)&dv, std::max<u64>(n, 1) * 4)) != cudaSuccess ||
+               (e = cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st)) != cudaSuccess ||
+               (e = launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, n, ctx->d_counters + 12)) != cudaSuccess ||
+               (e = cudaStreamSynchronize(st)) != cudaSuccess)
+                return cleanup(ctx->cuda_fail(e, "dumping the built table"));
+            ++ctx->stats.kernel_launches;
+            dumped = true;
+        }
         const TableFmt nf = fmt_for(ctx, want, mini);
-        cudaStream_t st = ctx->slots[0].st;
-        const u64 n = ctx->n_keys;
-        u64 *dk = nullptr, *new_slots = nullptr;
-        u32 *dv = nullptr;
+        u64 *new_slots = nullptr;
         unsigned long long h2[3];
+        if(mini && (rc = ensure_fail_list(ctx)) != BNS_OK) return cleanup(rc);
         auto rehome = [&]() -> cudaError_t {
             cudaError_t e;
-            if((e = cudaMalloc((void **)&dk, std::max<u64>(n, 1) * 8)) != cudaSuccess) return e;
-            if((e = cudaMalloc((void **)&dv, std::max<u64>(n, 1) * 4)) != cudaSuccess) return e;
             if((e = cudaMalloc((void **)&new_slots, (1ull << want) * 32)) != cudaSuccess) return e;
             if((e = cudaMemsetAsync(new_slots, 0xff, (1ull << want) * 32, st)) != cudaSuccess) return e;
-            if((e = cudaMemsetAsync(ctx->d_counters + 12, 0, 4 * sizeof(unsigned long long), st)) != cudaSuccess) return e;
-            if((e = launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, n, ctx->d_counters + 12)) != cudaSuccess) return e;
-            if((e = launch_insert(st, new_slots, nf, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13)) != cudaSuccess) return e;
-            ctx->stats.kernel_launches += 2;
+            if((e = cudaMemsetAsync(ctx->d_counters + 13, 0, 3 * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+            if((e = launch_insert(st, new_slots, nf, dk, dv, n, ctx->d_values, (u32)ctx->values.size(), ctx->d_counters + 13,
+                                  mini ? ctx->d_fail_k : nullptr, ctx->d_fail_v, FAIL_CAP)) != cudaSuccess) return e;
+            ++ctx->stats.kernel_launches;
             if((e = cudaMemcpyAsync(h2, ctx->d_counters + 13, sizeof h2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
             return cudaStreamSynchronize(st);
         };
         const cudaError_t re = rehome();
-        if(dk) cudaFree(dk);
-        if(dv) cudaFree(dv);
-        if(re != cudaSuccess) { if(new_slots) cudaFree(new_slots); return ctx->cuda_fail(re, "re-homing the built table"); }
+        if(re != cudaSuccess) { if(new_slots) cudaFree(new_slots); return cleanup(ctx->cuda_fail(re, "re-homing the built table")); }
+        if(!h2[2] && (rc = settle_failures(ctx, h2, n, mini ? (int)LAYOUT_MINIMIZER : (int)LAYOUT_HASH)) != BNS_OK) { cudaFree(new_slots); return cleanup(rc); }
         if(h2[0] || h2[2]) {                                              // no room
             cudaFree(new_slots);
             if(mini) ctx->no_minimizer = true;                            // same size, hash layout
@@ -913,10 +982,10 @@ int bns_b200_build_finish(bns_b200_t *ctx) {
         adopt_fmt(ctx, nf);
         ctx->n_displaced = h2[1];
         rc = refresh_table_stats(ctx);
-        if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return rc;
+        if(rc != BNS_OK || !minimizer_build_too_crowded(ctx)) return cleanup(rc);
         ctx->no_minimizer = true;                                         // same size, hash layout
     }
-    return BNS_OK;
+    return cleanup(BNS_OK);
 }
 
 int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out, uint64_t cap, uint64_t *n_out) {
@@ -935,6 +1004,10 @@ int bns_b200_table_dump(bns_b200_t *ctx, uint64_t *keys_out, uint32_t *vals_out,
         if((e = cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
         if((e = launch_dump(st, ctx->d_slots, ctx->n_buckets, table_fmt(ctx), ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12)) != cudaSuccess) return e;
         ++ctx->stats.kernel_launches;
+        if(ctx->d_stash) {                                                 // ... and the stash, behind them
+            if((e = launch_dump(st, ctx->d_stash, 1ull << ctx->stash_bits, stash_fmt(ctx), ctx->d_values, dk, dv, ctx->n_keys, ctx->d_counters + 12)) != cudaSuccess) return e;
+            ++ctx->stats.kernel_launches;
+        }
         if((e = cudaMemcpyAsync(keys_out, dk, ctx->n_keys * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if((e = cudaMemcpyAsync(vals_out, dv, ctx->n_keys * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         return cudaStreamSynchronize(st);
@@ -1032,6 +1105,8 @@ int bns_b200_db_export_header(const bns_b200_t *ctx_, bns_b200_db_header *hdr) {
     hdr->words[11] = ctx->fmt_bits;
     hdr->words[12] = ctx->table_k;
     hdr->words[13] = ctx->disp_bits;
+    hdr->words[14] = ctx->d_stash ? ((u64)ctx->stash_bits | ((u64)ctx->stash_flags << 8)) : 0;
+    hdr->words[15] = ctx->n_stash;
     return BNS_OK;
 }
 
@@ -1055,6 +1130,11 @@ int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr
     ctx->flag_count = (u32)hdr->words[9];
     if(!ctx->flag_count || (ctx->flag_count & (ctx->flag_count - 1)) || ctx->fmt_bits < ctx->disp_bits + ctx->flag_count)
         return ctx->fail(BNS_E_INVAL, "database header: bad slot format");
+    if(hdr->words[14]) {
+        ctx->stash_bits = (u32)(hdr->words[14] & 0xff); ctx->stash_flags = (u32)(hdr->words[14] >> 8); ctx->n_stash = hdr->words[15];
+        if(ctx->stash_bits > 32 || !ctx->stash_flags) return ctx->fail(BNS_E_INVAL, "database header: bad stash format");
+        CK(cudaMalloc((void **)&ctx->d_stash, 32ull << ctx->stash_bits));
+    }
     CK(cudaMalloc((void **)&ctx->d_values, std::max<size_t>(ctx->values.size(), 1) * sizeof(u32)));
     CK(cudaMalloc((void **)&ctx->d_val_info, std::max<size_t>(ctx->values.size(), 1) * sizeof(uint4)));
     CK(cudaMalloc((void **)&ctx->d_node_info, std::max<u32>(ctx->n_nodes, 1) * sizeof(uint4)));
@@ -1070,6 +1150,8 @@ int bns_b200_db_segments(const bns_b200_t *ctx, void **dev_ptrs, uint64_t *bytes
     dev_ptrs[2] = ctx->d_val_info;  bytes[2] = ctx->values.size() * sizeof(uint4);
     dev_ptrs[3] = ctx->d_node_info; bytes[3] = (uint64_t)ctx->n_nodes * sizeof(uint4);
     *n = 4;
+    if(ctx->d_stash && cap >= 5) { dev_ptrs[4] = ctx->d_stash; bytes[4] = 32ull << ctx->stash_bits; *n = 5; }
+    else if(ctx->d_stash) return BNS_E_CAPACITY;
     return BNS_OK;
 }
 
@@ -1173,19 +1255,20 @@ int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
     // topology discovery per process, which a short `bonsai classify --gpus N` run feels; the broadcast itself is milliseconds.
     if(const char *how = getenv("BNS_B200_REPLICATE")) {
         if(!strcmp(how, "p2p")) {
-            std::vector<void *> ptrs((size_t)n * 4);
-            uint64_t bytes[4] = {0, 0, 0, 0};
+            std::vector<void *> ptrs((size_t)n * 8);
+            uint64_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int nseg = 0;
             for(int i = 0; i < n; ++i) {
-                uint64_t b[4]; int ns = 0;
-                rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 4], b, 4, &ns);
-                if(rc != BNS_OK || ns != 4) return ctx->fail(BNS_E_STATE, "replica %d has no segments", i);
-                if(i == root) for(int s = 0; s < 4; ++s) bytes[s] = b[s];
+                uint64_t b[8]; int ns = 0;
+                rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 8], b, 8, &ns);
+                if(rc != BNS_OK || ns < 4) return ctx->fail(BNS_E_STATE, "replica %d has no segments", i);
+                if(i == root) { nseg = ns; for(int s = 0; s < ns; ++s) bytes[s] = b[s]; }
             }
             for(int i = 0; i < n; ++i) {
                 if(i == root) continue;
-                for(int s = 0; s < 4; ++s)
+                for(int s = 0; s < nseg; ++s)
                     if(bytes[s]) {
-                        const cudaError_t e = cudaMemcpyPeerAsync(ptrs[(size_t)i * 4 + s], handles[i]->device, ptrs[(size_t)root * 4 + s], ctx->device,
+                        const cudaError_t e = cudaMemcpyPeerAsync(ptrs[(size_t)i * 8 + s], handles[i]->device, ptrs[(size_t)root * 8 + s], ctx->device,
                                                                   (size_t)bytes[s], ctx->slots[0].st);
                         if(e != cudaSuccess) return ctx->cuda_fail(e, "cudaMemcpyPeerAsync");
                     }
@@ -1217,20 +1300,21 @@ int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
         for(int i = 0; i < n; ++i) if(comms[(size_t)i]) nc.CommDestroy(comms[(size_t)i]);
         return code;
     };
-    std::vector<void *> ptrs((size_t)n * 4);
-    uint64_t bytes[4] = {0, 0, 0, 0};
+    std::vector<void *> ptrs((size_t)n * 8);
+    uint64_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nseg = 0;
     for(int i = 0; i < n; ++i) {
-        uint64_t b[4]; int ns = 0;
-        rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 4], b, 4, &ns);
-        if(rc != BNS_OK || ns != 4) return done(ctx->fail(BNS_E_STATE, "replica %d has no segments", i));
-        if(i == root) for(int s = 0; s < 4; ++s) bytes[s] = b[s];
+        uint64_t b[8]; int ns = 0;
+        rc = bns_b200_db_segments(handles[i], &ptrs[(size_t)i * 8], b, 8, &ns);
+        if(rc != BNS_OK || ns < 4) return done(ctx->fail(BNS_E_STATE, "replica %d has no segments", i));
+        if(i == root) { nseg = ns; for(int s = 0; s < ns; ++s) bytes[s] = b[s]; }
     }
-    for(int s = 0; s < 4 && nr == ncclSuccess; ++s) {                       // one broadcast per segment, every rank of it in one group
+    for(int s = 0; s < nseg && nr == ncclSuccess; ++s) {                    // one broadcast per segment, every rank of it in one group
         if(!bytes[s]) continue;
         nc.GroupStart();
         for(int i = 0; i < n; ++i) {
             cudaSetDevice(handles[i]->device);
-            const ncclResult_t r = nc.Broadcast(ptrs[(size_t)root * 4 + s], ptrs[(size_t)i * 4 + s], (size_t)bytes[s], ncclChar, root,
+            const ncclResult_t r = nc.Broadcast(ptrs[(size_t)root * 8 + s], ptrs[(size_t)i * 8 + s], (size_t)bytes[s], ncclChar, root,
                                                 comms[(size_t)i], handles[i]->slots[0].st);
             if(r != ncclSuccess) nr = r;
         }

@@ -69,9 +69,10 @@ __device__ __forceinline__ u32 probe_displaced32(const ProbeConst Pc, u32 home, 
     return ~tl0;
 }
 // the overflow chain of ONE key of a LAYOUT_MINIMIZER table: 64-byte units from a scrambled image of the home unit on
-__device__ __forceinline__ u32 probe_chain_loc(const ProbeConst Pc, u32 home, u32 th, u32 tl0) {
+__device__ __forceinline__ u32 probe_chain_loc(const ProbeConst Pc, u32 home, u32 th, u32 tl0, bool &exhausted) {
     const u32 ub = Pc.b - 1, umask = (1u << ub) - 1;
     const u32 u0 = nmix(home >> 1, ub);
+    exhausted = false;
     for(u32 d = 1; d <= Pc.max_disp; ++d) {
         u32 w[16];
         const char *up = Pc.slots + ((u64)((u0 + (d - 1)) & umask) << 6);
@@ -81,8 +82,9 @@ __device__ __forceinline__ u32 probe_chain_loc(const ProbeConst Pc, u32 home, u3
 #pragma unroll
         for(int j = 0; j < 8; ++j)
             if(w[2 * j + 1] == th && ((w[2 * j] ^ tl) & Pc.hm) == 0) return w[2 * j];
-        if((w[14] & w[15]) == ~0u) break;                             // a unit with a free slot ends the run
+        if((w[14] & w[15]) == ~0u) return ~tl0;                       // a unit with a free slot ends the run
     }
+    exhausted = true;                                                 // full to its end: the key may sit in the stash
     return ~tl0;
 }
 
@@ -637,7 +639,13 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             const u32 t = base + lane;
                             if(t < tot) {
                                 const uint4 e = q[t];
-                                q[t].w = probe_chain_loc(Pc, e.x, e.y, e.z);
+                                bool exhausted;
+                                u32 c = probe_chain_loc(Pc, e.x, e.y, e.z, exhausted);
+                                if(exhausted && T.stash) {
+                                    const u32 v = probe_stash(T, loc_decode(e.x, ((u64)e.y << 32) | e.z, k, Pc.b));
+                                    if(v != VAL_MISS) c = (e.z & Pc.hm) | v;
+                                }
+                                q[t].w = c;
                             }
                         }
                         __syncwarp();

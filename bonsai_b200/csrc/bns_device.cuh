@@ -37,7 +37,7 @@ constexpr int PPL = 4;           // positions per lane
 constexpr int CMAX = 256;        // largest comb (spaced span) supported
 constexpr int AGG_CAP = 256;     // distinct taxa tracked per record in shared memory (covers any read up to k+255 bases)
 constexpr int DISP_BITS = 4;     // slot displacement field of LAYOUT_HASH; disp == 2^bits - 1 is reserved for the empty slot
-constexpr int DISP_BITS_LOC = 6; // LAYOUT_MINIMIZER: probes are 64-byte units; chains of up to 62 units
+constexpr int DISP_BITS_LOC = 3; // LAYOUT_MINIMIZER: probes are 64-byte units; chains of up to 6 units, then the stash
 
 struct EncParams {
     u32 k, c, W;                 // W = w_ - c_ + 1  (QueueMap size, encoder.h:142)
@@ -92,7 +92,20 @@ struct TableView {
     u32 flag_shift;              // tag_shift - F: the F overflow flags of slot 0 sit at [flag_shift, tag_shift)
     u32 flag_mask;               // F - 1 (F is a power of two): a key's flag is bit flag_shift + (flag selector & flag_mask)
     TableFmt fmt;
+    // LAYOUT_MINIMIZER only: the keys whose overflow chain was full to its end (repeated minimizers of real genomes crowd
+    // single groups) live in a small LAYOUT_HASH table of the same value ids, probed after an exhausted chain
+    const u64 *stash;
+    TableFmt sfmt;
 };
+// the stash as a table of its own
+__host__ __device__ inline TableView stash_view(const TableView &T) {
+    TableView S;
+    S.slots = T.stash; S.bucket_bits = T.sfmt.b; S.fmt = T.sfmt;
+    S.tag_shift = T.sfmt.tag_shift(); S.flag_shift = T.sfmt.flag_shift(); S.flag_mask = T.sfmt.F - 1;
+    S.val_mask = (1u << S.flag_shift) - 1; S.n_values = T.n_values;
+    S.stash = nullptr; S.sfmt = T.sfmt;
+    return S;
+}
 
 // Overflow flags. A key that found its home bucket full is stored in a later bucket and CLEARS, in slot 0 of the home
 // bucket, the one of F flag bits its hash selects (an empty slot is all ones and so reads "nothing displaced"). A lookup

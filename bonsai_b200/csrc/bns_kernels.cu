@@ -229,13 +229,16 @@ __device__ __forceinline__ u32 match_probe(const TableView &T, u64 bucket, u64 t
     }
     return v;
 }
-// probes after the home probe (rare: the home probe was full when the table was built)
-__device__ __noinline__ u32 probe_displaced(const TableView T, u64 home, u64 tag) {
+// probes after the home probe (rare: the home probe was full when the table was built). exhausted: the chain was full to its
+// end -- a LAYOUT_MINIMIZER key may then sit in the stash.
+__device__ __noinline__ u32 probe_displaced(const TableView T, u64 home, u64 tag, bool *exhausted = nullptr) {
+    if(exhausted) *exhausted = false;
     for(u32 d = 1; d <= T.fmt.max_disp(); ++d) {
         u32 fw; bool last_free;
         const u32 v = match_probe(T, probe_bucket(T.fmt.layout, home, d, T.fmt.b), tag | ((u64)d << T.tag_shift), fw, last_free);
         if(v != VAL_MISS || last_free) return v;                   // a probe with a free slot ends the run
     }
+    if(exhausted) *exhausted = true;
     return VAL_MISS;
 }
 // Home-bucket test relying on the build-time invariant that no two entries of a bucket share their upper 32 bits
@@ -248,6 +251,17 @@ __device__ __forceinline__ u32 match4_home(const TableView &T, u64 tag, u64 s0, 
     const bool ok = (m0 | m1 | m2 | m3) && (((cand ^ tl) & hm) == 0);            // an empty slot (disp 15) never passes
     return ok ? (cand & T.val_mask) : VAL_MISS;
 }
+// the stash of a LAYOUT_MINIMIZER table: an ordinary LAYOUT_HASH probe
+__device__ __noinline__ u32 probe_stash(const TableView T, u64 key) {
+    const TableView S = stash_view(T);
+    bool possible;
+    const TableHash h = table_hash(S.fmt, key, possible);
+    u64 a, b, c, d;
+    ld_bucket(S.slots + (h.home << 2), a, b, c, d);
+    u32 v = match4_home(S, h.tag, a, b, c, d);
+    if(v == VAL_MISS && !(((u32)a >> (S.flag_shift + (h.fsel & S.flag_mask))) & 1u)) v = probe_displaced(S, h.home, h.tag);
+    return v;
+}
 // kh_get + kh_val for one key (generic kernels: lookup, the stream kernels of LAYOUT_MINIMIZER tables)
 __device__ __forceinline__ u32 probe_key(const TableView &T, u64 key) {
     bool possible;
@@ -257,7 +271,11 @@ __device__ __forceinline__ u32 probe_key(const TableView &T, u64 key) {
     const u32 v = match_probe(T, probe_bucket(T.fmt.layout, h.home, 0, T.fmt.b), h.tag, fw, last_free);
     // The overflow mark is a CLEARED bit in slot 0 of a full home probe (an empty slot is all ones, so an empty or
     // part-filled one reads "no overflow"): a miss costs one probe unless a key homed there was displaced.
-    if(v == VAL_MISS && !((fw >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) return probe_displaced(T, h.home, h.tag);
+    if(v == VAL_MISS && !((fw >> (T.flag_shift + (h.fsel & T.flag_mask))) & 1u)) {
+        bool exhausted;
+        const u32 v2 = probe_displaced(T, h.home, h.tag, &exhausted);
+        return (v2 == VAL_MISS && exhausted && T.stash) ? probe_stash(T, key) : v2;
+    }
     return v;
 }
 // kh_get + kh_val for PPL keys per lane: all home-bucket sectors are requested before any is inspected. Lanes / slots
@@ -893,7 +911,10 @@ bns_classify_kernel(const __grid_constant__ EncParams P, const char *__restrict_
 // stop after one sector otherwise.
 __global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u64 *__restrict__ keys,
                                   const u32 *__restrict__ vals, u64 n, const u32 *__restrict__ values, u32 n_values,
-                                  unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */) {
+                                  unsigned long long *__restrict__ stats /* [0] failed, [1] displaced, [2] bad value */,
+                                  u64 *__restrict__ fail_keys, u32 *__restrict__ fail_vals, u64 fail_cap) {
+    // fail_keys != nullptr: the (key, value) pairs that found no room are listed there (the first fail_cap of them): the
+    // stash of a LAYOUT_MINIMIZER table is built from that list
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     const u64 key = keys[i];
@@ -923,7 +944,8 @@ __global__ void bns_insert_kernel(u64 *__restrict__ slots, TableFmt fmt, const u
         }
         if(d == 0) atomicAnd((unsigned long long *)&bk[0], ~(1ull << (flag_shift + (th.fsel & (F - 1)))));
     }
-    atomicAdd(&stats[0], 1ull);
+    const unsigned long long at = atomicAdd(&stats[0], 1ull);
+    if(fail_keys && at < fail_cap) { fail_keys[at] = key; fail_vals[at] = vals[i]; }
 }
 
 __global__ void bns_table_stats_kernel(const u64 *__restrict__ slots, u64 n_buckets, TableFmt fmt,
@@ -1307,9 +1329,9 @@ cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, const 
     return cudaGetLastError();
 }
 cudaError_t launch_insert(cudaStream_t st, u64 *slots, const TableFmt &fmt, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
-                          u32 n_values, unsigned long long *stats) {
+                          u32 n_values, unsigned long long *stats, u64 *fail_keys, u32 *fail_vals, u64 fail_cap) {
     if(!n) return cudaSuccess;
-    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, fmt, keys, vals, n, values, n_values, stats);
+    bns_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slots, fmt, keys, vals, n, values, n_values, stats, fail_keys, fail_vals, fail_cap);
     return cudaGetLastError();
 }
 cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, unsigned long long *out) {

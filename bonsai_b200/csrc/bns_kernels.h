@@ -45,7 +45,7 @@ cudaError_t launch_build(const EncParams &P, int grid, size_t smem, cudaStream_t
 cudaError_t launch_dump(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, const u32 *dict, u64 *keys_out, u32 *vals_out,
                         u64 cap, unsigned long long *counter);
 cudaError_t launch_insert(cudaStream_t st, u64 *slots, const TableFmt &fmt, const u64 *keys, const u32 *vals, u64 n, const u32 *values,
-                          u32 n_values, unsigned long long *stats);
+                          u32 n_values, unsigned long long *stats, u64 *fail_keys = nullptr, u32 *fail_vals = nullptr, u64 fail_cap = 0);
 cudaError_t launch_table_stats(cudaStream_t st, const u64 *slots, u64 n_buckets, const TableFmt &fmt, unsigned long long *out);
 cudaError_t launch_lookup(cudaStream_t st, const TableView &T, const u32 *dict, const u64 *keys, u64 n, u32 *vals_out,
                           uint8_t *found_out);

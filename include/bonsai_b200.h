@@ -77,8 +77,9 @@ typedef struct bns_b200_table_info {
     uint32_t bucket_bits, val_bits, n_values, max_disp;
     uint64_t n_displaced;       /* entries not in their home bucket */
     uint64_t n_overflowed;      /* home buckets with the overflow mark */
-    uint32_t layout;            /* 0 hash (bucket = mix64), 1 minimizer (128-byte line by the k-mer's 15-mer minimizer) */
+    uint32_t layout;            /* 0 hash (bucket = mix64), 1 minimizer (group of four 64-byte units by the k-mer's 16-mer minimizer) */
     uint32_t disp_bits;         /* width of the slot's displacement field */
+    uint64_t n_stash;           /* layout 1: entries kept in the overflow stash (keys whose probe chain was full) */
 } bns_b200_table_info;
 
 typedef struct bns_b200_stats {
@@ -151,7 +152,7 @@ int bns_b200_resolve_batch(bns_b200_t *ctx, const uint32_t *taxa, const uint16_t
 typedef struct bns_b200_db_header { uint64_t words[16]; } bns_b200_db_header;
 int bns_b200_db_export_header(const bns_b200_t *ctx, bns_b200_db_header *hdr);
 int bns_b200_db_alloc_from_header(bns_b200_t *ctx, const bns_b200_db_header *hdr);
-/* device segments that make up the database: fills up to `cap` (ptr, bytes) pairs, returns the count in *n */
+/* device segments that make up the database: fills up to `cap` (ptr, bytes) pairs (cap >= 5), returns the count in *n */
 int bns_b200_db_segments(const bns_b200_t *ctx, void **dev_ptrs, uint64_t *bytes, int cap, int *n);
 int bns_b200_db_commit(bns_b200_t *ctx);
 

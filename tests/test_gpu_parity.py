@@ -743,6 +743,52 @@ def test_minimizer_layout_vs_oracle(capi, oracle, toy_tax, monkeypatch):
     oracle.db_free(D)
 
 
+def test_minimizer_layout_real_genomes_use_the_stash(capi, oracle, dbcache, toy_tax, reads2000, monkeypatch):
+    """The 10.5 M canonical 31-mers of the four genomes in the minimizer layout: repeated 16-mers crowd single groups, the keys
+    whose six-unit chain is full go to the stash (a small hash-layout table) instead of sending the whole table back to the
+    hash layout. Every key is found with its value, absent keys are not, the dump is the key set, classification is the
+    oracle's -- also on a replica made from the exported segments."""
+    monkeypatch.setenv("BNS_B200_LAYOUT", "minimizer")
+    db = dbcache.get("lex_k31_w31")
+    keys, vals = oracle.db_pairs(db)
+    c, p = H.toy_tax_arrays()
+    bases, offs, _ = reads2000
+    exp = oracle.classify(db, toy_tax, bases, offs, 31, 31, want_taxa=True)
+    with capi.Context(31, 31) as ctx:
+        ctx.load_pairs(keys, vals)
+        ctx.load_taxonomy(c, p)
+        info = ctx.table_info()
+        assert info["layout"] == 1 and info["n_stash"] > 0 and info["n_keys"] == keys.size, info
+        assert info["max_disp"] <= 6
+        gv, gf = ctx.lookup(keys)
+        assert gf.all() and np.array_equal(gv, vals)
+        rng = np.random.default_rng(4)
+        probe = rng.integers(0, 1 << 62, 300000, dtype=np.uint64)
+        pv, pf = ctx.lookup(probe)
+        assert np.array_equal(pf, np.isin(probe, keys))
+        dk, dv = ctx.table_dump()
+        assert np.array_equal(dk, keys) and np.array_equal(dv, vals)
+        got = ctx.classify(bases, offs)
+        assert all(np.array_equal(a, b) for a, b in zip(exp[:3], got))
+        full = ctx.classify(bases, offs, want_taxa=True)
+        assert all(np.array_equal(a, b) for a, b in zip(exp[3], full[3]))
+        t, h, m, runs = ctx.classify_runs(bases, offs)
+        assert np.array_equal(t, exp[0]) and all(np.array_equal(rn, _rle(x)) for rn, x in zip(runs, exp[3]))
+        # a replica from the exported header + segments (the stash is the fifth segment)
+        import torch
+        with capi.Context(31, 31) as rep:
+            rep.db_alloc_from_header(ctx.db_export_header())
+            segs_a, segs_b = ctx.db_segments(), rep.db_segments()
+            assert len(segs_a) == 5 and [n for _, n in segs_a] == [n for _, n in segs_b]
+            for (pa, na), (pb, nb) in zip(segs_a, segs_b):
+                torch.as_tensor(capi.DevMem(pb, nb), device="cuda").copy_(torch.as_tensor(capi.DevMem(pa, na), device="cuda"))
+            torch.cuda.synchronize()
+            rep.db_commit()
+            assert rep.table_info()["n_stash"] == info["n_stash"]
+            got = rep.classify(bases, offs)
+            assert all(np.array_equal(a, b) for a, b in zip(exp[:3], got))
+
+
 # ---- the call-by-call Encoder surface (BNS_API_ITER) ---------------------------------------------------------------
 def test_iterator_surface_golden_and_fuzz(capi, oracle):
     """assign / has_next_kmer / next_minimizer / next_canonicalized_minimizer (encoder.h:201-206,594-628) as one unfiltered
