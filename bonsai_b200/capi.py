@@ -26,7 +26,7 @@ SYMBOLS = [
     "bns_b200_db_alloc_from_header", "bns_b200_db_segments", "bns_b200_db_commit", "bns_b200_encode_batch",
     "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_batch_runs", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
-    "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi", "bns_b200_device_status",
+    "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi", "bns_b200_device_status", "bns_b200_classify_device_runs",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library(path=None):
     lib.bns_b200_classify_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.bns_b200_sync.argtypes = [vp]
     lib.bns_b200_device_status.argtypes = [vp]
+    lib.bns_b200_classify_device_runs.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp]
     lib.bns_b200_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.bns_b200_stats_reset.argtypes = [vp]
     lib.bns_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -371,6 +372,12 @@ class Context:
         """All arguments are raw device pointers (ints); asynchronous on `stream`."""
         self._ck(self.lib.bns_b200_classify_device(self.h, d_bases, d_offsets, n_reads, int(paired), d_taxon, d_nhit or None,
                                                    d_nmiss or None, d_taxa or None, d_taxa_offsets or None, stream or None))
+
+    def classify_device_runs(self, d_bases, d_offsets, n_reads, d_taxon, d_nhit, d_runs, runs_cap, d_run_pos, d_nruns, d_total, d_nmiss=0,
+                             paired=False, stream=0):
+        """bns_b200_classify_device_runs: raw device pointers (ints); asynchronous on `stream`."""
+        self._ck(self.lib.bns_b200_classify_device_runs(self.h, d_bases, d_offsets, n_reads, int(paired), d_taxon, d_nhit, d_nmiss or None,
+                                                        d_runs, runs_cap, d_run_pos, d_nruns, d_total, stream or None))
 
     def sync(self):
         self._ck(self.lib.bns_b200_sync(self.h))

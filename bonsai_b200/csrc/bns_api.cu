@@ -1423,6 +1423,41 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
     return BNS_OK;
 }
 
+int bns_b200_classify_device_runs(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
+                                  uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing, uint64_t *d_runs, uint64_t runs_cap,
+                                  uint64_t *d_run_pos, uint32_t *d_n_runs, uint64_t *d_runs_total, void *stream) {
+    if(!ctx || !d_offsets || !d_taxon || !d_n_hit || !d_runs || !d_run_pos || !d_n_runs || !d_runs_total)
+        return ctx ? ctx->fail(BNS_E_INVAL, "null buffers") : BNS_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = classify_ready(ctx);
+    if(rc != BNS_OK) return rc;
+    const u32 mates = paired ? 2 : 1;
+    const u64 n_rec = n_reads / mates;
+    if(!n_rec) return BNS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ClassifyPlan pl = plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec, mates, true, false, true, true);
+    if(!pl.runs) return ctx->fail(BNS_E_INVAL, "this encoder's run lists come from bns_b200_classify_batch_runs (host buffers)");
+    Slot &s0 = ctx->slots[0];
+    if(pl.second_pass) {
+        rc = ensure(s0.d_defer, s0.cap_defer, n_rec);
+        if(rc == BNS_OK) rc = ensure(ctx->d_big, ctx->cap_big, pass2_scratch_words(pl));
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        CK(cudaMemsetAsync(s0.d_defer_cnt, 0, sizeof(unsigned long long), st));
+    }
+    CK(cudaMemsetAsync(d_runs_total, 0, sizeof(unsigned long long), st));
+    int nl = 1;
+    const RunsOut ro{(u64 *)d_runs, runs_cap, (unsigned long long *)d_runs_total, (u64 *)d_run_pos, d_n_runs};
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_classify(ctx->enc, pl, st, d_bases, (const u64 *)d_offsets, n_rec, mates, ~0ull, table_view(ctx), tax_view(ctx), d_taxon, d_n_hit,
+                       d_n_missing, nullptr, nullptr, nullptr, ctx->ring_cap, ctx->d_counters, ctx->d_status, s0.d_defer, s0.d_defer_cnt, &nl, &ro,
+                       ctx->d_big));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->stats.kernel_launches += nl;
+    ctx->stats.reads_processed += n_reads;
+    ctx->timed = true;
+    return BNS_OK;
+}
+
 int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                             uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
                             uint32_t *taxa_out, const uint64_t *taxa_offsets) {

@@ -207,6 +207,12 @@ int bns_b200_classify_device(bns_b200_t *ctx, const char *d_bases, const uint64_
                              uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing,
                              uint32_t *d_taxa, const uint64_t *d_taxa_offsets, void *stream);
 
+/* classify_device with the run lists of bns_b200_classify_batch_runs, every buffer on the device: d_runs (runs_cap entries; bases
+ * + 2 per record + 2^21 always suffice), d_run_pos / d_n_runs per record, *d_runs_total = entries used (zeroed by the call).
+ * For the encoders whose runs the lean kernel produces (every k-mer, no window: what `bonsai classify` runs); BNS_E_INVAL else. */
+int bns_b200_classify_device_runs(bns_b200_t *ctx, const char *d_bases, const uint64_t *d_offsets, uint64_t n_reads, int paired,
+                                  uint32_t *d_taxon, uint32_t *d_n_hit, uint32_t *d_n_missing, uint64_t *d_runs, uint64_t runs_cap,
+                                  uint64_t *d_run_pos, uint32_t *d_n_runs, uint64_t *d_runs_total, void *stream);
 int bns_b200_device_status(bns_b200_t *ctx);
 int bns_b200_sync(bns_b200_t *ctx);
 int bns_b200_stats_get(const bns_b200_t *ctx, bns_b200_stats *out);

@@ -753,9 +753,18 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     if(nthreads == 1) { format_range(0, nrec, cks); return; }
     std::vector<std::string> parts(nthreads);
     std::vector<std::thread> pool;
+    // a line is a few dozen bytes (plus the sequence and quality in FASTQ style): one allocation per slice instead of doublings
+    const size_t per_rec = (c.output_flag_ & FASTQ) ? 96 + 2 * (size_t)((offs[nrec * inc] - offs[0]) / nrec + 2) * inc : ((c.output_flag_ & KRAKEN) ? 96 : 0);
     for(unsigned t = 0; t < nthreads; ++t)
-        pool.emplace_back([&, t] { format_range((unsigned)((u64)nrec * t / nthreads), (unsigned)((u64)nrec * (t + 1) / nthreads), parts[t]); });
+        pool.emplace_back([&, t] {
+            const unsigned lo = (unsigned)((u64)nrec * t / nthreads), hi = (unsigned)((u64)nrec * (t + 1) / nthreads);
+            parts[t].reserve((size_t)(hi - lo) * per_rec);
+            format_range(lo, hi, parts[t]);
+        });
     for(auto &th : pool) th.join();
+    size_t total = cks.size();
+    for(auto &part : parts) total += part.size();
+    cks.reserve(total);
     for(auto &part : parts) cks += part;
 }
 
@@ -1114,12 +1123,23 @@ struct SimpleFile {
         std::vector<char> good(T, 1);
         std::vector<std::thread> pool;
         for(unsigned t = 0; t < T; ++t)
-            pool.emplace_back([&, t] { good[t] = index_range(p, cut[t], cut[t + 1], n, fastq, part[t]); });
+            pool.emplace_back([&, t] {
+                part[t].reserve((cut[t + 1] - cut[t]) / 96 + 64);          // ~ one record per 100-300 bytes of text: few regrowths
+                good[t] = index_range(p, cut[t], cut[t + 1], n, fastq, part[t]);
+            });
         for(auto &th : pool) th.join();
+        size_t total = 0;
+        std::vector<size_t> at(T + 1, 0);
         for(unsigned t = 0; t < T; ++t) {
             if(!good[t]) { recs.clear(); return false; }
-            recs.insert(recs.end(), part[t].begin(), part[t].end());
+            at[t + 1] = (total += part[t].size());
         }
+        // the parts become one array without a serial pass over it
+        recs.resize(total);
+        pool.clear();
+        for(unsigned t = 0; t < T; ++t)
+            pool.emplace_back([&, t] { if(!part[t].empty()) std::memcpy(recs.data() + at[t], part[t].data(), part[t].size() * sizeof(RecRef)); });
+        for(auto &th : pool) th.join();
         return true;
     }
     // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
@@ -1173,42 +1193,55 @@ struct SimpleFile {
 inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f, SimpleFile *f2 = nullptr) {
     b.clear();
     b.refs.clear();
-    u64 size = 0;
     auto have = [](SimpleFile &x) { return x.next_rec < x.recs.size() || x.refill(); };
-    // a batch points into ONE window per file: with gzip input it ends where a window does
-    auto at_window_end = [](SimpleFile &x) { return x.gz && x.next_rec >= x.recs.size(); };
-    for(;;) {
-        if(!b.refs.empty() && (at_window_end(f) || (f2 && at_window_end(*f2)))) break;
-        if(!have(f) || (f2 && !have(*f2))) break;                     // either file is out of indexed records: the caller hands over to kseq
-        const RecRef &r = f.recs[f.next_rec++];
-        b.refs.push_back(r);
-        size += r.seq_len;
-        if(f2) {
-            const RecRef &r2 = f2->recs[f2->next_rec++];
-            b.refs.push_back(r2);
-            size += r2.seq_len;
-        }
-        if((long)size >= chunk_size && (b.refs.size() & 1) == 0) break;
+    if(!have(f) || (f2 && !have(*f2))) return false;                  // either file is out of indexed records: the caller hands over to kseq
+    // the batch's records: a stretch [s1, e1) of file 1's window (and [s2, e2) of the mates' file), found by one read-only pass
+    // over the sequence lengths; a batch points into ONE window per file, so it also ends where a window does
+    const size_t s1 = f.next_rec, s2 = f2 ? f2->next_rec : 0;
+    const size_t avail = f2 ? std::min(f.recs.size() - s1, f2->recs.size() - s2) : f.recs.size() - s1;
+    u64 size = 0;
+    size_t take = 0;
+    while(take < avail) {
+        size += f.recs[s1 + take].seq_len;
+        if(f2) size += f2->recs[s2 + take].seq_len;
+        ++take;
+        const size_t nrec = f2 ? 2 * take : take;
+        if((long)size >= chunk_size && (nrec & 1) == 0) break;
     }
-    const size_t n = b.refs.size();
+    f.next_rec += take;
+    if(f2) f2->next_rec += take;
+    const size_t n = f2 ? 2 * take : take;
     if(!n) return false;
     b.map = f.text(); b.keep = f.hold;
     b.map2 = f2 ? f2->text() : nullptr;
     if(f2) b.keep2 = f2->hold;
     PinnedBatch::grow(b.bases, b.cap_bases, 0, size + 16);
     PinnedBatch::grow(b.offs, b.cap_offs, 0, n + 2);
-    b.offs[0] = 0;
-    for(size_t i = 0; i < n; ++i) b.offs[i + 1] = b.offs[i] + b.refs[i].seq_len;
+    b.refs.resize(n);
+    // two parallel passes over the stretch: bases per slice, then (with every slice's first offset known) the records' offsets,
+    // their references and the sequence bytes themselves
     const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(f.nthreads, n / 8192 + 1));
-    auto copy = [&](size_t lo, size_t hi) {
-        for(size_t i = lo; i < hi; ++i) std::memcpy(b.bases + b.offs[i], b.map_of(i) + b.refs[i].seq_off, b.refs[i].seq_len);
-    };
-    if(T == 1) copy(0, n);
-    else {
+    std::vector<u64> base(T + 1, 0);
+    auto rec_at = [&](size_t i) -> const RecRef & { return f2 ? ((i & 1) ? f2->recs[s2 + (i >> 1)] : f.recs[s1 + (i >> 1)]) : f.recs[s1 + i]; };
+    auto run = [&](auto &&fn) {
+        if(T == 1) { fn(0u); return; }
         std::vector<std::thread> pool;
-        for(unsigned t = 0; t < T; ++t) pool.emplace_back(copy, n * t / T, n * (t + 1) / T);
+        for(unsigned t = 0; t < T; ++t) pool.emplace_back(fn, t);
         for(auto &th : pool) th.join();
-    }
+    };
+    run([&](unsigned t) { u64 sum = 0; for(size_t i = n * t / T, hi = n * (t + 1) / T; i < hi; ++i) sum += rec_at(i).seq_len; base[t + 1] = sum; });
+    for(unsigned t = 0; t < T; ++t) base[t + 1] += base[t];
+    run([&](unsigned t) {
+        u64 off = base[t];
+        for(size_t i = n * t / T, hi = n * (t + 1) / T; i < hi; ++i) {
+            const RecRef &r = rec_at(i);
+            b.refs[i] = r;
+            b.offs[i] = off;
+            std::memcpy(b.bases + off, b.map_of(i) + r.seq_off, r.seq_len);
+            off += r.seq_len;
+        }
+    });
+    b.offs[n] = size;
     b.n = n; b.n_bases = size;
     return true;
 }
