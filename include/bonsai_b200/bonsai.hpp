@@ -695,9 +695,10 @@ inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxo
 }
 
 // One GPU call for a batch laid out as concatenated bases + offsets, then classify_seq's epilogue per record
-// (classifier.h:232-246). `views` has one entry per read (mates interleaved).
-template <typename ScoreType>
-void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ReadView *views, unsigned n_reads,
+// (classifier.h:232-246). view_at(i): what the emitters need of read i (mates interleaved), made where it is used -- on the
+// formatting threads -- instead of as an array per batch.
+template <typename ScoreType, typename ViewAt>
+void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ViewAt &view_at, unsigned n_reads,
                     int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
@@ -705,8 +706,13 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
     // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
     const bool need_taxa = (c.output_flag_ & KRAKEN) != 0;
-    std::vector<u32> taxon(nrec), nhit(nrec), nmiss(nrec), mate1(is_paired ? nrec : 0), nruns(need_taxa ? nrec : 0);
-    std::vector<u64> run_pos(need_taxa ? nrec : 0);
+    // result arrays the library fills: no need to zero them first
+    std::unique_ptr<u32[]> res(new u32[(size_t)nrec * 5]);
+    std::unique_ptr<u64[]> run_pos_buf(need_taxa ? new u64[nrec] : nullptr);
+    struct Arr { u32 *p; u32 *data() const { return p; } u32 &operator[](size_t i) const { return p[i]; } };
+    struct Arr64 { u64 *p; u64 *data() const { return p; } u64 &operator[](size_t i) const { return p[i]; } };
+    const Arr taxon{res.get()}, nhit{res.get() + nrec}, nmiss{res.get() + 2 * (size_t)nrec}, mate1{res.get() + 3 * (size_t)nrec}, nruns{res.get() + 4 * (size_t)nrec};
+    const Arr64 run_pos{run_pos_buf.get()};
     std::unique_ptr<u64[]> runs;
     if(need_taxa) {
         // run lists: encoded on the device, 8 bytes per run back instead of 4 per k-mer window slot. The number of runs is
@@ -733,9 +739,11 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     const u32 comb = c.sp_.c_;
     // classify_seq's epilogue (text) per record. The reference formats on its worker threads (-p, kt_for_helper,
     // classifier.h:254-266); here -p threads format contiguous slices of the batch and the slices are joined in order.
+    if(!(c.output_flag_ & (FASTQ | KRAKEN))) return;                  // nothing is printed (-K without -f): the counters are all there is
     auto format_range = [&](unsigned r_lo, unsigned r_hi, std::string &out) {
         for(unsigned r = r_lo; r < r_hi; ++r) {
-            const ReadView *b = views + r * inc;
+            const ReadView pair[2] = {view_at((size_t)r * inc), is_paired ? view_at((size_t)r * inc + 1) : ReadView{}};
+            const ReadView *b = pair;
             // classifier.h:232: unsigned ambig_count(l_seq - c + 1 - taxa.size() - missing_count), evaluated after mate 1
             u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
             if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
@@ -1281,10 +1289,9 @@ void classify_seqs(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, bseq1_
         std::memcpy(stage.bases + stage.offs[i], bs[i].seq.data(), bs[i].seq.size());
         stage.offs[i + 1] = stage.offs[i] + bs[i].seq.size();
     }
-    std::vector<detail::ReadView> views(n);
-    for(unsigned i = 0; i < n; ++i)
-        views[i] = detail::ReadView{bs[i].name.c_str(), stage.bases + stage.offs[i], bs[i].qual.empty() ? nullptr : bs[i].qual.c_str(), bs[i].l_seq};
-    detail::classify_views(c, stage.bases, stage.offs, views.data(), n, is_paired, cks);
+    detail::classify_views(c, stage.bases, stage.offs, [&](size_t i) {
+        return detail::ReadView{bs[i].name.c_str(), stage.bases + stage.offs[i], bs[i].qual.empty() ? nullptr : bs[i].qual.c_str(), bs[i].l_seq};
+    }, n, is_paired, cks);
 }
 
 }  // namespace bns
@@ -1433,7 +1440,6 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     std::vector<size_t> n_batches((size_t)G, 0);
     const unsigned fmt_threads = std::max(1u, (unsigned)c.nt_ / (unsigned)G);
     auto work = [&](int g) {
-        std::vector<detail::ReadView> views;
         bns_b200_t *h = c.gpu(g);
         for(u64 sq = (u64)g;; sq += (u64)G) {
             const size_t i = (size_t)(sq % (u64)NB);
@@ -1451,21 +1457,19 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
             { std::lock_guard<std::mutex> lk(mu); failed = !failure.empty(); }
             try {
                 if(!failed) {
-                    views.resize(b.n);
-                    if(b.map)
-                        for(size_t r = 0; r < b.n; ++r) {
+                    const double tc = now();
+                    if(b.map)                                          // indexed ingest: names / qualities stay in the file mapping
+                        detail::classify_views(c, b.bases, b.offs, [&b](size_t r) {
                             const detail::RecRef &ref = b.refs[r];
                             const char *mp = b.map_of(r);
-                            views[r] = detail::ReadView{mp + ref.name_off, b.bases + b.offs[r],
-                                                        b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
-                                                        (int)ref.seq_len, (int)ref.name_len};
-                        }
+                            return detail::ReadView{mp + ref.name_off, b.bases + b.offs[r], b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
+                                                    (int)ref.seq_len, (int)ref.name_len};
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads);
                     else
-                        for(size_t r = 0; r < b.n; ++r)
-                            views[r] = detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
-                                                        (int)(b.offs[r + 1] - b.offs[r])};
-                    const double tc = now();
-                    detail::classify_views(c, b.bases, b.offs, views.data(), (unsigned)b.n, is_paired, text, h, fmt_threads);
+                        detail::classify_views(c, b.bases, b.offs, [&b](size_t r) {
+                            return detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
+                                                    (int)(b.offs[r + 1] - b.offs[r])};
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads);
                     t_classify[(size_t)g] += now() - tc;
                     if(sq == 0) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
                 }
