@@ -716,6 +716,27 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                         if(RUNS) {
                             // The tile's hits in k-mer order (lane-major). A hit starts a run when no hit precedes it in the record
                             // or its value differs from the previous hit's; every start closes the run before it.
+                            // Most tiles hit ONE value: then the tile continues the open run or starts a single new one.
+                            const u32 lead = __shfl_sync(FULL, (todo & 1u) ? cand[0] : (todo & 2u) ? cand[1] : (todo & 4u) ? cand[2] : cand[3], __ffs(bal) - 1);
+                            const bool mixed = ((todo & 1u) && cand[0] != lead) || ((todo & 2u) && cand[1] != lead) || ((todo & 4u) && cand[2] != lead) ||
+                                               ((todo & 8u) && cand[3] != lead);
+                            if(!__any_sync(FULL, mixed)) {
+                                const u32 H1 = __reduce_add_sync(FULL, __popc(todo));
+                                if(run_val == lead) run_len += H1;
+                                else {
+                                    if(run_val != VAL_MISS) {
+                                        if(!run_direct && n_runs_rec + 2 > (u32)RUNBUF) {
+                                            const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
+                                            reserve_runs(n_runs_rec + rest);
+                                            for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                                            run_direct = true;
+                                        }
+                                        if(lane == 0) put_run(n_runs_rec, run_val, run_len);
+                                        ++n_runs_rec;
+                                    }
+                                    run_val = lead; run_len = H1;
+                                }
+                            } else {
                             u32 firstv = VAL_MISS, prevv = VAL_MISS, inner = 0;
 #pragma unroll
                             for(int i = 0; i < PPL; ++i)
@@ -767,6 +788,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                                 run_len = H - __shfl_sync(FULL, last_idx, top);
                                 n_runs_rec += SX - (carry ? 0u : 1u);
                             } else run_len += H;
+                            }
                             __syncwarp();
                         }
                         do {

@@ -163,6 +163,28 @@ def test_cli_host_pipeline_ingest_kinds(tmp_path, cli):
         assert many[2].split(b"classified")[-2:] == one[2].split(b"classified")[-2:]      # the counters add up over the contexts
 
 
+def test_reference_style_caller_compiles_and_runs(tmp_path, cli):
+    """tests/host/ref_style_main.cpp spells the classify path the way the reference's own classify_main does (Database<khash_t(c)>,
+    ClassifierGeneric(db.db_, ...), khash_t(p) *build_parent_map, process_dataset, classify_seqs(.., ks::string &, .., ForPool &),
+    kh_destroy(p, ..)): it must compile against bonsai.hpp unchanged and run (here against the dummy ABI)."""
+    import shutil
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "ref_style")
+    r = subprocess.run([shutil.which("g++") or "/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(here, "host", "ref_style_main.cpp"),
+                        os.path.join(here, "host", "abi_stub.cpp"), "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    keys = np.arange(1, 50, dtype=np.uint64)
+    with open(tmp_path / "pairs.bin", "wb") as f:
+        f.write(struct.pack("<Q", keys.size)); f.write(keys.tobytes()); f.write(np.full(keys.size, 11, np.uint32).tobytes())
+    subprocess.check_call([cli, "dbwrite", str(tmp_path / "t.db"), "31", "31", str(tmp_path / "pairs.bin")])
+    (tmp_path / "nodes.dmp").write_text("1\t|\t1\t|\n2\t|\t1\t|\n10\t|\t2\t|\n11\t|\t10\t|\n")
+    (tmp_path / "r.fq").write_text("".join("@q%d\n%s\n+\n%s\n" % (i, "ACGTTGCA" * 10, "I" * 80) for i in range(300)))
+    r = subprocess.run([exe, str(tmp_path / "t.db"), str(tmp_path / "nodes.dmp"), str(tmp_path / "r.fq")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 302 and all(l[0] in "CU" and l.split("\t")[1].startswith(("q", "a", "b")) for l in lines)
+
+
 def test_cpp_encoder_surface_compiles(tmp_path):
     """tests/host/encoder_api.cpp (the GPU test of the C++ Encoder mirror, incl. assign / next_kmer / next_minimizer) compiles
     and links against the dummy ABI; without a device every case reports the library's refusal instead of a stream."""
