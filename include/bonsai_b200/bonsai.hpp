@@ -699,9 +699,13 @@ inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxo
 // formatting threads -- instead of as an array per batch.
 template <typename ScoreType, typename ViewAt>
 void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ViewAt &view_at, unsigned n_reads,
-                    int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0) {
+                    int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0, std::mutex *device_mu = nullptr) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
+    // device_mu: a context runs one call at a time; two host workers that share a GPU take turns for the call and format their
+    // batches side by side
+    std::unique_lock<std::mutex> device_lock;
+    if(device_mu) device_lock = std::unique_lock<std::mutex>(*device_mu);
     if(!h) h = c.h_->h;                                               // the context (GPU) this batch runs on
     // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
     // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
@@ -739,6 +743,7 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     const u32 comb = c.sp_.c_;
     // classify_seq's epilogue (text) per record. The reference formats on its worker threads (-p, kt_for_helper,
     // classifier.h:254-266); here -p threads format contiguous slices of the batch and the slices are joined in order.
+    if(device_lock.owns_lock()) device_lock.unlock();
     if(!(c.output_flag_ & (FASTQ | KRAKEN))) return;                  // nothing is printed (-K without -f): the counters are all there is
     auto format_range = [&](unsigned r_lo, unsigned r_hi, std::string &out) {
         for(unsigned r = r_lo; r < r_hi; ++r) {
@@ -1358,7 +1363,10 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     bool use_index = simple != nullptr;          // the mappings stay alive to the end: batches in flight point into them
     const int fn = fileno(out), is_paired = fq2 != nullptr;
     const int G = c.replicas_.empty() ? 1 : c.n_gpus();
-    const int NB = 2 * G + 1;
+    // two host workers per GPU: batch s goes to worker s mod 2G, i.e. to GPU s mod G; while one worker formats its batch the
+    // other has the device
+    const int NW = 2 * G;
+    const int NB = 2 * NW + 1;
     std::vector<detail::PinnedBatch> ring((size_t)NB);
     for(auto &b : ring) { b.reserve(chunk_size); b.keep_qual = c.get_emit_fastq() != 0; }
     std::vector<int> state((size_t)NB, 0);       // 0 free, 1 filled
@@ -1436,12 +1444,14 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     std::string failure;
     const bool verbose = std::getenv("BNS_B200_VERBOSE") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    std::vector<double> t_wait((size_t)G, 0.), t_classify((size_t)G, 0.);
-    std::vector<size_t> n_batches((size_t)G, 0);
+    std::vector<double> t_wait((size_t)NW, 0.), t_classify((size_t)NW, 0.);
+    std::vector<size_t> n_batches((size_t)NW, 0);
+    std::vector<std::mutex> device_mu((size_t)G);
     const unsigned fmt_threads = std::max(1u, (unsigned)c.nt_ / (unsigned)G);
-    auto work = [&](int g) {
-        bns_b200_t *h = c.gpu(g);
-        for(u64 sq = (u64)g;; sq += (u64)G) {
+    auto work = [&](int g) {                                               // worker g of NW, on GPU g mod G
+        bns_b200_t *h = c.gpu(g % G);
+        std::mutex *dmu = &device_mu[(size_t)(g % G)];
+        for(u64 sq = (u64)g;; sq += (u64)NW) {
             const size_t i = (size_t)(sq % (u64)NB);
             const double tw = now();
             {
@@ -1464,12 +1474,12 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                             const char *mp = b.map_of(r);
                             return detail::ReadView{mp + ref.name_off, b.bases + b.offs[r], b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
                                                     (int)ref.seq_len, (int)ref.name_len};
-                        }, (unsigned)b.n, is_paired, text, h, fmt_threads);
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu);
                     else
                         detail::classify_views(c, b.bases, b.offs, [&b](size_t r) {
                             return detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
                                                     (int)(b.offs[r + 1] - b.offs[r])};
-                        }, (unsigned)b.n, is_paired, text, h, fmt_threads);
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu);
                     t_classify[(size_t)g] += now() - tc;
                     if(sq == 0) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
                 }
@@ -1481,8 +1491,8 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
         }
     };
     std::vector<std::thread> workers;
-    for(int g = 1; g < G; ++g) workers.emplace_back(work, g);
-    work(0);                                                               // GPU 0 on the caller's thread
+    for(int g = 1; g < NW; ++g) workers.emplace_back(work, g);
+    work(0);                                                               // the first worker of GPU 0 on the caller's thread
     for(auto &t : workers) t.join();
     reader.join();
     { std::lock_guard<std::mutex> lk(wmu); w_end = end_seq; }
@@ -1493,9 +1503,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
     if(verbose)
-        for(int g = 0; g < G; ++g)
-            std::fprintf(stderr, "[process_dataset] gpu %d: %zu batches, waiting for the reader %.2f s, classify + format %.2f s\n",
-                         g, n_batches[(size_t)g], t_wait[(size_t)g], t_classify[(size_t)g]);
+        for(int g = 0; g < NW; ++g)
+            std::fprintf(stderr, "[process_dataset] gpu %d worker %d: %zu batches, waiting for the reader %.2f s, classify + format %.2f s\n",
+                         g % G, g / G, n_batches[(size_t)g], t_wait[(size_t)g], t_classify[(size_t)g]);
 }
 
 }  // namespace bns
