@@ -1264,6 +1264,7 @@ int bns_b200_replicate(bns_b200_t *const *handles, int n, int root) {
                 if(rc != BNS_OK || ns < 4) return ctx->fail(BNS_E_STATE, "replica %d has no segments", i);
                 if(i == root) { nseg = ns; for(int s = 0; s < ns; ++s) bytes[s] = b[s]; }
             }
+            cudaSetDevice(ctx->device);                                   // the copies are queued on the root's stream
             for(int i = 0; i < n; ++i) {
                 if(i == root) continue;
                 for(int s = 0; s < nseg; ++s)

@@ -710,7 +710,8 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     u32 todo = ~nok & mask;
                     u32 bal = __ballot_sync(FULL, todo != 0);
                     if(bal) {
-                        if(COUNTS) n_hit += __reduce_add_sync(FULL, __popc(todo));
+                        const u32 tile_hits = (COUNTS || RUNS) ? __reduce_add_sync(FULL, __popc(todo)) : 0u;
+                        if(COUNTS) n_hit += tile_hits;
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) cand[i] &= Pc.val_mask;
                         if(RUNS) {
@@ -721,7 +722,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             const bool mixed = ((todo & 1u) && cand[0] != lead) || ((todo & 2u) && cand[1] != lead) || ((todo & 4u) && cand[2] != lead) ||
                                                ((todo & 8u) && cand[3] != lead);
                             if(!__any_sync(FULL, mixed)) {
-                                const u32 H1 = __reduce_add_sync(FULL, __popc(todo));
+                                const u32 H1 = tile_hits;
                                 if(run_val == lead) run_len += H1;
                                 else {
                                     if(run_val != VAL_MISS) {

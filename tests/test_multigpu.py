@@ -38,8 +38,11 @@ def _small_db(oracle, genomes, tax):
 
 
 @needs2
-def test_open_multi_replicate_in_library(oracle, genomes, toy_tax):
+@pytest.mark.parametrize("how", ["nccl", "p2p"])
+def test_open_multi_replicate_in_library(oracle, genomes, toy_tax, monkeypatch, how):
     from bonsai_b200 import capi
+    if how == "p2p":
+        monkeypatch.setenv("BNS_B200_REPLICATE", "p2p")           # peer copies instead of the NCCL broadcast
     dbo = _small_db(oracle, genomes, toy_tax)
     keys, vals = oracle.db_pairs(dbo)
     tc, tp = H.toy_tax_arrays()
