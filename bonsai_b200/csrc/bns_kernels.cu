@@ -401,7 +401,7 @@ struct ClassifySink {
             S.tin[i] = inf.x; S.tout[i] = inf.y;
         }
         __syncwarp();
-        u32 best = 0;
+        u32 best = 0, sc0 = 0;                                // sc0: this lane's score in the first (usually only) round of 32
         for(u32 base = 0; base < n; base += 32) {
             const u32 i = base + lane;
             u32 sc = 0;
@@ -410,17 +410,21 @@ struct ClassifySink {
                 for(u32 j = 0; j < n; ++j)
                     if(S.tin[j] <= ti && ti < S.tout[j]) sc += S.cnt[j] & 0xffffu;
             }
+            if(base == 0) sc0 = sc;
             best = max(best, __reduce_max_sync(FULL, sc));
         }
         // ties (score == best), folded in list order
         u32 node = 0, ntied = 0, first_id = 0;
         for(u32 base = 0; base < n; base += 32) {
             const u32 i = base + lane;
-            u32 sc = 0;
-            if(i < n) {
-                const u32 ti = S.tin[i];
-                for(u32 j = 0; j < n; ++j)
-                    if(S.tin[j] <= ti && ti < S.tout[j]) sc += S.cnt[j] & 0xffffu;
+            u32 sc = sc0;
+            if(base != 0) {                                    // lists of more than 32 taxa: the later rounds' scores again
+                sc = 0;
+                if(i < n) {
+                    const u32 ti = S.tin[i];
+                    for(u32 j = 0; j < n; ++j)
+                        if(S.tin[j] <= ti && ti < S.tout[j]) sc += S.cnt[j] & 0xffffu;
+                }
             }
             u32 tied = __ballot_sync(FULL, i < n && sc == best);
             while(tied) {
