@@ -844,20 +844,29 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             if(lane == (j >> msh)) { my_taxon = taxon; my_def = deferred; if(COUNTS) { my_hit = n_hit; my_miss = n_emit - n_hit; if(msh == 0) my_m1 = n_emit; } }
             if(RUNS) {
                 // the run still open ends with the record; then the record's runs take their place in the warp's stretch
-                if(run_val != VAL_MISS) {
-                    if(!run_direct && n_runs_rec + 1 > (u32)RUNBUF) {
-                        reserve_runs(n_runs_rec + 1);
-                        for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
-                        run_direct = true;
+                if(!run_direct && n_runs_rec == 0) {
+                    // at most that one run (most records): straight to its place
+                    if(run_val != VAL_MISS) {
+                        reserve_runs(1);
+                        if(lane == 0 && blk_pos < runs_cap) runs_out[blk_pos] = ((u64)sink.vi[run_val].w << 32) | run_len;
+                        n_runs_rec = 1;
                     }
-                    if(lane == 0) put_run(n_runs_rec, run_val, run_len);
-                    ++n_runs_rec;
-                    __syncwarp();
-                }
-                if(!run_direct) {
-                    reserve_runs(n_runs_rec);
-                    for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
-                    __syncwarp();
+                } else {
+                    if(run_val != VAL_MISS) {
+                        if(!run_direct && n_runs_rec + 1 > (u32)RUNBUF) {
+                            reserve_runs(n_runs_rec + 1);
+                            for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                            run_direct = true;
+                        }
+                        if(lane == 0) put_run(n_runs_rec, run_val, run_len);
+                        ++n_runs_rec;
+                        __syncwarp();
+                    }
+                    if(!run_direct) {
+                        reserve_runs(n_runs_rec);
+                        for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                        __syncwarp();
+                    }
                 }
                 if(lane == (j >> msh)) { my_rpos = blk_pos; my_nruns = n_runs_rec; }
                 blk_pos += n_runs_rec; blk_left -= n_runs_rec;

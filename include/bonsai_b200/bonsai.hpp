@@ -1368,7 +1368,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     const int NW = 2 * G;
     const int NB = 2 * NW + 1;
     std::vector<detail::PinnedBatch> ring((size_t)NB);
-    for(auto &b : ring) { b.reserve(chunk_size); b.keep_qual = c.get_emit_fastq() != 0; }
+    // pinned allocations are slow (tens of ms each): a ring slot gets its buffers when the reader first fills it, while the
+    // earlier batches are already on the device
+    for(auto &b : ring) b.keep_qual = c.get_emit_fastq() != 0;
     std::vector<int> state((size_t)NB, 0);       // 0 free, 1 filled
     std::vector<u64> seq_of((size_t)NB, ~0ull);
     u64 end_seq = ~0ull;                         // batches [0, end_seq) exist
@@ -1381,6 +1383,7 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                 const size_t i = (size_t)(sq % (u64)NB);
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
                 bool got = false;
+                if(!ring[i].bases) ring[i].reserve(chunk_size);
                 if(use_index) {
                     got = detail::fill_pinned((int)chunk_size, ring[i], *simple, simple2.get());
                     if(!got && simple->drained() && (!simple2 || simple2->drained())) {
