@@ -5,12 +5,12 @@ PKG  := bonsai_b200
 CSRC := $(PKG)/csrc
 LIB  := $(PKG)/libbonsai_b200.so
 CLI  := $(PKG)/bin/bonsai
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall -shared -ldl
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-Wall,-pthread -shared -ldl
 
 all: $(LIB) $(CLI)
 
-$(LIB): $(CSRC)/bns_kernels.cu $(CSRC)/bns_api.cu $(CSRC)/bns_device.cuh $(CSRC)/bns_classify_u.cuh $(CSRC)/bns_kernels.h $(CSRC)/bns_host_util.h include/bonsai_b200.h
-	$(NVCC) $(NVCCFLAGS) -o $@ $(CSRC)/bns_kernels.cu $(CSRC)/bns_api.cu
+$(LIB): $(CSRC)/bns_kernels.cu $(CSRC)/bns_api.cu $(CSRC)/bns_pack.cpp $(CSRC)/bns_pack.h $(CSRC)/bns_device.cuh $(CSRC)/bns_classify_u.cuh $(CSRC)/bns_kernels.h $(CSRC)/bns_host_util.h include/bonsai_b200.h
+	$(NVCC) $(NVCCFLAGS) -o $@ $(CSRC)/bns_kernels.cu $(CSRC)/bns_api.cu $(CSRC)/bns_pack.cpp
 
 $(CLI): $(CSRC)/cli/bonsai_main.cpp include/bonsai_b200/bonsai.hpp include/bonsai_b200.h $(LIB)
 	mkdir -p $(PKG)/bin

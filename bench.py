@@ -528,6 +528,27 @@ def run_workload(env, name, n, steps, warmup, e2e_steps, n_check, with_cpu_basel
                "d2h_bytes_per_step": int(d2h_step), "steps": e2e_steps,
                "h2d_gbs": world * h2d_step * e2e_steps / e2e_s / 1e9,
                "taxids_match_device_path": bool(np.array_equal(h_taxon.numpy().astype(np.uint32), taxon_dev))}
+        # The call packs chunks of the batch to 2 bits per base on the host's cores (inside the timed region) next to the chunks
+        # that cross as ASCII; the same call with the packing threads switched off is measured beside it.
+        hp = ctx.host_pack_threads()
+        e2e["host_pack_threads"] = hp
+        e2e["input"] = "ASCII bases in pinned host memory; the library packs part of them to 2-bit units on %d host threads inside the call" % hp \
+            if hp > 0 else "ASCII bases in pinned host memory, copied as they are"
+        if hp > 0:
+            ctx.set_host_pack_threads(0)
+            h_taxon.zero_()
+            step_host()
+            env.barrier()
+            sa = ctx.stats()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                step_host()
+            torch.cuda.synchronize()
+            dt = env.max_over_ranks(time.perf_counter() - t0)
+            sb_ = ctx.stats()
+            e2e["ascii_only"] = {"value": world * n * 3 / dt / 1e6, "unit": "Mreads/s", "h2d_bytes_per_step": int((sb_["h2d_bytes"] - sa["h2d_bytes"]) // 3),
+                                 "taxids_match_device_path": bool(np.array_equal(h_taxon.numpy().astype(np.uint32), taxon_dev))}
+            ctx.set_host_pack_threads(hp)
         # the same call with Kraken run lists (bns_b200_classify_batch_runs: runs produced by the lean kernel itself)
         if with_runs:
             import ctypes as C

@@ -11,10 +11,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbonsai_b200.so")
-SOURCES = ["bns_kernels.cu", "bns_api.cu"]
-DEPS = SOURCES + ["bns_device.cuh", "bns_classify_u.cuh", "bns_kernels.h", "bns_host_util.h", os.path.join("..", "..", "include", "bonsai_b200.h")]
+SOURCES = ["bns_kernels.cu", "bns_api.cu", "bns_pack.cpp"]
+DEPS = SOURCES + ["bns_device.cuh", "bns_classify_u.cuh", "bns_kernels.h", "bns_host_util.h", "bns_pack.h", os.path.join("..", "..", "include", "bonsai_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-ldl"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-pthread", "-shared", "-ldl"]
 
 
 def nvcc_path():

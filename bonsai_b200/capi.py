@@ -27,13 +27,14 @@ SYMBOLS = [
     "bns_b200_classify_batch", "bns_b200_classify_batch_ex", "bns_b200_classify_batch_runs", "bns_b200_classify_device", "bns_b200_sync", "bns_b200_stats_get",
     "bns_b200_stats_reset", "bns_b200_host_alloc", "bns_b200_host_free", "bns_b200_bench_gather",
     "bns_b200_open_multi", "bns_b200_replicate", "bns_b200_close_multi", "bns_b200_device_status", "bns_b200_classify_device_runs",
+    "bns_b200_set_host_pack_threads", "bns_b200_host_pack_threads",
 ]
 
 
 class Config(C.Structure):
     _fields_ = [("k", C.c_uint32), ("w", C.c_uint32), ("gaps", C.c_uint16 * MAX_K), ("score", C.c_uint32),
                 ("canonicalize", C.c_uint32), ("api", C.c_uint32), ("entropy_cast", C.c_uint32),
-                ("device", C.c_int32), ("n_gpus", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("device", C.c_int32), ("n_gpus", C.c_uint32), ("host_pack_threads", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class TableInfo(C.Structure):
@@ -85,6 +86,8 @@ def load_library(path=None):
     lib.bns_b200_last_error.argtypes = [vp]
     lib.bns_b200_open.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     lib.bns_b200_close.argtypes = [vp]
+    lib.bns_b200_set_host_pack_threads.argtypes = [vp, C.c_uint32]
+    lib.bns_b200_host_pack_threads.argtypes = [vp]
     lib.bns_b200_close.restype = None
     lib.bns_b200_geometry.argtypes = [vp, u32p, u32p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.bns_b200_encode_bound.restype = C.c_uint64
@@ -137,10 +140,12 @@ class Context:
     """One bns_b200 context = one ClassifierGeneric + its per-worker Encoder copy on one GPU."""
 
     @staticmethod
-    def _config(k, w, gaps, score, canonicalize, api, entropy_cast, device):
+    def _config(k, w, gaps, score, canonicalize, api, entropy_cast, device, host_pack_threads=None):
         cfg = Config()
         cfg.k, cfg.w, cfg.score, cfg.canonicalize, cfg.api = k, w, score, int(bool(canonicalize)), api
         cfg.entropy_cast, cfg.device = entropy_cast, device
+        # None: the library's default (this process's share of the hardware threads); 0: off; n: that many worker threads
+        cfg.host_pack_threads = 0 if host_pack_threads is None else (0xffffffff if host_pack_threads <= 0 else int(host_pack_threads))
         if gaps is not None:
             assert len(gaps) == k - 1, "gap vector must have k-1 entries"
             for i, g in enumerate(gaps):
@@ -148,9 +153,9 @@ class Context:
         return cfg
 
     def __init__(self, k, w=0, gaps=None, score=SCORE_LEX, canonicalize=True, api=API_STRING,
-                 entropy_cast=CAST_SATURATE, device=-1):
+                 entropy_cast=CAST_SATURATE, device=-1, host_pack_threads=None):
         self.lib = load_library()
-        cfg = self._config(k, w, gaps, score, canonicalize, api, entropy_cast, device)
+        cfg = self._config(k, w, gaps, score, canonicalize, api, entropy_cast, device, host_pack_threads)
         h = C.c_void_p()
         rc = self.lib.bns_b200_open(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -361,6 +366,13 @@ class Context:
             out.append(np.stack([(w >> np.uint64(32)).astype(np.uint32), (w & np.uint64(0xffffffff)).astype(np.uint32)], axis=1))
         assert int(total.value) >= int(nruns.sum())          # the entries used: runs plus the stretches a warp left unused
         return taxon, nhit, nmiss, out
+
+    def set_host_pack_threads(self, n):
+        """worker threads the host-buffer classify calls pack bases with (0: every chunk crosses PCIe as ASCII)"""
+        self._ck(self.lib.bns_b200_set_host_pack_threads(self.h, int(n)))
+
+    def host_pack_threads(self):
+        return int(self.lib.bns_b200_host_pack_threads(self.h))
 
     def classify_into(self, bases_ptr, offsets_ptr, n_reads, taxon_ptr, nhit_ptr=None, nmiss_ptr=None, paired=False):
         """bns_b200_classify_batch on raw HOST pointers (e.g. pinned buffers): blocks until outputs are written."""

@@ -4,12 +4,15 @@
 // ring of stream slots through which host batches are pipelined (H2D copy / kernel / D2H copy overlap
 // across slots), and the counters ClassifierGeneric keeps (classifier.h:138,170-171).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -20,12 +23,16 @@
 #include "bns_device.cuh"
 #include "bns_host_util.h"
 #include "bns_kernels.h"
+#include "bns_pack.h"
 
 using namespace bns;
 
 namespace {
 
-constexpr int N_SLOTS = 3;
+constexpr int N_SLOTS = 10;                 // stream slots; the packing call draws on all of them (small chunks, many in flight)
+constexpr int N_RING = 3;                   // ... the other host-buffer calls pipeline their (larger) chunks over the first three
+constexpr u64 PACK_CHUNK_READS = 1ull << 18;  // reads per chunk of the packing calls (both lanes draw from one chunk list)
+constexpr u64 PACK_MIN_BASES = 16ull << 20;   // smaller batches are not worth waking the worker threads for
 constexpr u64 CHUNK_BASES = 96ull << 20;      // bases per pipelined chunk
 constexpr u64 CHUNK_READS = 1ull << 20;
 constexpr double TARGET_LOAD_BIG = 1.75;
@@ -47,6 +54,15 @@ struct Slot {
     unsigned long long *d_defer_cnt = nullptr;                // [0] records left to the second pass  [1] run-buffer entries handed out
     cudaEvent_t ka = nullptr, kb = nullptr;                   // around the kernels of the chunk in flight (stats.kernel_ms_total)
     bool k_timed = false;
+    // host-packed chunks (bns_pack.h): pinned staging the worker threads pack into, and the device copies next to d_bases
+    uint16_t *h_units = nullptr;   size_t cap_h_units = 0;
+    u32 *h_susp = nullptr;         size_t cap_h_susp = 0;
+    u64 *h_exc = nullptr;          size_t cap_h_exc = 0;
+    u32 *d_susp = nullptr;         size_t cap_d_susp = 0;
+    u64 *d_exc = nullptr;          size_t cap_d_exc = 0;
+    cudaEvent_t h2d_done = nullptr;                           // behind the input copies of the chunk in flight
+    bool busy = false, raw = false;
+    bool reserved = false;                                    // being packed into / packed and not queued yet: the stream is idle, the staging is not
 };
 
 template <class T>
@@ -56,6 +72,16 @@ int ensure(T *&p, size_t &cap, size_t need) {
     p = nullptr; cap = 0;
     size_t want = need + need / 4 + 256;
     if(cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return BNS_E_NOMEM; }
+    cap = want;
+    return BNS_OK;
+}
+template <class T>
+int ensure_pinned(T *&p, size_t &cap, size_t need) {
+    if(need <= cap) return BNS_OK;
+    if(p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = need + need / 4 + 256;
+    if(cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return BNS_E_NOMEM; }
     cap = want;
     return BNS_OK;
 }
@@ -93,6 +119,12 @@ struct bns_b200_ctx {
     u32 *d_status = nullptr;
     u32 *d_big = nullptr; size_t cap_big = 0;   // global-memory taxon lists of the second classify pass (databases of > 256 values)
     Slot slots[N_SLOTS];
+    // host packing (bns_b200_config.host_pack_threads): worker threads, created at the first call large enough to use them
+    int pack_threads = 0;             // 0 = the host-buffer calls ship ASCII
+    int pack_mode = 2;                // 1 every chunk packed, 2 packed and ASCII chunks side by side (BNS_B200_HOST_PACK_MODE=pack|hybrid)
+    u64 pack_min_bases = PACK_MIN_BASES, pack_chunk_reads = PACK_CHUNK_READS;   // BNS_B200_PACK_MIN_BASES / _CHUNK_READS (tests use small ones)
+    std::unique_ptr<PackPool> pool;
+    std::vector<std::vector<uint64_t>> exc_parts[2];          // exception words per packing task, of the chunk being packed / being queued
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bns_b200_stats stats{};
     std::string err;
@@ -584,6 +616,24 @@ int bns_b200_open(const bns_b200_config *cfg, bns_b200_t **out) {
         if((e = cudaMalloc((void **)&ctx->slots[i].d_defer_cnt, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
         cudaMemset(ctx->slots[i].d_defer_cnt, 0, 2 * sizeof(unsigned long long));
         if((e = cudaEventCreate(&ctx->slots[i].ka)) != cudaSuccess || (e = cudaEventCreate(&ctx->slots[i].kb)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if((e = cudaEventCreateWithFlags(&ctx->slots[i].h2d_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
+    // Host packing: cfg.host_pack_threads = N worker threads, 0 = this process's share of the machine's threads (divided by
+    // LOCAL_WORLD_SIZE under torchrun) less the calling one, 0xffffffff = off; BNS_B200_HOST_PACK=N|0 overrides.
+    {
+        long want = cfg->host_pack_threads == 0xffffffffu ? 0 : (long)cfg->host_pack_threads;
+        bool given = cfg->host_pack_threads != 0;
+        if(const char *env = getenv("BNS_B200_HOST_PACK")) { want = atol(env); given = true; }
+        if(!given) {
+            long share = (long)std::thread::hardware_concurrency();
+            if(const char *lw = getenv("LOCAL_WORLD_SIZE")) { const long n = atol(lw); if(n > 1) share /= n; }
+            want = share - 1;
+            if(want < 2) want = 0;                                     // one helper does not beat the copy engine
+        }
+        ctx->pack_threads = (int)std::max(0l, std::min(want, 64l));
+        if(const char *env = getenv("BNS_B200_HOST_PACK_MODE")) ctx->pack_mode = !strcmp(env, "pack") ? 1 : 2;
+        if(const char *env = getenv("BNS_B200_PACK_MIN_BASES")) ctx->pack_min_bases = strtoull(env, nullptr, 10);
+        if(const char *env = getenv("BNS_B200_PACK_CHUNK_READS")) ctx->pack_chunk_reads = std::max<u64>(64, strtoull(env, nullptr, 10));
     }
     if((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -618,6 +668,12 @@ void bns_b200_close(bns_b200_t *ctx) {
         if(s.d_run_pos) cudaFree(s.d_run_pos);
         if(s.d_nruns) cudaFree(s.d_nruns);
         if(s.d_defer_cnt) cudaFree(s.d_defer_cnt);
+        if(s.d_susp) cudaFree(s.d_susp);
+        if(s.d_exc) cudaFree(s.d_exc);
+        if(s.h_units) cudaFreeHost(s.h_units);
+        if(s.h_susp) cudaFreeHost(s.h_susp);
+        if(s.h_exc) cudaFreeHost(s.h_exc);
+        if(s.h2d_done) cudaEventDestroy(s.h2d_done);
         if(s.ka) cudaEventDestroy(s.ka);
         if(s.kb) cudaEventDestroy(s.kb);
         if(s.st) cudaStreamDestroy(s.st);
@@ -1346,7 +1402,7 @@ int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *of
     u32 status_acc = 0;
     int slot_i = 0;
     u64 r0 = 0;
-    u32 h_status[N_SLOTS] = {0, 0, 0};
+    u32 h_status[N_SLOTS] = {};
     while(r0 < n_seqs) {
         u64 r1 = r0;
         while(r1 < n_seqs && r1 - r0 < CHUNK_READS && (r1 == r0 || offsets[r1 + 1] - offsets[r0] <= CHUNK_BASES)) ++r1;
@@ -1376,7 +1432,7 @@ int bns_b200_encode_batch(bns_b200_t *ctx, const char *bases, const uint64_t *of
         ctx->stats.reads_processed += nr;
         ctx->stats.bases_processed += nb;
         r0 = r1;
-        slot_i = (slot_i + 1) % N_SLOTS;
+        slot_i = (slot_i + 1) % N_RING;
     }
     for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); status_acc |= h_status[i]; }
     return check_status(ctx, status_acc & 1u);
@@ -1459,6 +1515,229 @@ int bns_b200_classify_device_runs(bns_b200_t *ctx, const char *d_bases, const ui
     return BNS_OK;
 }
 
+// classify_batch_ex for large batches when the context has packing threads: the batch is cut into chunks of PACK_CHUNK_READS
+// reads that two lanes draw from. The PACK lane has the worker threads turn a chunk's ASCII bases into 2-bit units in pinned
+// staging memory (bns_pack.h), then queues the copy of those (a quarter of the bytes) and the packed-input variant of the lean
+// kernel; the RAW lane keeps the copy engine busy meanwhile with chunks that cross as they are (at most two queued). Host cores
+// and PCIe link work side by side; every chunk's results land at its records' places in the caller's arrays.
+static int classify_batch_packing(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, u64 n_rec_total, u32 mates,
+                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out) {
+    if(!ctx->pool) ctx->pool.reset(new PackPool((unsigned)ctx->pack_threads));
+    PackPool &pool = *ctx->pool;
+    for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); ctx->slots[i].busy = ctx->slots[i].reserved = false; }
+    const bool counts = n_hit_out || n_missing_out;
+    // The chunk list, and for every chunk whether all its records have one length (then the kernel generates the offsets itself
+    // and they do not cross PCIe): the scan of offsets[] is the one per-read pass of the call, the worker threads share it.
+    struct Chunk { u64 q0, q1; u32 fixed_len; };
+    std::vector<Chunk> chunks;
+    for(u64 q0 = 0; q0 < n_rec_total;) {
+        u64 q1 = std::min(n_rec_total, q0 + std::max<u64>(1, ctx->pack_chunk_reads / mates));
+        while(q1 > q0 + 1 && offsets[q1 * mates] - offsets[q0 * mates] > CHUNK_BASES) q1 = q0 + (q1 - q0) / 2;
+        chunks.push_back(Chunk{q0, q1, 0u});
+        q0 = q1;
+    }
+    {
+        Chunk *cp = chunks.data();
+        pool.start((unsigned)chunks.size(), [=](unsigned i) {
+            const u64 r0 = cp[i].q0 * mates, r1 = cp[i].q1 * mates, nr = r1 - r0, nb = offsets[r1] - offsets[r0];
+            if(!nr || nb % nr || nb / nr == 0 || nb / nr >= 0xffffffffull) return;
+            const u64 flen = nb / nr;
+            u64 diff = 0;
+            for(u64 r = r0; r < r1; ++r) diff |= (offsets[r + 1] - offsets[r]) ^ flen;
+            if(!diff) cp[i].fixed_len = (u32)flen;
+        });
+        pool.wait();
+    }
+    // Every slot gets its buffers for the largest chunk now: which slot carries a packed and which an ASCII chunk is decided as the
+    // call goes, and an allocation (pinned or device) in the middle of it would stall both lanes.
+    {
+        u64 max_nb = 0, max_nr = 0;
+        for(const Chunk &c : chunks) {
+            max_nb = std::max<u64>(max_nb, offsets[c.q1 * mates] - offsets[c.q0 * mates]);
+            max_nr = std::max<u64>(max_nr, (c.q1 - c.q0) * mates);
+        }
+        const u64 n_units = (max_nb + 7) / 8, n_sw = (max_nb + 255) / 256;
+        const int n_use = (int)std::min<size_t>(N_SLOTS, chunks.size());
+        for(int i = 0; i < n_use; ++i) {
+            Slot &s = ctx->slots[i];
+            int rc = ensure(s.d_bases, s.cap_bases, std::max<u64>(max_nb + 16, 2 * n_units + 64));
+            if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, max_nr + 1);
+            if(rc == BNS_OK) rc = ensure(s.d_out, s.cap_out, 4 * max_nr);
+            if(rc == BNS_OK) rc = ensure(s.d_susp, s.cap_d_susp, n_sw + 2);
+            if(rc == BNS_OK) rc = ensure(s.d_exc, s.cap_d_exc, 1024);
+            if(rc == BNS_OK) rc = ensure_pinned(s.h_units, s.cap_h_units, n_units + 32);
+            if(rc == BNS_OK) rc = ensure_pinned(s.h_susp, s.cap_h_susp, n_sw + 2);
+            if(rc == BNS_OK) rc = ensure_pinned(s.h_exc, s.cap_h_exc, 1024);
+            if(rc != BNS_OK) return ctx->fail(rc, "chunk buffers");
+        }
+    }
+    // launch geometry per (records in the chunk, packed or not): all chunks but the last have one size
+    struct PlanKey { u64 nq; bool pk; ClassifyPlan pl; };
+    std::vector<PlanKey> plans;
+    auto plan_for = [&](u64 nq, bool pk) -> ClassifyPlan {
+        for(const PlanKey &k : plans) if(k.nq == nq && k.pk == pk) return k.pl;
+        plans.push_back(PlanKey{nq, pk, plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, nq, mates, false, mate1_kmers_out != nullptr, counts, false, pk)});
+        return plans.back().pl;
+    };
+    auto free_slot = [&]() -> int {
+        for(int i = 0; i < (int)std::min<size_t>(N_SLOTS, chunks.size()); ++i) {
+            Slot &s = ctx->slots[i];
+            if(s.reserved) continue;
+            if(s.busy && cudaStreamQuery(s.st) == cudaSuccess) { s.busy = false; collect_kernel_time(ctx, s); }
+            if(!s.busy) return i;
+        }
+        cudaGetLastError();                                            // cudaErrorNotReady is not an error
+        return -1;
+    };
+    auto raw_queued = [&]() -> int {
+        int n = 0;
+        for(int i = 0; i < N_SLOTS; ++i) if(ctx->slots[i].busy && ctx->slots[i].raw && cudaEventQuery(ctx->slots[i].h2d_done) != cudaSuccess) ++n;
+        cudaGetLastError();
+        return n;
+    };
+    // copies + kernel + result copies of one chunk on its slot's stream; `pk` = the chunk was packed into the slot's staging
+    auto enqueue = [&](int si, Chunk ch, bool pk, int set) -> int {
+        Slot &s = ctx->slots[si];
+        auto &exc_parts = ctx->exc_parts[set];
+        const u64 r0 = ch.q0 * mates, r1 = ch.q1 * mates, nr = r1 - r0, nq = ch.q1 - ch.q0, nb = offsets[r1] - offsets[r0];
+        ClassifyPlan pl = plan_for(nq, pk);
+        if(pk && !pl.packed) return ctx->fail(BNS_E_STATE, "packed chunk without a packed-input kernel");
+        const u64 n_units = (nb + 7) / 8, n_sw = (nb + 255) / 256;
+        u64 n_exc = 0;
+        int rc = ensure(s.d_out, s.cap_out, 4 * nq);
+        if(rc == BNS_OK) rc = ensure(s.d_offsets, s.cap_offsets, nr + 1);
+        if(rc == BNS_OK) rc = ensure(s.d_bases, s.cap_bases, pk ? 2 * n_units + 64 : nb + 16);
+        if(rc == BNS_OK && pk) {
+            for(auto &v : exc_parts) n_exc += v.size();
+            rc = ensure(s.d_susp, s.cap_d_susp, n_sw + 2);
+            if(rc == BNS_OK) rc = ensure(s.d_exc, s.cap_d_exc, n_exc + 1);
+            if(rc == BNS_OK) rc = ensure_pinned(s.h_exc, s.cap_h_exc, n_exc + 1);
+            if(n_exc >= 0xffffffffull) rc = BNS_E_CAPACITY;
+        }
+        if(rc != BNS_OK) return ctx->fail(rc, "device workspace");
+        if(ch.fixed_len) { pl.fixed_len = ch.fixed_len; pl.fixed_base = offsets[r0]; }
+        PackedIn pki{nullptr, nullptr, 0u, 0ull};
+        if(pk) {
+            u64 at = 0;
+            for(auto &v : exc_parts) { if(!v.empty()) memcpy(s.h_exc + at, v.data(), v.size() * 8); at += v.size(); }
+            CK(cudaMemcpyAsync(s.d_bases, s.h_units, 2 * n_units + 32, cudaMemcpyHostToDevice, s.st));   // + the zeroed slack the last tile may touch
+            CK(cudaMemcpyAsync(s.d_susp, s.h_susp, (n_sw + 2) * 4, cudaMemcpyHostToDevice, s.st));
+            if(n_exc) CK(cudaMemcpyAsync(s.d_exc, s.h_exc, n_exc * 8, cudaMemcpyHostToDevice, s.st));
+            pki = PackedIn{s.d_susp, (const unsigned long long *)s.d_exc, (u32)n_exc, offsets[r0]};
+            ctx->stats.h2d_bytes += 2 * n_units + 32 + (n_sw + 2) * 4 + n_exc * 8;
+        } else {
+            CK(cudaMemcpyAsync(s.d_bases, bases + offsets[r0], nb, cudaMemcpyHostToDevice, s.st));
+            ctx->stats.h2d_bytes += nb;
+        }
+        if(!pl.fixed_len) { CK(cudaMemcpyAsync(s.d_offsets, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, s.st)); ctx->stats.h2d_bytes += 8 * (nr + 1); }
+        CK(cudaEventRecord(s.h2d_done, s.st));
+        int nl = 1;
+        CK(cudaEventRecord(s.ka, s.st));
+        CK(launch_classify(ctx->enc, pl, s.st, pk ? s.d_bases : s.d_bases - offsets[r0], s.d_offsets, nq, mates, offsets[r1],
+                           table_view(ctx), tax_view(ctx), s.d_out, n_hit_out ? s.d_out + nq : nullptr,
+                           n_missing_out ? s.d_out + 2 * nq : nullptr, nullptr, nullptr, mate1_kmers_out ? s.d_out + 3 * nq : nullptr, ctx->ring_cap,
+                           ctx->d_counters, ctx->d_status, s.d_defer, s.d_defer_cnt, &nl, nullptr, ctx->d_big, pk ? &pki : nullptr));
+        CK(cudaEventRecord(s.kb, s.st));
+        s.k_timed = true;
+        ctx->stats.kernel_launches += nl;
+        CK(cudaMemcpyAsync(taxon_out + ch.q0, s.d_out, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(n_hit_out) CK(cudaMemcpyAsync(n_hit_out + ch.q0, s.d_out + nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(n_missing_out) CK(cudaMemcpyAsync(n_missing_out + ch.q0, s.d_out + 2 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        if(mate1_kmers_out) CK(cudaMemcpyAsync(mate1_kmers_out + ch.q0, s.d_out + 3 * nq, nq * 4, cudaMemcpyDeviceToHost, s.st));
+        ctx->stats.d2h_bytes += nq * 4 * (1 + (n_hit_out != nullptr) + (n_missing_out != nullptr) + (mate1_kmers_out != nullptr));
+        ctx->stats.reads_processed += nr;
+        ctx->stats.bases_processed += nb;
+        s.busy = true; s.raw = !pk; s.reserved = false;
+        return BNS_OK;
+    };
+    // the worker threads pack the chunk into the slot's staging buffers (pieces of whole suspicious-bit words)
+    auto start_pack = [&](int si, Chunk ch, int set) -> int {
+        Slot &s = ctx->slots[si];
+        s.busy = s.reserved = true; s.raw = false;
+        const u64 b0 = offsets[ch.q0 * mates], nb = offsets[ch.q1 * mates] - b0, n_units = (nb + 7) / 8, n_sw = (nb + 255) / 256;
+        int rc = ensure_pinned(s.h_units, s.cap_h_units, n_units + 32);
+        if(rc == BNS_OK) rc = ensure_pinned(s.h_susp, s.cap_h_susp, n_sw + 2);
+        if(rc != BNS_OK) return ctx->fail(rc, "pinned staging memory");
+        memset(s.h_units + n_units, 0, 64);
+        s.h_susp[n_sw] = s.h_susp[n_sw + 1] = 0;
+        const unsigned tasks = std::max(1u, std::min<unsigned>(pool.size() * 2, (unsigned)((nb + 65535) / 65536)));
+        const u64 per = ((nb + tasks - 1) / tasks + 255) / 256 * 256;
+        ctx->exc_parts[set].resize(tasks);
+        for(auto &v : ctx->exc_parts[set]) v.clear();
+        const char *src = bases + b0;
+        uint16_t *hu = s.h_units; u32 *hs = s.h_susp;
+        auto *parts = &ctx->exc_parts[set];
+        pool.start(tasks, [=](unsigned t) {
+            const u64 b = std::min(nb, per * t), e = std::min(nb, per * (t + 1));
+            if(e > b) pack_range(src + b, e - b, hu + b / 8, hs + b / 256, (*parts)[t], b / 8);
+        });
+        return BNS_OK;
+    };
+
+    size_t c_next = 0;
+    int rc = BNS_OK;
+    bool packing = false;                                              // the workers are on pack_chunk, bound for slot pack_slot
+    int pack_slot = -1, pack_set = 0;
+    Chunk pack_chunk{0, 0, 0u};
+    const bool verbose = getenv("BNS_B200_VERBOSE") != nullptr;
+    u64 n_packed = 0, n_raw = 0;
+    double t_idle = 0, t_enq = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_free = now();                                             // since when the workers have had nothing to do
+    const double t_call = t_free;
+    while(rc == BNS_OK && (c_next < chunks.size() || packing)) {
+        bool progressed = false;
+        int done_slot = -1, done_set = 0;
+        Chunk done_chunk{0, 0, 0u};
+        if(packing && pool.done()) {                                   // (a) a packed chunk is ready ...
+            done_slot = pack_slot; done_chunk = pack_chunk; done_set = pack_set;
+            packing = false;
+            t_free = now();
+            progressed = true;
+        }
+        if(!packing && c_next < chunks.size()) {                       // (b) ... the workers go on with the next one first ...
+            const int si = free_slot();
+            if(si >= 0) {
+                pack_chunk = chunks[c_next++];
+                pack_slot = si;
+                pack_set ^= 1;
+                rc = start_pack(si, pack_chunk, pack_set);
+                if(rc != BNS_OK) break;
+                t_idle += now() - t_free;
+                packing = true;
+                progressed = true;
+            }
+        }
+        if(done_slot >= 0) {                                           // ... then the ready chunk's copies and kernel are queued
+            const double t0 = now();
+            rc = enqueue(done_slot, done_chunk, true, done_set);
+            t_enq += now() - t0;
+            ++n_packed;
+            if(rc != BNS_OK) break;
+        }
+        if(ctx->pack_mode == 2 && c_next < chunks.size() && raw_queued() < 2) {   // (c) keep the copy engine fed with ASCII chunks
+            const int si = free_slot();
+            if(si >= 0) {
+                rc = enqueue(si, chunks[c_next++], false, 0);
+                ++n_raw;
+                progressed = true;
+            }
+        }
+        if(!progressed) std::this_thread::yield();
+    }
+    pool.wait();
+    for(int i = 0; i < N_SLOTS; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->slots[i].st);
+        if(e != cudaSuccess && rc == BNS_OK) rc = ctx->cuda_fail(e, "cudaStreamSynchronize");
+        ctx->slots[i].busy = ctx->slots[i].reserved = false;
+        collect_kernel_time(ctx, ctx->slots[i]);
+    }
+    if(verbose)
+        fprintf(stderr, "[classify_batch] %llu chunks packed on %u threads (%s), %llu as ASCII; %.2f ms in all, workers without a chunk %.2f ms, queueing packed chunks %.2f ms\n",
+                (unsigned long long)n_packed, pool.size(), pack_isa(), (unsigned long long)n_raw, (now() - t_call) * 1e3, t_idle * 1e3, t_enq * 1e3);
+    return rc;
+}
+
 int bns_b200_classify_batch(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, uint64_t n_reads, int paired,
                             uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out,
                             uint32_t *taxa_out, const uint64_t *taxa_offsets) {
@@ -1478,6 +1757,16 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
     if(!n_rec_total) return BNS_OK;
     CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
     CK(cudaStreamSynchronize(ctx->slots[0].st));
+    // large batches of what `bonsai classify` runs: the host's cores pack chunks to 2 bits next to the chunks crossing as ASCII
+    if(ctx->pack_threads > 0 && !taxa_out && offsets[n_rec_total * mates] - offsets[0] >= ctx->pack_min_bases &&
+       plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec_total, mates, false, mate1_kmers_out != nullptr,
+                     n_hit_out || n_missing_out, false, true).packed) {
+        rc = classify_batch_packing(ctx, bases, offsets, n_rec_total, mates, taxon_out, n_hit_out, n_missing_out, mate1_kmers_out);
+        if(rc != BNS_OK) return rc;
+        u32 status = 0;
+        CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
+        return check_status(ctx, status & 11u);
+    }
     int slot_i = 0;
     u64 q0 = 0;                                                    // record cursor
     while(q0 < n_rec_total) {
@@ -1541,7 +1830,7 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
         ctx->stats.reads_processed += nr;
         ctx->stats.bases_processed += nb;
         q0 = q1;
-        slot_i = (slot_i + 1) % N_SLOTS;
+        slot_i = (slot_i + 1) % N_RING;
     }
     for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); collect_kernel_time(ctx, ctx->slots[i]); }
     u32 status = 0;
@@ -1669,10 +1958,10 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
         ctx->stats.bases_processed += nb;
         pend[slot_i].live = true; pend[slot_i].q0 = q0; pend[slot_i].nq = nq;
         q0 = q1;
-        slot_i = (slot_i + 1) % N_SLOTS;
+        slot_i = (slot_i + 1) % N_RING;
     }
-    for(int i = 0; i < N_SLOTS; ++i) {                                      // in chunk order: positions in runs_out follow the records
-        rc = finalize((slot_i + i) % N_SLOTS);
+    for(int i = 0; i < N_RING; ++i) {                                       // in chunk order: positions in runs_out follow the records
+        rc = finalize((slot_i + i) % N_RING);
         if(rc != BNS_OK) return rc;
     }
     *n_runs_total_out = used;
@@ -1680,6 +1969,14 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
     CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
     return check_status(ctx, status & 11u);
 }
+
+int bns_b200_set_host_pack_threads(bns_b200_t *ctx, uint32_t n_threads) {
+    if(!ctx) return BNS_E_INVAL;
+    const int n = (int)std::min<uint32_t>(n_threads, 64u);
+    if(n != ctx->pack_threads) { ctx->pool.reset(); ctx->pack_threads = n; }
+    return BNS_OK;
+}
+int bns_b200_host_pack_threads(const bns_b200_t *ctx) { return ctx ? ctx->pack_threads : BNS_E_INVAL; }
 
 int bns_b200_device_status(bns_b200_t *ctx) {
     if(!ctx) return BNS_E_INVAL;

@@ -226,14 +226,23 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
 // (taxid << 32 | run length) words at runs_out[run_pos_out[r] .. + n_runs_out[r]). A record's runs are gathered in shared
 // memory and placed into a stretch of runs_out the warp reserved with one atomic per RUN_BLOCK entries (runs_total = entries
 // handed out so far, gaps included).
-template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC, bool RUNS>
+// PK: the bases arrive 2-bit packed by the host (bns_pack.cpp; 4x fewer bytes over PCIe): `bases` is the stream of 16-bit units
+// (8 bases each, first base in the top bits; base index g of the batch sits in unit (g - pk.base0) >> 3), pk.susp one bit per
+// unit ("holds a byte that is not ACGTacgt"), pk.exc the sorted (unit << 8 | invalid-bit mask) words of those units.
+__device__ __forceinline__ u32 pk_invalid_mask(const PackedIn &pk, u64 unit) {     // rare: binary search of the exceptions
+    u32 lo = 0, hi = pk.n_exc;
+    while(lo < hi) { const u32 mid = (lo + hi) >> 1; if((pk.exc[mid] >> 8) < unit) lo = mid + 1; else hi = mid; }
+    return (lo < pk.n_exc && (pk.exc[lo] >> 8) == unit) ? (u32)(pk.exc[lo] & 0xffu) : 0u;
+}
+template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC, bool RUNS, bool PK = false>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
                       u32 *__restrict__ nmiss_out, unsigned long long *__restrict__ counters, u32 *__restrict__ status,
                       u32 *__restrict__ defer_idx, unsigned long long *__restrict__ defer_cnt, u32 fixed_len, u64 fixed_base,
                       u32 mates, u32 *__restrict__ mate1_out, u64 *__restrict__ runs_out, u64 runs_cap,
-                      unsigned long long *__restrict__ runs_total, u64 *__restrict__ run_pos_out, u32 *__restrict__ n_runs_out) {
+                      unsigned long long *__restrict__ runs_total, u64 *__restrict__ run_pos_out, u32 *__restrict__ n_runs_out,
+                      const PackedIn pk) {
     // n_records counts SEQUENCES here: a record is `mates` (1 or 2) consecutive sequences sharing one taxon counter
     // (classify_seq encodes the second mate into the same counter, classifier.h:233-236); a batch of 32 sequences holds
     // whole records. mate1_out: k-mers the first mate produced (classifier.h:232's first ambig_count term).
@@ -327,6 +336,19 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     };
     // the 8-byte block of a record's first tile this lane stages -> s_rd[buf]: bases [rb, rb + min(rl, span))
     auto fetch_tile = [&](u64 rb, u32 rl, u32 buf) {
+        if(PK) {
+            // packed input: the (at most 24) units of the tile are bytes [2 * U0, 2 * (U0 + nun + 1)) of the unit stream, fetched as
+            // up to seven aligned 8-byte blocks; entry 8 of the buffer takes the two suspicious-bit words the units fall into
+            if(!rl) return;
+            const u64 g = rb - pk.base0, U0 = g >> 3, byte0 = (2 * U0) & ~7ull;
+            const u32 nun = ((u32)(g & 7u) + min(rl, span) + 7) >> 3;
+            const u32 nblk = (u32)((2 * (U0 + nun + 1) - byte0 + 7) >> 3);
+            if(lane < nblk) async8(s_rd + buf * 32 + lane, bases + byte0 + 8 * lane);
+            else if(lane == 8 || lane == 9)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared((u32 *)(s_rd + buf * 32 + 8) + (lane - 8))),
+                             "l"(pk.susp + (U0 >> 5) + (lane - 8)) : "memory");
+            return;
+        }
         const char *a0 = bases + rb;
         const u32 shift = (u32)((uintptr_t)a0 & 7u);
         const u32 nblk = rl ? (shift + min(rl, span) + 7) >> 3 : 0u;      // <= 22 for k <= 32
@@ -374,6 +396,17 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             if(j == 0) asm volatile("cp.async.wait_group 1;" ::: "memory"); else async_wait_all();
             __syncwarp();
             const uint2 pre = s_rd[tb * 32 + lane];
+            u32 pre_c16 = 0, pre_susp = 0;                                 // PK: this lane's unit of the first tile and its suspicious bit
+            if(PK && L != 0) {
+                const u64 g = rb - pk.base0, U0 = g >> 3;
+                const u32 nun = ((u32)(g & 7u) + min(L, span) + 7) >> 3;
+                if(lane <= nun) {                                      // one more than the tile covers: a lane's word takes the next lane's unit
+                    pre_c16 = reinterpret_cast<const unsigned short *>(s_rd + tb * 32)[(u32)(U0 & 3u) + lane];
+                    const u32 *sw = reinterpret_cast<const u32 *>(s_rd + tb * 32 + 8);
+                    const u64 un = U0 + lane;
+                    pre_susp = (sw[(un >> 5) - (U0 >> 5)] >> (un & 31u)) & 1u;
+                }
+            }
             // request the first tile of the record after this one before working on this one
             u64 xb = 0; u32 xl = 0;
             {
@@ -393,10 +426,25 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                 const u32 npos = L - c + 1;
                 for(u32 p0 = 0; p0 < npos; p0 += TILE) {
                     // ---- stage: 8 bases per lane -> 16 bits per lane -> one 16-base word per lane ----------------
-                    const uint2 v = p0 ? tile_block(rb + p0, L - p0) : pre;
-                    const u32 shift = (u32)((uintptr_t)(bases + rb + p0) & 7u);
-                    u32 c16;
-                    const u32 susp = pack8_fast(v, c16);
+                    uint2 v = make_uint2(0x41414141u, 0x41414141u);
+                    u32 shift, c16, susp;
+                    u64 pk_unit = 0;
+                    if(PK) {
+                        // this lane's unit of the packed stream and its "not all ACGT" bit
+                        const u64 g = rb - pk.base0 + p0;
+                        shift = (u32)(g & 7u);
+                        pk_unit = (g >> 3) + lane;
+                        const u32 nun = (shift + min(L - p0, span) + 7) >> 3;          // units the tile covers (<= 23)
+                        c16 = pre_c16; susp = pre_susp;
+                        if(p0 && lane <= nun) {                                        // later tiles of a long record: plain loads (rare)
+                            c16 = __ldg(reinterpret_cast<const unsigned short *>(bases) + pk_unit);
+                            susp = (__ldg(pk.susp + (pk_unit >> 5)) >> (pk_unit & 31u)) & 1u;
+                        } else if(p0) { c16 = 0; susp = 0; }
+                    } else {
+                        v = p0 ? tile_block(rb + p0, L - p0) : pre;
+                        shift = (u32)((uintptr_t)(bases + rb + p0) & 7u);
+                        susp = pack8_fast(v, c16);
+                    }
                     const bool slow = __any_sync(FULL, susp != 0);
                     const u32 word = (c16 << 16) | __shfl_down_sync(FULL, c16, 1);   // bases [8*lane, 8*lane+16) of the tile
                     const u32 q0 = shift + PPL * lane, ci = q0 >> 3, s = (q0 & 7u) * 2u;
@@ -406,8 +454,9 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     const u32 nlive = left > PPL * lane ? min((u32)PPL, left - PPL * lane) : 0u;
                     u32 mask = (1u << nlive) - 1;
                     if(slow) {                                         // some staged byte is not ACGTacgt (rare)
-                        u32 b8, cc;
-                        pack8(v, cc, b8);
+                        u32 b8 = 0, cc;
+                        if(PK) { if(susp) b8 = pk_invalid_mask(pk, pk_unit); }
+                        else pack8(v, cc, b8);
                         const u32 bw = (b8 << 8) | __shfl_down_sync(FULL, b8, 1);    // invalid bits of the same 16 bases, first at bit 15
                         const u32 b0 = __shfl_sync(FULL, bw, ci), b1 = __shfl_sync(FULL, bw, ci + 2),
                                   b2 = __shfl_sync(FULL, bw, ci + 4), b3 = __shfl_sync(FULL, bw, ci + 6);

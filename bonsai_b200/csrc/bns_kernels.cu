@@ -1192,12 +1192,19 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 }
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
                               unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64, u32, u32 *,
-                              u64 *, u64, unsigned long long *, u64 *, u32 *);
+                              u64 *, u64, unsigned long long *, u64 *, u32 *, const PackedIn);
 static size_t lean_smem(bool runs) {
     return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES + (runs ? RUNBUF * sizeof(u64) : 0));
 }
 template <int MODE, bool CANON, bool COUNTS, int KEY, bool RUNS = false>
-static classify_u_fn pick_lean_k(u32 k, bool loc) {
+static classify_u_fn pick_lean_k(u32 k, bool loc, bool pk = false) {
+    if(pk) {                                                          // host-packed bases: LEAN_U without run lists only (plan_classify)
+        if(MODE != LEAN_U || RUNS) return nullptr;
+        constexpr int M = (MODE == LEAN_U && !RUNS) ? MODE : LEAN_U;   // keeps the other modes from instantiating packed variants
+        constexpr bool C2 = (MODE == LEAN_U && !RUNS) ? CANON : true, N2 = (MODE == LEAN_U && !RUNS) ? COUNTS : true;
+        if(loc) return k == 31 ? bns_classify_u_kernel<M, C2, 31, N2, 0, true, false, true> : bns_classify_u_kernel<M, C2, 0, N2, 0, true, false, true>;
+        return k == 31 ? bns_classify_u_kernel<M, C2, 31, N2, 0, false, false, true> : bns_classify_u_kernel<M, C2, 0, N2, 0, false, false, true>;
+    }
     if(loc) return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, true, RUNS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, true, RUNS>;
     return k == 31 ? bns_classify_u_kernel<MODE, CANON, 31, COUNTS, KEY, false, RUNS> : bns_classify_u_kernel<MODE, CANON, 0, COUNTS, KEY, false, RUNS>;
 }
@@ -1218,7 +1225,11 @@ static int lean_key(const EncParams &P) {
     if(!P.cast_wrap && (P.score_kind == SC_ENT_NOTFULL || (P.score_kind == SC_ENT_ROLL && P.k >= 28))) return LEAN_KEY_ELEM;
     return LEAN_KEY_PAIR;
 }
-static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false) {
+static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false, bool pk = false) {
+    if(pk) {
+        if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc, true) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc, true);
+        return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k, loc, true) : pick_lean_k<LEAN_U, false, false, 0>(P.k, loc, true);
+    }
     if(mode == LEAN_S) return pick_lean_k<LEAN_S, false, true, 0>(P.k, loc);
     if(mode == LEAN_K) return pick_lean_key<LEAN_K, true>(P.k, lean_key(P), loc);
     if(mode == LEAN_R) return P.canon_emit ? pick_lean_key<LEAN_R, true>(P.k, lean_key(P), loc) : pick_lean_key<LEAN_R, false>(P.k, lean_key(P), loc);
@@ -1227,7 +1238,8 @@ static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool l
     return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k, loc) : pick_lean_k<LEAN_U, false, false, 0>(P.k, loc);
 }
 
-ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts, bool runs) {
+ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts, bool runs,
+                           bool packed) {
     ClassifyPlan pl;
     // run lists come out of the lean kernel for what `bonsai classify` runs (every k-mer, no window); the other encoders keep the
     // ordered hit list of the generic kernel, run-length encoded by bns_rle_kernel
@@ -1239,9 +1251,12 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     pl.lean = pl.lean_mode >= 0;
     pl.runs = runs && pl.lean_mode == LEAN_U;
     pl.counts = counts || mates == 2 || mate1 || runs;                // the pair bookkeeping lives in the COUNTS variants
+    // host-packed bases (bns_pack.h) are read by the variants of what `bonsai classify` runs; a database of more than AGG_CAP
+    // values may send records to the generic kernel's second pass, which reads ASCII
+    pl.packed = packed && pl.lean_mode == LEAN_U && !pl.runs && T.n_values <= (u32)AGG_CAP;
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
         pl.smem = lean_smem(pl.runs);
         cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1274,14 +1289,16 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u64 n_records, u32 mates, u64 total_bases, const TableView &T, const TaxView &X,
                             u32 *taxon_out, u32 *nhit_out, u32 *nmiss_out, u32 *taxa_out, const u64 *taxa_offsets,
                             u32 *mate1_out, u32 ring_cap, unsigned long long *counters, u32 *status,
-                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro, u32 *big_scratch) {
+                            u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro, u32 *big_scratch, const PackedIn *pk) {
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
+        if(pl.packed && !pk) return cudaErrorInvalidValue;
+        const PackedIn pki = pl.packed ? *pk : PackedIn{nullptr, nullptr, 0u, 0ull};
         f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,
                                                     counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base, mates, mate1_out,
                                                     pl.runs ? ro->runs : nullptr, pl.runs ? ro->cap : 0, pl.runs ? ro->total : nullptr,
-                                                    pl.runs ? ro->run_pos : nullptr, pl.runs ? ro->n_runs : nullptr);
+                                                    pl.runs ? ro->run_pos : nullptr, pl.runs ? ro->n_runs : nullptr, pki);
         cudaError_t e = cudaGetLastError();
         if(e != cudaSuccess || !pl.second_pass) return e;
     } else {

@@ -65,7 +65,10 @@ typedef struct bns_b200_config {
     uint32_t entropy_cast;      /* BNS_CAST_* */
     int32_t  device;            /* CUDA ordinal, -1 = current device */
     uint32_t n_gpus;            /* bns_b200_open_multi: contexts to open when its n_gpus argument is 0 (0 = every visible device) */
-    uint32_t reserved[6];
+    uint32_t host_pack_threads; /* host-buffer classify calls pack the bases to 2 bits on this many worker threads of the caller's machine
+                                 * (chunk by chunk, next to chunks that cross as ASCII: 38 instead of 150 bytes per 150 bp read over PCIe).
+                                 * 0 = the process's share of the hardware threads, 0xffffffff = off (every chunk crosses as ASCII) */
+    uint32_t reserved[5];
 } bns_b200_config;
 
 typedef struct bns_b200_ctx bns_b200_t;
@@ -199,6 +202,10 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out,
                                  uint64_t *runs_out, uint64_t runs_cap, uint64_t *run_pos_out, uint32_t *n_runs_out,
                                  uint64_t *n_runs_total_out);
+/* Worker threads the host-buffer classify calls pack bases with (see bns_b200_config.host_pack_threads); 0 = every chunk
+ * crosses PCIe as ASCII. The second call reports the current number. */
+int bns_b200_set_host_pack_threads(bns_b200_t *ctx, uint32_t n_threads);
+int bns_b200_host_pack_threads(const bns_b200_t *ctx);
 /* Same with every buffer resident on the context's device; asynchronous on `stream` (a cudaStream_t). Window of record r in
  * d_taxa: at least (bases of the record) + 2 entries. Nothing is read back: conditions the host-pointer calls report as
  * BNS_E_CAPACITY (a record of 2^32-1 bases or more, more than 65536 distinct taxa in one record) are latched on the device

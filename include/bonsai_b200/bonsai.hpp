@@ -127,6 +127,9 @@ inline std::shared_ptr<Handle> open_handle(const Spacer &sp, u32 score, bool can
     // the reference's entropy score casts a negative double to u64 (UB): do what a `-march=native` build of the reference
     // does on THIS host -- vcvttsd2usi saturates where AVX-512 exists, the cvttsd2si sequence wraps elsewhere
     cfg.entropy_cast = __builtin_cpu_supports("avx512f") ? BNS_CAST_SATURATE : BNS_CAST_WRAP;
+    // the callers of this header run their own threads next to the device calls (process_dataset's readers and formatters, the
+    // reference's kt_for workers): the library does not add packing threads of its own unless BNS_B200_HOST_PACK asks for them
+    cfg.host_pack_threads = 0xffffffffu;
     auto ret = std::make_shared<Handle>();
     const int rc = bns_b200_open(&cfg, &ret->h);
     if(rc) BNS_RUNTIME_ERROR(std::string("bns_b200_open: ") + bns_b200_last_error(nullptr));

@@ -1,0 +1,23 @@
+#!/bin/bash
+# host packing, second pass: the packer alone on the box's cores, then bench.py e2e with the pipelined dispatcher
+mkdir -p gpurun_out
+g++ -O3 -std=c++17 -pthread -I bonsai_b200/csrc tests/host/pack_check.cpp bonsai_b200/csrc/bns_pack.cpp -o /tmp/pack_check
+for t in 2 4 8 12 15; do /tmp/pack_check bench $t | tail -1; done
+BNS_B200_PACK_NO_NT=1 /tmp/pack_check bench 15 | tail -1
+BNS_B200_PACK_NO_NT=1 /tmp/pack_check bench 8 | tail -1
+python -m pytest tests -m gpu -x -q -k "host_packed" 2>&1 | tail -3
+for cfg in "15 hybrid 262144" "15 pack 262144" "15 hybrid 131072" "8 hybrid 131072" "15 hybrid 65536"; do
+  set -- $cfg
+  echo "== BNS_B200_HOST_PACK=$1 mode=$2 chunk=$3"
+  BNS_B200_VERBOSE=1 BNS_B200_HOST_PACK=$1 BNS_B200_HOST_PACK_MODE=$2 BNS_B200_PACK_CHUNK_READS=$3 python bench.py --no-sub --no-cpu-baseline --steps 20 --e2e-steps 10 > gpurun_out/pack2_$1_$2_$3.json 2> gpurun_out/pack2_$1_$2_$3.err
+  grep "classify_batch" gpurun_out/pack2_$1_$2_$3.err | tail -2
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/pack2_$1_$2_$3.json").read().strip().splitlines()[-1])
+    e = d["e2e"]
+    print("value %.0f  e2e %.1f Mreads/s  h2d %.0f MB/step (%.1f GB/s)  match %s" % (d["value"], e["value"], e["h2d_bytes_per_step"] / 1e6, e["h2d_gbs"], e["taxids_match_device_path"]))
+except Exception as ex:
+    print("failed", ex); print(open("gpurun_out/pack2_$1_$2_$3.err").read()[-2000:])
+PY
+done

@@ -2,6 +2,7 @@
 the database file is the raw khash_t(c) layout the reference intends (database.h:81-102, util.h:281-296), so the
 restated kh_get must find every key in the arrays the writer produced."""
 import os
+import shutil
 import struct
 import subprocess
 
@@ -211,3 +212,21 @@ def test_cpp_encoder_file_overloads_batching(tmp_path):
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") >= 48, r.stdout
+
+
+@pytest.mark.parametrize("isa", ["native", "avx2", "scalar"])
+def test_host_packer_matches_its_format(tmp_path, isa):
+    """bonsai_b200/csrc/bns_pack.cpp (ASCII bases -> 2-bit units + suspicious bits + exception words, what the packed-input
+    kernel reads) against a byte-at-a-time model of the format, for every instruction-set body this machine can run, and cut
+    into pieces on the worker pool: tests/host/pack_check.cpp, host code only."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(here, "..", "bonsai_b200", "csrc")
+    exe = str(tmp_path / "pack_check")
+    r = subprocess.run([shutil.which("g++") or "/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", csrc, "-o", exe,
+                        os.path.join(here, "host", "pack_check.cpp"), os.path.join(csrc, "bns_pack.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ)
+    if isa != "native":
+        env["BNS_B200_PACK_ISA"] = isa
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout + r.stderr

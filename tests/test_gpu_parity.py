@@ -393,6 +393,72 @@ def test_classify_ragged_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, geno
     assert t.size == 0
 
 
+@pytest.mark.parametrize("mode", ["pack", "hybrid"])
+def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, monkeypatch, mode):
+    """bns_b200_classify_batch with host packing threads (bns_b200_config.host_pack_threads): chunks packed to 2 bits on the
+    host and read by the packed-input kernel, alone ("pack") and next to chunks that cross as ASCII ("hybrid"), against the
+    oracle and the ASCII-only call: ragged, empty and long reads, N / lower case / arbitrary bytes, records that straddle
+    units, chunks and suspicious-bit words, a fixed-length batch (offsets generated on the device), mate pairs, both layouts."""
+    monkeypatch.setenv("BNS_B200_PACK_MIN_BASES", "1")
+    monkeypatch.setenv("BNS_B200_PACK_CHUNK_READS", "700")
+    monkeypatch.setenv("BNS_B200_HOST_PACK_MODE", mode)
+    db = dbcache.get("lex_k31_w31")
+    keys, vals, flags, nb, _ = oracle.db_arrays(db)
+    rb, ro, _ = H.make_reads(6000, seed=41, ragged=True)
+    reads = [bytes(rb[int(ro[i]):int(ro[i + 1])]) for i in range(ro.size - 1)]
+    rng = np.random.default_rng(5)
+    g = genomes
+    for i in range(0, len(reads), 7):                     # lower case, runs of N, arbitrary bytes
+        r = bytearray(reads[i])
+        if not r:
+            continue
+        if i % 3 == 0:
+            r = bytearray(bytes(r).lower())
+        elif i % 3 == 1:
+            a, nn = int(rng.integers(0, len(r))), int(rng.integers(1, 12))
+            r[a:a + nn] = b"N" * len(r[a:a + nn])
+        else:
+            for _ in range(3):
+                r[int(rng.integers(0, len(r)))] = int(rng.integers(0, 256))
+        reads[i] = bytes(r)
+    for _ in range(6):                                    # long records: many tiles, later tiles read the unit stream directly
+        s0 = int(rng.integers(0, g["bases"].size - 9000))
+        r = bytearray(g["bases"][s0:s0 + int(rng.integers(500, 9000))].tobytes())
+        r[len(r) // 2] = ord("n")
+        reads.insert(int(rng.integers(0, len(reads))), bytes(r))
+    bases, offs = po.pack_reads(reads)
+    fixed_b, fixed_o, _ = H.make_reads(5000, seed=43)
+    for layout in ("hash", "minimizer"):
+        monkeypatch.setenv("BNS_B200_LAYOUT", layout)
+        with capi.Context(31, 31, host_pack_threads=3) as ctx, capi.Context(31, 31, host_pack_threads=0) as plain:
+            for c in (ctx, plain):
+                c.load_table(keys, vals, flags, nb)
+                c.load_taxonomy(*H.toy_tax_arrays())
+            assert ctx.table_info()["layout"] == (1 if layout == "minimizer" else 0)
+            exp = oracle.classify(db, toy_tax, bases, offs, 31, 31)
+            h0 = ctx.stats()["h2d_bytes"]
+            got = ctx.classify(bases, offs)
+            packed_bytes = ctx.stats()["h2d_bytes"] - h0
+            ref = plain.classify(bases, offs)
+            for a, b, c in zip(exp, got, ref):
+                assert np.array_equal(a, b) and np.array_equal(a, c)
+            if mode == "pack":                            # the bases crossed as 2-bit units (+ offsets): well under one byte each
+                assert packed_bytes < bases.size * 0.25 + offs.size * 8 + 4096 * 16
+            t_only, _, _ = ctx.classify(bases, offs, want_counts=False)
+            assert np.array_equal(t_only, exp[0])
+            ne = ((offs.size - 1) // 2) * 2
+            expp = oracle.classify(db, toy_tax, bases[:int(offs[ne])], offs[:ne + 1], 31, 31, paired=True)
+            gotp = ctx.classify(bases[:int(offs[ne])], offs[:ne + 1], paired=True)
+            for a, b in zip(expp, gotp):
+                assert np.array_equal(a, b)
+            expf = oracle.classify(db, toy_tax, fixed_b, fixed_o, 31, 31)
+            gotf = ctx.classify(fixed_b, fixed_o)
+            for a, b in zip(expf, gotf):
+                assert np.array_equal(a, b)
+            st, sp = ctx.stats(), plain.stats()
+            assert st["n_classified"] == sp["n_classified"] + int((exp[0] != 0).sum()) + int((expp[0] != 0).sum()) + int((expf[0] != 0).sum())
+
+
 def test_classify_device_and_replication(capi, golden, gpu_dbs, reads2000):
     """device-resident call + the broadcast path (header, segments, commit) into a second context"""
     import torch
