@@ -1198,10 +1198,11 @@ static size_t lean_smem(bool runs) {
 }
 template <int MODE, bool CANON, bool COUNTS, int KEY, bool RUNS = false>
 static classify_u_fn pick_lean_k(u32 k, bool loc, bool pk = false) {
-    if(pk) {                                                          // host-packed bases: LEAN_U without run lists only (plan_classify)
-        if(MODE != LEAN_U || RUNS) return nullptr;
-        constexpr int M = (MODE == LEAN_U && !RUNS) ? MODE : LEAN_U;   // keeps the other modes from instantiating packed variants
-        constexpr bool C2 = (MODE == LEAN_U && !RUNS) ? CANON : true, N2 = (MODE == LEAN_U && !RUNS) ? COUNTS : true;
+    if(pk) {                                                          // host-packed bases: LEAN_U / LEAN_S without run lists (plan_classify)
+        constexpr bool OK = (MODE == LEAN_U || MODE == LEAN_S) && !RUNS;
+        if(!OK) return nullptr;
+        constexpr int M = OK ? MODE : LEAN_U;                          // keeps the other modes from instantiating packed variants
+        constexpr bool C2 = OK ? CANON : true, N2 = OK ? COUNTS : true;
         if(loc) return k == 31 ? bns_classify_u_kernel<M, C2, 31, N2, 0, true, false, true> : bns_classify_u_kernel<M, C2, 0, N2, 0, true, false, true>;
         return k == 31 ? bns_classify_u_kernel<M, C2, 31, N2, 0, false, false, true> : bns_classify_u_kernel<M, C2, 0, N2, 0, false, false, true>;
     }
@@ -1227,6 +1228,7 @@ static int lean_key(const EncParams &P) {
 }
 static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false, bool pk = false) {
     if(pk) {
+        if(mode == LEAN_S) return pick_lean_k<LEAN_S, false, true, 0>(P.k, loc, true);
         if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc, true) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc, true);
         return counts ? pick_lean_k<LEAN_U, false, true, 0>(P.k, loc, true) : pick_lean_k<LEAN_U, false, false, 0>(P.k, loc, true);
     }
@@ -1253,7 +1255,7 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     pl.counts = counts || mates == 2 || mate1 || runs;                // the pair bookkeeping lives in the COUNTS variants
     // host-packed bases (bns_pack.h) are read by the variants of what `bonsai classify` runs; a database of more than AGG_CAP
     // values may send records to the generic kernel's second pass, which reads ASCII
-    pl.packed = packed && pl.lean_mode == LEAN_U && !pl.runs && T.n_values <= (u32)AGG_CAP;
+    pl.packed = packed && (pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) && !pl.runs && T.n_values <= (u32)AGG_CAP;
     int nb = 0;
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);

@@ -394,7 +394,7 @@ def test_classify_ragged_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, geno
 
 
 @pytest.mark.parametrize("mode", ["pack", "hybrid"])
-def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, monkeypatch, mode):
+def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, golden, reads2000, monkeypatch, mode):
     """bns_b200_classify_batch with host packing threads (bns_b200_config.host_pack_threads): chunks packed to 2 bits on the
     host and read by the packed-input kernel, alone ("pack") and next to chunks that cross as ASCII ("hybrid"), against the
     oracle and the ASCII-only call: ragged, empty and long reads, N / lower case / arbitrary bytes, records that straddle
@@ -428,6 +428,22 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, m
         reads.insert(int(rng.integers(0, len(reads))), bytes(r))
     bases, offs = po.pack_reads(reads)
     fixed_b, fixed_o, _ = H.make_reads(5000, seed=43)
+    # the spaced-seed encoder (BASELINE configs[3]) reads packed chunks too: the reference-generated golden answers
+    spec = golden["classify"]["config4_spaced"]
+    sk, sv, sf, snb, _ = oracle.db_arrays(dbcache.get(spec["db"]))
+    with capi.Context(spec["k"], spec["w"], spec["gaps"], capi.SCORE_LEX, spec["canon"], spec["api"], host_pack_threads=3) as sctx:
+        sctx.load_table(sk, sv, sf, snb)
+        sctx.load_taxonomy(*H.toy_tax_arrays())
+        h0 = sctx.stats()["h2d_bytes"]
+        t, nh, nm = sctx.classify(reads2000[0], reads2000[1])
+        assert t.tolist() == spec["taxon"] and nh.tolist() == spec["nhit"] and nm.tolist() == spec["nmiss"]
+        if mode == "pack":
+            assert sctx.stats()["h2d_bytes"] - h0 < reads2000[0].size * 0.3 + 4096 * 16
+        db4 = dbcache.get(spec["db"])
+        exp4 = oracle.classify(db4, toy_tax, bases, offs, spec["k"], spec["w"], spec["gaps"], 0, spec["canon"], spec["api"])
+        got4 = sctx.classify(bases, offs)
+        for a, b in zip(exp4, got4):
+            assert np.array_equal(a, b)
     for layout in ("hash", "minimizer"):
         monkeypatch.setenv("BNS_B200_LAYOUT", layout)
         with capi.Context(31, 31, host_pack_threads=3) as ctx, capi.Context(31, 31, host_pack_threads=0) as plain:
