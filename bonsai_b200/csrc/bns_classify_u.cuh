@@ -27,13 +27,19 @@ constexpr int RB = 32;                       // records per warp batch
 constexpr int LEAN_STAGE_BYTES = 2 * (RB + 2) * 8 + 2 * 32 * 8;      // per warp: offsets ring + first-tile ring
 constexpr int RUNBUF = 128;                  // run-list variants: runs of one record buffered per warp before they are placed
 constexpr u32 RUN_BLOCK = 256;               // ... into stretches of the chunk's run buffer a warp reserves with one atomic each
+// Warps per CTA of the lean kernel: compiled for up to LEAN_WARPS (one CTA of 24 warps per SM at 80 registers), launched with
+// that many when the batch fills every SM with such CTAs and with LEAN_WARPS_SMALL (three CTAs per SM) when it does not.
+// Same 24 warps per SM either way; measured on B200 (profiles/occupancy_r02.log), 10 M reads of configs[1] / the 2^28-key stress
+// table: 6 warps x 4 CTAs 1 560 / 492 Mreads/s, 8 x 3 1 611 / 502, 12 x 2 1 649 / 509, 24 x 1 1 729 / 527; more warps at fewer
+// registers lose (7 x 4 and 9 x 3 at 72 registers: 1 523 / 462 and 1 526 / 454).
 #ifndef BNS_LEAN_WARPS
-#define BNS_LEAN_WARPS 8
+#define BNS_LEAN_WARPS 24
 #endif
 #ifndef BNS_CLASSIFY_U_MIN_CTAS
-#define BNS_CLASSIFY_U_MIN_CTAS 3
+#define BNS_CLASSIFY_U_MIN_CTAS 1
 #endif
-constexpr int LEAN_WARPS = BNS_LEAN_WARPS;   // warps per CTA of the lean kernel
+constexpr int LEAN_WARPS = BNS_LEAN_WARPS;   // most warps a CTA of the lean kernel is launched with (blockDim.x / 32 is what it has)
+constexpr int LEAN_WARPS_SMALL = 8;
 
 
 __device__ __forceinline__ void ld_bucket8(const void *p, u32 (&w)[8]) {
@@ -250,7 +256,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     // not read (the host did not even copy it: 8 of the 158 bytes per 150 bp read that cross PCIe)
     __shared__ __align__(16) uint4 s_vi[VI_CAP];
     __shared__ __align__(8) unsigned long long s_mbar;
-    const u32 lane = lane_id(), wid = threadIdx.x >> 5;
+    const u32 lane = lane_id(), wid = threadIdx.x >> 5, n_cta_warps = blockDim.x >> 5;
     const u32 k = KT ? (u32)KT : P.k;
     constexpr bool CANON_ELEM = MODE == LEAN_K || (MODE == LEAN_U && CANON);
     const bool staged = T.n_values > 0 && T.n_values <= (u32)VI_CAP;
@@ -287,10 +293,10 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     // with other loads (ncu showed the register prefetch of v2 stalling a full DRAM latency per record for that reason).
     //   s_off[2][RB+1]  offsets of the current / next batch of records
     //   s_rd[2][32]     8 bytes per lane of the first tile of the current / next record
-    u64 *s_off = (u64 *)(g_smem + (size_t)LEAN_WARPS * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
+    u64 *s_off = (u64 *)(g_smem + (size_t)n_cta_warps * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
     uint2 *s_rd = (uint2 *)(s_off + 2 * (RB + 2));
     // run lists: this warp's record buffer, its reserved stretch of runs_out, and the run that is still open
-    u64 *s_run = (u64 *)(g_smem + (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES) + (size_t)wid * RUNBUF * sizeof(u64));
+    u64 *s_run = (u64 *)(g_smem + (size_t)n_cta_warps * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES) + (size_t)wid * RUNBUF * sizeof(u64));
     u64 blk_pos = 0;
     u32 blk_left = 0, run_val = VAL_MISS, run_len = 0, n_runs_rec = 0;
     bool run_direct = false;                                          // this record's runs go straight to runs_out[blk_pos ...]
@@ -313,9 +319,9 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     s_rd[lane] = make_uint2(0x41414141u, 0x41414141u);                 // lanes past a tile read 'A's: code 0, never "suspicious"
     s_rd[32 + lane] = make_uint2(0x41414141u, 0x41414141u);
     __syncwarp();
-    const u64 nwarps = (u64)gridDim.x * LEAN_WARPS;
+    const u64 nwarps = (u64)gridDim.x * n_cta_warps;
     const u64 n_batches = (n_records + RB - 1) / RB;
-    u64 bt = (u64)blockIdx.x * LEAN_WARPS + wid;
+    u64 bt = (u64)blockIdx.x * n_cta_warps + wid;
     auto async8 = [](void *dst, const void *src) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
     };

@@ -1193,8 +1193,8 @@ static int lean_mode(const EncParams &P, u32 mates, bool taxa, bool mate1) {
 typedef void (*classify_u_fn)(const EncParams, const char *, const u64 *, u64, TableView, TaxView, u32 *, u32 *, u32 *,
                               unsigned long long *, u32 *, u32 *, unsigned long long *, u32, u64, u32, u32 *,
                               u64 *, u64, unsigned long long *, u64 *, u32 *, const PackedIn);
-static size_t lean_smem(bool runs) {
-    return (size_t)LEAN_WARPS * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES + (runs ? RUNBUF * sizeof(u64) : 0));
+static size_t lean_smem(bool runs, int warps) {
+    return (size_t)warps * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES + (runs ? RUNBUF * sizeof(u64) : 0));
 }
 template <int MODE, bool CANON, bool COUNTS, int KEY, bool RUNS = false>
 static classify_u_fn pick_lean_k(u32 k, bool loc, bool pk = false) {
@@ -1259,11 +1259,14 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     int nb = 0;
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
-        pl.smem = lean_smem(pl.runs);
-        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        // one CTA of LEAN_WARPS warps per SM when the batches fill every SM that way, else CTAs of LEAN_WARPS_SMALL (bns_classify_u.cuh)
+        const u64 n_batches = (n_records * mates + RB - 1) / RB;
+        pl.lean_warps = n_batches >= (u64)n_sm * LEAN_WARPS ? LEAN_WARPS : LEAN_WARPS_SMALL;
+        pl.smem = lean_smem(pl.runs, pl.lean_warps);
+        cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem(pl.runs, LEAN_WARPS));
         cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, LEAN_WARPS * 32, pl.smem);
-        const u64 want = ((n_records * mates + RB - 1) / RB + LEAN_WARPS - 1) / LEAN_WARPS;   // one batch per warp at least
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, pl.lean_warps * 32, pl.smem);
+        const u64 want = (n_batches + pl.lean_warps - 1) / pl.lean_warps;                     // one batch per warp at least
         pl.grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)n_sm * (nb > 0 ? nb : 1)));
     }
     // A second pass of the generic kernel takes what the first leaves: windowed records of more than one tile and 32-T restarts
@@ -1297,7 +1300,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
         if(pl.packed && !pk) return cudaErrorInvalidValue;
         const PackedIn pki = pl.packed ? *pk : PackedIn{nullptr, nullptr, 0u, 0ull};
-        f<<<pl.grid, LEAN_WARPS * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,
+        f<<<pl.grid, pl.lean_warps * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,
                                                     counters, status, defer_idx, defer_cnt, pl.fixed_len, pl.fixed_base, mates, mate1_out,
                                                     pl.runs ? ro->runs : nullptr, pl.runs ? ro->cap : 0, pl.runs ? ro->total : nullptr,
                                                     pl.runs ? ro->run_pos : nullptr, pl.runs ? ro->n_runs : nullptr, pki);
@@ -1321,7 +1324,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
     return cudaGetLastError();
 }
 size_t pass2_scratch_words(const ClassifyPlan &pl) { return pl.big_cap ? (size_t)pl.pass2_grid * WARPS_PER_CTA * 4 * pl.big_cap : 0; }
-u64 runs_slack(const ClassifyPlan &pl) { return pl.runs ? (u64)pl.grid * LEAN_WARPS * RUN_BLOCK : 0; }
+u64 runs_slack(const ClassifyPlan &pl) { return pl.runs ? (u64)pl.grid * pl.lean_warps * RUN_BLOCK : 0; }
 int encode_occupancy(const EncParams &P, size_t smem) {
     int nb = 0;
     encode_fn f = pick_encode(P.family);
