@@ -1,7 +1,7 @@
 #!/bin/bash
 # warps per SM of the lean kernel: 8 warps x 3 CTAs (80 registers) against 7 x 4 and 9 x 3 (72 registers) and 12 x 2
 mkdir -p gpurun_out
-for lib in bonsai_b200/variants/w6c4.so bonsai_b200/variants/w24c1.so bonsai_b200/variants/w10c2.so bonsai_b200/variants/w11c2.so bonsai_b200/variants/w12c2.so; do
+for lib in bonsai_b200/libbonsai_b200.so bonsai_b200/variants/w20c1.so bonsai_b200/variants/w16c1.so; do
   name=$(basename $lib .so)
   for wl in config2 stress; do
     BNS_B200_LIB=$PWD/$lib python bench.py --workload $wl --stress-keys 268435456 --no-sub --no-cpu-baseline --steps 20 --warmup 3 --e2e-steps 0 --check-reads 100000 > gpurun_out/occ_${name}_$wl.json 2> gpurun_out/occ_${name}_$wl.err
