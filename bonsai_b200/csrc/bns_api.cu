@@ -75,6 +75,11 @@ int ensure(T *&p, size_t &cap, size_t need) {
     cap = want;
     return BNS_OK;
 }
+// chunk sizes in whole waves of the lean kernel (every warp of every SM one batch): no warp idles while others run a last batch
+u64 whole_waves(u64 reads, int n_sm) {
+    const u64 w = lean_wave_reads(n_sm);
+    return reads >= w ? reads / w * w : reads;
+}
 template <class T>
 int ensure_pinned(T *&p, size_t &cap, size_t need) {
     if(need <= cap) return BNS_OK;
@@ -1530,8 +1535,10 @@ static int classify_batch_packing(bns_b200_t *ctx, const char *bases, const uint
     // and they do not cross PCIe): the scan of offsets[] is the one per-read pass of the call, the worker threads share it.
     struct Chunk { u64 q0, q1; u32 fixed_len; };
     std::vector<Chunk> chunks;
+    // whole waves of the kernel per chunk (2^18 reads would be 2.3 waves on 148 SMs: a third of the warps idle in the last one)
+    const u64 chunk_reads = whole_waves(ctx->pack_chunk_reads, ctx->n_sm);
     for(u64 q0 = 0; q0 < n_rec_total;) {
-        u64 q1 = std::min(n_rec_total, q0 + std::max<u64>(1, ctx->pack_chunk_reads / mates));
+        u64 q1 = std::min(n_rec_total, q0 + std::max<u64>(1, chunk_reads / mates));
         while(q1 > q0 + 1 && offsets[q1 * mates] - offsets[q0 * mates] > CHUNK_BASES) q1 = q0 + (q1 - q0) / 2;
         chunks.push_back(Chunk{q0, q1, 0u});
         q0 = q1;
@@ -1769,9 +1776,10 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
     }
     int slot_i = 0;
     u64 q0 = 0;                                                    // record cursor
+    const u64 chunk_reads = whole_waves(CHUNK_READS, ctx->n_sm);
     while(q0 < n_rec_total) {
         u64 q1 = q0;
-        while(q1 < n_rec_total && (q1 - q0) * mates < CHUNK_READS &&
+        while(q1 < n_rec_total && (q1 - q0) * mates < chunk_reads &&
               (q1 == q0 || offsets[(q1 + 1) * mates] - offsets[q0 * mates] <= CHUNK_BASES)) ++q1;
         const u64 r0 = q0 * mates, r1 = q1 * mates, nr = r1 - r0, nq = q1 - q0;
         const u64 nb = offsets[r1] - offsets[r0];
@@ -1891,9 +1899,10 @@ int bns_b200_classify_batch_runs(bns_b200_t *ctx, const char *bases, const uint6
     };
     int slot_i = 0;
     u64 q0 = 0;
+    const u64 chunk_reads = whole_waves(CHUNK_READS, ctx->n_sm);
     while(q0 < n_rec_total) {
         u64 q1 = q0;
-        while(q1 < n_rec_total && (q1 - q0) * mates < CHUNK_READS &&
+        while(q1 < n_rec_total && (q1 - q0) * mates < chunk_reads &&
               (q1 == q0 || offsets[(q1 + 1) * mates] - offsets[q0 * mates] <= CHUNK_BASES)) ++q1;
         const u64 r0 = q0 * mates, r1 = q1 * mates, nr = r1 - r0, nq = q1 - q0;
         const u64 nb = offsets[r1] - offsets[r0];

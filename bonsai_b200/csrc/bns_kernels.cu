@@ -1323,6 +1323,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
     if(n_launched) *n_launched = 2;
     return cudaGetLastError();
 }
+u64 lean_wave_reads(int n_sm) { return (u64)n_sm * LEAN_WARPS * RB; }
 size_t pass2_scratch_words(const ClassifyPlan &pl) { return pl.big_cap ? (size_t)pl.pass2_grid * WARPS_PER_CTA * 4 * pl.big_cap : 0; }
 u64 runs_slack(const ClassifyPlan &pl) { return pl.runs ? (u64)pl.grid * pl.lean_warps * RUN_BLOCK : 0; }
 int encode_occupancy(const EncParams &P, size_t smem) {

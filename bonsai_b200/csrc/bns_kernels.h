@@ -31,6 +31,9 @@ struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts =
 ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap, int n_sm, u64 n_records, u32 mates, bool taxa, bool mate1, bool counts,
                            bool runs = false, bool packed = false);
 int encode_occupancy(const EncParams &P, size_t smem);
+// sequences one full wave of the lean kernel takes (every warp of every SM one batch): chunk sizes that are multiples of it leave no
+// warp idle while others run a last batch
+u64 lean_wave_reads(int n_sm);
 // entries of the chunk's run buffer beyond one per possible hit: every warp of the lean run-list kernel may leave a stretch unused
 u64 runs_slack(const ClassifyPlan &pl);
 
