@@ -23,6 +23,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 #include <deque>
 #include <memory>
 #include <mutex>
@@ -786,6 +790,24 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
 
 // one record of a mapped plain file (parallel ingest, below): offsets into the mapping
 struct RecRef { u64 name_off, seq_off, qual_off; u32 name_len, seq_len; };
+// An array of trivially constructible elements whose resize() does not value-initialise them: the record indices are tens of
+// millions of 40-byte entries that the -p threads fill in parallel right after -- a std::vector would first zero them (and
+// first-touch their pages) on one thread, which was a quarter of the ingest's time.
+template <class T>
+struct RawVec {
+    std::unique_ptr<T[]> p;
+    size_t n = 0, cap = 0;
+    void resize(size_t m) { if(m > cap) { p.reset(new T[m]); cap = m; } n = m; }     // contents are NOT kept and NOT initialised
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p.get(); }
+    const T *data() const { return p.get(); }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    const T *begin() const { return p.get(); }
+    const T *end() const { return p.get() + n; }
+};
 // A batch parsed straight into PINNED host memory (bns_b200_host_alloc): the library DMAs from it without staging.
 struct PinnedBatch {
     char *bases = nullptr; size_t cap_bases = 0, n_bases = 0;
@@ -793,7 +815,7 @@ struct PinnedBatch {
     std::vector<std::string> names, quals;
     std::vector<char> has_qual;
     bool keep_qual = true;             // qualities are only printed by the FASTQ-style output
-    std::vector<RecRef> refs;   // parallel-ingest batches: names / qualities stay in the file mapping `map`
+    RawVec<RecRef> refs;        // parallel-ingest batches: names / qualities stay in the file mapping `map`
     const char *map = nullptr, *map2 = nullptr;                        // map2: the mates' file (records at odd indices)
     std::shared_ptr<char> keep, keep2;                                 // gzip input: the inflated windows `map` / `map2` point into
     const char *map_of(size_t i) const { return (map2 && (i & 1)) ? map2 : map; }
@@ -811,8 +833,10 @@ struct PinnedBatch {
     }
     void clear() { n_bases = 0; n = 0; names.clear(); quals.clear(); has_qual.clear(); map = map2 = nullptr; keep.reset(); keep2.reset(); }
     void reserve(size_t bases_hint) {                   // pinned allocations are slow: size the ring once per dataset
-        grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 4 + (1 << 16));
-        grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 32 + 1024);
+        // a batch ends with the record that takes it past bases_hint (bseq_read's rule): 1/16 of headroom covers reads of up to
+        // 4 M bases at the default chunk; longer records and batches of reads shorter than 64 bases grow the buffers (slowly: pinned)
+        grow(bases, cap_bases, n_bases, bases_hint + bases_hint / 16 + (1 << 16));
+        grow(offs, cap_offs, n ? n + 1 : 0, bases_hint / 64 + 1024);
     }
     void push(KSeq *k) {
         trim_readno(k->name);
@@ -825,6 +849,54 @@ struct PinnedBatch {
         names.push_back(k->name);
         has_qual.push_back(keep_qual && !k->qual.empty());
         if(keep_qual) quals.push_back(k->qual); else quals.emplace_back();
+    }
+};
+// The -p threads of the ingest as a fixed set: run(n, fn) executes fn(0 .. n-1) on them and on the calling thread and returns when
+// all are done. (Spawning threads per window and per batch -- ~700 spawns for 8 M reads -- was a tenth of the reader's time.)
+class WorkPool {
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, cvd_;
+    const std::function<void(unsigned)> *fn_ = nullptr;
+    unsigned n_tasks_ = 0, active_ = 0;
+    std::atomic<unsigned> next_{0};
+    u64 gen_ = 0;
+    bool stop_ = false;
+    void loop() {
+        u64 seen = 0;
+        for(;;) {
+            const std::function<void(unsigned)> *fn;
+            unsigned n;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if(stop_) return;
+                seen = gen_; fn = fn_; n = n_tasks_;
+            }
+            for(unsigned t; (t = next_.fetch_add(1)) < n;) (*fn)(t);
+            std::lock_guard<std::mutex> lk(m_);
+            if(--active_ == 0) cvd_.notify_all();
+        }
+    }
+  public:
+    explicit WorkPool(unsigned n) { for(unsigned i = 1; i < n; ++i) th_.emplace_back([this] { loop(); }); }
+    WorkPool(const WorkPool &) = delete;
+    ~WorkPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for(auto &t : th_) t.join();
+    }
+    unsigned size() const { return (unsigned)th_.size() + 1; }
+    void run(unsigned n_tasks, const std::function<void(unsigned)> &fn) {
+        if(n_tasks <= 1 || th_.empty()) { for(unsigned t = 0; t < n_tasks; ++t) fn(t); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; n_tasks_ = n_tasks; next_.store(0); active_ = (unsigned)th_.size(); ++gen_;
+        }
+        cv_.notify_all();
+        for(unsigned t; (t = next_.fetch_add(1)) < n_tasks;) fn(t);
+        std::unique_lock<std::mutex> lk(m_);
+        cvd_.wait(lk, [&] { return active_ == 0; });
     }
 };
 // ---- parallel ingest of plain (uncompressed) files in the simple form ---------------------------------------------
@@ -904,6 +976,91 @@ inline bool index_range(const char *p, size_t lo, size_t hi, size_t n, bool fast
         x = next;
     }
     return x == hi || (x == n + 1 && hi == n);                            // a last line without a newline ends at n
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+// index_range with the line ends found 32 bytes at a time (one compare + movemask per block, every block of the text touched
+// once) and the sequence line checked for the bytes kseq would stop at in one pass of four compares: ~3x the records per second
+// of the memchr-per-line version on one thread. Same acceptance rules, same RecRefs.
+struct NewlineScan {
+    const char *p; size_t n;
+    size_t blk = ~(size_t)0; unsigned mask = 0;          // newline bits of p[blk, blk + 32) not consumed yet
+    __attribute__((target("avx2"))) size_t next(size_t x) {     // offset of the first '\n' at or after x, or n (x never goes backwards)
+        if(x >= n) return n;
+        if(blk == ~(size_t)0 || x >= blk + 32) { blk = x; mask = 0; load(); }
+        else mask &= ~0u << (x - blk);
+        while(mask == 0) {
+            blk += 32;
+            if(blk >= n) return n;
+            load();
+        }
+        const size_t pos = blk + (size_t)__builtin_ctz(mask);
+        mask &= mask - 1;
+        return pos;
+    }
+    __attribute__((target("avx2"))) void load() {
+        if(blk + 32 <= n) {
+            const __m256i v = _mm256_loadu_si256((const __m256i *)(p + blk));
+            mask = (unsigned)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('\n')));
+        } else {
+            mask = 0;
+            for(size_t i = blk; i < n; ++i) if(p[i] == '\n') mask |= 1u << (i - blk);
+        }
+    }
+};
+// does s[0, len) hold a '>', '@', '+' or '\r' ?
+__attribute__((target("avx2"))) inline bool seq_has_stop_byte(const char *s, size_t len) {
+    const __m256i a = _mm256_set1_epi8('>'), b = _mm256_set1_epi8('@'), c = _mm256_set1_epi8('+'), d = _mm256_set1_epi8('\r');
+    __m256i acc = _mm256_setzero_si256();
+    size_t i = 0;
+    for(; i + 32 <= len; i += 32) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(s + i));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, a), _mm256_cmpeq_epi8(v, b)),
+                                                   _mm256_or_si256(_mm256_cmpeq_epi8(v, c), _mm256_cmpeq_epi8(v, d))));
+    }
+    bool hit = _mm256_movemask_epi8(acc) != 0;
+    for(; i < len; ++i) hit |= s[i] == '>' || s[i] == '@' || s[i] == '+' || s[i] == '\r';
+    return hit;
+}
+__attribute__((target("avx2"))) inline bool index_range_avx2(const char *p, size_t lo, size_t hi, size_t n, bool fastq, std::vector<RecRef> &out) {
+    NewlineScan nl{p, n};
+    size_t x = lo;
+    while(x < hi) {
+        if(p[x] != (fastq ? '@' : '>')) return false;
+        const size_t e1 = nl.next(x);
+        if(e1 >= n) return false;
+        size_t ne = x + 1;
+        while(ne < e1 && !std::isspace((unsigned char)p[ne])) ++ne;
+        RecRef r;
+        r.name_off = x + 1; r.name_len = (u32)(ne - (x + 1));
+        if(r.name_len > 2 && p[ne - 2] == '/' && std::isdigit((unsigned char)p[ne - 1])) r.name_len -= 2;   // trim_readno
+        const size_t e2 = nl.next(e1 + 1);
+        if(e2 - (e1 + 1) > 0x7fffffffull) return false;
+        r.seq_off = e1 + 1; r.seq_len = (u32)(e2 - (e1 + 1));
+        if(r.seq_len == 0 || std::memchr(p + x, '\r', e1 - x)) return false;
+        if(seq_has_stop_byte(p + r.seq_off, r.seq_len)) return false;     // kseq would end the sequence there (or keep a CR)
+        r.qual_off = ~0ull;
+        size_t next = e2 + 1;
+        if(fastq) {
+            if(e2 + 1 >= n || p[e2 + 1] != '+') return false;
+            const size_t e3 = nl.next(e2 + 1);
+            if(e3 >= n) return false;
+            const size_t e4 = nl.next(e3 + 1);
+            if(e4 - (e3 + 1) != r.seq_len) return false;
+            r.qual_off = e3 + 1;
+            next = e4 + 1;
+        }
+        out.push_back(r);
+        x = next;
+    }
+    return x == hi || (x == n + 1 && hi == n);
+}
+#endif
+inline bool index_range_best(const char *p, size_t lo, size_t hi, size_t n, bool fastq, std::vector<RecRef> &out) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !std::getenv("BNS_B200_INDEX_SCALAR");
+    if(avx2) return index_range_avx2(p, lo, hi, n, fastq, out);
+#endif
+    return index_range(p, lo, hi, n, fastq, out);
 }
 // gzip input in the same simple form: one decompressor thread per file inflates the stream window after window (zlib is a
 // serial format; this takes inflate off the parser's thread and lets two mate files inflate side by side). A window is cut at
@@ -1091,10 +1248,12 @@ struct SimpleFile {
     MappedFile map;
     bool fastq = false, ok = false;
     size_t cursor = 0;                     // next unindexed byte of the (uncompressed) stream, a record start
-    std::vector<RecRef> recs;              // the current window; offsets are relative to text()
+    RawVec<RecRef> recs;                   // the current window; offsets are relative to text()
     size_t next_rec = 0;
     unsigned nthreads;
     size_t window;
+    std::unique_ptr<WorkPool> pool;        // the -p threads
+    std::vector<std::vector<RecRef>> part; // per-task pieces of a window's index, reused from window to window
     // gzip input
     std::unique_ptr<GzWindows> gz;
     std::shared_ptr<char> hold;            // the current window's buffer
@@ -1103,9 +1262,11 @@ struct SimpleFile {
     std::string carry;
     bool gz_first = true;
     bool at_end = false;                   // the whole stream has been indexed
-    SimpleFile(const char *path, unsigned nt) : map(path), nthreads(std::max(1u, nt)) {
+    SimpleFile(const char *path, unsigned nt) : map(path), nthreads(std::max(1u, nt)), pool(new WorkPool(std::max(1u, nt))) {
         const char *e = std::getenv("BNS_B200_FASTQ_WINDOW");              // bytes per indexing window (tests use a small one)
-        window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)1 << 30);
+        // 256 MB of text: a couple of batches per window, the first batch after a quarter of the time of a 1 GB window, and the
+        // per-task pieces (reused) stay a few MB each
+        window = e && std::atoll(e) > 0 ? (size_t)std::atoll(e) : ((size_t)256 << 20);
         if(map.p && (unsigned char)map.p[0] == 0x1f && (unsigned char)map.p[1] == 0x8b) {
             const char *g = std::getenv("BNS_B200_GZ_WINDOW");             // inflated bytes per window
             gz.reset(new GzWindows(path, g && std::atoll(g) > 0 ? (size_t)std::atoll(g) : ((size_t)64 << 20), map.p, map.n, nthreads));
@@ -1135,15 +1296,13 @@ struct SimpleFile {
         cut[0] = lo; cut[T] = hi;
         for(unsigned t = 1; t < T; ++t) cut[t] = std::min(hi, next_record_start(p, lo + (hi - lo) / T * t, n, fastq));
         for(unsigned t = 1; t <= T; ++t) if(cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
-        std::vector<std::vector<RecRef>> part(T);
+        if(part.size() < T) part.resize(T);
         std::vector<char> good(T, 1);
-        std::vector<std::thread> pool;
-        for(unsigned t = 0; t < T; ++t)
-            pool.emplace_back([&, t] {
-                part[t].reserve((cut[t + 1] - cut[t]) / 96 + 64);          // ~ one record per 100-300 bytes of text: few regrowths
-                good[t] = index_range(p, cut[t], cut[t + 1], n, fastq, part[t]);
-            });
-        for(auto &th : pool) th.join();
+        pool->run(T, [&](unsigned t) {
+            part[t].clear();
+            part[t].reserve((cut[t + 1] - cut[t]) / 96 + 64);              // ~ one record per 100-300 bytes of text: few regrowths
+            good[t] = index_range_best(p, cut[t], cut[t + 1], n, fastq, part[t]);
+        });
         size_t total = 0;
         std::vector<size_t> at(T + 1, 0);
         for(unsigned t = 0; t < T; ++t) {
@@ -1152,10 +1311,7 @@ struct SimpleFile {
         }
         // the parts become one array without a serial pass over it
         recs.resize(total);
-        pool.clear();
-        for(unsigned t = 0; t < T; ++t)
-            pool.emplace_back([&, t] { if(!part[t].empty()) std::memcpy(recs.data() + at[t], part[t].data(), part[t].size() * sizeof(RecRef)); });
-        for(auto &th : pool) th.join();
+        pool->run(T, [&](unsigned t) { if(!part[t].empty()) std::memcpy(recs.data() + at[t], part[t].data(), part[t].size() * sizeof(RecRef)); });
         return true;
     }
     // index the next window; false when the file is exhausted or leaves the simple form (then ok is false and `cursor` is where
@@ -1239,12 +1395,7 @@ inline bool fill_pinned(int chunk_size, PinnedBatch &b, SimpleFile &f, SimpleFil
     const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(f.nthreads, n / 8192 + 1));
     std::vector<u64> base(T + 1, 0);
     auto rec_at = [&](size_t i) -> const RecRef & { return f2 ? ((i & 1) ? f2->recs[s2 + (i >> 1)] : f.recs[s1 + (i >> 1)]) : f.recs[s1 + i]; };
-    auto run = [&](auto &&fn) {
-        if(T == 1) { fn(0u); return; }
-        std::vector<std::thread> pool;
-        for(unsigned t = 0; t < T; ++t) pool.emplace_back(fn, t);
-        for(auto &th : pool) th.join();
-    };
+    auto run = [&](const std::function<void(unsigned)> &fn) { f.pool->run(T, fn); };
     run([&](unsigned t) { u64 sum = 0; for(size_t i = n * t / T, hi = n * (t + 1) / T; i < hi; ++i) sum += rec_at(i).seq_len; base[t + 1] = sum; });
     for(unsigned t = 0; t < T; ++t) base[t + 1] += base[t];
     run([&](unsigned t) {
@@ -1355,6 +1506,9 @@ void classify_seqs(ClassifierGeneric<ScoreType> &c, const kh_p_t *taxmap, bseq1_
 template <typename ScoreType>
 void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, const char *fq1, const char *fq2, std::FILE *out,
                      unsigned chunk_size, unsigned /*per_set*/) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since_enter = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enter).count(); };
+    double t_first_batch = 0, t_reader_reserve = 0, t_reader_fill = 0, t_reader_done = 0;   // BNS_B200_VERBOSE: where the reader's time goes
     if(!c.tax_loaded_) c.load_taxonomy(taxmap);
     detail::KSeq ks1(fq1);
     std::unique_ptr<detail::KSeq> ks2(fq2 ? new detail::KSeq(fq2) : nullptr);
@@ -1369,7 +1523,9 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     // two host workers per GPU: batch s goes to worker s mod 2G, i.e. to GPU s mod G; while one worker formats its batch the
     // other has the device
     const int NW = 2 * G;
-    const int NB = 2 * NW + 1;
+    // one slot per worker and one the reader fills meanwhile: pinning memory costs ~0.6 ms per MB and holds a driver lock the
+    // workers' calls wait for, so the ring is as small as the pipeline allows (five slots of 100 MB were 0.28 s on 8 M reads)
+    const int NB = NW + 1;
     std::vector<detail::PinnedBatch> ring((size_t)NB);
     // pinned allocations are slow (tens of ms each): a ring slot gets its buffers when the reader first fills it, while the
     // earlier batches are already on the device
@@ -1380,18 +1536,43 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     std::mutex mu;
     std::condition_variable cv;
     std::string reader_error;
+    // Pinned allocations take tens of milliseconds each (five slots of 84 MB were 0.2 of the reader's 0.5 s on 8 M reads): a
+    // helper thread makes them, slot after slot, while the reader indexes the first window and fills the slots that are ready.
+    std::vector<int> slot_ready((size_t)NB, 0);
+    std::atomic<bool> alloc_stop(false);
+    std::string alloc_error;
+    std::thread allocator([&]() {
+        for(size_t i = 0; i < (size_t)NB && !alloc_stop.load(); ++i) {
+            try { ring[i].reserve(chunk_size); } catch(const std::exception &e) { std::lock_guard<std::mutex> lk(mu); alloc_error = e.what(); }
+            { std::lock_guard<std::mutex> lk(mu); slot_ready[i] = 1; }
+            cv.notify_all();
+        }
+        { std::lock_guard<std::mutex> lk(mu); for(auto &r : slot_ready) r = 1; }   // stopped early: the slots left are not needed
+        cv.notify_all();
+    });
     std::thread reader([&]() {
+        struct StopAlloc { std::atomic<bool> &f; ~StopAlloc() { f = true; } } stop_alloc{alloc_stop};   // no more slots are needed once the input has ended
         try {
             for(u64 sq = 0;; ++sq) {
                 const size_t i = (size_t)(sq % (u64)NB);
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[i] == 0; }); }
                 bool got = false;
-                if(!ring[i].bases) ring[i].reserve(chunk_size);
+                const double tr0 = since_enter();
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return slot_ready[i] != 0; });
+                    if(!alloc_error.empty()) BNS_RUNTIME_ERROR(alloc_error);
+                }
+                const double tr1 = since_enter();
+                t_reader_reserve += tr1 - tr0;
                 if(use_index) {
                     got = detail::fill_pinned((int)chunk_size, ring[i], *simple, simple2.get());
+                    t_reader_fill += since_enter() - tr1;
+                    if(sq == 0) t_first_batch = since_enter();
                     if(!got && simple->drained() && (!simple2 || simple2->drained())) {
                         // the index served the input to its end (a gzip stream would inflate once more to seek there)
                         use_index = false;
+                        t_reader_done = since_enter();
                         { std::lock_guard<std::mutex> lk(mu); end_seq = sq; }
                         cv.notify_all();
                         return;
@@ -1501,13 +1682,20 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     work(0);                                                               // the first worker of GPU 0 on the caller's thread
     for(auto &t : workers) t.join();
     reader.join();
+    alloc_stop = true;
+    allocator.join();
+    const double t_workers_done = since_enter();
     { std::lock_guard<std::mutex> lk(wmu); w_end = end_seq; }
     wcv.notify_all();
     writer.join();
+    const double t_writer_done = since_enter();
     if(!reader_error.empty()) BNS_RUNTIME_ERROR(reader_error);
     if(!failure.empty()) BNS_RUNTIME_ERROR(failure);
     if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
+    if(verbose)
+        std::fprintf(stderr, "[process_dataset] first batch ready at %.3f s, reader done at %.3f s (waiting for pinned buffers %.3f s, index + fill %.3f s), workers done at %.3f s, "
+                     "writer done at %.3f s\n", t_first_batch, t_reader_done, t_reader_reserve, t_reader_fill, t_workers_done, t_writer_done);
     if(verbose)
         for(int g = 0; g < NW; ++g)
             std::fprintf(stderr, "[process_dataset] gpu %d worker %d: %zu batches, waiting for the reader %.2f s, classify + format %.2f s\n",
