@@ -126,7 +126,9 @@ struct bns_b200_ctx {
     Slot slots[N_SLOTS];
     // host packing (bns_b200_config.host_pack_threads): worker threads, created at the first call large enough to use them
     int pack_threads = 0;             // 0 = the host-buffer calls ship ASCII
-    int pack_mode = 2;                // 1 every chunk packed, 2 packed and ASCII chunks side by side (BNS_B200_HOST_PACK_MODE=pack|hybrid)
+    int pack_mode = 0;                // 1 every chunk packed, 2 packed and ASCII chunks side by side (BNS_B200_HOST_PACK_MODE=pack|hybrid),
+                                      // 0 (default) decided per call: 2 for pinned / registered host memory, 1 for pageable memory, whose
+                                      // "asynchronous" copies are staged by the driver on the calling thread
     u64 pack_min_bases = PACK_MIN_BASES, pack_chunk_reads = PACK_CHUNK_READS;   // BNS_B200_PACK_MIN_BASES / _CHUNK_READS (tests use small ones)
     std::unique_ptr<PackPool> pool;
     std::vector<std::vector<uint64_t>> exc_parts[2];          // exception words per packing task, of the chunk being packed / being queued
@@ -1529,6 +1531,13 @@ static int classify_batch_packing(bns_b200_t *ctx, const char *bases, const uint
                                   uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out) {
     if(!ctx->pool) ctx->pool.reset(new PackPool((unsigned)ctx->pack_threads));
     PackPool &pool = *ctx->pool;
+    int pack_mode = ctx->pack_mode;
+    if(pack_mode == 0) {
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, bases) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        pack_mode = pinned ? 2 : 1;
+    }
     for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); ctx->slots[i].busy = ctx->slots[i].reserved = false; }
     const bool counts = n_hit_out || n_missing_out;
     // The chunk list, and for every chunk whether all its records have one length (then the kernel generates the offsets itself
@@ -1722,7 +1731,7 @@ static int classify_batch_packing(bns_b200_t *ctx, const char *bases, const uint
             ++n_packed;
             if(rc != BNS_OK) break;
         }
-        if(ctx->pack_mode == 2 && c_next < chunks.size() && raw_queued() < 2) {   // (c) keep the copy engine fed with ASCII chunks
+        if(pack_mode == 2 && c_next < chunks.size() && raw_queued() < 2) {   // (c) keep the copy engine fed with ASCII chunks
             const int si = free_slot();
             if(si >= 0) {
                 rc = enqueue(si, chunks[c_next++], false, 0);

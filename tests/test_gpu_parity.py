@@ -393,7 +393,7 @@ def test_classify_ragged_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, geno
     assert t.size == 0
 
 
-@pytest.mark.parametrize("mode", ["pack", "hybrid"])
+@pytest.mark.parametrize("mode", ["pack", "hybrid", "auto"])
 def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, golden, reads2000, monkeypatch, mode):
     """bns_b200_classify_batch with host packing threads (bns_b200_config.host_pack_threads): chunks packed to 2 bits on the
     host and read by the packed-input kernel, alone ("pack") and next to chunks that cross as ASCII ("hybrid"), against the
@@ -401,7 +401,10 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
     units, chunks and suspicious-bit words, a fixed-length batch (offsets generated on the device), mate pairs, both layouts."""
     monkeypatch.setenv("BNS_B200_PACK_MIN_BASES", "1")
     monkeypatch.setenv("BNS_B200_PACK_CHUNK_READS", "700")
-    monkeypatch.setenv("BNS_B200_HOST_PACK_MODE", mode)
+    if mode != "auto":                                    # auto: numpy arrays are pageable memory, every chunk is packed
+        monkeypatch.setenv("BNS_B200_HOST_PACK_MODE", mode)
+    else:
+        monkeypatch.delenv("BNS_B200_HOST_PACK_MODE", raising=False)
     db = dbcache.get("lex_k31_w31")
     keys, vals, flags, nb, _ = oracle.db_arrays(db)
     rb, ro, _ = H.make_reads(6000, seed=41, ragged=True)
@@ -437,7 +440,7 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
         h0 = sctx.stats()["h2d_bytes"]
         t, nh, nm = sctx.classify(reads2000[0], reads2000[1])
         assert t.tolist() == spec["taxon"] and nh.tolist() == spec["nhit"] and nm.tolist() == spec["nmiss"]
-        if mode == "pack":
+        if mode != "hybrid":
             assert sctx.stats()["h2d_bytes"] - h0 < reads2000[0].size * 0.3 + 4096 * 16
         db4 = dbcache.get(spec["db"])
         exp4 = oracle.classify(db4, toy_tax, bases, offs, spec["k"], spec["w"], spec["gaps"], 0, spec["canon"], spec["api"])
@@ -458,7 +461,7 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
             ref = plain.classify(bases, offs)
             for a, b, c in zip(exp, got, ref):
                 assert np.array_equal(a, b) and np.array_equal(a, c)
-            if mode == "pack":                            # the bases crossed as 2-bit units (+ offsets): well under one byte each
+            if mode != "hybrid":                          # the bases crossed as 2-bit units (+ offsets): well under one byte each
                 assert packed_bytes < bases.size * 0.25 + offs.size * 8 + 4096 * 16
             t_only, _, _ = ctx.classify(bases, offs, want_counts=False)
             assert np.array_equal(t_only, exp[0])
