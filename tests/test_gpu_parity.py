@@ -465,6 +465,16 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
                 assert packed_bytes < bases.size * 0.25 + offs.size * 8 + 4096 * 16
             t_only, _, _ = ctx.classify(bases, offs, want_counts=False)
             assert np.array_equal(t_only, exp[0])
+            # the worker threads can be switched off and on again on a live context (bns_b200_set_host_pack_threads)
+            assert ctx.host_pack_threads() == 3 and plain.host_pack_threads() == 0
+            ctx.set_host_pack_threads(0)
+            h1 = ctx.stats()["h2d_bytes"]
+            off_run = ctx.classify(bases, offs)
+            assert all(np.array_equal(a, b) for a, b in zip(exp, off_run)) and ctx.stats()["h2d_bytes"] - h1 >= bases.size
+            ctx.set_host_pack_threads(2)
+            assert ctx.host_pack_threads() == 2
+            on_run = ctx.classify(bases, offs)
+            assert all(np.array_equal(a, b) for a, b in zip(exp, on_run))
             ne = ((offs.size - 1) // 2) * 2
             expp = oracle.classify(db, toy_tax, bases[:int(offs[ne])], offs[:ne + 1], 31, 31, paired=True)
             gotp = ctx.classify(bases[:int(offs[ne])], offs[:ne + 1], paired=True)
@@ -475,7 +485,7 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
             for a, b in zip(expf, gotf):
                 assert np.array_equal(a, b)
             st, sp = ctx.stats(), plain.stats()
-            assert st["n_classified"] == sp["n_classified"] + int((exp[0] != 0).sum()) + int((expp[0] != 0).sum()) + int((expf[0] != 0).sum())
+            assert st["n_classified"] == sp["n_classified"] + 3 * int((exp[0] != 0).sum()) + int((expp[0] != 0).sum()) + int((expf[0] != 0).sum())
 
 
 def test_classify_device_and_replication(capi, golden, gpu_dbs, reads2000):
