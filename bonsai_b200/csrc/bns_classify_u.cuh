@@ -293,10 +293,12 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
     // with other loads (ncu showed the register prefetch of v2 stalling a full DRAM latency per record for that reason).
     //   s_off[2][RB+1]  offsets of the current / next batch of records
     //   s_rd[2][32]     8 bytes per lane of the first tile of the current / next record
-    u64 *s_off = (u64 *)(g_smem + (size_t)n_cta_warps * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * LEAN_STAGE_BYTES);
+    // (the run buffer of the RUNS variants follows the warp's staging area: one base address for both)
+    constexpr u32 WARP_STAGE_BYTES = LEAN_STAGE_BYTES + (RUNS ? RUNBUF * sizeof(u64) : 0);
+    u64 *s_off = (u64 *)(g_smem + (size_t)n_cta_warps * 4 * AGG_CAP * sizeof(u32) + (size_t)wid * WARP_STAGE_BYTES);
     uint2 *s_rd = (uint2 *)(s_off + 2 * (RB + 2));
     // run lists: this warp's record buffer, its reserved stretch of runs_out, and the run that is still open
-    u64 *s_run = (u64 *)(g_smem + (size_t)n_cta_warps * (4 * AGG_CAP * sizeof(u32) + LEAN_STAGE_BYTES) + (size_t)wid * RUNBUF * sizeof(u64));
+    u64 *s_run = s_off + LEAN_STAGE_BYTES / sizeof(u64);
     u64 blk_pos = 0;
     u32 blk_left = 0, run_val = VAL_MISS, run_len = 0, n_runs_rec = 0;
     bool run_direct = false;                                          // this record's runs go straight to runs_out[blk_pos ...]
@@ -765,88 +767,11 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                     u32 todo = ~nok & mask;
                     u32 bal = __ballot_sync(FULL, todo != 0);
                     if(bal) {
-                        const u32 tile_hits = (COUNTS || RUNS) ? __reduce_add_sync(FULL, __popc(todo)) : 0u;
-                        if(COUNTS) n_hit += tile_hits;
+                        if(COUNTS) n_hit += __reduce_add_sync(FULL, __popc(todo));
 #pragma unroll
                         for(int i = 0; i < PPL; ++i) cand[i] &= Pc.val_mask;
-                        if(RUNS) {
-                            // The tile's hits in k-mer order (lane-major). A hit starts a run when no hit precedes it in the record
-                            // or its value differs from the previous hit's; every start closes the run before it.
-                            // Most tiles hit ONE value: then the tile continues the open run or starts a single new one.
-                            const u32 lead = __shfl_sync(FULL, (todo & 1u) ? cand[0] : (todo & 2u) ? cand[1] : (todo & 4u) ? cand[2] : cand[3], __ffs(bal) - 1);
-                            const bool mixed = ((todo & 1u) && cand[0] != lead) || ((todo & 2u) && cand[1] != lead) || ((todo & 4u) && cand[2] != lead) ||
-                                               ((todo & 8u) && cand[3] != lead);
-                            if(!__any_sync(FULL, mixed)) {
-                                const u32 H1 = tile_hits;
-                                if(run_val == lead) run_len += H1;
-                                else {
-                                    if(run_val != VAL_MISS) {
-                                        if(!run_direct && n_runs_rec + 2 > (u32)RUNBUF) {
-                                            const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
-                                            reserve_runs(n_runs_rec + rest);
-                                            for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
-                                            run_direct = true;
-                                        }
-                                        if(lane == 0) put_run(n_runs_rec, run_val, run_len);
-                                        ++n_runs_rec;
-                                    }
-                                    run_val = lead; run_len = H1;
-                                }
-                            } else {
-                            u32 firstv = VAL_MISS, prevv = VAL_MISS, inner = 0;
-#pragma unroll
-                            for(int i = 0; i < PPL; ++i)
-                                if(todo >> i & 1u) {
-                                    if(prevv == VAL_MISS) firstv = cand[i]; else if(cand[i] != prevv) inner |= 1u << i;
-                                    prevv = cand[i];
-                                }
-                            const u32 lower = bal & ((1u << lane) - 1);                    // lanes before this one that hold hits
-                            u32 pv = __shfl_sync(FULL, prevv, (31 - __clz(lower)) & 31);   // value of the last hit before this lane
-                            if(lower == 0) pv = run_val;
-                            u32 starts = inner;
-                            if(todo && (pv == VAL_MISS || firstv != pv)) starts |= todo & (0u - todo);
-                            const u32 m = __popc(todo), ns = __popc(starts);
-                            u32 tot;
-                            const u32 ex = warp_excl_scan(m | (ns << 16), lane, tot);
-                            const u32 hbase = ex & 0xffffu, sbase = ex >> 16, H = tot & 0xffffu, SX = tot >> 16;
-                            const bool carry = run_val != VAL_MISS;
-                            // more runs than the record buffer holds (long reads): from here on straight into a reserved stretch
-                            if(!run_direct && n_runs_rec + SX + 1 > (u32)RUNBUF) {
-                                const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
-                                reserve_runs(n_runs_rec + rest);
-                                for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
-                                run_direct = true;
-                            }
-                            u32 last_idx = 0, last_val = 0;                               // this lane's last start
-                            {
-                                u32 rank = 0;
-#pragma unroll
-                                for(int i = 0; i < PPL; ++i)
-                                    if(todo >> i & 1u) { if(starts >> i & 1u) { last_idx = hbase + rank; last_val = cand[i]; } ++rank; }
-                            }
-                            const u32 sl = __ballot_sync(FULL, ns != 0), slower = sl & ((1u << lane) - 1);
-                            int open_start = (int)__shfl_sync(FULL, last_idx, (31 - __clz(slower)) & 31);   // where the run open before this lane began
-                            if(slower == 0) open_start = -(int)run_len;
-                            u32 open_val = pv, rank = 0, srank = 0;
-#pragma unroll
-                            for(int i = 0; i < PPL; ++i)
-                                if(todo >> i & 1u) {
-                                    if(starts >> i & 1u) {
-                                        const u32 t = sbase + srank;                      // the t-th start of the tile
-                                        if(carry || t > 0) put_run(n_runs_rec + t - (carry ? 0u : 1u), open_val, (u32)((int)(hbase + rank) - open_start));
-                                        open_val = cand[i]; open_start = (int)(hbase + rank); ++srank;
-                                    }
-                                    ++rank;
-                                }
-                            if(SX) {
-                                const u32 top = 31 - __clz(sl);
-                                run_val = __shfl_sync(FULL, last_val, top);
-                                run_len = H - __shfl_sync(FULL, last_idx, top);
-                                n_runs_rec += SX - (carry ? 0u : 1u);
-                            } else run_len += H;
-                            }
-                            __syncwarp();
-                        }
+                        const u32 todo0 = todo, bal0 = bal;
+                        bool first_round = true;
                         do {
                             const u32 leader = __ffs(bal) - 1;
                             u32 fv = cand[3];
@@ -870,6 +795,84 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                                 sink.add(S, vv, total, lane);
                             }
                             bal = __ballot_sync(FULL, todo != 0);
+                            if(RUNS && first_round) {
+                                // The tile's hits in k-mer order (lane-major). A hit starts a run when no hit precedes it in the record
+                                // or its value differs from the previous hit's; every start closes the run before it. Most tiles hit
+                                // ONE value -- this round of the counting loop has just found that out (no hit is left) and knows the
+                                // value and the count: the tile continues the open run or starts a single new one.
+                                first_round = false;
+                                if(!bal) {
+                                    const u32 lead = vv, H1 = total;
+                                    if(run_val == lead) run_len += H1;
+                                    else {
+                                        if(run_val != VAL_MISS) {
+                                            if(!run_direct && n_runs_rec + 2 > (u32)RUNBUF) {
+                                                const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
+                                                reserve_runs(n_runs_rec + rest);
+                                                for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                                                run_direct = true;
+                                            }
+                                            if(lane == 0) put_run(n_runs_rec, run_val, run_len);
+                                            ++n_runs_rec;
+                                        }
+                                        run_val = lead; run_len = H1;
+                                    }
+                                } else {
+                                    const u32 todo = todo0, bal = bal0;                   // the tile's hits as they were before this round
+                                    u32 firstv = VAL_MISS, prevv = VAL_MISS, inner = 0;
+#pragma unroll
+                                    for(int i = 0; i < PPL; ++i)
+                                        if(todo >> i & 1u) {
+                                            if(prevv == VAL_MISS) firstv = cand[i]; else if(cand[i] != prevv) inner |= 1u << i;
+                                            prevv = cand[i];
+                                        }
+                                    const u32 lower = bal & ((1u << lane) - 1);                    // lanes before this one that hold hits
+                                    u32 pv = __shfl_sync(FULL, prevv, (31 - __clz(lower)) & 31);   // value of the last hit before this lane
+                                    if(lower == 0) pv = run_val;
+                                    u32 starts = inner;
+                                    if(todo && (pv == VAL_MISS || firstv != pv)) starts |= todo & (0u - todo);
+                                    const u32 m = __popc(todo), ns = __popc(starts);
+                                    u32 tot;
+                                    const u32 ex = warp_excl_scan(m | (ns << 16), lane, tot);
+                                    const u32 hbase = ex & 0xffffu, sbase = ex >> 16, H = tot & 0xffffu, SX = tot >> 16;
+                                    const bool carry = run_val != VAL_MISS;
+                                    // more runs than the record buffer holds (long reads): from here on straight into a reserved stretch
+                                    if(!run_direct && n_runs_rec + SX + 1 > (u32)RUNBUF) {
+                                        const u32 rest = (npos - p0) + ((first_mate && !last_mate && xl >= c) ? xl - c + 1 : 0u) + 1u;
+                                        reserve_runs(n_runs_rec + rest);
+                                        for(u32 q = lane; q < n_runs_rec; q += 32) if(blk_pos + q < runs_cap) runs_out[blk_pos + q] = s_run[q];
+                                        run_direct = true;
+                                    }
+                                    u32 last_idx = 0, last_val = 0;                               // this lane's last start
+                                    {
+                                        u32 rank = 0;
+#pragma unroll
+                                        for(int i = 0; i < PPL; ++i)
+                                            if(todo >> i & 1u) { if(starts >> i & 1u) { last_idx = hbase + rank; last_val = cand[i]; } ++rank; }
+                                    }
+                                    const u32 sl = __ballot_sync(FULL, ns != 0), slower = sl & ((1u << lane) - 1);
+                                    int open_start = (int)__shfl_sync(FULL, last_idx, (31 - __clz(slower)) & 31);   // where the run open before this lane began
+                                    if(slower == 0) open_start = -(int)run_len;
+                                    u32 open_val = pv, rank = 0, srank = 0;
+#pragma unroll
+                                    for(int i = 0; i < PPL; ++i)
+                                        if(todo >> i & 1u) {
+                                            if(starts >> i & 1u) {
+                                                const u32 t = sbase + srank;                      // the t-th start of the tile
+                                                if(carry || t > 0) put_run(n_runs_rec + t - (carry ? 0u : 1u), open_val, (u32)((int)(hbase + rank) - open_start));
+                                                open_val = cand[i]; open_start = (int)(hbase + rank); ++srank;
+                                            }
+                                            ++rank;
+                                        }
+                                    if(SX) {
+                                        const u32 top = 31 - __clz(sl);
+                                        run_val = __shfl_sync(FULL, last_val, top);
+                                        run_len = H - __shfl_sync(FULL, last_idx, top);
+                                        n_runs_rec += SX - (carry ? 0u : 1u);
+                                    } else run_len += H;
+                                }
+                                __syncwarp();
+                            }
                         } while(bal);
                     }
                 }
