@@ -86,10 +86,11 @@ def test_hist(cli, tmp_path):
     assert [r[1] for r in rows] == sorted(r[1] for r in rows)
 
 
-def test_parallel_ingest_index_matches_kseq(tmp_path):
+@pytest.mark.parametrize("scanner", ["avx2", "scalar"])
+def test_parallel_ingest_index_matches_kseq(tmp_path, scanner):
     """detail::SimpleFile (parallel index of plain, gzip or BGZF 4-line FASTQ / 2-line FASTA, hand-over to kseq elsewhere) yields
-    the same records as the kseq state machine, window by window and batch by batch (single and mate files):
-    tests/host/ingest_index.cpp, host code only."""
+    the same records as the kseq state machine, window by window and batch by batch (single and mate files), with the AVX2 line
+    scanner (where the CPU has it) and with the memchr-per-line one: tests/host/ingest_index.cpp, host code only."""
     import shutil
     import subprocess
     gxx = shutil.which("g++") or "/usr/bin/g++"
@@ -97,7 +98,10 @@ def test_parallel_ingest_index_matches_kseq(tmp_path):
     src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "ingest_index.cpp")
     r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe, src, "-lz", "-lpthread"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
-    r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    env = dict(os.environ)
+    if scanner == "scalar":
+        env["BNS_B200_INDEX_SCALAR"] = "1"
+    r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" ok") == 80, r.stdout
 
 
