@@ -1528,16 +1528,10 @@ int bns_b200_classify_device_runs(bns_b200_t *ctx, const char *d_bases, const ui
 // kernel; the RAW lane keeps the copy engine busy meanwhile with chunks that cross as they are (at most two queued). Host cores
 // and PCIe link work side by side; every chunk's results land at its records' places in the caller's arrays.
 static int classify_batch_packing(bns_b200_t *ctx, const char *bases, const uint64_t *offsets, u64 n_rec_total, u32 mates,
-                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out) {
+                                  uint32_t *taxon_out, uint32_t *n_hit_out, uint32_t *n_missing_out, uint32_t *mate1_kmers_out, bool bases_pinned) {
     if(!ctx->pool) ctx->pool.reset(new PackPool((unsigned)ctx->pack_threads));
     PackPool &pool = *ctx->pool;
-    int pack_mode = ctx->pack_mode;
-    if(pack_mode == 0) {
-        cudaPointerAttributes at;
-        const bool pinned = cudaPointerGetAttributes(&at, bases) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
-        cudaGetLastError();
-        pack_mode = pinned ? 2 : 1;
-    }
+    const int pack_mode = ctx->pack_mode ? ctx->pack_mode : bases_pinned ? 2 : 1;
     for(int i = 0; i < N_SLOTS; ++i) { CK(cudaStreamSynchronize(ctx->slots[i].st)); ctx->slots[i].busy = ctx->slots[i].reserved = false; }
     const bool counts = n_hit_out || n_missing_out;
     // The chunk list, and for every chunk whether all its records have one length (then the kernel generates the offsets itself
@@ -1774,10 +1768,15 @@ int bns_b200_classify_batch_ex(bns_b200_t *ctx, const char *bases, const uint64_
     CK(cudaMemsetAsync(ctx->d_status, 0, 4, ctx->slots[0].st));
     CK(cudaStreamSynchronize(ctx->slots[0].st));
     // large batches of what `bonsai classify` runs: the host's cores pack chunks to 2 bits next to the chunks crossing as ASCII
-    if(ctx->pack_threads > 0 && !taxa_out && offsets[n_rec_total * mates] - offsets[0] >= ctx->pack_min_bases &&
+    // (memory the CPU cannot read -- a device pointer handed to the host-buffer call copies device to device below -- is not packed)
+    cudaPointerAttributes at;
+    const bool at_ok = ctx->pack_threads > 0 && cudaPointerGetAttributes(&at, bases) == cudaSuccess;
+    cudaGetLastError();
+    if(at_ok && at.type != cudaMemoryTypeDevice && !taxa_out && offsets[n_rec_total * mates] - offsets[0] >= ctx->pack_min_bases &&
        plan_classify(ctx->enc, table_view(ctx), ctx->ring_cap, ctx->n_sm, n_rec_total, mates, false, mate1_kmers_out != nullptr,
                      n_hit_out || n_missing_out, false, true).packed) {
-        rc = classify_batch_packing(ctx, bases, offsets, n_rec_total, mates, taxon_out, n_hit_out, n_missing_out, mate1_kmers_out);
+        rc = classify_batch_packing(ctx, bases, offsets, n_rec_total, mates, taxon_out, n_hit_out, n_missing_out, mate1_kmers_out,
+                                    at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
         if(rc != BNS_OK) return rc;
         u32 status = 0;
         CK(cudaMemcpy(&status, ctx->d_status, 4, cudaMemcpyDeviceToHost));
