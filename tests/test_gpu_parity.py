@@ -488,6 +488,51 @@ def test_host_packed_chunks_vs_oracle(capi, oracle, dbcache, toy_tax, genomes, g
             assert st["n_classified"] == sp["n_classified"] + 3 * int((exp[0] != 0).sum()) + int((expp[0] != 0).sum()) + int((expf[0] != 0).sum())
 
 
+@pytest.mark.parametrize("k,canon", [(21, True), (31, False), (32, True), (16, False)])
+def test_host_packed_other_k_and_strands(capi, oracle, toy_tax, genomes, monkeypatch, k, canon):
+    """The packed-input variants for k other than 31 (run-time k) and for uncanonical k-mers: a database of the first 120 kb of
+    each genome built on the device for that encoder, ragged reads with N / lower case, packing threads on vs the oracle."""
+    from bonsai_b200 import dbbuild, workload as W
+    monkeypatch.setenv("BNS_B200_PACK_MIN_BASES", "1")
+    monkeypatch.setenv("BNS_B200_PACK_CHUNK_READS", "900")
+    monkeypatch.setenv("BNS_B200_HOST_PACK_MODE", "pack")
+    tc, tp = H.toy_tax_arrays()
+    g = W.load_genomes()
+    gen = []
+    for gi in range(4):
+        b, off = W.genome_records(g, gi)
+        gen.append((b[:120_000].copy(), np.array([0, 120_000], np.uint64)))
+    with capi.Context(k, k, canonicalize=canon) as bctx:
+        dbbuild.build_on_device(bctx, gen, W.GENOME_TAXIDS, tc, tp, k, k, canonicalize=canon)
+        keys, vals = bctx.table_dump()
+    db = oracle.db_from_pairs(keys, vals)
+    rng = np.random.default_rng(k)
+    reads = []
+    for i in range(5000):
+        src = gen[i % 4][0]
+        L = int(rng.integers(0, 260))
+        s0 = int(rng.integers(0, src.size - 300))
+        r = bytearray(src[s0:s0 + L].tobytes())
+        if r and i % 9 == 0:
+            r[int(rng.integers(0, len(r)))] = ord("N")
+        if i % 13 == 0:
+            r = bytearray(bytes(r).lower())
+        if i % 2:
+            r = bytearray(bytes(r)[::-1].translate(bytes.maketrans(b"ACGTacgt", b"TGCAtgca")))
+        reads.append(bytes(r))
+    bases, offs = po.pack_reads(reads)
+    exp = oracle.classify(db, toy_tax, bases, offs, k, k, None, 0, canon, capi.API_STRING)
+    with capi.Context(k, k, canonicalize=canon, host_pack_threads=3) as ctx:
+        ctx.load_pairs(keys, vals)
+        ctx.load_taxonomy(tc, tp)
+        h0 = ctx.stats()["h2d_bytes"]
+        got = ctx.classify(bases, offs)
+        assert ctx.stats()["h2d_bytes"] - h0 < bases.size * 0.3 + offs.size * 8 + 4096 * 16      # it did go packed
+        for a, b in zip(exp, got):
+            assert np.array_equal(a, b)
+    assert int((exp[0] != 0).sum()) > 1000
+
+
 def test_classify_device_and_replication(capi, golden, gpu_dbs, reads2000):
     """device-resident call + the broadcast path (header, segments, commit) into a second context"""
     import torch
