@@ -57,12 +57,18 @@ static int classify_main(int argc, char *argv[]) {
         std::unique_ptr<TaxMap> taxmap(build_parent_map(argv[optind + 1]));
         const char *fq2 = (argc - optind >= 4) ? argv[optind + 3] : nullptr;
         const double t3 = now();
+        c.set_exit_follows(true);
         process_dataset(c, taxmap.get(), argv[optind + 2], fq2, ofp, (unsigned)chunk_size, (unsigned)per_set);
         if(verbose)
             std::fprintf(stderr, "[bonsai classify] database file %.2f s, classifier (device open + table load) %.2f s, taxonomy %.2f s, "
                          "dataset %.2f s\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
         std::fprintf(stderr, "Successfully finished classify_main. classified %" PRIu64 ", unclassified %" PRIu64 "\n",
                      c.n_classified(), c.n_unclassified());
+        // Everything is written: the process ends here instead of unpinning buffers, freeing device memory and tearing the CUDA
+        // context down object by object (0.2 - 0.5 s of a run whose work took as long)
+        if(ofp != stdout) std::fclose(ofp);
+        std::fflush(nullptr);
+        std::_Exit(EXIT_SUCCESS);
     } catch(const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());
         return EXIT_FAILURE;

@@ -567,6 +567,11 @@ struct ClassifierGeneric {
     std::vector<std::shared_ptr<detail::Handle>> replicas_;      // contexts on GPUs 1 .. n-1 holding a copy of the database (set_gpus)
     int n_gpus_ = 1;
     bool tax_loaded_ = false;
+    bool exit_follows_ = false;                                  // the caller ends the process right after process_dataset (the CLI):
+                                                                 // pinned buffers are left to the operating system instead of being
+                                                                 // unpinned one by one (0.03 - 0.24 s for the three ring slots)
+    void set_exit_follows(bool v) { exit_follows_ = v; }
+    std::atomic<u64> t_device_ns_{0}, t_format_ns_{0}, t_join_ns_{0};   // BNS_B200_VERBOSE: where classify_views spent its time (all workers)
     std::atomic<u32> runs_per_record_hint_{4};                   // run-buffer entries per record the batches so far needed (classify_views)
     void set_emit_all(bool s) { if(s) output_flag_ |= EMIT_ALL; else output_flag_ &= ~EMIT_ALL; }
     void set_emit_kraken(bool s) { if(s) output_flag_ |= KRAKEN; else output_flag_ &= ~KRAKEN; }
@@ -709,6 +714,8 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
                     int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0, std::mutex *device_mu = nullptr) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
+    const auto t_in = std::chrono::steady_clock::now();
+    auto ns_since = [](std::chrono::steady_clock::time_point t) { return (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); };
     // device_mu: a context runs one call at a time; two host workers that share a GPU take turns for the call and format their
     // batches side by side
     std::unique_lock<std::mutex> device_lock;
@@ -751,7 +758,9 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     // classify_seq's epilogue (text) per record. The reference formats on its worker threads (-p, kt_for_helper,
     // classifier.h:254-266); here -p threads format contiguous slices of the batch and the slices are joined in order.
     if(device_lock.owns_lock()) device_lock.unlock();
+    c.t_device_ns_ += ns_since(t_in);                                 // includes waiting for the other worker's call
     if(!(c.output_flag_ & (FASTQ | KRAKEN))) return;                  // nothing is printed (-K without -f): the counters are all there is
+    const auto t_fmt = std::chrono::steady_clock::now();
     auto format_range = [&](unsigned r_lo, unsigned r_hi, std::string &out) {
         for(unsigned r = r_lo; r < r_hi; ++r) {
             const ReadView pair[2] = {view_at((size_t)r * inc), is_paired ? view_at((size_t)r * inc + 1) : ReadView{}};
@@ -770,7 +779,7 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
         }
     };
     const unsigned nthreads = std::max(1u, std::min<unsigned>(max_threads ? max_threads : c.nt_, nrec / 256 + 1));
-    if(nthreads == 1) { format_range(0, nrec, cks); return; }
+    if(nthreads == 1) { format_range(0, nrec, cks); c.t_format_ns_ += ns_since(t_fmt); return; }
     std::vector<std::string> parts(nthreads);
     std::vector<std::thread> pool;
     // a line is a few dozen bytes (plus the sequence and quality in FASTQ style): one allocation per slice instead of doublings
@@ -782,10 +791,13 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
             format_range(lo, hi, parts[t]);
         });
     for(auto &th : pool) th.join();
+    c.t_format_ns_ += ns_since(t_fmt);
+    const auto t_join = std::chrono::steady_clock::now();
     size_t total = cks.size();
     for(auto &part : parts) total += part.size();
     cks.reserve(total);
     for(auto &part : parts) cks += part;
+    c.t_join_ns_ += ns_since(t_join);
 }
 
 // one record of a mapped plain file (parallel ingest, below): offsets into the mapping
@@ -1693,9 +1705,24 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     if(!failure.empty()) BNS_RUNTIME_ERROR(failure);
     if(!werr.empty()) BNS_RUNTIME_ERROR(werr);
     if(first) std::fprintf(stderr, "Could not get any sequences from file, fyi.\n");
+    // what the function holds is released here, step by step, so that BNS_B200_VERBOSE can say what each step costs
+    const double t_rel0 = since_enter();
+    if(c.exit_follows_) {
+        static std::vector<std::vector<detail::PinnedBatch>> *kept = new std::vector<std::vector<detail::PinnedBatch>>();   // never destroyed
+        kept->push_back(std::move(ring));
+    }
+    ring.clear();
+    const double t_rel1 = since_enter();
+    simple.reset(); simple2.reset();
+    const double t_rel2 = since_enter();
+    if(verbose)
+        std::fprintf(stderr, "[process_dataset] releasing the pinned ring %.3f s, the file mappings and indices %.3f s\n", t_rel1 - t_rel0, t_rel2 - t_rel1);
     if(verbose)
         std::fprintf(stderr, "[process_dataset] first batch ready at %.3f s, reader done at %.3f s (waiting for pinned buffers %.3f s, index + fill %.3f s), workers done at %.3f s, "
                      "writer done at %.3f s\n", t_first_batch, t_reader_done, t_reader_reserve, t_reader_fill, t_workers_done, t_writer_done);
+    if(verbose)
+        std::fprintf(stderr, "[process_dataset] all workers: device calls (incl. waiting for the GPU's other worker) %.3f s, formatting %.3f s, joining the slices %.3f s\n",
+                     c.t_device_ns_.load() * 1e-9, c.t_format_ns_.load() * 1e-9, c.t_join_ns_.load() * 1e-9);
     if(verbose)
         for(int g = 0; g < NW; ++g)
             std::fprintf(stderr, "[process_dataset] gpu %d worker %d: %zu batches, waiting for the reader %.2f s, classify + format %.2f s\n",
