@@ -709,9 +709,29 @@ inline void append_fastq_classification(const tax_t *taxa, u32 ntaxa, tax_t taxo
 // One GPU call for a batch laid out as concatenated bases + offsets, then classify_seq's epilogue per record
 // (classifier.h:232-246). view_at(i): what the emitters need of read i (mates interleaved), made where it is used -- on the
 // formatting threads -- instead of as an array per batch.
+// A grow-only pinned buffer per calling thread for what a batch call copies back (taxa, counts, run lists: ~35 bytes per read).
+// Into pageable memory those copies are staged by the driver at a few GB/s and were most of a batch call's time.
+struct PinnedScratch {
+    void *p = nullptr; size_t cap = 0;
+    bool keep = false;                                               // the process is about to end: leave the buffer to the operating system
+    ~PinnedScratch() { if(p && !keep) bns_b200_host_free(p); }
+    void *get(size_t bytes) {                                        // nullptr if pinned memory cannot be had: the caller uses the heap
+        if(bytes > cap) {
+            if(p) bns_b200_host_free(p);
+            p = nullptr; cap = 0;
+            const size_t want = bytes + bytes / 4 + 4096;
+            if(bns_b200_host_alloc(&p, want) != 0) { p = nullptr; return nullptr; }
+            cap = want;
+        }
+        return p;
+    }
+};
+// parts_out: the formatted slices are handed over as they are (process_dataset writes them one after the other) instead of being
+// appended to cks
 template <typename ScoreType, typename ViewAt>
 void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u64 *offs, const ViewAt &view_at, unsigned n_reads,
-                    int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0, std::mutex *device_mu = nullptr) {
+                    int is_paired, std::string &cks, bns_b200_t *h = nullptr, unsigned max_threads = 0, std::mutex *device_mu = nullptr,
+                    std::vector<std::string> *parts_out = nullptr) {
     const unsigned inc = is_paired ? 2 : 1, nrec = n_reads / inc;
     if(!nrec) return;
     const auto t_in = std::chrono::steady_clock::now();
@@ -724,14 +744,21 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
     // The ordered hit list is only printed by the Kraken run lists, and the k-mer count of mate 1 only differs from
     // hits + missing for pairs: without them the library runs its lean kernel and copies 12 bytes per record back.
     const bool need_taxa = (c.output_flag_ & KRAKEN) != 0;
-    // result arrays the library fills: no need to zero them first
-    std::unique_ptr<u32[]> res(new u32[(size_t)nrec * 5]);
-    std::unique_ptr<u64[]> run_pos_buf(need_taxa ? new u64[nrec] : nullptr);
+    // result arrays the library fills (no need to zero them first), in this thread's pinned scratch where that can be had
+    thread_local PinnedScratch res_scratch, runs_scratch;
+    res_scratch.keep = runs_scratch.keep = c.exit_follows_;
+    const size_t res_bytes = (size_t)nrec * 5 * sizeof(u32) + (need_taxa ? (size_t)nrec * sizeof(u64) : 0) + 16;
+    std::unique_ptr<char[]> res_heap;
+    char *res_mem = (char *)res_scratch.get(res_bytes);
+    if(!res_mem) { res_heap.reset(new char[res_bytes]); res_mem = res_heap.get(); }
+    u64 *const run_pos_p = (u64 *)res_mem;                            // (first: 8-byte aligned)
+    u32 *const res_p = (u32 *)(res_mem + (need_taxa ? (size_t)nrec * sizeof(u64) : 0));
     struct Arr { u32 *p; u32 *data() const { return p; } u32 &operator[](size_t i) const { return p[i]; } };
     struct Arr64 { u64 *p; u64 *data() const { return p; } u64 &operator[](size_t i) const { return p[i]; } };
-    const Arr taxon{res.get()}, nhit{res.get() + nrec}, nmiss{res.get() + 2 * (size_t)nrec}, mate1{res.get() + 3 * (size_t)nrec}, nruns{res.get() + 4 * (size_t)nrec};
-    const Arr64 run_pos{run_pos_buf.get()};
-    std::unique_ptr<u64[]> runs;
+    const Arr taxon{res_p}, nhit{res_p + nrec}, nmiss{res_p + 2 * (size_t)nrec}, mate1{res_p + 3 * (size_t)nrec}, nruns{res_p + 4 * (size_t)nrec};
+    const Arr64 run_pos{need_taxa ? run_pos_p : nullptr};
+    std::unique_ptr<u64[]> runs_heap;
+    u64 *runs = nullptr;
     if(need_taxa) {
         // run lists: encoded on the device, 8 bytes per run back instead of 4 per k-mer window slot. The number of runs is
         // not known beforehand: the buffer is sized from what earlier batches of this classifier needed (entries per record,
@@ -741,9 +768,10 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
         const u64 bound = windows + ((u64)1 << 21);                       // always enough (bonsai_b200.h)
         u64 cap = std::min<u64>(bound, (u64)nrec * c.runs_per_record_hint_.load() + ((u64)1 << 20)), total = 0;
         for(;;) {
-            runs.reset(new u64[cap ? cap : 1]);
+            runs = (u64 *)runs_scratch.get((cap ? cap : 1) * sizeof(u64));
+            if(!runs) { runs_heap.reset(new u64[cap ? cap : 1]); runs = runs_heap.get(); }
             const int rc = bns_b200_classify_batch_runs(h, bases, offs, nrec * inc, is_paired, taxon.data(), nhit.data(), nmiss.data(),
-                                                        is_paired ? mate1.data() : nullptr, runs.get(), cap, run_pos.data(), nruns.data(), &total);
+                                                        is_paired ? mate1.data() : nullptr, runs, cap, run_pos.data(), nruns.data(), &total);
             if(rc == BNS_E_CAPACITY && cap < bound) { cap = std::min<u64>(bound, std::max<u64>(cap * 2, total + total / 2)); continue; }
             check(h, rc, "bns_b200_classify_batch_runs");
             break;
@@ -769,7 +797,7 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
             u32 ambig = (u32)((u64)(u32)((u32)b->l_seq - comb + 1) - (u64)(is_paired ? mate1[r] : nhit[r] + nmiss[r]));
             if(is_paired) ambig += (u32)((u64)(u32)((u32)(b + 1)->l_seq - (comb - 1)) - (u64)nhit[r] - nmiss[r]);   // :235
             if(c.get_emit_all() || taxon[r]) {
-                const u64 *rn = need_taxa ? runs.get() + run_pos[r] : nullptr;
+                const u64 *rn = need_taxa ? runs + run_pos[r] : nullptr;
                 const u32 nrn = need_taxa ? nruns[r] : 0;
                 if(c.output_flag_ & FASTQ)
                     append_fastq_classification(nullptr, nhit[r], taxon[r], ambig, nmiss[r], b, out, c.get_emit_kraken(), is_paired, rn, nrn);
@@ -779,7 +807,12 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
         }
     };
     const unsigned nthreads = std::max(1u, std::min<unsigned>(max_threads ? max_threads : c.nt_, nrec / 256 + 1));
-    if(nthreads == 1) { format_range(0, nrec, cks); c.t_format_ns_ += ns_since(t_fmt); return; }
+    if(nthreads == 1) {
+        format_range(0, nrec, cks);
+        c.t_format_ns_ += ns_since(t_fmt);
+        if(parts_out) { parts_out->push_back(std::move(cks)); cks.clear(); }
+        return;
+    }
     std::vector<std::string> parts(nthreads);
     std::vector<std::thread> pool;
     // a line is a few dozen bytes (plus the sequence and quality in FASTQ style): one allocation per slice instead of doublings
@@ -792,6 +825,7 @@ void classify_views(ClassifierGeneric<ScoreType> &c, const char *bases, const u6
         });
     for(auto &th : pool) th.join();
     c.t_format_ns_ += ns_since(t_fmt);
+    if(parts_out) { for(auto &part : parts) parts_out->push_back(std::move(part)); return; }
     const auto t_join = std::chrono::steady_clock::now();
     size_t total = cks.size();
     for(auto &part : parts) total += part.size();
@@ -1618,24 +1652,26 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
     std::fflush(out);
     std::mutex wmu;
     std::condition_variable wcv;
-    std::map<u64, std::string> wq;               // finished texts by batch number (at most NB: a worker holds its ring slot until it has queued its text)
+    std::map<u64, std::vector<std::string>> wq;  // finished texts (the formatting threads' slices, in order) by batch number (at most NB: a worker holds its ring slot until it has queued its text)
     u64 w_end = ~0ull;                           // set once the last batch number is known
     std::string werr;
     std::thread writer([&]() {
         for(u64 next = 0;; ++next) {
-            std::string t;
+            std::vector<std::string> ts;
             {
                 std::unique_lock<std::mutex> lk(wmu);
                 wcv.wait(lk, [&] { return wq.count(next) || next >= w_end; });
                 if(!wq.count(next)) return;
-                t = std::move(wq[next]); wq.erase(next);
+                ts = std::move(wq[next]); wq.erase(next);
             }
-            if(!werr.empty()) continue;                                    // after a failed write: drain and drop
-            size_t put = 0;
-            while(put < t.size()) {
-                const ssize_t r = ::write(fn, t.data() + put, t.size() - put);
-                if(r <= 0) { std::lock_guard<std::mutex> lk(wmu); werr = "write failed"; break; }
-                put += (size_t)r;
+            for(const std::string &t : ts) {
+                if(!werr.empty()) break;                                   // after a failed write: drain and drop
+                size_t put = 0;
+                while(put < t.size()) {
+                    const ssize_t r = ::write(fn, t.data() + put, t.size() - put);
+                    if(r <= 0) { std::lock_guard<std::mutex> lk(wmu); werr = "write failed"; break; }
+                    put += (size_t)r;
+                }
             }
         }
     });
@@ -1662,6 +1698,7 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
             detail::PinnedBatch &b = ring[i];
             ++n_batches[(size_t)g];
             std::string text;
+            std::vector<std::string> slices;
             bool failed;
             { std::lock_guard<std::mutex> lk(mu); failed = !failure.empty(); }
             try {
@@ -1673,17 +1710,18 @@ void process_dataset(ClassifierGeneric<ScoreType> &c, const TaxMap *taxmap, cons
                             const char *mp = b.map_of(r);
                             return detail::ReadView{mp + ref.name_off, b.bases + b.offs[r], b.keep_qual && ref.qual_off != ~0ull ? mp + ref.qual_off : nullptr,
                                                     (int)ref.seq_len, (int)ref.name_len};
-                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu);
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu, &slices);
                     else
                         detail::classify_views(c, b.bases, b.offs, [&b](size_t r) {
                             return detail::ReadView{b.names[r].c_str(), b.bases + b.offs[r], b.has_qual[r] ? b.quals[r].c_str() : nullptr,
                                                     (int)(b.offs[r + 1] - b.offs[r])};
-                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu);
+                        }, (unsigned)b.n, is_paired, text, h, fmt_threads, dmu, &slices);
                     t_classify[(size_t)g] += now() - tc;
                     if(sq == 0) { std::fprintf(stderr, "nseq: %i\n", (int)b.n); first = false; }     // classifier.h:312
                 }
             } catch(const std::exception &e) { std::lock_guard<std::mutex> lk(mu); if(failure.empty()) failure = e.what(); }
-            { std::lock_guard<std::mutex> lk(wmu); wq[sq] = std::move(text); }
+            if(!text.empty()) slices.push_back(std::move(text));
+            { std::lock_guard<std::mutex> lk(wmu); wq[sq] = std::move(slices); }
             wcv.notify_all();
             { std::lock_guard<std::mutex> lk(mu); state[i] = 0; }
             cv.notify_all();
