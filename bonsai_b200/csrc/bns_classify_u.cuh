@@ -217,6 +217,46 @@ __device__ __forceinline__ u64 score_lean(const EncParams &cP, u64 x, u64 kmask)
     return score_of(cP, x);
 }
 
+// resolve_tree (util.h:831-869) when the record's counts live one value id per lane (SV variants: dictionaries of at most 32
+// values): score(t) = sum of the u16 counts over t's root path (Euler intervals), unique maximum wins, ties -> lca of the tied
+// taxa. The ties are folded in value-id order, not first-seen order: lca is commutative and associative on the loader's
+// well-formed taxonomy, so the result is the same.
+__device__ __forceinline__ u32 resolve_lanes(u32 cnt_lane, const uint4 *vi, const TaxView &X, u32 n_values, u32 lane) {
+    const u32 present = __ballot_sync(FULL, cnt_lane != 0);
+    if(!present) return 0;
+    if(!(present & (present - 1))) return vi[__ffs(present) - 1].w;
+    const u32 ti = vi[min(lane, n_values - 1)].x;
+    u32 sc = 0;
+    for(u32 m = present; m; m &= m - 1) {
+        const u32 u = __ffs(m) - 1;
+        const uint4 iu = vi[u];
+        const u32 cu = __shfl_sync(FULL, cnt_lane, u) & 0xffffu;         // the reference's counts are u16
+        if(iu.x <= ti && ti < iu.y) sc += cu;
+    }
+    const bool mine = (present >> lane) & 1u;
+    const u32 best = __reduce_max_sync(FULL, mine ? sc : 0u);
+    u32 tied = __ballot_sync(FULL, mine && sc == best);
+    u32 node = 0, ntied = 0, first_id = 0;
+    while(tied) {
+        const u32 l = __ffs(tied) - 1;
+        tied &= tied - 1;
+        const uint4 inf = vi[l];
+        if(ntied == 0) { node = inf.z; first_id = l; }
+        else {                                                         // lca(node, l): climb until the interval covers l (util.h:634-663)
+            const u32 tb = inf.x;
+            u32 a = node;
+            while(a) {
+                const uint4 na = X.node_info[a];
+                if(na.x <= tb && tb < na.y) break;
+                a = na.z;
+            }
+            node = a ? a : X.node_of_one;
+        }
+        ++ntied;
+    }
+    return ntied == 1 ? vi[first_id].w : X.node_info[node].w;
+}
+
 // MODE: LEAN_U every (canonical if CANON) k-mer                      encoder.h:240-272 (+ :218-232)
 //       LEAN_K canonical k-mer at every position, invalid -> 0, windowed  encoder.h:211-217,622-628   (CANON must be true)
 //       LEAN_R valid forward k-mers, windowed over the compacted sequence, tail flush, canonical on emit if CANON
@@ -240,7 +280,9 @@ __device__ __forceinline__ u32 pk_invalid_mask(const PackedIn &pk, u64 unit) {  
     while(lo < hi) { const u32 mid = (lo + hi) >> 1; if((pk.exc[mid] >> 8) < unit) lo = mid + 1; else hi = mid; }
     return (lo < pk.n_exc && (pk.exc[lo] >> 8) == unit) ? (u32)(pk.exc[lo] & 0xffu) : 0u;
 }
-template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC, bool RUNS, bool PK = false>
+// SV: the value dictionary has at most 32 entries: lane v keeps the record's count of value id v in a register (linear::counter::add
+// is one predicated add, no list in shared memory), resolve_lanes() reads the counts by shuffle.
+template <int MODE, bool CANON, int KT, bool COUNTS, int KEY, bool LOC, bool RUNS, bool PK = false, bool SV = false>
 __global__ void __launch_bounds__(LEAN_WARPS * 32, BNS_CLASSIFY_U_MIN_CTAS)
 bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restrict__ bases, const u64 *__restrict__ offsets,
                       u64 n_records, TableView T, TaxView X, u32 *__restrict__ taxon_out, u32 *__restrict__ nhit_out,
@@ -395,6 +437,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
         u32 my_taxon = 0, my_hit = 0, my_miss = 0, my_def = 0, my_m1 = 0;
         // ---- per-record state: linear::counter with its first key in registers --------------------------------------
         u32 nd = 0, id0 = 0, cnt0 = 0, n_hit = 0, n_emit = 0;
+        u32 cnt_lane = 0;                                              // SV: this record's hits of value id `lane`
         bool spilled = false, deferred = false;
         const u32 msh = COUNTS ? mates - 1 : 0u;                       // record of sequence j: j >> msh (pairs always run a COUNTS variant)
         for(u32 j = 0; j < nrec; ++j) {
@@ -425,7 +468,7 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             }
             fetch_tile(xb, xl, tb ^ 1);
             async_commit();
-            if(first_mate) { nd = 0; id0 = 0; cnt0 = 0; n_hit = 0; n_emit = 0; deferred = false; }
+            if(first_mate) { nd = 0; id0 = 0; cnt0 = 0; n_hit = 0; n_emit = 0; deferred = false; if(SV) cnt_lane = 0; }
             if(RUNS && first_mate) { run_val = VAL_MISS; run_len = 0; n_runs_rec = 0; run_direct = false; }
             if(L == 0xffffffffu) { if(lane == 0) atomicOr(status, 8u); }
             else if(deferred) {}                                       // the first mate already sent the record to the generic kernel
@@ -783,7 +826,8 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
                             e &= todo;
                             todo ^= e;
                             const u32 total = __reduce_add_sync(FULL, __popc(e));
-                            if(nd == 0) { id0 = vv; cnt0 = total; nd = 1; }
+                            if(SV) { if(lane == vv) cnt_lane += total; }
+                            else if(nd == 0) { id0 = vv; cnt0 = total; nd = 1; }
                             else if(!spilled && vv == id0) cnt0 += total;
                             else {
                                 if(!spilled) {                         // second distinct taxon: move the list to shared memory
@@ -889,7 +933,8 @@ bns_classify_u_kernel(const __grid_constant__ EncParams P, const char *__restric
             }
             // ---- resolve_tree (util.h:831-869) -------------------------------------------------------------------
             u32 taxon = 0;
-            if(spilled) {
+            if(SV) taxon = resolve_lanes(cnt_lane, sink.vi, X, T.n_values, lane);
+            else if(spilled) {
                 if(sink.overflow) {
                     // more distinct taxa than the shared-memory lists hold (only a database of more than AGG_CAP values can do
                     // that): the second pass redoes the record with its lists in global memory

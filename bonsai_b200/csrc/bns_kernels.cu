@@ -1226,7 +1226,11 @@ static int lean_key(const EncParams &P) {
     if(!P.cast_wrap && (P.score_kind == SC_ENT_NOTFULL || (P.score_kind == SC_ENT_ROLL && P.k >= 28))) return LEAN_KEY_ELEM;
     return LEAN_KEY_PAIR;
 }
-static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false, bool pk = false) {
+static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false, bool pk = false, bool sv = false) {
+    if(sv) {                                                          // small value dictionary: counts in lane registers (plan_classify)
+        if(loc) return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, true, false, false, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, true, false, false, true>;
+        return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, false, false, false, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, false, false, false, true>;
+    }
     if(pk) {
         if(mode == LEAN_S) return pick_lean_k<LEAN_S, false, true, 0>(P.k, loc, true);
         if(P.canon_elem) return counts ? pick_lean_k<LEAN_U, true, true, 0>(P.k, loc, true) : pick_lean_k<LEAN_U, true, false, 0>(P.k, loc, true);
@@ -1256,9 +1260,12 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     // host-packed bases (bns_pack.h) are read by the variants of what `bonsai classify` runs; a database of more than AGG_CAP
     // values may send records to the generic kernel's second pass, which reads ASCII
     pl.packed = packed && (pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) && !pl.runs && T.n_values <= (u32)AGG_CAP;
+    // value dictionaries of at most 32 entries (one lane per value): what `bonsai classify` runs at k = 31 keeps its counts in registers
+    static const bool no_sv = [] { const char *e = getenv("BNS_B200_NO_SV"); return e && e[0] == '1'; }();
+    pl.sv = !no_sv && pl.lean_mode == LEAN_U && P.canon_elem && P.k == 31 && !pl.runs && !pl.packed && T.n_values >= 1 && T.n_values <= 32;
     int nb = 0;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed, pl.sv);
         // one CTA of LEAN_WARPS warps per SM when the batches fill every SM that way, else CTAs of LEAN_WARPS_SMALL (bns_classify_u.cuh)
         const u64 n_batches = (n_records * mates + RB - 1) / RB;
         pl.lean_warps = n_batches >= (u64)n_sm * LEAN_WARPS ? LEAN_WARPS : LEAN_WARPS_SMALL;
@@ -1297,7 +1304,7 @@ cudaError_t launch_classify(const EncParams &P, const ClassifyPlan &pl, cudaStre
                             u32 *defer_idx, unsigned long long *defer_cnt, int *n_launched, const RunsOut *ro, u32 *big_scratch, const PackedIn *pk) {
     if(n_launched) *n_launched = 1;
     if(pl.lean) {
-        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed);
+        classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed, pl.sv);
         if(pl.packed && !pk) return cudaErrorInvalidValue;
         const PackedIn pki = pl.packed ? *pk : PackedIn{nullptr, nullptr, 0u, 0ull};
         f<<<pl.grid, pl.lean_warps * 32, pl.smem, st>>>(P, bases, offsets, n_records * mates, T, X, taxon_out, nhit_out, nmiss_out,

@@ -25,6 +25,7 @@ struct RunsOut { u64 *runs; u64 cap; unsigned long long *total; u64 *run_pos; u3
 struct ClassifyPlan { int grid = 1; size_t smem = 0; bool lean = false, counts = true, loc = false, runs = false; int occupancy = 0, lean_mode = -1, gen_grid = 1; size_t gen_smem = 0;
                       bool second_pass = false; int pass2_grid = 1; u32 big_cap = 0;   // the pass over the records the first kernel left (bns_kernels.cu)
                       u32 fixed_len = 0; u64 fixed_base = 0;   // set by the caller: all records have fixed_len bases, offsets are not on the device
+                      bool sv = false;                        // value dictionary of <= 32 entries: the lean kernel counts in lane registers
                       int lean_warps = 8;                     // warps per CTA the lean kernel is launched with
                       bool packed = false;                    // `bases` is the 2-bit unit stream of bns_pack.h (launch_classify needs its PackedIn)
                     };
