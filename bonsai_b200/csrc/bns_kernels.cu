@@ -1228,6 +1228,11 @@ static int lean_key(const EncParams &P) {
 }
 static classify_u_fn pick_lean(const EncParams &P, int mode, bool counts, bool loc, bool runs = false, bool pk = false, bool sv = false) {
     if(sv) {                                                          // small value dictionary: counts in lane registers (plan_classify)
+        if(runs) return loc ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, true, true, false, true> : bns_classify_u_kernel<LEAN_U, true, 31, true, 0, false, true, false, true>;
+        if(pk) {
+            if(loc) return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, true, false, true, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, true, false, true, true>;
+            return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, false, false, true, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, false, false, true, true>;
+        }
         if(loc) return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, true, false, false, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, true, false, false, true>;
         return counts ? bns_classify_u_kernel<LEAN_U, true, 31, true, 0, false, false, false, true> : bns_classify_u_kernel<LEAN_U, true, 31, false, 0, false, false, false, true>;
     }
@@ -1262,7 +1267,7 @@ ClassifyPlan plan_classify(const EncParams &P, const TableView &T, u32 ring_cap,
     pl.packed = packed && (pl.lean_mode == LEAN_U || pl.lean_mode == LEAN_S) && !pl.runs && T.n_values <= (u32)AGG_CAP;
     // value dictionaries of at most 32 entries (one lane per value): what `bonsai classify` runs at k = 31 keeps its counts in registers
     static const bool no_sv = [] { const char *e = getenv("BNS_B200_NO_SV"); return e && e[0] == '1'; }();
-    pl.sv = !no_sv && pl.lean_mode == LEAN_U && P.canon_elem && P.k == 31 && !pl.runs && !pl.packed && T.n_values >= 1 && T.n_values <= 32;
+    pl.sv = !no_sv && pl.lean_mode == LEAN_U && P.canon_elem && P.k == 31 && T.n_values >= 1 && T.n_values <= 32;
     int nb = 0;
     if(pl.lean) {
         classify_u_fn f = pick_lean(P, pl.lean_mode, pl.counts, pl.loc, pl.runs, pl.packed, pl.sv);
