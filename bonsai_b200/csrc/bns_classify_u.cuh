@@ -13,7 +13,8 @@
 //   * everything is 32-bit: the bucket arrives as eight u32 (LDG.256), the bucket address is one IMAD.WIDE, tags are
 //     funnel shifts;
 //   * the first distinct taxon of a record and its count live in (warp-uniform) registers; shared memory is touched
-//     only by records with >= 2 distinct taxa (resolve_tree's real work) -- 78 % of the classified reads have one;
+//     only by records with >= 2 distinct taxa (resolve_tree's real work) -- 78 % of the classified reads have one; with a
+//     value dictionary of at most 32 entries (SV variants) the counts live one value id per lane and no list exists at all;
 //   * displaced-key probes (home bucket overflowed at build time: the key's overflow flag is cleared there) run in one
 //     warp-level loop behind a one-vote conservative test;
 //   * window minima (LEAN_K / LEAN_R) are computed with shuffles only, on one 64-bit word per element where that is exact;
