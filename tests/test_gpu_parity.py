@@ -533,6 +533,45 @@ def test_host_packed_other_k_and_strands(capi, oracle, toy_tax, genomes, monkeyp
     assert int((exp[0] != 0).sum()) > 1000
 
 
+def test_chimeric_reads_tied_taxa_vs_oracle(capi, oracle, dbcache, toy_tax, gpu_dbs, genomes):
+    """resolve_tree's tie rule (equal root-path scores -> lca of the tied taxa, util.h:850-866) on reads built to tie: two to four
+    segments of equal length from different genomes, so that sibling taxa, cousins and three-way ties occur; single reads and
+    pairs, with and without counts. The small value dictionary of this database runs the lean kernel's SV variants (counts in
+    lane registers, ties folded in value-id order), which must give the reference's taxon."""
+    g = genomes
+    rng = np.random.default_rng(77)
+    coff = g["contig_off"]
+    by_g = [np.nonzero((g["contig_genome"] == x) & ((coff[1:] - coff[:-1]) >= 400))[0] for x in range(4)]
+    reads = []
+    for i in range(4000):
+        nseg = int(rng.integers(2, 5))
+        seg = int(rng.choice([45, 60, 75]))
+        gs = rng.choice(4, size=nseg, replace=False)
+        parts = []
+        for x in gs:
+            c = int(by_g[x][rng.integers(0, by_g[x].size)])
+            s0 = int(coff[c]) + int(rng.integers(0, int(coff[c + 1] - coff[c]) - seg))
+            parts.append(g["bases"][s0:s0 + seg].tobytes())
+        reads.append(b"".join(parts))
+    bases, offs = po.pack_reads(reads)
+    db = dbcache.get("lex_k31_w31")
+    ctx = gpu_dbs("config1_lex_w31")
+    assert ctx.table_info()["n_values"] <= 32
+    exp = oracle.classify(db, toy_tax, bases, offs, 31, 31)
+    got = ctx.classify(bases, offs)
+    for a, b in zip(exp, got):
+        assert np.array_equal(a, b)
+    t_only, _, _ = ctx.classify(bases, offs, want_counts=False)
+    assert np.array_equal(t_only, exp[0])
+    expp = oracle.classify(db, toy_tax, bases, offs, 31, 31, paired=True)
+    gotp = ctx.classify(bases, offs, paired=True)
+    for a, b in zip(expp, gotp):
+        assert np.array_equal(a, b)
+    # the reads do tie: inner taxonomy nodes win a good share of them
+    leaves = np.isin(exp[0], [11, 12, 13, 20])
+    assert int((~leaves & (exp[0] != 0)).sum()) > 300
+
+
 def test_classify_device_and_replication(capi, golden, gpu_dbs, reads2000):
     """device-resident call + the broadcast path (header, segments, commit) into a second context"""
     import torch
